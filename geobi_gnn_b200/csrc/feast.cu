@@ -1,0 +1,370 @@
+// FeaSt convolution (aggregate-first) and the fused FC head — fp32 CUDA-core path.
+//
+//   P[n,h]   = U_h . x_n                      (fp64, so P_j - P_i is as accurate as U(x_j - x_i))
+//   q_ijh    = softmax_h((float)(P_j - P_i) + c)
+//   Z[i,h,:] = 1/(deg_i+1) * sum_{j in N(i)+{i}} q_ijh x_j         <- the only per-edge work
+//   out_i    = act(W_flat . Z_i + b),  W_flat[o, h*C_in+c] = lin.weight[h*C_out+o, c]
+//
+// No per-edge tensor is written to HBM (the reference materialises [E, 9*C_out]).
+// The bf16 tensor-core projection lives in feast_tc.cu.
+#include "common.cuh"
+
+namespace geobi {
+
+constexpr int H = GEOBI_HEADS;
+
+// ------------------------------------------------------------------------------ P = X U^T (fp64)
+constexpr int PROJ_NODES = 64;
+constexpr int PROJ_THREADS = 192;  // 3 head groups x 64 nodes
+
+__global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
+                                                                     const float* __restrict__ U, double* __restrict__ P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Us = reinterpret_cast<double*>(smem_raw);          // [H][C]
+  float* xs = reinterpret_cast<float*>(Us + H * C);          // [PROJ_NODES][C+1]
+  const int tid = threadIdx.x;
+  const int64_t node0 = (int64_t)blockIdx.x * PROJ_NODES;
+  for (int i = tid; i < H * C; i += PROJ_THREADS) Us[i] = (double)U[i];
+  for (int i = tid; i < PROJ_NODES * C; i += PROJ_THREADS) {
+    const int r = i / C, c = i - r * C;
+    const int64_t n = node0 + r;
+    xs[r * (C + 1) + c] = n < N ? x[n * ldx + c] : 0.f;
+  }
+  __syncthreads();
+  const int r = tid & (PROJ_NODES - 1), g = tid / PROJ_NODES;
+  const int64_t n = node0 + r;
+  if (n >= N) return;
+  const float* xr = xs + r * (C + 1);
+#pragma unroll
+  for (int hh = 0; hh < 3; ++hh) {
+    const int h = g * 3 + hh;
+    const double* u = Us + h * C;
+    double acc = 0.0;
+    for (int c = 0; c < C; ++c) acc = fma((double)xr[c], u[c], acc);
+    P[n * H + h] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------ Z = softmax-weighted neighbour sums
+// One warp per target node; lane l owns channels l, l+32, ... (coalesced row reads).
+// Per 32-edge chunk: lanes compute one edge's 9 soft assignments each (-> smem), then the warp
+// walks the chunk accumulating 9 x CPL FMAs per edge per lane.
+template <int CPL>
+__global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
+                                                              const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                              const double* __restrict__ P, const float* __restrict__ cvec,
+                                                              float* __restrict__ Z) {
+  __shared__ __align__(16) float qs[8][32][12];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= N) return;
+  const int b = rowptr[i];
+  const int total = rowptr[i + 1] - b + 1;  // neighbours + implicit self loop (slot 0)
+  double Pi[H];
+  float ch[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    Pi[h] = P[i * H + h];
+    ch[h] = cvec[h];
+  }
+  float acc[H][CPL];
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[h][k] = 0.f;
+
+  for (int s0 = 0; s0 < total; s0 += 32) {
+    const int s = s0 + lane;
+    int64_t j = i;
+    if (s < total) {
+      if (s > 0) j = nbr[b + s - 1];
+      float l[H];
+      float m = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        l[h] = (float)(P[j * H + h] - Pi[h]) + ch[h];
+        m = fmaxf(m, l[h]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        l[h] = expf(l[h] - m);
+        sum += l[h];
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) qs[warp][lane][h] = l[h] / sum;
+    }
+    __syncwarp();
+    const int cnt = min(32, total - s0);
+    for (int t = 0; t < cnt; ++t) {
+      const int64_t jt = __shfl_sync(0xffffffffu, j, t);
+      float xj[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const int c = lane + 32 * k;
+        xj[k] = c < C ? x[jt * ldx + c] : 0.f;
+      }
+      const float4 qa = *reinterpret_cast<const float4*>(&qs[warp][t][0]);
+      const float4 qb = *reinterpret_cast<const float4*>(&qs[warp][t][4]);
+      const float q8 = qs[warp][t][8];
+      const float q[H] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w, q8};
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) acc[h][k] = fmaf(q[h], xj[k], acc[h][k]);
+    }
+    __syncwarp();
+  }
+  const float cntf = (float)total;
+  float* zrow = Z + i * (int64_t)(H * C);
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) {
+      const int c = lane + 32 * k;
+      if (c < C) zrow[h * C + c] = acc[h][k] / cntf;
+    }
+}
+
+// Wt[(h*C_in + c), o] = W[(h*C_out + o), c]
+__global__ void feast_transpose_w_kernel(const float* __restrict__ W, int C_in, int C_out, float* __restrict__ Wt) {
+  const int total = H * C_in * C_out;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int o = t % C_out;
+    const int k = t / C_out;
+    const int h = k / C_in, c = k - h * C_in;
+    Wt[t] = W[(int64_t)(h * C_out + o) * C_in + c];
+  }
+}
+
+// ------------------------------------------------------------------------------ out = act(A . Bt + bias)
+// Plain smem-tiled fp32 GEMM, 64 x BN tile, 4x4 per thread.  A [M,K] row-major, Bt [K,Ntot].
+template <int BN>
+__global__ void __launch_bounds__(16 * (BN / 4)) gemm_bias_act_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ Bt,
+                                                                       int Ntot, const float* __restrict__ bias, int64_t M, int K,
+                                                                       float slope, float* __restrict__ out, int64_t ldo) {
+  constexpr int BM = 64, BK = 16, TM = 4, TN = 4, NT = 16 * (BN / 4);
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN];
+  const int tid = threadIdx.x;
+  const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  float acc[TM][TN];
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int idx = tid; idx < BM * BK; idx += NT) {
+      const int r = idx / BK, kk = idx - r * BK;
+      const int64_t m = m0 + r;
+      As[kk][r] = (m < M && k0 + kk < K) ? A[m * lda + k0 + kk] : 0.f;
+    }
+    for (int idx = tid; idx < BK * BN; idx += NT) {
+      const int kk = idx / BN, n = idx - kk * BN;
+      Bs[kk][n] = (k0 + kk < K) ? Bt[(int64_t)(k0 + kk) * Ntot + n0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
+      const float a[TM] = {a4.x, a4.y, a4.z, a4.w};
+      const float b[TN] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int p = 0; p < TM; ++p)
+#pragma unroll
+        for (int q = 0; q < TN; ++q) acc[p][q] = fmaf(a[p], b[q], acc[p][q]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int p = 0; p < TM; ++p) {
+    const int64_t m = m0 + ty * TM + p;
+    if (m >= M) continue;
+#pragma unroll
+    for (int q = 0; q < TN; ++q) {
+      const int n = n0 + tx * TN + q;
+      float v = acc[p][q] + bias[n];
+      v = v > 0.f ? v : v * slope;
+      out[m * ldo + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ fused FC head
+// y = W2 . lrelu(W1 . f + b1) + b2 (+ epilogue).  64 nodes per CTA, 4 hidden sub-ranges per node;
+// W1 streams through smem in 128-row chunks, the [N,hidden] activation never leaves registers.
+template <int CIN>
+__global__ void __launch_bounds__(256) fc_head_kernel(const float* __restrict__ f, int64_t ldf, int64_t N, const float* __restrict__ W1,
+                                                      const float* __restrict__ b1, int hidden, const float* __restrict__ W2,
+                                                      const float* __restrict__ b2, int CO, int epilogue, const float* __restrict__ res,
+                                                      int64_t ldres, const float* __restrict__ res2, int64_t ldres2, float* __restrict__ out,
+                                                      int64_t ldo) {
+  constexpr int NODES = 64, HC = 128;
+  __shared__ __align__(16) float W1s[HC][CIN];
+  __shared__ float b1s[HC];
+  __shared__ float W2s[4][HC];
+  __shared__ float part[4][NODES][4];
+  const int tid = threadIdx.x;
+  const int node = tid & (NODES - 1), sub = tid / NODES;
+  const int64_t n = (int64_t)blockIdx.x * NODES + node;
+  float fr[CIN];
+#pragma unroll
+  for (int k = 0; k < CIN; ++k) fr[k] = n < N ? f[n * ldf + k] : 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int h0 = 0; h0 < hidden; h0 += HC) {
+    __syncthreads();
+    for (int idx = tid; idx < HC * CIN; idx += 256) (&W1s[0][0])[idx] = W1[(int64_t)h0 * CIN + idx];
+    for (int idx = tid; idx < HC; idx += 256) b1s[idx] = b1[h0 + idx];
+    for (int idx = tid; idx < 4 * HC; idx += 256) {
+      const int c = idx / HC, j = idx - c * HC;
+      W2s[c][j] = c < CO ? W2[(int64_t)c * hidden + h0 + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < HC / 4; ++jj) {
+      const int j = sub * (HC / 4) + jj;
+      float hsum = b1s[j];
+#pragma unroll
+      for (int k = 0; k < CIN; k += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&W1s[j][k]);
+        hsum = fmaf(w4.x, fr[k], hsum);
+        hsum = fmaf(w4.y, fr[k + 1], hsum);
+        hsum = fmaf(w4.z, fr[k + 2], hsum);
+        hsum = fmaf(w4.w, fr[k + 3], hsum);
+      }
+      hsum = hsum > 0.f ? hsum : 0.2f * hsum;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] = fmaf(W2s[c][j], hsum, acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) part[sub][node][c] = acc[c];
+  __syncthreads();
+  if (sub != 0 || n >= N) return;
+  float y[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) y[c] = c < CO ? ((part[0][node][c] + part[1][node][c]) + (part[2][node][c] + part[3][node][c])) + b2[c] : 0.f;
+  int co = CO;
+  if (epilogue == 2) {
+    if (CO == 1) {
+      const float s = y[0];
+      for (int c = 0; c < 3; ++c) y[c] = s * res2[n * ldres2 + c];
+      co = 3;
+    } else {
+      for (int c = 0; c < co; ++c) y[c] *= res2[n * ldres2 + c];
+    }
+  }
+  if (epilogue == 1 || epilogue == 2)
+    for (int c = 0; c < co; ++c) y[c] += res[n * ldres + c];
+  if (epilogue == 3) {
+    float s = 0.f;
+    for (int c = 0; c < co; ++c) s += y[c] * y[c];
+    const float d = fmaxf(sqrtf(s), 1e-12f);
+    for (int c = 0; c < co; ++c) y[c] /= d;
+  }
+  for (int c = 0; c < co; ++c) out[n * ldo + c] = y[c];
+}
+
+struct FeastWs {
+  double* P;
+  float* Z;
+  float* Wt;
+};
+template <class C>
+static void carve_feast(C& c, int64_t N, int c_in, int c_out, FeastWs* out) {
+  double* P = c.template take<double>((size_t)N * H);
+  float* Z = c.template take<float>((size_t)N * H * c_in);
+  float* Wt = c.template take<float>((size_t)H * c_in * c_out);
+  if (out) *out = FeastWs{P, Z, Wt};
+}
+struct NullCarverF {
+  Sizer s;
+  template <typename T>
+  T* take(size_t n) { s.take<T>(n); return nullptr; }
+};
+
+int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
+                 const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo, void* ws, size_t ws_bytes,
+                 cudaStream_t st);  // feast_tc.cu
+size_t feast_fwd_tc_ws_bytes(int64_t N, int c_in, int c_out);
+int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
+                   const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
+                   int64_t ldo, cudaStream_t st);
+
+}  // namespace geobi
+
+using namespace geobi;
+
+extern "C" size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision) {
+  if (precision == GEOBI_PREC_BF16) return feast_fwd_tc_ws_bytes(n_nodes, c_in, c_out);
+  NullCarverF c;
+  carve_feast(c, n_nodes, c_in, c_out, nullptr);
+  return c.s.total();
+}
+
+extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* W,
+                               const float* U, const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo,
+                               int precision, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(x && rowptr && W && U && c && bias && out && N >= 0, "feast_fwd: null argument");
+  GEOBI_REQUIRE(c_in >= 1 && c_in <= 128, "feast_fwd: C_in must be in 1..128 (got %d)", c_in);
+  GEOBI_REQUIRE(c_out == 32 || c_out == 64 || c_out == 128, "feast_fwd: C_out must be 32, 64 or 128 (got %d)", c_out);
+  GEOBI_REQUIRE(ldx >= c_in && ldo >= c_out, "feast_fwd: leading dimension smaller than channel count");
+  GEOBI_REQUIRE(precision == GEOBI_PREC_FP32 || precision == GEOBI_PREC_BF16, "feast_fwd: unknown precision %d", precision);
+  if (N == 0) return GEOBI_OK;
+  if (precision == GEOBI_PREC_BF16)
+    return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, W, U, c, bias, c_out, act_slope, out, ldo, ws, ws_bytes, st);
+  if (!ws || ws_bytes < geobi_feast_fwd_ws_bytes(N, c_in, c_out, precision)) {
+    set_error("feast_fwd: workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  Carver cv(ws, ws_bytes);
+  FeastWs Wk;
+  carve_feast(cv, N, c_in, c_out, &Wk);
+  const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
+  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, Wk.P);
+  GEOBI_LAUNCH_OK("feast_project");
+  feast_transpose_w_kernel<<<64, 256, 0, st>>>(W, c_in, c_out, Wk.Wt);
+  const unsigned ab = (unsigned)cdiv(N, 8);
+  if (c_in <= 32) feast_aggregate_kernel<1><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, Wk.P, c, Wk.Z);
+  else if (c_in <= 64) feast_aggregate_kernel<2><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, Wk.P, c, Wk.Z);
+  else feast_aggregate_kernel<4><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, Wk.P, c, Wk.Z);
+  GEOBI_LAUNCH_OK("feast_aggregate");
+  const int K = H * c_in;
+  if (c_out == 32) {
+    dim3 g((unsigned)cdiv(N, 64), 1);
+    gemm_bias_act_kernel<32><<<g, 128, 0, st>>>(Wk.Z, K, Wk.Wt, c_out, bias, N, K, act_slope, out, ldo);
+  } else {
+    dim3 g((unsigned)cdiv(N, 64), c_out / 64);
+    gemm_bias_act_kernel<64><<<g, 256, 0, st>>>(Wk.Z, K, Wk.Wt, c_out, bias, N, K, act_slope, out, ldo);
+  }
+  GEOBI_LAUNCH_OK("feast_gemm");
+  return GEOBI_OK;
+}
+
+extern "C" int geobi_fc_head_fwd(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
+                                 const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2,
+                                 float* out, int64_t ldo, int precision, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(f && W1 && b1 && W2 && b2 && out && n >= 0, "fc_head_fwd: null argument");
+  GEOBI_REQUIRE(c_in == 32 || c_in == 64, "fc_head_fwd: c_in must be 32 or 64 (got %d)", c_in);
+  GEOBI_REQUIRE(hidden > 0 && hidden % 128 == 0, "fc_head_fwd: hidden must be a multiple of 128 (got %d)", hidden);
+  GEOBI_REQUIRE(c_out >= 1 && c_out <= 4, "fc_head_fwd: c_out must be in 1..4 (got %d)", c_out);
+  GEOBI_REQUIRE(epilogue >= 0 && epilogue <= 3, "fc_head_fwd: unknown epilogue %d", epilogue);
+  GEOBI_REQUIRE(!(epilogue == 1 || epilogue == 2) || res, "fc_head_fwd: epilogue %d needs res", epilogue);
+  GEOBI_REQUIRE(epilogue != 2 || res2, "fc_head_fwd: epilogue 2 needs res2");
+  GEOBI_REQUIRE(precision == GEOBI_PREC_FP32 || precision == GEOBI_PREC_BF16, "fc_head_fwd: unknown precision %d", precision);
+  if (n == 0) return GEOBI_OK;
+  if (precision == GEOBI_PREC_BF16)
+    return fc_head_fwd_tc(f, ldf, n, c_in, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2, ldres2, out, ldo, st);
+  const unsigned blocks = (unsigned)cdiv(n, 64);
+  if (c_in == 32)
+    fc_head_kernel<32><<<blocks, 256, 0, st>>>(f, ldf, n, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2, ldres2, out, ldo);
+  else
+    fc_head_kernel<64><<<blocks, 256, 0, st>>>(f, ldf, n, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2, ldres2, out, ldo);
+  GEOBI_LAUNCH_OK("fc_head");
+  return GEOBI_OK;
+}

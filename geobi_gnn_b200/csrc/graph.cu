@@ -1,0 +1,762 @@
+// Integer / graph kernels of libgeobi: scan, COO->CSR (coalesce), facet graph, exact parallel
+// greedy matching (graclus), cluster relabel / grouping, edge coarsening.  All results are
+// bit-exact w.r.t. the oracle (sorted-unique CSR == torch_sparse.coalesce order).
+//
+// One device primitive carries every "sort + dedup a short adjacency row" need: rows are
+// filled as 64-bit keys (primary<<32 | secondary), one warp rank-sorts its row (O(L^2/32),
+// L ~ 6..40 on meshes), marks run heads, and a second pass compacts after a scan.
+#include "common.cuh"
+
+namespace geobi {
+
+constexpr uint64_t KEY_INVALID = ~0ull;
+constexpr int MAX_ROW = 32768;  // rank sort is quadratic; longer rows are rejected (status)
+
+// status words kept in every graph workspace
+enum { ST_ERR = 0, ST_AUX = 1, ST_WORDS = 4 };
+
+// ------------------------------------------------------------------------------ scan
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// exclusive scan of one int per thread over a 256-thread block; total -> *total (all threads)
+__device__ __forceinline__ int block_excl_scan(int v, int* total) {
+  __shared__ int wsum[SCAN_THREADS / 32];
+  __shared__ int tot;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int s = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+    int si = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, si, o);
+      if (lane >= o) si += t;
+    }
+    if (lane < SCAN_THREADS / 32) wsum[lane] = si - s;
+    if (lane == 31) tot = si;
+  }
+  __syncthreads();
+  const int r = wsum[wid] + incl - v;
+  *total = tot;
+  __syncthreads();  // wsum/tot reusable by a following call
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int* __restrict__ in, int64_t n, int* __restrict__ partial) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k * SCAN_THREADS + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  int tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(int* partial, int64_t nb) {
+  int carry = 0;
+  for (int64_t base = 0; base < nb; base += SCAN_THREADS) {
+    int64_t i = base + threadIdx.x;
+    int v = i < nb ? partial[i] : 0;
+    int tot;
+    int ex = block_excl_scan(v, &tot);
+    if (i < nb) partial[i] = carry + ex;
+    carry += tot;
+  }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const int* __restrict__ in, int64_t n, const int* __restrict__ partial, int* __restrict__ out) {
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k;
+    v[k] = i < n ? in[i] : 0;
+    s += v[k];
+  }
+  int tot;
+  int ex = block_excl_scan(s, &tot) + partial[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k;
+    if (i < n) out[i] = ex;
+    ex += v[k];
+    if (i == n - 1) out[n] = ex;
+  }
+}
+
+size_t scan_ws_bytes(int64_t n) { return align256((size_t)(cdiv(n > 0 ? n : 1, SCAN_TILE)) * sizeof(int)) + 256; }
+
+int scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, size_t ws_bytes, cudaStream_t st) {
+  GEOBI_REQUIRE(n >= 0 && out != nullptr, "scan: bad arguments");
+  if (n == 0) {
+    GEOBI_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(int), st));
+    return GEOBI_OK;
+  }
+  if (ws_bytes < scan_ws_bytes(n) || ws == nullptr) {
+    set_error("scan: workspace too small (%zu < %zu)", ws_bytes, scan_ws_bytes(n));
+    return GEOBI_ERR_WORKSPACE;
+  }
+  const int64_t nb = cdiv(n, SCAN_TILE);
+  int* partial = static_cast<int*>(ws);
+  scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, partial);
+  scan_partials_kernel<<<1, SCAN_THREADS, 0, st>>>(partial, nb);
+  scan_final_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, partial, out);
+  GEOBI_LAUNCH_OK("scan");
+  return GEOBI_OK;
+}
+
+// ------------------------------------------------------------------------------ row sort / compact
+// One warp per row.  Row r occupies raw[start, end): start = raw_rowptr[r] (or r*stride).
+// Valid keys are unique.  sorted[start + rank] = key;  vcount[r] = #valid;  ucount[r] = #run heads
+// (runs = equal high words) when dedup, else #valid.
+__global__ void __launch_bounds__(256) sort_rows_kernel(const int* __restrict__ raw_rowptr, int stride, const uint64_t* __restrict__ raw,
+                                                        uint64_t* __restrict__ sorted, int* __restrict__ vcount, int* __restrict__ ucount,
+                                                        int64_t nrows, int dedup, int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= nrows) return;
+  const int64_t start = raw_rowptr ? (int64_t)raw_rowptr[r] : r * (int64_t)stride;
+  const int64_t end = raw_rowptr ? (int64_t)raw_rowptr[r + 1] : start + stride;
+  const int L = (int)(end - start);
+  if (L > MAX_ROW) {
+    if (lane == 0) {
+      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+      vcount[r] = 0;
+      ucount[r] = 0;
+    }
+    return;
+  }
+  const uint64_t* row = raw + start;
+  int nvalid = 0;
+  for (int i0 = 0; i0 < L; i0 += 32) {
+    const int i = i0 + lane;
+    const uint64_t key = i < L ? row[i] : KEY_INVALID;
+    const bool valid = key != KEY_INVALID;
+    if (valid) {
+      int rank = 0;
+      for (int k = 0; k < L; ++k) rank += (row[k] < key) ? 1 : 0;
+      sorted[start + rank] = key;
+    }
+    nvalid += __popc(__ballot_sync(0xffffffffu, valid));
+  }
+  __syncwarp();
+  int heads = nvalid;
+  if (dedup) {
+    heads = 0;
+    for (int t0 = 0; t0 < nvalid; t0 += 32) {
+      const int t = t0 + lane;
+      bool head = false;
+      if (t < nvalid) head = (t == 0) || ((sorted[start + t] >> 32) != (sorted[start + t - 1] >> 32));
+      heads += __popc(__ballot_sync(0xffffffffu, head));
+    }
+  }
+  if (lane == 0) {
+    vcount[r] = nvalid;
+    ucount[r] = heads;
+  }
+}
+
+// Second pass: write the compacted CSR row.  nbr = high word (nbr_in_hi) or low word of the key; the
+// other word ("tag") indexes the weight source: widx = tag (+ raw row start if w_rel); tags >= w_mod
+// (w_mod > 0) are flipped copies of edge tag - w_mod.
+__global__ void __launch_bounds__(256) compact_rows_kernel(const int* __restrict__ raw_rowptr, int stride, const uint64_t* __restrict__ sorted,
+                                                           const int* __restrict__ vcount, const int* __restrict__ out_rowptr, int64_t nrows,
+                                                           int dedup, int nbr_in_hi, const float* __restrict__ wsrc, int w_rel, int64_t w_mod,
+                                                           int w_mean, int32_t* __restrict__ out_nbr, float* __restrict__ out_w,
+                                                           int64_t* __restrict__ eid_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= nrows) return;
+  const int64_t start = raw_rowptr ? (int64_t)raw_rowptr[r] : r * (int64_t)stride;
+  const int nvalid = vcount[r];
+  const int64_t ostart = out_rowptr[r];
+  int base = 0;
+  for (int t0 = 0; t0 < nvalid; t0 += 32) {
+    const int t = t0 + lane;
+    uint64_t key = 0;
+    bool head = false;
+    if (t < nvalid) {
+      key = sorted[start + t];
+      head = !dedup || t == 0 || ((key >> 32) != (sorted[start + t - 1] >> 32));
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int64_t o = ostart + base + __popc(mask & ((1u << lane) - 1u));
+      const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+      out_nbr[o] = (int32_t)(nbr_in_hi ? hi : lo);
+      const uint32_t tag = nbr_in_hi ? lo : hi;
+      if (eid_out) eid_out[o] = (w_mod > 0 && (int64_t)tag >= w_mod) ? -1 - ((int64_t)tag - w_mod) : (int64_t)tag;
+      if (out_w) {
+        float s = 0.f;
+        int cnt = 0;
+        for (int q = t; q < nvalid; ++q) {
+          const uint64_t kq = sorted[start + q];
+          if (q > t && (!dedup || (kq >> 32) != (key >> 32))) break;
+          int64_t tg = nbr_in_hi ? (uint32_t)kq : (uint32_t)(kq >> 32);
+          if (w_mod > 0 && tg >= w_mod) tg -= w_mod;
+          s += wsrc[w_rel ? start + tg : tg];
+          ++cnt;
+        }
+        out_w[o] = w_mean ? s / (float)cnt : s;
+      }
+    }
+    base += __popc(mask);
+  }
+}
+
+static int rows_sort_compact(const int* raw_rowptr, int stride, const uint64_t* raw, uint64_t* sorted, int* vcount, int* ucount,
+                             int64_t nrows, int dedup, int nbr_in_hi, const float* wsrc, int w_rel, int64_t w_mod, int w_mean,
+                             int32_t* out_rowptr, int32_t* out_nbr, float* out_w, int64_t* eid_out, int* status, void* scan_ws,
+                             size_t scan_bytes, cudaStream_t st) {
+  if (nrows > 0) {
+    const unsigned blocks = (unsigned)cdiv(nrows * 32, 256);
+    sort_rows_kernel<<<blocks, 256, 0, st>>>(raw_rowptr, stride, raw, sorted, vcount, ucount, nrows, dedup, status);
+    GEOBI_LAUNCH_OK("sort_rows");
+  }
+  int rc = scan_i32(ucount, out_rowptr, nrows, scan_ws, scan_bytes, st);
+  if (rc) return rc;
+  if (nrows > 0) {
+    const unsigned blocks = (unsigned)cdiv(nrows * 32, 256);
+    compact_rows_kernel<<<blocks, 256, 0, st>>>(raw_rowptr, stride, sorted, vcount, out_rowptr, nrows, dedup, nbr_in_hi, wsrc, w_rel,
+                                                w_mod, w_mean, out_nbr, out_w, eid_out);
+    GEOBI_LAUNCH_OK("compact_rows");
+  }
+  return GEOBI_OK;
+}
+
+// copies status + rowptr[n] to the host and synchronises; turns device-side errors into return codes
+static int finish_sync(const int* status, const int32_t* rowptr, int64_t nrows, int64_t* nnz_host, const char* what, cudaStream_t st) {
+  int h_status[ST_WORDS] = {0, 0, 0, 0};
+  int h_nnz = 0;
+  GEOBI_CUDA_OK(cudaMemcpyAsync(h_status, status, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+  if (rowptr) GEOBI_CUDA_OK(cudaMemcpyAsync(&h_nnz, rowptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, st));
+  GEOBI_CUDA_OK(cudaStreamSynchronize(st));
+  if (h_status[ST_ERR] != 0) {
+    set_error("%s: device-side check failed (index out of range or adjacency row longer than %d)", what, MAX_ROW);
+    return h_status[ST_ERR];
+  }
+  if (nnz_host) *nnz_host = h_nnz;
+  return GEOBI_OK;
+}
+
+// ------------------------------------------------------------------------------ COO -> CSR
+struct CooView {
+  const int64_t* row;
+  const int64_t* col;
+  int64_t n_edges;
+  int64_t n_nodes;
+  int by_col, drop_self, symmetrize;
+  // element id t in [0, n_edges * (symmetrize ? 2 : 1)); returns false if skipped
+  __device__ __forceinline__ bool get(int64_t t, int64_t& seg, int64_t& other, int* status) const {
+    const bool flip = t >= n_edges;
+    const int64_t e = flip ? t - n_edges : t;
+    int64_t a = row[e], b = col[e];
+    if (a < 0 || a >= n_nodes || b < 0 || b >= n_nodes) {
+      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+      return false;
+    }
+    if (drop_self && a == b) return false;
+    if (flip != (by_col != 0)) { int64_t x = a; a = b; b = x; }
+    seg = a;
+    other = b;
+    return true;
+  }
+};
+
+__global__ void coo_count_kernel(CooView v, int64_t total, int* __restrict__ count, int* status) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s, o;
+    if (v.get(t, s, o, status)) atomicAdd(&count[s], 1);
+  }
+}
+
+__global__ void coo_fill_kernel(CooView v, int64_t total, const int* __restrict__ raw_rowptr, int* __restrict__ cursor, int sort_nbr,
+                                uint64_t* __restrict__ raw, int* status) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    int64_t s, o;
+    if (!v.get(t, s, o, status)) continue;
+    const int pos = raw_rowptr[s] + atomicAdd(&cursor[s], 1);
+    raw[pos] = sort_nbr ? (((uint64_t)o << 32) | (uint64_t)(uint32_t)t) : (((uint64_t)(uint32_t)t << 32) | (uint64_t)(uint32_t)o);
+  }
+}
+
+static unsigned grid_for(int64_t n, int threads) {
+  int64_t b = cdiv(n, threads);
+  const int64_t cap = 148 * 64;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+struct CooWs {
+  int *count, *raw_rowptr, *vcount, *ucount, *status;
+  uint64_t *raw, *sorted;
+  void* scan;
+  size_t scan_bytes;
+};
+template <class C>
+static void carve_coo(C& c, int64_t total, int64_t n, CooWs* out) {
+  int* count = c.template take<int>(n + 1);
+  int* raw_rowptr = c.template take<int>(n + 1);
+  int* vcount = c.template take<int>(n + 1);
+  int* ucount = c.template take<int>(n + 1);
+  int* status = c.template take<int>(ST_WORDS);
+  uint64_t* raw = c.template take<uint64_t>(total + 1);
+  uint64_t* sorted = c.template take<uint64_t>(total + 1);
+  const size_t sb = scan_ws_bytes(n + 1);
+  char* scan = c.template take<char>(sb);
+  if (out) *out = CooWs{count, raw_rowptr, vcount, ucount, status, raw, sorted, scan, sb};
+}
+struct NullCarver {
+  Sizer s;
+  template <typename T>
+  T* take(size_t n) { s.take<T>(n); return nullptr; }
+};
+
+}  // namespace geobi
+
+using namespace geobi;
+
+extern "C" size_t geobi_scan_ws_bytes(int64_t n) { return scan_ws_bytes(n); }
+
+extern "C" int geobi_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, size_t ws_bytes, void* stream) {
+  return scan_i32(in, out, n, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t geobi_csr_from_coo_ws_bytes(int64_t n_edges, int64_t n_nodes, int flags) {
+  NullCarver c;
+  carve_coo(c, n_edges * ((flags & GEOBI_COO_SYMMETRIZE) ? 2 : 1), n_nodes, nullptr);
+  return c.s.total();
+}
+
+extern "C" int geobi_csr_from_coo(const int64_t* row, const int64_t* col, const float* w, int64_t n_edges, int64_t n_nodes, int flags,
+                                  int32_t* rowptr, int32_t* nbr, float* w_out, int64_t* eid_out, int64_t* nnz_host, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int sym = (flags & GEOBI_COO_SYMMETRIZE) ? 1 : 0;
+  const int64_t total = n_edges * (sym ? 2 : 1);
+  GEOBI_REQUIRE(n_edges >= 0 && n_nodes >= 0 && rowptr && (nbr || total == 0), "csr_from_coo: bad arguments");
+  GEOBI_REQUIRE(total < (int64_t)1 << 31 && n_nodes < (int64_t)1 << 31, "csr_from_coo: sizes exceed int32 indexing");
+  GEOBI_REQUIRE(!(flags & GEOBI_COO_DEDUP) || (flags & GEOBI_COO_SORT_NBR), "csr_from_coo: DEDUP needs SORT_NBR");
+  GEOBI_REQUIRE((w == nullptr) == (w_out == nullptr), "csr_from_coo: w and w_out must both be given or both be NULL");
+  if (ws_bytes < geobi_csr_from_coo_ws_bytes(n_edges, n_nodes, flags) || !ws) {
+    set_error("csr_from_coo: workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  Carver c(ws, ws_bytes);
+  CooWs W;
+  carve_coo(c, total, n_nodes, &W);
+  GEOBI_CUDA_OK(cudaMemsetAsync(W.count, 0, sizeof(int) * (n_nodes + 1), st));
+  GEOBI_CUDA_OK(cudaMemsetAsync(W.status, 0, sizeof(int) * ST_WORDS, st));
+  CooView v{row, col, n_edges, n_nodes, (flags & GEOBI_COO_BY_COL) ? 1 : 0, (flags & GEOBI_COO_DROP_SELF) ? 1 : 0, sym};
+  if (total > 0) {
+    coo_count_kernel<<<grid_for(total, 256), 256, 0, st>>>(v, total, W.count, W.status);
+    GEOBI_LAUNCH_OK("coo_count");
+  }
+  int rc = scan_i32(W.count, W.raw_rowptr, n_nodes, W.scan, W.scan_bytes, st);
+  if (rc) return rc;
+  GEOBI_CUDA_OK(cudaMemsetAsync(W.count, 0, sizeof(int) * (n_nodes + 1), st));
+  const int sort_nbr = (flags & GEOBI_COO_SORT_NBR) ? 1 : 0;
+  if (total > 0) {
+    coo_fill_kernel<<<grid_for(total, 256), 256, 0, st>>>(v, total, W.raw_rowptr, W.count, sort_nbr, W.raw, W.status);
+    GEOBI_LAUNCH_OK("coo_fill");
+  }
+  rc = rows_sort_compact(W.raw_rowptr, 0, W.raw, W.sorted, W.vcount, W.ucount, n_nodes, (flags & GEOBI_COO_DEDUP) ? 1 : 0, sort_nbr, w,
+                         /*w_rel=*/0, /*w_mod=*/sym ? n_edges : 0, (flags & GEOBI_COO_W_MEAN) ? 1 : 0, rowptr, nbr, w_out, eid_out,
+                         W.status, W.scan, W.scan_bytes, st);
+  if (rc) return rc;
+  if (nnz_host) return finish_sync(W.status, rowptr, n_nodes, nnz_host, "csr_from_coo", st);
+  return GEOBI_OK;
+}
+
+// ------------------------------------------------------------------------------ CSR -> COO
+namespace geobi {
+__global__ void csr_to_coo_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr, int64_t n, int64_t nnz,
+                                  int64_t* __restrict__ ei) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= n) return;
+  const int s = rowptr[r], e = rowptr[r + 1];
+  for (int k = s + lane; k < e; k += 32) {
+    ei[k] = r;
+    ei[nnz + k] = nbr[k];
+  }
+}
+}  // namespace geobi
+
+extern "C" int geobi_csr_to_coo(const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes, int64_t nnz, int64_t* edge_index, void* stream) {
+  GEOBI_REQUIRE(rowptr && edge_index && n_nodes >= 0 && nnz >= 0, "csr_to_coo: bad arguments");
+  if (n_nodes == 0 || nnz == 0) return GEOBI_OK;
+  csr_to_coo_kernel<<<(unsigned)cdiv(n_nodes * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, nbr, n_nodes, nnz, edge_index);
+  GEOBI_LAUNCH_OK("csr_to_coo");
+  return GEOBI_OK;
+}
+
+// ------------------------------------------------------------------------------ facet graph
+namespace geobi {
+__global__ void facet_fill_kernel(const int64_t* __restrict__ fv, const int64_t* __restrict__ vf, int64_t F, int64_t V, int K,
+                                  uint64_t* __restrict__ raw, int* status) {
+  const int64_t total = F * 3 * K;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = t / (3 * K);
+    const int slot = (int)(t - f * 3 * K);
+    const int64_t v = fv[f * 3 + slot / K];
+    uint64_t key = KEY_INVALID;
+    if (v < 0 || v >= V) {
+      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+    } else {
+      const int64_t g = vf[v * K + slot % K];
+      if (g >= F) atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+      else if (g >= 0) key = ((uint64_t)g << 32) | (uint32_t)slot;
+    }
+    raw[t] = key;
+  }
+}
+struct FacetWs {
+  int *vcount, *ucount, *status;
+  uint64_t *raw, *sorted;
+  void* scan;
+  size_t scan_bytes;
+};
+template <class C>
+static void carve_facet(C& c, int64_t F, int64_t K, FacetWs* out) {
+  int* vcount = c.template take<int>(F + 1);
+  int* ucount = c.template take<int>(F + 1);
+  int* status = c.template take<int>(ST_WORDS);
+  uint64_t* raw = c.template take<uint64_t>(F * 3 * K + 1);
+  uint64_t* sorted = c.template take<uint64_t>(F * 3 * K + 1);
+  const size_t sb = scan_ws_bytes(F + 1);
+  char* scan = c.template take<char>(sb);
+  if (out) *out = FacetWs{vcount, ucount, status, raw, sorted, scan, sb};
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_build_facet_graph_ws_bytes(int64_t n_faces, int64_t k) {
+  NullCarver c;
+  carve_facet(c, n_faces, k, nullptr);
+  return c.s.total();
+}
+
+extern "C" int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts, int64_t k, int32_t* rowptr,
+                                       int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(fv && vf && rowptr && nbr && n_faces > 0 && n_verts > 0 && k > 0, "build_facet_graph: bad arguments");
+  GEOBI_REQUIRE(n_faces * 3 * k < (int64_t)1 << 31, "build_facet_graph: 3*K*F exceeds int32 indexing");
+  if (ws_bytes < geobi_build_facet_graph_ws_bytes(n_faces, k) || !ws) {
+    set_error("build_facet_graph: workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  Carver c(ws, ws_bytes);
+  FacetWs W;
+  carve_facet(c, n_faces, k, &W);
+  GEOBI_CUDA_OK(cudaMemsetAsync(W.status, 0, sizeof(int) * ST_WORDS, st));
+  facet_fill_kernel<<<grid_for(n_faces * 3 * k, 256), 256, 0, st>>>(fv, vf, n_faces, n_verts, (int)k, W.raw, W.status);
+  GEOBI_LAUNCH_OK("facet_fill");
+  int rc = rows_sort_compact(nullptr, (int)(3 * k), W.raw, W.sorted, W.vcount, W.ucount, n_faces, /*dedup=*/1, /*nbr_in_hi=*/1, nullptr, 0, 0,
+                             0, rowptr, nbr, nullptr, nullptr, W.status, W.scan, W.scan_bytes, st);
+  if (rc) return rc;
+  if (nnz_host) return finish_sync(W.status, rowptr, n_faces, nnz_host, "build_facet_graph", st);
+  return GEOBI_OK;
+}
+
+// ------------------------------------------------------------------------------ graclus (exact parallel greedy)
+namespace geobi {
+constexpr int M_NONE = -1, M_SINGLE = -2;
+
+// Phase A: decide from the state at round start.  match[u] = partner | M_SINGLE | M_NONE.
+__global__ void graclus_propose_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr, const float* __restrict__ w,
+                                       const int* __restrict__ rank, const int* __restrict__ label, int64_t n, int* __restrict__ match,
+                                       const int* __restrict__ decided) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  if (*decided >= n) { match[u] = M_NONE; return; }  // finished: make the paired apply a no-op
+  int m = M_NONE;
+  if (label[u] < 0) {
+    const int ru = rank[u];
+    int best = -1;
+    float wmax = 0.f;
+    bool localmin = true;
+    for (int e = rowptr[u]; e < rowptr[u + 1]; ++e) {
+      const int v = nbr[e];
+      if (label[v] >= 0) continue;
+      if (rank[v] < ru) { localmin = false; break; }
+      if (!w) { if (best < 0) best = v; }
+      else if (w[e] >= wmax) { best = v; wmax = w[e]; }
+    }
+    if (localmin) {
+      if (best < 0) m = M_SINGLE;
+      else {
+        bool first = true;  // u must precede every undecided neighbour of its partner
+        for (int e = rowptr[best]; e < rowptr[best + 1]; ++e) {
+          const int z = nbr[e];
+          if (label[z] < 0 && rank[z] < ru) { first = false; break; }
+        }
+        if (first) m = best;
+      }
+    }
+  }
+  match[u] = m;
+}
+
+// Phase B: apply.  Pairs are disjoint by construction, so plain stores suffice.
+__global__ void graclus_apply_kernel(const int* __restrict__ match, int* __restrict__ label, int64_t n, int* __restrict__ decided) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int add = 0;
+  if (u < n) {
+    const int m = match[u];
+    if (m == M_SINGLE) { label[u] = (int)u; add = 1; }
+    else if (m >= 0) { const int l = m < (int)u ? m : (int)u; label[u] = l; label[m] = l; add = 2; }
+  }
+  // block-level count, one atomic per warp
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+  if (lane == 0 && add) atomicAdd(decided, add);
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_graclus_ws_bytes(int64_t n_nodes) { return align256((size_t)(n_nodes + 1) * sizeof(int)) + 512; }
+
+extern "C" int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const float* w, const int32_t* rank, int64_t n_nodes, int32_t* label,
+                             int* rounds_host, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(rowptr && rank && label && n_nodes >= 0, "graclus: bad arguments");
+  if (rounds_host) *rounds_host = 0;
+  if (n_nodes == 0) return GEOBI_OK;
+  if (ws_bytes < geobi_graclus_ws_bytes(n_nodes) || !ws) {
+    set_error("graclus: workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  int* decided = static_cast<int*>(ws);                       // one counter (256-byte slot)
+  int* match = reinterpret_cast<int*>(static_cast<char*>(ws) + 256);
+  GEOBI_CUDA_OK(cudaMemsetAsync(decided, 0, sizeof(int), st));
+  GEOBI_CUDA_OK(cudaMemsetAsync(label, 0xff, sizeof(int) * n_nodes, st));  // -1 = undecided
+  const unsigned blocks = (unsigned)cdiv(n_nodes, 256);
+  int rounds = 0, h_decided = 0, batch = 12;
+  const int max_rounds = 4096;
+  while (rounds < max_rounds) {
+    for (int k = 0; k < batch; ++k) {
+      graclus_propose_kernel<<<blocks, 256, 0, st>>>(rowptr, nbr, w, rank, label, n_nodes, match, decided);
+      graclus_apply_kernel<<<blocks, 256, 0, st>>>(match, label, n_nodes, decided);
+    }
+    GEOBI_LAUNCH_OK("graclus round");
+    rounds += batch;
+    GEOBI_CUDA_OK(cudaMemcpyAsync(&h_decided, decided, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GEOBI_CUDA_OK(cudaStreamSynchronize(st));
+    if (h_decided >= n_nodes) break;
+    batch = 6;
+  }
+  if (rounds_host) *rounds_host = rounds;
+  if (h_decided < n_nodes) {
+    set_error("graclus: %lld of %lld nodes undecided after %d rounds", (long long)(n_nodes - h_decided), (long long)n_nodes, rounds);
+    return GEOBI_ERR_NOCONVERGE;
+  }
+  return GEOBI_OK;
+}
+
+// ------------------------------------------------------------------------------ relabel / group_by
+namespace geobi {
+__global__ void mark_labels_kernel(const int* __restrict__ label, int64_t n, int* __restrict__ flag, int* status) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const int l = label[u];
+  if (l < 0 || l >= n) atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+  else flag[l] = 1;
+}
+__global__ void apply_labels_kernel(const int* __restrict__ label, const int* __restrict__ newid, int64_t n, int* __restrict__ cluster) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const int l = label[u];
+  cluster[u] = (l >= 0 && l < n) ? newid[l] : 0;
+}
+__global__ void group_count_kernel(const int* __restrict__ cluster, int64_t n, int64_t nc, int* __restrict__ count, int* status) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const int c = cluster[u];
+  if (c < 0 || c >= nc) atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+  else atomicAdd(&count[c], 1);
+}
+__global__ void group_fill_kernel(const int* __restrict__ cluster, int64_t n, int64_t nc, const int* __restrict__ raw_rowptr,
+                                  int* __restrict__ cursor, uint64_t* __restrict__ raw) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  const int c = cluster[u];
+  if (c < 0 || c >= nc) return;
+  const int pos = raw_rowptr[c] + atomicAdd(&cursor[c], 1);
+  raw[pos] = (uint64_t)(uint32_t)u << 32;
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_relabel_ws_bytes(int64_t n) {
+  Sizer s;
+  s.take<int>(n + 1);
+  s.take<int>(n + 2);
+  s.take<int>(ST_WORDS);
+  s.take<char>(scan_ws_bytes(n + 1));
+  return s.total();
+}
+
+extern "C" int geobi_relabel_clusters(const int32_t* label, int64_t n, int32_t* cluster, int64_t* n_clusters_host, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(label && cluster && n_clusters_host && n >= 0, "relabel_clusters: bad arguments");
+  if (n == 0) { *n_clusters_host = 0; return GEOBI_OK; }
+  if (ws_bytes < geobi_relabel_ws_bytes(n) || !ws) { set_error("relabel_clusters: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  Carver c(ws, ws_bytes);
+  int* flag = c.take<int>(n + 1);
+  int* newid = c.take<int>(n + 2);
+  int* status = c.take<int>(ST_WORDS);
+  const size_t sb = scan_ws_bytes(n + 1);
+  char* scan = c.take<char>(sb);
+  GEOBI_CUDA_OK(cudaMemsetAsync(flag, 0, sizeof(int) * (n + 1), st));
+  GEOBI_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int) * ST_WORDS, st));
+  const unsigned blocks = (unsigned)cdiv(n, 256);
+  mark_labels_kernel<<<blocks, 256, 0, st>>>(label, n, flag, status);
+  int rc = scan_i32(flag, newid, n, scan, sb, st);
+  if (rc) return rc;
+  apply_labels_kernel<<<blocks, 256, 0, st>>>(label, newid, n, cluster);
+  GEOBI_LAUNCH_OK("relabel");
+  return finish_sync(status, newid, n, n_clusters_host, "relabel_clusters", st);
+}
+
+extern "C" size_t geobi_group_by_ws_bytes(int64_t n, int64_t nc) {
+  Sizer s;
+  s.take<int>(nc + 1); s.take<int>(nc + 1); s.take<int>(nc + 1); s.take<int>(nc + 1);
+  s.take<int>(ST_WORDS);
+  s.take<uint64_t>(n + 1); s.take<uint64_t>(n + 1);
+  s.take<char>(scan_ws_bytes(nc + 1));
+  return s.total();
+}
+
+extern "C" int geobi_group_by(const int32_t* cluster, int64_t n, int64_t nc, int32_t* mrowptr, int32_t* members, void* ws, size_t ws_bytes,
+                              void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(cluster && mrowptr && members && n >= 0 && nc >= 0, "group_by: bad arguments");
+  if (ws_bytes < geobi_group_by_ws_bytes(n, nc) || !ws) { set_error("group_by: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  Carver c(ws, ws_bytes);
+  int* count = c.take<int>(nc + 1);
+  int* raw_rowptr = c.take<int>(nc + 1);
+  int* vcount = c.take<int>(nc + 1);
+  int* ucount = c.take<int>(nc + 1);
+  int* status = c.take<int>(ST_WORDS);
+  uint64_t* raw = c.take<uint64_t>(n + 1);
+  uint64_t* sorted = c.take<uint64_t>(n + 1);
+  const size_t sb = scan_ws_bytes(nc + 1);
+  char* scan = c.take<char>(sb);
+  GEOBI_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int) * (nc + 1), st));
+  GEOBI_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int) * ST_WORDS, st));
+  const unsigned blocks = (unsigned)cdiv(n > 0 ? n : 1, 256);
+  group_count_kernel<<<blocks, 256, 0, st>>>(cluster, n, nc, count, status);
+  int rc = scan_i32(count, raw_rowptr, nc, scan, sb, st);
+  if (rc) return rc;
+  GEOBI_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(int) * (nc + 1), st));
+  group_fill_kernel<<<blocks, 256, 0, st>>>(cluster, n, nc, raw_rowptr, count, raw);
+  GEOBI_LAUNCH_OK("group_by");
+  return rows_sort_compact(raw_rowptr, 0, raw, sorted, vcount, ucount, nc, 0, 1, nullptr, 0, 0, 0, mrowptr, members, nullptr, nullptr, status,
+                           scan, sb, st);
+}
+
+// ------------------------------------------------------------------------------ pool_edges
+namespace geobi {
+__global__ void pool_count_kernel(const int* __restrict__ rowptr, const int* __restrict__ mrowptr, const int* __restrict__ members,
+                                  int64_t nc, int* __restrict__ count) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  int s = 0;
+  for (int k = mrowptr[c]; k < mrowptr[c + 1]; ++k) {
+    const int m = members[k];
+    s += rowptr[m + 1] - rowptr[m];
+  }
+  count[c] = s;
+}
+// one warp per coarse node: concatenates its members' fine rows, relabelled
+__global__ void __launch_bounds__(256) pool_fill_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr, const float* __restrict__ w,
+                                                        const int* __restrict__ cluster, const int* __restrict__ mrowptr,
+                                                        const int* __restrict__ members, int64_t nc, const int* __restrict__ raw_rowptr,
+                                                        uint64_t* __restrict__ raw, float* __restrict__ raw_w) {
+  const int lane = threadIdx.x & 31;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= nc) return;
+  const int64_t start = raw_rowptr[c];
+  int pos = 0;
+  for (int k = mrowptr[c]; k < mrowptr[c + 1]; ++k) {
+    const int m = members[k];
+    const int s = rowptr[m], e = rowptr[m + 1];
+    for (int q = s + lane; q < e; q += 32) {
+      const int cv = cluster[nbr[q]];
+      const int p = pos + (q - s);
+      raw[start + p] = (cv == (int)c) ? KEY_INVALID : (((uint64_t)(uint32_t)cv << 32) | (uint32_t)p);
+      if (raw_w) raw_w[start + p] = w[q];
+    }
+    pos += e - s;
+  }
+}
+struct PoolWs {
+  int *count, *raw_rowptr, *vcount, *ucount, *status;
+  uint64_t *raw, *sorted;
+  float* raw_w;
+  void* scan;
+  size_t scan_bytes;
+};
+template <class C>
+static void carve_pool(C& c, int64_t nnz, int64_t nc, PoolWs* out) {
+  int* count = c.template take<int>(nc + 1);
+  int* raw_rowptr = c.template take<int>(nc + 1);
+  int* vcount = c.template take<int>(nc + 1);
+  int* ucount = c.template take<int>(nc + 1);
+  int* status = c.template take<int>(ST_WORDS);
+  uint64_t* raw = c.template take<uint64_t>(nnz + 1);
+  uint64_t* sorted = c.template take<uint64_t>(nnz + 1);
+  float* raw_w = c.template take<float>(nnz + 1);
+  const size_t sb = scan_ws_bytes(nc + 1);
+  char* scan = c.template take<char>(sb);
+  if (out) *out = PoolWs{count, raw_rowptr, vcount, ucount, status, raw, sorted, raw_w, scan, sb};
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_pool_edges_ws_bytes(int64_t nnz_fine, int64_t n_clusters) {
+  NullCarver c;
+  carve_pool(c, nnz_fine, n_clusters, nullptr);
+  return c.s.total();
+}
+
+extern "C" int geobi_pool_edges(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_t n_nodes, int64_t nnz_fine, const int32_t* cluster,
+                                const int32_t* mrowptr, const int32_t* members, int64_t n_clusters, int32_t* out_rowptr, int32_t* out_nbr,
+                                float* out_w, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(rowptr && cluster && mrowptr && members && out_rowptr && n_nodes >= 0 && n_clusters >= 0 && nnz_fine >= 0, "pool_edges: bad arguments");
+  GEOBI_REQUIRE((w == nullptr) == (out_w == nullptr), "pool_edges: w and out_w must both be given or both be NULL");
+  const int64_t h_nnz = nnz_fine;
+  if (ws_bytes < geobi_pool_edges_ws_bytes(h_nnz, n_clusters) || !ws) { set_error("pool_edges: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  Carver c(ws, ws_bytes);
+  PoolWs W;
+  carve_pool(c, h_nnz, n_clusters, &W);
+  GEOBI_CUDA_OK(cudaMemsetAsync(W.status, 0, sizeof(int) * ST_WORDS, st));
+  if (n_clusters > 0) {
+    pool_count_kernel<<<(unsigned)cdiv(n_clusters, 256), 256, 0, st>>>(rowptr, mrowptr, members, n_clusters, W.count);
+    GEOBI_LAUNCH_OK("pool_count");
+  }
+  int rc = scan_i32(W.count, W.raw_rowptr, n_clusters, W.scan, W.scan_bytes, st);
+  if (rc) return rc;
+  if (n_clusters > 0) {
+    pool_fill_kernel<<<(unsigned)cdiv(n_clusters * 32, 256), 256, 0, st>>>(rowptr, nbr, w, cluster, mrowptr, members, n_clusters, W.raw_rowptr,
+                                                                          W.raw, w ? W.raw_w : nullptr);
+    GEOBI_LAUNCH_OK("pool_fill");
+  }
+  rc = rows_sort_compact(W.raw_rowptr, 0, W.raw, W.sorted, W.vcount, W.ucount, n_clusters, 1, 1, w ? W.raw_w : nullptr, /*w_rel=*/1, 0,
+                         /*w_mean=*/1, out_rowptr, out_nbr, out_w, nullptr, W.status, W.scan, W.scan_bytes, st);
+  if (rc) return rc;
+  if (nnz_host) return finish_sync(W.status, out_rowptr, n_clusters, nnz_host, "pool_edges", st);
+  return GEOBI_OK;
+}

@@ -1,0 +1,83 @@
+"""Graph + feature assembly with the reference's surface (/root/reference/code/dataset.py:196-269),
+on the device.
+
+``process_one_submesh`` / ``post_processing`` keep their names, argument meaning and the layout
+of the returned ``(graph_v, graph_f)`` tuple.  OpenMesh (not installable here) is replaced by
+any object exposing its index arrays as numpy: ``points, ev, fv, vf, vv, face_normals,
+vertex_normals`` (geobi_gnn_b200/synth.py:TriMesh).  File I/O, the .pt
+cache and the Kinect readers are out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import data_util
+from .data import Data
+
+
+def _t(a, dtype, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(device)
+
+
+def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda"):
+    """dataset.py:196-243."""
+    ev, fv = _t(mesh_n.ev, torch.long, device), _t(mesh_n.fv, torch.long, device)
+    vf = _t(mesh_n.vf, torch.long, device)
+    edge_dual_fv = data_util.build_edge_fv(fv)
+    pos_v = _t(mesh_n.points, torch.float32, device)
+    normal_v = _t(mesh_n.vertex_normals, torch.float32, device)
+    edge_idx_v = data_util.to_undirected_with_self_loops(ev.t().contiguous(), pos_v.size(0))
+    edge_wei_v = data_util.calc_weight(pos_v, normal_v, edge_idx_v)
+    graph_v = Data(name=f"{name}-v", pos=pos_v, normal=normal_v, edge_index=edge_idx_v, edge_weight=edge_wei_v,
+                   depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1])
+    pos_f = pos_v[fv].mean(1)
+    normal_f = _t(mesh_n.face_normals, torch.float32, device).reshape(-1, 3)
+    edge_idx_f = data_util.build_facet_graph(fv, vf)
+    edge_wei_f = data_util.calc_weight(pos_f, normal_f, edge_idx_f)
+    graph_f = Data(name=f"{name}-f", pos=pos_f, normal=normal_f, edge_index=edge_idx_f, edge_weight=edge_wei_f,
+                   fv_indices=fv, edge_dual=edge_dual_fv[0])
+    if mesh_o is not None:
+        graph_v.y = _t(mesh_o.points, torch.float32, device)
+        graph_f.y = _t(mesh_o.face_normals, torch.float32, device)
+    return graph_v, graph_f
+
+
+def attach_normalisation(dual_data, points_noisy, ev):
+    """dataset.py:140,151-152: centroid / scale of the whole noisy mesh (numpy fp32, as upstream)."""
+    p = np.asarray(points_noisy, dtype=np.float32)
+    centroid = p.mean(0, keepdims=True)
+    q = p - centroid
+    e = q[ev]
+    scale = 1 / (((e[:, 0] - e[:, 1]) ** 2).sum(1) ** 0.5).mean()
+    dual_data[0].centroid = torch.from_numpy(centroid).float().to(dual_data[0].pos.device)
+    dual_data[0].scale = float(scale)
+    return dual_data
+
+
+def post_processing(dual_data, data_type="Synthetic", is_plot=False):
+    """dataset.py:245-269."""
+    data_v, data_f = dual_data
+    data_f.x = torch.cat(((data_f.pos - data_v.centroid) * data_v.scale, data_f.normal), 1)
+    data_f.normal = data_f.edge_dual = None
+    if not is_plot:
+        data_f.pos = None
+    data_v.x = torch.cat(((data_v.pos - data_v.centroid) * data_v.scale, data_v.normal), 1)
+    data_v.y = None if data_v.y is None else (data_v.y - data_v.centroid) * data_v.scale
+    data_v.normal = data_v.centroid = data_v.scale = data_v.edge_dual = None
+    if not is_plot:
+        data_v.pos = None
+    else:
+        data_v.pos = data_v.y
+        data_v.fv_indices = data_f.fv_indices
+    if data_type not in ["Kinect_v1", "Kinect_v2"]:
+        data_v.depth_direction = None
+    return data_v, data_f
+
+
+def build_dual_data(mesh_n, mesh_o=None, data_type="Synthetic", name="graph", device="cuda"):
+    """Single-patch branch of process_one_data (dataset.py:144-153) followed by post_processing."""
+    dd = process_one_submesh(mesh_n, name, mesh_o, device)
+    attach_normalisation(dd, mesh_n.points, mesh_n.ev)
+    return post_processing(dd, data_type)

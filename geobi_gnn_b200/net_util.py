@@ -1,0 +1,203 @@
+"""Pooling / fusion layers with the reference's surface (/root/reference/code/net_util.py),
+running on libgeobi kernels.
+
+* ``PoolingLayer(in_channel, pool_type, pool_step, edge_weight_type, wei_param)``  net_util.py:56-245
+* ``DualFusionLayer(in_channel)``                                                  net_util.py:248-278
+* ``pool_edge`` / ``pool_face``                                                    net_util.py:289-302
+
+Differences a caller can see: the Graclus matching is deterministic given the node
+visiting order (``PoolingLayer.perm_fn``; default = ``torch.randperm`` on the device, as the
+upstream CPU kernel draws one), and ``PoolingLayer.forced`` / ``.trace`` allow teacher forcing
+and inspection in tests.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch.nn import Linear, Parameter, init
+
+from . import nn as gnn
+from . import ops
+from .data import Data
+from .ops import CSRGraph
+
+
+def _match_csr(data) -> Optional[CSRGraph]:
+    """Source-indexed CSR (stable edge order) + weights, self loops dropped — what graclus sees.
+    Also performs the reference's write-back of the stripped edge list (net_util.py:163-167)."""
+    ei = data.edge_index
+    w = data.edge_weight if "edge_weight" in data else None
+    n = data.x.size(0)
+    tag = gnn.tag_of(ei)
+    g = tag.get("src")
+    if g is not None and g.n == n:                       # built by us: no self loops, CSR order == edge order
+        if g.nnz == 0:
+            return None
+        return dataclasses.replace(g, w=w)
+    keep = ei[0] != ei[1]
+    ei2 = ei[:, keep]
+    if ei2.numel() == 0:
+        return None
+    w2 = None if w is None else w[keep]
+    g = ops.csr_from_coo(ei2, n, w2, 0)                  # stable sort by source
+    if "tgt" in tag:
+        gnn.tag_of(ei2)["tgt"] = tag["tgt"]
+    data.edge_index, data.edge_weight = ei2, w2
+    return g
+
+
+def _minmax(v):
+    return (v - v.min()) / (v.max() - v.min() + 1e-12)
+
+
+class PoolingLayer(torch.nn.Module):
+    def __init__(self, in_channel, pool_type="max", pool_step=2, edge_weight_type=0, wei_param=2):
+        super().__init__()
+        assert pool_type in ["max", "mean"]
+        self.pool_type, self.pool_step = pool_type, pool_step
+        self.edge_weight_type, self.wei_param = edge_weight_type, wei_param
+        if edge_weight_type in [4, 5]:
+            self.lin = Linear(in_channel, in_channel)
+        if edge_weight_type in [3, 4, 5]:
+            self.att_l = Parameter(torch.empty(1, in_channel))
+            self.att_r = Parameter(torch.empty(1, in_channel))
+            init.xavier_uniform_(self.att_l.data, gain=1.414)
+            init.xavier_uniform_(self.att_r.data, gain=1.414)
+        self.unpooling_indices = None
+        self._unpool_i32 = None
+        self.perm_fn = None          # callable(n, device) -> permutation; None = torch.randperm on device
+        self.forced = None           # list of raw label tensors (teacher forcing)
+        self.trace = []
+
+    # ------------------------------------------------------------------ net_util.py:160-240
+    def _get_edge_weight(self, data) -> Optional[CSRGraph]:
+        g = _match_csr(data)
+        if g is None:
+            return None
+        t, x, w = self.edge_weight_type, data.x, g.w
+        if t == -1:
+            nw = None
+        elif t == 0:
+            nw = w
+        elif t == 1:
+            nw = ops.edge_weight_feat(x, g, 1, self.wei_param)
+        elif t == 2:
+            nw = ops.edge_weight_feat(x, g, 2, self.wei_param, w)
+        elif t == 10:
+            nw = ops.edge_weight_feat(x, g, 10, 2.0, w)
+        elif t in (3, 4, 5):
+            h = x if t == 3 else F.leaky_relu(self.lin(x), 0.2)
+            al, ar = (h * self.att_l).sum(-1), (h * self.att_r).sum(-1)
+            ei = g.edge_index()
+            s = torch.sigmoid((al[ei[0]] + ar[ei[1]]) + (al[ei[1]] + ar[ei[0]]))
+            nw = s if t != 5 else (s + w) / 2
+        elif t == 6:
+            nw = _minmax(w)
+        else:
+            d2 = ops.edge_weight_feat(x, g, 0)
+            if t == 7:
+                nw = _minmax(-d2)
+            elif t == 8:
+                nw = _minmax((d2 / (-2)).exp())
+            elif t == 9:
+                nw = _minmax(w) + _minmax((d2 / (-2)).exp())
+            else:
+                raise ValueError(f"edge_weight_type {t}")
+        return dataclasses.replace(g, w=None if nw is None else nw.detach().contiguous())
+
+    # ------------------------------------------------------------------ net_util.py:76-158
+    def forward(self, data, visual=False):
+        g = self._get_edge_weight(data)
+        x, pos = data.x, data.pos
+        edge_dual = data.edge_dual if "edge_dual" in data else None
+        face = data.fv_indices if "fv_indices" in data else None
+        dev = x.device
+        if g is None:            # no edges at all: every node is its own cluster at each step
+            g = CSRGraph(torch.zeros(x.size(0) + 1, dtype=torch.int32, device=dev),
+                         torch.empty(0, dtype=torch.int32, device=dev), x.size(0), 0, None, True)
+        clusts, self.trace = [], []
+        op = ops.OP_MAX if self.pool_type == "max" else ops.OP_MEAN
+        for step in range(self.pool_step):
+            n = x.size(0)
+            if self.forced is not None:
+                label, perm = self.forced[step].to(dev).to(torch.int32), None
+            else:
+                perm = torch.randperm(n, device=dev) if self.perm_fn is None else self.perm_fn(n).to(dev)
+                label, _ = ops.graclus(g, perm, use_weight=g.w is not None)
+            self.trace.append((g, perm, label))
+            cluster, nc = ops.relabel_clusters(label)
+            clusts.append(cluster)
+            mrowptr, members = ops.group_by(cluster, nc)
+            x = ops.segment_reduce(x, mrowptr, members, nc, op)
+            g = ops.pool_edges(g, cluster, mrowptr, members, nc)
+            pos = None if pos is None else ops.segment_reduce(pos, mrowptr, members, nc, ops.OP_MEAN)
+            edge_dual = None if edge_dual is None else cluster.long()[edge_dual]
+            if g.nnz == 0:
+                break
+        up = clusts[-1]
+        for c in clusts[-2::-1]:
+            up = up[c.long()]
+        self._unpool_i32 = up.contiguous()
+        self.unpooling_indices = up.long()
+        ei = g.edge_index()
+        gnn.attach_symmetric_csr(ei, g, has_self_loops=False)
+        return Data(x, ei, edge_dual=edge_dual, edge_weight=g.w, pos=pos, fv_indices=face)
+
+    def unpooling(self, x, out=None):
+        if self.unpooling_indices is None:
+            return x
+        return ops.gather_rows(x, self._unpool_i32, out=out)
+
+
+class DualFusionLayer(torch.nn.Module):
+    """Not instantiated by DualGNN (and edge_dual is nulled at dataset.py:252,260); kept for API parity."""
+
+    def __init__(self, in_channel):
+        super().__init__()
+        self.lin_v1 = Linear(in_channel * 2, in_channel)
+        self.lin_v2 = Linear(in_channel, in_channel)
+        self.lin_f1 = Linear(in_channel * 2, in_channel)
+        self.lin_f2 = Linear(in_channel, in_channel)
+
+    @staticmethod
+    def fusion(x_i, g: CSRGraph, x_j):
+        """cat(x_i, mean over the incident rows of x_j) — the incidence mean is one CSR segment reduce."""
+        return torch.cat([x_i, ops.segment_reduce(x_j, g.rowptr, g.nbr, g.n, ops.OP_MEAN)], dim=1)
+
+    def forward(self, data_v, data_f):
+        m, n = data_v.x.shape[0], data_f.x.shape[0]
+        ed = torch.stack([data_v.edge_dual, data_f.edge_dual], dim=0)
+        big = max(m, n)
+        g_vf = ops.csr_from_coo(ed, big, None, ops.COO_SORT_NBR | ops.COO_DEDUP)
+        g_fv = ops.csr_from_coo(ed, big, None, ops.COO_BY_COL | ops.COO_SORT_NBR | ops.COO_DEDUP)
+        g_vf = dataclasses.replace(g_vf, rowptr=g_vf.rowptr[:m + 1], n=m)
+        g_fv = dataclasses.replace(g_fv, rowptr=g_fv.rowptr[:n + 1], n=n)
+        x_v = self.fusion(data_v.x, g_vf, data_f.x)
+        x_f = self.fusion(data_f.x, g_fv, data_v.x)
+        x_v = F.leaky_relu(self.lin_v2(F.leaky_relu(self.lin_v1(x_v), 0.2)), 0.2)
+        x_f = F.leaky_relu(self.lin_f2(F.leaky_relu(self.lin_f1(x_f), 0.2)), 0.2)
+        return x_v, x_f
+
+
+def pool_edge(cluster, edge_index, edge_attr=None, op="mean"):
+    """net_util.py:289-295 on int64 edge lists (API parity; the layers above stay in CSR)."""
+    if op not in ("mean", "add"):
+        raise ValueError(op)
+    n = cluster.size(0)
+    ei = cluster.long()[edge_index.reshape(-1)].view(2, -1)
+    flags = ops.COO_DROP_SELF | ops.COO_SORT_NBR | ops.COO_DEDUP | (ops.COO_W_MEAN if op == "mean" else 0)
+    keep = ei[0] != ei[1]
+    if int(keep.sum()) == 0:
+        return ei[:, keep], (None if edge_attr is None else edge_attr[keep])
+    g = ops.csr_from_coo(ei, n, edge_attr, flags)
+    return g.edge_index(), g.w
+
+
+def pool_face(cluster, fv_indices):
+    """net_util.py:298-302."""
+    face = cluster.long()[fv_indices.reshape(-1)].view(-1, 3)
+    bad = (face[:, 0] == face[:, 1]) | (face[:, 0] == face[:, 2]) | (face[:, 1] == face[:, 2])
+    return face[~bad]

@@ -1,0 +1,353 @@
+"""Tensor-level wrappers over the C ABI (include/geobi.h).
+
+PyTorch is used only as plumbing: device memory, the current stream and dtype
+bookkeeping.  Every function here launches hand-written sm_100a kernels from
+libgeobi.so; none has a CPU path (CPU tensors raise).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+PREC_FP32, PREC_BF16 = 0, 1
+COO_BY_COL, COO_DROP_SELF, COO_SORT_NBR, COO_DEDUP, COO_W_MEAN, COO_SYMMETRIZE = 1, 2, 4, 8, 16, 32
+OP_MEAN, OP_MAX, OP_SUM = 0, 1, 2
+
+_launches = 0  # kernels-launching ABI calls made (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.GeobiError("geobi_gnn_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws_cache = {}
+
+
+def _ws(nbytes: int, device, slot: int = 0) -> torch.Tensor:
+    """Per-device scratch buffer, grown on demand (single-stream use)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def release_workspaces():
+    _ws_cache.clear()
+
+
+def _rows(x: torch.Tensor):
+    """(tensor, ld, channels) of a 2-D fp32 tensor whose rows are contiguous (column slices allowed)."""
+    if x.dim() != 2 or x.dtype != torch.float32:
+        raise _lib.GeobiError(f"expected a 2-D float32 tensor, got {tuple(x.shape)} {x.dtype}")
+    if x.size(1) > 1 and x.stride(1) != 1:
+        x = x.contiguous()
+    if x.size(0) > 1 and x.stride(0) < x.size(1):
+        x = x.contiguous()
+    return x, (x.stride(0) if x.size(0) > 1 else max(x.size(1), 1)), x.size(1)
+
+
+# ----------------------------------------------------------------------------- graph container
+@dataclass
+class CSRGraph:
+    """int32 CSR adjacency without self loops (+ optional per-entry fp32 weight)."""
+    rowptr: torch.Tensor
+    nbr: torch.Tensor
+    n: int
+    nnz: int
+    w: Optional[torch.Tensor] = None
+    symmetric: bool = False
+    _ei: Optional[torch.Tensor] = None
+
+    def edge_index(self) -> torch.Tensor:
+        """int64 [2, nnz], row-major sorted when rows are sorted (coalesce layout)."""
+        if self._ei is None:
+            ei = torch.empty((2, self.nnz), dtype=torch.int64, device=self.rowptr.device)
+            if self.nnz:
+                lib = _lib.load()
+                _lib.check(lib.geobi_csr_to_coo(_ptr(self.rowptr), _ptr(self.nbr), self.n, self.nnz, _ptr(ei), _stream()), "csr_to_coo")
+                _count()
+            self._ei = ei
+        return self._ei
+
+
+def exclusive_scan(v: torch.Tensor) -> torch.Tensor:
+    _need_cuda(v)
+    lib = _lib.load()
+    v = v.contiguous().to(torch.int32)
+    n = v.numel()
+    out = torch.empty(n + 1, dtype=torch.int32, device=v.device)
+    ws = _ws(lib.geobi_scan_ws_bytes(n), v.device)
+    _lib.check(lib.geobi_exclusive_scan_i32(_ptr(v), _ptr(out), n, _ptr(ws), ws.numel(), _stream()), "exclusive_scan")
+    _count(3)
+    return out
+
+
+def csr_from_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional[torch.Tensor] = None, flags: int = 0,
+                 want_eid: bool = False):
+    """COO int64 [2,E] -> CSRGraph (+ eid).  Syncs once (nnz)."""
+    _need_cuda(edge_index, weight)
+    lib = _lib.load()
+    ei = edge_index.contiguous()
+    if ei.dtype != torch.int64:
+        ei = ei.long()
+    e = ei.size(1)
+    cap = e * (2 if flags & COO_SYMMETRIZE else 1)
+    dev = ei.device
+    rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+    nbr = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    w = None if weight is None else weight.contiguous().float()
+    w_out = None if w is None else torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+    eid = torch.empty(max(cap, 1), dtype=torch.int64, device=dev) if want_eid else None
+    ws = _ws(lib.geobi_csr_from_coo_ws_bytes(e, n_nodes, flags), dev)
+    nnz = C.c_int64(0)
+    row, col = ei[0], ei[1]
+    _lib.check(lib.geobi_csr_from_coo(_ptr(row), _ptr(col), _ptr(w), e, n_nodes, flags, _ptr(rowptr), _ptr(nbr), _ptr(w_out),
+                                      _ptr(eid), C.byref(nnz), _ptr(ws), ws.numel(), _stream()), "csr_from_coo")
+    _count(10)
+    k = int(nnz.value)
+    g = CSRGraph(rowptr, nbr[:k], n_nodes, k, None if w_out is None else w_out[:k])
+    return (g, eid[:k]) if want_eid else g
+
+
+def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor) -> CSRGraph:
+    """Facet 1-ring CSR with the self entry (data_util.build_facet_graph).  Syncs once."""
+    _need_cuda(fv, vf)
+    lib = _lib.load()
+    fv, vf = fv.contiguous().long(), vf.contiguous().long()
+    f, v, k = fv.size(0), vf.size(0), vf.size(1)
+    dev = fv.device
+    rowptr = torch.empty(f + 1, dtype=torch.int32, device=dev)
+    nbr = torch.empty(max(3 * k * f, 1), dtype=torch.int32, device=dev)
+    ws = _ws(lib.geobi_build_facet_graph_ws_bytes(f, k), dev)
+    nnz = C.c_int64(0)
+    _lib.check(lib.geobi_build_facet_graph(_ptr(fv), _ptr(vf), f, v, k, _ptr(rowptr), _ptr(nbr), C.byref(nnz), _ptr(ws), ws.numel(),
+                                           _stream()), "build_facet_graph")
+    _count(6)
+    n = int(nnz.value)
+    return CSRGraph(rowptr, nbr[:n].clone(), f, n, symmetric=True)
+
+
+def graclus(g: CSRGraph, perm: torch.Tensor, weight: Optional[torch.Tensor] = None, use_weight: bool = True):
+    """Exact greedy matching for visiting order `perm` -> raw labels int32 [N] (= min(u, partner))."""
+    lib = _lib.load()
+    dev = g.rowptr.device
+    _need_cuda(g.rowptr, perm)
+    rank = torch.empty(g.n, dtype=torch.int32, device=dev)
+    rank[perm.to(dev).long()] = torch.arange(g.n, dtype=torch.int32, device=dev)
+    w = (g.w if weight is None else weight) if use_weight else None
+    label = torch.empty(g.n, dtype=torch.int32, device=dev)
+    ws = _ws(lib.geobi_graclus_ws_bytes(g.n), dev)
+    rounds = C.c_int(0)
+    _lib.check(lib.geobi_graclus(_ptr(g.rowptr), _ptr(g.nbr), _ptr(w), _ptr(rank), g.n, _ptr(label), C.byref(rounds), _ptr(ws),
+                                 ws.numel(), _stream()), "graclus")
+    _count(2 * rounds.value)
+    return label, rounds.value
+
+
+def relabel_clusters(label: torch.Tensor):
+    """consecutive_cluster: (dense int32 cluster ids [N], number of clusters).  Syncs."""
+    _need_cuda(label)
+    lib = _lib.load()
+    label = label.contiguous().to(torch.int32)
+    n = label.numel()
+    cluster = torch.empty(n, dtype=torch.int32, device=label.device)
+    ws = _ws(lib.geobi_relabel_ws_bytes(n), label.device)
+    nc = C.c_int64(0)
+    _lib.check(lib.geobi_relabel_clusters(_ptr(label), n, _ptr(cluster), C.byref(nc), _ptr(ws), ws.numel(), _stream()), "relabel_clusters")
+    _count(5)
+    return cluster, int(nc.value)
+
+
+def group_by(cluster: torch.Tensor, n_clusters: int):
+    _need_cuda(cluster)
+    lib = _lib.load()
+    cluster = cluster.contiguous().to(torch.int32)
+    n = cluster.numel()
+    dev = cluster.device
+    mrowptr = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
+    members = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ws = _ws(lib.geobi_group_by_ws_bytes(n, n_clusters), dev)
+    _lib.check(lib.geobi_group_by(_ptr(cluster), n, n_clusters, _ptr(mrowptr), _ptr(members), _ptr(ws), ws.numel(), _stream()), "group_by")
+    _count(10)
+    return mrowptr, members[:n]
+
+
+def pool_edges(g: CSRGraph, cluster: torch.Tensor, mrowptr: torch.Tensor, members: torch.Tensor, n_clusters: int) -> CSRGraph:
+    """net_util.pool_edge on CSR.  Syncs once (nnz)."""
+    lib = _lib.load()
+    dev = g.rowptr.device
+    out_rowptr = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
+    out_nbr = torch.empty(max(g.nnz, 1), dtype=torch.int32, device=dev)
+    out_w = None if g.w is None else torch.empty(max(g.nnz, 1), dtype=torch.float32, device=dev)
+    ws = _ws(lib.geobi_pool_edges_ws_bytes(g.nnz, n_clusters), dev)
+    nnz = C.c_int64(0)
+    _lib.check(lib.geobi_pool_edges(_ptr(g.rowptr), _ptr(g.nbr), _ptr(g.w), g.n, g.nnz, _ptr(cluster), _ptr(mrowptr), _ptr(members),
+                                    n_clusters, _ptr(out_rowptr), _ptr(out_nbr), _ptr(out_w), C.byref(nnz), _ptr(ws), ws.numel(),
+                                    _stream()), "pool_edges")
+    _count(8)
+    k = int(nnz.value)
+    return CSRGraph(out_rowptr, out_nbr[:k], n_clusters, k, None if out_w is None else out_w[:k], symmetric=g.symmetric)
+
+
+# ----------------------------------------------------------------------------- segment / gather
+def segment_reduce(x: torch.Tensor, rowptr: Optional[torch.Tensor], idx: torch.Tensor, n_seg: int, op: int, fixed: int = 0,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, idx)
+    lib = _lib.load()
+    x, ldx, c = _rows(x)
+    idx = idx.contiguous().to(torch.int32)
+    if out is None:
+        out = torch.empty((n_seg, c), dtype=torch.float32, device=x.device)
+    o, ldo, _ = _rows(out)
+    _lib.check(lib.geobi_segment_reduce(_ptr(x), ldx, c, _ptr(rowptr), _ptr(idx), fixed, n_seg, op, _ptr(o), ldo, _stream()), "segment_reduce")
+    _count()
+    return out
+
+
+def gather_rows(x: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, idx)
+    lib = _lib.load()
+    x, ldx, c = _rows(x)
+    idx = idx.contiguous().to(torch.int32)
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    o, ldo, _ = _rows(out)
+    _lib.check(lib.geobi_gather_rows(_ptr(x), ldx, c, _ptr(idx), n, _ptr(o), ldo, _stream()), "gather_rows")
+    _count()
+    return out
+
+
+def edge_weight_feat(x: torch.Tensor, g: CSRGraph, mode: int, param: float = 2.0, w_in: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, g.rowptr)
+    lib = _lib.load()
+    x, ldx, c = _rows(x)
+    w_out = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=x.device)[:g.nnz]
+    _lib.check(lib.geobi_edge_weight_feat(_ptr(x), ldx, c, _ptr(g.rowptr), _ptr(g.nbr), g.n, _ptr(w_in), mode, float(param), _ptr(w_out),
+                                          _stream()), "edge_weight_feat")
+    _count()
+    return w_out
+
+
+def calc_weight(pos: torch.Tensor, nrm: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    _need_cuda(pos, nrm, edge_index)
+    lib = _lib.load()
+    pos, nrm = pos.contiguous().float(), nrm.contiguous().float()
+    ei = edge_index.contiguous().long()
+    e = ei.size(1)
+    w = torch.empty(e, dtype=torch.float32, device=pos.device)
+    ws = _ws(lib.geobi_calc_weight_ws_bytes(e), pos.device)
+    _lib.check(lib.geobi_calc_weight(_ptr(pos), _ptr(nrm), _ptr(ei[0]), _ptr(ei[1]), e, _ptr(w), _ptr(ws), ws.numel(), _stream()), "calc_weight")
+    _count(3)
+    return w
+
+
+# ----------------------------------------------------------------------------- conv / heads / transfer
+def feast_fwd(x: torch.Tensor, g: CSRGraph, W: torch.Tensor, U: torch.Tensor, c: torch.Tensor, bias: torch.Tensor,
+              act_slope: float = 1.0, out: Optional[torch.Tensor] = None, precision: int = PREC_FP32) -> torch.Tensor:
+    """FeaStConv forward on a TARGET-indexed CSR without self loops (implicit self loop)."""
+    _need_cuda(x, g.rowptr, W)
+    lib = _lib.load()
+    x, ldx, c_in = _rows(x)
+    c_out = bias.numel()
+    n = x.size(0)
+    if out is None:
+        out = torch.empty((n, c_out), dtype=torch.float32, device=x.device)
+    o, ldo, _ = _rows(out)
+    if o.data_ptr() != out.data_ptr():
+        raise _lib.GeobiError("feast_fwd: `out` must have contiguous rows")
+    ws = _ws(lib.geobi_feast_fwd_ws_bytes(n, c_in, c_out, precision), x.device, slot=1)
+    _lib.check(lib.geobi_feast_fwd(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g.nbr), _ptr(W.contiguous()), _ptr(U.contiguous()),
+                                   _ptr(c.contiguous()), _ptr(bias.contiguous()), c_out, float(act_slope), _ptr(o), ldo, precision,
+                                   _ptr(ws), ws.numel(), _stream()), "feast_fwd")
+    _count(4)
+    return out
+
+
+def fc_head_fwd(f: torch.Tensor, W1, b1, W2, b2, epilogue: int = 0, res: Optional[torch.Tensor] = None,
+                res2: Optional[torch.Tensor] = None, precision: int = PREC_FP32) -> torch.Tensor:
+    _need_cuda(f, W1)
+    lib = _lib.load()
+    f, ldf, c_in = _rows(f)
+    n, hidden, c_out = f.size(0), W1.size(0), W2.size(0)
+    oc = 3 if (epilogue == 2 and c_out == 1) else c_out
+    out = torch.empty((n, oc), dtype=torch.float32, device=f.device)
+    ldres = ldres2 = 0
+    if res is not None:
+        res, ldres, _ = _rows(res)
+    if res2 is not None:
+        res2, ldres2, _ = _rows(res2)
+    _lib.check(lib.geobi_fc_head_fwd(_ptr(f), ldf, n, c_in, _ptr(W1.contiguous()), _ptr(b1.contiguous()), hidden, _ptr(W2.contiguous()),
+                                     _ptr(b2.contiguous()), c_out, epilogue, _ptr(res), ldres, _ptr(res2), ldres2, _ptr(out), oc,
+                                     precision, _stream()), "fc_head_fwd")
+    _count()
+    return out
+
+
+def face_normal(points: torch.Tensor, fv: torch.Tensor) -> torch.Tensor:
+    _need_cuda(points, fv)
+    lib = _lib.load()
+    p, ldp, _ = _rows(points)
+    fv = fv.contiguous().long()
+    out = torch.empty((fv.size(0), 3), dtype=torch.float32, device=p.device)
+    _lib.check(lib.geobi_face_normal(_ptr(p), ldp, _ptr(fv), fv.size(0), _ptr(out), 3, _stream()), "face_normal")
+    _count()
+    return out
+
+
+def v2f_transfer(feat_v: torch.Tensor, fv: torch.Tensor, xf: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[xf | corner mean of feat_v | face normal of feat_v]  (network.py:335-337)."""
+    _need_cuda(feat_v, fv, xf)
+    lib = _lib.load()
+    p, ldv, _ = _rows(feat_v)
+    xf_, ldxf, cf = _rows(xf)
+    fv = fv.contiguous().long()
+    f = fv.size(0)
+    if out is None:
+        out = torch.empty((f, cf + 6), dtype=torch.float32, device=p.device)
+    o, ldo, _ = _rows(out)
+    _lib.check(lib.geobi_v2f_transfer(_ptr(p), ldv, _ptr(fv), _ptr(xf_), ldxf, cf, f, _ptr(o), ldo, _stream()), "v2f_transfer")
+    _count()
+    return out
+
+
+def update_position(points, fv, vf, face_normals, n_iter=20, depth_direction=None) -> torch.Tensor:
+    _need_cuda(points, fv, vf, face_normals)
+    lib = _lib.load()
+    p = points.contiguous().float()
+    fv, vf = fv.contiguous().long(), vf.contiguous().long()
+    fn = face_normals.contiguous().float()
+    d = None if depth_direction is None else depth_direction.contiguous().float()
+    v, f, k = p.size(0), fv.size(0), vf.size(1)
+    out = torch.empty_like(p)
+    ws = _ws(lib.geobi_update_position_ws_bytes(v, f), p.device)
+    _lib.check(lib.geobi_update_position(_ptr(p), _ptr(fv), _ptr(vf), k, _ptr(fn), int(n_iter), _ptr(d), v, f, _ptr(out), _ptr(ws),
+                                         ws.numel(), _stream()), "update_position")
+    _count(2 * int(n_iter))
+    return out

@@ -1,0 +1,207 @@
+/* geobi.h — C ABI of libgeobi.so: the B200 (sm_100a) kernels behind the GeoBi-GNN
+ * dual-domain forward.
+ *
+ * The reference (zhangyk18/GeoBi-GNN) has NO native / FFI boundary: its seam is the
+ * Python module surface imported by train_dual.py / test_dual.py.  This
+ * header is therefore the boundary a maintainer would bind underneath that surface;
+ * every entry point cites the reference expression(s) it replaces (file:line under
+ * /root/reference/code/).  The Python binding is geobi_gnn_b200/_lib.py (ctypes); see
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless the parameter name ends in `_host`.
+ *  - Features are fp32 row-major with an explicit leading dimension (`ld*`, in floats),
+ *    so a conv can write straight into a column block of a wider buffer (no torch.cat).
+ *  - Graphs are CSR with int32 indices: rowptr[N+1], nbr[nnz]; no self loops unless said.
+ *    Reference-facing edge lists are int64 [2,E] row-major (edge_index) as in PyG.
+ *  - `stream` is a cudaStream_t passed as void*.  Calls are asynchronous on that stream
+ *    except the ones documented "syncs" (they return a size to the host).
+ *  - No allocation inside: scratch comes from the caller (`ws`, `ws_bytes`), sized by the
+ *    matching *_ws_bytes() query.  Workspaces need 256-byte alignment.
+ *  - Return 0 on success, <0 on error (GEOBI_ERR_*); geobi_last_error() gives the text.
+ *  - There is no CPU fallback anywhere in this library.
+ */
+#ifndef GEOBI_H
+#define GEOBI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GEOBI_API __attribute__((visibility("default")))
+#else
+#define GEOBI_API
+#endif
+
+#define GEOBI_OK 0
+#define GEOBI_ERR_INVALID (-1)  /* bad argument (shape, null, unsupported channel count) */
+#define GEOBI_ERR_CUDA (-2)     /* CUDA runtime error (launch, memcpy)                   */
+#define GEOBI_ERR_WORKSPACE (-3) /* ws_bytes too small                                    */
+#define GEOBI_ERR_RANGE (-4)    /* index out of range / row too long, found on device    */
+#define GEOBI_ERR_NOCONVERGE (-5)
+
+#define GEOBI_HEADS 9           /* FeaStConv(heads=9): network.py:258-268 */
+
+GEOBI_API const char* geobi_last_error(void);
+GEOBI_API int geobi_version(void);
+/* sm count and compute capability of the current device (host outputs). */
+GEOBI_API int geobi_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ------------------------------------------------------------------ integer / graph */
+
+/* out[i] = sum_{k<i} in[k], i = 0..n  (n+1 outputs).  Building block of every CSR here
+ * (replaces torch.cumsum in torch_cluster's rowptr build and torch.unique's counting). */
+GEOBI_API size_t geobi_scan_ws_bytes(int64_t n);
+GEOBI_API int geobi_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, size_t ws_bytes, void* stream);
+
+/* COO (int64 edge_index rows) -> CSR.
+ * Replaces: torch_sparse.coalesce (net_util.py:263,294; data_util.py:432,455),
+ * torch_geometric.utils.remove_self_loops (net_util.py:163,292), to_undirected
+ * (dataset.py:212) and the CSR build inside torch_cluster.graclus (net_util.py:127).
+ *   segment key  = row[e] (or col[e] with GEOBI_COO_BY_COL), neighbour = the other end.
+ *   GEOBI_COO_DROP_SELF   drop row==col
+ *   GEOBI_COO_SORT_NBR    order each CSR row by (neighbour, edge id); otherwise by edge id
+ *                         (= a stable sort by segment key, the order graclus sees)
+ *   GEOBI_COO_DEDUP       merge equal (key, neighbour) pairs (needs SORT_NBR); weights
+ *                         reduced with GEOBI_COO_W_MEAN (pool_edge's op) or summed.
+ *   GEOBI_COO_SYMMETRIZE  also insert every (col,row): to_undirected.
+ * Outputs: rowptr[N+1], nbr[cap], w_out[cap] (if w), eid_out[cap] (optional: source edge id
+ * of each CSR entry, -1-e for a flipped copy), cap >= E (2E with SYMMETRIZE).
+ * nnz = rowptr[N] stays on the device; *nnz_host (optional) is filled -> then SYNCS. */
+#define GEOBI_COO_BY_COL 1
+#define GEOBI_COO_DROP_SELF 2
+#define GEOBI_COO_SORT_NBR 4
+#define GEOBI_COO_DEDUP 8
+#define GEOBI_COO_W_MEAN 16
+#define GEOBI_COO_SYMMETRIZE 32
+GEOBI_API size_t geobi_csr_from_coo_ws_bytes(int64_t n_edges, int64_t n_nodes, int flags);
+GEOBI_API int geobi_csr_from_coo(const int64_t* row, const int64_t* col, const float* w, int64_t n_edges,
+                       int64_t n_nodes, int flags, int32_t* rowptr, int32_t* nbr, float* w_out,
+                       int64_t* eid_out, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream);
+
+/* CSR -> int64 edge_index [2, nnz] (row-major sorted, the layout coalesce returns). */
+GEOBI_API int geobi_csr_to_coo(const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes, int64_t nnz,
+                     int64_t* edge_index, void* stream);
+
+/* Facet 1-ring graph, self included: data_util.build_facet_graph (data_util.py:436-456).
+ * fv [F,3], vf [V,K] int64 (pad -1).  nbr capacity 3*K*F.  SYNCS if nnz_host != NULL. */
+GEOBI_API size_t geobi_build_facet_graph_ws_bytes(int64_t n_faces, int64_t k);
+GEOBI_API int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts,
+                            int64_t k, int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws,
+                            size_t ws_bytes, void* stream);
+
+/* Heavy-edge matching identical to torch_cluster.graclus's serial CPU kernel for the visiting
+ * order `perm` (net_util.py:127), computed in parallel rounds: a node acts when it
+ * precedes all its undecided neighbours and also all undecided neighbours of its chosen partner.
+ * rank[u] = position of u in perm (int32).  w may be NULL (unweighted: first free neighbour).
+ * Adjacency must be symmetric (true for every graph on this path).  label[u] = min(u, partner).
+ * SYNCS (round count is data dependent); *rounds_host optional. */
+GEOBI_API size_t geobi_graclus_ws_bytes(int64_t n_nodes);
+GEOBI_API int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const float* w, const int32_t* rank,
+                  int64_t n_nodes, int32_t* label, int* rounds_host, void* ws, size_t ws_bytes, void* stream);
+
+/* torch_geometric consecutive_cluster (net_util.py:128): dense relabel of labels in [0,N) by
+ * ascending label value.  SYNCS: *n_clusters_host. */
+GEOBI_API size_t geobi_relabel_ws_bytes(int64_t n_nodes);
+GEOBI_API int geobi_relabel_clusters(const int32_t* label, int64_t n_nodes, int32_t* cluster, int64_t* n_clusters_host,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/* Members of each cluster as a CSR (ascending node id): the index that turns
+ * scatter(x, cluster, reduce=max|mean) (net_util.py:131-134) into a segment reduce. */
+GEOBI_API size_t geobi_group_by_ws_bytes(int64_t n_nodes, int64_t n_clusters);
+GEOBI_API int geobi_group_by(const int32_t* cluster, int64_t n_nodes, int64_t n_clusters, int32_t* mrowptr,
+                   int32_t* members, void* ws, size_t ws_bytes, void* stream);
+
+/* net_util.pool_edge (net_util.py:289-295): relabel by cluster, drop loops, coalesce with MEAN
+ * weights; emitted directly as the coarse CSR (rows sorted by neighbour = coalesce order).
+ * out capacity = nnz of the fine graph.  SYNCS if nnz_host != NULL. */
+GEOBI_API size_t geobi_pool_edges_ws_bytes(int64_t nnz_fine, int64_t n_clusters);
+GEOBI_API int geobi_pool_edges(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_t n_nodes,
+                     int64_t nnz_fine, const int32_t* cluster, const int32_t* mrowptr, const int32_t* members,
+                     int64_t n_clusters, int32_t* out_rowptr, int32_t* out_nbr, float* out_w,
+                     int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ segment / gather */
+
+/* out[s, :] = reduce_{k in rowptr[s]..rowptr[s+1]} x[idx[k], :]   (op 0 = mean with count
+ * clamped to 1, 1 = max with empty -> 0, 2 = sum).  One kernel for: cluster max/mean pool
+ * (net_util.py:131-134), pool_pos, vertex->facet corner mean (network.py:335),
+ * facet->vertex incident mean (DualFusionLayer.fusion, net_util.py:274-278).
+ * rowptr == NULL means fixed-size segments of `fixed` entries (idx is [n_seg, fixed]). */
+GEOBI_API int geobi_segment_reduce(const float* x, int64_t ldx, int channels, const int32_t* rowptr,
+                         const int32_t* idx, int fixed, int64_t n_seg, int op, float* out, int64_t ldo,
+                         void* stream);
+
+/* out[i, :] = x[idx[i], :]  — PoolingLayer.unpooling (net_util.py:242-245). */
+GEOBI_API int geobi_gather_rows(const float* x, int64_t ldx, int channels, const int32_t* idx, int64_t n_out,
+                      float* out, int64_t ldo, void* stream);
+
+/* Squared feature distance per CSR entry d2[e] = |x_i - x_nbr(e)|^2 and the live Graclus
+ * weight of PoolingLayer._get_edge_weight (net_util.py:160-240):
+ *   mode 0: w_out = d2;  1: exp(d2/-p);  2: w*exp(d2/-p);  10: w + exp(d2/-2)  (type 10, :226-230) */
+GEOBI_API int geobi_edge_weight_feat(const float* x, int64_t ldx, int channels, const int32_t* rowptr,
+                           const int32_t* nbr, int64_t n_nodes, const float* w_in, int mode, float param,
+                           float* w_out, void* stream);
+
+/* data_util.calc_weight (data_util.py:383-398) over an int64 edge list (self loops count in
+ * the mean length, as upstream): w = clamp(n_i.n_j, 1e-3) * exp(l2 / (-2*mean(sqrt(l2)) + 1e-12)). */
+GEOBI_API size_t geobi_calc_weight_ws_bytes(int64_t n_edges);
+GEOBI_API int geobi_calc_weight(const float* pos, const float* nrm, const int64_t* row, const int64_t* col,
+                      int64_t n_edges, float* w_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------ FeaSt convolution */
+
+/* torch_geometric.nn.FeaStConv(C_in, C_out, heads=9) forward (call sites network.py:271-299):
+ *   out_i = act( 1/(deg_i+1) * sum_{j in N(i) + {i}} sum_h softmax_h(U(x_j-x_i)+c) * (W_h x_j) + b )
+ * on a CSR by TARGET node without self loops (the self loop is implicit, as remove_self_loops +
+ * add_self_loops make it upstream).  W = lin.weight [9*C_out, C_in] (row h*C_out+o),
+ * U = u.weight [9, C_in].  act_slope: 1.0 = none, 0.2 = the leaky_relu after most convs.
+ * Evaluation is aggregate-first: Z[i,h,:] = sum_j q_ijh x_j, out = W_flat . Z — no per-edge
+ * tensor is ever written to HBM.  Supported C_in: 1..128, C_out: multiple of 4 up to 128.
+ * precision: GEOBI_PREC_FP32 (all fp32 CUDA cores; parity 1e-5) or GEOBI_PREC_BF16
+ * (projection on tcgen05 tensor cores with bf16 operands / fp32 accumulate; parity 2e-3). */
+#define GEOBI_PREC_FP32 0
+#define GEOBI_PREC_BF16 1
+GEOBI_API size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision);
+GEOBI_API int geobi_feast_fwd(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
+                    const int32_t* nbr, const float* W, const float* U, const float* c, const float* bias,
+                    int c_out, float act_slope, float* out, int64_t ldo, int precision, void* ws,
+                    size_t ws_bytes, void* stream);
+
+/* The two linear heads of DualGNN (network.py:324-325,340-341) fused so the [N,1024] hidden never
+ * reaches HBM:  y = W2 . leaky_relu(W1 . f + b1, 0.2) + b2, then epilogue
+ *   0: none | 1: y += res (network.py:332) | 2: y = y * res2 (force_depth, :327; c_out==1
+ *   broadcasts) then += res | 3: y = normalize(y) (network.py:343, eps 1e-12).
+ * f [N, c_in] (c_in <= 64), W1 [hidden, c_in], W2 [c_out, hidden], c_out <= 4. */
+GEOBI_API int geobi_fc_head_fwd(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1,
+                      int hidden, const float* W2, const float* b2, int c_out, int epilogue,
+                      const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
+                      int64_t ldo, int precision, void* stream);
+
+/* ------------------------------------------------------------------ dual-domain transfer */
+
+/* data_util.computer_face_normal (data_util.py:182-198): normalize(cross(v1-v0, v2-v0)), eps 1e-12. */
+GEOBI_API int geobi_face_normal(const float* points, int64_t ldp, const int64_t* fv, int64_t n_faces, float* out,
+                      int64_t ldo, void* stream);
+
+/* Vertex->facet transfer of DualGNN.forward (network.py:335-337) in one pass:
+ * out[f] = [ xf[f, 0:cf] | mean of the 3 corner predictions | face normal of the predictions ]. */
+GEOBI_API int geobi_v2f_transfer(const float* feat_v, int64_t ldv, const int64_t* fv, const float* xf, int64_t ldxf,
+                       int cf, int64_t n_faces, float* out, int64_t ldo, void* stream);
+
+/* data_util.update_position2 (data_util.py:529-556; test_dual.py:72 runs 60 iterations):
+ * n_iter Jacobi sweeps p_v += mean_{f in vf[v]} n_f (n_f . (c_f - p_v)), optional projection on
+ * depth_direction.  vf [V,K] int64 padded -1.  out may not alias points. */
+GEOBI_API size_t geobi_update_position_ws_bytes(int64_t n_verts, int64_t n_faces);
+GEOBI_API int geobi_update_position(const float* points, const int64_t* fv, const int64_t* vf, int64_t k,
+                          const float* face_normals, int n_iter, const float* depth, int64_t n_verts,
+                          int64_t n_faces, float* out, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOBI_H */

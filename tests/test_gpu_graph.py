@@ -1,0 +1,164 @@
+"""GPU: integer / graph kernels through the C ABI, bit-exact against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+from tests.util import pyg
+from oracle import ref_data_util, ref_net_util
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from geobi_gnn_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 2048, 2049, 100000, 3000001])
+def test_exclusive_scan(n):
+    ops = _ops()
+    v = torch.randint(0, 7, (n,), dtype=torch.int32)
+    out = ops.exclusive_scan(v.to(DEV)).cpu()
+    want = torch.zeros(n + 1, dtype=torch.int64)
+    want[1:] = torch.cumsum(v.long(), 0)
+    assert torch.equal(out.long(), want)
+
+
+def _random_coo(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, n, (2, e), generator=g), torch.rand(e, generator=g)
+
+
+@pytest.mark.parametrize("n,e", [(1, 0), (7, 40), (300, 5000), (20000, 300000)])
+def test_csr_from_coo_matches_coalesce(n, e):
+    ops = _ops()
+    ei, w = _random_coo(n, e, 1)
+    # coalesce(op=mean) after remove_self_loops  == pool_edge's tail
+    g = ops.csr_from_coo(ei.to(DEV), n, w.to(DEV), ops.COO_DROP_SELF | ops.COO_SORT_NBR | ops.COO_DEDUP | ops.COO_W_MEAN)
+    e2, w2 = pyg.remove_self_loops(ei, w)
+    if e2.numel():
+        e2, w2 = pyg.coalesce(e2, w2, n, n, op="mean")
+    assert torch.equal(g.edge_index().cpu(), e2)
+    assert g.nnz == e2.shape[1]
+    if g.nnz:
+        assert util.rel_err(g.w, w2) < 1e-6
+    # add
+    g = ops.csr_from_coo(ei.to(DEV), n, w.to(DEV), ops.COO_SORT_NBR | ops.COO_DEDUP)
+    e3, w3 = pyg.coalesce(ei, w, n, n) if e else (ei, w)
+    assert torch.equal(g.edge_index().cpu(), e3)
+    if e:
+        assert util.rel_err(g.w, w3) < 1e-6
+    # stable by-source order (what the matcher sees)
+    g, eid = ops.csr_from_coo(ei.to(DEV), n, w.to(DEV), ops.COO_DROP_SELF, want_eid=True)
+    rowptr, col, ww = pyg.graclus_csr(ei, w, n)
+    assert torch.equal(g.rowptr.cpu().long(), rowptr) and torch.equal(g.nbr.cpu().long(), col)
+    if g.nnz:
+        assert torch.equal(g.w.cpu(), ww)
+        assert torch.equal(w[eid.cpu()], ww)
+    # by target
+    g = ops.csr_from_coo(ei.to(DEV), n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+    rowptr, col, _ = pyg.graclus_csr(ei.flip(0), None, n)
+    assert torch.equal(g.rowptr.cpu().long(), rowptr)
+    if g.nnz:
+        srt = torch.cat([c.sort()[0] for c in torch.split(col, torch.diff(rowptr).tolist())])
+        assert torch.equal(g.nbr.cpu().long(), srt)
+
+
+def test_csr_from_coo_rejects_out_of_range():
+    ops = _ops()
+    from geobi_gnn_b200._lib import GeobiError
+    ei = torch.tensor([[0, 5], [1, 2]])
+    with pytest.raises(GeobiError):
+        ops.csr_from_coo(ei.to(DEV), 3)
+
+
+@pytest.mark.parametrize("n", [1, 3, 16])
+def test_mesh_graphs_bit_exact(n):
+    ops = _ops()
+    from geobi_gnn_b200 import data_util
+    mesh, _ = util.noisy_icosphere(n)
+    ev, fv, vf, vv = (torch.from_numpy(a) for a in (mesh.ev, mesh.fv, mesh.vf, mesh.vv))
+    # vertex graph: to_undirected + add_self_loops  (dataset.py:211-213)
+    want, _ = pyg.add_self_loops(pyg.to_undirected(ev.t()))
+    got = data_util.to_undirected_with_self_loops(ev.t().contiguous().to(DEV), mesh.n_vertices)
+    assert torch.equal(got.cpu(), want)
+    # facet graph  (data_util.py:436-456)
+    want = ref_data_util.build_facet_graph(fv, vf)
+    got = data_util.build_facet_graph(fv.to(DEV), vf.to(DEV))
+    assert torch.equal(got.cpu(), want)
+    # 2-ring vertex graph, incidence lists
+    assert torch.equal(data_util.build_vertex_graph(ev.to(DEV), vv.to(DEV)).cpu(), ref_data_util.build_vertex_graph(ev, vv))
+    assert torch.equal(data_util.build_edge_vf(vf.to(DEV)).cpu(), ref_data_util.build_edge_vf(vf))
+    assert torch.equal(data_util.build_edge_fv(fv.to(DEV)).cpu(), ref_data_util.build_edge_fv(fv))
+
+
+@pytest.mark.parametrize("n,weighted", [(2, True), (8, True), (8, False), (40, True)])
+def test_graclus_equals_serial_greedy(n, weighted):
+    ops = _ops()
+    (dv, df), _, _ = util.oracle_inputs(n)
+    for d, seed in ((dv, 3), (df, 4)):
+        N = d.x.shape[0]
+        perm = torch.randperm(N, generator=torch.Generator().manual_seed(seed))
+        w = d.edge_weight if weighted else None
+        want = pyg.graclus(d.edge_index, w, N, perm=perm)
+        ei, ww = pyg.remove_self_loops(d.edge_index, w)
+        g = ops.csr_from_coo(ei.to(DEV), N, None if ww is None else ww.to(DEV), 0)
+        got, rounds = ops.graclus(g, perm.to(DEV), use_weight=weighted)
+        assert torch.equal(got.cpu().long(), want), f"rounds={rounds}"
+        cluster, nc = ops.relabel_clusters(got)
+        want_c, _ = pyg.consecutive_cluster(want)
+        assert torch.equal(cluster.cpu().long(), want_c) and nc == int(want_c.max()) + 1
+
+
+def test_graclus_ties_and_isolated_nodes():
+    ops = _ops()
+    # path 0-1-2-3 with equal weights + isolated node 4: `>=` makes the LATER neighbour win
+    ei = torch.tensor([[0, 1, 1, 2, 2, 3], [1, 0, 2, 1, 3, 2]])
+    w = torch.ones(6)
+    for perm in ([1, 0, 2, 3, 4], [4, 3, 2, 1, 0], [2, 4, 0, 1, 3]):
+        perm = torch.tensor(perm)
+        want = pyg.graclus(ei, w, 5, perm=perm)
+        g = ops.csr_from_coo(ei.to(DEV), 5, w.to(DEV), 0)
+        got, _ = ops.graclus(g, perm.to(DEV))
+        assert got.cpu().tolist() == want.tolist()
+
+
+@pytest.mark.parametrize("n", [2, 12])
+def test_pool_step_matches_oracle(n):
+    """One full pooling step: relabel -> group -> max/mean pool -> pool_edge (net_util.py:126-137)."""
+    ops = _ops()
+    (dv, df), _, _ = util.oracle_inputs(n)
+    for d in (dv, df):
+        N = d.x.shape[0]
+        perm = torch.randperm(N, generator=torch.Generator().manual_seed(5))
+        ei, w = pyg.remove_self_loops(d.edge_index, d.edge_weight)
+        raw = pyg.graclus(ei, w, N, perm=perm)
+        cl, _ = pyg.consecutive_cluster(raw)
+        x = torch.randn(N, 32, generator=torch.Generator().manual_seed(6))
+        want_ei, want_w = ref_net_util.pool_edge(cl, ei, w)
+        g = ops.csr_from_coo(ei.to(DEV), N, w.to(DEV), 0)
+        cluster, nc = ops.relabel_clusters(raw.to(DEV).int())
+        mrowptr, members = ops.group_by(cluster, nc)
+        assert torch.equal(cluster.cpu().long(), cl)
+        for name, op in (("max", ops.OP_MAX), ("mean", ops.OP_MEAN)):
+            got = ops.segment_reduce(x.to(DEV), mrowptr, members, nc, op)
+            want = pyg.scatter(x, cl, dim=0, reduce=name)
+            assert util.rel_err(got, want) < (1e-7 if name == "max" else 1e-6)
+        g2 = ops.pool_edges(g, cluster, mrowptr, members, nc)
+        assert torch.equal(g2.edge_index().cpu(), want_ei)
+        assert util.rel_err(g2.w, want_w) < 1e-6
+        # second step on the coarse graph, arbitrary (non-matching) labels: clusters of any size
+        lab = torch.randint(0, nc, (nc,), generator=torch.Generator().manual_seed(9))
+        cl2, _ = pyg.consecutive_cluster(lab)
+        want_ei2, want_w2 = ref_net_util.pool_edge(cl2, want_ei, want_w)
+        c2, nc2 = ops.relabel_clusters(lab.to(DEV).int())
+        m2, mem2 = ops.group_by(c2, nc2)
+        g3 = ops.pool_edges(g2, c2, m2, mem2, nc2)
+        assert torch.equal(c2.cpu().long(), cl2)
+        assert torch.equal(g3.edge_index().cpu(), want_ei2)
+        if want_ei2.numel():
+            assert util.rel_err(g3.w, want_w2) < 1e-5
+        xm = ops.segment_reduce(x.to(DEV)[:nc], m2, mem2, nc2, ops.OP_MAX)
+        assert util.rel_err(xm, pyg.scatter(x[:nc], cl2, dim=0, reduce="max")) < 1e-7

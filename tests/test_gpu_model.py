@@ -1,0 +1,119 @@
+"""GPU: the whole dual-domain forward through the reference-facing modules, against the CPU oracle and
+the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+from tests.util import pyg, ref_network
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _run_pair(n, seed=0, force_depth=False, perm_seed=77):
+    """Oracle forward (recording) + product forward teacher-forced with the oracle's matchings."""
+    from geobi_gnn_b200 import network
+    data_type = "Kinect_v1" if force_depth else "Synthetic"
+    (dv, df), mesh_n, mesh_o = util.oracle_inputs(n, seed=seed, data_type=data_type)
+    ref = util.oracle_net(seed, force_depth=force_depth)
+    util.set_perm_fn(ref, perm_seed)
+    ref.record = True
+    mine = network.DualGNN(force_depth=force_depth).to(DEV)
+    mine.load_state_dict(ref.state_dict())
+    mine.eval()
+    dv_m, df_m = util.data_to(dv, DEV), util.data_to(df, DEV)
+    with torch.no_grad():
+        want = ref([dv, df])
+    for a, b in zip(util.poolings(mine), util.poolings(ref)):
+        a.forced = [t[3] for t in b.trace]
+    mine.taps = {}
+    with torch.no_grad():
+        got = mine([dv_m, df_m])
+    return ref, mine, want, got, (dv, df), (dv_m, df_m)
+
+
+@pytest.mark.parametrize("n,force_depth", [(3, False), (12, False), (6, True), (32, False)])
+def test_dualgnn_forward_matches_oracle_teacher_forced(n, force_depth):
+    ref, mine, want, got, d_ref, d_mine = _run_pair(n, force_depth=force_depth)
+    assert got[2] is None and got[0].shape == want[0].shape and got[1].shape == want[1].shape
+    # integer structure is bit exact at every level
+    for a, b in zip(util.poolings(mine), util.poolings(ref)):
+        assert torch.equal(a.unpooling_indices.cpu(), b.unpooling_indices)
+    # per-layer taps: each compared with the oracle's tensor of the same name
+    worst = 0.0
+    for gname in ("v", "f"):
+        for k in ("l1", "p1", "l2", "p2", "l3", "l4", "r1", "r2", "r3", "r4"):
+            e = util.rel_err(mine.taps[gname][k], ref.taps[gname][k])
+            worst = max(worst, e)
+            assert e < 5e-5, (gname, k, e)       # errors accumulate over up to 8 stacked convs
+    assert util.rel_err(mine.taps["xf12"], ref.taps["xf12"]) < 5e-5
+    assert util.rel_err(got[0], want[0]) < 5e-5
+    assert util.rel_err(got[1], want[1]) < 2e-4   # unit normals after a 1024-wide head
+    # inputs are mutated as upstream: 64-channel x on graph_v, 12->64 on graph_f, self loops stripped
+    assert d_mine[0].x.shape[1] == 64 and d_mine[1].x.shape[1] == 64
+    assert torch.equal(d_mine[0].edge_index.cpu(), d_ref[0].edge_index)
+    assert torch.equal(d_mine[1].edge_index.cpu(), d_ref[1].edge_index)
+    # downstream metric agrees
+    e_ref = ref_network.error_n(want[1], d_ref[1].y)
+    from geobi_gnn_b200 import network
+    e_mine = network.error_n(got[1], d_mine[1].y)
+    assert abs(float(e_ref) - float(e_mine)) < 1e-2
+
+
+def test_dualgnn_matches_golden_vectors():
+    from geobi_gnn_b200 import network
+    from geobi_gnn_b200.data import Data
+    g = np.load(os.path.join(util.GOLDEN, "dualgnn_ico3.npz"))
+    t = lambda k: torch.from_numpy(g[k]).to(DEV)
+    dv = Data(x=t("x_v"), edge_index=t("ei_v"), edge_weight=t("w_v"))
+    df = Data(x=t("x_f"), edge_index=t("ei_f"), edge_weight=t("w_f"), fv_indices=t("faces"))
+    mine = network.DualGNN().to(DEV)
+    mine.load_state_dict(util.oracle_net(0).state_dict())
+    for name, pl in zip(("v1", "v2", "f1", "f2"), util.poolings(mine)):
+        perms = [torch.from_numpy(g[f"perm_{name}_{s}"]) for s in range(2)]
+        pl.perm_fn = lambda n, it=iter(perms): next(it)
+    with torch.no_grad():
+        vp, nrm, _ = mine([dv, df])
+    # free-running (same visiting order): matchings should coincide with the oracle's on this small mesh
+    for name, pl in zip(("v1", "v2", "f1", "f2"), util.poolings(mine)):
+        for s, tr in enumerate(pl.trace):
+            assert np.array_equal(tr[2].cpu().numpy(), g[f"label_{name}_{s}"]), (name, s)
+        assert np.array_equal(pl.unpooling_indices.cpu().numpy(), g[f"unpool_{name}"])
+    assert util.rel_err(vp, g["vert_p"]) < 5e-5
+    assert util.rel_err(nrm, g["norm_p"]) < 2e-4
+
+
+def test_dataset_builder_matches_oracle():
+    from geobi_gnn_b200 import dataset
+    mesh_n, mesh_o = util.noisy_icosphere(9, seed=2)
+    (dv, df), _, _ = util.oracle_inputs(9, seed=2)
+    mv, mf = dataset.build_dual_data(mesh_n, mesh_o, device=DEV)
+    assert torch.equal(mv.edge_index.cpu(), dv.edge_index) and torch.equal(mf.edge_index.cpu(), df.edge_index)
+    assert torch.equal(mf.fv_indices.cpu(), df.fv_indices)
+    for a, b in ((mv.x, dv.x), (mf.x, df.x), (mv.edge_weight, dv.edge_weight), (mf.edge_weight, df.edge_weight), (mv.y, dv.y), (mf.y, df.y)):
+        assert util.rel_err(a, b) < util.TOL_FP32
+    assert "pos" not in mv and "normal" not in mv and "depth_direction" not in mv and "edge_dual" not in mf
+
+
+def test_free_running_forward_invariants():
+    """Default path (random visiting order on the device): outputs are finite, normals unit, matching valid."""
+    from geobi_gnn_b200 import dataset, network
+    mesh_n, mesh_o = util.noisy_icosphere(16)
+    dv, df = dataset.build_dual_data(mesh_n, mesh_o, device=DEV)
+    torch.manual_seed(0)
+    net = network.DualGNN().to(DEV).eval()
+    with torch.no_grad():
+        vp, nrm, _ = net([dv, df])
+    assert torch.isfinite(vp).all() and torch.isfinite(nrm).all()
+    assert util.rel_err(nrm.norm(dim=1), torch.ones(nrm.shape[0])) < 1e-5
+    for pl in util.poolings(net):
+        for g, perm, label in pl.trace:
+            lab = label.cpu().long()
+            n = lab.numel()
+            assert torch.bincount(lab, minlength=n).max() <= 2 and torch.all(lab <= torch.arange(n))
+            single = torch.bincount(lab, minlength=n)[lab] == 1
+            ei = g.edge_index().cpu()
+            assert not (single[ei[0]] & single[ei[1]]).any()

@@ -1,0 +1,70 @@
+"""Shared helpers for the parity tests: synthetic inputs, seeded weights, error metrics."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from geobi_gnn_b200 import synth  # noqa: E402  (host-side input builder, numpy only)
+from oracle import pyg, ref_dataset, ref_network  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+TOL_FP32 = 1e-5   # BASELINE.json north_star: "within 1e-5 relative (fp32)"
+TOL_BF16 = 2e-3   # "... or 2e-3 (bf16 GEMM)"
+
+
+def rel_err(a, b):
+    """max-norm relative error  max|a-b| / max(|b|, tiny)."""
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if b.numel() == 0:
+        return 0.0
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def noisy_icosphere(n, sigma=0.2, seed=0):
+    p, f = synth.icosphere(n)
+    pn = synth.add_normal_noise(p, f, sigma, seed)
+    return synth.TriMesh(pn, f), synth.TriMesh(p, f)
+
+
+def oracle_inputs(n, seed=0, data_type="Synthetic"):
+    mesh_n, mesh_o = noisy_icosphere(n, seed=seed)
+    return ref_dataset.build_dual_data(mesh_n, mesh_o, data_type), mesh_n, mesh_o
+
+
+def oracle_net(seed=0, **kw):
+    torch.manual_seed(seed)
+    net = ref_network.DualGNN(**kw)
+    net.eval()
+    return net
+
+
+def seeded_perm_fn(seed):
+    g = torch.Generator().manual_seed(seed)
+    return lambda n: torch.randperm(n, generator=g)
+
+
+def set_perm_fn(net, seed):
+    fn = seeded_perm_fn(seed)
+    for m in net.modules():
+        if hasattr(m, "perm_fn"):
+            m.perm_fn = fn
+
+
+def poolings(net):
+    return [net.gnn_v.pooling1, net.gnn_v.pooling2, net.gnn_f.pooling1, net.gnn_f.pooling2]
+
+
+def data_to(d, device):
+    """Copy of an oracle Data as a product Data on `device`."""
+    from geobi_gnn_b200.data import Data
+    out = Data()
+    for k in d.keys():
+        v = getattr(d, k)
+        setattr(out, k, v.clone().to(device) if torch.is_tensor(v) else v)
+    return out
