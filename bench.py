@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — faces/sec of the GeoBi-GNN dual-domain forward on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+
+Workload (BASELINE.json configs[1]): a disjoint-union batch of 64 synthetic noisy icosphere patches
+(frequency 20 -> 8000 faces / 4002 vertices each, 512 000 faces per GPU), random-init DualGNN
+(torch.manual_seed(0)), one full forward per step from the reference's input layout
+(x, int64 edge_index, edge_weight, fv_indices).  Weak scaling: every rank gets its own 64 patches,
+no collective on the data path.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+PATCH_FREQ = 20          # icosphere frequency -> 8000 faces per patch ("Synthetic-set shape, ~8k faces")
+N_PATCHES = 64
+METRIC = "mesh faces/sec (GeoBi-GNN dual-domain forward)"
+UNIT = "faces/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------- workload
+def patch_meshes(count, first_seed):
+    from geobi_gnn_b200 import synth
+    p, f = synth.icosphere(PATCH_FREQ)
+    clean = synth.TriMesh(p, f)
+    return [(synth.TriMesh(synth.add_normal_noise(p, f, 0.2, first_seed + i), f), clean) for i in range(count)]
+
+
+def feast_bytes_alg(n, e, c_in, c_out):
+    """compulsory HBM traffic of one FeaSt layer (int32 CSR, fp32 features)."""
+    return 4 * (n * c_in + n * c_out) + 4 * e + 4 * (n + 1) + 4 * (9 * c_in * c_out + 9 * c_in + 9 + c_out)
+
+
+def run_ours(args, rank, world, local_rank):
+    from geobi_gnn_b200 import batching, config, dataset, network, ops
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    config.set_precision(args.precision)
+
+    meshes = patch_meshes(N_PATCHES, first_seed=rank * N_PATCHES)
+    patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in meshes]
+    data_v, data_f, _ = batching.collate_dual(patches)
+    del patches
+    faces_per_rank = data_f.x.size(0)
+    torch.manual_seed(0)
+    net = network.DualGNN().to(dev).eval()
+
+    in_keys_v, in_keys_f = ("x", "edge_index", "edge_weight"), ("x", "edge_index", "edge_weight", "fv_indices")
+    host_v = {k: getattr(data_v, k).cpu().pin_memory() for k in in_keys_v}
+    host_f = {k: getattr(data_f, k).cpu().pin_memory() for k in in_keys_f}
+    h2d_bytes = sum(t.numel() * t.element_size() for t in list(host_v.values()) + list(host_f.values()))
+
+    def step_resident():
+        with torch.no_grad():
+            return net([batching.fresh_view(data_v), batching.fresh_view(data_f)])
+
+    out_host = {}
+
+    def step_e2e():
+        from geobi_gnn_b200.data import Data
+        dv = Data(**{k: t.to(dev, non_blocking=True) for k, t in host_v.items()})
+        df = Data(**{k: t.to(dev, non_blocking=True) for k, t in host_f.items()})
+        with torch.no_grad():
+            vp, nrm, _ = net([dv, df])
+        for k, t in (("v", vp), ("n", nrm)):
+            if k not in out_host:
+                out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            out_host[k].copy_(t, non_blocking=True)
+        return vp, nrm
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall
+
+    for _ in range(args.warmup):
+        step_resident()
+    l0 = ops.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms, wall = timed(step_resident, args.steps)
+    launches = ops.launch_count() - l0
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
+    d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
+
+    total_faces = faces_per_rank * world
+    value = total_faces * args.steps / (ms / 1e3)
+    e2e_value = total_faces * args.steps / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel: the fused FeaSt conv on the largest layer (facet r_conv4: N=F, 64->32)
+    roof = None
+    if rank == 0:
+        g = ops.csr_from_coo(data_f.edge_index, faces_per_rank, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+        conv = net.gnn_f.r_conv4
+        x = torch.randn(faces_per_rank, 64, device=dev)
+        out = torch.empty(faces_per_rank, 32, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+        prec = config.precision_code()
+        call = lambda: ops.feast_fwd(x, g, conv.lin.weight, conv.u.weight, conv.c, conv.bias, 0.2, out=out, precision=prec)
+        for _ in range(3):
+            call()
+        times = []
+        for _ in range(10):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            call()
+            b.record()
+            torch.cuda.synchronize()
+            times.append(a.elapsed_time(b))
+        t_ms = float(np.mean(times))
+        alg = feast_bytes_alg(faces_per_rank, g.nnz + faces_per_rank, 64, 32)
+        peak, how = peaks()
+        achieved = alg / (t_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "kernel": "geobi_feast_fwd (facet r_conv4: N=%d, E=%d incl. self, 64->32)" % (faces_per_rank, g.nnz + faces_per_rank),
+                "alg_bytes_per_launch": alg, "ms_per_launch": round(t_ms, 4), "peak_source": how, "l2": "flushed between launches"}
+
+    cpu = cpu_baseline(sample_seconds=12.0) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.precision == "fp32" else "bf16 (projections) / f32 (aggregation)", "data": "synthetic",
+                "config": {"workload": "configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init",
+                           "faces_per_gpu": faces_per_rank, "precision": args.precision,
+                           "l2": "per-step working set (inputs 150 MB + >2 GB intermediates) exceeds the 126 MB L2",
+                           "timing": "CUDA events on the launch stream, max over ranks", "wall_s": round(wall, 4)},
+                "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------- CPU legs (oracle)
+def _oracle_patch_inputs(count, first_seed=0):
+    from oracle import ref_dataset
+    return [ref_dataset.build_dual_data(mn, mo) for mn, mo in patch_meshes(count, first_seed)]
+
+
+def cpu_baseline(sample_seconds):
+    """Oracle ('port' of the reference path; the reference itself cannot be imported here) timed on the host cores
+    on a bounded sample of the same workload: whole patches, one forward each, until ~sample_seconds elapsed."""
+    from oracle import ref_network
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    net = ref_network.DualGNN().eval()
+    pool = _oracle_patch_inputs(4)
+    with torch.no_grad():
+        net([pool[0][0].clone(), pool[0][1].clone()])        # warm-up
+        done, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < sample_seconds or done < 3:
+            dv, df = pool[done % len(pool)]
+            net([dv.clone(), df.clone()])
+            done += 1
+        dt = time.perf_counter() - t0
+    faces = done * 20 * PATCH_FREQ ** 2
+    return {"value": round(faces / dt, 1), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} patches of {20 * PATCH_FREQ ** 2} faces, one oracle forward each, {dt:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's own CPU path for this metric.  The reference cannot be imported or installed
+    here (torch_geometric / torch_scatter / torch_sparse / torch_cluster / openmesh absent), so this
+    times its restatement in oracle/ (kind 'port') with all host threads; each step = a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle import ref_network
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    net = ref_network.DualGNN().eval()
+    per_step = 2
+    pool = _oracle_patch_inputs(per_step)
+
+    def step():
+        with torch.no_grad():
+            for dv, df in pool:
+                net([dv.clone(), df.clone()])
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    faces = per_step * 20 * PATCH_FREQ ** 2
+    value = faces * args.steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init",
+                       "sample": f"{per_step} of the 64 patches per step (the reference runs one patch per forward, dataset.py:29-31)"},
+            "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{per_step} patches x {20 * PATCH_FREQ ** 2} faces per step, {args.steps} steps"},
+            "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("GEOBI_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: geobi_gnn_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch multi-GPU runs with torch.distributed.run --nproc-per-node N (see README)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

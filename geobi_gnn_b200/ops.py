@@ -36,8 +36,20 @@ def _need_cuda(*tensors):
             raise _lib.GeobiError("geobi_gnn_b200 ops need CUDA tensors (there is no CPU fallback)")
 
 
+_dummy = {}
+
+
 def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device pointer of `t`; empty tensors (data_ptr()==0) get a valid 256-byte dummy so that the ABI's
+    NULL-means-absent convention keeps working."""
+    if t is None:
+        return None
+    if t.numel() == 0:
+        d = _dummy.get(t.device)
+        if d is None:
+            d = _dummy[t.device] = torch.zeros(256, dtype=torch.uint8, device=t.device)
+        return C.c_void_p(d.data_ptr())
+    return C.c_void_p(t.data_ptr())
 
 
 def _stream():
