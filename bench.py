@@ -164,6 +164,13 @@ def run_ours(args, rank, world, local_rank):
 
     for _ in range(args.warmup):
         step_resident()
+    if args.profile_step:            # for `ncu --profile-from-start off`: exactly one step between cudaProfilerStart/Stop
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     l0 = ops.launch_count()
     with ClockSampler(local_rank) as clk:
         ms, wall = timed(step_resident, args.steps)
@@ -298,6 +305,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("GEOBI_PRECISION", "fp32"), choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
