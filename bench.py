@@ -218,7 +218,8 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.precision == "fp32" else "bf16 (projections) / f32 (aggregation)", "data": "synthetic",
+                "dtype": {"fp32": "f32", "bf16": "bf16 tensor-core projections (1 pass), f32 elsewhere",
+                          "bf16x3": "f32-grade: split-bf16 x3 tensor-core projections with f32 accumulate, f32 elsewhere"}[args.precision], "data": "synthetic",
                 "config": {"workload": "configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init",
                            "faces_per_gpu": faces_per_rank, "precision": args.precision,
                            "l2": "per-step working set (inputs 150 MB + >2 GB intermediates) exceeds the 126 MB L2",
@@ -303,7 +304,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("GEOBI_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("GEOBI_PRECISION", "bf16x3"), choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()

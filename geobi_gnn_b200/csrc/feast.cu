@@ -53,7 +53,7 @@ template <int CPL>
 __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
                                                               const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                               const double* __restrict__ P, const float* __restrict__ cvec,
-                                                              float* __restrict__ Z) {
+                                                              float* __restrict__ Z, int64_t ldz) {
   __shared__ __align__(16) float qs[8][32][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 8 + warp;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
     __syncwarp();
   }
   const float cntf = (float)total;
-  float* zrow = Z + i * (int64_t)(H * C);
+  float* zrow = Z + i * ldz;
 #pragma unroll
   for (int h = 0; h < H; ++h)
 #pragma unroll
@@ -286,9 +286,23 @@ struct NullCarverF {
   T* take(size_t n) { s.take<T>(n); return nullptr; }
 };
 
+// P = X U^T (fp64) then Z[i, h*C_in + c] (row stride ldz) = mean over N(i)+{i} of q_ijh x_j[c]
+int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
+                                const float* c, double* P, float* Z, int64_t ldz, cudaStream_t st) {
+  const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
+  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, P);
+  GEOBI_LAUNCH_OK("feast_project");
+  const unsigned ab = (unsigned)cdiv(N, 8);
+  if (c_in <= 32) feast_aggregate_kernel<1><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else if (c_in <= 64) feast_aggregate_kernel<2><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else feast_aggregate_kernel<4><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  GEOBI_LAUNCH_OK("feast_aggregate");
+  return GEOBI_OK;
+}
+
 int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
-                 const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo, void* ws, size_t ws_bytes,
-                 cudaStream_t st);  // feast_tc.cu
+                 const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo, int passes, void* ws,
+                 size_t ws_bytes, cudaStream_t st);  // feast_tc.cu
 size_t feast_fwd_tc_ws_bytes(int64_t N, int c_in, int c_out);
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
@@ -299,7 +313,7 @@ int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float
 using namespace geobi;
 
 extern "C" size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision) {
-  if (precision == GEOBI_PREC_BF16) return feast_fwd_tc_ws_bytes(n_nodes, c_in, c_out);
+  if (precision != GEOBI_PREC_FP32) return feast_fwd_tc_ws_bytes(n_nodes, c_in, c_out);
   NullCarverF c;
   carve_feast(c, n_nodes, c_in, c_out, nullptr);
   return c.s.total();
@@ -313,10 +327,11 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   GEOBI_REQUIRE(c_in >= 1 && c_in <= 128, "feast_fwd: C_in must be in 1..128 (got %d)", c_in);
   GEOBI_REQUIRE(c_out == 32 || c_out == 64 || c_out == 128, "feast_fwd: C_out must be 32, 64 or 128 (got %d)", c_out);
   GEOBI_REQUIRE(ldx >= c_in && ldo >= c_out, "feast_fwd: leading dimension smaller than channel count");
-  GEOBI_REQUIRE(precision == GEOBI_PREC_FP32 || precision == GEOBI_PREC_BF16, "feast_fwd: unknown precision %d", precision);
+  GEOBI_REQUIRE(precision >= GEOBI_PREC_FP32 && precision <= GEOBI_PREC_BF16X3, "feast_fwd: unknown precision %d", precision);
   if (N == 0) return GEOBI_OK;
-  if (precision == GEOBI_PREC_BF16)
-    return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, W, U, c, bias, c_out, act_slope, out, ldo, ws, ws_bytes, st);
+  if (precision != GEOBI_PREC_FP32)
+    return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, W, U, c, bias, c_out, act_slope, out, ldo, precision == GEOBI_PREC_BF16X3 ? 3 : 1, ws,
+                        ws_bytes, st);
   if (!ws || ws_bytes < geobi_feast_fwd_ws_bytes(N, c_in, c_out, precision)) {
     set_error("feast_fwd: workspace too small");
     return GEOBI_ERR_WORKSPACE;
@@ -324,15 +339,9 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   Carver cv(ws, ws_bytes);
   FeastWs Wk;
   carve_feast(cv, N, c_in, c_out, &Wk);
-  const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
-  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, Wk.P);
-  GEOBI_LAUNCH_OK("feast_project");
   feast_transpose_w_kernel<<<64, 256, 0, st>>>(W, c_in, c_out, Wk.Wt);
-  const unsigned ab = (unsigned)cdiv(N, 8);
-  if (c_in <= 32) feast_aggregate_kernel<1><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, Wk.P, c, Wk.Z);
-  else if (c_in <= 64) feast_aggregate_kernel<2><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, Wk.P, c, Wk.Z);
-  else feast_aggregate_kernel<4><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, Wk.P, c, Wk.Z);
-  GEOBI_LAUNCH_OK("feast_aggregate");
+  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, (int64_t)H * c_in, st);
+  if (rc) return rc;
   const int K = H * c_in;
   if (c_out == 32) {
     dim3 g((unsigned)cdiv(N, 64), 1);
@@ -356,9 +365,9 @@ extern "C" int geobi_fc_head_fwd(const float* f, int64_t ldf, int64_t n, int c_i
   GEOBI_REQUIRE(epilogue >= 0 && epilogue <= 3, "fc_head_fwd: unknown epilogue %d", epilogue);
   GEOBI_REQUIRE(!(epilogue == 1 || epilogue == 2) || res, "fc_head_fwd: epilogue %d needs res", epilogue);
   GEOBI_REQUIRE(epilogue != 2 || res2, "fc_head_fwd: epilogue 2 needs res2");
-  GEOBI_REQUIRE(precision == GEOBI_PREC_FP32 || precision == GEOBI_PREC_BF16, "fc_head_fwd: unknown precision %d", precision);
+  GEOBI_REQUIRE(precision >= GEOBI_PREC_FP32 && precision <= GEOBI_PREC_BF16X3, "fc_head_fwd: unknown precision %d", precision);
   if (n == 0) return GEOBI_OK;
-  if (precision == GEOBI_PREC_BF16)
+  if (precision != GEOBI_PREC_FP32 && c_in == 32 && c_out <= 3 && hidden % 256 == 0)
     return fc_head_fwd_tc(f, ldf, n, c_in, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2, ldres2, out, ldo, st);
   const unsigned blocks = (unsigned)cdiv(n, 64);
   if (c_in == 32)

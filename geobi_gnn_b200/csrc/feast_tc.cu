@@ -1,17 +1,494 @@
-// bf16 tensor-core (tcgen05 / TMEM) projection path for FeaSt conv and the FC head.
-// Placeholder until the tcgen05 kernels land: reports a clear error instead of falling back.
+// bf16 tensor-core (tcgen05 / TMEM) path for the per-node projections of the FeaSt conv and the FC heads.
+//
+// Building block: D[128 x N] (fp32, TMEM) += A[128 x 64] . B[N x 64]^T with bf16 operands staged in shared memory
+// by the CTA's own threads in the canonical K-major SWIZZLE_128B layout (rows of 128 B, 8-row groups of 1 KB,
+// 16-byte chunks XOR-ed with row%8), issued by one thread as four K=16 tcgen05.mma, completion tracked with
+// tcgen05.commit -> mbarrier, accumulator read back with tcgen05.ld (32 lanes x 32 columns per warp).
+// Operands come from fp32 global memory and are rounded to bf16 on the way into shared memory, so no bf16 copy of
+// the activations ever exists in HBM.  No TMA: the A operand is produced by threads (converted / aggregated).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace geobi {
-size_t feast_fwd_tc_ws_bytes(int64_t, int, int) { return 256; }
-int feast_fwd_tc(const float*, int64_t, int64_t, int, const int32_t*, const int32_t*, const float*, const float*, const float*, const float*, int,
-                 float, float*, int64_t, void*, size_t, cudaStream_t) {
-  set_error("feast_fwd: GEOBI_PREC_BF16 path is not built in this version of libgeobi");
+namespace tc {
+
+constexpr int H = GEOBI_HEADS;
+constexpr int BM = 128;   // rows per CTA tile = TMEM lanes
+constexpr int BK = 64;    // bf16 elements per 128-byte swizzle row
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// one full warp allocates `cols` (power of two >= 32) TMEM columns; the base address lands in *slot (shared)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4 |
+// version=1 (bit 46) | layout SWIZZLE_128B=2 (bits 61..63).  `base` must be 1024-byte aligned; +32 B per K=16 step.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of the 16-byte chunk `chunk` (0..7) of row r inside a K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<uint32_t*>(&lo);
+  u.y = *reinterpret_cast<uint32_t*>(&hi);
+  return u;
+}
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): |x - hi - lo| <= 2^-18 |x|.  Three MMA passes
+// (hi.hi + hi.lo + lo.hi) then reproduce an fp32 product to ~1e-6 relative ("bf16x3").
+__device__ __forceinline__ void split_bf16x4(float4 v, uint2& hi, uint2& lo) {
+  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+  hi.x = *reinterpret_cast<const uint32_t*>(&h0);
+  hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l0);
+  lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+
+// ------------------------------------------------------------------------------ weight preparation
+// Bq[n, k] (bf16, row stride kpad, zero padded).  mode 0: plain W[n, k];  mode 1: FeaSt lin.weight -> W_flat,
+// Bq[o, h*C_in + c] = W[(h*C_out + o)*C_in + c].
+// Bq holds two planes: hi at [0, N*kpad), lo (residual) at [N*kpad, 2*N*kpad).
+__global__ void prep_weight_kernel(const float* __restrict__ W, int N, int K, int kpad, int mode, int c_in, __nv_bfloat16* __restrict__ Bq) {
+  const int total = N * kpad;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int n = t / kpad, k = t - n * kpad;
+    float v = 0.f;
+    if (k < K) {
+      if (mode == 0) v = W[(int64_t)n * K + k];
+      else {
+        const int h = k / c_in, c = k - h * c_in;
+        v = W[(int64_t)(h * N + n) * c_in + c];
+      }
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    Bq[t] = hi;
+    Bq[total + t] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+// ------------------------------------------------------------------------------ out = act(A . Bq^T + bias)
+// A fp32 [M, lda] (lda % 4 == 0, 16-byte aligned rows, columns >= K read as given up to kpad: the caller zero-pads),
+// Bq bf16 [NT, kpad].  One CTA = 128 rows x NT columns; 2-stage smem ring; 128 threads.
+template <int NT, int PASSES>
+__global__ void __launch_bounds__(128) tc_gemm_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int kpad,
+                                                      const __nv_bfloat16* __restrict__ Bq, const float* __restrict__ bias, float slope,
+                                                      float* __restrict__ out, int64_t ldo) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int SPLIT = PASSES == 3 ? 2 : 1;
+  constexpr int A_BYTES = BM * 128, B_BYTES = NT * 128;
+  constexpr int STAGE = SPLIT * (A_BYTES + B_BYTES);   // [A_hi | A_lo | B_hi | B_lo]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int64_t lo_plane = (int64_t)NT * kpad;           // elements between the hi and lo planes of Bq
+
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, NT < 32 ? 32 : NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  constexpr uint32_t idesc = make_idesc(BM, NT);
+  const int KB = kpad / BK;
+
+  for (int kb = 0; kb < KB; ++kb) {
+    const int s = kb & 1;
+    uint8_t* a_hi = sm + s * STAGE;
+    uint8_t* a_lo = a_hi + A_BYTES;
+    uint8_t* b_hi = a_hi + SPLIT * A_BYTES;
+    uint8_t* b_lo = b_hi + B_BYTES;
+    if (kb >= 2) {
+      mbar_wait(&mbar[s], (uint32_t)(((kb >> 1) - 1) & 1));   // the MMAs that read stage s have retired
+      tc_fence_after();
+    }
+    // A block: 128 rows x 16 float4 -> bf16x4 (hi [+ lo]), two rows per warp-iteration (coalesced 256 B rows)
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int idx = it * 128 + tid;
+      const int r = idx >> 4, c4 = idx & 15;
+      const int64_t m = m0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M) v = *reinterpret_cast<const float4*>(A + m * lda + (int64_t)kb * BK + c4 * 4);
+      const uint32_t off = sw128_off(r, c4 >> 1) + (c4 & 1) * 8;
+      if (PASSES == 3) {
+        uint2 hi, lo;
+        split_bf16x4(v, hi, lo);
+        *reinterpret_cast<uint2*>(a_hi + off) = hi;
+        *reinterpret_cast<uint2*>(a_lo + off) = lo;
+      } else {
+        *reinterpret_cast<uint2*>(a_hi + off) = pack_bf16x4(v);
+      }
+    }
+    // B block: NT rows x 8 chunks of 16 B (already bf16), hi [+ lo] plane
+    for (int idx = tid; idx < NT * 8; idx += 128) {
+      const int r = idx >> 3, ch = idx & 7;
+      const __nv_bfloat16* src = Bq + (int64_t)r * kpad + (int64_t)kb * BK + ch * 8;
+      *reinterpret_cast<uint4*>(b_hi + sw128_off(r, ch)) = *reinterpret_cast<const uint4*>(src);
+      if (PASSES == 3) *reinterpret_cast<uint4*>(b_lo + sw128_off(r, ch)) = *reinterpret_cast<const uint4*>(src + lo_plane);
+    }
+    fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ah = make_desc(smem_u32(a_hi)), bh = make_desc(smem_u32(b_hi));
+#pragma unroll
+      for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bh + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+      if (PASSES == 3) {
+        const uint64_t al = make_desc(smem_u32(a_lo)), bl = make_desc(smem_u32(b_lo));
+#pragma unroll
+        for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bl + 2 * k16, idesc, 1u);
+#pragma unroll
+        for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, al + 2 * k16, bh + 2 * k16, idesc, 1u);
+      }
+      mma_commit(&mbar[s]);
+    }
+  }
+  const int last = KB - 1;
+  mbar_wait(&mbar[last & 1], (uint32_t)((last >> 1) & 1));
+  tc_fence_after();
+
+  // epilogue: thread = output row (TMEM lane); 32 columns at a time
+  const int64_t m = m0 + tid;
+  const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 32) {
+    float v[32];
+    tmem_ld32(lane_addr + (uint32_t)c0, v);
+    if (m < M) {
+      float* o = out + m * ldo + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 r;
+        r.x = v[j] + bias[c0 + j];
+        r.y = v[j + 1] + bias[c0 + j + 1];
+        r.z = v[j + 2] + bias[c0 + j + 2];
+        r.w = v[j + 3] + bias[c0 + j + 3];
+        r.x = r.x > 0.f ? r.x : r.x * slope;
+        r.y = r.y > 0.f ? r.y : r.y * slope;
+        r.z = r.z > 0.f ? r.z : r.z * slope;
+        r.w = r.w > 0.f ? r.w : r.w * slope;
+        *reinterpret_cast<float4*>(o + j) = r;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, NT < 32 ? 32 : NT);
+}
+
+template <int NT, int PASSES>
+static int launch_gemm(const float* A, int64_t lda, int64_t M, int kpad, const __nv_bfloat16* Bq, const float* bias, float slope, float* out,
+                       int64_t ldo, cudaStream_t st) {
+  const size_t smem = 2 * (PASSES == 3 ? 2 : 1) * (BM * 128 + NT * 128) + 1024;
+  GEOBI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<NT, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_gemm_kernel<NT, PASSES><<<(unsigned)cdiv(M, BM), 128, smem, st>>>(A, lda, M, kpad, Bq, bias, slope, out, ldo);
+  GEOBI_LAUNCH_OK("tc_gemm");
+  return GEOBI_OK;
+}
+
+int gemm_dispatch(const float* A, int64_t lda, int64_t M, int kpad, const __nv_bfloat16* Bq, int N, const float* bias, float slope, float* out,
+                  int64_t ldo, int passes, cudaStream_t st) {
+#define GEOBI_TC_CASE(NT)                                                                              \
+  case NT:                                                                                             \
+    return passes == 3 ? launch_gemm<NT, 3>(A, lda, M, kpad, Bq, bias, slope, out, ldo, st)            \
+                       : launch_gemm<NT, 1>(A, lda, M, kpad, Bq, bias, slope, out, ldo, st);
+  switch (N) {
+    GEOBI_TC_CASE(32)
+    GEOBI_TC_CASE(64)
+    GEOBI_TC_CASE(128)
+    GEOBI_TC_CASE(256)
+  }
+#undef GEOBI_TC_CASE
+  set_error("tc gemm: N must be 32, 64, 128 or 256 (got %d)", N);
   return GEOBI_ERR_INVALID;
 }
-int fc_head_fwd_tc(const float*, int64_t, int64_t, int, const float*, const float*, int, const float*, const float*, int, int, const float*,
-                   int64_t, const float*, int64_t, float*, int64_t, cudaStream_t) {
-  set_error("fc_head_fwd: GEOBI_PREC_BF16 path is not built in this version of libgeobi");
-  return GEOBI_ERR_INVALID;
+
+// ------------------------------------------------------------------------------ fused FC head on tensor cores
+// y = W2 . lrelu(W1 . f + b1) + b2 with c_in = 32: GEMM1 [128 nodes x 32] x [32 x 256-chunk] runs on tcgen05 (split bf16, 3 passes,
+// hi|lo packed side by side in one 128-byte swizzle row), the 256 hidden activations of a chunk are consumed straight out of TMEM:
+// +b1, leaky_relu, dotted with W2 (<= 4 outputs) on CUDA cores.  The [N,1024] hidden never reaches shared memory or HBM.
+// 256 threads: warps w and w+4 share a TMEM lane quadrant and split each chunk's columns.
+constexpr int FC_CHUNK = 256;
+__global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict__ f, int64_t ldf, int64_t N, const float* __restrict__ W1,
+                                                         const float* __restrict__ b1, int hidden, const float* __restrict__ W2,
+                                                         const float* __restrict__ b2, int CO, int epilogue, const float* __restrict__ res,
+                                                         int64_t ldres, const float* __restrict__ res2, int64_t ldres2,
+                                                         float* __restrict__ out, int64_t ldo) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float part[128][4];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* a_t = sm;                                   // [128 rows x 128 B]: k 0..31 = hi, 32..63 = lo
+  uint8_t* b_t = sm + BM * 128;                        // [256 rows x 128 B]: same packing for the W1 chunk
+  float4* tab = reinterpret_cast<float4*>(sm + BM * 128 + FC_CHUNK * 128);   // [hidden] {b1, w2_0, w2_1, w2_2}
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, FC_CHUNK);
+  for (int j = tid; j < hidden; j += 256)
+    tab[j] = make_float4(b1[j], W2[j], CO > 1 ? W2[hidden + j] : 0.f, CO > 2 ? W2[2 * hidden + j] : 0.f);
+  // A tile: 128 rows x 8 float4
+  for (int idx = tid; idx < BM * 8; idx += 256) {
+    const int r = idx >> 3, c4 = idx & 7;
+    const int64_t m = m0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < N) v = *reinterpret_cast<const float4*>(f + m * ldf + c4 * 4);
+    uint2 hi, lo;
+    split_bf16x4(v, hi, lo);
+    *reinterpret_cast<uint2*>(a_t + sw128_off(r, c4 >> 1) + (c4 & 1) * 8) = hi;
+    *reinterpret_cast<uint2*>(a_t + sw128_off(r, 4 + (c4 >> 1)) + (c4 & 1) * 8) = lo;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  constexpr uint32_t idesc = make_idesc(BM, FC_CHUNK);
+  const int row = (warp & 3) * 32 + lane;
+  const int chalf = warp >> 2;                         // which 128 columns of the chunk this warp consumes
+  const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * 128);
+  float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+
+  const int n_chunks = hidden / FC_CHUNK;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    // W1 chunk: 256 rows x 8 float4 (the previous chunk's MMAs have retired: we waited on mbar before its epilogue)
+    for (int idx = tid; idx < FC_CHUNK * 8; idx += 256) {
+      const int r = idx >> 3, c4 = idx & 7;
+      const float4 v = *reinterpret_cast<const float4*>(W1 + (int64_t)(ch * FC_CHUNK + r) * 32 + c4 * 4);
+      uint2 hi, lo;
+      split_bf16x4(v, hi, lo);
+      *reinterpret_cast<uint2*>(b_t + sw128_off(r, c4 >> 1) + (c4 & 1) * 8) = hi;
+      *reinterpret_cast<uint2*>(b_t + sw128_off(r, 4 + (c4 >> 1)) + (c4 & 1) * 8) = lo;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();                                   // also: every warp has finished reading TMEM of the previous chunk
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t ad = make_desc(smem_u32(a_t)), bd = make_desc(smem_u32(b_t));
+      mma_f16(tmem_d, ad + 0, bd + 0, idesc, 0u);      // hi . hi   (k 0..15)
+      mma_f16(tmem_d, ad + 2, bd + 2, idesc, 1u);      // hi . hi   (k 16..31)
+      mma_f16(tmem_d, ad + 0, bd + 4, idesc, 1u);      // hi . lo
+      mma_f16(tmem_d, ad + 2, bd + 6, idesc, 1u);
+      mma_f16(tmem_d, ad + 4, bd + 0, idesc, 1u);      // lo . hi
+      mma_f16(tmem_d, ad + 6, bd + 2, idesc, 1u);
+      mma_commit(&mbar);
+    }
+    mbar_wait(&mbar, (uint32_t)(ch & 1));
+    tc_fence_after();
+    const float4* t4 = tab + ch * FC_CHUNK + chalf * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      float v[32];
+      tmem_ld32(lane_addr + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float4 t = t4[c0 + j];
+        float h = v[j] + t.x;
+        h = h > 0.f ? h : 0.2f * h;
+        y0 = fmaf(t.y, h, y0);
+        y1 = fmaf(t.z, h, y1);
+        y2 = fmaf(t.w, h, y2);
+      }
+    }
+    tc_fence_before();
+  }
+  if (chalf == 1) {
+    part[row][0] = y0;
+    part[row][1] = y1;
+    part[row][2] = y2;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, FC_CHUNK);
+  const int64_t n = m0 + row;
+  if (chalf != 0 || n >= N) return;
+  float y[3] = {y0 + part[row][0] + b2[0], CO > 1 ? y1 + part[row][1] + b2[1] : 0.f, CO > 2 ? y2 + part[row][2] + b2[2] : 0.f};
+  int co = CO;
+  if (epilogue == 2) {
+    if (CO == 1) {
+      const float s0 = y[0];
+      for (int c = 0; c < 3; ++c) y[c] = s0 * res2[n * ldres2 + c];
+      co = 3;
+    } else {
+      for (int c = 0; c < co; ++c) y[c] *= res2[n * ldres2 + c];
+    }
+  }
+  if (epilogue == 1 || epilogue == 2)
+    for (int c = 0; c < co; ++c) y[c] += res[n * ldres + c];
+  if (epilogue == 3) {
+    float s2 = 0.f;
+    for (int c = 0; c < co; ++c) s2 += y[c] * y[c];
+    const float d = fmaxf(sqrtf(s2), 1e-12f);
+    for (int c = 0; c < co; ++c) y[c] /= d;
+  }
+  for (int c = 0; c < co; ++c) out[n * ldo + c] = y[c];
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------ FeaSt forward, bf16 projection
+// defined in feast.cu
+int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
+                                const float* c, double* P, float* Z, int64_t ldz, cudaStream_t st);
+
+struct TcWs {
+  double* P;
+  float* Z;
+  __nv_bfloat16* Bq;
+};
+template <class C>
+static void carve_tc(C& c, int64_t N, int c_in, int c_out, TcWs* out) {
+  const int kpad = (int)(cdiv(tc::H * c_in, tc::BK) * tc::BK);
+  double* P = c.template take<double>((size_t)N * tc::H);
+  float* Z = c.template take<float>((size_t)N * kpad);
+  __nv_bfloat16* Bq = c.template take<__nv_bfloat16>((size_t)2 * c_out * kpad);
+  if (out) *out = TcWs{P, Z, Bq};
+}
+struct NullCarverT {
+  Sizer s;
+  template <typename T>
+  T* take(size_t n) { s.take<T>(n); return nullptr; }
+};
+
+size_t feast_fwd_tc_ws_bytes(int64_t N, int c_in, int c_out) {
+  NullCarverT c;
+  carve_tc(c, N, c_in, c_out, nullptr);
+  return c.s.total();
+}
+
+int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
+                 const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo, int passes, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < feast_fwd_tc_ws_bytes(N, c_in, c_out)) {
+    set_error("feast_fwd (bf16): workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  GEOBI_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "feast_fwd (bf16): out rows must be 16-byte aligned");
+  Carver cv(ws, ws_bytes);
+  TcWs Wk;
+  carve_tc(cv, N, c_in, c_out, &Wk);
+  const int K = tc::H * c_in;
+  const int kpad = (int)(cdiv(K, tc::BK) * tc::BK);
+  if (kpad != K) GEOBI_CUDA_OK(cudaMemsetAsync(Wk.Z, 0, sizeof(float) * (size_t)N * kpad, st));
+  tc::prep_weight_kernel<<<64, 256, 0, st>>>(W, c_out, K, kpad, 1, c_in, Wk.Bq);
+  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, kpad, st);
+  if (rc) return rc;
+  return tc::gemm_dispatch(Wk.Z, kpad, N, kpad, Wk.Bq, c_out, bias, act_slope, out, ldo, passes, st);
+}
+
+int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
+                   const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
+                   int64_t ldo, cudaStream_t st) {
+  GEOBI_REQUIRE(c_in == 32, "fc_head_fwd (tensor core): c_in must be 32 (got %d)", c_in);
+  GEOBI_REQUIRE(hidden % tc::FC_CHUNK == 0 && hidden <= 4096, "fc_head_fwd (tensor core): hidden must be a multiple of 256, <= 4096");
+  GEOBI_REQUIRE(c_out <= 3, "fc_head_fwd (tensor core): c_out must be <= 3 (got %d)", c_out);
+  GEOBI_REQUIRE(ldf % 4 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "fc_head_fwd (tensor core): feature rows must be 16-byte aligned");
+  const size_t smem = (size_t)tc::BM * 128 + tc::FC_CHUNK * 128 + (size_t)hidden * 16 + 1024;
+  GEOBI_CUDA_OK(cudaFuncSetAttribute(tc::fc_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc::fc_head_tc_kernel<<<(unsigned)cdiv(n, tc::BM), 256, smem, st>>>(f, ldf, n, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2,
+                                                                     ldres2, out, ldo);
+  GEOBI_LAUNCH_OK("fc_head_tc");
+  return GEOBI_OK;
 }
 }  // namespace geobi
+
+// ------------------------------------------------------------------------------ public: tensor-core linear layer
+using namespace geobi;
+
+extern "C" size_t geobi_linear_tc_ws_bytes(int k, int n) { return align256((size_t)2 * n * (size_t)(cdiv(k, tc::BK) * tc::BK) * 2) + 256; }
+
+extern "C" int geobi_linear_tc(const float* A, int64_t lda, int64_t M, int K, const float* W, int N, const float* bias, float act_slope,
+                               float* out, int64_t ldo, int precision, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(A && W && bias && out && M >= 0 && K > 0, "linear_tc: bad arguments");
+  GEOBI_REQUIRE(precision == GEOBI_PREC_BF16 || precision == GEOBI_PREC_BF16X3, "linear_tc: precision must be BF16 or BF16X3");
+  GEOBI_REQUIRE(K % tc::BK == 0, "linear_tc: K must be a multiple of 64 (got %d); pad the activations", K);
+  GEOBI_REQUIRE(lda % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "linear_tc: rows must be 16-byte aligned");
+  if (!ws || ws_bytes < geobi_linear_tc_ws_bytes(K, N)) { set_error("linear_tc: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  if (M == 0) return GEOBI_OK;
+  __nv_bfloat16* Bq = static_cast<__nv_bfloat16*>(ws);
+  tc::prep_weight_kernel<<<64, 256, 0, st>>>(W, N, K, K, 0, 0, Bq);
+  return tc::gemm_dispatch(A, lda, M, K, Bq, N, bias, act_slope, out, ldo, precision == GEOBI_PREC_BF16X3 ? 3 : 1, st);
+}

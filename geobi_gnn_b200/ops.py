@@ -14,7 +14,7 @@ import torch
 
 from . import _lib
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
 COO_BY_COL, COO_DROP_SELF, COO_SORT_NBR, COO_DEDUP, COO_W_MEAN, COO_SYMMETRIZE = 1, 2, 4, 8, 16, 32
 OP_MEAN, OP_MAX, OP_SUM = 0, 1, 2
 
@@ -299,6 +299,23 @@ def feast_fwd(x: torch.Tensor, g: CSRGraph, W: torch.Tensor, U: torch.Tensor, c:
                                    _ptr(c.contiguous()), _ptr(bias.contiguous()), c_out, float(act_slope), _ptr(o), ldo, precision,
                                    _ptr(ws), ws.numel(), _stream()), "feast_fwd")
     _count(4)
+    return out
+
+
+def linear_tc(a: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, act_slope: float = 1.0, out: Optional[torch.Tensor] = None,
+              precision: int = PREC_BF16X3):
+    """act(a @ W.T + bias) on tcgen05 tensor cores (bf16 operands, fp32 accumulate)."""
+    _need_cuda(a, W, bias)
+    lib = _lib.load()
+    a, lda, k = _rows(a)
+    n = W.size(0)
+    if out is None:
+        out = torch.empty((a.size(0), n), dtype=torch.float32, device=a.device)
+    o, ldo, _ = _rows(out)
+    ws = _ws(lib.geobi_linear_tc_ws_bytes(k, n), a.device)
+    _lib.check(lib.geobi_linear_tc(_ptr(a), lda, a.size(0), k, _ptr(W.contiguous()), n, _ptr(bias.contiguous()), float(act_slope),
+                                   _ptr(o), ldo, precision, _ptr(ws), ws.numel(), _stream()), "linear_tc")
+    _count(2)
     return out
 
 

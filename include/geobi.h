@@ -162,15 +162,26 @@ GEOBI_API int geobi_calc_weight(const float* pos, const float* nrm, const int64_
  * U = u.weight [9, C_in].  act_slope: 1.0 = none, 0.2 = the leaky_relu after most convs.
  * Evaluation is aggregate-first: Z[i,h,:] = sum_j q_ijh x_j, out = W_flat . Z — no per-edge
  * tensor is ever written to HBM.  Supported C_in: 1..128, C_out: multiple of 4 up to 128.
- * precision: GEOBI_PREC_FP32 (all fp32 CUDA cores; parity 1e-5) or GEOBI_PREC_BF16
- * (projection on tcgen05 tensor cores with bf16 operands / fp32 accumulate; parity 2e-3). */
+ * precision: GEOBI_PREC_FP32 (all fp32 CUDA cores; parity 1e-5), GEOBI_PREC_BF16 (projection on tcgen05
+ * tensor cores, bf16 operands / fp32 accumulate, one pass) or GEOBI_PREC_BF16X3 (same, operands split
+ * hi + lo, three passes: fp32-grade results from the tensor cores). */
 #define GEOBI_PREC_FP32 0
 #define GEOBI_PREC_BF16 1
+#define GEOBI_PREC_BF16X3 2   /* tcgen05 with split operands x = hi + lo (both bf16), 3 passes: ~1e-6, fp32-grade */
 GEOBI_API size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision);
 GEOBI_API int geobi_feast_fwd(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
                     const int32_t* nbr, const float* W, const float* U, const float* c, const float* bias,
                     int c_out, float act_slope, float* out, int64_t ldo, int precision, void* ws,
                     size_t ws_bytes, void* stream);
+
+/* Per-node linear layer on the tcgen05 tensor cores: out = act(A . W^T + bias), A fp32 [M,K] rounded to bf16 while it
+ * is staged in shared memory, W fp32 [N,K] (nn.Linear layout), fp32 accumulation in TMEM.  K % 64 == 0,
+ * N in {32,64,128,256}, rows 16-byte aligned.  Replaces F.linear / cuBLAS sgemm for the projections
+ * (FeaSt `lin`, network.py:258-268; DualFusionLayer linears, net_util.py:252-256).  ws: bf16 copy of W. */
+GEOBI_API size_t geobi_linear_tc_ws_bytes(int k, int n);
+GEOBI_API int geobi_linear_tc(const float* A, int64_t lda, int64_t M, int K, const float* W, int N, const float* bias,
+                              float act_slope, float* out, int64_t ldo, int precision, void* ws, size_t ws_bytes,
+                              void* stream);
 
 /* The two linear heads of DualGNN (network.py:324-325,340-341) fused so the [N,1024] hidden never
  * reaches HBM:  y = W2 . leaky_relu(W1 . f + b1, 0.2) + b2, then epilogue
