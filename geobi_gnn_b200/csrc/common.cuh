@@ -39,6 +39,7 @@ struct Sizer {
   do {                                                                                 \
     cudaError_t _e = (expr);                                                           \
     if (_e != cudaSuccess) {                                                           \
+      (void)cudaGetLastError(); /* clear the non-sticky error so that later launches are not blamed */ \
       ::geobi::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
       return GEOBI_ERR_CUDA;                                                           \
     }                                                                                  \

@@ -7,6 +7,8 @@
 //
 // No per-edge tensor is written to HBM (the reference materialises [E, 9*C_out]).
 // The bf16 tensor-core projection lives in feast_tc.cu.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace geobi {
@@ -46,20 +48,43 @@ __global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float
 }
 
 // ------------------------------------------------------------------------------ Z = softmax-weighted neighbour sums
-// One warp per target node; lane l owns channels l, l+32, ... (coalesced row reads).
-// Per 32-edge chunk: lanes compute one edge's 9 soft assignments each (-> smem), then the warp
-// walks the chunk accumulating 9 x CPL FMAs per edge per lane.
+// One warp per target node; lane l owns the CPL adjacent channels [l*CPL, (l+1)*CPL) (one coalesced vector load per
+// gathered row).  Per 32-edge chunk: lanes compute one edge's 9 soft assignments each (-> smem), then the warp walks the
+// chunk accumulating 9 x CPL FMAs per edge per lane.
+// OUT = 0: Z fp32 [N, ldz];  1: bf16 plane (hi);  2: two bf16 planes hi | lo (lo = bf16(z - hi)), plane stride = N*ldz.
 template <int CPL>
+struct VecLoad;
+template <>
+struct VecLoad<1> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) { v[0] = *p; }
+};
+template <>
+struct VecLoad<2> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+};
+template <>
+struct VecLoad<4> {
+  static __device__ __forceinline__ void ld(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+
+template <int CPL, int OUT>
 __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
                                                               const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                               const double* __restrict__ P, const float* __restrict__ cvec,
-                                                              float* __restrict__ Z, int64_t ldz) {
+                                                              void* __restrict__ Zout, int64_t ldz, int vec_ok) {
   __shared__ __align__(16) float qs[8][32][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 8 + warp;
   if (i >= N) return;
   const int b = rowptr[i];
   const int total = rowptr[i + 1] - b + 1;  // neighbours + implicit self loop (slot 0)
+  const int c0 = lane * CPL;
   double Pi[H];
   float ch[H];
 #pragma unroll
@@ -96,34 +121,89 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
     }
     __syncwarp();
     const int cnt = min(32, total - s0);
-    for (int t = 0; t < cnt; ++t) {
-      const int64_t jt = __shfl_sync(0xffffffffu, j, t);
-      float xj[CPL];
+    // two edges per iteration: both gathers are in flight before either is consumed
+    for (int t = 0; t < cnt; t += 2) {
+      const int64_t ja = __shfl_sync(0xffffffffu, j, t);
+      const int64_t jb = __shfl_sync(0xffffffffu, j, (t + 1) & 31);
+      const bool has_b = t + 1 < cnt;
+      float xa[CPL], xb[CPL];
 #pragma unroll
-      for (int k = 0; k < CPL; ++k) {
-        const int c = lane + 32 * k;
-        xj[k] = c < C ? x[jt * ldx + c] : 0.f;
+      for (int k = 0; k < CPL; ++k) xa[k] = xb[k] = 0.f;
+      if (c0 < C) {
+        if (vec_ok) {
+          VecLoad<CPL>::ld(x + ja * ldx + c0, xa);
+          if (has_b) VecLoad<CPL>::ld(x + jb * ldx + c0, xb);
+        } else {
+#pragma unroll
+          for (int k = 0; k < CPL; ++k)
+            if (c0 + k < C) {
+              xa[k] = x[ja * ldx + c0 + k];
+              if (has_b) xb[k] = x[jb * ldx + c0 + k];
+            }
+        }
       }
-      const float4 qa = *reinterpret_cast<const float4*>(&qs[warp][t][0]);
-      const float4 qb = *reinterpret_cast<const float4*>(&qs[warp][t][4]);
-      const float q8 = qs[warp][t][8];
-      const float q[H] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w, q8};
+      {
+        const float4 qa = *reinterpret_cast<const float4*>(&qs[warp][t][0]);
+        const float4 qb = *reinterpret_cast<const float4*>(&qs[warp][t][4]);
+        const float q8 = qs[warp][t][8];
+        const float q[H] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w, q8};
 #pragma unroll
-      for (int h = 0; h < H; ++h)
+        for (int h = 0; h < H; ++h)
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) acc[h][k] = fmaf(q[h], xj[k], acc[h][k]);
+          for (int k = 0; k < CPL; ++k) acc[h][k] = fmaf(q[h], xa[k], acc[h][k]);
+      }
+      if (has_b) {
+        const float4 qa = *reinterpret_cast<const float4*>(&qs[warp][t + 1][0]);
+        const float4 qb = *reinterpret_cast<const float4*>(&qs[warp][t + 1][4]);
+        const float q8 = qs[warp][t + 1][8];
+        const float q[H] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w, q8};
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int k = 0; k < CPL; ++k) acc[h][k] = fmaf(q[h], xb[k], acc[h][k]);
+      }
     }
     __syncwarp();
   }
   const float cntf = (float)total;
-  float* zrow = Z + i * ldz;
+  if (c0 >= C) return;
+  if (OUT == 0) {
+    float* zrow = static_cast<float*>(Zout) + i * ldz;
 #pragma unroll
-  for (int h = 0; h < H; ++h)
+    for (int h = 0; h < H; ++h)
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) {
-      const int c = lane + 32 * k;
-      if (c < C) zrow[h * C + c] = acc[h][k] / cntf;
+      for (int k = 0; k < CPL; ++k)
+        if (c0 + k < C) zrow[h * C + c0 + k] = acc[h][k] / cntf;
+  } else {
+    __nv_bfloat16* zhi = static_cast<__nv_bfloat16*>(Zout) + i * ldz;
+    __nv_bfloat16* zlo = zhi + N * ldz;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      __nv_bfloat16 hi[CPL], lo[CPL];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const float z = acc[h][k] / cntf;
+        hi[k] = __float2bfloat16_rn(z);
+        lo[k] = __float2bfloat16_rn(z - __bfloat162float(hi[k]));
+      }
+      if (CPL > 1 && vec_ok) {    // C % CPL == 0 here: one 4- or 8-byte store per plane
+        if (CPL == 2) {
+          *reinterpret_cast<uint32_t*>(zhi + h * C + c0) = *reinterpret_cast<const uint32_t*>(hi);
+          if (OUT == 2) *reinterpret_cast<uint32_t*>(zlo + h * C + c0) = *reinterpret_cast<const uint32_t*>(lo);
+        } else {
+          *reinterpret_cast<uint2*>(zhi + h * C + c0) = *reinterpret_cast<const uint2*>(hi);
+          if (OUT == 2) *reinterpret_cast<uint2*>(zlo + h * C + c0) = *reinterpret_cast<const uint2*>(lo);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k)
+          if (c0 + k < C) {
+            zhi[h * C + c0 + k] = hi[k];
+            if (OUT == 2) zlo[h * C + c0 + k] = lo[k];
+          }
+      }
     }
+  }
 }
 
 // Wt[(h*C_in + c), o] = W[(h*C_out + o), c]
@@ -286,16 +366,28 @@ struct NullCarverF {
   T* take(size_t n) { s.take<T>(n); return nullptr; }
 };
 
-// P = X U^T (fp64) then Z[i, h*C_in + c] (row stride ldz) = mean over N(i)+{i} of q_ijh x_j[c]
+// P = X U^T (fp64) then Z[i, h*C_in + c] (row stride ldz) = mean over N(i)+{i} of q_ijh x_j[c].
+// out_mode 0: fp32 Z;  1: bf16 hi plane;  2: bf16 hi | lo planes.
+template <int CPL>
+static void launch_aggregate(int out_mode, unsigned blocks, cudaStream_t st, const float* x, int64_t ldx, int64_t N, int c_in,
+                             const int32_t* rowptr, const int32_t* nbr, const double* P, const float* c, void* Z, int64_t ldz, int vec_ok) {
+  if (out_mode == 0) feast_aggregate_kernel<CPL, 0><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
+  else if (out_mode == 1) feast_aggregate_kernel<CPL, 1><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
+  else feast_aggregate_kernel<CPL, 2><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
+}
+
 int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
-                                const float* c, double* P, float* Z, int64_t ldz, cudaStream_t st) {
+                                const float* c, double* P, void* Z, int64_t ldz, int out_mode, cudaStream_t st) {
   const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
   feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, P);
   GEOBI_LAUNCH_OK("feast_project");
   const unsigned ab = (unsigned)cdiv(N, 8);
-  if (c_in <= 32) feast_aggregate_kernel<1><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
-  else if (c_in <= 64) feast_aggregate_kernel<2><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
-  else feast_aggregate_kernel<4><<<ab, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  const int cpl = c_in <= 32 ? 1 : (c_in <= 64 ? 2 : 4);
+  // vector path: every lane's CPL-channel group is whole and 4*CPL-byte aligned in x (and in Z for the packed stores)
+  const int vec_ok = (c_in % cpl == 0) && (ldx % cpl == 0) && ((reinterpret_cast<uintptr_t>(x) % (4 * cpl)) == 0) && (ldz % cpl == 0);
+  if (cpl == 1) launch_aggregate<1>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
+  else if (cpl == 2) launch_aggregate<2>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
+  else launch_aggregate<4>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
   GEOBI_LAUNCH_OK("feast_aggregate");
   return GEOBI_OK;
 }
@@ -340,7 +432,7 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   FeastWs Wk;
   carve_feast(cv, N, c_in, c_out, &Wk);
   feast_transpose_w_kernel<<<64, 256, 0, st>>>(W, c_in, c_out, Wk.Wt);
-  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, (int64_t)H * c_in, st);
+  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, (int64_t)H * c_in, 0, st);
   if (rc) return rc;
   const int K = H * c_in;
   if (c_out == 32) {

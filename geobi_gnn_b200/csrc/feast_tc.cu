@@ -135,27 +135,35 @@ __global__ void prep_weight_kernel(const float* __restrict__ W, int N, int K, in
 }
 
 // ------------------------------------------------------------------------------ out = act(A . Bq^T + bias)
-// A fp32 [M, lda] (lda % 4 == 0, 16-byte aligned rows, columns >= K read as given up to kpad: the caller zero-pads),
-// Bq bf16 [NT, kpad].  One CTA = 128 rows x NT columns; 2-stage smem ring; 128 threads.
-template <int NT, int PASSES>
-__global__ void __launch_bounds__(128) tc_gemm_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int kpad,
+// A and Bq are bf16 planes (hi, and lo = residual when PASSES == 3; plane strides a_plane / NT*kpad elements), row stride kpad.
+// One CTA = 128 rows x NT columns, 128 threads.  STAGES-deep cp.async ring: 16-byte chunks go straight from global memory into
+// the swizzled operand tiles (no registers, no conversion), so the kernel streams A at HBM rate while one thread issues the
+// MMAs of the stage that has landed.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0 -> 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NT, int PASSES, int STAGES>
+__global__ void __launch_bounds__(128) tc_gemm_kernel(const __nv_bfloat16* __restrict__ A, int64_t a_plane, int64_t M, int kpad,
                                                       const __nv_bfloat16* __restrict__ Bq, const float* __restrict__ bias, float slope,
                                                       float* __restrict__ out, int64_t ldo) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t mbar[STAGES];
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   constexpr int SPLIT = PASSES == 3 ? 2 : 1;
   constexpr int A_BYTES = BM * 128, B_BYTES = NT * 128;
   constexpr int STAGE = SPLIT * (A_BYTES + B_BYTES);   // [A_hi | A_lo | B_hi | B_lo]
   const int tid = threadIdx.x, warp = tid >> 5;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int64_t lo_plane = (int64_t)NT * kpad;           // elements between the hi and lo planes of Bq
+  const int64_t b_plane = (int64_t)NT * kpad;
 
   if (tid == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    for (int s = 0; s < STAGES; ++s) mbar_init(&mbar[s], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, NT < 32 ? 32 : NT);
@@ -166,51 +174,45 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const float* __restrict__ 
   constexpr uint32_t idesc = make_idesc(BM, NT);
   const int KB = kpad / BK;
 
-  for (int kb = 0; kb < KB; ++kb) {
-    const int s = kb & 1;
-    uint8_t* a_hi = sm + s * STAGE;
-    uint8_t* a_lo = a_hi + A_BYTES;
-    uint8_t* b_hi = a_hi + SPLIT * A_BYTES;
-    uint8_t* b_lo = b_hi + B_BYTES;
-    if (kb >= 2) {
-      mbar_wait(&mbar[s], (uint32_t)(((kb >> 1) - 1) & 1));   // the MMAs that read stage s have retired
-      tc_fence_after();
-    }
-    // A block: 128 rows x 16 float4 -> bf16x4 (hi [+ lo]), two rows per warp-iteration (coalesced 256 B rows)
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
+  auto issue_stage = [&](int kb) {
+    const uint32_t st = base + (uint32_t)((kb % STAGES) * STAGE);
+    // A: 128 rows x 8 chunks (x planes)
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
       const int idx = it * 128 + tid;
-      const int r = idx >> 4, c4 = idx & 15;
+      const int r = idx >> 3, ch = idx & 7;
       const int64_t m = m0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M) v = *reinterpret_cast<const float4*>(A + m * lda + (int64_t)kb * BK + c4 * 4);
-      const uint32_t off = sw128_off(r, c4 >> 1) + (c4 & 1) * 8;
-      if (PASSES == 3) {
-        uint2 hi, lo;
-        split_bf16x4(v, hi, lo);
-        *reinterpret_cast<uint2*>(a_hi + off) = hi;
-        *reinterpret_cast<uint2*>(a_lo + off) = lo;
-      } else {
-        *reinterpret_cast<uint2*>(a_hi + off) = pack_bf16x4(v);
-      }
+      const bool ok = m < M;
+      const __nv_bfloat16* src = A + (ok ? m : 0) * (int64_t)kpad + (int64_t)kb * BK + ch * 8;
+      cp_async16(st + sw128_off(r, ch), src, ok);
+      if (PASSES == 3) cp_async16(st + A_BYTES + sw128_off(r, ch), src + a_plane, ok);
     }
-    // B block: NT rows x 8 chunks of 16 B (already bf16), hi [+ lo] plane
     for (int idx = tid; idx < NT * 8; idx += 128) {
       const int r = idx >> 3, ch = idx & 7;
       const __nv_bfloat16* src = Bq + (int64_t)r * kpad + (int64_t)kb * BK + ch * 8;
-      *reinterpret_cast<uint4*>(b_hi + sw128_off(r, ch)) = *reinterpret_cast<const uint4*>(src);
-      if (PASSES == 3) *reinterpret_cast<uint4*>(b_lo + sw128_off(r, ch)) = *reinterpret_cast<const uint4*>(src + lo_plane);
+      cp_async16(st + SPLIT * A_BYTES + sw128_off(r, ch), src, true);
+      if (PASSES == 3) cp_async16(st + SPLIT * A_BYTES + B_BYTES + sw128_off(r, ch), src + b_plane, true);
     }
-    fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  };
+
+  for (int kb = 0; kb < STAGES - 1; ++kb) {
+    if (kb < KB) issue_stage(kb);
+    cp_async_commit();
+  }
+  for (int kb = 0; kb < KB; ++kb) {
+    const int s = kb % STAGES;
+    cp_async_wait<STAGES - 2>();   // this thread's copies of stage kb have landed
+    fence_proxy_async();           // ... and are visible to the tensor core's async proxy
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();               // ... for every thread's copies
     if (tid == 0) {
       tc_fence_after();
-      const uint64_t ah = make_desc(smem_u32(a_hi)), bh = make_desc(smem_u32(b_hi));
+      const uint32_t st = base + (uint32_t)(s * STAGE);
+      const uint64_t ah = make_desc(st), bh = make_desc(st + SPLIT * A_BYTES);
 #pragma unroll
       for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bh + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
       if (PASSES == 3) {
-        const uint64_t al = make_desc(smem_u32(a_lo)), bl = make_desc(smem_u32(b_lo));
+        const uint64_t al = make_desc(st + A_BYTES), bl = make_desc(st + SPLIT * A_BYTES + B_BYTES);
 #pragma unroll
         for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bl + 2 * k16, idesc, 1u);
 #pragma unroll
@@ -218,9 +220,19 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const float* __restrict__ 
       }
       mma_commit(&mbar[s]);
     }
+    // refill the ring: stage kb+STAGES-1 reuses the buffer read by the MMAs of stage kb-1
+    const int nk = kb + STAGES - 1;
+    if (nk < KB) {
+      if (kb >= 1) {
+        mbar_wait(&mbar[(kb - 1) % STAGES], (uint32_t)(((kb - 1) / STAGES) & 1));
+        tc_fence_after();
+      }
+      issue_stage(nk);
+    }
+    cp_async_commit();
   }
   const int last = KB - 1;
-  mbar_wait(&mbar[last & 1], (uint32_t)((last >> 1) & 1));
+  mbar_wait(&mbar[last % STAGES], (uint32_t)((last / STAGES) & 1));
   tc_fence_after();
 
   // epilogue: thread = output row (TMEM lane); 32 columns at a time
@@ -253,21 +265,23 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const float* __restrict__ 
 }
 
 template <int NT, int PASSES>
-static int launch_gemm(const float* A, int64_t lda, int64_t M, int kpad, const __nv_bfloat16* Bq, const float* bias, float slope, float* out,
-                       int64_t ldo, cudaStream_t st) {
-  const size_t smem = 2 * (PASSES == 3 ? 2 : 1) * (BM * 128 + NT * 128) + 1024;
-  GEOBI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<NT, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc_gemm_kernel<NT, PASSES><<<(unsigned)cdiv(M, BM), 128, smem, st>>>(A, lda, M, kpad, Bq, bias, slope, out, ldo);
+static int launch_gemm(const __nv_bfloat16* A, int64_t a_plane, int64_t M, int kpad, const __nv_bfloat16* Bq, const float* bias, float slope,
+                       float* out, int64_t ldo, cudaStream_t st) {
+  constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * 128 + NT * 128);
+  constexpr int STAGES = 3 * STAGE_BYTES <= 200 * 1024 ? 3 : 2;     // stay under the 227 KB per-CTA limit
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  GEOBI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<NT, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tc_gemm_kernel<NT, PASSES, STAGES><<<(unsigned)cdiv(M, BM), 128, smem, st>>>(A, a_plane, M, kpad, Bq, bias, slope, out, ldo);
   GEOBI_LAUNCH_OK("tc_gemm");
   return GEOBI_OK;
 }
 
-int gemm_dispatch(const float* A, int64_t lda, int64_t M, int kpad, const __nv_bfloat16* Bq, int N, const float* bias, float slope, float* out,
-                  int64_t ldo, int passes, cudaStream_t st) {
-#define GEOBI_TC_CASE(NT)                                                                              \
-  case NT:                                                                                             \
-    return passes == 3 ? launch_gemm<NT, 3>(A, lda, M, kpad, Bq, bias, slope, out, ldo, st)            \
-                       : launch_gemm<NT, 1>(A, lda, M, kpad, Bq, bias, slope, out, ldo, st);
+int gemm_dispatch(const __nv_bfloat16* A, int64_t a_plane, int64_t M, int kpad, const __nv_bfloat16* Bq, int N, const float* bias, float slope,
+                  float* out, int64_t ldo, int passes, cudaStream_t st) {
+#define GEOBI_TC_CASE(NT)                                                                                  \
+  case NT:                                                                                                 \
+    return passes == 3 ? launch_gemm<NT, 3>(A, a_plane, M, kpad, Bq, bias, slope, out, ldo, st)            \
+                       : launch_gemm<NT, 1>(A, a_plane, M, kpad, Bq, bias, slope, out, ldo, st);
   switch (N) {
     GEOBI_TC_CASE(32)
     GEOBI_TC_CASE(64)
@@ -277,6 +291,19 @@ int gemm_dispatch(const float* A, int64_t lda, int64_t M, int kpad, const __nv_b
 #undef GEOBI_TC_CASE
   set_error("tc gemm: N must be 32, 64, 128 or 256 (got %d)", N);
   return GEOBI_ERR_INVALID;
+}
+
+// fp32 [M, lda] -> bf16 planes hi | lo with row stride kpad (zero padded)
+__global__ void split_rows_kernel(const float* __restrict__ A, int64_t lda, int64_t M, int K, int kpad, __nv_bfloat16* __restrict__ out) {
+  const int64_t total = M * kpad;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / kpad;
+    const int k = (int)(t - m * kpad);
+    const float v = k < K ? A[m * lda + k] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[t] = hi;
+    out[total + t] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
 }
 
 // ------------------------------------------------------------------------------ fused FC head on tensor cores
@@ -410,18 +437,18 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
 // ------------------------------------------------------------------------------ FeaSt forward, bf16 projection
 // defined in feast.cu
 int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
-                                const float* c, double* P, float* Z, int64_t ldz, cudaStream_t st);
+                                const float* c, double* P, void* Z, int64_t ldz, int out_mode, cudaStream_t st);
 
 struct TcWs {
   double* P;
-  float* Z;
+  __nv_bfloat16* Z;   // hi | lo planes, [N, kpad] each
   __nv_bfloat16* Bq;
 };
 template <class C>
 static void carve_tc(C& c, int64_t N, int c_in, int c_out, TcWs* out) {
   const int kpad = (int)(cdiv(tc::H * c_in, tc::BK) * tc::BK);
   double* P = c.template take<double>((size_t)N * tc::H);
-  float* Z = c.template take<float>((size_t)N * kpad);
+  __nv_bfloat16* Z = c.template take<__nv_bfloat16>((size_t)2 * N * kpad);
   __nv_bfloat16* Bq = c.template take<__nv_bfloat16>((size_t)2 * c_out * kpad);
   if (out) *out = TcWs{P, Z, Bq};
 }
@@ -450,11 +477,11 @@ int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t
   carve_tc(cv, N, c_in, c_out, &Wk);
   const int K = tc::H * c_in;
   const int kpad = (int)(cdiv(K, tc::BK) * tc::BK);
-  if (kpad != K) GEOBI_CUDA_OK(cudaMemsetAsync(Wk.Z, 0, sizeof(float) * (size_t)N * kpad, st));
+  if (kpad != K) GEOBI_CUDA_OK(cudaMemsetAsync(Wk.Z, 0, sizeof(__nv_bfloat16) * (size_t)(passes == 3 ? 2 : 1) * N * kpad, st));
   tc::prep_weight_kernel<<<64, 256, 0, st>>>(W, c_out, K, kpad, 1, c_in, Wk.Bq);
-  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, kpad, st);
+  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, kpad, passes == 3 ? 2 : 1, st);
   if (rc) return rc;
-  return tc::gemm_dispatch(Wk.Z, kpad, N, kpad, Wk.Bq, c_out, bias, act_slope, out, ldo, passes, st);
+  return tc::gemm_dispatch(Wk.Z, (int64_t)N * kpad, N, kpad, Wk.Bq, c_out, bias, act_slope, out, ldo, passes, st);
 }
 
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
@@ -476,19 +503,25 @@ int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float
 // ------------------------------------------------------------------------------ public: tensor-core linear layer
 using namespace geobi;
 
-extern "C" size_t geobi_linear_tc_ws_bytes(int k, int n) { return align256((size_t)2 * n * (size_t)(cdiv(k, tc::BK) * tc::BK) * 2) + 256; }
+extern "C" size_t geobi_linear_tc_ws_bytes(int64_t m, int k, int n) {
+  const size_t kpad = (size_t)(cdiv(k, tc::BK) * tc::BK);
+  return align256((size_t)2 * n * kpad * 2) + align256((size_t)2 * (size_t)m * kpad * 2) + 512;
+}
 
 extern "C" int geobi_linear_tc(const float* A, int64_t lda, int64_t M, int K, const float* W, int N, const float* bias, float act_slope,
                                float* out, int64_t ldo, int precision, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GEOBI_REQUIRE(A && W && bias && out && M >= 0 && K > 0, "linear_tc: bad arguments");
   GEOBI_REQUIRE(precision == GEOBI_PREC_BF16 || precision == GEOBI_PREC_BF16X3, "linear_tc: precision must be BF16 or BF16X3");
-  GEOBI_REQUIRE(K % tc::BK == 0, "linear_tc: K must be a multiple of 64 (got %d); pad the activations", K);
-  GEOBI_REQUIRE(lda % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
-                "linear_tc: rows must be 16-byte aligned");
-  if (!ws || ws_bytes < geobi_linear_tc_ws_bytes(K, N)) { set_error("linear_tc: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  GEOBI_REQUIRE(ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "linear_tc: out rows must be 16-byte aligned");
+  if (!ws || ws_bytes < geobi_linear_tc_ws_bytes(M, K, N)) { set_error("linear_tc: workspace too small"); return GEOBI_ERR_WORKSPACE; }
   if (M == 0) return GEOBI_OK;
-  __nv_bfloat16* Bq = static_cast<__nv_bfloat16*>(ws);
-  tc::prep_weight_kernel<<<64, 256, 0, st>>>(W, N, K, K, 0, 0, Bq);
-  return tc::gemm_dispatch(A, lda, M, K, Bq, N, bias, act_slope, out, ldo, precision == GEOBI_PREC_BF16X3 ? 3 : 1, st);
+  const int kpad = (int)(cdiv(K, tc::BK) * tc::BK);
+  Carver cv(ws, ws_bytes);
+  __nv_bfloat16* Bq = cv.take<__nv_bfloat16>((size_t)2 * N * kpad);
+  __nv_bfloat16* Aq = cv.take<__nv_bfloat16>((size_t)2 * M * kpad);
+  tc::prep_weight_kernel<<<64, 256, 0, st>>>(W, N, K, kpad, 0, 0, Bq);
+  tc::split_rows_kernel<<<(unsigned)(cdiv(M * kpad, 256) > 148 * 32 ? 148 * 32 : cdiv(M * kpad, 256)), 256, 0, st>>>(A, lda, M, K, kpad, Aq);
+  GEOBI_LAUNCH_OK("linear_tc prep");
+  return tc::gemm_dispatch(Aq, (int64_t)M * kpad, M, kpad, Bq, N, bias, act_slope, out, ldo, precision == GEOBI_PREC_BF16X3 ? 3 : 1, st);
 }

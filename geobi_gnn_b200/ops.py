@@ -312,10 +312,10 @@ def linear_tc(a: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, act_slope: f
     if out is None:
         out = torch.empty((a.size(0), n), dtype=torch.float32, device=a.device)
     o, ldo, _ = _rows(out)
-    ws = _ws(lib.geobi_linear_tc_ws_bytes(k, n), a.device)
+    ws = _ws(lib.geobi_linear_tc_ws_bytes(a.size(0), k, n), a.device)
     _lib.check(lib.geobi_linear_tc(_ptr(a), lda, a.size(0), k, _ptr(W.contiguous()), n, _ptr(bias.contiguous()), float(act_slope),
                                    _ptr(o), ldo, precision, _ptr(ws), ws.numel(), _stream()), "linear_tc")
-    _count(2)
+    _count(3)
     return out
 
 

@@ -174,11 +174,12 @@ GEOBI_API int geobi_feast_fwd(const float* x, int64_t ldx, int64_t n_nodes, int 
                     int c_out, float act_slope, float* out, int64_t ldo, int precision, void* ws,
                     size_t ws_bytes, void* stream);
 
-/* Per-node linear layer on the tcgen05 tensor cores: out = act(A . W^T + bias), A fp32 [M,K] rounded to bf16 while it
- * is staged in shared memory, W fp32 [N,K] (nn.Linear layout), fp32 accumulation in TMEM.  K % 64 == 0,
- * N in {32,64,128,256}, rows 16-byte aligned.  Replaces F.linear / cuBLAS sgemm for the projections
- * (FeaSt `lin`, network.py:258-268; DualFusionLayer linears, net_util.py:252-256).  ws: bf16 copy of W. */
-GEOBI_API size_t geobi_linear_tc_ws_bytes(int k, int n);
+/* Per-node linear layer on the tcgen05 tensor cores: out = act(A . W^T + bias), A fp32 [M,K] rounded to bf16
+ * (split hi + lo for BF16X3), W fp32 [N,K] (nn.Linear layout), fp32 accumulation in TMEM.  Any K (zero padded to a
+ * multiple of 64), N in {32,64,128,256}, out rows 16-byte aligned.  Replaces F.linear / cuBLAS sgemm for the
+ * projections (FeaSt `lin`, network.py:258-268; DualFusionLayer linears, net_util.py:252-256).
+ * ws: bf16 planes of W and A. */
+GEOBI_API size_t geobi_linear_tc_ws_bytes(int64_t m, int k, int n);
 GEOBI_API int geobi_linear_tc(const float* A, int64_t lda, int64_t M, int K, const float* W, int N, const float* bias,
                               float act_slope, float* out, int64_t ldo, int precision, void* ws, size_t ws_bytes,
                               void* stream);
