@@ -73,11 +73,24 @@ struct VecLoad<4> {
   }
 };
 
+// packed fp32x2 FMA (Blackwell FFMA2): d = a * b + c on both halves of 64-bit register pairs
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
 template <int CPL, int OUT>
 __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
                                                               const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                               const double* __restrict__ P, const float* __restrict__ cvec,
                                                               void* __restrict__ Zout, int64_t ldz, int vec_ok) {
+  // soft assignments of up to 32 edges per warp: heads (0,1)(2,3)(4,5)(6,7) as 64-bit pairs + head 8
   __shared__ __align__(16) float qs[8][32][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 8 + warp;
@@ -92,88 +105,102 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
     Pi[h] = P[i * H + h];
     ch[h] = cvec[h];
   }
-  float acc[H][CPL];
+  // acc2[p][k]: heads (2p, 2p+1) of channel c0+k;  acc8[k]: head 8
+  unsigned long long acc2[4][CPL];
+  float acc8[CPL];
 #pragma unroll
-  for (int h = 0; h < H; ++h)
+  for (int k = 0; k < CPL; ++k) {
+    acc8[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) acc[h][k] = 0.f;
+    for (int p2 = 0; p2 < 4; ++p2) acc2[p2][k] = 0ull;
+  }
 
   for (int s0 = 0; s0 < total; s0 += 32) {
     const int s = s0 + lane;
-    int64_t j = i;
+    int j = (int)i;
     if (s < total) {
       if (s > 0) j = nbr[b + s - 1];
       float l[H];
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = (float)(P[j * H + h] - Pi[h]) + ch[h];
+        l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
         m = fmaxf(m, l[h]);
       }
       float sum = 0.f;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = expf(l[h] - m);
+        l[h] = __expf(l[h] - m);
         sum += l[h];
       }
-#pragma unroll
-      for (int h = 0; h < H; ++h) qs[warp][lane][h] = l[h] / sum;
+      const float inv = 1.0f / sum;
+      float4* q4 = reinterpret_cast<float4*>(&qs[warp][lane][0]);
+      q4[0] = make_float4(l[0] * inv, l[1] * inv, l[2] * inv, l[3] * inv);
+      q4[1] = make_float4(l[4] * inv, l[5] * inv, l[6] * inv, l[7] * inv);
+      qs[warp][lane][8] = l[8] * inv;
     }
     __syncwarp();
     const int cnt = min(32, total - s0);
     // two edges per iteration: both gathers are in flight before either is consumed
     for (int t = 0; t < cnt; t += 2) {
-      const int64_t ja = __shfl_sync(0xffffffffu, j, t);
-      const int64_t jb = __shfl_sync(0xffffffffu, j, (t + 1) & 31);
+      const int ja = __shfl_sync(0xffffffffu, j, t);
+      const int jb = __shfl_sync(0xffffffffu, j, (t + 1) & 31);
       const bool has_b = t + 1 < cnt;
       float xa[CPL], xb[CPL];
 #pragma unroll
       for (int k = 0; k < CPL; ++k) xa[k] = xb[k] = 0.f;
       if (c0 < C) {
         if (vec_ok) {
-          VecLoad<CPL>::ld(x + ja * ldx + c0, xa);
-          if (has_b) VecLoad<CPL>::ld(x + jb * ldx + c0, xb);
+          VecLoad<CPL>::ld(x + (int64_t)ja * ldx + c0, xa);
+          if (has_b) VecLoad<CPL>::ld(x + (int64_t)jb * ldx + c0, xb);
         } else {
 #pragma unroll
           for (int k = 0; k < CPL; ++k)
             if (c0 + k < C) {
-              xa[k] = x[ja * ldx + c0 + k];
-              if (has_b) xb[k] = x[jb * ldx + c0 + k];
+              xa[k] = x[(int64_t)ja * ldx + c0 + k];
+              if (has_b) xb[k] = x[(int64_t)jb * ldx + c0 + k];
             }
         }
       }
-      {
-        const float4 qa = *reinterpret_cast<const float4*>(&qs[warp][t][0]);
-        const float4 qb = *reinterpret_cast<const float4*>(&qs[warp][t][4]);
-        const float q8 = qs[warp][t][8];
-        const float q[H] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w, q8};
 #pragma unroll
-        for (int h = 0; h < H; ++h)
+      for (int e = 0; e < 2; ++e) {
+        if (e == 1 && !has_b) break;
+        const float* xe = e ? xb : xa;
+        const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(&qs[warp][t + e][0]);
+        const ulonglong2 qb = *reinterpret_cast<const ulonglong2*>(&qs[warp][t + e][4]);
+        const float q8 = qs[warp][t + e][8];
 #pragma unroll
-          for (int k = 0; k < CPL; ++k) acc[h][k] = fmaf(q[h], xa[k], acc[h][k]);
-      }
-      if (has_b) {
-        const float4 qa = *reinterpret_cast<const float4*>(&qs[warp][t + 1][0]);
-        const float4 qb = *reinterpret_cast<const float4*>(&qs[warp][t + 1][4]);
-        const float q8 = qs[warp][t + 1][8];
-        const float q[H] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w, q8};
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-#pragma unroll
-          for (int k = 0; k < CPL; ++k) acc[h][k] = fmaf(q[h], xb[k], acc[h][k]);
+        for (int k = 0; k < CPL; ++k) {
+          const unsigned long long xx = pack2(xe[k], xe[k]);
+          acc2[0][k] = ffma2(qa.x, xx, acc2[0][k]);
+          acc2[1][k] = ffma2(qa.y, xx, acc2[1][k]);
+          acc2[2][k] = ffma2(qb.x, xx, acc2[2][k]);
+          acc2[3][k] = ffma2(qb.y, xx, acc2[3][k]);
+          acc8[k] = fmaf(q8, xe[k], acc8[k]);
+        }
       }
     }
     __syncwarp();
   }
-  const float cntf = (float)total;
   if (c0 >= C) return;
+  const float rcnt = 1.0f / (float)total;   // mean over the neighbourhood (scatter-mean upstream)
+  float z[H][CPL];
+#pragma unroll
+  for (int k = 0; k < CPL; ++k) {
+#pragma unroll
+    for (int p2 = 0; p2 < 4; ++p2) {
+      z[2 * p2][k] = lo32(acc2[p2][k]) * rcnt;
+      z[2 * p2 + 1][k] = hi32(acc2[p2][k]) * rcnt;
+    }
+    z[8][k] = acc8[k] * rcnt;
+  }
   if (OUT == 0) {
     float* zrow = static_cast<float*>(Zout) + i * ldz;
 #pragma unroll
     for (int h = 0; h < H; ++h)
 #pragma unroll
       for (int k = 0; k < CPL; ++k)
-        if (c0 + k < C) zrow[h * C + c0 + k] = acc[h][k] / cntf;
+        if (c0 + k < C) zrow[h * C + c0 + k] = z[h][k];
   } else {
     __nv_bfloat16* zhi = static_cast<__nv_bfloat16*>(Zout) + i * ldz;
     __nv_bfloat16* zlo = zhi + N * ldz;
@@ -182,9 +209,8 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
       __nv_bfloat16 hi[CPL], lo[CPL];
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
-        const float z = acc[h][k] / cntf;
-        hi[k] = __float2bfloat16_rn(z);
-        lo[k] = __float2bfloat16_rn(z - __bfloat162float(hi[k]));
+        hi[k] = __float2bfloat16_rn(z[h][k]);
+        lo[k] = __float2bfloat16_rn(z[h][k] - __bfloat162float(hi[k]));
       }
       if (CPL > 1 && vec_ok) {    // C % CPL == 0 here: one 4- or 8-byte store per plane
         if (CPL == 2) {

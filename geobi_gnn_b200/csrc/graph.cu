@@ -473,82 +473,121 @@ extern "C" int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int
 // ------------------------------------------------------------------------------ graclus (exact parallel greedy)
 namespace geobi {
 constexpr int M_NONE = -1, M_SINGLE = -2;
+constexpr int GRACLUS_MAX_ROUNDS = 4096;
 
-// Phase A: decide from the state at round start.  match[u] = partner | M_SINGLE | M_NONE.
-__global__ void graclus_propose_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr, const float* __restrict__ w,
-                                       const int* __restrict__ rank, const int* __restrict__ label, int64_t n, int* __restrict__ match,
-                                       const int* __restrict__ decided) {
-  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n) return;
-  if (*decided >= n) { match[u] = M_NONE; return; }  // finished: make the paired apply a no-op
-  int m = M_NONE;
-  if (label[u] < 0) {
+// visiting order: u precedes v iff (rank[u], u) < (rank[v], v); ranks may therefore be any int32 keys (an inverse permutation
+// reproduces torch_cluster's order exactly, i.i.d. random keys give a uniformly random order without a sort)
+__device__ __forceinline__ bool precedes(int rv, int v, int ru, int u) { return rv < ru || (rv == ru && v < u); }
+
+// Phase A of round r.  Walks the list of nodes that were undecided one round ago (round 0: all nodes), drops the ones
+// decided since, appends the rest to the next list and decides, from the state at round start:
+// match[u] = partner | M_SINGLE | M_NONE.
+__global__ void __launch_bounds__(256) graclus_propose_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                              const float* __restrict__ w, const int* __restrict__ rank,
+                                                              const int* __restrict__ label, const int* __restrict__ act_in,
+                                                              const int* __restrict__ n_in, int n_all, int* __restrict__ match,
+                                                              int* __restrict__ act_out, int* __restrict__ n_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = act_in ? *n_in : n_all;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n; base += warps * 32) {
+    const int idx = base + lane;
+    int u = -1;
+    if (idx < n) {
+      u = act_in ? act_in[idx] : idx;
+      if (label[u] >= 0) u = -1;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, u >= 0);
+    if (mask == 0) continue;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(n_out, __popc(mask));
+    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(mask & ((1u << lane) - 1u));
+    if (u < 0) continue;
+    act_out[pos] = u;
     const int ru = rank[u];
-    int best = -1;
+    int m = M_NONE, best = -1;
     float wmax = 0.f;
-    bool localmin = true;
+    bool first = true;   // u precedes all its undecided neighbours
     for (int e = rowptr[u]; e < rowptr[u + 1]; ++e) {
       const int v = nbr[e];
       if (label[v] >= 0) continue;
-      if (rank[v] < ru) { localmin = false; break; }
+      if (precedes(rank[v], v, ru, u)) { first = false; break; }
       if (!w) { if (best < 0) best = v; }
       else if (w[e] >= wmax) { best = v; wmax = w[e]; }
     }
-    if (localmin) {
+    if (first) {
       if (best < 0) m = M_SINGLE;
       else {
-        bool first = true;  // u must precede every undecided neighbour of its partner
+        bool ok = true;  // ... and all undecided neighbours of its chosen partner
         for (int e = rowptr[best]; e < rowptr[best + 1]; ++e) {
           const int z = nbr[e];
-          if (label[z] < 0 && rank[z] < ru) { first = false; break; }
+          if (label[z] < 0 && precedes(rank[z], z, ru, u)) { ok = false; break; }
         }
-        if (first) m = best;
+        if (ok) m = best;
       }
     }
+    match[u] = m;
   }
-  match[u] = m;
 }
 
-// Phase B: apply.  Pairs are disjoint by construction, so plain stores suffice.
-__global__ void graclus_apply_kernel(const int* __restrict__ match, int* __restrict__ label, int64_t n, int* __restrict__ decided) {
-  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  int add = 0;
-  if (u < n) {
-    const int m = match[u];
-    if (m == M_SINGLE) { label[u] = (int)u; add = 1; }
-    else if (m >= 0) { const int l = m < (int)u ? m : (int)u; label[u] = l; label[m] = l; add = 2; }
-  }
-  // block-level count, one atomic per warp
-  const unsigned lane = threadIdx.x & 31;
+// Phase B: apply the round's decisions (pairs are disjoint by construction, so plain stores suffice).
+__global__ void __launch_bounds__(256) graclus_apply_kernel(const int* __restrict__ match, int* __restrict__ label,
+                                                            const int* __restrict__ act, const int* __restrict__ n_act,
+                                                            int* __restrict__ decided) {
+  const int n = *n_act;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n; base += warps * 32) {
+    const int idx = base + lane;
+    int add = 0;
+    if (idx < n) {
+      const int u = act[idx];
+      const int m = match[u];
+      if (m == M_SINGLE) { label[u] = u; add = 1; }
+      else if (m >= 0) { const int l = m < u ? m : u; label[u] = l; label[m] = l; add = 2; }
+    }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
-  if (lane == 0 && add) atomicAdd(decided, add);
+    for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
+    if (lane == 0 && add) atomicAdd(decided, add);
+  }
 }
 }  // namespace geobi
 
-extern "C" size_t geobi_graclus_ws_bytes(int64_t n_nodes) { return align256((size_t)(n_nodes + 1) * sizeof(int)) + 512; }
+// ws: [counters: decided, n_list[GRACLUS_MAX_ROUNDS+1]] | match[N] | list A[N] | list B[N]
+extern "C" size_t geobi_graclus_ws_bytes(int64_t n_nodes) {
+  return align256((size_t)(GRACLUS_MAX_ROUNDS + 8) * sizeof(int)) + 3 * align256((size_t)(n_nodes + 1) * sizeof(int)) + 256;
+}
 
 extern "C" int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const float* w, const int32_t* rank, int64_t n_nodes, int32_t* label,
                              int* rounds_host, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GEOBI_REQUIRE(rowptr && rank && label && n_nodes >= 0, "graclus: bad arguments");
+  GEOBI_REQUIRE(rowptr && rank && label && n_nodes >= 0 && n_nodes < ((int64_t)1 << 31), "graclus: bad arguments");
   if (rounds_host) *rounds_host = 0;
   if (n_nodes == 0) return GEOBI_OK;
   if (ws_bytes < geobi_graclus_ws_bytes(n_nodes) || !ws) {
     set_error("graclus: workspace too small");
     return GEOBI_ERR_WORKSPACE;
   }
-  int* decided = static_cast<int*>(ws);                       // one counter (256-byte slot)
-  int* match = reinterpret_cast<int*>(static_cast<char*>(ws) + 256);
-  GEOBI_CUDA_OK(cudaMemsetAsync(decided, 0, sizeof(int), st));
+  Carver c(ws, ws_bytes);
+  int* counters = c.take<int>(GRACLUS_MAX_ROUNDS + 8);
+  int* match = c.take<int>(n_nodes + 1);
+  int* lists[2] = {c.take<int>(n_nodes + 1), c.take<int>(n_nodes + 1)};
+  int* decided = counters;
+  int* n_list = counters + 1;   // n_list[r] = length of the list produced by round r's propose
+  GEOBI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int) * (GRACLUS_MAX_ROUNDS + 8), st));
   GEOBI_CUDA_OK(cudaMemsetAsync(label, 0xff, sizeof(int) * n_nodes, st));  // -1 = undecided
-  const unsigned blocks = (unsigned)cdiv(n_nodes, 256);
+  int64_t nb = cdiv(n_nodes, 256);
+  if (nb > 148 * 8) nb = 148 * 8;
+  const unsigned blocks = (unsigned)nb;
   int rounds = 0, h_decided = 0, batch = 12;
-  const int max_rounds = 4096;
-  while (rounds < max_rounds) {
+  while (rounds < GRACLUS_MAX_ROUNDS) {
+    if (rounds + batch > GRACLUS_MAX_ROUNDS) batch = GRACLUS_MAX_ROUNDS - rounds;
     for (int k = 0; k < batch; ++k) {
-      graclus_propose_kernel<<<blocks, 256, 0, st>>>(rowptr, nbr, w, rank, label, n_nodes, match, decided);
-      graclus_apply_kernel<<<blocks, 256, 0, st>>>(match, label, n_nodes, decided);
+      const int r = rounds + k;
+      const int* in = r == 0 ? nullptr : lists[(r - 1) & 1];
+      const int* n_in = r == 0 ? nullptr : n_list + (r - 1);
+      graclus_propose_kernel<<<blocks, 256, 0, st>>>(rowptr, nbr, w, rank, label, in, n_in, (int)n_nodes, match, lists[r & 1], n_list + r);
+      graclus_apply_kernel<<<blocks, 256, 0, st>>>(match, label, lists[r & 1], n_list + r, decided);
     }
     GEOBI_LAUNCH_OK("graclus round");
     rounds += batch;

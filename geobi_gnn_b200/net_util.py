@@ -68,7 +68,7 @@ class PoolingLayer(torch.nn.Module):
             init.xavier_uniform_(self.att_r.data, gain=1.414)
         self.unpooling_indices = None
         self._unpool_i32 = None
-        self.perm_fn = None          # callable(n, device) -> permutation; None = torch.randperm on device
+        self.perm_fn = None          # callable(n) -> permutation (upstream draws torch.randperm); None = random keys on device
         self.forced = None           # list of raw label tensors (teacher forcing)
         self.trace = []
 
@@ -125,7 +125,7 @@ class PoolingLayer(torch.nn.Module):
             if self.forced is not None:
                 label, perm = self.forced[step].to(dev).to(torch.int32), None
             else:
-                perm = torch.randperm(n, device=dev) if self.perm_fn is None else self.perm_fn(n).to(dev)
+                perm = None if self.perm_fn is None else self.perm_fn(n).to(dev)   # None: random priority keys on the device
                 label, _ = ops.graclus(g, perm, use_weight=g.w is not None)
             self.trace.append((g, perm, label))
             cluster, nc = ops.relabel_clusters(label)

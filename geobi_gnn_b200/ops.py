@@ -165,13 +165,21 @@ def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor) -> CSRGraph:
     return CSRGraph(rowptr, nbr[:n].clone(), f, n, symmetric=True)
 
 
-def graclus(g: CSRGraph, perm: torch.Tensor, weight: Optional[torch.Tensor] = None, use_weight: bool = True):
-    """Exact greedy matching for visiting order `perm` -> raw labels int32 [N] (= min(u, partner))."""
+def graclus(g: CSRGraph, perm: Optional[torch.Tensor] = None, weight: Optional[torch.Tensor] = None, use_weight: bool = True,
+            keys: Optional[torch.Tensor] = None):
+    """Exact greedy matching -> raw labels int32 [N] (= min(u, partner)).
+    Visiting order: `perm` (torch_cluster's randperm semantics; rank = inverse permutation) or int32 priority `keys`
+    (u before v iff (keys[u], u) < (keys[v], v)); with neither, i.i.d. random keys = a uniformly random order, no sort."""
     lib = _lib.load()
     dev = g.rowptr.device
-    _need_cuda(g.rowptr, perm)
-    rank = torch.empty(g.n, dtype=torch.int32, device=dev)
-    rank[perm.to(dev).long()] = torch.arange(g.n, dtype=torch.int32, device=dev)
+    _need_cuda(g.rowptr, perm, keys)
+    if perm is not None:
+        rank = torch.empty(g.n, dtype=torch.int32, device=dev)
+        rank[perm.to(dev).long()] = torch.arange(g.n, dtype=torch.int32, device=dev)
+    elif keys is not None:
+        rank = keys.to(torch.int32).contiguous()
+    else:
+        rank = torch.randint(0, 2 ** 31 - 1, (g.n,), dtype=torch.int32, device=dev)
     w = (g.w if weight is None else weight) if use_weight else None
     label = torch.empty(g.n, dtype=torch.int32, device=dev)
     ws = _ws(lib.geobi_graclus_ws_bytes(g.n), dev)
