@@ -21,6 +21,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# level sizes vary from step to step (random matching order): let the caching allocator grow segments in place instead of
+# falling back to cudaMalloc / cudaFree (each one a device-wide sync) when a request does not fit a cached block
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -175,7 +178,7 @@ def run_ours(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clk:
         ms, wall = timed(step_resident, args.steps)
     launches = ops.launch_count() - l0
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(args.warmup):
         step_e2e()
     ms_e2e, wall_e2e = timed(step_e2e, args.steps)
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())

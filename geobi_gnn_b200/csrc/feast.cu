@@ -85,11 +85,11 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
-template <int CPL, int OUT>
+template <int CPL, int OUT, bool VEC>
 __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
                                                               const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                               const double* __restrict__ P, const float* __restrict__ cvec,
-                                                              void* __restrict__ Zout, int64_t ldz, int vec_ok) {
+                                                              void* __restrict__ Zout, int64_t ldz) {
   // soft assignments of up to 32 edges per warp: heads (0,1)(2,3)(4,5)(6,7) as 64-bit pairs + head 8
   __shared__ __align__(16) float qs[8][32][12];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
   const int b = rowptr[i];
   const int total = rowptr[i + 1] - b + 1;  // neighbours + implicit self loop (slot 0)
   const int c0 = lane * CPL;
+  const int cl = c0 < C ? c0 : 0;           // lanes past the last channel gather channel 0 and never store
+  const unsigned ldx32 = (unsigned)ldx;     // host guarantees N * ldx < 2^32 elements
   double Pi[H];
   float ch[H];
 #pragma unroll
@@ -118,9 +120,9 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
   for (int s0 = 0; s0 < total; s0 += 32) {
     const int s = s0 + lane;
     int j = (int)i;
+    float l[H];
     if (s < total) {
       if (s > 0) j = nbr[b + s - 1];
-      float l[H];
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
@@ -134,50 +136,58 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
         sum += l[h];
       }
       const float inv = 1.0f / sum;
-      float4* q4 = reinterpret_cast<float4*>(&qs[warp][lane][0]);
-      q4[0] = make_float4(l[0] * inv, l[1] * inv, l[2] * inv, l[3] * inv);
-      q4[1] = make_float4(l[4] * inv, l[5] * inv, l[6] * inv, l[7] * inv);
-      qs[warp][lane][8] = l[8] * inv;
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] *= inv;
+    } else {
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] = 0.f;   // padding slot: weight 0 on a valid row, keeps the pair loop branch-free
     }
+    float4* q4 = reinterpret_cast<float4*>(&qs[warp][lane][0]);
+    q4[0] = make_float4(l[0], l[1], l[2], l[3]);
+    q4[1] = make_float4(l[4], l[5], l[6], l[7]);
+    qs[warp][lane][8] = l[8];
     __syncwarp();
     const int cnt = min(32, total - s0);
-    // two edges per iteration: both gathers are in flight before either is consumed
+    // two edges per iteration, both gathers in flight before either is consumed
     for (int t = 0; t < cnt; t += 2) {
-      const int ja = __shfl_sync(0xffffffffu, j, t);
-      const int jb = __shfl_sync(0xffffffffu, j, (t + 1) & 31);
-      const bool has_b = t + 1 < cnt;
+      const unsigned ja = (unsigned)__shfl_sync(0xffffffffu, j, t);
+      const unsigned jb = (unsigned)__shfl_sync(0xffffffffu, j, t + 1);   // t+1 <= 31 since t is even
       float xa[CPL], xb[CPL];
-#pragma unroll
-      for (int k = 0; k < CPL; ++k) xa[k] = xb[k] = 0.f;
-      if (c0 < C) {
-        if (vec_ok) {
-          VecLoad<CPL>::ld(x + (int64_t)ja * ldx + c0, xa);
-          if (has_b) VecLoad<CPL>::ld(x + (int64_t)jb * ldx + c0, xb);
-        } else {
-#pragma unroll
-          for (int k = 0; k < CPL; ++k)
-            if (c0 + k < C) {
-              xa[k] = x[(int64_t)ja * ldx + c0 + k];
-              if (has_b) xb[k] = x[(int64_t)jb * ldx + c0 + k];
-            }
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        if (e == 1 && !has_b) break;
-        const float* xe = e ? xb : xa;
-        const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(&qs[warp][t + e][0]);
-        const ulonglong2 qb = *reinterpret_cast<const ulonglong2*>(&qs[warp][t + e][4]);
-        const float q8 = qs[warp][t + e][8];
+      if (VEC) {
+        VecLoad<CPL>::ld(x + (ja * ldx32 + (unsigned)cl), xa);
+        VecLoad<CPL>::ld(x + (jb * ldx32 + (unsigned)cl), xb);
+      } else {
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
-          const unsigned long long xx = pack2(xe[k], xe[k]);
-          acc2[0][k] = ffma2(qa.x, xx, acc2[0][k]);
-          acc2[1][k] = ffma2(qa.y, xx, acc2[1][k]);
-          acc2[2][k] = ffma2(qb.x, xx, acc2[2][k]);
-          acc2[3][k] = ffma2(qb.y, xx, acc2[3][k]);
-          acc8[k] = fmaf(q8, xe[k], acc8[k]);
+          const unsigned ck = cl + k < C ? cl + k : cl;
+          xa[k] = x[ja * ldx32 + ck];
+          xb[k] = x[jb * ldx32 + ck];
         }
+      }
+      const float* qrow = &qs[warp][t][0];
+      const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(qrow);
+      const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(qrow + 4);
+      const float qa8 = qrow[8];
+      const ulonglong2 qb0 = *reinterpret_cast<const ulonglong2*>(qrow + 12);
+      const ulonglong2 qb1 = *reinterpret_cast<const ulonglong2*>(qrow + 16);
+      const float qb8 = qrow[20];
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const unsigned long long xxa = pack2(xa[k], xa[k]);
+        acc2[0][k] = ffma2(qa0.x, xxa, acc2[0][k]);
+        acc2[1][k] = ffma2(qa0.y, xxa, acc2[1][k]);
+        acc2[2][k] = ffma2(qa1.x, xxa, acc2[2][k]);
+        acc2[3][k] = ffma2(qa1.y, xxa, acc2[3][k]);
+        acc8[k] = fmaf(qa8, xa[k], acc8[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < CPL; ++k) {
+        const unsigned long long xxb = pack2(xb[k], xb[k]);
+        acc2[0][k] = ffma2(qb0.x, xxb, acc2[0][k]);
+        acc2[1][k] = ffma2(qb0.y, xxb, acc2[1][k]);
+        acc2[2][k] = ffma2(qb1.x, xxb, acc2[2][k]);
+        acc2[3][k] = ffma2(qb1.y, xxb, acc2[3][k]);
+        acc8[k] = fmaf(qb8, xb[k], acc8[k]);
       }
     }
     __syncwarp();
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
         hi[k] = __float2bfloat16_rn(z[h][k]);
         lo[k] = __float2bfloat16_rn(z[h][k] - __bfloat162float(hi[k]));
       }
-      if (CPL > 1 && vec_ok) {    // C % CPL == 0 here: one 4- or 8-byte store per plane
+      if (CPL > 1 && VEC) {    // C % CPL == 0 here: one 4- or 8-byte store per plane
         if (CPL == 2) {
           *reinterpret_cast<uint32_t*>(zhi + h * C + c0) = *reinterpret_cast<const uint32_t*>(hi);
           if (OUT == 2) *reinterpret_cast<uint32_t*>(zlo + h * C + c0) = *reinterpret_cast<const uint32_t*>(lo);
@@ -394,12 +404,12 @@ struct NullCarverF {
 
 // P = X U^T (fp64) then Z[i, h*C_in + c] (row stride ldz) = mean over N(i)+{i} of q_ijh x_j[c].
 // out_mode 0: fp32 Z;  1: bf16 hi plane;  2: bf16 hi | lo planes.
-template <int CPL>
+template <int CPL, bool VEC>
 static void launch_aggregate(int out_mode, unsigned blocks, cudaStream_t st, const float* x, int64_t ldx, int64_t N, int c_in,
-                             const int32_t* rowptr, const int32_t* nbr, const double* P, const float* c, void* Z, int64_t ldz, int vec_ok) {
-  if (out_mode == 0) feast_aggregate_kernel<CPL, 0><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
-  else if (out_mode == 1) feast_aggregate_kernel<CPL, 1><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
-  else feast_aggregate_kernel<CPL, 2><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
+                             const int32_t* rowptr, const int32_t* nbr, const double* P, const float* c, void* Z, int64_t ldz) {
+  if (out_mode == 0) feast_aggregate_kernel<CPL, 0, VEC><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else if (out_mode == 1) feast_aggregate_kernel<CPL, 1, VEC><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else feast_aggregate_kernel<CPL, 2, VEC><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
 }
 
 int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
@@ -410,10 +420,13 @@ int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in
   const unsigned ab = (unsigned)cdiv(N, 8);
   const int cpl = c_in <= 32 ? 1 : (c_in <= 64 ? 2 : 4);
   // vector path: every lane's CPL-channel group is whole and 4*CPL-byte aligned in x (and in Z for the packed stores)
-  const int vec_ok = (c_in % cpl == 0) && (ldx % cpl == 0) && ((reinterpret_cast<uintptr_t>(x) % (4 * cpl)) == 0) && (ldz % cpl == 0);
-  if (cpl == 1) launch_aggregate<1>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
-  else if (cpl == 2) launch_aggregate<2>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
-  else launch_aggregate<4>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz, vec_ok);
+  const bool vec_ok = (c_in % cpl == 0) && (ldx % cpl == 0) && ((reinterpret_cast<uintptr_t>(x) % (4 * cpl)) == 0) && (ldz % cpl == 0);
+  GEOBI_REQUIRE(N * ldx < ((int64_t)1 << 32), "feast_fwd: N * ldx must stay below 2^32 elements (32-bit gather offsets)");
+  if (cpl == 1) launch_aggregate<1, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);   // scalar loads are always aligned
+  else if (cpl == 2 && vec_ok) launch_aggregate<2, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else if (cpl == 2) launch_aggregate<2, false>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else if (vec_ok) launch_aggregate<4, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else launch_aggregate<4, false>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
   GEOBI_LAUNCH_OK("feast_aggregate");
   return GEOBI_OK;
 }

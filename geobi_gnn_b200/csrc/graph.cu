@@ -473,133 +473,131 @@ extern "C" int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int
 // ------------------------------------------------------------------------------ graclus (exact parallel greedy)
 namespace geobi {
 constexpr int M_NONE = -1, M_SINGLE = -2;
-constexpr int GRACLUS_MAX_ROUNDS = 4096;
 
 // visiting order: u precedes v iff (rank[u], u) < (rank[v], v); ranks may therefore be any int32 keys (an inverse permutation
 // reproduces torch_cluster's order exactly, i.i.d. random keys give a uniformly random order without a sort)
 __device__ __forceinline__ bool precedes(int rv, int v, int ru, int u) { return rv < ru || (rv == ru && v < u); }
 
-// Phase A of round r.  Walks the list of nodes that were undecided one round ago (round 0: all nodes), drops the ones
-// decided since, appends the rest to the next list and decides, from the state at round start:
-// match[u] = partner | M_SINGLE | M_NONE.
-__global__ void __launch_bounds__(256) graclus_propose_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr,
-                                                              const float* __restrict__ w, const int* __restrict__ rank,
-                                                              const int* __restrict__ label, const int* __restrict__ act_in,
-                                                              const int* __restrict__ n_in, int n_all, int* __restrict__ match,
-                                                              int* __restrict__ act_out, int* __restrict__ n_out) {
-  const int lane = threadIdx.x & 31;
-  const int n = act_in ? *n_in : n_all;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n; base += warps * 32) {
-    const int idx = base + lane;
-    int u = -1;
-    if (idx < n) {
-      u = act_in ? act_in[idx] : idx;
-      if (label[u] >= 0) u = -1;
-    }
-    const unsigned mask = __ballot_sync(0xffffffffu, u >= 0);
-    if (mask == 0) continue;
-    int pos = 0;
-    if (lane == 0) pos = atomicAdd(n_out, __popc(mask));
-    pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(mask & ((1u << lane) - 1u));
-    if (u < 0) continue;
-    act_out[pos] = u;
-    const int ru = rank[u];
-    int m = M_NONE, best = -1;
-    float wmax = 0.f;
-    bool first = true;   // u precedes all its undecided neighbours
-    for (int e = rowptr[u]; e < rowptr[u + 1]; ++e) {
-      const int v = nbr[e];
-      if (label[v] >= 0) continue;
-      if (precedes(rank[v], v, ru, u)) { first = false; break; }
-      if (!w) { if (best < 0) best = v; }
-      else if (w[e] >= wmax) { best = v; wmax = w[e]; }
-    }
-    if (first) {
-      if (best < 0) m = M_SINGLE;
-      else {
-        bool ok = true;  // ... and all undecided neighbours of its chosen partner
-        for (int e = rowptr[best]; e < rowptr[best + 1]; ++e) {
-          const int z = nbr[e];
-          if (label[z] < 0 && precedes(rank[z], z, ru, u)) { ok = false; break; }
-        }
-        if (ok) m = best;
-      }
-    }
-    match[u] = m;
+// Asynchronous exact greedy matching, one launch, no grid barriers.
+//
+// Every node is owned by one resident thread (grid-stride ownership over a co-resident grid); the thread sweeps over its
+// still-undecided nodes until all are decided.  A node u may act when (1) every neighbour that precedes it is decided and
+// (2) every undecided neighbour of its chosen partner v comes after u; it then claims v with atomicCAS(label[v], -1, min)
+// and publishes its own label afterwards.  Labels only ever go from -1 to their final value, so a stale read can only make
+// a node wait (it sees a decided node as undecided), never act wrongly; the CAS is the linearisation point of a claim.
+// The result is therefore the serial greedy matching for the visiting order, independent of thread timing.
+// pos[u] caches how far u's "who precedes me" scan has got (decided neighbours stay decided), so a blocked node costs
+// ~4 loads per sweep.
+constexpr int GRACLUS_MAX_SWEEPS = 1 << 20;
+
+__device__ __forceinline__ int graclus_try(int u, const int* __restrict__ rowptr, const int* __restrict__ nbr, const float* __restrict__ w,
+                                           const int* __restrict__ rank, int* label, int* pos) {
+  if (__ldcg(label + u) >= 0) return 1;  // claimed by a partner
+  const int ru = rank[u];
+  const int end = rowptr[u + 1];
+  int e = pos[u];
+  for (; e < end; ++e) {
+    const int v = nbr[e];
+    if (__ldcg(label + v) < 0 && precedes(rank[v], v, ru, u)) break;
   }
+  pos[u] = e;
+  if (e < end) return 0;                 // an earlier neighbour is still undecided
+  // Only earlier neighbours can claim u, and a claimer CASes label[u] *before* it publishes its own label.  All of them
+  // are now observed decided, so after this fence a claim on u (if any) is visible; if none, nobody can claim u any more.
+  __threadfence();
+  if (__ldcg(label + u) >= 0) return 1;
+  int best = -1;
+  float wmax = 0.f;
+  for (e = rowptr[u]; e < end; ++e) {
+    const int v = nbr[e];
+    if (__ldcg(label + v) >= 0) continue;
+    if (!w) { best = v; break; }
+    if (w[e] >= wmax) { best = v; wmax = w[e]; }
+  }
+  if (best < 0) {
+    __stcg(label + u, u);                // no free neighbour: singleton
+    return 1;
+  }
+  for (e = rowptr[best]; e < rowptr[best + 1]; ++e) {
+    const int z = nbr[e];
+    if (__ldcg(label + z) < 0 && precedes(rank[z], z, ru, u)) return 0;   // someone earlier may still claim `best`
+  }
+  const int l = best < u ? best : u;
+  if (atomicCAS(label + best, -1, l) != -1) return 0;   // lost a race against a stale view: retry with fresh labels
+  __threadfence();
+  __stcg(label + u, l);
+  return 1;
 }
 
-// Phase B: apply the round's decisions (pairs are disjoint by construction, so plain stores suffice).
-__global__ void __launch_bounds__(256) graclus_apply_kernel(const int* __restrict__ match, int* __restrict__ label,
-                                                            const int* __restrict__ act, const int* __restrict__ n_act,
-                                                            int* __restrict__ decided) {
-  const int n = *n_act;
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n; base += warps * 32) {
-    const int idx = base + lane;
-    int add = 0;
-    if (idx < n) {
-      const int u = act[idx];
-      const int m = match[u];
-      if (m == M_SINGLE) { label[u] = u; add = 1; }
-      else if (m >= 0) { const int l = m < u ? m : u; label[u] = l; label[m] = l; add = 2; }
+__global__ void __launch_bounds__(256) graclus_async_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                            const float* __restrict__ w, const int* __restrict__ rank, int* label,
+                                                            int n, int* pos, int* undecided) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (int u = tid; u < n; u += stride) pos[u] = rowptr[u];
+  int left = 0;
+  for (int u = tid; u < n; u += stride) ++left;
+  unsigned backoff = 32;
+  for (int sweep = 0; left > 0 && sweep < GRACLUS_MAX_SWEEPS; ++sweep) {
+    int still = 0;
+    for (int u = tid; u < n; u += stride) {
+      if (pos[u] < 0) continue;          // done marker
+      if (graclus_try(u, rowptr, nbr, w, rank, label, pos)) pos[u] = -1;
+      else ++still;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(0xffffffffu, add, o);
-    if (lane == 0 && add) atomicAdd(decided, add);
+    if (still == left) {                 // no progress: let the owners of the blocking nodes run
+      __nanosleep(backoff);
+      if (backoff < 1024) backoff <<= 1;
+    } else {
+      backoff = 32;
+    }
+    left = still;
   }
+  if (left > 0) atomicAdd(undecided, left);
 }
 }  // namespace geobi
 
-// ws: [counters: decided, n_list[GRACLUS_MAX_ROUNDS+1]] | match[N] | list A[N] | list B[N]
-extern "C" size_t geobi_graclus_ws_bytes(int64_t n_nodes) {
-  return align256((size_t)(GRACLUS_MAX_ROUNDS + 8) * sizeof(int)) + 3 * align256((size_t)(n_nodes + 1) * sizeof(int)) + 256;
-}
+// ws: [undecided counter] | pos[N]
+extern "C" size_t geobi_graclus_ws_bytes(int64_t n_nodes) { return 256 + align256((size_t)(n_nodes + 1) * sizeof(int)) + 256; }
 
 extern "C" int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const float* w, const int32_t* rank, int64_t n_nodes, int32_t* label,
-                             int* rounds_host, void* ws, size_t ws_bytes, void* stream) {
+                             int* undecided_host, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GEOBI_REQUIRE(rowptr && rank && label && n_nodes >= 0 && n_nodes < ((int64_t)1 << 31), "graclus: bad arguments");
-  if (rounds_host) *rounds_host = 0;
+  if (undecided_host) *undecided_host = 0;
   if (n_nodes == 0) return GEOBI_OK;
   if (ws_bytes < geobi_graclus_ws_bytes(n_nodes) || !ws) {
     set_error("graclus: workspace too small");
     return GEOBI_ERR_WORKSPACE;
   }
-  Carver c(ws, ws_bytes);
-  int* counters = c.take<int>(GRACLUS_MAX_ROUNDS + 8);
-  int* match = c.take<int>(n_nodes + 1);
-  int* lists[2] = {c.take<int>(n_nodes + 1), c.take<int>(n_nodes + 1)};
-  int* decided = counters;
-  int* n_list = counters + 1;   // n_list[r] = length of the list produced by round r's propose
-  GEOBI_CUDA_OK(cudaMemsetAsync(counters, 0, sizeof(int) * (GRACLUS_MAX_ROUNDS + 8), st));
+  int* undecided = static_cast<int*>(ws);
+  int* pos = reinterpret_cast<int*>(static_cast<char*>(ws) + 256);
+  GEOBI_CUDA_OK(cudaMemsetAsync(undecided, 0, sizeof(int), st));
   GEOBI_CUDA_OK(cudaMemsetAsync(label, 0xff, sizeof(int) * n_nodes, st));  // -1 = undecided
-  int64_t nb = cdiv(n_nodes, 256);
-  if (nb > 148 * 8) nb = 148 * 8;
-  const unsigned blocks = (unsigned)nb;
-  int rounds = 0, h_decided = 0, batch = 12;
-  while (rounds < GRACLUS_MAX_ROUNDS) {
-    if (rounds + batch > GRACLUS_MAX_ROUNDS) batch = GRACLUS_MAX_ROUNDS - rounds;
-    for (int k = 0; k < batch; ++k) {
-      const int r = rounds + k;
-      const int* in = r == 0 ? nullptr : lists[(r - 1) & 1];
-      const int* n_in = r == 0 ? nullptr : n_list + (r - 1);
-      graclus_propose_kernel<<<blocks, 256, 0, st>>>(rowptr, nbr, w, rank, label, in, n_in, (int)n_nodes, match, lists[r & 1], n_list + r);
-      graclus_apply_kernel<<<blocks, 256, 0, st>>>(match, label, lists[r & 1], n_list + r, decided);
-    }
-    GEOBI_LAUNCH_OK("graclus round");
-    rounds += batch;
-    GEOBI_CUDA_OK(cudaMemcpyAsync(&h_decided, decided, sizeof(int), cudaMemcpyDeviceToHost, st));
-    GEOBI_CUDA_OK(cudaStreamSynchronize(st));
-    if (h_decided >= n_nodes) break;
-    batch = 6;
+  static int coresident = 0;   // blocks that are guaranteed to be resident together (threads wait on each other's nodes)
+  if (coresident == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    GEOBI_CUDA_OK(cudaGetDevice(&dev));
+    GEOBI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GEOBI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graclus_async_kernel, 256, 0));
+    coresident = sms * per_sm;
+    GEOBI_REQUIRE(coresident > 0, "graclus: cooperative launch not possible on this device");
   }
-  if (rounds_host) *rounds_host = rounds;
-  if (h_decided < n_nodes) {
-    set_error("graclus: %lld of %lld nodes undecided after %d rounds", (long long)(n_nodes - h_decided), (long long)n_nodes, rounds);
-    return GEOBI_ERR_NOCONVERGE;
+  int64_t nb = cdiv(n_nodes, 256);
+  if (nb > coresident) nb = coresident;
+  int n_all = (int)n_nodes;
+  void* args[] = {(void*)&rowptr, (void*)&nbr, (void*)&w, (void*)&rank, (void*)&label, (void*)&n_all, (void*)&pos, (void*)&undecided};
+  // cooperative launch = the runtime refuses the launch unless all blocks are co-resident (no grid barrier is used)
+  GEOBI_CUDA_OK(cudaLaunchCooperativeKernel((const void*)graclus_async_kernel, dim3((unsigned)nb), dim3(256), args, 0, st));
+  if (undecided_host) {   // optional convergence check (SYNCS); callers on the hot path fold it into geobi_relabel_clusters
+    int h_und = 0;
+    GEOBI_CUDA_OK(cudaMemcpyAsync(&h_und, undecided, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GEOBI_CUDA_OK(cudaStreamSynchronize(st));
+    *undecided_host = h_und;
+    if (h_und > 0) {
+      set_error("graclus: %d of %lld nodes undecided (sweep limit)", h_und, (long long)n_nodes);
+      return GEOBI_ERR_NOCONVERGE;
+    }
   }
   return GEOBI_OK;
 }
@@ -797,5 +795,48 @@ extern "C" int geobi_pool_edges(const int32_t* rowptr, const int32_t* nbr, const
                          /*w_mean=*/1, out_rowptr, out_nbr, out_w, nullptr, W.status, W.scan, W.scan_bytes, st);
   if (rc) return rc;
   if (nnz_host) return finish_sync(W.status, out_rowptr, n_clusters, nnz_host, "pool_edges", st);
+  return GEOBI_OK;
+}
+
+// ------------------------------------------------------------------------------ remove_self_loops (order preserving)
+namespace geobi {
+__global__ void rsl_flag_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col, int64_t E, int* __restrict__ flag) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < E) flag[e] = row[e] != col[e] ? 1 : 0;
+}
+__global__ void rsl_scatter_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col, const float* __restrict__ w, int64_t E,
+                                   const int* __restrict__ offs, int64_t count, int64_t* __restrict__ out, float* __restrict__ w_out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E || row[e] == col[e]) return;
+  const int64_t o = offs[e];
+  if (o >= count) return;   // the caller's count was too small: never write out of bounds
+  out[o] = row[e];
+  out[count + o] = col[e];
+  if (w_out) w_out[o] = w[e];
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_remove_self_loops_ws_bytes(int64_t n_edges) {
+  return 2 * align256((size_t)(n_edges + 2) * sizeof(int)) + scan_ws_bytes(n_edges + 1) + 256;
+}
+
+extern "C" int geobi_remove_self_loops(const int64_t* row, const int64_t* col, const float* w, int64_t n_edges, int64_t count, int64_t* out,
+                                       float* w_out, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(row && col && n_edges >= 0 && count >= 0 && (out || count == 0), "remove_self_loops: bad arguments");
+  GEOBI_REQUIRE((w == nullptr) == (w_out == nullptr), "remove_self_loops: w and w_out must both be given or both be NULL");
+  if (n_edges == 0 || count == 0) return GEOBI_OK;
+  if (!ws || ws_bytes < geobi_remove_self_loops_ws_bytes(n_edges)) { set_error("remove_self_loops: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  Carver c(ws, ws_bytes);
+  int* flag = c.take<int>(n_edges + 2);
+  int* offs = c.take<int>(n_edges + 2);
+  const size_t sb = scan_ws_bytes(n_edges + 1);
+  char* scan = c.take<char>(sb);
+  const unsigned blocks = (unsigned)cdiv(n_edges, 256);
+  rsl_flag_kernel<<<blocks, 256, 0, st>>>(row, col, n_edges, flag);
+  int rc = scan_i32(flag, offs, n_edges, scan, sb, st);
+  if (rc) return rc;
+  rsl_scatter_kernel<<<blocks, 256, 0, st>>>(row, col, w, n_edges, offs, count, out, w_out);
+  GEOBI_LAUNCH_OK("remove_self_loops");
   return GEOBI_OK;
 }

@@ -34,18 +34,17 @@ def _match_csr(data) -> Optional[CSRGraph]:
     tag = gnn.tag_of(ei)
     g = tag.get("src")
     if g is not None and g.n == n:                       # built by us: no self loops, CSR order == edge order
-        if g.nnz == 0:
+        if g.cap == 0:
             return None
-        return dataclasses.replace(g, w=w)
-    keep = ei[0] != ei[1]
-    ei2 = ei[:, keep]
-    if ei2.numel() == 0:
+        return g.with_weight(w)
+    g = ops.csr_from_coo(ei, n, w, ops.COO_DROP_SELF)    # stable sort by source; syncs once (nnz = edges that are not loops)
+    if g.nnz == 0:
         return None
-    w2 = None if w is None else w[keep]
-    g = ops.csr_from_coo(ei2, n, w2, 0)                  # stable sort by source
-    if "tgt" in tag:
-        gnn.tag_of(ei2)["tgt"] = tag["tgt"]
-    data.edge_index, data.edge_weight = ei2, w2
+    if g.nnz != ei.size(1):                              # strip the loops from the caller-visible list too (no second sync)
+        ei2, w2 = ops.remove_self_loops(ei, w, g.nnz)
+        if "tgt" in tag:
+            gnn.tag_of(ei2)["tgt"] = tag["tgt"]
+        data.edge_index, data.edge_weight = ei2, w2
     return g
 
 
@@ -106,7 +105,7 @@ class PoolingLayer(torch.nn.Module):
                 nw = _minmax(w) + _minmax((d2 / (-2)).exp())
             else:
                 raise ValueError(f"edge_weight_type {t}")
-        return dataclasses.replace(g, w=None if nw is None else nw.detach().contiguous())
+        return g.with_weight(None if nw is None else nw.detach().contiguous())
 
     # ------------------------------------------------------------------ net_util.py:76-158
     def forward(self, data, visual=False):
@@ -118,6 +117,7 @@ class PoolingLayer(torch.nn.Module):
         if g is None:            # no edges at all: every node is its own cluster at each step
             g = CSRGraph(torch.zeros(x.size(0) + 1, dtype=torch.int32, device=dev),
                          torch.empty(0, dtype=torch.int32, device=dev), x.size(0), 0, None, True)
+        empty_in = g.cap == 0
         clusts, self.trace = [], []
         op = ops.OP_MAX if self.pool_type == "max" else ops.OP_MEAN
         for step in range(self.pool_step):
@@ -126,7 +126,7 @@ class PoolingLayer(torch.nn.Module):
                 label, perm = self.forced[step].to(dev).to(torch.int32), None
             else:
                 perm = None if self.perm_fn is None else self.perm_fn(n).to(dev)   # None: random priority keys on the device
-                label, _ = ops.graclus(g, perm, use_weight=g.w is not None)
+                label, _ = ops.graclus(g, perm, use_weight=g._w is not None)
             self.trace.append((g, perm, label))
             cluster, nc = ops.relabel_clusters(label)
             clusts.append(cluster)
@@ -135,7 +135,9 @@ class PoolingLayer(torch.nn.Module):
             g = ops.pool_edges(g, cluster, mrowptr, members, nc)
             pos = None if pos is None else ops.segment_reduce(pos, mrowptr, members, nc, ops.OP_MEAN)
             edge_dual = None if edge_dual is None else cluster.long()[edge_dual]
-            if g.nnz == 0:
+            # upstream breaks here when no edge is left (net_util.py:139); continuing is equivalent (every node becomes its
+            # own cluster: identity pooling) and keeps the edge count on the device, so we only stop when it is known.
+            if empty_in or g.cap == 0:
                 break
         up = clusts[-1]
         for c in clusts[-2::-1]:
@@ -173,8 +175,8 @@ class DualFusionLayer(torch.nn.Module):
         big = max(m, n)
         g_vf = ops.csr_from_coo(ed, big, None, ops.COO_SORT_NBR | ops.COO_DEDUP)
         g_fv = ops.csr_from_coo(ed, big, None, ops.COO_BY_COL | ops.COO_SORT_NBR | ops.COO_DEDUP)
-        g_vf = dataclasses.replace(g_vf, rowptr=g_vf.rowptr[:m + 1], n=m)
-        g_fv = dataclasses.replace(g_fv, rowptr=g_fv.rowptr[:n + 1], n=n)
+        g_vf = CSRGraph(g_vf.rowptr[:m + 1], g_vf.nbr, m, g_vf.nnz)
+        g_fv = CSRGraph(g_fv.rowptr[:n + 1], g_fv.nbr, n, g_fv.nnz)
         x_v = self.fusion(data_v.x, g_vf, data_f.x)
         x_f = self.fusion(data_f.x, g_fv, data_v.x)
         x_v = F.leaky_relu(self.lin_v2(F.leaky_relu(self.lin_v1(x_v), 0.2)), 0.2)

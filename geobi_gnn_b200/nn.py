@@ -44,7 +44,7 @@ def conv_csr(edge_index: Union[torch.Tensor, CSRGraph], n: int) -> CSRGraph:
     tag = tag_of(edge_index)
     g = tag.get("tgt")
     if g is None or g.n != n:
-        g = ops.csr_from_coo(edge_index, n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+        g = ops.csr_from_coo(edge_index, n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR, sync=False)
         tag["tgt"] = g
     return g
 

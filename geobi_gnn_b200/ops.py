@@ -7,7 +7,6 @@ libgeobi.so; none has a CPU path (CPU tensors raise).
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass
 from typing import Optional
 
 import torch
@@ -53,7 +52,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 _ws_cache = {}
@@ -85,24 +84,45 @@ def _rows(x: torch.Tensor):
 
 
 # ----------------------------------------------------------------------------- graph container
-@dataclass
 class CSRGraph:
-    """int32 CSR adjacency without self loops (+ optional per-entry fp32 weight)."""
-    rowptr: torch.Tensor
-    nbr: torch.Tensor
-    n: int
-    nnz: int
-    w: Optional[torch.Tensor] = None
-    symmetric: bool = False
-    _ei: Optional[torch.Tensor] = None
+    """int32 CSR adjacency without self loops (+ optional per-entry fp32 weight).
+
+    `nbr` / `w` may be capacity-sized buffers: the exact entry count lives on the device in rowptr[n] and is only
+    copied to the host (one stream sync) when somebody asks for `.nnz` — kernels walk rows and never need it."""
+
+    def __init__(self, rowptr, nbr, n, nnz=None, w=None, symmetric=False, _ei=None):
+        self.rowptr, self._nbr, self.n, self._nnz, self._w, self.symmetric, self._ei = rowptr, nbr, n, nnz, w, symmetric, _ei
+
+    @property
+    def cap(self) -> int:
+        """Upper bound on the number of entries (buffer length)."""
+        return self._nnz if self._nnz is not None else self._nbr.numel()
+
+    @property
+    def nnz(self) -> int:
+        if self._nnz is None:
+            self._nnz = int(self.rowptr[self.n].item()) if self.n > 0 else 0      # syncs
+        return self._nnz
+
+    @property
+    def nbr(self) -> torch.Tensor:
+        return self._nbr if self._nnz is None else self._nbr[:self._nnz]
+
+    @property
+    def w(self) -> Optional[torch.Tensor]:
+        return self._w if (self._w is None or self._nnz is None) else self._w[:self._nnz]
+
+    def with_weight(self, w) -> "CSRGraph":
+        return CSRGraph(self.rowptr, self._nbr, self.n, self._nnz, w, self.symmetric, self._ei)
 
     def edge_index(self) -> torch.Tensor:
-        """int64 [2, nnz], row-major sorted when rows are sorted (coalesce layout)."""
+        """int64 [2, nnz], row-major sorted when rows are sorted (coalesce layout).  Syncs if nnz is not known yet."""
         if self._ei is None:
-            ei = torch.empty((2, self.nnz), dtype=torch.int64, device=self.rowptr.device)
-            if self.nnz:
+            nnz = self.nnz
+            ei = torch.empty((2, nnz), dtype=torch.int64, device=self.rowptr.device)
+            if nnz:
                 lib = _lib.load()
-                _lib.check(lib.geobi_csr_to_coo(_ptr(self.rowptr), _ptr(self.nbr), self.n, self.nnz, _ptr(ei), _stream()), "csr_to_coo")
+                _lib.check(lib.geobi_csr_to_coo(_ptr(self.rowptr), _ptr(self._nbr), self.n, nnz, _ptr(ei), _stream()), "csr_to_coo")
                 _count()
             self._ei = ei
         return self._ei
@@ -121,8 +141,9 @@ def exclusive_scan(v: torch.Tensor) -> torch.Tensor:
 
 
 def csr_from_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional[torch.Tensor] = None, flags: int = 0,
-                 want_eid: bool = False):
-    """COO int64 [2,E] -> CSRGraph (+ eid).  Syncs once (nnz)."""
+                 want_eid: bool = False, sync: bool = True):
+    """COO int64 [2,E] -> CSRGraph (+ eid).  sync=True reads nnz back (one stream sync) and trims the buffers;
+    sync=False leaves nnz on the device (lazy)."""
     _need_cuda(edge_index, weight)
     lib = _lib.load()
     ei = edge_index.contiguous()
@@ -140,8 +161,11 @@ def csr_from_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional[torch.
     nnz = C.c_int64(0)
     row, col = ei[0], ei[1]
     _lib.check(lib.geobi_csr_from_coo(_ptr(row), _ptr(col), _ptr(w), e, n_nodes, flags, _ptr(rowptr), _ptr(nbr), _ptr(w_out),
-                                      _ptr(eid), C.byref(nnz), _ptr(ws), ws.numel(), _stream()), "csr_from_coo")
+                                      _ptr(eid), C.byref(nnz) if sync else None, _ptr(ws), ws.numel(), _stream()), "csr_from_coo")
     _count(10)
+    if not sync:
+        g = CSRGraph(rowptr, nbr, n_nodes, None, w_out)
+        return (g, eid) if want_eid else g
     k = int(nnz.value)
     g = CSRGraph(rowptr, nbr[:k], n_nodes, k, None if w_out is None else w_out[:k])
     return (g, eid[:k]) if want_eid else g
@@ -162,11 +186,11 @@ def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor) -> CSRGraph:
                                            _stream()), "build_facet_graph")
     _count(6)
     n = int(nnz.value)
-    return CSRGraph(rowptr, nbr[:n].clone(), f, n, symmetric=True)
+    return CSRGraph(rowptr, nbr[:n].clone(), f, n, None, True)
 
 
 def graclus(g: CSRGraph, perm: Optional[torch.Tensor] = None, weight: Optional[torch.Tensor] = None, use_weight: bool = True,
-            keys: Optional[torch.Tensor] = None):
+            keys: Optional[torch.Tensor] = None, check: bool = False):
     """Exact greedy matching -> raw labels int32 [N] (= min(u, partner)).
     Visiting order: `perm` (torch_cluster's randperm semantics; rank = inverse permutation) or int32 priority `keys`
     (u before v iff (keys[u], u) < (keys[v], v)); with neither, i.i.d. random keys = a uniformly random order, no sort."""
@@ -180,14 +204,14 @@ def graclus(g: CSRGraph, perm: Optional[torch.Tensor] = None, weight: Optional[t
         rank = keys.to(torch.int32).contiguous()
     else:
         rank = torch.randint(0, 2 ** 31 - 1, (g.n,), dtype=torch.int32, device=dev)
-    w = (g.w if weight is None else weight) if use_weight else None
+    w = (g._w if weight is None else weight) if use_weight else None
     label = torch.empty(g.n, dtype=torch.int32, device=dev)
-    ws = _ws(lib.geobi_graclus_ws_bytes(g.n), dev)
-    rounds = C.c_int(0)
-    _lib.check(lib.geobi_graclus(_ptr(g.rowptr), _ptr(g.nbr), _ptr(w), _ptr(rank), g.n, _ptr(label), C.byref(rounds), _ptr(ws),
-                                 ws.numel(), _stream()), "graclus")
-    _count(2 * rounds.value)
-    return label, rounds.value
+    ws = _ws(lib.geobi_graclus_ws_bytes(g.n), dev, slot=2)
+    und = C.c_int(0)
+    _lib.check(lib.geobi_graclus(_ptr(g.rowptr), _ptr(g._nbr), _ptr(w), _ptr(rank), g.n, _ptr(label), C.byref(und) if check else None,
+                                 _ptr(ws), ws.numel(), _stream()), "graclus")
+    _count(1)
+    return label, und.value
 
 
 def relabel_clusters(label: torch.Tensor):
@@ -219,20 +243,39 @@ def group_by(cluster: torch.Tensor, n_clusters: int):
 
 
 def pool_edges(g: CSRGraph, cluster: torch.Tensor, mrowptr: torch.Tensor, members: torch.Tensor, n_clusters: int) -> CSRGraph:
-    """net_util.pool_edge on CSR.  Syncs once (nnz)."""
+    """net_util.pool_edge on CSR.  Asynchronous: the coarse nnz stays on the device (CSRGraph.nnz reads it lazily)."""
     lib = _lib.load()
     dev = g.rowptr.device
+    cap = g.cap
     out_rowptr = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
-    out_nbr = torch.empty(max(g.nnz, 1), dtype=torch.int32, device=dev)
-    out_w = None if g.w is None else torch.empty(max(g.nnz, 1), dtype=torch.float32, device=dev)
-    ws = _ws(lib.geobi_pool_edges_ws_bytes(g.nnz, n_clusters), dev)
-    nnz = C.c_int64(0)
-    _lib.check(lib.geobi_pool_edges(_ptr(g.rowptr), _ptr(g.nbr), _ptr(g.w), g.n, g.nnz, _ptr(cluster), _ptr(mrowptr), _ptr(members),
-                                    n_clusters, _ptr(out_rowptr), _ptr(out_nbr), _ptr(out_w), C.byref(nnz), _ptr(ws), ws.numel(),
+    out_nbr = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    gw = g._w
+    out_w = None if gw is None else torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+    ws = _ws(lib.geobi_pool_edges_ws_bytes(cap, n_clusters), dev)
+    _lib.check(lib.geobi_pool_edges(_ptr(g.rowptr), _ptr(g._nbr), _ptr(gw), g.n, cap, _ptr(cluster), _ptr(mrowptr), _ptr(members),
+                                    n_clusters, _ptr(out_rowptr), _ptr(out_nbr), _ptr(out_w), None, _ptr(ws), ws.numel(),
                                     _stream()), "pool_edges")
     _count(8)
-    k = int(nnz.value)
-    return CSRGraph(out_rowptr, out_nbr[:k], n_clusters, k, None if out_w is None else out_w[:k], symmetric=g.symmetric)
+    return CSRGraph(out_rowptr, out_nbr[:cap] if cap else out_nbr[:0], n_clusters, 0 if cap == 0 else None,
+                    None if out_w is None else (out_w[:cap] if cap else out_w[:0]), g.symmetric)
+
+
+def remove_self_loops(edge_index: torch.Tensor, weight: Optional[torch.Tensor], count: int):
+    """Order-preserving removal of row==col pairs when the surviving `count` is already known (no sync):
+    torch_geometric.utils.remove_self_loops (net_util.py:163)."""
+    _need_cuda(edge_index, weight)
+    lib = _lib.load()
+    ei = edge_index.contiguous().long()
+    e = ei.size(1)
+    dev = ei.device
+    out = torch.empty((2, count), dtype=torch.int64, device=dev)
+    w = None if weight is None else weight.contiguous().float()
+    w_out = None if w is None else torch.empty(count, dtype=torch.float32, device=dev)
+    ws = _ws(lib.geobi_remove_self_loops_ws_bytes(e), dev)
+    _lib.check(lib.geobi_remove_self_loops(_ptr(ei[0]), _ptr(ei[1]), _ptr(w), e, count, _ptr(out), _ptr(w_out), _ptr(ws), ws.numel(),
+                                           _stream()), "remove_self_loops")
+    _count(5)
+    return out, w_out
 
 
 # ----------------------------------------------------------------------------- segment / gather
@@ -268,8 +311,9 @@ def edge_weight_feat(x: torch.Tensor, g: CSRGraph, mode: int, param: float = 2.0
     _need_cuda(x, g.rowptr)
     lib = _lib.load()
     x, ldx, c = _rows(x)
-    w_out = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=x.device)[:g.nnz]
-    _lib.check(lib.geobi_edge_weight_feat(_ptr(x), ldx, c, _ptr(g.rowptr), _ptr(g.nbr), g.n, _ptr(w_in), mode, float(param), _ptr(w_out),
+    cap = g.cap
+    w_out = torch.empty(max(cap, 1), dtype=torch.float32, device=x.device)[:cap]
+    _lib.check(lib.geobi_edge_weight_feat(_ptr(x), ldx, c, _ptr(g.rowptr), _ptr(g._nbr), g.n, _ptr(w_in), mode, float(param), _ptr(w_out),
                                           _stream()), "edge_weight_feat")
     _count()
     return w_out
@@ -303,7 +347,7 @@ def feast_fwd(x: torch.Tensor, g: CSRGraph, W: torch.Tensor, U: torch.Tensor, c:
     if o.data_ptr() != out.data_ptr():
         raise _lib.GeobiError("feast_fwd: `out` must have contiguous rows")
     ws = _ws(lib.geobi_feast_fwd_ws_bytes(n, c_in, c_out, precision), x.device, slot=1)
-    _lib.check(lib.geobi_feast_fwd(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g.nbr), _ptr(W.contiguous()), _ptr(U.contiguous()),
+    _lib.check(lib.geobi_feast_fwd(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(W.contiguous()), _ptr(U.contiguous()),
                                    _ptr(c.contiguous()), _ptr(bias.contiguous()), c_out, float(act_slope), _ptr(o), ldo, precision,
                                    _ptr(ws), ws.numel(), _stream()), "feast_fwd")
     _count(4)

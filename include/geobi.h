@@ -83,6 +83,12 @@ GEOBI_API int geobi_csr_from_coo(const int64_t* row, const int64_t* col, const f
                        int64_t n_nodes, int flags, int32_t* rowptr, int32_t* nbr, float* w_out,
                        int64_t* eid_out, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream);
 
+/* torch_geometric.utils.remove_self_loops (net_util.py:163,292) with the surviving count already known to the caller
+ * (e.g. the nnz of a DROP_SELF CSR of the same list): order-preserving compaction into out [2,count] (+ w_out), no sync. */
+GEOBI_API size_t geobi_remove_self_loops_ws_bytes(int64_t n_edges);
+GEOBI_API int geobi_remove_self_loops(const int64_t* row, const int64_t* col, const float* w, int64_t n_edges, int64_t count,
+                                      int64_t* out, float* w_out, void* ws, size_t ws_bytes, void* stream);
+
 /* CSR -> int64 edge_index [2, nnz] (row-major sorted, the layout coalesce returns). */
 GEOBI_API int geobi_csr_to_coo(const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes, int64_t nnz,
                      int64_t* edge_index, void* stream);
@@ -95,14 +101,18 @@ GEOBI_API int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int6
                             size_t ws_bytes, void* stream);
 
 /* Heavy-edge matching identical to torch_cluster.graclus's serial CPU kernel for the visiting
- * order `perm` (net_util.py:127), computed in parallel rounds: a node acts when it
- * precedes all its undecided neighbours and also all undecided neighbours of its chosen partner.
- * rank[u] = position of u in perm (int32).  w may be NULL (unweighted: first free neighbour).
+ * order `perm` (net_util.py:127), computed in parallel: a node acts when it precedes all its
+ * undecided neighbours and also all undecided neighbours of its chosen partner, claiming the partner with a CAS.
+ * w may be NULL (unweighted: first free neighbour).
  * Adjacency must be symmetric (true for every graph on this path).  label[u] = min(u, partner).
- * SYNCS (round count is data dependent); *rounds_host optional. */
+ * rank: any int32 priority keys, u is visited before v iff (rank[u], u) < (rank[v], v) — an inverse permutation reproduces
+ * torch_cluster's order exactly, i.i.d. random keys give a uniformly random order without a sort.
+ * One launch, no grid barriers (resident threads re-evaluate their nodes until decided; the result does not depend on
+ * timing); asynchronous on the stream unless undecided_host != NULL (then SYNCS and
+ * reports nodes left undecided, 0 on success).  A label < 0 is caught by geobi_relabel_clusters (GEOBI_ERR_RANGE). */
 GEOBI_API size_t geobi_graclus_ws_bytes(int64_t n_nodes);
 GEOBI_API int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const float* w, const int32_t* rank,
-                  int64_t n_nodes, int32_t* label, int* rounds_host, void* ws, size_t ws_bytes, void* stream);
+                            int64_t n_nodes, int32_t* label, int* undecided_host, void* ws, size_t ws_bytes, void* stream);
 
 /* torch_geometric consecutive_cluster (net_util.py:128): dense relabel of labels in [0,N) by
  * ascending label value.  SYNCS: *n_clusters_host. */
