@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # level sizes vary from step to step (random matching order): let the caching allocator grow segments in place instead of
 # falling back to cudaMalloc / cudaFree (each one a device-wide sync) when a request does not fit a cached block
-os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True,roundup_power2_divisions:4")
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -44,48 +44,55 @@ def peaks():
 
 # ------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs (a thread polling every 20 ms;
+    cheaper and less intrusive than spawning nvidia-smi, same counters as the recipe's `nvidia-smi --query-gpu` line)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.stop, self.thread, self.h = index, [], threading.Event(), None, None
+        self.period = float(os.environ.get("BENCH_CLOCK_PERIOD", "0.02"))
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception:
+            self.h = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                                  nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
+                                  else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)))
+            except Exception:
+                pass
+            self.stop.wait(self.period)
 
     def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.stop.set()
+        if self.thread is not None:
             self.thread.join(timeout=2)
 
     def summary(self):
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                smax.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for nme, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
-        if not sm:
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted({name for _, r in self.rows for name, b in bits.items() if r & b})
+        return {"sm_mhz": float(np.median([c for c, _ in self.rows])), "sm_max_mhz": float(self.smax), "reasons": reasons,
+                "samples": len(self.rows), "source": "NVML, 20 ms polling during the timed region"}
 
 
 # ------------------------------------------------------------------------------------- workload

@@ -8,6 +8,7 @@
 // No per-edge tensor is written to HBM (the reference materialises [E, 9*C_out]).
 // The bf16 tensor-core projection lives in feast_tc.cu.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -242,6 +243,327 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
   }
 }
 
+// ------------------------------------------------------------------------------ packed variant: 128/C nodes per warp
+// For C in {32, 64, 128} every lane owns 4 adjacent channels (one 128-bit gather per row) and a warp carries
+// NPW = 128 / C nodes side by side: lane group g (LPN = C/4 lanes) owns node g.  The softmax pass then fills all 32 lanes
+// (group g's lanes take that node's edges) and every instruction of the accumulation loop advances NPW nodes, which
+// halves (C=64) or quarters (C=32) the instruction count per node of the one-node-per-warp version.
+template <int NPW, int OUT>
+__global__ void __launch_bounds__(256) feast_aggregate_packed_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
+                                                                     const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                                     const double* __restrict__ P, const float* __restrict__ cvec,
+                                                                     void* __restrict__ Zout, int64_t ldz) {
+  constexpr int LPN = 32 / NPW;      // lanes per node = slots per node per chunk
+  constexpr int C = 4 * LPN;
+  __shared__ __align__(16) float qs[8][32][12];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane / LPN, sl = lane % LPN;
+  const int64_t i_raw = ((int64_t)blockIdx.x * 8 + warp) * NPW + g;
+  const bool live = i_raw < N;
+  const int64_t i = live ? i_raw : N - 1;          // dead groups shadow the last node and never store
+  if (((int64_t)blockIdx.x * 8 + warp) * NPW >= N) return;   // whole warp past the end
+  const int b = rowptr[i];
+  const int total = rowptr[i + 1] - b + 1;         // neighbours + implicit self loop (slot 0)
+  int maxtotal = total;
+#pragma unroll
+  for (int o = 16; o >= LPN; o >>= 1) maxtotal = max(maxtotal, __shfl_xor_sync(0xffffffffu, maxtotal, o));
+  const unsigned ldx32 = (unsigned)ldx;
+  const int c0 = sl * 4;
+  double Pi[H];
+  float ch[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    Pi[h] = P[i * H + h];
+    ch[h] = cvec[h];
+  }
+  unsigned long long acc2[4][4];
+  float acc8[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc8[k] = 0.f;
+#pragma unroll
+    for (int p2 = 0; p2 < 4; ++p2) acc2[p2][k] = 0ull;
+  }
+
+  for (int s0 = 0; s0 < maxtotal; s0 += LPN) {
+    // lane (g, sl) handles edge slot s0 + sl of node g
+    const int s = s0 + sl;
+    int j = (int)i;
+    float l[H];
+    if (s < total) {
+      if (s > 0) j = nbr[b + s - 1];
+      float m = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+        m = fmaxf(m, l[h]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        l[h] = __expf(l[h] - m);
+        sum += l[h];
+      }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] *= inv;
+    } else {
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] = 0.f;       // padding slot: weight 0 on a valid row
+    }
+    float4* q4 = reinterpret_cast<float4*>(&qs[warp][lane][0]);
+    q4[0] = make_float4(l[0], l[1], l[2], l[3]);
+    q4[1] = make_float4(l[4], l[5], l[6], l[7]);
+    qs[warp][lane][8] = l[8];
+    __syncwarp();
+    const int cnt = min(LPN, maxtotal - s0);        // warp-uniform
+    const float* qbase = &qs[warp][g * LPN][0];
+#pragma unroll 1
+    for (int t = 0; t < cnt; t += 2) {
+      const unsigned ja = (unsigned)__shfl_sync(0xffffffffu, j, t, LPN);
+      const unsigned jb = (unsigned)__shfl_sync(0xffffffffu, j, (t + 1) & (LPN - 1), LPN);
+      const float4 xa = *reinterpret_cast<const float4*>(x + (ja * ldx32 + (unsigned)c0));
+      const float4 xb = *reinterpret_cast<const float4*>(x + (jb * ldx32 + (unsigned)c0));
+      const bool has_b = t + 1 < cnt;
+      const float* qa = qbase + t * 12;
+      const float* qb = qbase + ((t + 1) & (LPN - 1)) * 12;
+      const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(qa);
+      const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(qa + 4);
+      const float qa8 = qa[8];
+      ulonglong2 qb0 = *reinterpret_cast<const ulonglong2*>(qb);
+      ulonglong2 qb1 = *reinterpret_cast<const ulonglong2*>(qb + 4);
+      float qb8 = qb[8];
+      if (!has_b) { qb0.x = qb0.y = qb1.x = qb1.y = 0ull; qb8 = 0.f; }
+      const float xav[4] = {xa.x, xa.y, xa.z, xa.w};
+      const float xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned long long xx = pack2(xav[k], xav[k]);
+        acc2[0][k] = ffma2(qa0.x, xx, acc2[0][k]);
+        acc2[1][k] = ffma2(qa0.y, xx, acc2[1][k]);
+        acc2[2][k] = ffma2(qa1.x, xx, acc2[2][k]);
+        acc2[3][k] = ffma2(qa1.y, xx, acc2[3][k]);
+        acc8[k] = fmaf(qa8, xav[k], acc8[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned long long xx = pack2(xbv[k], xbv[k]);
+        acc2[0][k] = ffma2(qb0.x, xx, acc2[0][k]);
+        acc2[1][k] = ffma2(qb0.y, xx, acc2[1][k]);
+        acc2[2][k] = ffma2(qb1.x, xx, acc2[2][k]);
+        acc2[3][k] = ffma2(qb1.y, xx, acc2[3][k]);
+        acc8[k] = fmaf(qb8, xbv[k], acc8[k]);
+      }
+    }
+    __syncwarp();
+  }
+  if (!live) return;
+  const float rcnt = 1.0f / (float)total;
+  float z[H][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int p2 = 0; p2 < 4; ++p2) {
+      z[2 * p2][k] = lo32(acc2[p2][k]) * rcnt;
+      z[2 * p2 + 1][k] = hi32(acc2[p2][k]) * rcnt;
+    }
+    z[8][k] = acc8[k] * rcnt;
+  }
+  if (OUT == 0) {
+    float* zrow = static_cast<float*>(Zout) + i * ldz;
+#pragma unroll
+    for (int h = 0; h < H; ++h) *reinterpret_cast<float4*>(zrow + h * C + c0) = make_float4(z[h][0], z[h][1], z[h][2], z[h][3]);
+  } else {
+    __nv_bfloat16* zhi = static_cast<__nv_bfloat16*>(Zout) + i * ldz;
+    __nv_bfloat16* zlo = zhi + N * ldz;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        hi[k] = __float2bfloat16_rn(z[h][k]);
+        lo[k] = __float2bfloat16_rn(z[h][k] - __bfloat162float(hi[k]));
+      }
+      *reinterpret_cast<uint2*>(zhi + h * C + c0) = *reinterpret_cast<const uint2*>(hi);
+      if (OUT == 2) *reinterpret_cast<uint2*>(zlo + h * C + c0) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
+template <int NPW>
+static void launch_packed(int out_mode, cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
+                          const double* P, const float* c, void* Z, int64_t ldz) {
+  const unsigned blocks = (unsigned)cdiv(N, 8 * NPW);
+  if (out_mode == 0) feast_aggregate_packed_kernel<NPW, 0><<<blocks, 256, 0, st>>>(x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+  else if (out_mode == 1) feast_aggregate_packed_kernel<NPW, 1><<<blocks, 256, 0, st>>>(x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+  else feast_aggregate_packed_kernel<NPW, 2><<<blocks, 256, 0, st>>>(x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+}
+
+// ------------------------------------------------------------------------------ packed + staged variant (cp.async)
+// Packed layout as above, and the feature rows of the chunk's edges are first copied into shared memory with 16-byte
+// cp.async — every gather of the chunk in flight at once, no registers held — while the soft assignments are computed;
+// the accumulation loop then runs load-free out of shared memory.  This is what hides the gather latency: the direct
+// version keeps only two rows per warp in flight (ncu: long-scoreboard stalls dominate, issue slots < 50 % busy).
+// SLOTS = edge slots per node per chunk (<= LPN).
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <int NPW, int OUT, int SLOTS>
+__global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
+                                                                 const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                                 const double* __restrict__ P, const float* __restrict__ cvec,
+                                                                 void* __restrict__ Zout, int64_t ldz) {
+  constexpr int LPN = 32 / NPW;      // lanes per node
+  constexpr int C = 4 * LPN;
+  static_assert(SLOTS <= LPN, "one lane per edge slot in the softmax pass");
+  extern __shared__ __align__(16) float smem_f[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* xs = smem_f + (size_t)warp * (NPW * SLOTS) * C;                              // [NPW*SLOTS][C]
+  float* qs = smem_f + (size_t)8 * (NPW * SLOTS) * C + (size_t)warp * (NPW * SLOTS) * 12;  // [NPW*SLOTS][12]
+  const int g = lane / LPN, sl = lane % LPN;
+  const int64_t i_raw = ((int64_t)blockIdx.x * 8 + warp) * NPW + g;
+  if (((int64_t)blockIdx.x * 8 + warp) * NPW >= N) return;   // whole warp past the end
+  const bool live = i_raw < N;
+  const int64_t i = live ? i_raw : N - 1;          // dead groups shadow the last node and never store
+  const int b = rowptr[i];
+  const int total = rowptr[i + 1] - b + 1;         // neighbours + implicit self loop (slot 0)
+  int maxtotal = total;
+#pragma unroll
+  for (int o = 16; o >= LPN; o >>= 1) maxtotal = max(maxtotal, __shfl_xor_sync(0xffffffffu, maxtotal, o));
+  const unsigned ldx32 = (unsigned)ldx;
+  const int c0 = sl * 4;
+  double Pi[H];
+  float ch[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    Pi[h] = P[i * H + h];
+    ch[h] = cvec[h];
+  }
+  unsigned long long acc2[4][4];
+  float acc8[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc8[k] = 0.f;
+#pragma unroll
+    for (int p2 = 0; p2 < 4; ++p2) acc2[p2][k] = 0ull;
+  }
+  float* xrow = xs + (size_t)(g * SLOTS) * C + c0;   // this lane's 16-byte piece of slot 0 of its node
+  float* qrow = qs + (size_t)(g * SLOTS) * 12;
+
+  for (int s0 = 0; s0 < maxtotal; s0 += SLOTS) {
+    const int cnt = min(SLOTS, maxtotal - s0);      // warp-uniform
+    const int s = s0 + sl;
+    int j = (int)i;                                 // padding slots re-read the node's own row with weight 0
+    if (sl < SLOTS && s > 0 && s < total) j = nbr[b + s - 1];
+    // 1. launch every gather of the chunk: group g's lanes copy the LPN pieces of each of their node's rows
+    for (int t = 0; t < cnt; ++t) {
+      const unsigned jt = (unsigned)__shfl_sync(0xffffffffu, j, t, LPN);
+      cp_async_16(xrow + t * C, x + (jt * ldx32 + (unsigned)c0));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // 2. soft assignments (lane (g, sl) -> edge slot s0 + sl of node g) while the rows are in flight
+    if (sl < SLOTS) {
+      float l[H];
+      if (s < total) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+          m = fmaxf(m, l[h]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          l[h] = __expf(l[h] - m);
+          sum += l[h];
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int h = 0; h < H; ++h) l[h] *= inv;
+      } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) l[h] = 0.f;
+      }
+      float4* q4 = reinterpret_cast<float4*>(qrow + sl * 12);
+      q4[0] = make_float4(l[0], l[1], l[2], l[3]);
+      q4[1] = make_float4(l[4], l[5], l[6], l[7]);
+      qrow[sl * 12 + 8] = l[8];
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // 3. load-free accumulation out of shared memory
+#pragma unroll 2
+    for (int t = 0; t < cnt; ++t) {
+      const float4 xv = *reinterpret_cast<const float4*>(xrow + t * C);
+      const float* qt = qrow + t * 12;
+      const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(qt);
+      const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(qt + 4);
+      const float q8 = qt[8];
+      const float xe[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned long long xx = pack2(xe[k], xe[k]);
+        acc2[0][k] = ffma2(q0.x, xx, acc2[0][k]);
+        acc2[1][k] = ffma2(q0.y, xx, acc2[1][k]);
+        acc2[2][k] = ffma2(q1.x, xx, acc2[2][k]);
+        acc2[3][k] = ffma2(q1.y, xx, acc2[3][k]);
+        acc8[k] = fmaf(q8, xe[k], acc8[k]);
+      }
+    }
+    __syncwarp();
+  }
+  if (!live) return;
+  const float rcnt = 1.0f / (float)total;
+  float z[H][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int p2 = 0; p2 < 4; ++p2) {
+      z[2 * p2][k] = lo32(acc2[p2][k]) * rcnt;
+      z[2 * p2 + 1][k] = hi32(acc2[p2][k]) * rcnt;
+    }
+    z[8][k] = acc8[k] * rcnt;
+  }
+  if (OUT == 0) {
+    float* zrow = static_cast<float*>(Zout) + i * ldz;
+#pragma unroll
+    for (int h = 0; h < H; ++h) *reinterpret_cast<float4*>(zrow + h * C + c0) = make_float4(z[h][0], z[h][1], z[h][2], z[h][3]);
+  } else {
+    __nv_bfloat16* zhi = static_cast<__nv_bfloat16*>(Zout) + i * ldz;
+    __nv_bfloat16* zlo = zhi + N * ldz;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        hi[k] = __float2bfloat16_rn(z[h][k]);
+        lo[k] = __float2bfloat16_rn(z[h][k] - __bfloat162float(hi[k]));
+      }
+      *reinterpret_cast<uint2*>(zhi + h * C + c0) = *reinterpret_cast<const uint2*>(hi);
+      if (OUT == 2) *reinterpret_cast<uint2*>(zlo + h * C + c0) = *reinterpret_cast<const uint2*>(lo);
+    }
+  }
+}
+
+template <int NPW, int OUT, int SLOTS>
+static int launch_ps2(cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const double* P,
+                      const float* c, void* Z, int64_t ldz) {
+  constexpr int C = 128 / NPW;
+  const size_t smem = (size_t)8 * NPW * SLOTS * (C + 12) * sizeof(float);
+  GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_aggregate_ps_kernel<NPW, OUT, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  feast_aggregate_ps_kernel<NPW, OUT, SLOTS><<<(unsigned)cdiv(N, 8 * NPW), 256, smem, st>>>(x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+  return GEOBI_OK;
+}
+template <int NPW, int SLOTS>
+static int launch_ps(int out_mode, cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
+                     const double* P, const float* c, void* Z, int64_t ldz) {
+  if (out_mode == 0) return launch_ps2<NPW, 0, SLOTS>(st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+  if (out_mode == 1) return launch_ps2<NPW, 1, SLOTS>(st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+  return launch_ps2<NPW, 2, SLOTS>(st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+}
+
 // Wt[(h*C_in + c), o] = W[(h*C_out + o), c]
 __global__ void feast_transpose_w_kernel(const float* __restrict__ W, int C_in, int C_out, float* __restrict__ Wt) {
   const int total = H * C_in * C_out;
@@ -422,7 +744,22 @@ int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in
   // vector path: every lane's CPL-channel group is whole and 4*CPL-byte aligned in x (and in Z for the packed stores)
   const bool vec_ok = (c_in % cpl == 0) && (ldx % cpl == 0) && ((reinterpret_cast<uintptr_t>(x) % (4 * cpl)) == 0) && (ldz % cpl == 0);
   GEOBI_REQUIRE(N * ldx < ((int64_t)1 << 32), "feast_fwd: N * ldx must stay below 2^32 elements (32-bit gather offsets)");
-  if (cpl == 1) launch_aggregate<1, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);   // scalar loads are always aligned
+  // staged (cp.async) variant: whole 16-byte pieces, 32 % (C/4) == 0, lanes own whole CPL groups
+  const bool staged_ok = (c_in == 32 || c_in == 64 || c_in == 128) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                         (ldz % cpl == 0);
+  if (staged_ok && (ldz % 4 == 0)) {
+    // C=32: 4 nodes/warp, 8 slots each; C=64: 2 nodes/warp, 16 slots; C=128: 1 node/warp, 16 slots (64 KB of rows per CTA)
+    const bool direct = getenv("GEOBI_AGG_DIRECT") != nullptr;   // A/B switch for profiling
+    int rc = GEOBI_OK;
+    if (direct) {
+      if (c_in == 32) launch_packed<4>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+      else if (c_in == 64) launch_packed<2>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+      else launch_packed<1>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+    } else if (c_in == 32) rc = launch_ps<4, 8>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+    else if (c_in == 64) rc = launch_ps<2, 16>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+    else rc = launch_ps<1, 16>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+    if (rc) return rc;
+  } else if (cpl == 1) launch_aggregate<1, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);   // scalar loads are always aligned
   else if (cpl == 2 && vec_ok) launch_aggregate<2, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
   else if (cpl == 2) launch_aggregate<2, false>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
   else if (vec_ok) launch_aggregate<4, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
