@@ -30,6 +30,8 @@ import torch  # noqa: E402
 
 PATCH_FREQ = 20          # icosphere frequency -> 8000 faces per patch ("Synthetic-set shape, ~8k faces")
 N_PATCHES = 64
+PRIME_STEPS = 16         # untimed allocator-priming forwards before the W warm-up steps (see run_ours)
+print_json = None
 METRIC = "mesh faces/sec (GeoBi-GNN dual-domain forward)"
 UNIT = "faces/s"
 
@@ -172,6 +174,11 @@ def run_ours(args, rank, world, local_rank):
             ms, wall = float(t[0]), float(t[1]) / 1e3
         return ms, wall
 
+    # allocator priming: steps run back to back keep more blocks alive than synchronised ones; let the caching allocator
+    # reach its high-water mark (a handful of cudaMallocs) before the W warm-up steps so the timed region sees none
+    for _ in range(PRIME_STEPS):
+        step_resident()
+    torch.cuda.synchronize()
     for _ in range(args.warmup):
         step_resident()
     if args.profile_step:            # for `ncu --profile-from-start off`: exactly one step between cudaProfilerStart/Stop
@@ -185,7 +192,7 @@ def run_ours(args, rank, world, local_rank):
     with ClockSampler(local_rank) as clk:
         ms, wall = timed(step_resident, args.steps)
     launches = ops.launch_count() - l0
-    for _ in range(args.warmup):
+    for _ in range(PRIME_STEPS // 2 + args.warmup):
         step_e2e()
     ms_e2e, wall_e2e = timed(step_e2e, args.steps)
     d2h_bytes = sum(t.numel() * t.element_size() for t in out_host.values())
@@ -233,11 +240,12 @@ def run_ours(args, rank, world, local_rank):
                 "config": {"workload": "configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init",
                            "faces_per_gpu": faces_per_rank, "precision": args.precision,
                            "l2": "per-step working set (inputs 150 MB + >2 GB intermediates) exceeds the 126 MB L2",
-                           "timing": "CUDA events on the launch stream, max over ranks", "wall_s": round(wall, 4)},
+                           "timing": "CUDA events on the launch stream, max over ranks", "wall_s": round(wall, 4),
+                           "priming": f"{PRIME_STEPS} untimed forwards before the {args.warmup} warm-up steps (caching-allocator high-water mark)"},
                 "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": round(ms_e2e / args.steps, 4)},
                 "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        print_json(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
@@ -305,10 +313,16 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{per_step} patches x {20 * PATCH_FREQ ** 2} faces per step, {args.steps} steps"},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print_json(line)
 
 
 def main():
+    # stdout carries exactly ONE line (the JSON): anything a library prints there (e.g. "NCCL version ...") goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global print_json
+    def print_json(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

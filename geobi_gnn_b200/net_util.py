@@ -109,6 +109,10 @@ class PoolingLayer(torch.nn.Module):
 
     # ------------------------------------------------------------------ net_util.py:76-158
     def forward(self, data, visual=False):
+        with ops.size_ref(data.x.size(0)):     # size-stable allocations for everything derived from this level
+            return self._forward(data, visual)
+
+    def _forward(self, data, visual=False):
         g = self._get_edge_weight(data)
         x, pos = data.x, data.pos
         edge_dual = data.edge_dual if "edge_dual" in data else None
@@ -141,7 +145,7 @@ class PoolingLayer(torch.nn.Module):
                 break
         up = clusts[-1]
         for c in clusts[-2::-1]:
-            up = up[c.long()]
+            up = torch.index_select(up, 0, c)          # composition of the per-step maps (net_util.py:153-156)
         self._unpool_i32 = up.contiguous()
         self.unpooling_indices = up.long()
         ei = g.edge_index()

@@ -59,19 +59,19 @@ class GNNModule(nn.Module):
 
         n2 = data_r2.x.size(0)
         g2 = conv_csr(data_r2.edge_index, n2)
-        buf2 = x0.new_empty((n2, 128))                                  # [ l_conv2 | r_conv1 ]  (network.py:292 cat)
+        buf2 = ops.valloc(n2, (128,), torch.float32, x0.device, ref=n1)  # [ l_conv2 | r_conv1 ]  (network.py:292 cat)
         data_r2.x = rec("l2", self.l_conv2(data_r2.x, g2, 0.2, out=buf2[:, :64]))
         data_r3 = self.pooling2(data_r2)
         rec("p2", data_r3.x)
 
         g3 = conv_csr(data_r3.edge_index, data_r3.x.size(0))
-        data_r3.x = rec("l3", self.l_conv3(data_r3.x, g3, 0.2))
-        data_r3.x = rec("l4", self.l_conv4(data_r3.x, g3, 0.2))
-
-        up2 = self.pooling2.unpooling(data_r3.x)
-        rec("r1", self.r_conv1(up2, g2, 1.0, out=buf2[:, 64:]))         # no activation (network.py:290)
-        data_r2.x = buf2
-        data_r2.x = rec("r2", self.r_conv2(buf2, g2, 0.2))
+        with ops.size_ref(n1):                                          # coarse-level buffers: sizes stable across forwards
+            data_r3.x = rec("l3", self.l_conv3(data_r3.x, g3, 0.2))
+            data_r3.x = rec("l4", self.l_conv4(data_r3.x, g3, 0.2))
+            up2 = self.pooling2.unpooling(data_r3.x)
+            rec("r1", self.r_conv1(up2, g2, 1.0, out=buf2[:, 64:]))     # no activation (network.py:290)
+            data_r2.x = buf2
+            data_r2.x = rec("r2", self.r_conv2(buf2, g2, 0.2))
 
         up1 = self.pooling1.unpooling(data_r2.x)
         rec("r3", self.r_conv3(up1, g1, 1.0, out=buf1[:, 32:]))         # no activation (network.py:296)

@@ -72,6 +72,46 @@ def release_workspaces():
     _ws_cache.clear()
 
 
+# ----------------------------------------------------------------------------- size-stable allocation
+# Level sizes depend on the (random) matching and change by a percent or so from one forward to the next.  If every
+# intermediate were allocated at its exact size the caching allocator would keep meeting sizes it has no cached block for
+# and fall back to cudaMalloc / cudaFree (device-wide syncs: 10-300 ms spikes).  Inside `size_ref(ref)` every variable-size
+# buffer is instead carved from a capacity rounded up to ref/16 steps (never above ref), so the request sizes are the same
+# on every forward and the allocator always hits its cache.
+_REF = None
+
+
+class size_ref:
+    def __init__(self, ref: int):
+        self.ref = int(ref)
+
+    def __enter__(self):
+        global _REF
+        self.prev, _REF = _REF, self.ref
+        return self
+
+    def __exit__(self, *a):
+        global _REF
+        _REF = self.prev
+
+
+def _cap(n: int, ref) -> int:
+    if ref is None or n > ref:
+        return max(n, 1)
+    q = max(ref // 16, 1)
+    return min(max(ref, 1), -(-max(n, 1) // q) * q)
+
+
+def valloc(n: int, tail, dtype, device, ref=None) -> torch.Tensor:
+    """Uninitialised [n, *tail] tensor (contiguous) backed by a capacity-bucketed allocation (see above)."""
+    ref = _REF if ref is None else ref
+    m = 1
+    for t in tail:
+        m *= t
+    flat = torch.empty(_cap(n, ref) * m, dtype=dtype, device=device)
+    return flat[:n * m].view((n,) + tuple(tail))
+
+
 def _rows(x: torch.Tensor):
     """(tensor, ld, channels) of a 2-D fp32 tensor whose rows are contiguous (column slices allowed)."""
     if x.dim() != 2 or x.dtype != torch.float32:
@@ -119,7 +159,8 @@ class CSRGraph:
         """int64 [2, nnz], row-major sorted when rows are sorted (coalesce layout).  Syncs if nnz is not known yet."""
         if self._ei is None:
             nnz = self.nnz
-            ei = torch.empty((2, nnz), dtype=torch.int64, device=self.rowptr.device)
+            flat = torch.empty(2 * _cap(nnz, max(self._nbr.numel(), nnz)), dtype=torch.int64, device=self.rowptr.device)
+            ei = flat[:2 * nnz].view(2, nnz)
             if nnz:
                 lib = _lib.load()
                 _lib.check(lib.geobi_csr_to_coo(_ptr(self.rowptr), _ptr(self._nbr), self.n, nnz, _ptr(ei), _stream()), "csr_to_coo")
@@ -198,14 +239,16 @@ def graclus(g: CSRGraph, perm: Optional[torch.Tensor] = None, weight: Optional[t
     dev = g.rowptr.device
     _need_cuda(g.rowptr, perm, keys)
     if perm is not None:
-        rank = torch.empty(g.n, dtype=torch.int32, device=dev)
+        rank = valloc(g.n, (), torch.int32, dev)
         rank[perm.to(dev).long()] = torch.arange(g.n, dtype=torch.int32, device=dev)
     elif keys is not None:
         rank = keys.to(torch.int32).contiguous()
     else:
-        rank = torch.randint(0, 2 ** 31 - 1, (g.n,), dtype=torch.int32, device=dev)
+        rank = valloc(g.n, (), torch.int32, dev)
+        if g.n:
+            torch.randint(0, 2 ** 31 - 1, (g.n,), dtype=torch.int32, device=dev, out=rank)
     w = (g._w if weight is None else weight) if use_weight else None
-    label = torch.empty(g.n, dtype=torch.int32, device=dev)
+    label = valloc(g.n, (), torch.int32, dev)
     ws = _ws(lib.geobi_graclus_ws_bytes(g.n), dev, slot=2)
     und = C.c_int(0)
     _lib.check(lib.geobi_graclus(_ptr(g.rowptr), _ptr(g._nbr), _ptr(w), _ptr(rank), g.n, _ptr(label), C.byref(und) if check else None,
@@ -220,7 +263,7 @@ def relabel_clusters(label: torch.Tensor):
     lib = _lib.load()
     label = label.contiguous().to(torch.int32)
     n = label.numel()
-    cluster = torch.empty(n, dtype=torch.int32, device=label.device)
+    cluster = valloc(n, (), torch.int32, label.device)
     ws = _ws(lib.geobi_relabel_ws_bytes(n), label.device)
     nc = C.c_int64(0)
     _lib.check(lib.geobi_relabel_clusters(_ptr(label), n, _ptr(cluster), C.byref(nc), _ptr(ws), ws.numel(), _stream()), "relabel_clusters")
@@ -234,8 +277,8 @@ def group_by(cluster: torch.Tensor, n_clusters: int):
     cluster = cluster.contiguous().to(torch.int32)
     n = cluster.numel()
     dev = cluster.device
-    mrowptr = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
-    members = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    mrowptr = valloc(n_clusters + 1, (), torch.int32, dev)
+    members = valloc(max(n, 1), (), torch.int32, dev)
     ws = _ws(lib.geobi_group_by_ws_bytes(n, n_clusters), dev)
     _lib.check(lib.geobi_group_by(_ptr(cluster), n, n_clusters, _ptr(mrowptr), _ptr(members), _ptr(ws), ws.numel(), _stream()), "group_by")
     _count(10)
@@ -247,7 +290,7 @@ def pool_edges(g: CSRGraph, cluster: torch.Tensor, mrowptr: torch.Tensor, member
     lib = _lib.load()
     dev = g.rowptr.device
     cap = g.cap
-    out_rowptr = torch.empty(n_clusters + 1, dtype=torch.int32, device=dev)
+    out_rowptr = valloc(n_clusters + 1, (), torch.int32, dev)
     out_nbr = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
     gw = g._w
     out_w = None if gw is None else torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
@@ -286,7 +329,7 @@ def segment_reduce(x: torch.Tensor, rowptr: Optional[torch.Tensor], idx: torch.T
     x, ldx, c = _rows(x)
     idx = idx.contiguous().to(torch.int32)
     if out is None:
-        out = torch.empty((n_seg, c), dtype=torch.float32, device=x.device)
+        out = valloc(n_seg, (c,), torch.float32, x.device)
     o, ldo, _ = _rows(out)
     _lib.check(lib.geobi_segment_reduce(_ptr(x), ldx, c, _ptr(rowptr), _ptr(idx), fixed, n_seg, op, _ptr(o), ldo, _stream()), "segment_reduce")
     _count()
@@ -300,7 +343,7 @@ def gather_rows(x: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] 
     idx = idx.contiguous().to(torch.int32)
     n = idx.numel()
     if out is None:
-        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+        out = valloc(n, (c,), torch.float32, x.device)
     o, ldo, _ = _rows(out)
     _lib.check(lib.geobi_gather_rows(_ptr(x), ldx, c, _ptr(idx), n, _ptr(o), ldo, _stream()), "gather_rows")
     _count()
@@ -342,7 +385,7 @@ def feast_fwd(x: torch.Tensor, g: CSRGraph, W: torch.Tensor, U: torch.Tensor, c:
     c_out = bias.numel()
     n = x.size(0)
     if out is None:
-        out = torch.empty((n, c_out), dtype=torch.float32, device=x.device)
+        out = valloc(n, (c_out,), torch.float32, x.device)
     o, ldo, _ = _rows(out)
     if o.data_ptr() != out.data_ptr():
         raise _lib.GeobiError("feast_fwd: `out` must have contiguous rows")

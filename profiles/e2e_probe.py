@@ -4,7 +4,7 @@ import bench
 from geobi_gnn_b200 import batching, config, dataset, network
 from geobi_gnn_b200.data import Data
 config.set_precision("bf16x3")
-dev = torch.device("cuda")
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))); torch.cuda.set_device(dev)
 patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in bench.patch_meshes(bench.N_PATCHES, 0)]
 dv, df, _ = batching.collate_dual(patches)
 torch.manual_seed(0)
