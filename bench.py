@@ -30,6 +30,7 @@ import torch  # noqa: E402
 
 PATCH_FREQ = 20          # icosphere frequency -> 8000 faces per patch ("Synthetic-set shape, ~8k faces")
 N_PATCHES = 64
+TRACE = bool(os.environ.get("BENCH_TRACE"))
 PRIME_STEPS = 16         # untimed allocator-priming forwards before the W warm-up steps (see run_ours)
 print_json = None
 METRIC = "mesh faces/sec (GeoBi-GNN dual-domain forward)"
@@ -157,16 +158,36 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        import gc
+        gc.collect()
+        if not os.environ.get("BENCH_KEEP_GC"):
+            gc.disable()       # a generation-2 collection inside the timed region shows up as a 10-40 ms host stall
+        try:
+            return _timed(fn, steps)
+        finally:
+            gc.enable()
+
+    def _timed(fn, steps):
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record()
+        marks = []
         for _ in range(steps):
             fn()
+            if TRACE:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((e, time.perf_counter()))
         ev1.record()
         barrier()
         wall = time.perf_counter() - t0
         ms = ev0.elapsed_time(ev1)
+        if TRACE:
+            prev_e, prev_t = ev0, t0
+            for e, t in marks:
+                print(f"[trace rank {rank}] gpu {prev_e.elapsed_time(e):8.2f} ms  host-issue {1e3 * (t - prev_t):8.2f} ms", file=sys.stderr)
+                prev_e, prev_t = e, t
         if world > 1:
             import torch.distributed as dist
             t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)

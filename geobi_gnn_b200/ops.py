@@ -7,6 +7,7 @@ libgeobi.so; none has a CPU path (CPU tensors raise).
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional
 
 import torch
@@ -131,7 +132,10 @@ class CSRGraph:
     copied to the host (one stream sync) when somebody asks for `.nnz` — kernels walk rows and never need it."""
 
     def __init__(self, rowptr, nbr, n, nnz=None, w=None, symmetric=False, _ei=None):
-        self.rowptr, self._nbr, self.n, self._nnz, self._w, self.symmetric, self._ei = rowptr, nbr, n, nnz, w, symmetric, _ei
+        self.rowptr, self._nbr, self.n, self._nnz, self._w, self.symmetric = rowptr, nbr, n, nnz, w, symmetric
+        # weak: the edge_index tensor carries this graph in its tag (nn.tag_of); a strong back-reference would be a cycle
+        # that only the cyclic GC frees, i.e. hundreds of MB per forward released late and in bursts
+        self._ei_ref = None if _ei is None else weakref.ref(_ei)
 
     @property
     def cap(self) -> int:
@@ -153,11 +157,12 @@ class CSRGraph:
         return self._w if (self._w is None or self._nnz is None) else self._w[:self._nnz]
 
     def with_weight(self, w) -> "CSRGraph":
-        return CSRGraph(self.rowptr, self._nbr, self.n, self._nnz, w, self.symmetric, self._ei)
+        return CSRGraph(self.rowptr, self._nbr, self.n, self._nnz, w, self.symmetric, self._ei_ref() if self._ei_ref else None)
 
     def edge_index(self) -> torch.Tensor:
         """int64 [2, nnz], row-major sorted when rows are sorted (coalesce layout).  Syncs if nnz is not known yet."""
-        if self._ei is None:
+        ei = self._ei_ref() if self._ei_ref is not None else None
+        if ei is None:
             nnz = self.nnz
             flat = torch.empty(2 * _cap(nnz, max(self._nbr.numel(), nnz)), dtype=torch.int64, device=self.rowptr.device)
             ei = flat[:2 * nnz].view(2, nnz)
@@ -165,8 +170,8 @@ class CSRGraph:
                 lib = _lib.load()
                 _lib.check(lib.geobi_csr_to_coo(_ptr(self.rowptr), _ptr(self._nbr), self.n, nnz, _ptr(ei), _stream()), "csr_to_coo")
                 _count()
-            self._ei = ei
-        return self._ei
+            self._ei_ref = weakref.ref(ei)
+        return ei
 
 
 def exclusive_scan(v: torch.Tensor) -> torch.Tensor:
