@@ -1,0 +1,122 @@
+"""Autograd wrappers for the training step (train_dual.py:199-218).
+
+Forward passes are the same libgeobi kernels as inference.  Backward passes: the edge part of the FeaSt backward and the
+max-pool routing are libgeobi kernels (`geobi_feast_bwd_edges`, `geobi_segment_max_bwd`); the dense parts
+(dZ = g.W_flat, dW = g^T.Z, dX += dP.U, dU = dP^T.X) are plain library GEMMs (torch.matmul, fp32).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from .ops import _count, _ptr, _rows, _stream
+
+H = 9
+
+
+def feast_aggregate(x, g, U, c):
+    """(P fp64 [N,9], Z fp32 [N, 9*C_in]) of the forward."""
+    lib = _lib.load()
+    x, ldx, c_in = _rows(x)
+    n = x.size(0)
+    P = torch.empty((n, H), dtype=torch.float64, device=x.device)
+    Z = torch.empty((n, H * c_in), dtype=torch.float32, device=x.device)
+    _lib.check(lib.geobi_feast_aggregate(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(U.contiguous()), _ptr(c.contiguous()),
+                                         _ptr(P), _ptr(Z), _stream()), "feast_aggregate")
+    _count(2)
+    return P, Z
+
+
+def feast_bwd_edges(x, g, P, c, dZ):
+    lib = _lib.load()
+    x, ldx, c_in = _rows(x)
+    n = x.size(0)
+    dx = torch.zeros((n, c_in), dtype=torch.float32, device=x.device)
+    dP = torch.zeros((n, H), dtype=torch.float32, device=x.device)
+    dc = torch.zeros(H, dtype=torch.float32, device=x.device)
+    _lib.check(lib.geobi_feast_bwd_edges(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(P), _ptr(c.contiguous()),
+                                         _ptr(dZ.contiguous()), _ptr(dx), c_in, _ptr(dP), _ptr(dc), _stream()), "feast_bwd_edges")
+    _count()
+    return dx, dP, dc
+
+
+class FeaStFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, U, c, bias, g, act_slope, precision):
+        out = ops.feast_fwd(x.detach(), g, W.detach(), U.detach(), c.detach(), bias.detach(), act_slope=act_slope, precision=precision)
+        ctx.save_for_backward(x, W, U, c, out)
+        ctx.g, ctx.slope = g, act_slope
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, W, U, c, out = ctx.saved_tensors
+        g, slope = ctx.g, ctx.slope
+        c_in, c_out = x.size(1), out.size(1)
+        gpre = go if slope == 1.0 else go * torch.where(out > 0, 1.0, slope)   # leaky_relu keeps the sign of its input
+        gpre = gpre.contiguous()
+        dbias = gpre.sum(0)
+        P, Z = feast_aggregate(x, g, U, c)
+        Wf = W.view(H, c_out, c_in).permute(1, 0, 2).reshape(c_out, H * c_in)
+        dW = (gpre.t() @ Z).view(c_out, H, c_in).permute(1, 0, 2).reshape(H * c_out, c_in)
+        dZ = gpre @ Wf
+        dx, dP, dc = feast_bwd_edges(x, g, P, c, dZ)
+        dx = dx + dP @ U
+        dU = dP.t() @ x
+        return dx, dW, dU, dc, dbias, None, None, None
+
+
+class SegmentMaxFn(torch.autograd.Function):
+    """scatter(x, cluster, reduce='max') through the cluster-member CSR."""
+
+    @staticmethod
+    def forward(ctx, x, mrowptr, members, n_seg):
+        out = ops.segment_reduce(x.detach(), mrowptr, members, n_seg, ops.OP_MAX)
+        ctx.save_for_backward(x, mrowptr, members)
+        ctx.n_seg = n_seg
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        x, mrowptr, members = ctx.saved_tensors
+        lib = _lib.load()
+        xr, ldx, c = _rows(x)
+        go = go.contiguous()
+        dx = torch.zeros((x.size(0), c), dtype=torch.float32, device=x.device)
+        _lib.check(lib.geobi_segment_max_bwd(_ptr(xr), ldx, c, _ptr(mrowptr), _ptr(members), ctx.n_seg, _ptr(go), c, _ptr(dx), c,
+                                             _stream()), "segment_max_bwd")
+        _count()
+        return dx, None, None, None
+
+
+class SegmentMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mrowptr, members, n_seg, cluster):
+        out = ops.segment_reduce(x.detach(), mrowptr, members, n_seg, ops.OP_MEAN)
+        ctx.save_for_backward(mrowptr, cluster)
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        mrowptr, cluster = ctx.saved_tensors
+        cnt = (mrowptr[1:] - mrowptr[:-1]).clamp(min=1).to(go.dtype)
+        return (go / cnt.unsqueeze(1))[cluster.long()], None, None, None, None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """x[idx] (PoolingLayer.unpooling); backward = scatter-add."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = x.size(0)
+        return ops.gather_rows(x.detach(), idx)
+
+    @staticmethod
+    def backward(ctx, go):
+        (idx,) = ctx.saved_tensors
+        dx = torch.zeros((ctx.n, go.size(1)), dtype=go.dtype, device=go.device)
+        dx.index_add_(0, idx.long(), go)
+        return dx, None

@@ -76,7 +76,7 @@ class PoolingLayer(torch.nn.Module):
         g = _match_csr(data)
         if g is None:
             return None
-        t, x, w = self.edge_weight_type, data.x, g.w
+        t, x, w = self.edge_weight_type, data.x.detach(), g.w
         if t == -1:
             nw = None
         elif t == 0:
@@ -135,7 +135,11 @@ class PoolingLayer(torch.nn.Module):
             cluster, nc = ops.relabel_clusters(label)
             clusts.append(cluster)
             mrowptr, members = ops.group_by(cluster, nc)
-            x = ops.segment_reduce(x, mrowptr, members, nc, op)
+            if torch.is_grad_enabled() and x.requires_grad:
+                from .autograd import SegmentMaxFn, SegmentMeanFn
+                x = SegmentMaxFn.apply(x, mrowptr, members, nc) if op == ops.OP_MAX else SegmentMeanFn.apply(x, mrowptr, members, nc, cluster)
+            else:
+                x = ops.segment_reduce(x, mrowptr, members, nc, op)
             g = ops.pool_edges(g, cluster, mrowptr, members, nc)
             pos = None if pos is None else ops.segment_reduce(pos, mrowptr, members, nc, ops.OP_MEAN)
             edge_dual = None if edge_dual is None else cluster.long()[edge_dual]
@@ -155,6 +159,9 @@ class PoolingLayer(torch.nn.Module):
     def unpooling(self, x, out=None):
         if self.unpooling_indices is None:
             return x
+        if torch.is_grad_enabled() and x.requires_grad:
+            from .autograd import GatherRowsFn
+            return GatherRowsFn.apply(x, self._unpool_i32)
         return ops.gather_rows(x, self._unpool_i32, out=out)
 
 

@@ -52,6 +52,8 @@ class GNNModule(nn.Module):
         x0 = data_r1.x
         n1 = x0.size(0)
         g1 = conv_csr(data_r1.edge_index, n1)
+        if torch.is_grad_enabled() and (x0.requires_grad or self.l_conv1.lin.weight.requires_grad):
+            return self._forward_train(data_r1, g1, rec)
         buf1 = x0.new_empty((n1, 64))                                   # [ l_conv1 | r_conv3 ]  (network.py:298 cat)
         data_r1.x = rec("l1", self.l_conv1(x0, g1, 0.2, out=buf1[:, :32]))
         data_r2 = self.pooling1(data_r1)
@@ -79,6 +81,26 @@ class GNNModule(nn.Module):
         return rec("r4", self.r_conv4(buf1, g1, 0.2))
 
 
+    def _forward_train(self, data_r1, g1, rec):
+        """Same wiring with autograd-tracked tensors (explicit concatenations instead of the shared output buffers)."""
+        data_r1.x = rec("l1", self.l_conv1(data_r1.x, g1, 0.2))
+        data_r2 = self.pooling1(data_r1)
+        rec("p1", data_r2.x)
+        g2 = conv_csr(data_r2.edge_index, data_r2.x.size(0))
+        data_r2.x = rec("l2", self.l_conv2(data_r2.x, g2, 0.2))
+        data_r3 = self.pooling2(data_r2)
+        rec("p2", data_r3.x)
+        g3 = conv_csr(data_r3.edge_index, data_r3.x.size(0))
+        data_r3.x = rec("l3", self.l_conv3(data_r3.x, g3, 0.2))
+        data_r3.x = rec("l4", self.l_conv4(data_r3.x, g3, 0.2))
+        up2 = rec("r1", self.r_conv1(self.pooling2.unpooling(data_r3.x), g2, 1.0))
+        data_r2.x = torch.cat((data_r2.x, up2), 1)
+        data_r2.x = rec("r2", self.r_conv2(data_r2.x, g2, 0.2))
+        up1 = rec("r3", self.r_conv3(self.pooling1.unpooling(data_r2.x), g1, 1.0))
+        data_r1.x = torch.cat((data_r1.x, up1), 1)
+        return rec("r4", self.r_conv4(data_r1.x, g1, 0.2))
+
+
 class DualGNN(nn.Module):
     """network.py:303-343."""
 
@@ -100,6 +122,8 @@ class DualGNN(nn.Module):
         if self.taps is not None:
             self.gnn_v.taps, self.gnn_f.taps = {}, {}
         g_v = self.gnn_v(data_v)
+        if torch.is_grad_enabled() and g_v.requires_grad:
+            return self._forward_train_tail(data_v, data_f, g_v, xyz)
         if self.force_depth:
             feat_v = ops.fc_head_fwd(g_v, self.fc_v1.weight, self.fc_v1.bias, self.fc_v2.weight, self.fc_v2.bias,
                                      epilogue=2, res=xyz, res2=data_v.depth_direction, precision=prec)
@@ -116,6 +140,23 @@ class DualGNN(nn.Module):
             self.taps = dict(g_v=g_v, feat_v=feat_v, xf12=xf12, g_f=g_f, v=self.gnn_v.taps, f=self.gnn_f.taps)
             self.gnn_v.taps = self.gnn_f.taps = None
         return feat_v, norm_f, None
+
+
+    def _forward_train_tail(self, data_v, data_f, g_v, xyz):
+        """Training step: heads are plain library GEMMs, the transfer is elementwise (autograd handles both)."""
+        import torch.nn.functional as F
+        feat_v = self.fc_v2(F.leaky_relu(self.fc_v1(g_v), 0.2))
+        if self.force_depth:
+            feat_v = feat_v * data_v.depth_direction
+        feat_v = feat_v + xyz
+        fv = data_f.fv_indices
+        tri = feat_v[fv]
+        cent = tri.mean(1)
+        nrm = F.normalize(torch.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], dim=1), dim=1)
+        data_f.x = torch.cat((data_f.x, cent, nrm), 1)
+        g_f = self.gnn_f(data_f)
+        feat_f = self.fc_f2(F.leaky_relu(self.fc_f1(g_f), 0.2))
+        return feat_v, F.normalize(feat_f, dim=1), None
 
 
 # ---------------------------------------------------------------- losses / metrics (network.py:347-413)

@@ -81,6 +81,12 @@ class FeaStConv(torch.nn.Module):
         if self.heads != 9:
             raise NotImplementedError("libgeobi's fused FeaSt kernel is specialised for heads=9 (network.py:258-268)")
         g = conv_csr(edge_index, x.size(0))
+        if torch.is_grad_enabled() and (x.requires_grad or self.lin.weight.requires_grad):
+            from .autograd import FeaStFn            # training step: same forward kernels + backward kernels
+            y = FeaStFn.apply(x, self.lin.weight, self.u.weight, self.c, self.bias, g, float(act_slope), config.precision_code())
+            if out is not None:
+                raise RuntimeError("FeaStConv(out=...) is an inference-only fusion; call it under torch.no_grad()")
+            return y
         return ops.feast_fwd(x, g, self.lin.weight, self.u.weight, self.c, self.bias, act_slope=act_slope, out=out,
                              precision=config.precision_code())
 

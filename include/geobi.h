@@ -184,6 +184,25 @@ GEOBI_API int geobi_feast_fwd(const float* x, int64_t ldx, int64_t n_nodes, int 
                     int c_out, float act_slope, float* out, int64_t ldo, int precision, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* ---- training step (train_dual.py:199-218): pieces of the FeaSt / pooling backward that are not plain GEMMs ---- */
+
+/* Forward intermediates for the backward pass: P = X.U^T (fp64 [N,9]) and the aggregate Z (fp32 [N, 9*C_in],
+ * Z[i, h*C_in + c] = mean_{j in N(i)+{i}} q_ijh x_j[c]).  out = act(Z . W_flat^T + b) is then a dense product. */
+GEOBI_API int geobi_feast_aggregate(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
+                                    const int32_t* nbr, const float* U, const float* c, double* P, float* Z, void* stream);
+
+/* Edge part of the FeaSt backward: given dZ [N, 9*C_in] accumulates (atomically, into zero-initialised buffers)
+ * dx [N, C_in] (gradient reaching x through the gathered rows), dP [N, 9] (gradient of the head logits' projections,
+ * fp32) and dc [9].  The caller finishes with dX += dP.U, dU = dP^T.X (PyG FeaStConv's autograd, network.py:271-299). */
+GEOBI_API int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
+                                    const int32_t* nbr, const double* P, const float* c, const float* dZ, float* dx,
+                                    int64_t lddx, float* dP, float* dc, void* stream);
+
+/* Backward of scatter(x, cluster, reduce='max') (net_util.py:134): routes g[s,:] to the arg-max member of segment s
+ * (first member on ties).  dx must be zero-initialised. */
+GEOBI_API int geobi_segment_max_bwd(const float* x, int64_t ldx, int channels, const int32_t* rowptr, const int32_t* idx,
+                                    int64_t n_seg, const float* g, int64_t ldg, float* dx, int64_t lddx, void* stream);
+
 /* Per-node linear layer on the tcgen05 tensor cores: out = act(A . W^T + bias), A fp32 [M,K] rounded to bf16
  * (split hi + lo for BF16X3), W fp32 [N,K] (nn.Linear layout), fp32 accumulation in TMEM.  Any K (zero padded to a
  * multiple of 64), N in {32,64,128,256}, out rows 16-byte aligned.  Replaces F.linear / cuBLAS sgemm for the
