@@ -1,0 +1,33 @@
+"""BASELINE.json configs[2]: one 1 003 520-face synthetic noisy mesh (icosphere n=224), full vertex + facet graph, 1 GPU.
+Times graph build, the dual-domain forward and the 60-sweep vertex update (test_dual.py:72); checks size-independent
+properties (unit normals, finite outputs, matching validity) since the CPU oracle cannot run this size in seconds."""
+import json, os, sys, time
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from geobi_gnn_b200 import batching, config, data_util, dataset, network, synth
+config.set_precision(os.environ.get("GEOBI_PRECISION", "bf16x3"))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 224
+dev = torch.device("cuda", 0); torch.cuda.set_device(dev)
+t0 = time.perf_counter(); p, f = synth.icosphere(n); pn = synth.add_normal_noise(p, f, 0.2, 0)
+mesh, clean = synth.TriMesh(pn, f), synth.TriMesh(p, f); t_host = time.perf_counter() - t0
+torch.cuda.synchronize(); t0 = time.perf_counter()
+dv, df = dataset.build_dual_data(mesh, clean, device=dev); torch.cuda.synchronize(); t_build = time.perf_counter() - t0
+torch.manual_seed(0); net = network.DualGNN().to(dev).eval()
+def step():
+    with torch.no_grad():
+        return net([batching.fresh_view(dv), batching.fresh_view(df)])
+for _ in range(6): vp, nrm, _ = step()
+torch.cuda.synchronize(); t0 = time.perf_counter()
+K = 10
+for _ in range(K): vp, nrm, _ = step()
+torch.cuda.synchronize(); t_fwd = (time.perf_counter() - t0) / K
+fv = torch.from_numpy(mesh.fv).to(dev); vf = torch.from_numpy(mesh.vf).to(dev)
+for _ in range(2): V = data_util.update_position2(vp, fv, vf, nrm, 60)
+torch.cuda.synchronize(); t0 = time.perf_counter(); V = data_util.update_position2(vp, fv, vf, nrm, 60); torch.cuda.synchronize(); t_upd = time.perf_counter() - t0
+ok = bool(torch.isfinite(vp).all() and torch.isfinite(nrm).all() and torch.isfinite(V).all())
+unit = float((nrm.norm(dim=1) - 1).abs().max())
+F = df.x.size(0)
+print(json.dumps({"config": f"configs[2]: single {F}-face mesh (icosphere n={n}), full graphs, 1 GPU", "faces": F, "vertices": dv.x.size(0),
+                  "host_mesh_build_s": round(t_host, 2), "gpu_graph_build_ms": round(t_build * 1e3, 1), "forward_ms": round(t_fwd * 1e3, 2),
+                  "forward_faces_per_s": round(F / t_fwd, 1), "update_position2_60_ms": round(t_upd * 1e3, 2), "finite": ok,
+                  "max_abs(|n|-1)": unit, "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 2)}))
