@@ -1,0 +1,81 @@
+"""Whole-mesh inference with the reference's pipeline (test_dual.predict_one, /root/reference/code/test_dual.py:25-87):
+normalise -> (split into BFS face patches when the mesh has more than `sub_size` faces) -> per-patch dual-domain
+forward -> overlap-average stitch -> de-normalise -> 60 sweeps of the facet->vertex update.
+
+Multi-GPU: patches are dealt round-robin to ranks (`rank`, `world`), every rank runs its patches locally with no
+collective on the data path; the three accumulators are summed onto rank 0 once at the end (result collection).
+File I/O (.obj) stays outside: `mesh` is any object with OpenMesh's index arrays (synth.TriMesh).
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import batching, data_util, dataset, patches, synth
+
+
+def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device="cuda", n_iter: int = 60, rank: int = 0, world: int = 1,
+                 forced: Optional[List] = None, return_parts: bool = False):
+    """Returns (V [Nv,3] updated vertices, Np [Nf,3] unit facet normals, Vp [Nv,3] network vertices) on `device`
+    (meaningful on rank 0 when world > 1).  `forced`: per patch, the 4 pooling layers' raw label lists (tests)."""
+    dev = torch.device(device)
+    points_noisy = np.asarray(mesh.points, dtype=np.float32)
+    poolings = [net.gnn_v.pooling1, net.gnn_v.pooling2, net.gnn_f.pooling1, net.gnn_f.pooling2]
+
+    def run(dual, k):
+        if forced is not None:
+            for pl, f in zip(poolings, forced[k]):
+                pl.forced = f
+        with torch.no_grad():
+            vert_p, norm_p, _ = net([dual[0], dual[1]])
+        return vert_p, norm_p
+
+    centroid = scale = None
+    if mesh.n_faces <= sub_size:                                   # test_dual.py:44-47
+        dual = dataset.process_one_submesh(mesh, "mesh", None, dev)
+        dataset.attach_normalisation(dual, points_noisy, mesh.ev)
+        centroid, scale = dual[0].centroid, dual[0].scale
+        dual = dataset.post_processing(dual, data_type)
+        Vp, Np = run(dual, 0) if rank == 0 else (None, None)
+        n_patches = 1
+    else:                                                          # test_dual.py:49-61
+        parts = patches.split_mesh(points_noisy, mesh.fv, mesh.vf, sub_size)
+        n_patches = len(parts)
+        st = patches.Stitcher(mesh.n_vertices, mesh.n_faces, dev)
+        slot = np.full(mesh.n_vertices, -1, dtype=np.int64)
+        for k, (sel, seed) in enumerate(parts):
+            if k % world != rank:
+                continue
+            v_idx, faces = patches.get_submesh(mesh.fv, sel, _slot=slot)
+            sub = synth.TriMesh(mesh.points[v_idx], faces)
+            dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev)
+            dataset.attach_normalisation(dual, points_noisy, mesh.ev)   # centroid / scale of the WHOLE mesh (dataset.py:140,179-180)
+            centroid, scale = dual[0].centroid, dual[0].scale
+            dual = dataset.post_processing(dual, data_type)
+            vert_p, norm_p = run(dual, k)
+            st.add(vert_p, norm_p, v_idx, sel)
+        if world > 1:
+            import torch.distributed as dist
+            for t in (st.sum_v, st.vp, st.np_):
+                dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        if centroid is None:                                        # a rank that received no patch
+            centroid = torch.from_numpy(points_noisy.mean(0, keepdims=True)).to(dev)
+            q = points_noisy - points_noisy.mean(0, keepdims=True)
+            e = q[mesh.ev]
+            scale = float(1 / (((e[:, 0] - e[:, 1]) ** 2).sum(1) ** 0.5).mean())
+        Vp, Np = st.finish()
+    if forced is not None:
+        for pl in poolings:
+            pl.forced = None
+    if rank != 0:
+        return None, None, None
+    Vp = Vp / scale + centroid                                      # test_dual.py:63
+    fv = torch.from_numpy(np.ascontiguousarray(mesh.fv)).to(dev)
+    vf = torch.from_numpy(np.ascontiguousarray(mesh.vf)).to(dev)
+    depth = None
+    if data_type in ("Kinect_v1", "Kinect_v2"):
+        depth = torch.nn.functional.normalize(torch.from_numpy(points_noisy).to(dev), dim=1)
+    V = data_util.update_position2(Vp, fv, vf, Np, n_iter, depth_direction=depth)
+    return (V, Np, Vp, n_patches) if return_parts else (V, Np, Vp)

@@ -1,0 +1,109 @@
+"""Mesh splitting into face patches and stitching of per-patch predictions (host side + two small kernels).
+
+Mirrors the reference's rule exactly (dataset.py:156-193 + data_util.mesh_get_neighbor_np / get_submesh,
+data_util.py:55-84,318-336): seed = unvisited face farthest from the centroid, ring-by-ring BFS through faces sharing a
+vertex until `sub_size` faces, vertices re-indexed in order of first appearance; predictions of overlapping patches are
+averaged (test_dual.py:49-61).  The BFS runs in C++ (libgeobi_host.so) instead of Python loops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Tuple
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_HOST = None
+
+
+def _host():
+    global _HOST
+    if _HOST is None:
+        path = os.path.join(_HERE, "libgeobi_host.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `make -C geobi_gnn_b200/csrc`")
+        lib = C.CDLL(path)
+        lib.geobi_host_grow_patch.restype = C.c_int64
+        lib.geobi_host_submesh.restype = C.c_int64
+        _HOST = lib
+    return _HOST
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data)
+
+
+def mesh_get_neighbor_np(fv_indices, vf_indices, seed_idx, neighbor_count=None, ring_count=None, _taken=None):
+    """data_util.py:55-84 — list of face ids in discovery order."""
+    assert neighbor_count is not None or ring_count is not None, "'neighbor_count' and 'ring_count' are both None"
+    fv = np.ascontiguousarray(fv_indices, dtype=np.int64)
+    vf = np.ascontiguousarray(vf_indices, dtype=np.int64)
+    f = fv.shape[0]
+    big = np.iinfo(np.int64).max
+    nc = big if neighbor_count is None else int(neighbor_count)
+    rc = big if ring_count is None else int(ring_count)
+    taken = np.zeros(f, dtype=np.uint8) if _taken is None else _taken
+    out = np.empty(min(nc, f), dtype=np.int64)
+    n = _host().geobi_host_grow_patch(_p(fv), _p(vf), C.c_int64(f), C.c_int64(vf.shape[1]), C.c_int64(int(seed_idx)), C.c_int64(nc),
+                                      C.c_int64(rc), _p(taken), _p(out))
+    return out[:n]
+
+
+def get_submesh(fv_indices, select_faces, _slot=None):
+    """data_util.py:318-336 — (V_idx in first-appearance order, faces re-indexed)."""
+    fv = np.ascontiguousarray(fv_indices, dtype=np.int64)
+    sel = np.ascontiguousarray(select_faces, dtype=np.int64)
+    slot = np.full(int(fv.max()) + 1, -1, dtype=np.int64) if _slot is None else _slot
+    v_idx = np.empty(min(3 * sel.shape[0], slot.shape[0]), dtype=np.int64)
+    faces = np.empty((sel.shape[0], 3), dtype=np.int64)
+    nv = _host().geobi_host_submesh(_p(fv), _p(sel), C.c_int64(sel.shape[0]), _p(slot), _p(v_idx), _p(faces))
+    return v_idx[:nv].copy(), faces
+
+
+def split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=0) -> List[Tuple[np.ndarray, int]]:
+    """dataset.py:156-193 — [(select_faces, seed), ...]."""
+    pts = np.asarray(points, dtype=np.float32)
+    fv = np.ascontiguousarray(fv_indices, dtype=np.int64)
+    vf = np.ascontiguousarray(vf_indices, dtype=np.int64)
+    centroid = pts.mean(0, keepdims=True)
+    d2 = ((pts[fv].mean(1) - centroid) ** 2).sum(1)
+    flag = np.zeros(fv.shape[0], dtype=bool)
+    taken = np.zeros(fv.shape[0], dtype=np.uint8)
+    seed = int(np.argmax(d2))
+    patches = []
+    while True:
+        sel = mesh_get_neighbor_np(fv, vf, seed, neighbor_count=submesh_size, _taken=taken)
+        flag[sel] = True
+        if len(sel) > filter_patch_count:
+            patches.append((sel, seed))
+        left = np.where(~flag)[0]
+        if left.size == 0:
+            break
+        seed = int(left[np.argmax(d2[left])])
+    return patches
+
+
+class Stitcher:
+    """Accumulates patch predictions into whole-mesh arrays and averages (test_dual.py:49-61)."""
+
+    def __init__(self, n_vertices, n_faces, device):
+        self.sum_v = torch.zeros((n_vertices, 1), dtype=torch.float32, device=device)
+        self.vp = torch.zeros((n_vertices, 3), dtype=torch.float32, device=device)
+        self.np_ = torch.zeros((n_faces, 3), dtype=torch.float32, device=device)
+
+    def add(self, vert_p, norm_p, v_idx, f_idx):
+        # indices are unique inside a patch, so these are plain scatters (index_add_ = one elementwise kernel each)
+        v_idx, f_idx = torch.as_tensor(v_idx, device=self.vp.device), torch.as_tensor(f_idx, device=self.vp.device)
+        self.sum_v.index_add_(0, v_idx, torch.ones((v_idx.numel(), 1), device=self.vp.device))
+        self.vp.index_add_(0, v_idx, vert_p)
+        self.np_.index_add_(0, f_idx, norm_p)
+
+    def merge(self, other_sum_v, other_vp, other_np):
+        self.sum_v += other_sum_v
+        self.vp += other_vp
+        self.np_ += other_np
+
+    def finish(self):
+        return self.vp / self.sum_v, torch.nn.functional.normalize(self.np_, dim=1)
