@@ -734,6 +734,13 @@ static void launch_aggregate(int out_mode, unsigned blocks, cudaStream_t st, con
   else feast_aggregate_kernel<CPL, 2, VEC><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
 }
 
+int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const float* U, double* P, cudaStream_t st) {
+  const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
+  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, P);
+  GEOBI_LAUNCH_OK("feast_project");
+  return GEOBI_OK;
+}
+
 int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
                                 const float* c, double* P, void* Z, int64_t ldz, int out_mode, cudaStream_t st) {
   const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
@@ -772,6 +779,9 @@ int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t
                  const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo, int passes, void* ws,
                  size_t ws_bytes, cudaStream_t st);  // feast_tc.cu
 size_t feast_fwd_tc_ws_bytes(int64_t N, int c_in, int c_out);
+bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t N);   // feast_fused.cu
+int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
+                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
                    int64_t ldo, cudaStream_t st);
@@ -797,6 +807,8 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   GEOBI_REQUIRE(ldx >= c_in && ldo >= c_out, "feast_fwd: leading dimension smaller than channel count");
   GEOBI_REQUIRE(precision >= GEOBI_PREC_FP32 && precision <= GEOBI_PREC_BF16X3, "feast_fwd: unknown precision %d", precision);
   if (N == 0) return GEOBI_OK;
+  if (precision == GEOBI_PREC_BF16X3 && feast_fused_supported(c_in, c_out, ldx, ldo, x, N) && getenv("GEOBI_NO_FUSED") == nullptr)
+    return feast_fwd_fused(x, ldx, N, rowptr, nbr, W, U, c, bias, act_slope, out, ldo, ws, ws_bytes, st);
   if (precision != GEOBI_PREC_FP32)
     return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, W, U, c, bias, c_out, act_slope, out, ldo, precision == GEOBI_PREC_BF16X3 ? 3 : 1, ws,
                         ws_bytes, st);

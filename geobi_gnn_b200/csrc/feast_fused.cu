@@ -1,0 +1,322 @@
+// Fused FeaSt convolution, C_in = 64 -> C_out = 32 (r_conv3 / r_conv4 of both U-Nets, network.py:267-268: the two
+// largest layers of each graph): aggregation + projection + bias + leaky_relu in ONE persistent kernel.
+//
+//   per tile of 32 target nodes (16 warps x 2 nodes, lanes own 4 adjacent channels):
+//     1. aggregate Z_i[h, :] = 1/d_i sum_j q_ijh x_j in registers (same arithmetic as feast_aggregate_packed_kernel),
+//     2. write the rows, split x = hi + lo (bf16), straight into the K-major SWIZZLE_128B *B-operand* tiles in shared memory,
+//     3. one thread issues tcgen05.mma (M = 64: the weight tile W_flat[32 (+32 aliased) x 576] is the resident A operand,
+//        N = 32 nodes, 36 K-steps x 3 split passes) -> D^T[channel, node] in TMEM,
+//     4. two warps drain TMEM (+bias, leaky_relu) and write out[node, channel]; meanwhile everybody aggregates the next tile.
+//
+// Z (2.3 KB per node) never reaches HBM: per node the kernel reads 256 B of x per gathered row (L2) + 72 B of P, and writes
+// 128 B.  The unfused path writes and re-reads 2 x 2.3 KB per node (ncu: 1.12 GB written by the aggregation of one layer).
+#include "tc.cuh"
+
+namespace geobi {
+namespace fused {
+
+using namespace tc;
+
+constexpr int C_IN = 64, C_OUT = 32;
+constexpr int NT = 32;            // nodes per tile = MMA N
+constexpr int WARPS = 16;         // 2 nodes per warp
+constexpr int THREADS = WARPS * 32;
+constexpr int KB = H;             // one 64-wide K block per head
+constexpr int TILE_BYTES = 32 * 128;   // [32 rows x 128 B] of one K block (W rows = channels, Z rows = nodes)
+constexpr int PLANE_BYTES = KB * TILE_BYTES;
+constexpr int SMEM_BYTES = 4 * PLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * 32 * 12 * 4 + 1024;
+
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+__global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
+                                                                       const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                                       const double* __restrict__ P, const float* __restrict__ cvec,
+                                                                       const __nv_bfloat16* __restrict__ Wq /* hi | lo, [32][576] each */,
+                                                                       const float* __restrict__ bias, float slope, float* __restrict__ out,
+                                                                       int64_t ldo) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t mbar;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* w_hi = sm;
+  uint8_t* w_lo = sm + PLANE_BYTES;
+  uint8_t* z_hi = sm + 2 * PLANE_BYTES;
+  uint8_t* z_lo = sm + 3 * PLANE_BYTES;
+  float* qs_all = reinterpret_cast<float*>(sm + 4 * PLANE_BYTES + TILE_BYTES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* qs = qs_all + warp * 32 * 12;
+  constexpr int LPN = 16;
+  const int g = lane / LPN, sl = lane % LPN, c0 = sl * 4;
+  const int row = warp * 2 + g;              // node slot inside the tile = row of the B operand
+  const unsigned ldx32 = (unsigned)ldx;
+
+  // ---- one-time setup: barrier, TMEM, resident weight tiles
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  for (int idx = tid; idx < 2 * KB * 32 * 8; idx += THREADS) {
+    const int plane = idx / (KB * 32 * 8), rem = idx - plane * (KB * 32 * 8);
+    const int kb = rem / (32 * 8), r = (rem / 8) % 32, chk = rem % 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(Wq + (int64_t)plane * C_OUT * (KB * 64) + (int64_t)r * (KB * 64) + kb * 64 + chk * 8);
+    *reinterpret_cast<uint4*>((plane ? w_lo : w_hi) + kb * TILE_BYTES + sw128_off(r, chk)) = v;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  constexpr uint32_t idesc = make_idesc(64, NT);
+  float ch[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) ch[h] = cvec[h];
+  const float my_bias = bias[(warp & 1) * 16 + (lane & 15)];   // epilogue warps 0,1: channel = 16*quadrant + lane
+
+  const int64_t n_tiles = (N + NT - 1) / NT;
+  const int64_t t_begin = (n_tiles * blockIdx.x) / gridDim.x, t_end = (n_tiles * (blockIdx.x + 1)) / gridDim.x;
+  uint32_t mma_phase = 0;
+
+  auto epilogue = [&](int64_t tile) {
+    // warps 0 and 1 own TMEM quadrants 0 and 1; for M = 64 accumulator row r lives in lane (r % 16) + 32 * (r / 16)
+    if (warp < 2) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), v);
+      if (lane < 16) {
+        const int o = warp * 16 + lane;
+        const int64_t n0 = tile * NT;
+#pragma unroll
+        for (int col = 0; col < NT; ++col) {
+          if (n0 + col < N) {
+            float r = v[col] + my_bias;
+            r = r > 0.f ? r : r * slope;
+            out[(n0 + col) * ldo + o] = r;
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  };
+
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+    // ---------------- 1. aggregation of this warp's two nodes (registers only)
+    const int64_t i_raw = tile * NT + row;
+    const bool live = i_raw < N;
+    const int64_t i = live ? i_raw : N - 1;
+    const int b = rowptr[i];
+    const int total = rowptr[i + 1] - b + 1;
+    int maxtotal = max(total, __shfl_xor_sync(0xffffffffu, total, 16));
+    double Pi[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) Pi[h] = P[i * H + h];
+    unsigned long long acc2[4][4];
+    float acc8[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      acc8[k] = 0.f;
+#pragma unroll
+      for (int p2 = 0; p2 < 4; ++p2) acc2[p2][k] = 0ull;
+    }
+    for (int s0 = 0; s0 < maxtotal; s0 += LPN) {
+      const int s = s0 + sl;
+      int j = (int)i;
+      float l[H];
+      if (s < total) {
+        if (s > 0) j = nbr[b + s - 1];
+        float m = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+          m = fmaxf(m, l[h]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          l[h] = __expf(l[h] - m);
+          sum += l[h];
+        }
+        const float inv = 1.0f / sum;
+#pragma unroll
+        for (int h = 0; h < H; ++h) l[h] *= inv;
+      } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) l[h] = 0.f;
+      }
+      float4* q4 = reinterpret_cast<float4*>(qs + lane * 12);
+      q4[0] = make_float4(l[0], l[1], l[2], l[3]);
+      q4[1] = make_float4(l[4], l[5], l[6], l[7]);
+      qs[lane * 12 + 8] = l[8];
+      __syncwarp();
+      const int cnt = min(LPN, maxtotal - s0);
+      const float* qbase = qs + g * LPN * 12;
+#pragma unroll 1
+      for (int t = 0; t < cnt; t += 2) {
+        const unsigned ja = (unsigned)__shfl_sync(0xffffffffu, j, t, LPN);
+        const unsigned jb = (unsigned)__shfl_sync(0xffffffffu, j, (t + 1) & (LPN - 1), LPN);
+        const float4 xa = *reinterpret_cast<const float4*>(x + (ja * ldx32 + (unsigned)c0));
+        const float4 xb = *reinterpret_cast<const float4*>(x + (jb * ldx32 + (unsigned)c0));
+        const bool has_b = t + 1 < cnt;
+        const float* qa = qbase + t * 12;
+        const float* qb = qbase + ((t + 1) & (LPN - 1)) * 12;
+        const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(qa);
+        const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(qa + 4);
+        const float qa8 = qa[8];
+        ulonglong2 qb0 = *reinterpret_cast<const ulonglong2*>(qb);
+        ulonglong2 qb1 = *reinterpret_cast<const ulonglong2*>(qb + 4);
+        float qb8 = qb[8];
+        if (!has_b) { qb0.x = qb0.y = qb1.x = qb1.y = 0ull; qb8 = 0.f; }
+        const float xav[4] = {xa.x, xa.y, xa.z, xa.w};
+        const float xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned long long xx = pack2(xav[k], xav[k]);
+          acc2[0][k] = ffma2(qa0.x, xx, acc2[0][k]);
+          acc2[1][k] = ffma2(qa0.y, xx, acc2[1][k]);
+          acc2[2][k] = ffma2(qa1.x, xx, acc2[2][k]);
+          acc2[3][k] = ffma2(qa1.y, xx, acc2[3][k]);
+          acc8[k] = fmaf(qa8, xav[k], acc8[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned long long xx = pack2(xbv[k], xbv[k]);
+          acc2[0][k] = ffma2(qb0.x, xx, acc2[0][k]);
+          acc2[1][k] = ffma2(qb0.y, xx, acc2[1][k]);
+          acc2[2][k] = ffma2(qb1.x, xx, acc2[2][k]);
+          acc2[3][k] = ffma2(qb1.y, xx, acc2[3][k]);
+          acc8[k] = fmaf(qb8, xbv[k], acc8[k]);
+        }
+      }
+      __syncwarp();
+    }
+    // ---------------- 2. the previous tile's MMAs have finished reading the Z tiles; drain its accumulator
+    if (tile > t_begin) {
+      mbar_wait(&mbar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after();
+      epilogue(tile - 1);
+    }
+    // ---------------- 3. this tile's rows -> B-operand tiles (split bf16), then the MMAs
+    {
+      const float rcnt = live ? 1.0f / (float)total : 0.f;   // dead rows become zeros
+      const uint32_t off = sw128_off(row, c0 >> 3) + (uint32_t)(c0 & 7) * 2;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float4 z;
+        if (h < 8) {
+          const unsigned long long a0 = acc2[h >> 1][0], a1 = acc2[h >> 1][1], a2 = acc2[h >> 1][2], a3 = acc2[h >> 1][3];
+          z = (h & 1) ? make_float4(hi32(a0), hi32(a1), hi32(a2), hi32(a3)) : make_float4(lo32(a0), lo32(a1), lo32(a2), lo32(a3));
+        } else {
+          z = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
+        }
+        z.x *= rcnt; z.y *= rcnt; z.z *= rcnt; z.w *= rcnt;
+        uint2 hi, lo;
+        split_bf16x4(z, hi, lo);
+        *reinterpret_cast<uint2*>(z_hi + h * TILE_BYTES + off) = hi;
+        *reinterpret_cast<uint2*>(z_lo + h * TILE_BYTES + off) = lo;
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t ah = make_desc(smem_u32(w_hi + kb * TILE_BYTES)), al = make_desc(smem_u32(w_lo + kb * TILE_BYTES));
+        const uint64_t bh = make_desc(smem_u32(z_hi + kb * TILE_BYTES)), bl = make_desc(smem_u32(z_lo + kb * TILE_BYTES));
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) mma_f16(tmem_d, ah + 2 * k16, bh + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) mma_f16(tmem_d, ah + 2 * k16, bl + 2 * k16, idesc, 1u);
+#pragma unroll
+        for (int k16 = 0; k16 < 4; ++k16) mma_f16(tmem_d, al + 2 * k16, bh + 2 * k16, idesc, 1u);
+      }
+      mma_commit(&mbar);
+    }
+  }
+  if (t_end > t_begin) {
+    mbar_wait(&mbar, mma_phase);
+    tc_fence_after();
+    epilogue(t_end - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, 32);
+}
+
+}  // namespace fused
+
+// feast.cu
+int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const float* U, double* P, cudaStream_t st);
+
+struct FusedWs {
+  double* P;
+  __nv_bfloat16* Wq;
+};
+template <class C>
+static void carve_fused(C& c, int64_t N, FusedWs* out) {
+  double* P = c.template take<double>((size_t)N * tc::H);
+  __nv_bfloat16* Wq = c.template take<__nv_bfloat16>((size_t)2 * fused::C_OUT * tc::H * fused::C_IN);
+  if (out) *out = FusedWs{P, Wq};
+}
+struct NullCarverFu {
+  Sizer s;
+  template <typename T>
+  T* take(size_t n) { s.take<T>(n); return nullptr; }
+};
+
+size_t feast_fwd_fused_ws_bytes(int64_t N) {
+  NullCarverFu c;
+  carve_fused(c, N, nullptr);
+  return c.s.total();
+}
+
+namespace tc {
+int prep_weight(const float* W, int N, int K, int kpad, int mode, int c_in, __nv_bfloat16* Bq, cudaStream_t st);  // feast_tc.cu
+}
+
+bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t N) {
+  return c_in == fused::C_IN && c_out == fused::C_OUT && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+         N * ldx < ((int64_t)1 << 32) && N > 0;
+}
+
+int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
+                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < feast_fwd_fused_ws_bytes(N)) {
+    set_error("feast_fwd (fused): workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  Carver cv(ws, ws_bytes);
+  FusedWs Wk;
+  carve_fused(cv, N, &Wk);
+  const int K = tc::H * fused::C_IN;
+  int rc = tc::prep_weight(W, fused::C_OUT, K, K, 1, fused::C_IN, Wk.Wq, st);
+  if (rc) return rc;
+  rc = feast_project_only(x, ldx, N, fused::C_IN, U, Wk.P, st);
+  if (rc) return rc;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    GEOBI_CUDA_OK(cudaGetDevice(&dev));
+    GEOBI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(fused::feast_fused_64_32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
+  }
+  const int64_t n_tiles = (N + fused::NT - 1) / fused::NT;
+  const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
+  fused::feast_fused_64_32_kernel<<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, Wk.P, c, Wk.Wq, bias, act_slope, out,
+                                                                                   ldo);
+  GEOBI_LAUNCH_OK("feast_fused");
+  return GEOBI_OK;
+}
+
+}  // namespace geobi

@@ -6,111 +6,10 @@
 // tcgen05.commit -> mbarrier, accumulator read back with tcgen05.ld (32 lanes x 32 columns per warp).
 // Operands come from fp32 global memory and are rounded to bf16 on the way into shared memory, so no bf16 copy of
 // the activations ever exists in HBM.  No TMA: the A operand is produced by threads (converted / aggregated).
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tc.cuh"
 
 namespace geobi {
 namespace tc {
-
-constexpr int H = GEOBI_HEADS;
-constexpr int BM = 128;   // rows per CTA tile = TMEM lanes
-constexpr int BK = 64;    // bf16 elements per 128-byte swizzle row
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// one full warp allocates `cols` (power of two >= 32) TMEM columns; the base address lands in *slot (shared)
-__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024>>4 |
-// version=1 (bit 46) | layout SWIZZLE_128B=2 (bits 61..63).  `base` must be 1024-byte aligned; +32 B per K=16 step.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
-      "tcgen05.wait::ld.sync.aligned;"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// byte offset of the 16-byte chunk `chunk` (0..7) of row r inside a K-major SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
-  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-}
-
-__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
-  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-  uint2 u;
-  u.x = *reinterpret_cast<uint32_t*>(&lo);
-  u.y = *reinterpret_cast<uint32_t*>(&hi);
-  return u;
-}
-
-// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): |x - hi - lo| <= 2^-18 |x|.  Three MMA passes
-// (hi.hi + hi.lo + lo.hi) then reproduce an fp32 product to ~1e-6 relative ("bf16x3").
-__device__ __forceinline__ void split_bf16x4(float4 v, uint2& hi, uint2& lo) {
-  const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-  const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-  const __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-  hi.x = *reinterpret_cast<const uint32_t*>(&h0);
-  hi.y = *reinterpret_cast<const uint32_t*>(&h1);
-  lo.x = *reinterpret_cast<const uint32_t*>(&l0);
-  lo.y = *reinterpret_cast<const uint32_t*>(&l1);
-}
 
 // ------------------------------------------------------------------------------ weight preparation
 // Bq[n, k] (bf16, row stride kpad, zero padded).  mode 0: plain W[n, k];  mode 1: FeaSt lin.weight -> W_flat,
@@ -132,6 +31,12 @@ __global__ void prep_weight_kernel(const float* __restrict__ W, int N, int K, in
     Bq[t] = hi;
     Bq[total + t] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
+}
+
+int prep_weight(const float* W, int N, int K, int kpad, int mode, int c_in, __nv_bfloat16* Bq, cudaStream_t st) {
+  prep_weight_kernel<<<64, 256, 0, st>>>(W, N, K, kpad, mode, c_in, Bq);
+  GEOBI_LAUNCH_OK("prep_weight");
+  return GEOBI_OK;
 }
 
 // ------------------------------------------------------------------------------ out = act(A . Bq^T + bias)
