@@ -231,25 +231,37 @@ def run_ours(args, rank, world, local_rank):
         out = torch.empty(faces_per_rank, 32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
         prec = config.precision_code()
-        call = lambda: ops.feast_fwd(x, g, conv.lin.weight, conv.u.weight, conv.c, conv.bias, 0.2, out=out, precision=prec)
+        fused = prec == ops.PREC_BF16X3
+        call = lambda p_=prec: ops.feast_fwd(x, g, conv.lin.weight, conv.u.weight, conv.c, conv.bias, 0.2, out=out, precision=p_)
         for _ in range(3):
             call()
-        times = []
-        for _ in range(10):
-            flush.fill_(1)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            call()
-            b.record()
-            torch.cuda.synchronize()
-            times.append(a.elapsed_time(b))
-        t_ms = float(np.mean(times))
+
+        def time_calls(p_):
+            ts = []
+            for _ in range(10):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                call(p_)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.mean(ts))
+
+        t_op = time_calls(prec)                                   # whole layer: projection P + weight split + main kernel
+        t_ms = time_calls(prec | ops.FEAST_REUSE_WS) if fused else t_op   # the dominant kernel alone
         alg = feast_bytes_alg(faces_per_rank, g.nnz + faces_per_rank, 64, 32)
         peak, how = peaks()
         achieved = alg / (t_ms / 1e3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this layer from the committed ncu --set full capture
+        # (profiles/r01_ncu_full_feast_fused.csv): 227.4 MB + 51.6 MB
+        traffic = 278_922_240 if fused else None
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "kernel": "geobi_feast_fwd (facet r_conv4: N=%d, E=%d incl. self, 64->32)" % (faces_per_rank, g.nnz + faces_per_rank),
-                "alg_bytes_per_launch": alg, "ms_per_launch": round(t_ms, 4), "peak_source": how, "l2": "flushed between launches"}
+                "traffic": traffic,
+                "kernel": ("feast_fused_64_32_kernel" if fused else "geobi_feast_fwd (project + aggregate + gemm)") +
+                          " on facet r_conv4: N=%d, E=%d incl. self loops, 64->32" % (faces_per_rank, g.nnz + faces_per_rank),
+                "alg_bytes_per_launch": alg, "ms_per_launch": round(t_ms, 4), "ms_whole_layer": round(t_op, 4), "peak_source": how,
+                "l2": "flushed (256 MB write) between launches", "traffic_source": "ncu --set full, profiles/r01_ncu_full_feast_fused.csv"}
 
     cpu = cpu_baseline(sample_seconds=12.0) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 

@@ -781,7 +781,8 @@ int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t
 size_t feast_fwd_tc_ws_bytes(int64_t N, int c_in, int c_out);
 bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t N);   // feast_fused.cu
 int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
-                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
+                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws, void* ws, size_t ws_bytes,
+                    cudaStream_t st);
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
                    int64_t ldo, cudaStream_t st);
@@ -791,6 +792,7 @@ int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float
 using namespace geobi;
 
 extern "C" size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision) {
+  precision &= ~GEOBI_FEAST_REUSE_WS;
   if (precision != GEOBI_PREC_FP32) return feast_fwd_tc_ws_bytes(n_nodes, c_in, c_out);
   NullCarverF c;
   carve_feast(c, n_nodes, c_in, c_out, nullptr);
@@ -805,10 +807,13 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   GEOBI_REQUIRE(c_in >= 1 && c_in <= 128, "feast_fwd: C_in must be in 1..128 (got %d)", c_in);
   GEOBI_REQUIRE(c_out == 32 || c_out == 64 || c_out == 128, "feast_fwd: C_out must be 32, 64 or 128 (got %d)", c_out);
   GEOBI_REQUIRE(ldx >= c_in && ldo >= c_out, "feast_fwd: leading dimension smaller than channel count");
+  const bool reuse_ws = (precision & GEOBI_FEAST_REUSE_WS) != 0;
+  precision &= ~GEOBI_FEAST_REUSE_WS;
   GEOBI_REQUIRE(precision >= GEOBI_PREC_FP32 && precision <= GEOBI_PREC_BF16X3, "feast_fwd: unknown precision %d", precision);
   if (N == 0) return GEOBI_OK;
-  if (precision == GEOBI_PREC_BF16X3 && feast_fused_supported(c_in, c_out, ldx, ldo, x, N) && getenv("GEOBI_NO_FUSED") == nullptr)
-    return feast_fwd_fused(x, ldx, N, rowptr, nbr, W, U, c, bias, act_slope, out, ldo, ws, ws_bytes, st);
+  const bool fused = precision == GEOBI_PREC_BF16X3 && feast_fused_supported(c_in, c_out, ldx, ldo, x, N) && getenv("GEOBI_NO_FUSED") == nullptr;
+  GEOBI_REQUIRE(!reuse_ws || fused, "feast_fwd: GEOBI_FEAST_REUSE_WS is only defined for the fused 64->32 bf16x3 kernel");
+  if (fused) return feast_fwd_fused(x, ldx, N, rowptr, nbr, W, U, c, bias, act_slope, out, ldo, reuse_ws, ws, ws_bytes, st);
   if (precision != GEOBI_PREC_FP32)
     return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, W, U, c, bias, c_out, act_slope, out, ldo, precision == GEOBI_PREC_BF16X3 ? 3 : 1, ws,
                         ws_bytes, st);

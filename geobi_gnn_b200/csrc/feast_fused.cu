@@ -19,8 +19,8 @@ using namespace tc;
 
 constexpr int C_IN = 64, C_OUT = 32;
 constexpr int NT = 32;            // nodes per tile = MMA N
-constexpr int WARPS = 16;         // 2 nodes per warp
-constexpr int THREADS = WARPS * 32;
+constexpr int WARPS = 16;         // aggregation warps, 2 nodes each
+constexpr int THREADS = (WARPS + 1) * 32;   // + one warp that only issues the MMAs (warp specialisation)
 constexpr int KB = H;             // one 64-wide K block per head
 constexpr int TILE_BYTES = 32 * 128;   // [32 rows x 128 B] of one K block (W rows = channels, Z rows = nodes)
 constexpr int PLANE_BYTES = KB * TILE_BYTES;
@@ -36,6 +36,9 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
 }
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+// named barrier 1: the 16 aggregation warps arrive (non-blocking) when their rows are in shared memory, the MMA warp waits
+__device__ __forceinline__ void z_ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(THREADS) : "memory"); }
+__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
                                                                        const int* __restrict__ rowptr, const int* __restrict__ nbr,
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   uint8_t* z_lo = sm + 3 * PLANE_BYTES;
   float* qs_all = reinterpret_cast<float*>(sm + 4 * PLANE_BYTES + TILE_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* qs = qs_all + warp * 32 * 12;
+  float* qs = qs_all + (warp < WARPS ? warp : 0) * 32 * 12;
   constexpr int LPN = 16;
   const int g = lane / LPN, sl = lane % LPN, c0 = sl * 4;
   const int row = warp * 2 + g;              // node slot inside the tile = row of the B operand
@@ -108,13 +111,78 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     }
   };
 
+  if (warp == WARPS) {
+    const uint64_t d0 = make_desc(smem_u32(w_hi));
+    const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+    const uint32_t wh_lo = (uint32_t)d0, wl_lo = (uint32_t)make_desc(smem_u32(w_lo)), zh_lo = (uint32_t)make_desc(smem_u32(z_hi)),
+                   zl_lo = (uint32_t)make_desc(smem_u32(z_lo));
+    // ===== MMA warp: waits for a tile's rows, issues 36 K-steps x 3 split passes, commits to the mbarrier =====
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+      z_ready_wait();
+      if (lane == 0) {
+        tc_fence_after();
+        // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
+        // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
+        uint32_t ah = wh_lo, al = wl_lo, bh = zh_lo, bl = zl_lo;
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          if (kb == 0) mma_f16_first(tmem_d, ah, bh, desc_hi, idesc);
+          else mma_f16_acc(tmem_d, ah, bh, desc_hi, idesc);
+#pragma unroll
+          for (int k16 = 1; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bl + 2 * k16, desc_hi, idesc);
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+          ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += TILE_BYTES >> 4; bl += TILE_BYTES >> 4;
+        }
+        mma_commit(&mbar);
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
+  // ===== aggregation warps =====
+  // Index prefetch pipeline (breaks the rowptr -> nbr -> data dependency chain across tiles):
+  //   iteration t holds (b, total, j) of tile t, loads nbr of tile t+1 with the rowptr loaded one iteration earlier,
+  //   and loads rowptr of tile t+2.
+  auto node_of = [&](int64_t tile) -> int64_t {
+    const int64_t r = tile * NT + row;
+    return r < N ? r : N - 1;          // slots past the end shadow the last node (their rows are zeroed)
+  };
+  auto load_rowptr = [&](int64_t tile, int& b_, int& total_) {
+    if (tile < t_end) {
+      const int64_t i_ = node_of(tile);
+      b_ = rowptr[i_];
+      total_ = rowptr[i_ + 1] - b_ + 1;
+    } else {
+      b_ = 0;
+      total_ = 1;
+    }
+  };
+  auto load_first_j = [&](int64_t tile, int b_, int total_) -> int {
+    int j_ = (int)node_of(tile < t_end ? tile : t_begin);
+    if (tile < t_end && sl > 0 && sl < total_) j_ = nbr[b_ + sl - 1];
+    return j_;
+  };
+  int b_cur, total_cur, b_nxt, total_nxt, b_nx2 = 0, total_nx2 = 1;
+  load_rowptr(t_begin, b_cur, total_cur);
+  load_rowptr(t_begin + 1, b_nxt, total_nxt);
+  int j_cur = load_first_j(t_begin, b_cur, total_cur);
+  int j_nxt = 0;
+
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
     // ---------------- 1. aggregation of this warp's two nodes (registers only)
     const int64_t i_raw = tile * NT + row;
     const bool live = i_raw < N;
     const int64_t i = live ? i_raw : N - 1;
-    const int b = rowptr[i];
-    const int total = rowptr[i + 1] - b + 1;
+    const int b = b_cur;
+    const int total = total_cur;
+    // prefetch: indices of the next tiles (consumed one / two iterations from now)
+    j_nxt = load_first_j(tile + 1, b_nxt, total_nxt);
+    load_rowptr(tile + 2, b_nx2, total_nx2);
     int maxtotal = max(total, __shfl_xor_sync(0xffffffffu, total, 16));
     double Pi[H];
 #pragma unroll
@@ -130,9 +198,16 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     for (int s0 = 0; s0 < maxtotal; s0 += LPN) {
       const int s = s0 + sl;
       int j = (int)i;
+      if (s0 == 0) j = j_cur;                      // first chunk: prefetched one tile ago
+      else if (s < total) j = nbr[b + s - 1];
+      const int cnt = min(LPN, maxtotal - s0);
+      // the first pair of rows does not depend on the soft assignments: get it in flight together with the P rows
+      const unsigned j0 = (unsigned)__shfl_sync(0xffffffffu, j, 0, LPN);
+      const unsigned j1 = (unsigned)__shfl_sync(0xffffffffu, j, 1, LPN);
+      float4 xa = *reinterpret_cast<const float4*>(x + (j0 * ldx32 + (unsigned)c0));
+      float4 xb = *reinterpret_cast<const float4*>(x + (j1 * ldx32 + (unsigned)c0));
       float l[H];
       if (s < total) {
-        if (s > 0) j = nbr[b + s - 1];
         float m = -INFINITY;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
@@ -157,14 +232,18 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       q4[1] = make_float4(l[4], l[5], l[6], l[7]);
       qs[lane * 12 + 8] = l[8];
       __syncwarp();
-      const int cnt = min(LPN, maxtotal - s0);
       const float* qbase = qs + g * LPN * 12;
 #pragma unroll 1
       for (int t = 0; t < cnt; t += 2) {
-        const unsigned ja = (unsigned)__shfl_sync(0xffffffffu, j, t, LPN);
-        const unsigned jb = (unsigned)__shfl_sync(0xffffffffu, j, (t + 1) & (LPN - 1), LPN);
-        const float4 xa = *reinterpret_cast<const float4*>(x + (ja * ldx32 + (unsigned)c0));
-        const float4 xb = *reinterpret_cast<const float4*>(x + (jb * ldx32 + (unsigned)c0));
+        // software pipeline: issue the next pair's gathers before consuming the current pair
+        const int tn = t + 2;
+        const unsigned ja = (unsigned)__shfl_sync(0xffffffffu, j, tn & (LPN - 1), LPN);
+        const unsigned jb = (unsigned)__shfl_sync(0xffffffffu, j, (tn + 1) & (LPN - 1), LPN);
+        float4 xna = xa, xnb = xb;
+        if (tn < cnt) {
+          xna = *reinterpret_cast<const float4*>(x + (ja * ldx32 + (unsigned)c0));
+          xnb = *reinterpret_cast<const float4*>(x + (jb * ldx32 + (unsigned)c0));
+        }
         const bool has_b = t + 1 < cnt;
         const float* qa = qbase + t * 12;
         const float* qb = qbase + ((t + 1) & (LPN - 1)) * 12;
@@ -195,9 +274,13 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
           acc2[3][k] = ffma2(qb1.y, xx, acc2[3][k]);
           acc8[k] = fmaf(qb8, xbv[k], acc8[k]);
         }
+        xa = xna;
+        xb = xnb;
       }
       __syncwarp();
     }
+    b_cur = b_nxt; total_cur = total_nxt; j_cur = j_nxt;
+    b_nxt = b_nx2; total_nxt = total_nx2;
     // ---------------- 2. the previous tile's MMAs have finished reading the Z tiles; drain its accumulator
     if (tile > t_begin) {
       mbar_wait(&mbar, mma_phase);
@@ -227,22 +310,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll 1
-      for (int kb = 0; kb < KB; ++kb) {
-        const uint64_t ah = make_desc(smem_u32(w_hi + kb * TILE_BYTES)), al = make_desc(smem_u32(w_lo + kb * TILE_BYTES));
-        const uint64_t bh = make_desc(smem_u32(z_hi + kb * TILE_BYTES)), bl = make_desc(smem_u32(z_lo + kb * TILE_BYTES));
-#pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) mma_f16(tmem_d, ah + 2 * k16, bh + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
-#pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) mma_f16(tmem_d, ah + 2 * k16, bl + 2 * k16, idesc, 1u);
-#pragma unroll
-        for (int k16 = 0; k16 < 4; ++k16) mma_f16(tmem_d, al + 2 * k16, bh + 2 * k16, idesc, 1u);
-      }
-      mma_commit(&mbar);
-    }
+    z_ready_arrive();      // non-blocking: go on with the next tile while the MMA warp issues this one
   }
   if (t_end > t_begin) {
     mbar_wait(&mbar, mma_phase);
@@ -291,7 +359,8 @@ bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const 
 }
 
 int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
-                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws, void* ws, size_t ws_bytes,
+                    cudaStream_t st) {
   if (!ws || ws_bytes < feast_fwd_fused_ws_bytes(N)) {
     set_error("feast_fwd (fused): workspace too small");
     return GEOBI_ERR_WORKSPACE;
@@ -300,10 +369,12 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
   FusedWs Wk;
   carve_fused(cv, N, &Wk);
   const int K = tc::H * fused::C_IN;
-  int rc = tc::prep_weight(W, fused::C_OUT, K, K, 1, fused::C_IN, Wk.Wq, st);
-  if (rc) return rc;
-  rc = feast_project_only(x, ldx, N, fused::C_IN, U, Wk.P, st);
-  if (rc) return rc;
+  if (!reuse_ws) {   // P = X.U^T (fp64) and the split-bf16 weight planes; skipped when the caller re-runs on the same inputs
+    int rc = tc::prep_weight(W, fused::C_OUT, K, K, 1, fused::C_IN, Wk.Wq, st);
+    if (rc) return rc;
+    rc = feast_project_only(x, ldx, N, fused::C_IN, U, Wk.P, st);
+    if (rc) return rc;
+  }
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

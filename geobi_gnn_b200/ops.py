@@ -15,6 +15,7 @@ import torch
 from . import _lib
 
 PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+FEAST_REUSE_WS = 0x100
 COO_BY_COL, COO_DROP_SELF, COO_SORT_NBR, COO_DEDUP, COO_W_MEAN, COO_SYMMETRIZE = 1, 2, 4, 8, 16, 32
 OP_MEAN, OP_MAX, OP_SUM = 0, 1, 2
 

@@ -171,13 +171,18 @@ GEOBI_API int geobi_calc_weight(const float* pos, const float* nrm, const int64_
  * add_self_loops make it upstream).  W = lin.weight [9*C_out, C_in] (row h*C_out+o),
  * U = u.weight [9, C_in].  act_slope: 1.0 = none, 0.2 = the leaky_relu after most convs.
  * Evaluation is aggregate-first: Z[i,h,:] = sum_j q_ijh x_j, out = W_flat . Z — no per-edge
- * tensor is ever written to HBM.  Supported C_in: 1..128, C_out: multiple of 4 up to 128.
+ * tensor is ever written to HBM; for C_in=64 -> C_out=32 with BF16X3 the whole layer is ONE persistent kernel
+ * (feast_fused.cu) and Z never leaves shared memory.  Supported C_in: 1..128, C_out: multiple of 4 up to 128.
  * precision: GEOBI_PREC_FP32 (all fp32 CUDA cores; parity 1e-5), GEOBI_PREC_BF16 (projection on tcgen05
  * tensor cores, bf16 operands / fp32 accumulate, one pass) or GEOBI_PREC_BF16X3 (same, operands split
  * hi + lo, three passes: fp32-grade results from the tensor cores). */
 #define GEOBI_PREC_FP32 0
 #define GEOBI_PREC_BF16 1
 #define GEOBI_PREC_BF16X3 2   /* tcgen05 with split operands x = hi + lo (both bf16), 3 passes: ~1e-6, fp32-grade */
+/* OR-ed into `precision`: the workspace still holds P = X.U^T and the split weights of the previous call on the SAME
+ * x / U / W (fused 64->32 kernel only) — skips the two small preparation kernels; bench.py uses it to time the fused
+ * kernel alone. */
+#define GEOBI_FEAST_REUSE_WS 0x100
 GEOBI_API size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision);
 GEOBI_API int geobi_feast_fwd(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
                     const int32_t* nbr, const float* W, const float* U, const float* c, const float* bias,
