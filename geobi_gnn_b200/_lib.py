@@ -34,6 +34,8 @@ SIGNATURES = {
     "geobi_relabel_clusters": (_i32, [_p, _i64, _p, _p, _p, _sz, _p]),
     "geobi_group_by_ws_bytes": (_sz, [_i64, _i64]),
     "geobi_group_by": (_i32, [_p, _i64, _i64, _p, _p, _p, _sz, _p]),
+    "geobi_group_pairs_ws_bytes": (_sz, [_i64]),
+    "geobi_group_pairs": (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _sz, _p]),
     "geobi_pool_edges_ws_bytes": (_sz, [_i64, _i64]),
     "geobi_pool_edges": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "geobi_segment_reduce": (_i32, [_p, _i64, _i32, _p, _p, _i32, _i64, _i32, _p, _i64, _p]),

@@ -79,6 +79,41 @@ __global__ void __launch_bounds__(256) edge_weight_feat_kernel(const float* __re
   }
 }
 
+// Vectorised variant for C in {32, 64, 128}: LPE = C/4 lanes per edge (one 128-bit load each), 32/LPE edges per warp
+// instruction, log2(LPE) shuffles per edge group instead of 5 per edge.
+template <int LPE>
+__global__ void __launch_bounds__(256) edge_weight_feat_vec_kernel(const float* __restrict__ x, int64_t ldx, const int* __restrict__ rowptr,
+                                                                   const int* __restrict__ nbr, int64_t n, const float* __restrict__ w_in,
+                                                                   int mode, float param, float* __restrict__ w_out) {
+  constexpr int EPW = 32 / LPE;   // edges per warp instruction
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= n) return;
+  const int eg = lane / LPE, sl = lane % LPE;
+  const int b = rowptr[i], e = rowptr[i + 1];
+  const float4 xi = *reinterpret_cast<const float4*>(x + i * ldx + sl * 4);
+  for (int q0 = b; q0 < e; q0 += EPW) {
+    const int q = q0 + eg;
+    float d2 = 0.f;
+    if (q < e) {
+      const int64_t j = nbr[q];
+      const float4 xj = *reinterpret_cast<const float4*>(x + j * ldx + sl * 4);
+      const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z, dw = xi.w - xj.w;
+      d2 = dx * dx + dy * dy + dz * dz + dw * dw;
+    }
+#pragma unroll
+    for (int o = LPE / 2; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    if (sl == 0 && q < e) {
+      float r;
+      if (mode == 0) r = d2;
+      else if (mode == 1) r = expf(d2 / (-param));
+      else if (mode == 2) r = w_in[q] * expf(d2 / (-param));
+      else r = w_in[q] + expf(d2 / (-2.0f));
+      w_out[q] = r;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ calc_weight
 __device__ __forceinline__ float edge_l2(const float* __restrict__ pos, int64_t a, int64_t b) {
   const float dx = pos[a * 3] - pos[b * 3], dy = pos[a * 3 + 1] - pos[b * 3 + 1], dz = pos[a * 3 + 2] - pos[b * 3 + 2];
@@ -236,8 +271,13 @@ extern "C" int geobi_edge_weight_feat(const float* x, int64_t ldx, int channels,
   GEOBI_REQUIRE(mode == 0 || mode == 1 || mode == 2 || mode == 10, "edge_weight_feat: unsupported mode %d", mode);
   GEOBI_REQUIRE(!(mode == 2 || mode == 10) || w_in, "edge_weight_feat: mode %d needs w_in", mode);
   if (n_nodes == 0) return GEOBI_OK;
-  edge_weight_feat_kernel<<<(unsigned)cdiv(n_nodes * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, channels, rowptr, nbr, n_nodes,
-                                                                                                            w_in, mode, param, w_out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)cdiv(n_nodes * 32, 256);
+  const bool vec = (channels == 32 || channels == 64 || channels == 128) && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (vec && channels == 32) edge_weight_feat_vec_kernel<8><<<blocks, 256, 0, st>>>(x, ldx, rowptr, nbr, n_nodes, w_in, mode, param, w_out);
+  else if (vec && channels == 64) edge_weight_feat_vec_kernel<16><<<blocks, 256, 0, st>>>(x, ldx, rowptr, nbr, n_nodes, w_in, mode, param, w_out);
+  else if (vec) edge_weight_feat_vec_kernel<32><<<blocks, 256, 0, st>>>(x, ldx, rowptr, nbr, n_nodes, w_in, mode, param, w_out);
+  else edge_weight_feat_kernel<<<blocks, 256, 0, st>>>(x, ldx, channels, rowptr, nbr, n_nodes, w_in, mode, param, w_out);
   GEOBI_LAUNCH_OK("edge_weight_feat");
   return GEOBI_OK;
 }

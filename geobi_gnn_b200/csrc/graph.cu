@@ -657,6 +657,45 @@ __global__ void group_fill_kernel(const int* __restrict__ cluster, int64_t n, in
 }
 }  // namespace geobi
 
+namespace geobi {
+// Matchings give clusters of one or two nodes with label = min(member): the member CSR needs no sort.
+__global__ void pair_count_kernel(const int* __restrict__ label, const int* __restrict__ cluster, int64_t n, int* __restrict__ count) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  if (label[u] != (int)u) count[cluster[u]] = 2;      // the larger member marks its cluster as a pair
+}
+__global__ void pair_fill_kernel(const int* __restrict__ label, const int* __restrict__ cluster, int64_t n, const int* __restrict__ mrowptr,
+                                 int* __restrict__ members) {
+  const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  members[mrowptr[cluster[u]] + (label[u] != (int)u ? 1 : 0)] = (int)u;
+}
+__global__ void fill_ones_kernel(int* __restrict__ p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 1;
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_group_pairs_ws_bytes(int64_t n_clusters) { return align256((size_t)(n_clusters + 1) * sizeof(int)) + scan_ws_bytes(n_clusters + 1) + 256; }
+
+extern "C" int geobi_group_pairs(const int32_t* label, const int32_t* cluster, int64_t n, int64_t nc, int32_t* mrowptr, int32_t* members, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(label && cluster && mrowptr && members && n >= 0 && nc >= 0, "group_pairs: bad arguments");
+  if (ws_bytes < geobi_group_pairs_ws_bytes(nc) || !ws) { set_error("group_pairs: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  Carver c(ws, ws_bytes);
+  int* count = c.take<int>(nc + 1);
+  const size_t sb = scan_ws_bytes(nc + 1);
+  char* scan = c.take<char>(sb);
+  if (nc > 0) fill_ones_kernel<<<(unsigned)cdiv(nc, 256), 256, 0, st>>>(count, nc);
+  if (n > 0) pair_count_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(label, cluster, n, count);
+  int rc = scan_i32(count, mrowptr, nc, scan, sb, st);
+  if (rc) return rc;
+  if (n > 0) pair_fill_kernel<<<(unsigned)cdiv(n, 256), 256, 0, st>>>(label, cluster, n, mrowptr, members);
+  GEOBI_LAUNCH_OK("group_pairs");
+  return GEOBI_OK;
+}
+
 extern "C" size_t geobi_relabel_ws_bytes(int64_t n) {
   Sizer s;
   s.take<int>(n + 1);

@@ -134,7 +134,8 @@ class PoolingLayer(torch.nn.Module):
             self.trace.append((g, perm, label))
             cluster, nc = ops.relabel_clusters(label)
             clusts.append(cluster)
-            mrowptr, members = ops.group_by(cluster, nc)
+            # matcher output = clusters of one or two nodes: member CSR without a sort; arbitrary (forced) labels: general path
+            mrowptr, members = ops.group_by(cluster, nc) if self.forced is not None else ops.group_pairs(label, cluster, nc)
             if torch.is_grad_enabled() and x.requires_grad:
                 from .autograd import SegmentMaxFn, SegmentMeanFn
                 x = SegmentMaxFn.apply(x, mrowptr, members, nc) if op == ops.OP_MAX else SegmentMeanFn.apply(x, mrowptr, members, nc, cluster)

@@ -291,6 +291,21 @@ def group_by(cluster: torch.Tensor, n_clusters: int):
     return mrowptr, members[:n]
 
 
+def group_pairs(label: torch.Tensor, cluster: torch.Tensor, n_clusters: int):
+    """Member CSR for matching labels (clusters of <= 2 nodes, label = min member): no sort."""
+    _need_cuda(label, cluster)
+    lib = _lib.load()
+    n = cluster.numel()
+    dev = cluster.device
+    mrowptr = valloc(n_clusters + 1, (), torch.int32, dev)
+    members = valloc(max(n, 1), (), torch.int32, dev)
+    ws = _ws(lib.geobi_group_pairs_ws_bytes(n_clusters), dev)
+    _lib.check(lib.geobi_group_pairs(_ptr(label), _ptr(cluster), n, n_clusters, _ptr(mrowptr), _ptr(members), _ptr(ws), ws.numel(),
+                                     _stream()), "group_pairs")
+    _count(6)
+    return mrowptr, members[:n]
+
+
 def pool_edges(g: CSRGraph, cluster: torch.Tensor, mrowptr: torch.Tensor, members: torch.Tensor, n_clusters: int) -> CSRGraph:
     """net_util.pool_edge on CSR.  Asynchronous: the coarse nnz stays on the device (CSRGraph.nnz reads it lazily)."""
     lib = _lib.load()

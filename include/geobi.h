@@ -126,6 +126,12 @@ GEOBI_API size_t geobi_group_by_ws_bytes(int64_t n_nodes, int64_t n_clusters);
 GEOBI_API int geobi_group_by(const int32_t* cluster, int64_t n_nodes, int64_t n_clusters, int32_t* mrowptr,
                    int32_t* members, void* ws, size_t ws_bytes, void* stream);
 
+/* Same member CSR when the labels come from a matching (clusters of one or two nodes, label = min member, as
+ * geobi_graclus emits them): no sort, three elementwise kernels.  label = raw labels, cluster = dense ids. */
+GEOBI_API size_t geobi_group_pairs_ws_bytes(int64_t n_clusters);
+GEOBI_API int geobi_group_pairs(const int32_t* label, const int32_t* cluster, int64_t n_nodes, int64_t n_clusters,
+                                int32_t* mrowptr, int32_t* members, void* ws, size_t ws_bytes, void* stream);
+
 /* net_util.pool_edge (net_util.py:289-295): relabel by cluster, drop loops, coalesce with MEAN
  * weights; emitted directly as the coarse CSR (rows sorted by neighbour = coalesce order).
  * out capacity = nnz of the fine graph.  SYNCS if nnz_host != NULL. */
