@@ -413,6 +413,7 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 template <int NPW, int OUT, int SLOTS>
 __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
                                                                  const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                                 const int* __restrict__ row_map,
                                                                  const double* __restrict__ P, const float* __restrict__ cvec,
                                                                  void* __restrict__ Zout, int64_t ldz) {
   constexpr int LPN = 32 / NPW;      // lanes per node
@@ -434,11 +435,13 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
   for (int o = 16; o >= LPN; o >>= 1) maxtotal = max(maxtotal, __shfl_xor_sync(0xffffffffu, maxtotal, o));
   const unsigned ldx32 = (unsigned)ldx;
   const int c0 = sl * 4;
+  // row_map (PoolingLayer.unpooling fused into the conv): x and P rows of node v live at row_map[v]
+  const int i_src = row_map ? row_map[i] : (int)i;
   double Pi[H];
   float ch[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
-    Pi[h] = P[i * H + h];
+    Pi[h] = P[(int64_t)i_src * H + h];
     ch[h] = cvec[h];
   }
   unsigned long long acc2[4][4];
@@ -455,8 +458,11 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
   for (int s0 = 0; s0 < maxtotal; s0 += SLOTS) {
     const int cnt = min(SLOTS, maxtotal - s0);      // warp-uniform
     const int s = s0 + sl;
-    int j = (int)i;                                 // padding slots re-read the node's own row with weight 0
-    if (sl < SLOTS && s > 0 && s < total) j = nbr[b + s - 1];
+    int j = i_src;                                  // padding slots re-read the node's own row with weight 0
+    if (sl < SLOTS && s > 0 && s < total) {
+      j = nbr[b + s - 1];
+      if (row_map) j = row_map[j];
+    }
     // 1. launch every gather of the chunk: group g's lanes copy the LPN pieces of each of their node's rows
     for (int t = 0; t < cnt; ++t) {
       const unsigned jt = (unsigned)__shfl_sync(0xffffffffu, j, t, LPN);
@@ -548,20 +554,20 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
 }
 
 template <int NPW, int OUT, int SLOTS>
-static int launch_ps2(cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const double* P,
-                      const float* c, void* Z, int64_t ldz) {
+static int launch_ps2(cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
+                      const int32_t* row_map, const double* P, const float* c, void* Z, int64_t ldz) {
   constexpr int C = 128 / NPW;
   const size_t smem = (size_t)8 * NPW * SLOTS * (C + 12) * sizeof(float);
   GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_aggregate_ps_kernel<NPW, OUT, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  feast_aggregate_ps_kernel<NPW, OUT, SLOTS><<<(unsigned)cdiv(N, 8 * NPW), 256, smem, st>>>(x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+  feast_aggregate_ps_kernel<NPW, OUT, SLOTS><<<(unsigned)cdiv(N, 8 * NPW), 256, smem, st>>>(x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
   return GEOBI_OK;
 }
 template <int NPW, int SLOTS>
 static int launch_ps(int out_mode, cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
-                     const double* P, const float* c, void* Z, int64_t ldz) {
-  if (out_mode == 0) return launch_ps2<NPW, 0, SLOTS>(st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
-  if (out_mode == 1) return launch_ps2<NPW, 1, SLOTS>(st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
-  return launch_ps2<NPW, 2, SLOTS>(st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+                     const int32_t* row_map, const double* P, const float* c, void* Z, int64_t ldz) {
+  if (out_mode == 0) return launch_ps2<NPW, 0, SLOTS>(st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
+  if (out_mode == 1) return launch_ps2<NPW, 1, SLOTS>(st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
+  return launch_ps2<NPW, 2, SLOTS>(st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
 }
 
 // Wt[(h*C_in + c), o] = W[(h*C_out + o), c]
@@ -741,19 +747,22 @@ int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const f
   return GEOBI_OK;
 }
 
-int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
-                                const float* c, double* P, void* Z, int64_t ldz, int out_mode, cudaStream_t st) {
+int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
+                                const int32_t* row_map, int64_t n_src, const float* U, const float* c, double* P, void* Z, int64_t ldz,
+                                int out_mode, cudaStream_t st) {
   const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
-  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, P);
+  feast_project_kernel<<<(unsigned)cdiv(n_src, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, n_src, c_in, U, P);
   GEOBI_LAUNCH_OK("feast_project");
   const unsigned ab = (unsigned)cdiv(N, 8);
   const int cpl = c_in <= 32 ? 1 : (c_in <= 64 ? 2 : 4);
   // vector path: every lane's CPL-channel group is whole and 4*CPL-byte aligned in x (and in Z for the packed stores)
   const bool vec_ok = (c_in % cpl == 0) && (ldx % cpl == 0) && ((reinterpret_cast<uintptr_t>(x) % (4 * cpl)) == 0) && (ldz % cpl == 0);
-  GEOBI_REQUIRE(N * ldx < ((int64_t)1 << 32), "feast_fwd: N * ldx must stay below 2^32 elements (32-bit gather offsets)");
+  GEOBI_REQUIRE(n_src * ldx < ((int64_t)1 << 32), "feast_fwd: rows * ldx must stay below 2^32 elements (32-bit gather offsets)");
   // staged (cp.async) variant: whole 16-byte pieces, 32 % (C/4) == 0, lanes own whole CPL groups
   const bool staged_ok = (c_in == 32 || c_in == 64 || c_in == 128) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                          (ldz % cpl == 0);
+  GEOBI_REQUIRE(!row_map || (staged_ok && ldz % 4 == 0 && getenv("GEOBI_AGG_DIRECT") == nullptr),
+                "feast_fwd: row_map needs C_in in {32,64,128} and 16-byte aligned rows");
   if (staged_ok && (ldz % 4 == 0)) {
     // C=32: 4 nodes/warp, 8 slots each; C=64: 2 nodes/warp, 16 slots; C=128: 1 node/warp, 16 slots (64 KB of rows per CTA)
     const bool direct = getenv("GEOBI_AGG_DIRECT") != nullptr;   // A/B switch for profiling
@@ -762,9 +771,9 @@ int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in
       if (c_in == 32) launch_packed<4>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
       else if (c_in == 64) launch_packed<2>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
       else launch_packed<1>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
-    } else if (c_in == 32) rc = launch_ps<4, 8>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
-    else if (c_in == 64) rc = launch_ps<2, 16>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
-    else rc = launch_ps<1, 16>(out_mode, st, x, ldx, N, rowptr, nbr, P, c, Z, ldz);
+    } else if (c_in == 32) rc = launch_ps<4, 8>(out_mode, st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
+    else if (c_in == 64) rc = launch_ps<2, 16>(out_mode, st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
+    else rc = launch_ps<1, 16>(out_mode, st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
     if (rc) return rc;
   } else if (cpl == 1) launch_aggregate<1, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);   // scalar loads are always aligned
   else if (cpl == 2 && vec_ok) launch_aggregate<2, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
@@ -775,14 +784,14 @@ int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in
   return GEOBI_OK;
 }
 
-int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
-                 const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo, int passes, void* ws,
-                 size_t ws_bytes, cudaStream_t st);  // feast_tc.cu
+int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map,
+                 int64_t n_src, const float* W, const float* U, const float* c, const float* bias, int c_out, float act_slope, float* out,
+                 int64_t ldo, int passes, void* ws, size_t ws_bytes, cudaStream_t st);  // feast_tc.cu
 size_t feast_fwd_tc_ws_bytes(int64_t N, int c_in, int c_out);
 bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t N);   // feast_fused.cu
-int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
-                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws, void* ws, size_t ws_bytes,
-                    cudaStream_t st);
+int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map, int64_t n_src,
+                    const float* W, const float* U, const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
                    int64_t ldo, cudaStream_t st);
@@ -799,10 +808,12 @@ extern "C" size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out,
   return c.s.total();
 }
 
-extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* W,
-                               const float* U, const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo,
-                               int precision, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
+                               const int32_t* row_map, int64_t n_src, const float* W, const float* U, const float* c, const float* bias,
+                               int c_out, float act_slope, float* out, int64_t ldo, int precision, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!row_map) n_src = N;
+  GEOBI_REQUIRE(n_src >= 0 && (N == 0 || n_src > 0), "feast_fwd: n_src must be the row count of x when row_map is given");
   GEOBI_REQUIRE(x && rowptr && W && U && c && bias && out && N >= 0, "feast_fwd: null argument");
   GEOBI_REQUIRE(c_in >= 1 && c_in <= 128, "feast_fwd: C_in must be in 1..128 (got %d)", c_in);
   GEOBI_REQUIRE(c_out == 32 || c_out == 64 || c_out == 128, "feast_fwd: C_out must be 32, 64 or 128 (got %d)", c_out);
@@ -811,12 +822,12 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   precision &= ~GEOBI_FEAST_REUSE_WS;
   GEOBI_REQUIRE(precision >= GEOBI_PREC_FP32 && precision <= GEOBI_PREC_BF16X3, "feast_fwd: unknown precision %d", precision);
   if (N == 0) return GEOBI_OK;
-  const bool fused = precision == GEOBI_PREC_BF16X3 && feast_fused_supported(c_in, c_out, ldx, ldo, x, N) && getenv("GEOBI_NO_FUSED") == nullptr;
+  const bool fused = precision == GEOBI_PREC_BF16X3 && feast_fused_supported(c_in, c_out, ldx, ldo, x, n_src) && getenv("GEOBI_NO_FUSED") == nullptr;
   GEOBI_REQUIRE(!reuse_ws || fused, "feast_fwd: GEOBI_FEAST_REUSE_WS is only defined for the fused 64->32 bf16x3 kernel");
-  if (fused) return feast_fwd_fused(x, ldx, N, rowptr, nbr, W, U, c, bias, act_slope, out, ldo, reuse_ws, ws, ws_bytes, st);
+  if (fused) return feast_fwd_fused(x, ldx, N, rowptr, nbr, row_map, n_src, W, U, c, bias, act_slope, out, ldo, reuse_ws, ws, ws_bytes, st);
   if (precision != GEOBI_PREC_FP32)
-    return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, W, U, c, bias, c_out, act_slope, out, ldo, precision == GEOBI_PREC_BF16X3 ? 3 : 1, ws,
-                        ws_bytes, st);
+    return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, row_map, n_src, W, U, c, bias, c_out, act_slope, out, ldo,
+                        precision == GEOBI_PREC_BF16X3 ? 3 : 1, ws, ws_bytes, st);
   if (!ws || ws_bytes < geobi_feast_fwd_ws_bytes(N, c_in, c_out, precision)) {
     set_error("feast_fwd: workspace too small");
     return GEOBI_ERR_WORKSPACE;
@@ -825,7 +836,7 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   FeastWs Wk;
   carve_feast(cv, N, c_in, c_out, &Wk);
   feast_transpose_w_kernel<<<64, 256, 0, st>>>(W, c_in, c_out, Wk.Wt);
-  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, (int64_t)H * c_in, 0, st);
+  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, row_map, n_src, U, c, Wk.P, Wk.Z, (int64_t)H * c_in, 0, st);
   if (rc) return rc;
   const int K = H * c_in;
   if (c_out == 32) {

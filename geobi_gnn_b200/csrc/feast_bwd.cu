@@ -143,8 +143,9 @@ __global__ void __launch_bounds__(256) segment_max_bwd_kernel(const float* __res
   dx[(int64_t)best * lddx + c] = g[s * ldg + c];
 }
 
-int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
-                                const float* c, double* P, void* Z, int64_t ldz, int out_mode, cudaStream_t st);  // feast.cu
+int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
+                                const int32_t* row_map, int64_t n_src, const float* U, const float* c, double* P, void* Z, int64_t ldz,
+                                int out_mode, cudaStream_t st);  // feast.cu
 }  // namespace geobi
 
 using namespace geobi;
@@ -154,7 +155,7 @@ extern "C" int geobi_feast_aggregate(const float* x, int64_t ldx, int64_t N, int
                                      const float* U, const float* c, double* P, float* Z, void* stream) {
   GEOBI_REQUIRE(x && rowptr && U && c && P && Z && N >= 0 && c_in >= 1 && c_in <= 128, "feast_aggregate: bad arguments");
   if (N == 0) return GEOBI_OK;
-  return feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, P, Z, (int64_t)H * c_in, 0, static_cast<cudaStream_t>(stream));
+  return feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, nullptr, N, U, c, P, Z, (int64_t)H * c_in, 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,

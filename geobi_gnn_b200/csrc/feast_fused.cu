@@ -42,6 +42,7 @@ __device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" 
 
 __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
                                                                        const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                                       const int* __restrict__ row_map,
                                                                        const double* __restrict__ P, const float* __restrict__ cvec,
                                                                        const __nv_bfloat16* __restrict__ Wq /* hi | lo, [32][576] each */,
                                                                        const float* __restrict__ bias, float slope, float* __restrict__ out,
@@ -162,10 +163,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       total_ = 1;
     }
   };
+  // row_map (PoolingLayer.unpooling fused into the conv): x and P rows of node v live at row_map[v]
   auto load_first_j = [&](int64_t tile, int b_, int total_) -> int {
     int j_ = (int)node_of(tile < t_end ? tile : t_begin);
     if (tile < t_end && sl > 0 && sl < total_) j_ = nbr[b_ + sl - 1];
-    return j_;
+    return row_map ? row_map[j_] : j_;
   };
   int b_cur, total_cur, b_nxt, total_nxt, b_nx2 = 0, total_nx2 = 1;
   load_rowptr(t_begin, b_cur, total_cur);
@@ -184,9 +186,10 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     j_nxt = load_first_j(tile + 1, b_nxt, total_nxt);
     load_rowptr(tile + 2, b_nx2, total_nx2);
     int maxtotal = max(total, __shfl_xor_sync(0xffffffffu, total, 16));
+    const int i_src = row_map ? row_map[i] : (int)i;
     double Pi[H];
 #pragma unroll
-    for (int h = 0; h < H; ++h) Pi[h] = P[i * H + h];
+    for (int h = 0; h < H; ++h) Pi[h] = P[(int64_t)i_src * H + h];
     unsigned long long acc2[4][4];
     float acc8[4];
 #pragma unroll
@@ -197,9 +200,12 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     }
     for (int s0 = 0; s0 < maxtotal; s0 += LPN) {
       const int s = s0 + sl;
-      int j = (int)i;
+      int j = i_src;
       if (s0 == 0) j = j_cur;                      // first chunk: prefetched one tile ago
-      else if (s < total) j = nbr[b + s - 1];
+      else if (s < total) {
+        j = nbr[b + s - 1];
+        if (row_map) j = row_map[j];
+      }
       const int cnt = min(LPN, maxtotal - s0);
       // the first pair of rows does not depend on the soft assignments: get it in flight together with the P rows
       const unsigned j0 = (unsigned)__shfl_sync(0xffffffffu, j, 0, LPN);
@@ -353,26 +359,26 @@ namespace tc {
 int prep_weight(const float* W, int N, int K, int kpad, int mode, int c_in, __nv_bfloat16* Bq, cudaStream_t st);  // feast_tc.cu
 }
 
-bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t N) {
+bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t n_src) {
   return c_in == fused::C_IN && c_out == fused::C_OUT && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
-         N * ldx < ((int64_t)1 << 32) && N > 0;
+         n_src * ldx < ((int64_t)1 << 32) && n_src > 0;
 }
 
-int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
-                    const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws, void* ws, size_t ws_bytes,
-                    cudaStream_t st) {
-  if (!ws || ws_bytes < feast_fwd_fused_ws_bytes(N)) {
+int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map, int64_t n_src,
+                    const float* W, const float* U, const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!ws || ws_bytes < feast_fwd_fused_ws_bytes(n_src)) {
     set_error("feast_fwd (fused): workspace too small");
     return GEOBI_ERR_WORKSPACE;
   }
   Carver cv(ws, ws_bytes);
   FusedWs Wk;
-  carve_fused(cv, N, &Wk);
+  carve_fused(cv, n_src, &Wk);
   const int K = tc::H * fused::C_IN;
   if (!reuse_ws) {   // P = X.U^T (fp64) and the split-bf16 weight planes; skipped when the caller re-runs on the same inputs
     int rc = tc::prep_weight(W, fused::C_OUT, K, K, 1, fused::C_IN, Wk.Wq, st);
     if (rc) return rc;
-    rc = feast_project_only(x, ldx, N, fused::C_IN, U, Wk.P, st);
+    rc = feast_project_only(x, ldx, n_src, fused::C_IN, U, Wk.P, st);
     if (rc) return rc;
   }
   static int sms = 0;
@@ -384,8 +390,8 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
   }
   const int64_t n_tiles = (N + fused::NT - 1) / fused::NT;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  fused::feast_fused_64_32_kernel<<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, Wk.P, c, Wk.Wq, bias, act_slope, out,
-                                                                                   ldo);
+  fused::feast_fused_64_32_kernel<<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wq, bias, act_slope,
+                                                                                   out, ldo);
   GEOBI_LAUNCH_OK("feast_fused");
   return GEOBI_OK;
 }

@@ -341,8 +341,9 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
 
 // ------------------------------------------------------------------------------ FeaSt forward, bf16 projection
 // defined in feast.cu
-int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* U,
-                                const float* c, double* P, void* Z, int64_t ldz, int out_mode, cudaStream_t st);
+int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
+                                const int32_t* row_map, int64_t n_src, const float* U, const float* c, double* P, void* Z, int64_t ldz,
+                                int out_mode, cudaStream_t st);
 
 struct TcWs {
   double* P;
@@ -369,9 +370,9 @@ size_t feast_fwd_tc_ws_bytes(int64_t N, int c_in, int c_out) {
   return c.s.total();
 }
 
-int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const float* W, const float* U,
-                 const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo, int passes, void* ws,
-                 size_t ws_bytes, cudaStream_t st) {
+int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map,
+                 int64_t n_src, const float* W, const float* U, const float* c, const float* bias, int c_out, float act_slope, float* out,
+                 int64_t ldo, int passes, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!ws || ws_bytes < feast_fwd_tc_ws_bytes(N, c_in, c_out)) {
     set_error("feast_fwd (bf16): workspace too small");
     return GEOBI_ERR_WORKSPACE;
@@ -384,7 +385,7 @@ int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t
   const int kpad = (int)(cdiv(K, tc::BK) * tc::BK);
   if (kpad != K) GEOBI_CUDA_OK(cudaMemsetAsync(Wk.Z, 0, sizeof(__nv_bfloat16) * (size_t)(passes == 3 ? 2 : 1) * N * kpad, st));
   tc::prep_weight_kernel<<<64, 256, 0, st>>>(W, c_out, K, kpad, 1, c_in, Wk.Bq);
-  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, U, c, Wk.P, Wk.Z, kpad, passes == 3 ? 2 : 1, st);
+  int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, row_map, n_src, U, c, Wk.P, Wk.Z, kpad, passes == 3 ? 2 : 1, st);
   if (rc) return rc;
   return tc::gemm_dispatch(Wk.Z, (int64_t)N * kpad, N, kpad, Wk.Bq, c_out, bias, act_slope, out, ldo, passes, st);
 }

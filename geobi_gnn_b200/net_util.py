@@ -157,6 +157,11 @@ class PoolingLayer(torch.nn.Module):
         gnn.attach_symmetric_csr(ei, g, has_self_loops=False)
         return Data(x, ei, edge_dual=edge_dual, edge_weight=g.w, pos=pos, fv_indices=face)
 
+    @property
+    def unpool_map(self):
+        """int32 fine-node -> coarse-node map of the last forward (None: identity); FeaStConv(row_map=...) consumes it."""
+        return self._unpool_i32
+
     def unpooling(self, x, out=None):
         if self.unpooling_indices is None:
             return x

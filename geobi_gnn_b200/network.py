@@ -70,13 +70,12 @@ class GNNModule(nn.Module):
         with ops.size_ref(n1):                                          # coarse-level buffers: sizes stable across forwards
             data_r3.x = rec("l3", self.l_conv3(data_r3.x, g3, 0.2))
             data_r3.x = rec("l4", self.l_conv4(data_r3.x, g3, 0.2))
-            up2 = self.pooling2.unpooling(data_r3.x)
-            rec("r1", self.r_conv1(up2, g2, 1.0, out=buf2[:, 64:]))     # no activation (network.py:290)
+            # unpooling (network.py:289) is fused into the conv: it gathers rows of the coarse features through the map
+            rec("r1", self.r_conv1(data_r3.x, g2, 1.0, out=buf2[:, 64:], row_map=self.pooling2.unpool_map))   # no activation (:290)
             data_r2.x = buf2
             data_r2.x = rec("r2", self.r_conv2(buf2, g2, 0.2))
 
-        up1 = self.pooling1.unpooling(data_r2.x)
-        rec("r3", self.r_conv3(up1, g1, 1.0, out=buf1[:, 32:]))         # no activation (network.py:296)
+        rec("r3", self.r_conv3(data_r2.x, g1, 1.0, out=buf1[:, 32:], row_map=self.pooling1.unpool_map))       # network.py:295-296
         data_r1.x = buf1
         return rec("r4", self.r_conv4(buf1, g1, 0.2))
 

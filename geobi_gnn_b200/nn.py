@@ -77,18 +77,19 @@ class FeaStConv(torch.nn.Module):
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def forward(self, x: torch.Tensor, edge_index: Union[torch.Tensor, CSRGraph], act_slope: float = 1.0,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """`row_map` (inference only): the conv reads x[row_map[v]] for node v — PoolingLayer.unpooling fused in."""
         if self.heads != 9:
             raise NotImplementedError("libgeobi's fused FeaSt kernel is specialised for heads=9 (network.py:258-268)")
-        g = conv_csr(edge_index, x.size(0))
+        n_nodes = x.size(0) if row_map is None else row_map.numel()
+        g = conv_csr(edge_index, n_nodes)
         if torch.is_grad_enabled() and (x.requires_grad or self.lin.weight.requires_grad):
+            if out is not None or row_map is not None:
+                raise RuntimeError("FeaStConv(out=..., row_map=...) are inference-only fusions; call it under torch.no_grad()")
             from .autograd import FeaStFn            # training step: same forward kernels + backward kernels
-            y = FeaStFn.apply(x, self.lin.weight, self.u.weight, self.c, self.bias, g, float(act_slope), config.precision_code())
-            if out is not None:
-                raise RuntimeError("FeaStConv(out=...) is an inference-only fusion; call it under torch.no_grad()")
-            return y
+            return FeaStFn.apply(x, self.lin.weight, self.u.weight, self.c, self.bias, g, float(act_slope), config.precision_code())
         return ops.feast_fwd(x, g, self.lin.weight, self.u.weight, self.c, self.bias, act_slope=act_slope, out=out,
-                             precision=config.precision_code())
+                             precision=config.precision_code(), row_map=row_map)
 
     def extra_repr(self):
         return f"{self.in_channels}, {self.out_channels}, heads={self.heads}"

@@ -398,24 +398,35 @@ def calc_weight(pos: torch.Tensor, nrm: torch.Tensor, edge_index: torch.Tensor) 
 
 # ----------------------------------------------------------------------------- conv / heads / transfer
 def feast_fwd(x: torch.Tensor, g: CSRGraph, W: torch.Tensor, U: torch.Tensor, c: torch.Tensor, bias: torch.Tensor,
-              act_slope: float = 1.0, out: Optional[torch.Tensor] = None, precision: int = PREC_FP32) -> torch.Tensor:
-    """FeaStConv forward on a TARGET-indexed CSR without self loops (implicit self loop)."""
-    _need_cuda(x, g.rowptr, W)
+              act_slope: float = 1.0, out: Optional[torch.Tensor] = None, precision: int = PREC_FP32,
+              row_map: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """FeaStConv forward on a TARGET-indexed CSR without self loops (implicit self loop).
+    row_map (int32 [g.n]): node v reads row row_map[v] of x (unpooling fused into the conv); x then has the coarse row count."""
+    _need_cuda(x, g.rowptr, W, row_map)
     lib = _lib.load()
     x, ldx, c_in = _rows(x)
     c_out = bias.numel()
-    n = x.size(0)
+    n = g.n if row_map is not None else x.size(0)
+    n_src = x.size(0)
+    if row_map is not None and not feast_row_map_supported(x):
+        x = gather_rows(x, row_map)            # generic fallback: materialise the unpooled rows
+        x, ldx, c_in = _rows(x)
+        row_map, n_src = None, n
     if out is None:
         out = valloc(n, (c_out,), torch.float32, x.device)
     o, ldo, _ = _rows(out)
     if o.data_ptr() != out.data_ptr():
         raise _lib.GeobiError("feast_fwd: `out` must have contiguous rows")
-    ws = _ws(lib.geobi_feast_fwd_ws_bytes(n, c_in, c_out, precision), x.device, slot=1)
-    _lib.check(lib.geobi_feast_fwd(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(W.contiguous()), _ptr(U.contiguous()),
-                                   _ptr(c.contiguous()), _ptr(bias.contiguous()), c_out, float(act_slope), _ptr(o), ldo, precision,
-                                   _ptr(ws), ws.numel(), _stream()), "feast_fwd")
+    ws = _ws(lib.geobi_feast_fwd_ws_bytes(max(n, n_src), c_in, c_out, precision & 0xff), x.device, slot=1)
+    _lib.check(lib.geobi_feast_fwd(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(row_map), n_src, _ptr(W.contiguous()),
+                                   _ptr(U.contiguous()), _ptr(c.contiguous()), _ptr(bias.contiguous()), c_out, float(act_slope), _ptr(o), ldo,
+                                   precision, _ptr(ws), ws.numel(), _stream()), "feast_fwd")
     _count(4)
     return out
+
+
+def feast_row_map_supported(x: torch.Tensor) -> bool:
+    return x.size(1) in (32, 64, 128) and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and x.stride(1) == 1
 
 
 def linear_tc(a: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, act_slope: float = 1.0, out: Optional[torch.Tensor] = None,

@@ -179,6 +179,9 @@ GEOBI_API int geobi_calc_weight(const float* pos, const float* nrm, const int64_
  * Evaluation is aggregate-first: Z[i,h,:] = sum_j q_ijh x_j, out = W_flat . Z — no per-edge
  * tensor is ever written to HBM; for C_in=64 -> C_out=32 with BF16X3 the whole layer is ONE persistent kernel
  * (feast_fused.cu) and Z never leaves shared memory.  Supported C_in: 1..128, C_out: multiple of 4 up to 128.
+ * row_map (optional, int32 [n_nodes]) fuses PoolingLayer.unpooling (net_util.py:242-245, network.py:289,295) into the conv:
+ * node v's features are row row_map[v] of x, which then has n_src (coarse) rows — the [n_nodes, C_in] unpooled copy is never
+ * built and U.x is evaluated once per coarse row.  Needs C_in in {32,64,128}, 16-byte aligned rows.  NULL: x has n_nodes rows.
  * precision: GEOBI_PREC_FP32 (all fp32 CUDA cores; parity 1e-5), GEOBI_PREC_BF16 (projection on tcgen05
  * tensor cores, bf16 operands / fp32 accumulate, one pass) or GEOBI_PREC_BF16X3 (same, operands split
  * hi + lo, three passes: fp32-grade results from the tensor cores). */
@@ -191,9 +194,9 @@ GEOBI_API int geobi_calc_weight(const float* pos, const float* nrm, const int64_
 #define GEOBI_FEAST_REUSE_WS 0x100
 GEOBI_API size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision);
 GEOBI_API int geobi_feast_fwd(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
-                    const int32_t* nbr, const float* W, const float* U, const float* c, const float* bias,
-                    int c_out, float act_slope, float* out, int64_t ldo, int precision, void* ws,
-                    size_t ws_bytes, void* stream);
+                    const int32_t* nbr, const int32_t* row_map, int64_t n_src, const float* W, const float* U,
+                    const float* c, const float* bias, int c_out, float act_slope, float* out, int64_t ldo,
+                    int precision, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- training step (train_dual.py:199-218): pieces of the FeaSt / pooling backward that are not plain GEMMs ---- */
 

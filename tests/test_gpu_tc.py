@@ -51,6 +51,33 @@ def test_feast_conv_tensor_core_projection(cin, cout):
     assert util.rel_err(one, want) < 5e-3
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("cin,cout", [(64, 32), (128, 64), (32, 64), (12, 32)])
+def test_feast_conv_row_map_equals_unpool_then_conv(cin, cout, prec):
+    """row_map fuses PoolingLayer.unpooling (net_util.py:242-245) into the conv: same bits as gather-then-conv,
+    and the oracle's conv on the unpooled features within the fp32 bar."""
+    from geobi_gnn_b200 import ops
+    (dv, df), _, _ = util.oracle_inputs(6)
+    torch.manual_seed(cin + cout)
+    conv = pyg.FeaStConv(cin, cout, 9)
+    n = df.x.shape[0]
+    n_coarse = n // 2 + 3
+    xc = torch.randn(n_coarse, cin) * 2.0
+    idx = torch.randint(0, n_coarse, (n,))
+    idx[:5] = torch.tensor([0, n_coarse - 1, 0, n_coarse - 1, 1])
+    with torch.no_grad():
+        want = conv(xc[idx], df.edge_index)
+    g = ops.csr_from_coo(df.edge_index.to(DEV), n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+    P = [t.data.to(DEV) for t in (conv.lin.weight, conv.u.weight, conv.c, conv.bias)]
+    code = ops.PREC_FP32 if prec == "fp32" else ops.PREC_BF16X3
+    xd, idd = xc.to(DEV), idx.to(DEV).int()
+    fused = ops.feast_fwd(xd, g, *P, precision=code, row_map=idd)
+    two_step = ops.feast_fwd(ops.gather_rows(xd, idd), g, *P, precision=code)
+    assert fused.shape == (n, cout)
+    assert torch.equal(fused, two_step)
+    assert util.rel_err(fused, want) < util.TOL_FP32
+
+
 @pytest.mark.parametrize("force_depth", [False, True])
 @pytest.mark.parametrize("n", [1, 127, 1000, 40000])
 def test_fc_head_tensor_core(n, force_depth):
