@@ -17,35 +17,103 @@ namespace geobi {
 constexpr int H = GEOBI_HEADS;
 
 // ------------------------------------------------------------------------------ P = X U^T (fp64)
-constexpr int PROJ_NODES = 64;
-constexpr int PROJ_THREADS = 192;  // 3 head groups x 64 nodes
+// One thread owns two nodes x all 9 heads (18 fp64 accumulators), so every staged x value is converted once and feeds
+// 9 DFMAs, and every broadcast U load feeds 4.  x is staged through shared memory in 32-channel chunks (coalesced
+// float4 reads, conflict-free float4 row reads at a 36-float pitch); the fp64 pipe, not the LSU, is the limiter.
+// Channels are accumulated in ascending order with one fma each - the same order as the oracle's float64 reference.
+constexpr int PROJ_NODES = 256;
+constexpr int PROJ_THREADS = 128;
+constexpr int PROJ_CC = 32;
+constexpr int PROJ_LD = PROJ_CC + 4;
+
+static inline size_t proj_smem_bytes(int c_in) {
+  const int cp = (c_in + 3) & ~3;
+  return (size_t)H * cp * sizeof(double) + (size_t)PROJ_NODES * PROJ_LD * sizeof(float);
+}
 
 __global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
                                                                      const float* __restrict__ U, double* __restrict__ P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* Us = reinterpret_cast<double*>(smem_raw);          // [H][C]
-  float* xs = reinterpret_cast<float*>(Us + H * C);          // [PROJ_NODES][C+1]
+  const int Cp = (C + 3) & ~3;
+  double* Us = reinterpret_cast<double*>(smem_raw);          // [H][Cp], zero padded
+  float* xs = reinterpret_cast<float*>(Us + H * Cp);         // [PROJ_NODES][PROJ_LD]
   const int tid = threadIdx.x;
   const int64_t node0 = (int64_t)blockIdx.x * PROJ_NODES;
-  for (int i = tid; i < H * C; i += PROJ_THREADS) Us[i] = (double)U[i];
-  for (int i = tid; i < PROJ_NODES * C; i += PROJ_THREADS) {
-    const int r = i / C, c = i - r * C;
-    const int64_t n = node0 + r;
-    xs[r * (C + 1) + c] = n < N ? x[n * ldx + c] : 0.f;
+  for (int i = tid; i < H * Cp; i += PROJ_THREADS) {
+    const int h = i / Cp, c = i - h * Cp;
+    Us[i] = c < C ? (double)U[h * C + c] : 0.0;
+  }
+  const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  double acc[2][H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[0][h] = acc[1][h] = 0.0;
+
+  for (int c0 = 0; c0 < Cp; c0 += PROJ_CC) {
+    const int cw = min(PROJ_CC, Cp - c0);                    // multiple of 4
+    __syncthreads();                                         // previous chunk consumed (first pass: nothing to wait for)
+    if (vec) {
+      const int units = cw >> 2;
+      for (int i = tid; i < PROJ_NODES * units; i += PROJ_THREADS) {
+        const int r = i / units, q = i - r * units;
+        const int64_t n = node0 + r;
+        const int c = c0 + q * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < N) {
+          const float* src = x + n * ldx + c;
+          if (c + 3 < C) v = __ldg(reinterpret_cast<const float4*>(src));
+          else {
+            v.x = src[0];
+            if (c + 1 < C) v.y = src[1];
+            if (c + 2 < C) v.z = src[2];
+          }
+        }
+        *reinterpret_cast<float4*>(xs + r * PROJ_LD + q * 4) = v;
+      }
+    } else {
+      for (int i = tid; i < PROJ_NODES * cw; i += PROJ_THREADS) {
+        const int r = i / cw, c = i - r * cw;
+        const int64_t n = node0 + r;
+        xs[r * PROJ_LD + c] = (n < N && c0 + c < C) ? x[n * ldx + c0 + c] : 0.f;
+      }
+    }
+    __syncthreads();
+    const float* xa = xs + tid * PROJ_LD;
+    const float* xb = xs + (tid + PROJ_THREADS) * PROJ_LD;
+    const double* ub = Us + c0;
+#pragma unroll 2
+    for (int q = 0; q < cw; q += 4) {
+      const float4 fa = *reinterpret_cast<const float4*>(xa + q);
+      const float4 fb = *reinterpret_cast<const float4*>(xb + q);
+      const double a0 = fa.x, a1 = fa.y, a2 = fa.z, a3 = fa.w;
+      const double b0 = fb.x, b1 = fb.y, b2 = fb.z, b3 = fb.w;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const double2 u01 = *reinterpret_cast<const double2*>(ub + h * Cp + q);
+        const double2 u23 = *reinterpret_cast<const double2*>(ub + h * Cp + q + 2);
+        acc[0][h] = fma(a0, u01.x, acc[0][h]);
+        acc[1][h] = fma(b0, u01.x, acc[1][h]);
+        acc[0][h] = fma(a1, u01.y, acc[0][h]);
+        acc[1][h] = fma(b1, u01.y, acc[1][h]);
+        acc[0][h] = fma(a2, u23.x, acc[0][h]);
+        acc[1][h] = fma(b2, u23.x, acc[1][h]);
+        acc[0][h] = fma(a3, u23.y, acc[0][h]);
+        acc[1][h] = fma(b3, u23.y, acc[1][h]);
+      }
+    }
+  }
+  // transpose through shared memory so P is written in whole rows of the block (coalesced)
+  __syncthreads();
+  double* ps = reinterpret_cast<double*>(xs);                // 256 x 9 doubles = 18 KB <= the 36 KB x stage
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    ps[tid * H + h] = acc[0][h];
+    ps[(tid + PROJ_THREADS) * H + h] = acc[1][h];
   }
   __syncthreads();
-  const int r = tid & (PROJ_NODES - 1), g = tid / PROJ_NODES;
-  const int64_t n = node0 + r;
-  if (n >= N) return;
-  const float* xr = xs + r * (C + 1);
-#pragma unroll
-  for (int hh = 0; hh < 3; ++hh) {
-    const int h = g * 3 + hh;
-    const double* u = Us + h * C;
-    double acc = 0.0;
-    for (int c = 0; c < C; ++c) acc = fma((double)xr[c], u[c], acc);
-    P[n * H + h] = acc;
-  }
+  const int64_t left = N - node0;
+  const int cnt = (int)(left < PROJ_NODES ? left : PROJ_NODES) * H;
+  double* dst = P + node0 * H;
+  for (int i = tid; i < cnt; i += PROJ_THREADS) dst[i] = ps[i];
 }
 
 // ------------------------------------------------------------------------------ Z = softmax-weighted neighbour sums
@@ -741,7 +809,7 @@ static void launch_aggregate(int out_mode, unsigned blocks, cudaStream_t st, con
 }
 
 int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const float* U, double* P, cudaStream_t st) {
-  const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
+  const size_t psm = proj_smem_bytes(c_in);
   feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, P);
   GEOBI_LAUNCH_OK("feast_project");
   return GEOBI_OK;
@@ -750,7 +818,7 @@ int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const f
 int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
                                 const int32_t* row_map, int64_t n_src, const float* U, const float* c, double* P, void* Z, int64_t ldz,
                                 int out_mode, cudaStream_t st) {
-  const size_t psm = (size_t)H * c_in * sizeof(double) + (size_t)PROJ_NODES * (c_in + 1) * sizeof(float);
+  const size_t psm = proj_smem_bytes(c_in);
   feast_project_kernel<<<(unsigned)cdiv(n_src, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, n_src, c_in, U, P);
   GEOBI_LAUNCH_OK("feast_project");
   const unsigned ab = (unsigned)cdiv(N, 8);
