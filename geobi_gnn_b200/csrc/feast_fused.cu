@@ -1,12 +1,13 @@
 // Fused FeaSt convolution, C_in = 64 -> C_out = 32 (r_conv3 / r_conv4 of both U-Nets, network.py:267-268: the two
 // largest layers of each graph): aggregation + projection + bias + leaky_relu in ONE persistent kernel.
 //
-//   per tile of 32 target nodes (16 warps x 2 nodes, lanes own 4 adjacent channels):
-//     1. aggregate Z_i[h, :] = 1/d_i sum_j q_ijh x_j in registers (same arithmetic as feast_aggregate_packed_kernel),
+//   per tile of 32 target nodes (16 aggregation warps x 2 nodes, lanes own 4 adjacent channels):
+//     1. aggregate Z_i[h, :] = 1/d_i sum_j q_ijh x_j in registers (1/d_i folded into the soft assignments),
 //     2. write the rows, split x = hi + lo (bf16), straight into the K-major SWIZZLE_128B *B-operand* tiles in shared memory,
-//     3. one thread issues tcgen05.mma (M = 64: the weight tile W_flat[32 (+32 aliased) x 576] is the resident A operand,
+//     3. warp 16 issues tcgen05.mma (M = 64: the weight tile W_flat[32 (+32 aliased) x 576] is the resident A operand,
 //        N = 32 nodes, 36 K-steps x 3 split passes) -> D^T[channel, node] in TMEM,
-//     4. two warps drain TMEM (+bias, leaky_relu) and write out[node, channel]; meanwhile everybody aggregates the next tile.
+//     4. warps 16 and 17 drain TMEM (+bias, leaky_relu) and write out[node, channel]; the aggregation warps never touch the
+//        accumulator, they only wait for the MMAs of tile t-1 before overwriting the operand tiles with tile t.
 //
 // Z (2.3 KB per node) never reaches HBM: per node the kernel reads 256 B of x per gathered row (L2) + 72 B of P, and writes
 // 128 B.  The unfused path writes and re-reads 2 x 2.3 KB per node (ncu: 1.12 GB written by the aggregation of one layer).
@@ -20,11 +21,13 @@ using namespace tc;
 constexpr int C_IN = 64, C_OUT = 32;
 constexpr int NT = 32;            // nodes per tile = MMA N
 constexpr int WARPS = 16;         // aggregation warps, 2 nodes each
-constexpr int THREADS = (WARPS + 1) * 32;   // + one warp that only issues the MMAs (warp specialisation)
+constexpr int EPI_WARPS = 2;      // warp 16: MMA issue + TMEM quadrant 0; warp 17: TMEM quadrant 1 (a warp reaches lanes 32*(warp%4)..+31)
+constexpr int THREADS = (WARPS + EPI_WARPS) * 32;
 constexpr int KB = H;             // one 64-wide K block per head
 constexpr int TILE_BYTES = 32 * 128;   // [32 rows x 128 B] of one K block (W rows = channels, Z rows = nodes)
 constexpr int PLANE_BYTES = KB * TILE_BYTES;
-constexpr int SMEM_BYTES = 4 * PLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * 32 * 12 * 4 + 1024;
+constexpr int QROW = 12;          // floats per soft-assignment row (9 used; 48-byte rows keep the float4 reads aligned)
+constexpr int SMEM_BYTES = 4 * PLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * 32 * QROW * 4 + WARPS * 32 * 4 + 64 + 1024;
 
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
@@ -37,8 +40,11 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 // named barrier 1: the 16 aggregation warps arrive (non-blocking) when their rows are in shared memory, the MMA warp waits
-__device__ __forceinline__ void z_ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(THREADS) : "memory"); }
-__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+__device__ __forceinline__ void z_ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"((WARPS + 1) * 32) : "memory"); }
+__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"n"((WARPS + 1) * 32) : "memory"); }
+// named barrier 2: both drain warps have read the accumulator (the next tile's first MMA overwrites it)
+__device__ __forceinline__ void drained_sync() { asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
                                                                        const int* __restrict__ rowptr, const int* __restrict__ nbr,
@@ -57,12 +63,9 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   uint8_t* z_hi = sm + 2 * PLANE_BYTES;
   uint8_t* z_lo = sm + 3 * PLANE_BYTES;
   float* qs_all = reinterpret_cast<float*>(sm + 4 * PLANE_BYTES + TILE_BYTES);
+  unsigned* joff_all = reinterpret_cast<unsigned*>(qs_all + WARPS * 32 * QROW);
+  float* chs = reinterpret_cast<float*>(joff_all + WARPS * 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* qs = qs_all + (warp < WARPS ? warp : 0) * 32 * 12;
-  constexpr int LPN = 16;
-  const int g = lane / LPN, sl = lane % LPN, c0 = sl * 4;
-  const int row = warp * 2 + g;              // node slot inside the tile = row of the B operand
-  const unsigned ldx32 = (unsigned)ldx;
 
   // ---- one-time setup: barrier, TMEM, resident weight tiles
   if (tid == 0) {
@@ -70,6 +73,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  if (tid < H) chs[tid] = cvec[tid];
   for (int idx = tid; idx < 2 * KB * 32 * 8; idx += THREADS) {
     const int plane = idx / (KB * 32 * 8), rem = idx - plane * (KB * 32 * 8);
     const int kb = rem / (32 * 8), r = (rem / 8) % 32, chk = rem % 8;
@@ -81,23 +85,52 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
-  constexpr uint32_t idesc = make_idesc(64, NT);
-  float ch[H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) ch[h] = cvec[h];
-  const float my_bias = bias[(warp & 1) * 16 + (lane & 15)];   // epilogue warps 0,1: channel = 16*quadrant + lane
 
   const int64_t n_tiles = (N + NT - 1) / NT;
   const int64_t t_begin = (n_tiles * blockIdx.x) / gridDim.x, t_end = (n_tiles * (blockIdx.x + 1)) / gridDim.x;
-  uint32_t mma_phase = 0;
 
-  auto epilogue = [&](int64_t tile) {
-    // warps 0 and 1 own TMEM quadrants 0 and 1; for M = 64 accumulator row r lives in lane (r % 16) + 32 * (r / 16)
-    if (warp < 2) {
+  if (warp >= WARPS) {
+    // ===== MMA / drain warps =====
+    const int quad = warp - WARPS;                 // TMEM quadrant; for M = 64 accumulator row r lives in lane (r % 16) + 32 * (r / 16)
+    const float my_bias = bias[quad * 16 + (lane & 15)];
+    constexpr uint32_t idesc = make_idesc(64, NT);
+    const uint64_t d0 = make_desc(smem_u32(w_hi));
+    const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+    const uint32_t wh_lo = (uint32_t)d0, wl_lo = (uint32_t)make_desc(smem_u32(w_lo)), zh_lo = (uint32_t)make_desc(smem_u32(z_hi)),
+                   zl_lo = (uint32_t)make_desc(smem_u32(z_lo));
+    uint32_t phase = 0;
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+      if (quad == 0) {
+        // waits for the tile's rows, issues 36 K-steps x 3 split passes, commits to the mbarrier
+        z_ready_wait();
+        if (lane == 0) {
+          tc_fence_after();
+          // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
+          // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
+          uint32_t ah = wh_lo, al = wl_lo, bh = zh_lo, bl = zl_lo;
+#pragma unroll 1
+          for (int kb = 0; kb < KB; ++kb) {
+            if (kb == 0) mma_f16_first(tmem_d, ah, bh, desc_hi, idesc);
+            else mma_f16_acc(tmem_d, ah, bh, desc_hi, idesc);
+#pragma unroll
+            for (int k16 = 1; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bl + 2 * k16, desc_hi, idesc);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+            ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += TILE_BYTES >> 4; bl += TILE_BYTES >> 4;
+          }
+          mma_commit(&mbar);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&mbar, phase);
+      phase ^= 1;
+      tc_fence_after();
       float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16), v);
+      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16), v);
       if (lane < 16) {
-        const int o = warp * 16 + lane;
+        const int o = quad * 16 + lane;
         const int64_t n0 = tile * NT;
 #pragma unroll
         for (int col = 0; col < NT; ++col) {
@@ -109,43 +142,20 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
         }
       }
       tc_fence_before();
+      drained_sync();
     }
-  };
-
-  if (warp == WARPS) {
-    const uint64_t d0 = make_desc(smem_u32(w_hi));
-    const uint32_t desc_hi = (uint32_t)(d0 >> 32);
-    const uint32_t wh_lo = (uint32_t)d0, wl_lo = (uint32_t)make_desc(smem_u32(w_lo)), zh_lo = (uint32_t)make_desc(smem_u32(z_hi)),
-                   zl_lo = (uint32_t)make_desc(smem_u32(z_lo));
-    // ===== MMA warp: waits for a tile's rows, issues 36 K-steps x 3 split passes, commits to the mbarrier =====
-    for (int64_t tile = t_begin; tile < t_end; ++tile) {
-      z_ready_wait();
-      if (lane == 0) {
-        tc_fence_after();
-        // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
-        // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
-        uint32_t ah = wh_lo, al = wl_lo, bh = zh_lo, bl = zl_lo;
-#pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
-          if (kb == 0) mma_f16_first(tmem_d, ah, bh, desc_hi, idesc);
-          else mma_f16_acc(tmem_d, ah, bh, desc_hi, idesc);
-#pragma unroll
-          for (int k16 = 1; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bh + 2 * k16, desc_hi, idesc);
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bl + 2 * k16, desc_hi, idesc);
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
-          ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += TILE_BYTES >> 4; bl += TILE_BYTES >> 4;
-        }
-        mma_commit(&mbar);
-      }
-      __syncwarp();
-    }
-    tc_fence_before();
     __syncthreads();
     return;
   }
+
   // ===== aggregation warps =====
+  constexpr int LPN = 16;
+  const int g = lane / LPN, sl = lane % LPN, c0 = sl * 4;
+  const int row = warp * 2 + g;              // node slot inside the tile = row of the B operand
+  const unsigned ldx32 = (unsigned)ldx;
+  const float* xl = x + c0;                  // this lane's 4 channels
+  float* qs = qs_all + warp * 32 * QROW;
+  unsigned* joffs = joff_all + warp * 32;
   // Index prefetch pipeline (breaks the rowptr -> nbr -> data dependency chain across tiles):
   //   iteration t holds (b, total, j) of tile t, loads nbr of tile t+1 with the rowptr loaded one iteration earlier,
   //   and loads rowptr of tile t+2.
@@ -174,6 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   load_rowptr(t_begin + 1, b_nxt, total_nxt);
   int j_cur = load_first_j(t_begin, b_cur, total_cur);
   int j_nxt = 0;
+  uint32_t mma_phase = 0;
 
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
     // ---------------- 1. aggregation of this warp's two nodes (registers only)
@@ -185,11 +196,9 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     // prefetch: indices of the next tiles (consumed one / two iterations from now)
     j_nxt = load_first_j(tile + 1, b_nxt, total_nxt);
     load_rowptr(tile + 2, b_nx2, total_nx2);
-    int maxtotal = max(total, __shfl_xor_sync(0xffffffffu, total, 16));
+    const int maxtotal = max(total, __shfl_xor_sync(0xffffffffu, total, 16));
     const int i_src = row_map ? row_map[i] : (int)i;
-    double Pi[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) Pi[h] = P[(int64_t)i_src * H + h];
+    const float rcnt = live ? 1.0f / (float)total : 0.f;   // mean over N(i)+{i}, folded into q; dead rows become zeros
     unsigned long long acc2[4][4];
     float acc8[4];
 #pragma unroll
@@ -207,17 +216,26 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
         if (row_map) j = row_map[j];
       }
       const int cnt = min(LPN, maxtotal - s0);
-      // the first pair of rows does not depend on the soft assignments: get it in flight together with the P rows
-      const unsigned j0 = (unsigned)__shfl_sync(0xffffffffu, j, 0, LPN);
-      const unsigned j1 = (unsigned)__shfl_sync(0xffffffffu, j, 1, LPN);
-      float4 xa = *reinterpret_cast<const float4*>(x + (j0 * ldx32 + (unsigned)c0));
-      float4 xb = *reinterpret_cast<const float4*>(x + (j1 * ldx32 + (unsigned)c0));
+      const unsigned joff = (unsigned)j * ldx32;
+      // the first pair of rows does not depend on the soft assignments: get it in flight together with the P rows,
+      // and pull every other row of the chunk into L1 now (the loop below reaches it a few hundred cycles later)
+      const unsigned o0 = __shfl_sync(0xffffffffu, joff, 0, LPN);
+      const unsigned o1 = __shfl_sync(0xffffffffu, joff, 1, LPN);
+      float4 xa = *reinterpret_cast<const float4*>(xl + o0);
+      float4 xb = *reinterpret_cast<const float4*>(xl + o1);
+      if (sl >= 2 && s < total) {
+        prefetch_l1(x + joff);
+        prefetch_l1(x + joff + 32);
+      }
+      joffs[lane] = joff;
       float l[H];
       if (s < total) {
+        const double* Pj = P + (int64_t)j * H;
+        const double* Pi = P + (int64_t)i_src * H;
         float m = -INFINITY;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+          l[h] = (float)(Pj[h] - Pi[h]) + chs[h];
           m = fmaxf(m, l[h]);
         }
         float sum = 0.f;
@@ -226,42 +244,31 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
           l[h] = __expf(l[h] - m);
           sum += l[h];
         }
-        const float inv = 1.0f / sum;
+        const float inv = rcnt / sum;
 #pragma unroll
         for (int h = 0; h < H; ++h) l[h] *= inv;
       } else {
 #pragma unroll
         for (int h = 0; h < H; ++h) l[h] = 0.f;
       }
-      float4* q4 = reinterpret_cast<float4*>(qs + lane * 12);
+      float4* q4 = reinterpret_cast<float4*>(qs + lane * QROW);
       q4[0] = make_float4(l[0], l[1], l[2], l[3]);
       q4[1] = make_float4(l[4], l[5], l[6], l[7]);
-      qs[lane * 12 + 8] = l[8];
+      qs[lane * QROW + 8] = l[8];
       __syncwarp();
-      const float* qbase = qs + g * LPN * 12;
-#pragma unroll 1
-      for (int t = 0; t < cnt; t += 2) {
-        // software pipeline: issue the next pair's gathers before consuming the current pair
-        const int tn = t + 2;
-        const unsigned ja = (unsigned)__shfl_sync(0xffffffffu, j, tn & (LPN - 1), LPN);
-        const unsigned jb = (unsigned)__shfl_sync(0xffffffffu, j, (tn + 1) & (LPN - 1), LPN);
-        float4 xna = xa, xnb = xb;
-        if (tn < cnt) {
-          xna = *reinterpret_cast<const float4*>(x + (ja * ldx32 + (unsigned)c0));
-          xnb = *reinterpret_cast<const float4*>(x + (jb * ldx32 + (unsigned)c0));
-        }
-        const bool has_b = t + 1 < cnt;
-        const float* qa = qbase + t * 12;
-        const float* qb = qbase + ((t + 1) & (LPN - 1)) * 12;
+      const float* qbase = qs + g * LPN * QROW;
+      const unsigned* jbase = joffs + g * LPN;
+      // slots >= total hold zero assignments and a valid row (the node's own), so pairs need no tail handling
+      auto consume = [&](const float4& va, const float4& vb, int t) {
+        const float* qa = qbase + t * QROW;
         const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(qa);
         const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(qa + 4);
         const float qa8 = qa[8];
-        ulonglong2 qb0 = *reinterpret_cast<const ulonglong2*>(qb);
-        ulonglong2 qb1 = *reinterpret_cast<const ulonglong2*>(qb + 4);
-        float qb8 = qb[8];
-        if (!has_b) { qb0.x = qb0.y = qb1.x = qb1.y = 0ull; qb8 = 0.f; }
-        const float xav[4] = {xa.x, xa.y, xa.z, xa.w};
-        const float xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+        const ulonglong2 qb0 = *reinterpret_cast<const ulonglong2*>(qa + QROW);
+        const ulonglong2 qb1 = *reinterpret_cast<const ulonglong2*>(qa + QROW + 4);
+        const float qb8 = qa[QROW + 8];
+        const float xav[4] = {va.x, va.y, va.z, va.w};
+        const float xbv[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const unsigned long long xx = pack2(xav[k], xav[k]);
@@ -280,23 +287,41 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
           acc2[3][k] = ffma2(qb1.y, xx, acc2[3][k]);
           acc8[k] = fmaf(qb8, xbv[k], acc8[k]);
         }
-        xa = xna;
-        xb = xnb;
+      };
+      // software pipeline, two register sets: the next pair's gathers are issued before the current pair is consumed
+      int t = 0;
+#pragma unroll 1
+      while (true) {
+        float4 xc = xa, xd = xb;
+        if (t + 2 < cnt) {
+          const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 2);
+          xc = *reinterpret_cast<const float4*>(xl + o.x);
+          xd = *reinterpret_cast<const float4*>(xl + o.y);
+        }
+        consume(xa, xb, t);
+        t += 2;
+        if (t >= cnt) break;
+        if (t + 2 < cnt) {
+          const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 2);
+          xa = *reinterpret_cast<const float4*>(xl + o.x);
+          xb = *reinterpret_cast<const float4*>(xl + o.y);
+        }
+        consume(xc, xd, t);
+        t += 2;
+        if (t >= cnt) break;
       }
       __syncwarp();
     }
     b_cur = b_nxt; total_cur = total_nxt; j_cur = j_nxt;
     b_nxt = b_nx2; total_nxt = total_nx2;
-    // ---------------- 2. the previous tile's MMAs have finished reading the Z tiles; drain its accumulator
+    // ---------------- 2. the previous tile's MMAs have finished reading the operand tiles
     if (tile > t_begin) {
       mbar_wait(&mbar, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
-      epilogue(tile - 1);
     }
     // ---------------- 3. this tile's rows -> B-operand tiles (split bf16), then the MMAs
     {
-      const float rcnt = live ? 1.0f / (float)total : 0.f;   // dead rows become zeros
       const uint32_t off = sw128_off(row, c0 >> 3) + (uint32_t)(c0 & 7) * 2;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
@@ -307,7 +332,6 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
         } else {
           z = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
         }
-        z.x *= rcnt; z.y *= rcnt; z.z *= rcnt; z.w *= rcnt;
         uint2 hi, lo;
         split_bf16x4(z, hi, lo);
         *reinterpret_cast<uint2*>(z_hi + h * TILE_BYTES + off) = hi;
@@ -316,16 +340,13 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     }
     fence_proxy_async();
     tc_fence_before();
-    z_ready_arrive();      // non-blocking: go on with the next tile while the MMA warp issues this one
+    z_ready_arrive();      // non-blocking: go on with the next tile while warp 16 issues this one
   }
-  if (t_end > t_begin) {
-    mbar_wait(&mbar, mma_phase);
-    tc_fence_after();
-    epilogue(t_end - 1);
-  }
-  tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, 32);
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, 32);
+  }
 }
 
 }  // namespace fused

@@ -31,3 +31,9 @@ for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
 # biggest idle gaps
 gaps = sorted(((ks[i+1][0] - ks[i][1], ks[i][2][:40], ks[i+1][2][:40]) for i in range(len(ks)-1)), reverse=True)[:12]
 print("largest gaps (us): ", [(round(g,1), a, b) for g, a, b in gaps])
+if os.environ.get("TIMELINE_DUMP"):
+    with open(os.environ["TIMELINE_DUMP"], "w") as f:
+        prev = ks[0][0]
+        for s, e, n in ks:
+            f.write(f"{s - ks[0][0]:10.1f} gap={s - prev:7.1f} dur={e - s:7.1f} {re.sub(r'\(.*', '', n)[:70]}\n")
+            prev = e
