@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgeobi.so")
+LIB_PATH = os.environ.get("GEOBI_LIB_PATH") or os.path.join(_HERE, "libgeobi.so")   # override: A/B kernel builds (profiles/)
 
 _i64, _i32, _f32, _sz, _p = C.c_int64, C.c_int, C.c_float, C.c_size_t, C.c_void_p
 

@@ -18,6 +18,9 @@ namespace fused {
 
 using namespace tc;
 
+#ifndef PREFETCH_MODE
+#define PREFETCH_MODE 0
+#endif
 constexpr int C_IN = 64, C_OUT = 32;
 constexpr int NT = 32;            // nodes per tile = MMA N
 constexpr int WARPS = 16;         // aggregation warps, 2 nodes each
@@ -27,7 +30,8 @@ constexpr int KB = H;             // one 64-wide K block per head
 constexpr int TILE_BYTES = 32 * 128;   // [32 rows x 128 B] of one K block (W rows = channels, Z rows = nodes)
 constexpr int PLANE_BYTES = KB * TILE_BYTES;
 constexpr int QROW = 12;          // floats per soft-assignment row (9 used; 48-byte rows keep the float4 reads aligned)
-constexpr int SMEM_BYTES = 4 * PLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * 32 * QROW * 4 + WARPS * 32 * 4 + 64 + 1024;
+constexpr int SCRATCH = 32 * QROW * 4;   // per-warp scratch: the soft-assignment rows of the chunk's 32 slots
+constexpr int SMEM_BYTES = 4 * PLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * SCRATCH + WARPS * 32 * 4 + 64 + 1024;
 
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
@@ -39,12 +43,29 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
 }
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
-// named barrier 1: the 16 aggregation warps arrive (non-blocking) when their rows are in shared memory, the MMA warp waits
-__device__ __forceinline__ void z_ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"((WARPS + 1) * 32) : "memory"); }
-__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"n"((WARPS + 1) * 32) : "memory"); }
+// named barrier 1: the 16 aggregation warps arrive (non-blocking) when their rows are in shared memory; the MMA warp and
+// the second drain warp sleep on it (so neither spins on the mbarrier while the tile is still being aggregated)
+__device__ __forceinline__ void z_ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(THREADS) : "memory"); }
+__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 // named barrier 2: both drain warps have read the accumulator (the next tile's first MMA overwrites it)
 __device__ __forceinline__ void drained_sync() { asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+#ifdef EXP_TIMELINE
+__device__ unsigned long long g_tl[64 * 8];
+__device__ unsigned long long g_tw[64 * 16 * 2];
+__device__ unsigned long long g_ts[64 * 2 * 8];
+#define TS(slot) do { if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 15) && tile - t_begin >= 20 && tile - t_begin < 84) g_ts[((tile - t_begin - 20) * 2 + (warp == 15)) * 8 + (slot)] = now_ns(); } while (0)
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL(slot) do { if (blockIdx.x == 0 && lane == 0 && tile - t_begin >= 20 && tile - t_begin < 84) g_tl[(tile - t_begin - 20) * 8 + (slot)] = now_ns(); } while (0)
+#else
+#define TL(slot) do { } while (0)
+#define TS(slot) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
                                                                        const int* __restrict__ rowptr, const int* __restrict__ nbr,
@@ -62,8 +83,8 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   uint8_t* w_lo = sm + PLANE_BYTES;
   uint8_t* z_hi = sm + 2 * PLANE_BYTES;
   uint8_t* z_lo = sm + 3 * PLANE_BYTES;
-  float* qs_all = reinterpret_cast<float*>(sm + 4 * PLANE_BYTES + TILE_BYTES);
-  unsigned* joff_all = reinterpret_cast<unsigned*>(qs_all + WARPS * 32 * QROW);
+  uint8_t* scratch_all = sm + 4 * PLANE_BYTES + TILE_BYTES;
+  unsigned* joff_all = reinterpret_cast<unsigned*>(scratch_all + WARPS * SCRATCH);
   float* chs = reinterpret_cast<float*>(joff_all + WARPS * 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -100,10 +121,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
                    zl_lo = (uint32_t)make_desc(smem_u32(z_lo));
     uint32_t phase = 0;
     for (int64_t tile = t_begin; tile < t_end; ++tile) {
+      z_ready_wait();
+      if (quad == 0) TL(0);
       if (quad == 0) {
-        // waits for the tile's rows, issues 36 K-steps x 3 split passes, commits to the mbarrier
-        z_ready_wait();
-        if (lane == 0) {
+        // the tile's rows are in place: issue 36 K-steps x 3 split passes, commit to the mbarrier
+        if (elect_one()) {
           tc_fence_after();
           // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
           // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
@@ -114,19 +136,23 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
             else mma_f16_acc(tmem_d, ah, bh, desc_hi, idesc);
 #pragma unroll
             for (int k16 = 1; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+#ifndef EXP_ONEPASS
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bl + 2 * k16, desc_hi, idesc);
 #pragma unroll
             for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+#endif
             ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += TILE_BYTES >> 4; bl += TILE_BYTES >> 4;
           }
           mma_commit(&mbar);
         }
         __syncwarp();
+        TL(1);
       }
       mbar_wait(&mbar, phase);
       phase ^= 1;
       tc_fence_after();
+      if (quad == 0) TL(2);
       float v[32];
       tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16), v);
       if (lane < 16) {
@@ -134,7 +160,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
         const int64_t n0 = tile * NT;
 #pragma unroll
         for (int col = 0; col < NT; ++col) {
+#ifdef EXP_NOSTORE
+          if (n0 + col < N && v[col] == 123.456f) {
+#else
           if (n0 + col < N) {
+#endif
             float r = v[col] + my_bias;
             r = r > 0.f ? r : r * slope;
             out[(n0 + col) * ldo + o] = r;
@@ -143,6 +173,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       }
       tc_fence_before();
       drained_sync();
+      if (quad == 0) TL(3);
     }
     __syncthreads();
     return;
@@ -154,7 +185,8 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   const int row = warp * 2 + g;              // node slot inside the tile = row of the B operand
   const unsigned ldx32 = (unsigned)ldx;
   const float* xl = x + c0;                  // this lane's 4 channels
-  float* qs = qs_all + warp * 32 * QROW;
+  asm volatile("" : "+l"(xl));               // keep the pointer in registers (ptxas otherwise re-derives it from %tid in the loop)
+  float* qs = reinterpret_cast<float*>(scratch_all + warp * SCRATCH);
   unsigned* joffs = joff_all + warp * 32;
   // Index prefetch pipeline (breaks the rowptr -> nbr -> data dependency chain across tiles):
   //   iteration t holds (b, total, j) of tile t, loads nbr of tile t+1 with the rowptr loaded one iteration earlier,
@@ -188,6 +220,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
 
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
     // ---------------- 1. aggregation of this warp's two nodes (registers only)
+    if (warp == 0) TL(4);
+    TS(0);
+#ifdef EXP_TIMELINE
+    if (blockIdx.x == 0 && lane == 0 && tile - t_begin >= 20 && tile - t_begin < 84) g_tw[((tile - t_begin - 20) * 16 + warp) * 2] = now_ns();
+#endif
     const int64_t i_raw = tile * NT + row;
     const bool live = i_raw < N;
     const int64_t i = live ? i_raw : N - 1;
@@ -199,14 +236,10 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     const int maxtotal = max(total, __shfl_xor_sync(0xffffffffu, total, 16));
     const int i_src = row_map ? row_map[i] : (int)i;
     const float rcnt = live ? 1.0f / (float)total : 0.f;   // mean over N(i)+{i}, folded into q; dead rows become zeros
-    unsigned long long acc2[4][4];
-    float acc8[4];
+    // accumulators: acc[h][0] = channels (c0, c0+1), acc[h][1] = (c0+2, c0+3) of head h, as packed fp32 pairs (FFMA2)
+    unsigned long long acc[H][2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      acc8[k] = 0.f;
-#pragma unroll
-      for (int p2 = 0; p2 < 4; ++p2) acc2[p2][k] = 0ull;
-    }
+    for (int h = 0; h < H; ++h) acc[h][0] = acc[h][1] = 0ull;
     for (int s0 = 0; s0 < maxtotal; s0 += LPN) {
       const int s = s0 + sl;
       int j = i_src;
@@ -216,131 +249,166 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
         if (row_map) j = row_map[j];
       }
       const int cnt = min(LPN, maxtotal - s0);
+#ifdef EXP_NOGATHER
+      j = i_src;
+#endif
       const unsigned joff = (unsigned)j * ldx32;
-      // the first pair of rows does not depend on the soft assignments: get it in flight together with the P rows,
-      // and pull every other row of the chunk into L1 now (the loop below reaches it a few hundred cycles later)
+      // the first pair of rows does not depend on the soft assignments: get it in flight together with the P rows
       const unsigned o0 = __shfl_sync(0xffffffffu, joff, 0, LPN);
       const unsigned o1 = __shfl_sync(0xffffffffu, joff, 1, LPN);
-      float4 xa = *reinterpret_cast<const float4*>(xl + o0);
-      float4 xb = *reinterpret_cast<const float4*>(xl + o1);
+      ulonglong2 xa = __ldg(reinterpret_cast<const ulonglong2*>(xl + o0));
+      ulonglong2 xb = __ldg(reinterpret_cast<const ulonglong2*>(xl + o1));
+#if PREFETCH_MODE == 1
       if (sl >= 2 && s < total) {
         prefetch_l1(x + joff);
         prefetch_l1(x + joff + 32);
       }
+#endif
       joffs[lane] = joff;
+      if (s0 == 0) TS(1);
       float l[H];
+#ifdef EXP_NOSOFTMAX
+      if (false) {
+#else
       if (s < total) {
+#endif
         const double* Pj = P + (int64_t)j * H;
         const double* Pi = P + (int64_t)i_src * H;
         float m = -INFINITY;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
+#ifdef EXP_NOPLOAD
+          l[h] = (float)(__longlong_as_double((long long)(j + h)) - __longlong_as_double((long long)(i_src + h))) + chs[h];
+#elif defined(EXP_NOEXP)
+          l[h] = (float)(Pj[h] - Pi[h]) * 1e-30f + 0.111f;
+#else
           l[h] = (float)(Pj[h] - Pi[h]) + chs[h];
+#endif
           m = fmaxf(m, l[h]);
         }
         float sum = 0.f;
+#ifndef EXP_NOEXP
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           l[h] = __expf(l[h] - m);
           sum += l[h];
         }
         const float inv = rcnt / sum;
+#else
+        const float inv = rcnt;
+#endif
 #pragma unroll
         for (int h = 0; h < H; ++h) l[h] *= inv;
       } else {
 #pragma unroll
         for (int h = 0; h < H; ++h) l[h] = 0.f;
       }
+#ifdef EXP_NOSOFTMAX
+      if (s < total) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) l[h] = rcnt * (1.0f / 9.0f);
+      }
+#endif
       float4* q4 = reinterpret_cast<float4*>(qs + lane * QROW);
       q4[0] = make_float4(l[0], l[1], l[2], l[3]);
       q4[1] = make_float4(l[4], l[5], l[6], l[7]);
       qs[lane * QROW + 8] = l[8];
+      if (s0 == 0) TS(2);
       __syncwarp();
       const float* qbase = qs + g * LPN * QROW;
       const unsigned* jbase = joffs + g * LPN;
       // slots >= total hold zero assignments and a valid row (the node's own), so pairs need no tail handling
-      auto consume = [&](const float4& va, const float4& vb, int t) {
+      auto consume = [&](const ulonglong2& va, const ulonglong2& vb, int t) {
         const float* qa = qbase + t * QROW;
-        const ulonglong2 qa0 = *reinterpret_cast<const ulonglong2*>(qa);
-        const ulonglong2 qa1 = *reinterpret_cast<const ulonglong2*>(qa + 4);
+        const float4 qa0 = *reinterpret_cast<const float4*>(qa);
+        const float4 qa1 = *reinterpret_cast<const float4*>(qa + 4);
         const float qa8 = qa[8];
-        const ulonglong2 qb0 = *reinterpret_cast<const ulonglong2*>(qa + QROW);
-        const ulonglong2 qb1 = *reinterpret_cast<const ulonglong2*>(qa + QROW + 4);
+        const float4 qb0 = *reinterpret_cast<const float4*>(qa + QROW);
+        const float4 qb1 = *reinterpret_cast<const float4*>(qa + QROW + 4);
         const float qb8 = qa[QROW + 8];
-        const float xav[4] = {va.x, va.y, va.z, va.w};
-        const float xbv[4] = {vb.x, vb.y, vb.z, vb.w};
+        const float qav[H] = {qa0.x, qa0.y, qa0.z, qa0.w, qa1.x, qa1.y, qa1.z, qa1.w, qa8};
+        const float qbv[H] = {qb0.x, qb0.y, qb0.z, qb0.w, qb1.x, qb1.y, qb1.z, qb1.w, qb8};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned long long xx = pack2(xav[k], xav[k]);
-          acc2[0][k] = ffma2(qa0.x, xx, acc2[0][k]);
-          acc2[1][k] = ffma2(qa0.y, xx, acc2[1][k]);
-          acc2[2][k] = ffma2(qa1.x, xx, acc2[2][k]);
-          acc2[3][k] = ffma2(qa1.y, xx, acc2[3][k]);
-          acc8[k] = fmaf(qa8, xav[k], acc8[k]);
+        for (int h = 0; h < H; ++h) {
+          const unsigned long long qq = pack2(qav[h], qav[h]);
+          acc[h][0] = ffma2(va.x, qq, acc[h][0]);
+          acc[h][1] = ffma2(va.y, qq, acc[h][1]);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const unsigned long long xx = pack2(xbv[k], xbv[k]);
-          acc2[0][k] = ffma2(qb0.x, xx, acc2[0][k]);
-          acc2[1][k] = ffma2(qb0.y, xx, acc2[1][k]);
-          acc2[2][k] = ffma2(qb1.x, xx, acc2[2][k]);
-          acc2[3][k] = ffma2(qb1.y, xx, acc2[3][k]);
-          acc8[k] = fmaf(qb8, xbv[k], acc8[k]);
+        for (int h = 0; h < H; ++h) {
+          const unsigned long long qq = pack2(qbv[h], qbv[h]);
+          acc[h][0] = ffma2(vb.x, qq, acc[h][0]);
+          acc[h][1] = ffma2(vb.y, qq, acc[h][1]);
         }
       };
-      // software pipeline, two register sets: the next pair's gathers are issued before the current pair is consumed
-      int t = 0;
+      // software pipeline over pairs of rows with two register sets: the next pair's gathers are issued before the
+      // current pair is consumed
+      ulonglong2 xc = xa, xd = xb;
 #pragma unroll 1
-      while (true) {
-        float4 xc = xa, xd = xb;
-        if (t + 2 < cnt) {
+      for (int t = 0; t < cnt; t += 4) {
+        const bool more = t + 2 < cnt;
+        if (more) {
           const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 2);
-          xc = *reinterpret_cast<const float4*>(xl + o.x);
-          xd = *reinterpret_cast<const float4*>(xl + o.y);
+          xc = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.x));
+          xd = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.y));
         }
         consume(xa, xb, t);
-        t += 2;
-        if (t >= cnt) break;
-        if (t + 2 < cnt) {
-          const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 2);
-          xa = *reinterpret_cast<const float4*>(xl + o.x);
-          xb = *reinterpret_cast<const float4*>(xl + o.y);
+        if (more) {
+          if (t + 4 < cnt) {
+            const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 4);
+            xa = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.x));
+            xb = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.y));
+          }
+          consume(xc, xd, t + 2);
         }
-        consume(xc, xd, t);
-        t += 2;
-        if (t >= cnt) break;
       }
       __syncwarp();
     }
     b_cur = b_nxt; total_cur = total_nxt; j_cur = j_nxt;
     b_nxt = b_nx2; total_nxt = total_nx2;
+    if (warp == 0) TL(5);
+    TS(3);
     // ---------------- 2. the previous tile's MMAs have finished reading the operand tiles
     if (tile > t_begin) {
       mbar_wait(&mbar, mma_phase);
       mma_phase ^= 1;
       tc_fence_after();
     }
+    if (warp == 0) TL(6);
+    TS(4);
     // ---------------- 3. this tile's rows -> B-operand tiles (split bf16), then the MMAs
     {
       const uint32_t off = sw128_off(row, c0 >> 3) + (uint32_t)(c0 & 7) * 2;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        float4 z;
-        if (h < 8) {
-          const unsigned long long a0 = acc2[h >> 1][0], a1 = acc2[h >> 1][1], a2 = acc2[h >> 1][2], a3 = acc2[h >> 1][3];
-          z = (h & 1) ? make_float4(hi32(a0), hi32(a1), hi32(a2), hi32(a3)) : make_float4(lo32(a0), lo32(a1), lo32(a2), lo32(a3));
-        } else {
-          z = make_float4(acc8[0], acc8[1], acc8[2], acc8[3]);
-        }
+        const float4 z = make_float4(lo32(acc[h][0]), hi32(acc[h][0]), lo32(acc[h][1]), hi32(acc[h][1]));
         uint2 hi, lo;
         split_bf16x4(z, hi, lo);
         *reinterpret_cast<uint2*>(z_hi + h * TILE_BYTES + off) = hi;
         *reinterpret_cast<uint2*>(z_lo + h * TILE_BYTES + off) = lo;
       }
     }
+    // the next tile's first 16 rows of x and P: pull them into L1 now (their indices, loaded at the top of this
+    // iteration, have arrived), so the next iteration starts on L1 hits
+#if PREFETCH_MODE == 2
+    if (tile + 1 < t_end) {
+      const float* xr = x + (unsigned)j_nxt * ldx32;
+      prefetch_l1(xr);
+      prefetch_l1(xr + 32);
+      const double* pr = P + (int64_t)j_nxt * H;
+      prefetch_l1(pr);
+      prefetch_l1(pr + H - 1);
+    }
+#endif
+    TS(5);
     fence_proxy_async();
     tc_fence_before();
     z_ready_arrive();      // non-blocking: go on with the next tile while warp 16 issues this one
+    if (warp == 0) TL(7);
+    TS(6);
+#ifdef EXP_TIMELINE
+    if (blockIdx.x == 0 && lane == 0 && tile - t_begin >= 20 && tile - t_begin < 84) g_tw[((tile - t_begin - 20) * 16 + warp) * 2 + 1] = now_ns();
+#endif
   }
   __syncthreads();
   if (warp == 0) {
@@ -416,5 +484,17 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
   GEOBI_LAUNCH_OK("feast_fused");
   return GEOBI_OK;
 }
+
+#ifdef EXP_TIMELINE
+extern "C" __attribute__((visibility("default"))) int geobi_debug_fused_timeline(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, fused::g_tl, sizeof(unsigned long long) * 64 * 8);
+}
+extern "C" __attribute__((visibility("default"))) int geobi_debug_fused_stages(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, fused::g_ts, sizeof(unsigned long long) * 64 * 2 * 8);
+}
+extern "C" __attribute__((visibility("default"))) int geobi_debug_fused_warps(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, fused::g_tw, sizeof(unsigned long long) * 64 * 16 * 2);
+}
+#endif
 
 }  // namespace geobi

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const __nv_bfloat16* __res
     fence_proxy_async();           // ... and are visible to the tensor core's async proxy
     tc_fence_before();
     __syncthreads();               // ... for every thread's copies
-    if (tid == 0) {
+    if (tid < 32 && elect_one()) {
       tc_fence_after();
       const uint32_t st = base + (uint32_t)(s * STAGE);
       const uint64_t ah = make_desc(st), bh = make_desc(st + SPLIT * A_BYTES);
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();                                   // also: every warp has finished reading TMEM of the previous chunk
-    if (tid == 0) {
+    if (tid < 32 && elect_one()) {
       tc_fence_after();
       const uint64_t ad = make_desc(smem_u32(a_t)), bd = make_desc(smem_u32(b_t));
       mma_f16(tmem_d, ad + 0, bd + 0, idesc, 0u);      // hi . hi   (k 0..15)
