@@ -458,6 +458,137 @@ __global__ void __launch_bounds__(256) feast_aggregate_packed_kernel(const float
   }
 }
 
+// ------------------------------------------------------------------------------ small-C variant (first layer: C_in = 6 / 12)
+// Four lanes per node (8 nodes per warp), lane sl owns channels [sl*V, sl*V+V).  Per chunk of four edge slots each lane
+// computes the soft assignments of one slot; the slot's nine weights and its row index then travel by quad shuffles, so
+// there is no shared memory and no warp barrier.  The generic kernel above spends a whole warp on such a node with
+// 6 or 12 of its 32 lanes active.
+template <int V, int OUT>
+__global__ void __launch_bounds__(256, V == 4 ? 3 : 2) feast_aggregate_small_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
+                                                                    const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                                    const double* __restrict__ P, const float* __restrict__ cvec,
+                                                                    void* __restrict__ Zout, int64_t ldz) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, sl = lane & 3;
+  const int64_t w0 = ((int64_t)blockIdx.x * 8 + warp) * 8;
+  if (w0 >= N) return;                               // whole warp past the end
+  const int64_t i_raw = w0 + g;
+  const bool live = i_raw < N;
+  const int64_t i = live ? i_raw : N - 1;            // dead quads shadow the last node and never store
+  const int b = rowptr[i];
+  const int total = rowptr[i + 1] - b + 1;           // neighbours + implicit self loop (slot 0)
+  int maxtotal = total;
+#pragma unroll
+  for (int o = 16; o >= 4; o >>= 1) maxtotal = max(maxtotal, __shfl_xor_sync(0xffffffffu, maxtotal, o));
+  const int c0 = sl * V;
+  const bool active = c0 < C;                        // C % V == 0 (host)
+  const unsigned ldx32 = (unsigned)ldx;
+  const float* xl = x + (active ? c0 : 0);
+  double Pi[H];
+  float ch[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    Pi[h] = P[i * H + h];
+    ch[h] = cvec[h];
+  }
+  float acc[H][V];
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[h][k] = 0.f;
+
+  for (int s0 = 0; s0 < maxtotal; s0 += 4) {
+    const int s = s0 + sl;
+    int j = (int)i;                                  // padding slots: weight 0 on the node's own (valid) row
+    float l[H];
+    if (s < total) {
+      if (s > 0) j = nbr[b + s - 1];
+      float m = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+        m = fmaxf(m, l[h]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        l[h] = __expf(l[h] - m);
+        sum += l[h];
+      }
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] *= inv;
+    } else {
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned jt = (unsigned)__shfl_sync(0xffffffffu, j, t, 4);
+      float xv[V];
+      VecLoad<V>::ld(xl + jt * ldx32, xv);
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float q = __shfl_sync(0xffffffffu, l[h], t, 4);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[h][k] = fmaf(q, xv[k], acc[h][k]);
+      }
+    }
+  }
+  if (!live) return;
+  if (!active) {
+    // bf16 planes feed a GEMM whose K is padded to a multiple of 64: the first idle lane zero-fills columns [9C, ldz)
+    if (OUT != 0 && c0 == C) {
+      __nv_bfloat16* zhi = static_cast<__nv_bfloat16*>(Zout) + i * ldz;
+      __nv_bfloat16* zlo = zhi + N * ldz;
+      for (int k = H * C; k < ldz; k += 2) {          // 9C and ldz are even
+        *reinterpret_cast<uint32_t*>(zhi + k) = 0u;
+        if (OUT == 2) *reinterpret_cast<uint32_t*>(zlo + k) = 0u;
+      }
+    }
+    return;
+  }
+  const float rcnt = 1.0f / (float)total;            // mean over the neighbourhood (scatter-mean upstream)
+  // one 4V-byte (fp32) / 2V-byte (bf16) store per head: C, c0 and ldz are multiples of V (host)
+  if (OUT == 0) {
+    float* zrow = static_cast<float*>(Zout) + i * ldz;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      if (V == 4) *reinterpret_cast<float4*>(zrow + h * C + c0) = make_float4(acc[h][0] * rcnt, acc[h][1] * rcnt, acc[h][2] * rcnt, acc[h][3] * rcnt);
+      else *reinterpret_cast<float2*>(zrow + h * C + c0) = make_float2(acc[h][0] * rcnt, acc[h][1] * rcnt);
+    }
+  } else {
+    __nv_bfloat16* zhi = static_cast<__nv_bfloat16*>(Zout) + i * ldz;
+    __nv_bfloat16* zlo = zhi + N * ldz;
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      __nv_bfloat16 hi[V], lo[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const float z = acc[h][k] * rcnt;
+        hi[k] = __float2bfloat16_rn(z);
+        lo[k] = __float2bfloat16_rn(z - __bfloat162float(hi[k]));
+      }
+      if (V == 4) {
+        *reinterpret_cast<uint2*>(zhi + h * C + c0) = *reinterpret_cast<const uint2*>(hi);
+        if (OUT == 2) *reinterpret_cast<uint2*>(zlo + h * C + c0) = *reinterpret_cast<const uint2*>(lo);
+      } else {
+        *reinterpret_cast<uint32_t*>(zhi + h * C + c0) = *reinterpret_cast<const uint32_t*>(hi);
+        if (OUT == 2) *reinterpret_cast<uint32_t*>(zlo + h * C + c0) = *reinterpret_cast<const uint32_t*>(lo);
+      }
+    }
+  }
+}
+
+template <int V>
+static void launch_small(int out_mode, cudaStream_t st, const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr,
+                         const int32_t* nbr, const double* P, const float* c, void* Z, int64_t ldz) {
+  const unsigned blocks = (unsigned)cdiv(N, 64);
+  if (out_mode == 0) feast_aggregate_small_kernel<V, 0><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else if (out_mode == 1) feast_aggregate_small_kernel<V, 1><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+  else feast_aggregate_small_kernel<V, 2><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
+}
+
 template <int NPW>
 static void launch_packed(int out_mode, cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
                           const double* P, const float* c, void* Z, int64_t ldz) {
@@ -808,6 +939,18 @@ static void launch_aggregate(int out_mode, unsigned blocks, cudaStream_t st, con
   else feast_aggregate_kernel<CPL, 2, VEC><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
 }
 
+// 4 / 2: channels per lane of the small-C kernel that will run for this layer; 0: another kernel
+static int small_c_variant(int c_in, int64_t ldx, int64_t ldz, const float* x, bool row_map) {
+  if (row_map || getenv("GEOBI_NO_SMALLC") != nullptr) return 0;
+  if (c_in <= 12 && c_in % 4 == 0 && ldx % 4 == 0 && ldz % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) return 4;
+  if (c_in <= 6 && c_in % 2 == 0 && ldx % 2 == 0 && ldz % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0) return 2;
+  return 0;
+}
+// true when the aggregation kernel itself zero-fills the K padding of the bf16 planes (no memset needed)
+bool feast_aggregate_fills_padding(int c_in, int64_t ldx, int64_t ldz, const float* x, bool row_map) {
+  return small_c_variant(c_in, ldx, ldz, x, row_map) != 0;
+}
+
 int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const float* U, double* P, cudaStream_t st) {
   const size_t psm = proj_smem_bytes(c_in);
   feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, P);
@@ -843,7 +986,11 @@ int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in
     else if (c_in == 64) rc = launch_ps<2, 16>(out_mode, st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
     else rc = launch_ps<1, 16>(out_mode, st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
     if (rc) return rc;
-  } else if (cpl == 1) launch_aggregate<1, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);   // scalar loads are always aligned
+  } else if (small_c_variant(c_in, ldx, ldz, x, row_map != nullptr) == 4)
+    launch_small<4>(out_mode, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);     // first facet layer (C_in = 12)
+  else if (small_c_variant(c_in, ldx, ldz, x, row_map != nullptr) == 2)
+    launch_small<2>(out_mode, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);     // first vertex layer (C_in = 6)
+  else if (cpl == 1) launch_aggregate<1, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);   // scalar loads are always aligned
   else if (cpl == 2 && vec_ok) launch_aggregate<2, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
   else if (cpl == 2) launch_aggregate<2, false>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
   else if (vec_ok) launch_aggregate<4, true>(out_mode, ab, st, x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);

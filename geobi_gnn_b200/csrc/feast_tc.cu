@@ -344,6 +344,7 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
 int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
                                 const int32_t* row_map, int64_t n_src, const float* U, const float* c, double* P, void* Z, int64_t ldz,
                                 int out_mode, cudaStream_t st);
+bool feast_aggregate_fills_padding(int c_in, int64_t ldx, int64_t ldz, const float* x, bool row_map);
 
 struct TcWs {
   double* P;
@@ -383,7 +384,7 @@ int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t
   carve_tc(cv, N, c_in, c_out, &Wk);
   const int K = tc::H * c_in;
   const int kpad = (int)(cdiv(K, tc::BK) * tc::BK);
-  if (kpad != K) GEOBI_CUDA_OK(cudaMemsetAsync(Wk.Z, 0, sizeof(__nv_bfloat16) * (size_t)(passes == 3 ? 2 : 1) * N * kpad, st));
+  if (kpad != K && !feast_aggregate_fills_padding(c_in, ldx, kpad, x, row_map != nullptr)) GEOBI_CUDA_OK(cudaMemsetAsync(Wk.Z, 0, sizeof(__nv_bfloat16) * (size_t)(passes == 3 ? 2 : 1) * N * kpad, st));
   tc::prep_weight_kernel<<<64, 256, 0, st>>>(W, c_out, K, kpad, 1, c_in, Wk.Bq);
   int rc = feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, row_map, n_src, U, c, Wk.P, Wk.Z, kpad, passes == 3 ? 2 : 1, st);
   if (rc) return rc;
