@@ -38,6 +38,11 @@ def collate_dual(patches: Sequence[Tuple[Data, Data]]) -> Tuple[Data, Data, dict
         data_v.depth_direction = cat(vs, "depth_direction")
     data_f = Data(x=cat(fs, "x"), edge_index=cat(fs, "edge_index", f_off, 1), edge_weight=cat(fs, "edge_weight"), y=cat(fs, "y"),
                   fv_indices=cat(fs, "fv_indices", v_off))
+    # the union of sorted lists with increasing offsets is sorted; it stays symmetric and duplicate-free
+    if all("coalesced_undirected" in d and d.coalesced_undirected for d in vs):
+        data_v.coalesced_undirected = True
+    if all("coalesced_undirected" in d and d.coalesced_undirected for d in fs):
+        data_f.coalesced_undirected = True
     slices = dict(v=[(o, o + d.x.size(0)) for o, d in zip(v_off, vs)], f=[(o, o + d.x.size(0)) for o, d in zip(f_off, fs)])
     return data_v, data_f, slices
 
@@ -49,7 +54,8 @@ def shard(items: Sequence, rank: int, world: int) -> List:
 
 def fresh_view(data: Data) -> Data:
     """New Data over the same tensors with graph tags dropped: what a caller holding only the
-    reference's input layout (x, int64 edge_index, edge_weight, fv_indices) would pass."""
+    reference's input layout (x, int64 edge_index, edge_weight, fv_indices) would pass (the `coalesced_undirected`
+    flag, a fact about how the dataset built the list, travels with it)."""
     out = Data()
     for k in data.keys:
         v = getattr(data, k)

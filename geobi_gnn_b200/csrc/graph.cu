@@ -901,3 +901,96 @@ extern "C" int geobi_remove_self_loops(const int64_t* row, const int64_t* col, c
   GEOBI_LAUNCH_OK("remove_self_loops");
   return GEOBI_OK;
 }
+
+// ------------------------------------------------------------------------------ CSR of a coalesced undirected edge list
+// When the caller knows its edge list is what to_undirected / coalesce produce (non-loop entries sorted by (row, col), no
+// duplicates, (j,i) present for every (i,j)) the CSR needs no counting pass, no atomics and no row sort: dropping the loops
+// is an order-preserving compaction and rowptr is the list of row boundaries.  Being symmetric, the same CSR is the
+// conv's target-indexed adjacency and the matcher's source-indexed one.  The promise is verified on the device; a list
+// that breaks it poisons rowptr[n_nodes] with -1, which the caller sees with the entry count it has to read anyway.
+namespace geobi {
+__global__ void sorted_scatter_kernel(const int64_t* __restrict__ row, const int64_t* __restrict__ col, const float* __restrict__ w, int64_t E,
+                                      int64_t n, const int* __restrict__ offs, int* __restrict__ rows32, int32_t* __restrict__ nbr,
+                                      float* __restrict__ w_out, int64_t* __restrict__ ei_out, int* __restrict__ bad) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t r = row[e], c = col[e];
+  if (r < 0 || r >= n || c < 0 || c >= n) {
+    *bad = 1;
+    return;
+  }
+  if (r == c) return;
+  const int64_t o = offs[e];
+  rows32[o] = (int)r;
+  nbr[o] = (int)c;
+  if (w_out) w_out[o] = w[e];
+  if (ei_out) {
+    ei_out[o] = r;
+    ei_out[E + o] = c;
+  }
+}
+// thread p in [0, nnz]: rowptr entries of the rows that start between entries p-1 and p; order check of the pair
+__global__ void sorted_rowptr_kernel(const int* __restrict__ rows32, const int32_t* __restrict__ nbr, const int* __restrict__ offs, int64_t E,
+                                     int64_t n, int32_t* __restrict__ rowptr, int* __restrict__ bad) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nnz = offs[E];
+  if (p > nnz) return;
+  const int64_t r = p < nnz ? rows32[p] : n;
+  const int64_t prev = p > 0 ? rows32[p - 1] : -1;
+  if (p > 0 && p < nnz && (prev > r || (prev == r && nbr[p - 1] >= nbr[p]))) *bad = 1;   // not sorted / duplicate
+  for (int64_t q = prev + 1; q <= r; ++q) rowptr[q] = (int)p;
+}
+__global__ void sorted_symmetry_kernel(const int* __restrict__ rows32, const int32_t* __restrict__ nbr, const int* __restrict__ offs, int64_t E,
+                                       const int32_t* __restrict__ rowptr, int* __restrict__ bad) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= offs[E]) return;
+  const int r = rows32[p], c = nbr[p];
+  int lo = rowptr[c], hi = rowptr[c + 1];            // find r in row c
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (nbr[mid] < r) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lo >= rowptr[c + 1] || nbr[lo] != r) *bad = 1;
+}
+__global__ void sorted_verdict_kernel(const int* __restrict__ bad, int32_t* __restrict__ rowptr, int64_t n) {
+  if (*bad) rowptr[n] = -1;
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_csr_from_sorted_coo_ws_bytes(int64_t n_edges) {
+  return 3 * align256((size_t)(n_edges + 2) * sizeof(int)) + scan_ws_bytes(n_edges + 1) + 512;
+}
+
+extern "C" int geobi_csr_from_sorted_coo(const int64_t* row, const int64_t* col, const float* w, int64_t n_edges, int64_t n_nodes, int flags,
+                                         int32_t* rowptr, int32_t* nbr, float* w_out, int64_t* ei_out, void* ws, size_t ws_bytes,
+                                         void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(n_edges >= 0 && n_nodes >= 0 && rowptr != nullptr, "csr_from_sorted_coo: bad arguments");
+  GEOBI_REQUIRE(n_edges == 0 || (row && col && nbr), "csr_from_sorted_coo: null edge arrays");
+  GEOBI_REQUIRE((w == nullptr) == (w_out == nullptr), "csr_from_sorted_coo: w and w_out must both be given or both be NULL");
+  GEOBI_REQUIRE(n_edges < ((int64_t)1 << 31) && n_nodes < ((int64_t)1 << 31), "csr_from_sorted_coo: int32 CSR overflow");
+  if (n_edges == 0) {
+    GEOBI_CUDA_OK(cudaMemsetAsync(rowptr, 0, sizeof(int32_t) * (size_t)(n_nodes + 1), st));
+    return GEOBI_OK;
+  }
+  if (!ws || ws_bytes < geobi_csr_from_sorted_coo_ws_bytes(n_edges)) { set_error("csr_from_sorted_coo: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  Carver c(ws, ws_bytes);
+  int* flag = c.take<int>(n_edges + 2);
+  int* offs = c.take<int>(n_edges + 2);
+  int* rows32 = c.take<int>(n_edges + 2);
+  int* bad = c.take<int>(64);
+  const size_t sb = scan_ws_bytes(n_edges + 1);
+  char* scan = c.take<char>(sb);
+  GEOBI_CUDA_OK(cudaMemsetAsync(bad, 0, sizeof(int), st));
+  const unsigned blocks = (unsigned)cdiv(n_edges + 1, 256);
+  rsl_flag_kernel<<<blocks, 256, 0, st>>>(row, col, n_edges, flag);
+  int rc = scan_i32(flag, offs, n_edges, scan, sb, st);
+  if (rc) return rc;
+  sorted_scatter_kernel<<<blocks, 256, 0, st>>>(row, col, w, n_edges, n_nodes, offs, rows32, nbr, w_out, ei_out, bad);
+  sorted_rowptr_kernel<<<blocks, 256, 0, st>>>(rows32, nbr, offs, n_edges, n_nodes, rowptr, bad);
+  if (flags & GEOBI_SORTED_CHECK_SYMMETRIC) sorted_symmetry_kernel<<<blocks, 256, 0, st>>>(rows32, nbr, offs, n_edges, rowptr, bad);
+  sorted_verdict_kernel<<<1, 1, 0, st>>>(bad, rowptr, n_nodes);
+  GEOBI_LAUNCH_OK("csr_from_sorted_coo");
+  return GEOBI_OK;
+}

@@ -31,13 +31,15 @@ def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda"):
     edge_idx_v = data_util.to_undirected_with_self_loops(ev.t().contiguous(), pos_v.size(0))
     edge_wei_v = data_util.calc_weight(pos_v, normal_v, edge_idx_v)
     graph_v = Data(name=f"{name}-v", pos=pos_v, normal=normal_v, edge_index=edge_idx_v, edge_weight=edge_wei_v,
-                   depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1])
+                   depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1], coalesced_undirected=True)
     pos_f = pos_v[fv].mean(1)
     normal_f = _t(mesh_n.face_normals, torch.float32, device).reshape(-1, 3)
     edge_idx_f = data_util.build_facet_graph(fv, vf)
     edge_wei_f = data_util.calc_weight(pos_f, normal_f, edge_idx_f)
     graph_f = Data(name=f"{name}-f", pos=pos_f, normal=normal_f, edge_index=edge_idx_f, edge_weight=edge_wei_f,
-                   fv_indices=fv, edge_dual=edge_dual_fv[0])
+                   fv_indices=fv, edge_dual=edge_dual_fv[0], coalesced_undirected=True)
+    # coalesced_undirected: both builders above emit sorted, duplicate-free, symmetric lists (self loops aside), which
+    # lets the network build one CSR per graph without a sort (nn.input_graph); the device verifies the claim
     if mesh_o is not None:
         graph_v.y = _t(mesh_o.points, torch.float32, device)
         graph_f.y = _t(mesh_o.face_normals, torch.float32, device)

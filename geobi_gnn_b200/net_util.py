@@ -32,6 +32,18 @@ def _match_csr(data) -> Optional[CSRGraph]:
     w = data.edge_weight if "edge_weight" in data else None
     n = data.x.size(0)
     tag = gnn.tag_of(ei)
+    st = tag.get("sorted")
+    if st is not None and st[0].n == n and st[3] is w:   # nn.input_graph built it from this very (edge_index, edge_weight)
+        g, ei2, w2, _ = st
+        nnz = g.nnz                                      # the one sync of this level; raises if the list broke its promise
+        if nnz == 0:
+            return None
+        if nnz != ei.size(1):                            # the reference's write-back of the stripped list (net_util.py:163-167)
+            ei_s = ei2[:, :nnz]
+            t2 = gnn.tag_of(ei_s)
+            t2["tgt"] = t2["src"] = g
+            data.edge_index, data.edge_weight = ei_s, (None if w2 is None else w2[:nnz])
+        return g
     g = tag.get("src")
     if g is not None and g.n == n:                       # built by us: no self loops, CSR order == edge order
         if g.cap == 0:

@@ -21,7 +21,7 @@ from torch import nn
 
 from . import config, data_util, ops
 from .net_util import PoolingLayer, DualFusionLayer  # noqa: F401  (DualFusionLayer re-exported as upstream, network.py:19)
-from .nn import FeaStConv, conv_csr
+from .nn import FeaStConv, conv_csr, input_graph
 
 
 class GNNModule(nn.Module):
@@ -51,7 +51,7 @@ class GNNModule(nn.Module):
 
         x0 = data_r1.x
         n1 = x0.size(0)
-        g1 = conv_csr(data_r1.edge_index, n1)
+        g1 = input_graph(data_r1, n1)
         if torch.is_grad_enabled() and (x0.requires_grad or self.l_conv1.lin.weight.requires_grad):
             return self._forward_train(data_r1, g1, rec)
         buf1 = x0.new_empty((n1, 64))                                   # [ l_conv1 | r_conv3 ]  (network.py:298 cat)

@@ -49,6 +49,24 @@ def conv_csr(edge_index: Union[torch.Tensor, CSRGraph], n: int) -> CSRGraph:
     return g
 
 
+def input_graph(data, n: int) -> CSRGraph:
+    """Conv CSR of an input-level graph.  A Data that carries `coalesced_undirected=True` (dataset.py builds its graphs
+    with to_undirected / build_facet_graph, so ours sets it) gets the sort-free builder, whose result also serves the
+    matcher of the first pooling layer (net_util._match_csr); anything else goes through conv_csr."""
+    ei = data.edge_index
+    tag = tag_of(ei)
+    g = tag.get("tgt")
+    if g is not None and g.n == n:
+        return g
+    if "coalesced_undirected" in data and data.coalesced_undirected:
+        w = data.edge_weight if "edge_weight" in data else None
+        g, ei2, w2 = ops.csr_from_sorted_coo(ei, n, w)
+        tag["tgt"] = g
+        tag["sorted"] = (g, ei2, w2, w)
+        return g
+    return conv_csr(ei, n)
+
+
 class FeaStConv(torch.nn.Module):
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1):
         super().__init__()

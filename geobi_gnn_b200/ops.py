@@ -147,6 +147,9 @@ class CSRGraph:
     def nnz(self) -> int:
         if self._nnz is None:
             self._nnz = int(self.rowptr[self.n].item()) if self.n > 0 else 0      # syncs
+            if self._nnz < 0:      # geobi_csr_from_sorted_coo's verdict
+                raise _lib.GeobiError("edge list was declared coalesced_undirected but is not: its non-loop entries must be sorted "
+                                      "by (row, col), unique, in range, and contain (j,i) for every (i,j)")
         return self._nnz
 
     @property
@@ -216,6 +219,30 @@ def csr_from_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional[torch.
     k = int(nnz.value)
     g = CSRGraph(rowptr, nbr[:k], n_nodes, k, None if w_out is None else w_out[:k])
     return (g, eid[:k]) if want_eid else g
+
+
+def csr_from_sorted_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional[torch.Tensor] = None, check_symmetric: bool = True):
+    """CSR of a coalesced, undirected edge list (self loops allowed anywhere, they are dropped): no sort, no sync.
+    Returns (CSRGraph with lazy nnz, stripped edge list buffer int64 [2,E], stripped weight buffer or None); the first
+    `.nnz` read raises if the list was not what it was declared to be."""
+    _need_cuda(edge_index, weight)
+    lib = _lib.load()
+    ei = edge_index.contiguous()
+    if ei.dtype != torch.int64:
+        ei = ei.long()
+    e = ei.size(1)
+    dev = ei.device
+    rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+    nbr = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+    w = None if weight is None else weight.contiguous().float()
+    w_out = None if w is None else torch.empty(max(e, 1), dtype=torch.float32, device=dev)
+    ei_out = torch.empty((2, max(e, 1)), dtype=torch.int64, device=dev)
+    ws = _ws(lib.geobi_csr_from_sorted_coo_ws_bytes(e), dev)
+    _lib.check(lib.geobi_csr_from_sorted_coo(_ptr(ei[0]), _ptr(ei[1]), _ptr(w), e, n_nodes, 1 if check_symmetric else 0, _ptr(rowptr),
+                                             _ptr(nbr), _ptr(w_out), _ptr(ei_out) if e else None, _ptr(ws), ws.numel(), _stream()),
+               "csr_from_sorted_coo")
+    _count(8)
+    return CSRGraph(rowptr, nbr, n_nodes, 0 if e == 0 else None, w_out, True), ei_out, w_out
 
 
 def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor) -> CSRGraph:

@@ -83,6 +83,21 @@ GEOBI_API int geobi_csr_from_coo(const int64_t* row, const int64_t* col, const f
                        int64_t n_nodes, int flags, int32_t* rowptr, int32_t* nbr, float* w_out,
                        int64_t* eid_out, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream);
 
+/* CSR of an edge list the caller knows to be coalesced and undirected — what the reference's dataset builds with
+ * to_undirected (+ add_self_loops appended last, dataset.py:211-213) and build_facet_graph (data_util.py:436-456): the
+ * non-loop entries are sorted by (row, col) without duplicates and (j,i) is present for every (i,j).  Self loops are
+ * dropped (net_util.py:163; FeaStConv re-adds its own) by an order-preserving compaction, rowptr is the list of row
+ * boundaries: no counting pass, no atomics, no row sort.  The result serves the conv (target-indexed) and the matcher
+ * (source-indexed, entry order == edge order, so w_out lines up with it).  ei_out (optional, int64 [2, n_edges] with row
+ * stride n_edges) receives the stripped edge list.  The entry count stays on the device in rowptr[n_nodes]; if the list
+ * breaks the promise (out of range, unsorted, duplicate, or - with GEOBI_SORTED_CHECK_SYMMETRIC - a missing reverse edge)
+ * rowptr[n_nodes] is set to -1 instead.  Asynchronous. */
+#define GEOBI_SORTED_CHECK_SYMMETRIC 1
+GEOBI_API size_t geobi_csr_from_sorted_coo_ws_bytes(int64_t n_edges);
+GEOBI_API int geobi_csr_from_sorted_coo(const int64_t* row, const int64_t* col, const float* w, int64_t n_edges,
+                              int64_t n_nodes, int flags, int32_t* rowptr, int32_t* nbr, float* w_out,
+                              int64_t* ei_out, void* ws, size_t ws_bytes, void* stream);
+
 /* torch_geometric.utils.remove_self_loops (net_util.py:163,292) with the surviving count already known to the caller
  * (e.g. the nnz of a DROP_SELF CSR of the same list): order-preserving compaction into out [2,count] (+ w_out), no sync. */
 GEOBI_API size_t geobi_remove_self_loops_ws_bytes(int64_t n_edges);

@@ -162,3 +162,38 @@ def test_pool_step_matches_oracle(n):
             assert util.rel_err(g3.w, want_w2) < 1e-5
         xm = ops.segment_reduce(x.to(DEV)[:nc], m2, mem2, nc2, ops.OP_MAX)
         assert util.rel_err(xm, pyg.scatter(x[:nc], cl2, dim=0, reduce="max")) < 1e-7
+
+
+@pytest.mark.gpu
+def test_csr_from_sorted_coo_matches_general_builder_and_rejects_broken_promises():
+    """nn.input_graph's sort-free CSR (dataset lists are coalesced + undirected) == the general builder's, bit for bit;
+    a list that is not what it claims poisons the count and the first nnz read raises."""
+    import geobi_gnn_b200 as pkg
+    from geobi_gnn_b200 import ops, _lib
+    (dv, df), _, _ = util.oracle_inputs(5)
+    for d in (dv, df):
+        ei = d.edge_index.to(DEV)
+        n = d.x.shape[0]
+        w = torch.rand(ei.size(1), device=DEV)
+        want = ops.csr_from_coo(ei, n, w, ops.COO_DROP_SELF)                       # stable by source = matcher CSR
+        conv = ops.csr_from_coo(ei, n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+        g, ei2, w2 = ops.csr_from_sorted_coo(ei, n, w)
+        assert g.nnz == want.nnz
+        assert torch.equal(g.rowptr, want.rowptr) and torch.equal(g.nbr, want.nbr) and torch.equal(g.w, want.w)
+        assert torch.equal(g.rowptr, conv.rowptr) and torch.equal(g.nbr, conv.nbr)
+        keep = ei[0] != ei[1]
+        assert torch.equal(ei2[:, :g.nnz], ei[:, keep]) and torch.equal(w2[:g.nnz], w[keep])
+    ei = dv.edge_index.to(DEV)
+    n = dv.x.shape[0]
+    broken = [ei.flip(1),                                                        # unsorted
+              torch.cat([ei[:, :5], ei[:, 4:]], 1),                              # duplicate
+              ei[:, (ei[0] != ei[0, 0]) | (ei[1] == ei[0])]]                     # one node's out-edges missing: asymmetric
+    for bad in broken:
+        g, _, _ = ops.csr_from_sorted_coo(bad.contiguous(), n, None)
+        with pytest.raises(_lib.GeobiError):
+            g.nnz
+    g, _, _ = ops.csr_from_sorted_coo(broken[2].contiguous(), n, None, check_symmetric=False)
+    assert g.nnz > 0
+    e0 = torch.empty((2, 0), dtype=torch.int64, device=DEV)
+    g, _, _ = ops.csr_from_sorted_coo(e0, 7, None)
+    assert g.nnz == 0 and torch.equal(g.rowptr, torch.zeros(8, dtype=torch.int32, device=DEV))

@@ -117,3 +117,36 @@ def test_free_running_forward_invariants():
             single = torch.bincount(lab, minlength=n)[lab] == 1
             ei = g.edge_index().cpu()
             assert not (single[ei[0]] & single[ei[1]]).any()
+
+
+@pytest.mark.gpu
+def test_dualgnn_same_bits_with_and_without_the_coalesced_hint():
+    """The sort-free input-graph path (Data.coalesced_undirected) must not change a single bit of the forward."""
+    from geobi_gnn_b200 import batching, dataset, network, synth
+    torch.manual_seed(3)
+    net = network.DualGNN().to(DEV).eval()
+    patches = []
+    for seed in range(2):
+        mn, mo = util.noisy_icosphere(3, seed=seed)
+        patches.append(dataset.build_dual_data(mn, mo, device=DEV))
+    dv, df, _ = batching.collate_dual(patches)
+    assert dv.coalesced_undirected and df.coalesced_undirected
+
+    def run(hint):
+        a, b = batching.fresh_view(dv), batching.fresh_view(df)
+        if not hint:
+            a.coalesced_undirected = None
+            b.coalesced_undirected = None
+        for pl in util.poolings(net):
+            pl.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
+        with torch.no_grad():
+            out = net([a, b])
+        return [o.clone() for o in out if torch.is_tensor(o)], a, b
+
+    o1, a1, b1 = run(True)
+    o0, a0, b0 = run(False)
+    assert len(o1) == len(o0) and len(o1) > 0
+    for x, y in zip(o1, o0):
+        assert torch.equal(x, y)
+    assert torch.equal(a1.edge_index, a0.edge_index) and torch.equal(b1.edge_index, b0.edge_index)   # stripped write-back
+    assert torch.equal(a1.edge_weight, a0.edge_weight)
