@@ -79,3 +79,50 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         depth = torch.nn.functional.normalize(torch.from_numpy(points_noisy).to(dev), dim=1)
     V = data_util.update_position2(Vp, fv, vf, Np, n_iter, depth_direction=depth)
     return (V, Np, Vp, n_patches) if return_parts else (V, Np, Vp)
+
+
+class HostBatchRunner:
+    """DualGNN over a stream of HOST-resident batches (the reference's DataLoader hands the network CPU tensors,
+    train_dual.py:204-218 / test_dual.py:44-61): batch k+1 is uploaded on a copy stream while batch k computes, and
+    each batch's outputs are read back into pinned host buffers.
+
+        runner = HostBatchRunner(net, "cuda")
+        nxt = runner.upload(host_v, host_f)            # dicts of pinned CPU tensors: x, edge_index, edge_weight (+ fv_indices)
+        for ...:
+            cur, nxt = nxt, runner.upload(next_host_v, next_host_f)
+            vert_host, normal_host = runner.run(cur)   # valid after torch.cuda.current_stream().synchronize()
+    """
+
+    def __init__(self, net, device="cuda", coalesced_undirected: bool = False):
+        self.net, self.dev = net, torch.device(device)
+        self.copy_stream = torch.cuda.Stream(self.dev)
+        self.flag = coalesced_undirected      # the host lists come from dataset.py's builders (see nn.input_graph)
+        self.out_host = {}
+
+    def upload(self, host_v: dict, host_f: dict):
+        from .data import Data
+        with torch.cuda.stream(self.copy_stream):
+            dv = Data(**{k: t.to(self.dev, non_blocking=True) for k, t in host_v.items()})
+            df = Data(**{k: t.to(self.dev, non_blocking=True) for k, t in host_f.items()})
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        if self.flag:
+            dv.coalesced_undirected = df.coalesced_undirected = True
+        return dv, df, ev
+
+    def run(self, handle):
+        dv, df, ev = handle
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(ev)
+        for d in (dv, df):
+            for k in d.keys:
+                t = getattr(d, k)
+                if torch.is_tensor(t):
+                    t.record_stream(cur)       # allocated on the copy stream, consumed here
+        with torch.no_grad():
+            vert_p, norm_p, _ = self.net([dv, df])
+        for k, t in (("v", vert_p), ("n", norm_p)):
+            if k not in self.out_host or self.out_host[k].shape != t.shape:
+                self.out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            self.out_host[k].copy_(t, non_blocking=True)
+        return self.out_host["v"], self.out_host["n"]

@@ -150,3 +150,34 @@ def test_dualgnn_same_bits_with_and_without_the_coalesced_hint():
         assert torch.equal(x, y)
     assert torch.equal(a1.edge_index, a0.edge_index) and torch.equal(b1.edge_index, b0.edge_index)   # stripped write-back
     assert torch.equal(a1.edge_weight, a0.edge_weight)
+
+
+@pytest.mark.gpu
+def test_host_batch_runner_equals_direct_forward():
+    """inference.HostBatchRunner (pinned host batches, upload on a copy stream) returns the bits of a plain forward."""
+    from geobi_gnn_b200 import batching, dataset, inference, network
+    torch.manual_seed(5)
+    net = network.DualGNN().to(DEV).eval()
+    batches = []
+    for seed in range(3):
+        mn, mo = util.noisy_icosphere(3, seed=10 + seed)
+        dv, df = dataset.build_dual_data(mn, mo, device=DEV)
+        batches.append((dv, df))
+    for pl in util.poolings(net):
+        pl.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
+    want = []
+    with torch.no_grad():
+        for dv, df in batches:
+            vp, nrm, _ = net([batching.fresh_view(dv), batching.fresh_view(df)])
+            want.append((vp.cpu(), nrm.cpu()))
+    host = [({k: getattr(dv, k).cpu().pin_memory() for k in ("x", "edge_index", "edge_weight")},
+             {k: getattr(df, k).cpu().pin_memory() for k in ("x", "edge_index", "edge_weight", "fv_indices")}) for dv, df in batches]
+    runner = inference.HostBatchRunner(net, DEV, coalesced_undirected=True)
+    nxt = runner.upload(*host[0])
+    for i in range(3):
+        cur = nxt
+        if i + 1 < 3:
+            nxt = runner.upload(*host[i + 1])
+        v, n = runner.run(cur)
+        torch.cuda.synchronize()
+        assert torch.equal(v, want[i][0]) and torch.equal(n, want[i][1])
