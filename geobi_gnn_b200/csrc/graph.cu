@@ -489,34 +489,42 @@ __device__ __forceinline__ bool precedes(int rv, int v, int ru, int u) { return 
 // blk[u] caches the node u is waiting for, so a blocked node costs 3 loads per sweep.
 constexpr int GRACLUS_MAX_SWEEPS = 1 << 20;
 
-// One evaluation of node u.  Neighbour rows are read in chunks of 8 with all loads of a chunk (ids -> labels, ranks,
-// weights) issued back to back, so a decision costs ~3 dependent memory latencies per chunk instead of 3 per neighbour:
+// One evaluation of node u.  Neighbour rows are read in chunks of 8 with all loads of a chunk (ids -> states, weights)
+// issued back to back, so a decision costs ~2 dependent memory latencies per chunk instead of 3 per neighbour:
 // the critical path of the whole matching is (dependency depth ~18) x (decision latency).
+// st[v] = {label, rank} interleaved: one 8-byte gather per neighbour returns both (the kernel is bound by L2 sector
+// requests: ~50 scattered reads per evaluation with separate arrays, ~25 with the pair).
 constexpr int GCH = 8;
+__device__ __forceinline__ int2 ld_state(const int2* st, int v) {
+  const long long raw = __ldcg(reinterpret_cast<const long long*>(st) + v);
+  return make_int2((int)(raw & 0xffffffffll), (int)(raw >> 32));
+}
 __device__ __forceinline__ int graclus_try(int u, const int* __restrict__ rowptr, const int* __restrict__ nbr, const float* __restrict__ w,
-                                           const int* __restrict__ rank, int* label, int* blk) {
-  if (__ldcg(label + u) >= 0) return 1;  // claimed by a partner
+                                           int2* st, int* blk, int* __restrict__ label_out) {
+  int* lab = reinterpret_cast<int*>(st);           // label of node v at lab[2 * v]
+  const int2 su = ld_state(st, u);
+  if (su.x >= 0) { label_out[u] = su.x; return 1; }   // claimed by a partner
   const int b = blk[u];
-  if (b >= 0 && __ldcg(label + b) < 0) return 0;   // the node we are waiting for is still undecided (fast path)
-  const int ru = rank[u];
+  if (b >= 0 && __ldcg(lab + 2 * b) < 0) return 0;    // the node we are waiting for is still undecided (fast path)
+  const int ru = su.y;
   const int end = rowptr[u + 1];
   int best = -1, blocker = -1;
   float wmax = 0.f;
   for (int e0 = rowptr[u]; e0 < end && blocker < 0; e0 += GCH) {
-    int v[GCH], lv[GCH], rk[GCH];
+    int v[GCH];
+    int2 sv[GCH];
     float wt[GCH];
 #pragma unroll
     for (int k = 0; k < GCH; ++k) v[k] = e0 + k < end ? nbr[e0 + k] : -1;
 #pragma unroll
     for (int k = 0; k < GCH; ++k) {
-      lv[k] = v[k] >= 0 ? __ldcg(label + v[k]) : 0;
-      rk[k] = v[k] >= 0 ? rank[v[k]] : 0;
+      sv[k] = v[k] >= 0 ? ld_state(st, v[k]) : make_int2(0, 0);
       wt[k] = (w && v[k] >= 0) ? w[e0 + k] : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < GCH; ++k) {
-      if (v[k] < 0 || lv[k] >= 0 || blocker >= 0) continue;
-      if (precedes(rk[k], v[k], ru, u)) { blocker = v[k]; continue; }   // an earlier neighbour is still undecided
+      if (v[k] < 0 || sv[k].x >= 0 || blocker >= 0) continue;
+      if (precedes(sv[k].y, v[k], ru, u)) { blocker = v[k]; continue; }   // an earlier neighbour is still undecided
       if (!w) { if (best < 0) best = v[k]; }
       else if (wt[k] >= wmax) { best = v[k]; wmax = wt[k]; }
     }
@@ -525,38 +533,45 @@ __device__ __forceinline__ int graclus_try(int u, const int* __restrict__ rowptr
   // Only earlier neighbours can claim u, and a claimer CASes label[u] *before* it publishes its own label.  All of them
   // are now observed decided, so after this fence a claim on u (if any) is visible; if none, nobody can claim u any more.
   __threadfence();
-  if (__ldcg(label + u) >= 0) return 1;
+  const int lu = __ldcg(lab + 2 * u);
+  if (lu >= 0) { label_out[u] = lu; return 1; }
   if (best < 0) {
-    __stcg(label + u, u);                // no free neighbour: singleton
+    __stcg(lab + 2 * u, u);              // no free neighbour: singleton
+    label_out[u] = u;
     return 1;
   }
   const int bend = rowptr[best + 1];
   for (int e0 = rowptr[best]; e0 < bend; e0 += GCH) {
-    int z[GCH], lz[GCH], rz[GCH];
+    int z[GCH];
+    int2 sz[GCH];
 #pragma unroll
     for (int k = 0; k < GCH; ++k) z[k] = e0 + k < bend ? nbr[e0 + k] : -1;
 #pragma unroll
-    for (int k = 0; k < GCH; ++k) {
-      lz[k] = z[k] >= 0 ? __ldcg(label + z[k]) : 0;
-      rz[k] = z[k] >= 0 ? rank[z[k]] : 0;
-    }
+    for (int k = 0; k < GCH; ++k) sz[k] = z[k] >= 0 ? ld_state(st, z[k]) : make_int2(0, 0);
 #pragma unroll
     for (int k = 0; k < GCH; ++k)
-      if (z[k] >= 0 && lz[k] < 0 && precedes(rz[k], z[k], ru, u)) { blk[u] = z[k]; return 0; }   // it may still claim `best`
+      if (z[k] >= 0 && sz[k].x < 0 && precedes(sz[k].y, z[k], ru, u)) { blk[u] = z[k]; return 0; }   // it may still claim `best`
   }
   const int l = best < u ? best : u;
-  if (atomicCAS(label + best, -1, l) != -1) { blk[u] = -1; return 0; }   // lost a race against a stale view: retry
+  if (atomicCAS(lab + 2 * best, -1, l) != -1) { blk[u] = -1; return 0; }   // lost a race against a stale view: retry
   __threadfence();
-  __stcg(label + u, l);
+  __stcg(lab + 2 * u, l);
+  label_out[u] = l;
   return 1;
 }
 
+__global__ void graclus_init_kernel(const int* __restrict__ rank, int n, int2* __restrict__ st, int* __restrict__ pos) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n) return;
+  st[u] = make_int2(-1, rank[u]);        // -1 = undecided
+  pos[u] = -1;                           // node this one is waiting for (-1 none, -2 done)
+}
+
 __global__ void __launch_bounds__(256) graclus_async_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr,
-                                                            const float* __restrict__ w, const int* __restrict__ rank, int* label,
-                                                            int n, int* pos, int* undecided) {
+                                                            const float* __restrict__ w, int2* st, int* __restrict__ label, int n, int* pos,
+                                                            int* undecided) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
-  for (int u = tid; u < n; u += stride) pos[u] = -1;   // pos = node this one is waiting for (-1 none, -2 done)
   int left = 0;
   for (int u = tid; u < n; u += stride) ++left;
   unsigned backoff = 32;
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(256) graclus_async_kernel(const int* __restric
     int still = 0;
     for (int u = tid; u < n; u += stride) {
       if (pos[u] == -2) continue;        // done marker
-      if (graclus_try(u, rowptr, nbr, w, rank, label, pos)) pos[u] = -2;
+      if (graclus_try(u, rowptr, nbr, w, st, pos, label)) pos[u] = -2;
       else ++still;
     }
     if (still == left) {                 // no progress: let the owners of the blocking nodes run
@@ -575,12 +590,18 @@ __global__ void __launch_bounds__(256) graclus_async_kernel(const int* __restric
     }
     left = still;
   }
-  if (left > 0) atomicAdd(undecided, left);
+  if (left > 0) {
+    atomicAdd(undecided, left);
+    for (int u = tid; u < n; u += stride)
+      if (pos[u] != -2) label[u] = -1;   // sweep limit: leave a detectable marker (relabel_clusters rejects it)
+  }
 }
 }  // namespace geobi
 
-// ws: [undecided counter] | pos[N]
-extern "C" size_t geobi_graclus_ws_bytes(int64_t n_nodes) { return 256 + align256((size_t)(n_nodes + 1) * sizeof(int)) + 256; }
+// ws: [undecided counter] | pos[N] | st[N] = {label, rank}
+extern "C" size_t geobi_graclus_ws_bytes(int64_t n_nodes) {
+  return 256 + align256((size_t)(n_nodes + 1) * sizeof(int)) + align256((size_t)(n_nodes + 1) * sizeof(int2)) + 256;
+}
 
 extern "C" int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const float* w, const int32_t* rank, int64_t n_nodes, int32_t* label,
                              int* undecided_host, void* ws, size_t ws_bytes, void* stream) {
@@ -594,8 +615,9 @@ extern "C" int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const fl
   }
   int* undecided = static_cast<int*>(ws);
   int* pos = reinterpret_cast<int*>(static_cast<char*>(ws) + 256);
+  int2* state = reinterpret_cast<int2*>(static_cast<char*>(ws) + 256 + align256((size_t)(n_nodes + 1) * sizeof(int)));
   GEOBI_CUDA_OK(cudaMemsetAsync(undecided, 0, sizeof(int), st));
-  GEOBI_CUDA_OK(cudaMemsetAsync(label, 0xff, sizeof(int) * n_nodes, st));  // -1 = undecided
+  graclus_init_kernel<<<(unsigned)cdiv(n_nodes, 256), 256, 0, st>>>(rank, (int)n_nodes, state, pos);
   static int coresident = 0;   // blocks that are guaranteed to be resident together (threads wait on each other's nodes)
   if (coresident == 0) {
     int dev = 0, sms = 0, per_sm = 0;
@@ -608,7 +630,7 @@ extern "C" int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const fl
   int64_t nb = cdiv(n_nodes, 256);
   if (nb > coresident) nb = coresident;
   int n_all = (int)n_nodes;
-  void* args[] = {(void*)&rowptr, (void*)&nbr, (void*)&w, (void*)&rank, (void*)&label, (void*)&n_all, (void*)&pos, (void*)&undecided};
+  void* args[] = {(void*)&rowptr, (void*)&nbr, (void*)&w, (void*)&state, (void*)&label, (void*)&n_all, (void*)&pos, (void*)&undecided};
   // cooperative launch = the runtime refuses the launch unless all blocks are co-resident (no grid barrier is used)
   GEOBI_CUDA_OK(cudaLaunchCooperativeKernel((const void*)graclus_async_kernel, dim3((unsigned)nb), dim3(256), args, 0, st));
   if (undecided_host) {   // optional convergence check (SYNCS); callers on the hot path fold it into geobi_relabel_clusters
