@@ -239,9 +239,14 @@ static int rows_sort_compact(const int* raw_rowptr, int stride, const uint64_t* 
 
 // copies status + rowptr[n] to the host and synchronises; turns device-side errors into return codes
 static int finish_sync(const int* status, const int32_t* rowptr, int64_t nrows, int64_t* nnz_host, const char* what, cudaStream_t st) {
-  int h_status[ST_WORDS] = {0, 0, 0, 0};
-  int h_nnz = 0;
-  GEOBI_CUDA_OK(cudaMemcpyAsync(h_status, status, sizeof(h_status), cudaMemcpyDeviceToHost, st));
+  // pinned landing pad (one per host thread): both copies are queued asynchronously and one synchronise covers them; into
+  // pageable memory each copy is staged and blocks on its own (two stream drains and ~12 us between them in the timeline)
+  static thread_local int* pad = nullptr;
+  if (pad == nullptr) GEOBI_CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&pad), 64, cudaHostAllocDefault));
+  int* h_status = pad;
+  int& h_nnz = pad[ST_WORDS];
+  h_nnz = 0;
+  GEOBI_CUDA_OK(cudaMemcpyAsync(h_status, status, sizeof(int) * ST_WORDS, cudaMemcpyDeviceToHost, st));
   if (rowptr) GEOBI_CUDA_OK(cudaMemcpyAsync(&h_nnz, rowptr + nrows, sizeof(int), cudaMemcpyDeviceToHost, st));
   GEOBI_CUDA_OK(cudaStreamSynchronize(st));
   if (h_status[ST_ERR] != 0) {

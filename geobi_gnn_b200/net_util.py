@@ -28,9 +28,12 @@ from .ops import CSRGraph
 def _match_csr(data) -> Optional[CSRGraph]:
     """Source-indexed CSR (stable edge order) + weights, self loops dropped — what graclus sees.
     Also performs the reference's write-back of the stripped edge list (net_util.py:163-167)."""
+    n = data.x.size(0)
+    if "csr" in data and data.csr.n == n:                # a PoolingLayer's output: its coarse CSR (weights included) is attached
+        g = data.csr
+        return None if g.cap == 0 else g
     ei = data.edge_index
     w = data.edge_weight if "edge_weight" in data else None
-    n = data.x.size(0)
     tag = gnn.tag_of(ei)
     st = tag.get("sorted")
     if st is not None and st[0].n == n and st[3] is w:   # nn.input_graph built it from this very (edge_index, edge_weight)
@@ -77,8 +80,8 @@ class PoolingLayer(torch.nn.Module):
             self.att_r = Parameter(torch.empty(1, in_channel))
             init.xavier_uniform_(self.att_l.data, gain=1.414)
             init.xavier_uniform_(self.att_r.data, gain=1.414)
-        self.unpooling_indices = None
         self._unpool_i32 = None
+        self._unpool_i64 = None
         self.perm_fn = None          # callable(n) -> permutation (upstream draws torch.randperm); None = random keys on device
         self.forced = None           # list of raw label tensors (teacher forcing)
         self.trace = []
@@ -164,18 +167,41 @@ class PoolingLayer(torch.nn.Module):
         for c in clusts[-2::-1]:
             up = torch.index_select(up, 0, c)          # composition of the per-step maps (net_util.py:153-156)
         self._unpool_i32 = up.contiguous()
-        self.unpooling_indices = up.long()
-        ei = g.edge_index()
-        gnn.attach_symmetric_csr(ei, g, has_self_loops=False)
-        return Data(x, ei, edge_dual=edge_dual, edge_weight=g.w, pos=pos, fv_indices=face)
+        self._unpool_i64 = None
+        out = Data(x, None, edge_dual=edge_dual, pos=pos, fv_indices=face)
+
+        def coarse_edge_index(g=g):
+            ei = g.edge_index()                      # syncs once (entry count), then one csr_to_coo launch
+            gnn.attach_symmetric_csr(ei, g, has_self_loops=False)
+            return ei
+
+        def coarse_edge_weight(g=g):
+            g.nnz
+            return g.w
+
+        # the coarse COO list and its weights exist for callers that look at them (net_util.py:158 returns them); the
+        # next conv / pooling layer walks `csr` directly and needs neither the list nor the entry count on the host
+        out.set_lazy("edge_index", coarse_edge_index)
+        out.set_lazy("edge_weight", coarse_edge_weight)
+        out.csr = g
+        return out
 
     @property
     def unpool_map(self):
         """int32 fine-node -> coarse-node map of the last forward (None: identity); FeaStConv(row_map=...) consumes it."""
         return self._unpool_i32
 
+    @property
+    def unpooling_indices(self):
+        """int64 map as upstream keeps it (net_util.py:153-156); converted from the int32 map on first read."""
+        if self._unpool_i32 is None:
+            return None
+        if self._unpool_i64 is None:
+            self._unpool_i64 = self._unpool_i32.long()
+        return self._unpool_i64
+
     def unpooling(self, x, out=None):
-        if self.unpooling_indices is None:
+        if self._unpool_i32 is None:
             return x
         if torch.is_grad_enabled() and x.requires_grad:
             from .autograd import GatherRowsFn

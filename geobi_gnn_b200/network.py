@@ -60,13 +60,13 @@ class GNNModule(nn.Module):
         rec("p1", data_r2.x)
 
         n2 = data_r2.x.size(0)
-        g2 = conv_csr(data_r2.edge_index, n2)
+        g2 = input_graph(data_r2, n2)
         buf2 = ops.valloc(n2, (128,), torch.float32, x0.device, ref=n1)  # [ l_conv2 | r_conv1 ]  (network.py:292 cat)
         data_r2.x = rec("l2", self.l_conv2(data_r2.x, g2, 0.2, out=buf2[:, :64]))
         data_r3 = self.pooling2(data_r2)
         rec("p2", data_r3.x)
 
-        g3 = conv_csr(data_r3.edge_index, data_r3.x.size(0))
+        g3 = input_graph(data_r3, data_r3.x.size(0))
         with ops.size_ref(n1):                                          # coarse-level buffers: sizes stable across forwards
             data_r3.x = rec("l3", self.l_conv3(data_r3.x, g3, 0.2))
             data_r3.x = rec("l4", self.l_conv4(data_r3.x, g3, 0.2))
@@ -85,11 +85,11 @@ class GNNModule(nn.Module):
         data_r1.x = rec("l1", self.l_conv1(data_r1.x, g1, 0.2))
         data_r2 = self.pooling1(data_r1)
         rec("p1", data_r2.x)
-        g2 = conv_csr(data_r2.edge_index, data_r2.x.size(0))
+        g2 = input_graph(data_r2, data_r2.x.size(0))
         data_r2.x = rec("l2", self.l_conv2(data_r2.x, g2, 0.2))
         data_r3 = self.pooling2(data_r2)
         rec("p2", data_r3.x)
-        g3 = conv_csr(data_r3.edge_index, data_r3.x.size(0))
+        g3 = input_graph(data_r3, data_r3.x.size(0))
         data_r3.x = rec("l3", self.l_conv3(data_r3.x, g3, 0.2))
         data_r3.x = rec("l4", self.l_conv4(data_r3.x, g3, 0.2))
         up2 = rec("r1", self.r_conv1(self.pooling2.unpooling(data_r3.x), g2, 1.0))

@@ -53,6 +53,8 @@ def input_graph(data, n: int) -> CSRGraph:
     """Conv CSR of an input-level graph.  A Data that carries `coalesced_undirected=True` (dataset.py builds its graphs
     with to_undirected / build_facet_graph, so ours sets it) gets the sort-free builder, whose result also serves the
     matcher of the first pooling layer (net_util._match_csr); anything else goes through conv_csr."""
+    if "csr" in data and data.csr.n == n:      # a PoolingLayer's output carries its coarse CSR; edge_index stays unmaterialised
+        return data.csr
     ei = data.edge_index
     tag = tag_of(ei)
     g = tag.get("tgt")
