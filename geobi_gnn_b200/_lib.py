@@ -23,6 +23,9 @@ SIGNATURES = {
     "geobi_exclusive_scan_i32": (_i32, [_p, _p, _i64, _p, _sz, _p]),
     "geobi_csr_from_coo_ws_bytes": (_sz, [_i64, _i64, _i32]),
     "geobi_csr_from_coo": (_i32, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "geobi_pool_step_ws_bytes": (_sz, [_i64, _i64]),
+    "geobi_pool_step": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _i64, _i32, _i32, _p, _i64, _i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p,
+                               _p, _p, _sz, _p]),
     "geobi_csr_from_sorted_coo_ws_bytes": (_sz, [_i64]),
     "geobi_csr_from_sorted_coo": (_i32, [_p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _sz, _p]),
     "geobi_remove_self_loops_ws_bytes": (_sz, [_i64]),

@@ -147,6 +147,14 @@ class PoolingLayer(torch.nn.Module):
                 perm = None if self.perm_fn is None else self.perm_fn(n).to(dev)   # None: random priority keys on the device
                 label, _ = ops.graclus(g, perm, use_weight=g._w is not None)
             self.trace.append((g, perm, label))
+            if self.forced is None and not (torch.is_grad_enabled() and x.requires_grad):
+                # inference: the rest of the step is one library call (same kernels, queued right behind the count read-back)
+                cluster, nc, mrowptr, members, x, g, pos = ops.pool_step(g, label, x, op, pos)
+                clusts.append(cluster)
+                edge_dual = None if edge_dual is None else cluster.long()[edge_dual]
+                if empty_in or g.cap == 0:
+                    break
+                continue
             cluster, nc = ops.relabel_clusters(label)
             clusts.append(cluster)
             # matcher output = clusters of one or two nodes: member CSR without a sort; arbitrary (forced) labels: general path

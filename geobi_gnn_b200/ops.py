@@ -351,6 +351,39 @@ def pool_edges(g: CSRGraph, cluster: torch.Tensor, mrowptr: torch.Tensor, member
                     None if out_w is None else (out_w[:cap] if cap else out_w[:0]), g.symmetric)
 
 
+def pool_step(g: CSRGraph, label: torch.Tensor, x: torch.Tensor, op: int, pos: Optional[torch.Tensor] = None):
+    """relabel_clusters + group_pairs + segment_reduce(x[, pos]) + pool_edges in one library call (one sync: the cluster
+    count).  Outputs are allocated at capacity up front and trimmed to views afterwards.
+    Returns (cluster, n_clusters, mrowptr, members, x_coarse, coarse CSRGraph, pos_coarse)."""
+    _need_cuda(g.rowptr, label, x, pos)
+    lib = _lib.load()
+    dev = x.device
+    n, cap = g.n, g.cap
+    x, ldx, c = _rows(x)
+    cluster = valloc(n, (), torch.int32, dev)
+    mrowptr = valloc(n + 1, (), torch.int32, dev)
+    members = valloc(max(n, 1), (), torch.int32, dev)
+    x_out = valloc(n, (c,), torch.float32, dev)
+    out_rowptr = valloc(n + 1, (), torch.int32, dev)
+    out_nbr = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+    gw = g._w
+    out_w = None if gw is None else torch.empty(max(cap, 1), dtype=torch.float32, device=dev)
+    p = ldp = cp = pos_out = None
+    if pos is not None:
+        p, ldp, cp = _rows(pos)
+        pos_out = valloc(n, (cp,), torch.float32, dev)
+    ws = _ws(lib.geobi_pool_step_ws_bytes(n, cap), dev)
+    nc = C.c_int64(0)
+    _lib.check(lib.geobi_pool_step(_ptr(g.rowptr), _ptr(g._nbr), _ptr(gw), n, cap, _ptr(label), _ptr(x), ldx, c, op, _ptr(p), ldp or 0, cp or 0,
+                                   _ptr(cluster), _ptr(mrowptr), _ptr(members), _ptr(x_out), c, _ptr(pos_out), cp or 0, _ptr(out_rowptr),
+                                   _ptr(out_nbr), _ptr(out_w), C.byref(nc), _ptr(ws), ws.numel(), _stream()), "pool_step")
+    _count(5 + 6 + 1 + 8 + (1 if pos is not None else 0))
+    k = int(nc.value)
+    gc = CSRGraph(out_rowptr[:k + 1], out_nbr[:cap] if cap else out_nbr[:0], k, 0 if cap == 0 else None,
+                  None if out_w is None else (out_w[:cap] if cap else out_w[:0]), g.symmetric)
+    return cluster, k, mrowptr[:k + 1], members[:n], x_out[:k], gc, (None if pos_out is None else pos_out[:k])
+
+
 def remove_self_loops(edge_index: torch.Tensor, weight: Optional[torch.Tensor], count: int):
     """Order-preserving removal of row==col pairs when the surviving `count` is already known (no sync):
     torch_geometric.utils.remove_self_loops (net_util.py:163)."""

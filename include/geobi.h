@@ -156,6 +156,20 @@ GEOBI_API int geobi_pool_edges(const int32_t* rowptr, const int32_t* nbr, const 
                      int64_t n_clusters, int32_t* out_rowptr, int32_t* out_nbr, float* out_w,
                      int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream);
 
+/* One iteration of PoolingLayer.forward's loop after the matching (net_util.py:100-140) in a single call:
+ * geobi_relabel_clusters (SYNCS: *n_clusters_host) -> geobi_group_pairs -> geobi_segment_reduce of the features (op) and,
+ * if given, of the positions (mean) -> geobi_pool_edges.  `label` must come from a matching (geobi_graclus).  All outputs
+ * are caller-allocated at capacity (n_nodes rows / nnz_cap entries; rows [0, n_clusters) are written), so the kernels that
+ * depend on the cluster count are queued from inside this call right after the synchronisation.  Results are identical
+ * to the five separate calls. */
+GEOBI_API size_t geobi_pool_step_ws_bytes(int64_t n_nodes, int64_t nnz_cap);
+GEOBI_API int geobi_pool_step(const int32_t* rowptr, const int32_t* nbr, const float* w, int64_t n_nodes, int64_t nnz_cap,
+                    const int32_t* label, const float* x, int64_t ldx, int channels, int op, const float* pos,
+                    int64_t ldp, int pos_channels, int32_t* cluster, int32_t* mrowptr, int32_t* members,
+                    float* x_out, int64_t ldxo, float* pos_out, int64_t ldpo, int32_t* out_rowptr,
+                    int32_t* out_nbr, float* out_w, int64_t* n_clusters_host, void* ws, size_t ws_bytes,
+                    void* stream);
+
 /* ------------------------------------------------------------------ segment / gather */
 
 /* out[s, :] = reduce_{k in rowptr[s]..rowptr[s+1]} x[idx[k], :]   (op 0 = mean with count

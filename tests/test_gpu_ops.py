@@ -193,3 +193,30 @@ def test_segment_reduce_and_gather_edge_cases():
     g = ops.gather_rows(x.to(DEV), idx.to(DEV))
     assert torch.equal(g.cpu(), x[idx.long()])
     assert ops.gather_rows(x.to(DEV), idx[:0].to(DEV)).shape == (0, 5)
+
+
+@pytest.mark.gpu
+def test_pool_step_equals_the_separate_calls():
+    """geobi_pool_step = relabel_clusters + group_pairs + segment_reduce + pool_edges (net_util.py:100-140), bit for bit."""
+    ops = _ops()
+    (dv, df), _, _ = util.oracle_inputs(5)
+    for d, op in ((dv, ops.OP_MAX), (df, ops.OP_MEAN)):
+        n = d.x.shape[0]
+        ei = d.edge_index.to(DEV)
+        torch.manual_seed(n)
+        w = torch.rand(ei.size(1), device=DEV)
+        g = ops.csr_from_coo(ei, n, w, ops.COO_DROP_SELF)
+        x = torch.randn(n, 32, device=DEV)
+        pos = torch.randn(n, 3, device=DEV)
+        label, _ = ops.graclus(g, torch.randperm(n).to(DEV))
+        cluster, nc = ops.relabel_clusters(label)
+        mrowptr, members = ops.group_pairs(label, cluster, nc)
+        xs = ops.segment_reduce(x, mrowptr, members, nc, op)
+        gs = ops.pool_edges(g, cluster, mrowptr, members, nc)
+        ps = ops.segment_reduce(pos, mrowptr, members, nc, ops.OP_MEAN)
+        c2, nc2, mr2, mem2, x2, g2, p2 = ops.pool_step(g, label, x, op, pos)
+        assert nc2 == nc and torch.equal(c2, cluster) and torch.equal(mr2, mrowptr) and torch.equal(mem2, members)
+        assert torch.equal(x2, xs) and torch.equal(p2, ps)
+        assert g2.nnz == gs.nnz and torch.equal(g2.rowptr, gs.rowptr) and torch.equal(g2.nbr, gs.nbr) and torch.equal(g2.w, gs.w)
+        c3, nc3, _, _, x3, g3, p3 = ops.pool_step(g.with_weight(None), label, x, op, None)
+        assert p3 is None and nc3 == nc and torch.equal(x3, xs) and g3.w is None and g3.nnz == gs.nnz and torch.equal(g3.nbr, gs.nbr)
