@@ -18,9 +18,14 @@ constexpr int H = GEOBI_HEADS;
 
 // ------------------------------------------------------------------------------ P = X U^T (fp64)
 // One thread owns two nodes x all 9 heads (18 fp64 accumulators), so every staged x value is converted once and feeds
-// 9 DFMAs, and every broadcast U load feeds 4.  x is staged through shared memory in 32-channel chunks (coalesced
-// float4 reads, conflict-free float4 row reads at a 36-float pitch); the fp64 pipe, not the LSU, is the limiter.
+// 9 DFMAs, and every broadcast U load feeds 4.  x streams through shared memory in 32-channel chunks, double buffered
+// with cp.async (the copy of chunk k+1 runs under the DFMAs of chunk k; conflict-free float4 row reads at a 36-float
+// pitch), which leaves the fp64 pipe (64 DFMA/clk/SM measured, profiles/micro/dfma_bench.cu) as the limiter.
 // Channels are accumulated in ascending order with one fma each - the same order as the oracle's float64 reference.
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 constexpr int PROJ_NODES = 256;
 constexpr int PROJ_THREADS = 128;
 constexpr int PROJ_CC = 32;
@@ -28,7 +33,7 @@ constexpr int PROJ_LD = PROJ_CC + 4;
 
 static inline size_t proj_smem_bytes(int c_in) {
   const int cp = (c_in + 3) & ~3;
-  return (size_t)H * cp * sizeof(double) + (size_t)PROJ_NODES * PROJ_LD * sizeof(float);
+  return (size_t)H * cp * sizeof(double) + (size_t)(cp > PROJ_CC ? 2 : 1) * PROJ_NODES * PROJ_LD * sizeof(float);
 }
 
 __global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
@@ -36,38 +41,35 @@ __global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Cp = (C + 3) & ~3;
   double* Us = reinterpret_cast<double*>(smem_raw);          // [H][Cp], zero padded
-  float* xs = reinterpret_cast<float*>(Us + H * Cp);         // [PROJ_NODES][PROJ_LD]
+  float* xs0 = reinterpret_cast<float*>(Us + H * Cp);        // [2][PROJ_NODES][PROJ_LD] (one buffer when a single chunk covers C)
   const int tid = threadIdx.x;
   const int64_t node0 = (int64_t)blockIdx.x * PROJ_NODES;
-  for (int i = tid; i < H * Cp; i += PROJ_THREADS) {
-    const int h = i / Cp, c = i - h * Cp;
-    Us[i] = c < C ? (double)U[h * C + c] : 0.0;
-  }
   const bool vec = (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  double acc[2][H];
-#pragma unroll
-  for (int h = 0; h < H; ++h) acc[0][h] = acc[1][h] = 0.0;
+  const int n_chunks = (Cp + PROJ_CC - 1) / PROJ_CC;
 
-  for (int c0 = 0; c0 < Cp; c0 += PROJ_CC) {
+  auto stage = [&](int chunk) {
+    float* xs = xs0 + (size_t)(chunk & 1) * PROJ_NODES * PROJ_LD;
+    const int c0 = chunk * PROJ_CC;
     const int cw = min(PROJ_CC, Cp - c0);                    // multiple of 4
-    __syncthreads();                                         // previous chunk consumed (first pass: nothing to wait for)
     if (vec) {
       const int units = cw >> 2;
       for (int i = tid; i < PROJ_NODES * units; i += PROJ_THREADS) {
         const int r = i / units, q = i - r * units;
         const int64_t n = node0 + r;
         const int c = c0 + q * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < N) {
-          const float* src = x + n * ldx + c;
-          if (c + 3 < C) v = __ldg(reinterpret_cast<const float4*>(src));
-          else {
+        float* dst = xs + r * PROJ_LD + q * 4;
+        if (n < N && c + 3 < C) {
+          cp_async_16(dst, x + n * ldx + c);
+        } else {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (n < N) {
+            const float* src = x + n * ldx + c;
             v.x = src[0];
             if (c + 1 < C) v.y = src[1];
             if (c + 2 < C) v.z = src[2];
           }
+          *reinterpret_cast<float4*>(dst) = v;
         }
-        *reinterpret_cast<float4*>(xs + r * PROJ_LD + q * 4) = v;
       }
     } else {
       for (int i = tid; i < PROJ_NODES * cw; i += PROJ_THREADS) {
@@ -76,7 +78,29 @@ __global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float
         xs[r * PROJ_LD + c] = (n < N && c0 + c < C) ? x[n * ldx + c0 + c] : 0.f;
       }
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  stage(0);
+  for (int i = tid; i < H * Cp; i += PROJ_THREADS) {
+    const int h = i / Cp, c = i - h * Cp;
+    Us[i] = c < C ? (double)U[h * C + c] : 0.0;
+  }
+  double acc[2][H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[0][h] = acc[1][h] = 0.0;
+
+  for (int chunk = 0; chunk < n_chunks; ++chunk) {
+    if (chunk + 1 < n_chunks) {
+      stage(chunk + 1);                                      // its buffer was released by the barrier that ended chunk - 1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();                                         // chunk's rows (and, first time, Us) visible to every thread
+    const int c0 = chunk * PROJ_CC;
+    const int cw = min(PROJ_CC, Cp - c0);
+    const float* xs = xs0 + (size_t)(chunk & 1) * PROJ_NODES * PROJ_LD;
     const float* xa = xs + tid * PROJ_LD;
     const float* xb = xs + (tid + PROJ_THREADS) * PROJ_LD;
     const double* ub = Us + c0;
@@ -100,10 +124,10 @@ __global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float
         acc[1][h] = fma(b3, u23.y, acc[1][h]);
       }
     }
+    __syncthreads();                                         // every thread is done with this buffer
   }
   // transpose through shared memory so P is written in whole rows of the block (coalesced)
-  __syncthreads();
-  double* ps = reinterpret_cast<double*>(xs);                // 256 x 9 doubles = 18 KB <= the 36 KB x stage
+  double* ps = reinterpret_cast<double*>(xs0);               // 256 x 9 doubles = 18 KB <= one 36 KB x buffer
 #pragma unroll
   for (int h = 0; h < H; ++h) {
     ps[tid * H + h] = acc[0][h];
@@ -604,10 +628,6 @@ static void launch_packed(int out_mode, cudaStream_t st, const float* x, int64_t
 // the accumulation loop then runs load-free out of shared memory.  This is what hides the gather latency: the direct
 // version keeps only two rows per warp in flight (ncu: long-scoreboard stalls dominate, issue slots < 50 % busy).
 // SLOTS = edge slots per node per chunk (<= LPN).
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
 
 template <int NPW, int OUT, int SLOTS>
 __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
@@ -939,6 +959,18 @@ static void launch_aggregate(int out_mode, unsigned blocks, cudaStream_t st, con
   else feast_aggregate_kernel<CPL, 2, VEC><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
 }
 
+static int launch_project(const float* x, int64_t ldx, int64_t N, int c_in, const float* U, double* P, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem_bytes(128)));
+    attr_set = true;
+  }
+  if (N == 0) return GEOBI_OK;
+  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, proj_smem_bytes(c_in), st>>>(x, ldx, N, c_in, U, P);
+  GEOBI_LAUNCH_OK("feast_project");
+  return GEOBI_OK;
+}
+
 // 4 / 2: channels per lane of the small-C kernel that will run for this layer; 0: another kernel
 static int small_c_variant(int c_in, int64_t ldx, int64_t ldz, const float* x, bool row_map) {
   if (row_map || getenv("GEOBI_NO_SMALLC") != nullptr) return 0;
@@ -952,18 +984,16 @@ bool feast_aggregate_fills_padding(int c_in, int64_t ldx, int64_t ldz, const flo
 }
 
 int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const float* U, double* P, cudaStream_t st) {
-  const size_t psm = proj_smem_bytes(c_in);
-  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, N, c_in, U, P);
-  GEOBI_LAUNCH_OK("feast_project");
-  return GEOBI_OK;
+  return launch_project(x, ldx, N, c_in, U, P, st);
 }
 
 int feast_project_and_aggregate(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
                                 const int32_t* row_map, int64_t n_src, const float* U, const float* c, double* P, void* Z, int64_t ldz,
                                 int out_mode, cudaStream_t st) {
-  const size_t psm = proj_smem_bytes(c_in);
-  feast_project_kernel<<<(unsigned)cdiv(n_src, PROJ_NODES), PROJ_THREADS, psm, st>>>(x, ldx, n_src, c_in, U, P);
-  GEOBI_LAUNCH_OK("feast_project");
+  {
+    const int prc = launch_project(x, ldx, n_src, c_in, U, P, st);
+    if (prc) return prc;
+  }
   const unsigned ab = (unsigned)cdiv(N, 8);
   const int cpl = c_in <= 32 ? 1 : (c_in <= 64 ? 2 : 4);
   // vector path: every lane's CPL-channel group is whole and 4*CPL-byte aligned in x (and in Z for the packed stores)

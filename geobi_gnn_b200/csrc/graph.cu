@@ -51,53 +51,55 @@ __device__ __forceinline__ int block_excl_scan(int v, int* total) {
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const int* __restrict__ in, int64_t n, int* __restrict__ partial) {
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
-  int s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; ++k) {
-    int64_t i = base + k * SCAN_THREADS + threadIdx.x;
-    if (i < n) s += in[i];
-  }
-  int tot;
-  block_excl_scan(s, &tot);
-  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(int* partial, int64_t nb) {
-  int carry = 0;
-  for (int64_t base = 0; base < nb; base += SCAN_THREADS) {
-    int64_t i = base + threadIdx.x;
-    int v = i < nb ? partial[i] : 0;
-    int tot;
-    int ex = block_excl_scan(v, &tot);
-    if (i < nb) partial[i] = carry + ex;
-    carry += tot;
-  }
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_final_kernel(const int* __restrict__ in, int64_t n, const int* __restrict__ partial, int* __restrict__ out) {
-  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+// Single-pass exclusive scan with decoupled look-back (Merrill & Garland): one launch instead of reduce / scan-partials /
+// final.  Tiles are handed out by a ticket counter, so a tile only ever waits on tiles that are already running.
+// desc[t]: bits 63..62 = 0 not ready, 1 tile aggregate, 2 inclusive prefix; low 32 bits = the value.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(const int* __restrict__ in, int64_t n, int* __restrict__ out,
+                                                                    unsigned long long* desc, unsigned* ticket) {
+  __shared__ unsigned s_tile;
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+  const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
   int v[SCAN_ITEMS];
   int s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
-    int64_t i = base + k;
+    const int64_t i = base + k;
     v[k] = i < n ? in[i] : 0;
     s += v[k];
   }
   int tot;
-  int ex = block_excl_scan(s, &tot) + partial[blockIdx.x];
+  int ex = block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) {
+    int run = 0;
+    if (tile > 0) {
+      atomicExch(desc + tile, (1ull << 62) | (unsigned)tot);
+      for (int t = (int)tile - 1;; --t) {
+        unsigned long long d;
+        do {
+          d = *reinterpret_cast<volatile unsigned long long*>(desc + t);
+        } while ((d >> 62) == 0);
+        run += (int)(unsigned)d;
+        if ((d >> 62) == 2) break;
+      }
+    }
+    atomicExch(desc + tile, (2ull << 62) | (unsigned)(run + tot));
+    s_prefix = run;
+  }
+  __syncthreads();
+  ex += s_prefix;
 #pragma unroll
   for (int k = 0; k < SCAN_ITEMS; ++k) {
-    int64_t i = base + k;
+    const int64_t i = base + k;
     if (i < n) out[i] = ex;
     ex += v[k];
     if (i == n - 1) out[n] = ex;
   }
 }
 
-size_t scan_ws_bytes(int64_t n) { return align256((size_t)(cdiv(n > 0 ? n : 1, SCAN_TILE)) * sizeof(int)) + 256; }
+size_t scan_ws_bytes(int64_t n) { return align256(16 + (size_t)(cdiv(n > 0 ? n : 1, SCAN_TILE)) * sizeof(unsigned long long)) + 256; }
 
 int scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, size_t ws_bytes, cudaStream_t st) {
   GEOBI_REQUIRE(n >= 0 && out != nullptr, "scan: bad arguments");
@@ -110,10 +112,10 @@ int scan_i32(const int32_t* in, int32_t* out, int64_t n, void* ws, size_t ws_byt
     return GEOBI_ERR_WORKSPACE;
   }
   const int64_t nb = cdiv(n, SCAN_TILE);
-  int* partial = static_cast<int*>(ws);
-  scan_reduce_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, partial);
-  scan_partials_kernel<<<1, SCAN_THREADS, 0, st>>>(partial, nb);
-  scan_final_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, partial, out);
+  unsigned* ticket = static_cast<unsigned*>(ws);
+  unsigned long long* desc = reinterpret_cast<unsigned long long*>(static_cast<char*>(ws) + 16);
+  GEOBI_CUDA_OK(cudaMemsetAsync(ws, 0, 16 + (size_t)nb * sizeof(unsigned long long), st));
+  scan_onepass_kernel<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(in, n, out, desc, ticket);
   GEOBI_LAUNCH_OK("scan");
   return GEOBI_OK;
 }
