@@ -19,7 +19,7 @@ namespace fused {
 using namespace tc;
 
 #ifndef PREFETCH_MODE
-#define PREFETCH_MODE 0
+#define PREFETCH_MODE 3   // 3: P rows of the next tile into L1 at the end of a tile (A/B: -2 %); x-row prefetches (1, 2) lost
 #endif
 constexpr int C_IN = 64, C_OUT = 32;
 constexpr int NT = 32;            // nodes per tile = MMA N
@@ -390,11 +390,13 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     }
     // the next tile's first 16 rows of x and P: pull them into L1 now (their indices, loaded at the top of this
     // iteration, have arrived), so the next iteration starts on L1 hits
-#if PREFETCH_MODE == 2
+#if PREFETCH_MODE >= 2
     if (tile + 1 < t_end) {
+#if PREFETCH_MODE == 2
       const float* xr = x + (unsigned)j_nxt * ldx32;
       prefetch_l1(xr);
       prefetch_l1(xr + 32);
+#endif
       const double* pr = P + (int64_t)j_nxt * H;
       prefetch_l1(pr);
       prefetch_l1(pr + H - 1);
