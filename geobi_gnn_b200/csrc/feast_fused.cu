@@ -4,10 +4,11 @@
 //   per tile of 32 target nodes (16 aggregation warps x 2 nodes, lanes own 4 adjacent channels):
 //     1. aggregate Z_i[h, :] = 1/d_i sum_j q_ijh x_j in registers (1/d_i folded into the soft assignments),
 //     2. write the rows, split x = hi + lo (bf16), straight into the K-major SWIZZLE_128B *B-operand* tiles in shared memory,
-//     3. warp 16 issues tcgen05.mma (M = 64: the weight tile W_flat[32 (+32 aliased) x 576] is the resident A operand,
-//        N = 32 nodes, 36 K-steps x 3 split passes) -> D^T[channel, node] in TMEM,
-//     4. warps 16 and 17 drain TMEM (+bias, leaky_relu) and write out[node, channel]; the aggregation warps never touch the
-//        accumulator, they only wait for the MMAs of tile t-1 before overwriting the operand tiles with tile t.
+//     3. warp 18 issues tcgen05.mma (M = 64: the weight tile W_flat[32 (+32 aliased) x 576] is the resident A operand,
+//        N = 32 nodes, 36 K-steps x 3 split passes) -> D^T[channel, node] in one of two TMEM accumulators,
+//     4. warps 16 and 17 drain that accumulator (+bias, leaky_relu) and write out[node, channel] while the next tile's MMAs
+//        fill the other one; the aggregation warps never touch TMEM, they only wait for the MMAs of tile t-1 before
+//        overwriting the operand tiles with tile t.
 //
 // Z (2.3 KB per node) never reaches HBM: per node the kernel reads 256 B of x per gathered row (L2) + 72 B of P, and writes
 // 128 B.  The unfused path writes and re-reads 2 x 2.3 KB per node (ncu: 1.12 GB written by the aggregation of one layer).
@@ -24,8 +25,9 @@ using namespace tc;
 constexpr int C_IN = 64, C_OUT = 32;
 constexpr int NT = 32;            // nodes per tile = MMA N
 constexpr int WARPS = 16;         // aggregation warps, 2 nodes each
-constexpr int EPI_WARPS = 2;      // warp 16: MMA issue + TMEM quadrant 0; warp 17: TMEM quadrant 1 (a warp reaches lanes 32*(warp%4)..+31)
-constexpr int THREADS = (WARPS + EPI_WARPS) * 32;
+constexpr int EPI_WARPS = 2;      // warps 16, 17 drain TMEM quadrants 0, 1 (a warp reaches lanes 32*(warp%4)..+31)
+constexpr int MMA_WARP = WARPS + EPI_WARPS;   // warp 18 issues the MMAs
+constexpr int THREADS = (WARPS + EPI_WARPS + 1) * 32;
 constexpr int KB = H;             // one 64-wide K block per head
 constexpr int TILE_BYTES = 32 * 128;   // [32 rows x 128 B] of one K block (W rows = channels, Z rows = nodes)
 constexpr int PLANE_BYTES = KB * TILE_BYTES;
@@ -43,12 +45,9 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
 }
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)v); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
-// named barrier 1: the 16 aggregation warps arrive (non-blocking) when their rows are in shared memory; the MMA warp and
-// the second drain warp sleep on it (so neither spins on the mbarrier while the tile is still being aggregated)
-__device__ __forceinline__ void z_ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"(THREADS) : "memory"); }
-__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
-// named barrier 2: both drain warps have read the accumulator (the next tile's first MMA overwrites it)
-__device__ __forceinline__ void drained_sync() { asm volatile("bar.sync 2, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+// named barrier 1: the 16 aggregation warps arrive (non-blocking) when their rows are in shared memory; the MMA warp sleeps on it
+__device__ __forceinline__ void z_ready_arrive() { asm volatile("bar.arrive 1, %0;" ::"n"((WARPS + 1) * 32) : "memory"); }
+__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"n"((WARPS + 1) * 32) : "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 #ifdef EXP_TIMELINE
@@ -75,7 +74,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
                                                                        const float* __restrict__ bias, float slope, float* __restrict__ out,
                                                                        int64_t ldo) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t mbar;
+  // mma_done[b]: the MMAs of a tile whose accumulator is TMEM buffer b have completed (operand tiles reusable, accumulator
+  // readable); acc_free[b]: both drain warps have read buffer b.  Two accumulators, so the MMAs of tile t+1 run while tile t
+  // is drained; each barrier completes once every second tile: the parity of local tile k is (k >> 1) & 1.
+  __shared__ __align__(8) uint64_t mma_done[2];
+  __shared__ __align__(8) uint64_t acc_free[2];
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -90,10 +93,13 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
 
   // ---- one-time setup: barrier, TMEM, resident weight tiles
   if (tid == 0) {
-    mbar_init(&mbar, 1);
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
+    mbar_init(&acc_free[0], EPI_WARPS);
+    mbar_init(&acc_free[1], EPI_WARPS);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 32);
+  if (warp == 0) tmem_alloc(&tmem_slot, 64);
   if (tid < H) chs[tid] = cvec[tid];
   for (int idx = tid; idx < 2 * KB * 32 * 8; idx += THREADS) {
     const int plane = idx / (KB * 32 * 8), rem = idx - plane * (KB * 32 * 8);
@@ -110,51 +116,60 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   const int64_t n_tiles = (N + NT - 1) / NT;
   const int64_t t_begin = (n_tiles * blockIdx.x) / gridDim.x, t_end = (n_tiles * (blockIdx.x + 1)) / gridDim.x;
 
-  if (warp >= WARPS) {
-    // ===== MMA / drain warps =====
-    const int quad = warp - WARPS;                 // TMEM quadrant; for M = 64 accumulator row r lives in lane (r % 16) + 32 * (r / 16)
-    const float my_bias = bias[quad * 16 + (lane & 15)];
+  if (warp == MMA_WARP) {
+    // ===== MMA warp: per tile, wait for its rows, issue 36 K-steps x 3 split passes into accumulator k & 1, commit =====
     constexpr uint32_t idesc = make_idesc(64, NT);
     const uint64_t d0 = make_desc(smem_u32(w_hi));
     const uint32_t desc_hi = (uint32_t)(d0 >> 32);
     const uint32_t wh_lo = (uint32_t)d0, wl_lo = (uint32_t)make_desc(smem_u32(w_lo)), zh_lo = (uint32_t)make_desc(smem_u32(z_hi)),
                    zl_lo = (uint32_t)make_desc(smem_u32(z_lo));
-    uint32_t phase = 0;
     for (int64_t tile = t_begin; tile < t_end; ++tile) {
+      const uint32_t k = (uint32_t)(tile - t_begin), buf = k & 1;
       z_ready_wait();
-      if (quad == 0) TL(0);
-      if (quad == 0) {
-        // the tile's rows are in place: issue 36 K-steps x 3 split passes, commit to the mbarrier
-        if (elect_one()) {
-          tc_fence_after();
-          // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
-          // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
-          uint32_t ah = wh_lo, al = wl_lo, bh = zh_lo, bl = zl_lo;
+      TL(0);
+      if (k >= 2) mbar_wait(&acc_free[buf], ((k >> 1) - 1) & 1);   // tile k-2 has been drained out of this accumulator
+      if (elect_one()) {
+        tc_fence_after();
+        const uint32_t acc = tmem_d + buf * NT;
+        // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
+        // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
+        uint32_t ah = wh_lo, al = wl_lo, bh = zh_lo, bl = zl_lo;
 #pragma unroll 1
-          for (int kb = 0; kb < KB; ++kb) {
-            if (kb == 0) mma_f16_first(tmem_d, ah, bh, desc_hi, idesc);
-            else mma_f16_acc(tmem_d, ah, bh, desc_hi, idesc);
+        for (int kb = 0; kb < KB; ++kb) {
+          if (kb == 0) mma_f16_first(acc, ah, bh, desc_hi, idesc);
+          else mma_f16_acc(acc, ah, bh, desc_hi, idesc);
 #pragma unroll
-            for (int k16 = 1; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+          for (int k16 = 1; k16 < 4; ++k16) mma_f16_acc(acc, ah + 2 * k16, bh + 2 * k16, desc_hi, idesc);
 #ifndef EXP_ONEPASS
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, ah + 2 * k16, bl + 2 * k16, desc_hi, idesc);
+          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(acc, ah + 2 * k16, bl + 2 * k16, desc_hi, idesc);
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(tmem_d, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(acc, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
 #endif
-            ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += TILE_BYTES >> 4; bl += TILE_BYTES >> 4;
-          }
-          mma_commit(&mbar);
+          ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += TILE_BYTES >> 4; bl += TILE_BYTES >> 4;
         }
-        __syncwarp();
-        TL(1);
+        mma_commit(&mma_done[buf]);
       }
-      mbar_wait(&mbar, phase);
-      phase ^= 1;
+      __syncwarp();
+      TL(1);
+    }
+    __syncthreads();
+    return;
+  }
+  if (warp >= WARPS) {
+    // ===== drain warps: accumulator -> +bias, leaky_relu -> out[node, channel] =====
+    const int quad = warp - WARPS;                 // TMEM quadrant; for M = 64 accumulator row r lives in lane (r % 16) + 32 * (r / 16)
+    const float my_bias = bias[quad * 16 + (lane & 15)];
+    for (int64_t tile = t_begin; tile < t_end; ++tile) {
+      const uint32_t k = (uint32_t)(tile - t_begin), buf = k & 1;
+      mbar_wait(&mma_done[buf], (k >> 1) & 1);
       tc_fence_after();
       if (quad == 0) TL(2);
       float v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16), v);
+      tmem_ld32(tmem_d + buf * NT + ((uint32_t)(quad * 32) << 16), v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[buf]);  // values are in registers: the accumulator may be overwritten
       if (lane < 16) {
         const int o = quad * 16 + lane;
         const int64_t n0 = tile * NT;
@@ -171,8 +186,6 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
           }
         }
       }
-      tc_fence_before();
-      drained_sync();
       if (quad == 0) TL(3);
     }
     __syncthreads();
@@ -216,7 +229,6 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   load_rowptr(t_begin + 1, b_nxt, total_nxt);
   int j_cur = load_first_j(t_begin, b_cur, total_cur);
   int j_nxt = 0;
-  uint32_t mma_phase = 0;
 
   for (int64_t tile = t_begin; tile < t_end; ++tile) {
     // ---------------- 1. aggregation of this warp's two nodes (registers only)
@@ -370,8 +382,8 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     TS(3);
     // ---------------- 2. the previous tile's MMAs have finished reading the operand tiles
     if (tile > t_begin) {
-      mbar_wait(&mbar, mma_phase);
-      mma_phase ^= 1;
+      const uint32_t kp = (uint32_t)(tile - t_begin) - 1;
+      mbar_wait(&mma_done[kp & 1], (kp >> 1) & 1);
       tc_fence_after();
     }
     if (warp == 0) TL(6);
@@ -415,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, 32);
+    tmem_dealloc(tmem_d, 64);
   }
 }
 
