@@ -186,7 +186,7 @@ def exclusive_scan(v: torch.Tensor) -> torch.Tensor:
     out = torch.empty(n + 1, dtype=torch.int32, device=v.device)
     ws = _ws(lib.geobi_scan_ws_bytes(n), v.device)
     _lib.check(lib.geobi_exclusive_scan_i32(_ptr(v), _ptr(out), n, _ptr(ws), ws.numel(), _stream()), "exclusive_scan")
-    _count(3)
+    _count(1)
     return out
 
 
@@ -212,7 +212,7 @@ def csr_from_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional[torch.
     row, col = ei[0], ei[1]
     _lib.check(lib.geobi_csr_from_coo(_ptr(row), _ptr(col), _ptr(w), e, n_nodes, flags, _ptr(rowptr), _ptr(nbr), _ptr(w_out),
                                       _ptr(eid), C.byref(nnz) if sync else None, _ptr(ws), ws.numel(), _stream()), "csr_from_coo")
-    _count(10)
+    _count(6)            # count, scan, fill, sort_rows, scan, compact_rows
     if not sync:
         g = CSRGraph(rowptr, nbr, n_nodes, None, w_out)
         return (g, eid) if want_eid else g
@@ -241,7 +241,7 @@ def csr_from_sorted_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional
     _lib.check(lib.geobi_csr_from_sorted_coo(_ptr(ei[0]), _ptr(ei[1]), _ptr(w), e, n_nodes, 1 if check_symmetric else 0, _ptr(rowptr),
                                              _ptr(nbr), _ptr(w_out), _ptr(ei_out) if e else None, _ptr(ws), ws.numel(), _stream()),
                "csr_from_sorted_coo")
-    _count(8)
+    _count(6 if check_symmetric else 5)
     return CSRGraph(rowptr, nbr, n_nodes, 0 if e == 0 else None, w_out, True), ei_out, w_out
 
 
@@ -258,7 +258,7 @@ def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor) -> CSRGraph:
     nnz = C.c_int64(0)
     _lib.check(lib.geobi_build_facet_graph(_ptr(fv), _ptr(vf), f, v, k, _ptr(rowptr), _ptr(nbr), C.byref(nnz), _ptr(ws), ws.numel(),
                                            _stream()), "build_facet_graph")
-    _count(6)
+    _count(4)
     n = int(nnz.value)
     return CSRGraph(rowptr, nbr[:n].clone(), f, n, None, True)
 
@@ -286,7 +286,7 @@ def graclus(g: CSRGraph, perm: Optional[torch.Tensor] = None, weight: Optional[t
     und = C.c_int(0)
     _lib.check(lib.geobi_graclus(_ptr(g.rowptr), _ptr(g._nbr), _ptr(w), _ptr(rank), g.n, _ptr(label), C.byref(und) if check else None,
                                  _ptr(ws), ws.numel(), _stream()), "graclus")
-    _count(1)
+    _count(2)
     return label, und.value
 
 
@@ -300,7 +300,7 @@ def relabel_clusters(label: torch.Tensor):
     ws = _ws(lib.geobi_relabel_ws_bytes(n), label.device)
     nc = C.c_int64(0)
     _lib.check(lib.geobi_relabel_clusters(_ptr(label), n, _ptr(cluster), C.byref(nc), _ptr(ws), ws.numel(), _stream()), "relabel_clusters")
-    _count(5)
+    _count(3)
     return cluster, int(nc.value)
 
 
@@ -314,7 +314,7 @@ def group_by(cluster: torch.Tensor, n_clusters: int):
     members = valloc(max(n, 1), (), torch.int32, dev)
     ws = _ws(lib.geobi_group_by_ws_bytes(n, n_clusters), dev)
     _lib.check(lib.geobi_group_by(_ptr(cluster), n, n_clusters, _ptr(mrowptr), _ptr(members), _ptr(ws), ws.numel(), _stream()), "group_by")
-    _count(10)
+    _count(6)
     return mrowptr, members[:n]
 
 
@@ -329,7 +329,7 @@ def group_pairs(label: torch.Tensor, cluster: torch.Tensor, n_clusters: int):
     ws = _ws(lib.geobi_group_pairs_ws_bytes(n_clusters), dev)
     _lib.check(lib.geobi_group_pairs(_ptr(label), _ptr(cluster), n, n_clusters, _ptr(mrowptr), _ptr(members), _ptr(ws), ws.numel(),
                                      _stream()), "group_pairs")
-    _count(6)
+    _count(4)
     return mrowptr, members[:n]
 
 
@@ -346,7 +346,7 @@ def pool_edges(g: CSRGraph, cluster: torch.Tensor, mrowptr: torch.Tensor, member
     _lib.check(lib.geobi_pool_edges(_ptr(g.rowptr), _ptr(g._nbr), _ptr(gw), g.n, cap, _ptr(cluster), _ptr(mrowptr), _ptr(members),
                                     n_clusters, _ptr(out_rowptr), _ptr(out_nbr), _ptr(out_w), None, _ptr(ws), ws.numel(),
                                     _stream()), "pool_edges")
-    _count(8)
+    _count(6)
     return CSRGraph(out_rowptr, out_nbr[:cap] if cap else out_nbr[:0], n_clusters, 0 if cap == 0 else None,
                     None if out_w is None else (out_w[:cap] if cap else out_w[:0]), g.symmetric)
 
@@ -377,7 +377,7 @@ def pool_step(g: CSRGraph, label: torch.Tensor, x: torch.Tensor, op: int, pos: O
     _lib.check(lib.geobi_pool_step(_ptr(g.rowptr), _ptr(g._nbr), _ptr(gw), n, cap, _ptr(label), _ptr(x), ldx, c, op, _ptr(p), ldp or 0, cp or 0,
                                    _ptr(cluster), _ptr(mrowptr), _ptr(members), _ptr(x_out), c, _ptr(pos_out), cp or 0, _ptr(out_rowptr),
                                    _ptr(out_nbr), _ptr(out_w), C.byref(nc), _ptr(ws), ws.numel(), _stream()), "pool_step")
-    _count(5 + 6 + 1 + 8 + (1 if pos is not None else 0))
+    _count(3 + 4 + 1 + 6 + (1 if pos is not None else 0))
     k = int(nc.value)
     gc = CSRGraph(out_rowptr[:k + 1], out_nbr[:cap] if cap else out_nbr[:0], k, 0 if cap == 0 else None,
                   None if out_w is None else (out_w[:cap] if cap else out_w[:0]), g.symmetric)
@@ -398,7 +398,7 @@ def remove_self_loops(edge_index: torch.Tensor, weight: Optional[torch.Tensor], 
     ws = _ws(lib.geobi_remove_self_loops_ws_bytes(e), dev)
     _lib.check(lib.geobi_remove_self_loops(_ptr(ei[0]), _ptr(ei[1]), _ptr(w), e, count, _ptr(out), _ptr(w_out), _ptr(ws), ws.numel(),
                                            _stream()), "remove_self_loops")
-    _count(5)
+    _count(3)
     return out, w_out
 
 
@@ -481,7 +481,8 @@ def feast_fwd(x: torch.Tensor, g: CSRGraph, W: torch.Tensor, U: torch.Tensor, c:
     _lib.check(lib.geobi_feast_fwd(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(row_map), n_src, _ptr(W.contiguous()),
                                    _ptr(U.contiguous()), _ptr(c.contiguous()), _ptr(bias.contiguous()), c_out, float(act_slope), _ptr(o), ldo,
                                    precision, _ptr(ws), ws.numel(), _stream()), "feast_fwd")
-    _count(4)
+    # bf16: weight split + projection + aggregation + GEMM; the fused 64->32 kernel merges the last two; fp32 has no weight split
+    _count(3 if (precision & 0xff) == PREC_FP32 or ((precision & 0xff) == PREC_BF16X3 and c_in == 64 and c_out == 32) else 4)
     return out
 
 
