@@ -72,21 +72,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_onepass_kernel(const int* _
   }
   int tot;
   int ex = block_excl_scan(s, &tot);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // warp-wide look-back: 32 predecessors per step; stop at the nearest one that already knows its inclusive prefix
+    const int lane = threadIdx.x;
     int run = 0;
     if (tile > 0) {
-      atomicExch(desc + tile, (1ull << 62) | (unsigned)tot);
-      for (int t = (int)tile - 1;; --t) {
-        unsigned long long d;
-        do {
-          d = *reinterpret_cast<volatile unsigned long long*>(desc + t);
-        } while ((d >> 62) == 0);
-        run += (int)(unsigned)d;
-        if ((d >> 62) == 2) break;
+      if (lane == 0) atomicExch(desc + tile, (1ull << 62) | (unsigned)tot);
+      for (int hi = (int)tile - 1; hi >= 0; hi -= 32) {
+        const int t = hi - lane;
+        unsigned long long d = 2ull << 62;             // lanes before tile 0 act as a zero prefix
+        if (t >= 0) {
+          do {
+            d = *reinterpret_cast<volatile unsigned long long*>(desc + t);
+          } while ((d >> 62) == 0);
+        }
+        const unsigned full = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+        const int stop = full ? __ffs(full) - 1 : 31;   // nearest predecessor with a full prefix
+        int v2 = lane <= stop ? (int)(unsigned)d : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        run += v2;
+        if (full) break;
       }
     }
-    atomicExch(desc + tile, (2ull << 62) | (unsigned)(run + tot));
-    s_prefix = run;
+    if (lane == 0) {
+      atomicExch(desc + tile, (2ull << 62) | (unsigned)(run + tot));
+      s_prefix = run;
+    }
   }
   __syncthreads();
   ex += s_prefix;
@@ -829,12 +841,122 @@ __global__ void __launch_bounds__(256) pool_fill_kernel(const int* __restrict__ 
     pos += e - s;
   }
 }
+// Fused row builder: one warp per coarse node gathers its members' relabelled fine rows, rank-sorts them, merges
+// duplicates (mean weight, summed in key order like compact_rows_kernel) and writes the unique entries to a temporary row
+// at the node's raw offset - all out of shared memory for rows of up to PR_ML raw entries (mesh coarsening: ~25-60), out
+// of the global scratch arrays beyond that.  Replaces pool_fill + sort_rows + compact_rows (three passes over 64-bit keys
+// in global memory) by this kernel and a plain copy once the unique counts have been scanned.
+constexpr int PR_ML = 64;
+__device__ __forceinline__ void pool_row(int lane, int c, int L, int64_t start, const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                         const float* __restrict__ w, const int* __restrict__ cluster, int mb, int me,
+                                         const int* __restrict__ members, uint64_t* K, uint64_t* S, float* Wt, int32_t* __restrict__ tmp_nbr,
+                                         float* __restrict__ tmp_w, int* __restrict__ ucount) {
+  int pos = 0;
+  for (int k = mb; k < me; ++k) {
+    const int m = members[k];
+    const int s = rowptr[m], e = rowptr[m + 1];
+    for (int q = s + lane; q < e; q += 32) {
+      const int cv = cluster[nbr[q]];
+      const int p = pos + (q - s);
+      K[p] = (cv == c) ? KEY_INVALID : (((uint64_t)(uint32_t)cv << 32) | (uint32_t)p);
+      if (w) Wt[p] = w[q];
+    }
+    pos += e - s;
+  }
+  __syncwarp();
+  int nvalid = 0;
+  for (int i0 = 0; i0 < L; i0 += 32) {
+    const int i = i0 + lane;
+    const uint64_t key = i < L ? K[i] : KEY_INVALID;
+    const bool valid = key != KEY_INVALID;
+    if (valid) {
+      int rank = 0;
+      for (int k = 0; k < L; ++k) rank += (K[k] < key) ? 1 : 0;
+      S[rank] = key;
+    }
+    nvalid += __popc(__ballot_sync(0xffffffffu, valid));
+  }
+  __syncwarp();
+  int base = 0;
+  for (int t0 = 0; t0 < nvalid; t0 += 32) {
+    const int t = t0 + lane;
+    uint64_t key = 0;
+    bool head = false;
+    if (t < nvalid) {
+      key = S[t];
+      head = t == 0 || ((key >> 32) != (S[t - 1] >> 32));
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int64_t o = start + base + __popc(mask & ((1u << lane) - 1u));
+      tmp_nbr[o] = (int32_t)(key >> 32);
+      if (w) {
+        float sum = 0.f;
+        int cnt = 0;
+        for (int q = t; q < nvalid; ++q) {
+          const uint64_t kq = S[q];
+          if (q > t && (kq >> 32) != (key >> 32)) break;
+          sum += Wt[(uint32_t)kq];
+          ++cnt;
+        }
+        tmp_w[o] = sum / (float)cnt;
+      }
+    }
+    base += __popc(mask);
+  }
+  if (lane == 0) ucount[c] = base;
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) pool_rows_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr, const float* __restrict__ w,
+                                                        const int* __restrict__ cluster, const int* __restrict__ mrowptr,
+                                                        const int* __restrict__ members, int64_t nc, const int* __restrict__ raw_rowptr,
+                                                        uint64_t* __restrict__ raw, uint64_t* __restrict__ sorted, float* __restrict__ raw_w,
+                                                        int32_t* __restrict__ tmp_nbr, float* __restrict__ tmp_w, int* __restrict__ ucount,
+                                                        int* __restrict__ status) {
+  __shared__ uint64_t sk[8][PR_ML], ss[8][PR_ML];
+  __shared__ float sw[8][PR_ML];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= nc) return;
+  const int64_t start = raw_rowptr[c];
+  const int L = raw_rowptr[c + 1] - (int)start;
+  const int mb = mrowptr[c], me = mrowptr[c + 1];
+  if (L > MAX_ROW) {
+    if (lane == 0) {
+      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+      ucount[c] = 0;
+    }
+    return;
+  }
+  if (L <= PR_ML) pool_row(lane, (int)c, L, start, rowptr, nbr, w, cluster, mb, me, members, sk[wid], ss[wid], sw[wid], tmp_nbr, tmp_w, ucount);
+  else pool_row(lane, (int)c, L, start, rowptr, nbr, w, cluster, mb, me, members, raw + start, sorted + start, raw_w + start, tmp_nbr, tmp_w, ucount);
+}
+
+// 8 lanes per coarse node: temporary row -> its final place
+__global__ void __launch_bounds__(256) pool_copy_kernel(const int* __restrict__ raw_rowptr, const int* __restrict__ out_rowptr, int64_t nc,
+                                                        const int32_t* __restrict__ tmp_nbr, const float* __restrict__ tmp_w,
+                                                        int32_t* __restrict__ out_nbr, float* __restrict__ out_w) {
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t c = gid >> 3;
+  if (c >= nc) return;
+  const int sub = (int)(gid & 7);
+  const int64_t src = raw_rowptr[c], dst = out_rowptr[c];
+  const int u = out_rowptr[c + 1] - (int)dst;
+  for (int t = sub; t < u; t += 8) {
+    out_nbr[dst + t] = tmp_nbr[src + t];
+    if (out_w) out_w[dst + t] = tmp_w[src + t];
+  }
+}
+
 struct PoolWs {
   int *count, *raw_rowptr, *vcount, *ucount, *status;
   uint64_t *raw, *sorted;
   float* raw_w;
   void* scan;
   size_t scan_bytes;
+  int32_t* tmp_nbr;
+  float* tmp_w;
 };
 template <class C>
 static void carve_pool(C& c, int64_t nnz, int64_t nc, PoolWs* out) {
@@ -848,7 +970,9 @@ static void carve_pool(C& c, int64_t nnz, int64_t nc, PoolWs* out) {
   float* raw_w = c.template take<float>(nnz + 1);
   const size_t sb = scan_ws_bytes(nc + 1);
   char* scan = c.template take<char>(sb);
-  if (out) *out = PoolWs{count, raw_rowptr, vcount, ucount, status, raw, sorted, raw_w, scan, sb};
+  int32_t* tmp_nbr = c.template take<int32_t>(nnz + 1);
+  float* tmp_w = c.template take<float>(nnz + 1);
+  if (out) *out = PoolWs{count, raw_rowptr, vcount, ucount, status, raw, sorted, raw_w, scan, sb, tmp_nbr, tmp_w};
 }
 }  // namespace geobi
 
@@ -876,6 +1000,21 @@ extern "C" int geobi_pool_edges(const int32_t* rowptr, const int32_t* nbr, const
   }
   int rc = scan_i32(W.count, W.raw_rowptr, n_clusters, W.scan, W.scan_bytes, st);
   if (rc) return rc;
+  if (getenv("GEOBI_POOL_GENERIC") == nullptr) {
+    if (n_clusters > 0) {
+      pool_rows_kernel<<<(unsigned)cdiv(n_clusters * 32, 256), 256, 0, st>>>(rowptr, nbr, w, cluster, mrowptr, members, n_clusters, W.raw_rowptr,
+                                                                            W.raw, W.sorted, W.raw_w, W.tmp_nbr, W.tmp_w, W.ucount, W.status);
+      GEOBI_LAUNCH_OK("pool_rows");
+    }
+    rc = scan_i32(W.ucount, out_rowptr, n_clusters, W.scan, W.scan_bytes, st);
+    if (rc) return rc;
+    if (n_clusters > 0 && h_nnz > 0) {
+      pool_copy_kernel<<<(unsigned)cdiv(n_clusters * 8, 256), 256, 0, st>>>(W.raw_rowptr, out_rowptr, n_clusters, W.tmp_nbr, W.tmp_w, out_nbr, out_w);
+      GEOBI_LAUNCH_OK("pool_copy");
+    }
+    if (nnz_host) return finish_sync(W.status, out_rowptr, n_clusters, nnz_host, "pool_edges", st);
+    return GEOBI_OK;
+  }
   if (n_clusters > 0) {
     pool_fill_kernel<<<(unsigned)cdiv(n_clusters * 32, 256), 256, 0, st>>>(rowptr, nbr, w, cluster, mrowptr, members, n_clusters, W.raw_rowptr,
                                                                           W.raw, w ? W.raw_w : nullptr);

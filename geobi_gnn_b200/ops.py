@@ -346,7 +346,7 @@ def pool_edges(g: CSRGraph, cluster: torch.Tensor, mrowptr: torch.Tensor, member
     _lib.check(lib.geobi_pool_edges(_ptr(g.rowptr), _ptr(g._nbr), _ptr(gw), g.n, cap, _ptr(cluster), _ptr(mrowptr), _ptr(members),
                                     n_clusters, _ptr(out_rowptr), _ptr(out_nbr), _ptr(out_w), None, _ptr(ws), ws.numel(),
                                     _stream()), "pool_edges")
-    _count(6)
+    _count(5)            # pool_count, scan, pool_rows, scan, pool_copy
     return CSRGraph(out_rowptr, out_nbr[:cap] if cap else out_nbr[:0], n_clusters, 0 if cap == 0 else None,
                     None if out_w is None else (out_w[:cap] if cap else out_w[:0]), g.symmetric)
 
@@ -377,7 +377,7 @@ def pool_step(g: CSRGraph, label: torch.Tensor, x: torch.Tensor, op: int, pos: O
     _lib.check(lib.geobi_pool_step(_ptr(g.rowptr), _ptr(g._nbr), _ptr(gw), n, cap, _ptr(label), _ptr(x), ldx, c, op, _ptr(p), ldp or 0, cp or 0,
                                    _ptr(cluster), _ptr(mrowptr), _ptr(members), _ptr(x_out), c, _ptr(pos_out), cp or 0, _ptr(out_rowptr),
                                    _ptr(out_nbr), _ptr(out_w), C.byref(nc), _ptr(ws), ws.numel(), _stream()), "pool_step")
-    _count(3 + 4 + 1 + 6 + (1 if pos is not None else 0))
+    _count(3 + 4 + 1 + 5 + (1 if pos is not None else 0))
     k = int(nc.value)
     gc = CSRGraph(out_rowptr[:k + 1], out_nbr[:cap] if cap else out_nbr[:0], k, 0 if cap == 0 else None,
                   None if out_w is None else (out_w[:cap] if cap else out_w[:0]), g.symmetric)

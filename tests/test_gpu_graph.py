@@ -197,3 +197,35 @@ def test_csr_from_sorted_coo_matches_general_builder_and_rejects_broken_promises
     e0 = torch.empty((2, 0), dtype=torch.int64, device=DEV)
     g, _, _ = ops.csr_from_sorted_coo(e0, 7, None)
     assert g.nnz == 0 and torch.equal(g.rowptr, torch.zeros(8, dtype=torch.int32, device=DEV))
+
+
+@pytest.mark.gpu
+def test_pool_edges_fused_rows_equal_generic_pipeline_including_long_rows():
+    """pool_rows_kernel (shared-memory rows, global scratch beyond 64 raw entries) == fill + sort_rows + compact_rows."""
+    import os
+    from geobi_gnn_b200 import ops
+    torch.manual_seed(11)
+    n = 3000
+    # random graph + two hubs (rows of ~400 entries) so both the shared-memory and the scratch path run
+    src = torch.randint(0, n, (9000,))
+    dst = torch.randint(0, n, (9000,))
+    hub = torch.cat([torch.zeros(400, dtype=torch.long), torch.ones(350, dtype=torch.long)])
+    spokes = torch.randint(2, n, (750,))
+    ei = torch.stack([torch.cat([src, hub]), torch.cat([dst, spokes])]).to(DEV)
+    w = torch.rand(ei.size(1), device=DEV)
+    g = ops.csr_from_coo(ei, n, w, ops.COO_SYMMETRIZE | ops.COO_SORT_NBR | ops.COO_DEDUP | ops.COO_DROP_SELF | ops.COO_W_MEAN)
+    assert int((g.rowptr[1:] - g.rowptr[:-1]).max()) > 64
+    label, _ = ops.graclus(g, torch.randperm(n).to(DEV))
+    cluster, nc = ops.relabel_clusters(label)
+    mrowptr, members = ops.group_pairs(label, cluster, nc)
+    fused = ops.pool_edges(g, cluster, mrowptr, members, nc)
+    os.environ["GEOBI_POOL_GENERIC"] = "1"
+    try:
+        generic = ops.pool_edges(g, cluster, mrowptr, members, nc)
+    finally:
+        del os.environ["GEOBI_POOL_GENERIC"]
+    assert fused.nnz == generic.nnz > 0
+    assert torch.equal(fused.rowptr, generic.rowptr) and torch.equal(fused.nbr, generic.nbr) and torch.equal(fused.w, generic.w)
+    # no weights
+    f2 = ops.pool_edges(g.with_weight(None), cluster, mrowptr, members, nc)
+    assert f2.nnz == generic.nnz and torch.equal(f2.nbr, generic.nbr) and f2.w is None
