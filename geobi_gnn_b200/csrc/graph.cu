@@ -518,13 +518,15 @@ __device__ __forceinline__ int2 ld_state(const int2* st, int v) {
   const long long raw = __ldcg(reinterpret_cast<const long long*>(st) + v);
   return make_int2((int)(raw & 0xffffffffll), (int)(raw >> 32));
 }
+// `blk` (in/out) is the node u is waiting for, -1 if none; the owner thread keeps it in a register, so a blocked node
+// costs ONE load per sweep (its blocker's label) - with the blocker in memory the poll was three dependent loads
+// (own state slot -> own label -> blocker's label), ~45 % of the kernel's stall samples.
 __device__ __forceinline__ int graclus_try(int u, const int* __restrict__ rowptr, const int* __restrict__ nbr, const float* __restrict__ w,
-                                           int2* st, int* blk, int* __restrict__ label_out) {
+                                           int2* st, int& blk, int* __restrict__ label_out) {
   int* lab = reinterpret_cast<int*>(st);           // label of node v at lab[2 * v]
+  if (blk >= 0 && __ldcg(lab + 2 * blk) < 0) return 0;   // the node we are waiting for is still undecided (fast path)
   const int2 su = ld_state(st, u);
   if (su.x >= 0) { label_out[u] = su.x; return 1; }   // claimed by a partner
-  const int b = blk[u];
-  if (b >= 0 && __ldcg(lab + 2 * b) < 0) return 0;    // the node we are waiting for is still undecided (fast path)
   const int ru = su.y;
   const int end = rowptr[u + 1];
   int best = -1, blocker = -1;
@@ -548,7 +550,7 @@ __device__ __forceinline__ int graclus_try(int u, const int* __restrict__ rowptr
       else if (wt[k] >= wmax) { best = v[k]; wmax = wt[k]; }
     }
   }
-  if (blocker >= 0) { blk[u] = blocker; return 0; }
+  if (blocker >= 0) { blk = blocker; return 0; }
   // Only earlier neighbours can claim u, and a claimer CASes label[u] *before* it publishes its own label.  All of them
   // are now observed decided, so after this fence a claim on u (if any) is visible; if none, nobody can claim u any more.
   __threadfence();
@@ -569,10 +571,10 @@ __device__ __forceinline__ int graclus_try(int u, const int* __restrict__ rowptr
     for (int k = 0; k < GCH; ++k) sz[k] = z[k] >= 0 ? ld_state(st, z[k]) : make_int2(0, 0);
 #pragma unroll
     for (int k = 0; k < GCH; ++k)
-      if (z[k] >= 0 && sz[k].x < 0 && precedes(sz[k].y, z[k], ru, u)) { blk[u] = z[k]; return 0; }   // it may still claim `best`
+      if (z[k] >= 0 && sz[k].x < 0 && precedes(sz[k].y, z[k], ru, u)) { blk = z[k]; return 0; }   // it may still claim `best`
   }
   const int l = best < u ? best : u;
-  if (atomicCAS(lab + 2 * best, -1, l) != -1) { blk[u] = -1; return 0; }   // lost a race against a stale view: retry
+  if (atomicCAS(lab + 2 * best, -1, l) != -1) { blk = -1; return 0; }   // lost a race against a stale view: retry
   __threadfence();
   __stcg(lab + 2 * u, l);
   label_out[u] = l;
@@ -591,15 +593,35 @@ __global__ void __launch_bounds__(256) graclus_async_kernel(const int* __restric
                                                             int* undecided) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
+  // per-node wait state: -2 done, -1 evaluate, >= 0 blocker.  The first GR_OWN nodes of a thread live in registers
+  // (a co-resident grid owns ~2 nodes per thread at the sizes of this path), any further ones in pos[].
+  constexpr int GR_OWN = 4;
+  int blk[GR_OWN];
   int left = 0;
-  for (int u = tid; u < n; u += stride) ++left;
+#pragma unroll
+  for (int k = 0; k < GR_OWN; ++k) {
+    const long long u = (long long)tid + (long long)k * stride;
+    blk[k] = u < n ? -1 : -2;
+    left += u < n ? 1 : 0;
+  }
+  const long long u_mem = (long long)tid + (long long)GR_OWN * stride;
+  for (long long u = u_mem; u < n; u += stride) ++left;
   unsigned backoff = 32;
   for (int sweep = 0; left > 0 && sweep < GRACLUS_MAX_SWEEPS; ++sweep) {
     int still = 0;
-    for (int u = tid; u < n; u += stride) {
-      if (pos[u] == -2) continue;        // done marker
-      if (graclus_try(u, rowptr, nbr, w, st, pos, label)) pos[u] = -2;
+#pragma unroll
+    for (int k = 0; k < GR_OWN; ++k) {
+      if (blk[k] == -2) continue;
+      const int u = tid + k * stride;
+      if (graclus_try(u, rowptr, nbr, w, st, blk[k], label)) blk[k] = -2;
       else ++still;
+    }
+    for (long long u = u_mem; u < n; u += stride) {
+      int b = pos[u];
+      if (b == -2) continue;
+      if (graclus_try((int)u, rowptr, nbr, w, st, b, label)) b = -2;
+      else ++still;
+      pos[u] = b;
     }
     if (still == left) {                 // no progress: let the owners of the blocking nodes run
       __nanosleep(backoff);
@@ -611,8 +633,11 @@ __global__ void __launch_bounds__(256) graclus_async_kernel(const int* __restric
   }
   if (left > 0) {
     atomicAdd(undecided, left);
-    for (int u = tid; u < n; u += stride)
-      if (pos[u] != -2) label[u] = -1;   // sweep limit: leave a detectable marker (relabel_clusters rejects it)
+#pragma unroll
+    for (int k = 0; k < GR_OWN; ++k)
+      if (blk[k] != -2) label[tid + k * stride] = -1;   // sweep limit: leave a detectable marker (relabel_clusters rejects it)
+    for (long long u = u_mem; u < n; u += stride)
+      if (pos[u] != -2) label[u] = -1;
   }
 }
 }  // namespace geobi
