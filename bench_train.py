@@ -21,6 +21,7 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1, help="informational; the world size comes from torchrun (WORLD_SIZE)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--patches", type=int, default=16, help="patches (8000 faces each) per rank per step")
