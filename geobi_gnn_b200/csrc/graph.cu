@@ -872,48 +872,53 @@ __global__ void __launch_bounds__(256) pool_fill_kernel(const int* __restrict__ 
 // of the global scratch arrays beyond that.  Replaces pool_fill + sort_rows + compact_rows (three passes over 64-bit keys
 // in global memory) by this kernel and a plain copy once the unique counts have been scanned.
 constexpr int PR_ML = 64;
-__device__ __forceinline__ void pool_row(int lane, int c, int L, int64_t start, const int* __restrict__ rowptr, const int* __restrict__ nbr,
-                                         const float* __restrict__ w, const int* __restrict__ cluster, int mb, int me,
-                                         const int* __restrict__ members, uint64_t* K, uint64_t* S, float* Wt, int32_t* __restrict__ tmp_nbr,
-                                         float* __restrict__ tmp_w, int* __restrict__ ucount) {
-  int pos = 0;
-  for (int k = mb; k < me; ++k) {
-    const int m = members[k];
-    const int s = rowptr[m], e = rowptr[m + 1];
-    for (int q = s + lane; q < e; q += 32) {
-      const int cv = cluster[nbr[q]];
-      const int p = pos + (q - s);
-      K[p] = (cv == c) ? KEY_INVALID : (((uint64_t)(uint32_t)cv << 32) | (uint32_t)p);
-      if (w) Wt[p] = w[q];
+constexpr int PR_W = 16;   // lanes per coarse node: raw rows are 25-50 entries on meshes, a full warp per row idles half its lanes
+// `sub`, `half`: lane within / index of the PR_W-lane group; ballots are taken warp-wide and masked to the group.
+__device__ __forceinline__ unsigned group_ballot(bool p, int half) { return (__ballot_sync(0xffffffffu, p) >> (half * PR_W)) & ((1u << PR_W) - 1u); }
+__device__ __forceinline__ void pool_row(int sub, int half, bool live, int c, int L, int64_t start, const int* __restrict__ rowptr,
+                                         const int* __restrict__ nbr, const float* __restrict__ w, const int* __restrict__ cluster, int mb,
+                                         int me, const int* __restrict__ members, uint64_t* K, uint64_t* S, float* Wt,
+                                         int32_t* __restrict__ tmp_nbr, float* __restrict__ tmp_w, int* __restrict__ ucount) {
+  if (live) {
+    int pos = 0;
+    for (int k = mb; k < me; ++k) {
+      const int m = members[k];
+      const int s = rowptr[m], e = rowptr[m + 1];
+      for (int q = s + sub; q < e; q += PR_W) {
+        const int cv = cluster[nbr[q]];
+        const int p = pos + (q - s);
+        K[p] = (cv == c) ? KEY_INVALID : (((uint64_t)(uint32_t)cv << 32) | (uint32_t)p);
+        if (w) Wt[p] = w[q];
+      }
+      pos += e - s;
     }
-    pos += e - s;
   }
   __syncwarp();
   int nvalid = 0;
-  for (int i0 = 0; i0 < L; i0 += 32) {
-    const int i = i0 + lane;
-    const uint64_t key = i < L ? K[i] : KEY_INVALID;
+  for (int i0 = 0; __any_sync(0xffffffffu, live && i0 < L); i0 += PR_W) {
+    const int i = i0 + sub;
+    const uint64_t key = (live && i < L) ? K[i] : KEY_INVALID;
     const bool valid = key != KEY_INVALID;
     if (valid) {
       int rank = 0;
       for (int k = 0; k < L; ++k) rank += (K[k] < key) ? 1 : 0;
       S[rank] = key;
     }
-    nvalid += __popc(__ballot_sync(0xffffffffu, valid));
+    nvalid += __popc(group_ballot(valid, half));
   }
   __syncwarp();
   int base = 0;
-  for (int t0 = 0; t0 < nvalid; t0 += 32) {
-    const int t = t0 + lane;
+  for (int t0 = 0; __any_sync(0xffffffffu, t0 < nvalid); t0 += PR_W) {
+    const int t = t0 + sub;
     uint64_t key = 0;
     bool head = false;
     if (t < nvalid) {
       key = S[t];
       head = t == 0 || ((key >> 32) != (S[t - 1] >> 32));
     }
-    const unsigned mask = __ballot_sync(0xffffffffu, head);
+    const unsigned mask = group_ballot(head, half);
     if (head) {
-      const int64_t o = start + base + __popc(mask & ((1u << lane) - 1u));
+      const int64_t o = start + base + __popc(mask & ((1u << sub) - 1u));
       tmp_nbr[o] = (int32_t)(key >> 32);
       if (w) {
         float sum = 0.f;
@@ -929,7 +934,7 @@ __device__ __forceinline__ void pool_row(int lane, int c, int L, int64_t start, 
     }
     base += __popc(mask);
   }
-  if (lane == 0) ucount[c] = base;
+  if (live && sub == 0) ucount[c] = base;
   __syncwarp();
 }
 
@@ -939,23 +944,38 @@ __global__ void __launch_bounds__(256) pool_rows_kernel(const int* __restrict__ 
                                                         uint64_t* __restrict__ raw, uint64_t* __restrict__ sorted, float* __restrict__ raw_w,
                                                         int32_t* __restrict__ tmp_nbr, float* __restrict__ tmp_w, int* __restrict__ ucount,
                                                         int* __restrict__ status) {
-  __shared__ uint64_t sk[8][PR_ML], ss[8][PR_ML];
-  __shared__ float sw[8][PR_ML];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= nc) return;
-  const int64_t start = raw_rowptr[c];
-  const int L = raw_rowptr[c + 1] - (int)start;
-  const int mb = mrowptr[c], me = mrowptr[c + 1];
-  if (L > MAX_ROW) {
-    if (lane == 0) {
-      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
-      ucount[c] = 0;
+  constexpr int GROUPS = 256 / PR_W;
+  __shared__ uint64_t sk[GROUPS][PR_ML], ss[GROUPS][PR_ML];
+  __shared__ float sw[GROUPS][PR_ML];
+  const int sub = threadIdx.x % PR_W, grp = threadIdx.x / PR_W, half = grp & (32 / PR_W - 1);
+  const int64_t c = (int64_t)blockIdx.x * GROUPS + grp;
+  bool live = c < nc;
+  int64_t start = 0;
+  int L = 0, mb = 0, me = 0;
+  if (live) {
+    start = raw_rowptr[c];
+    L = raw_rowptr[c + 1] - (int)start;
+    mb = mrowptr[c];
+    me = mrowptr[c + 1];
+    if (L > MAX_ROW) {
+      if (sub == 0) {
+        atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+        ucount[c] = 0;
+      }
+      live = false;
     }
-    return;
   }
-  if (L <= PR_ML) pool_row(lane, (int)c, L, start, rowptr, nbr, w, cluster, mb, me, members, sk[wid], ss[wid], sw[wid], tmp_nbr, tmp_w, ucount);
-  else pool_row(lane, (int)c, L, start, rowptr, nbr, w, cluster, mb, me, members, raw + start, sorted + start, raw_w + start, tmp_nbr, tmp_w, ucount);
+  // the two groups of a warp walk the same code together (warp-wide ballots / barriers); a long row sends both through
+  // the global-scratch variant one after the other
+  const bool small = !live || L <= PR_ML;
+  if (__all_sync(0xffffffffu, small)) {
+    pool_row(sub, half, live, (int)c, L, start, rowptr, nbr, w, cluster, mb, me, members, sk[grp], ss[grp], sw[grp], tmp_nbr, tmp_w, ucount);
+  } else {
+    pool_row(sub, half, live && small, (int)c, L, start, rowptr, nbr, w, cluster, mb, me, members, sk[grp], ss[grp], sw[grp], tmp_nbr, tmp_w,
+             ucount);
+    pool_row(sub, half, live && !small, (int)c, L, start, rowptr, nbr, w, cluster, mb, me, members, raw + start, sorted + start, raw_w + start,
+             tmp_nbr, tmp_w, ucount);
+  }
 }
 
 // 8 lanes per coarse node: temporary row -> its final place
@@ -1027,7 +1047,7 @@ extern "C" int geobi_pool_edges(const int32_t* rowptr, const int32_t* nbr, const
   if (rc) return rc;
   if (getenv("GEOBI_POOL_GENERIC") == nullptr) {
     if (n_clusters > 0) {
-      pool_rows_kernel<<<(unsigned)cdiv(n_clusters * 32, 256), 256, 0, st>>>(rowptr, nbr, w, cluster, mrowptr, members, n_clusters, W.raw_rowptr,
+      pool_rows_kernel<<<(unsigned)cdiv(n_clusters * PR_W, 256), 256, 0, st>>>(rowptr, nbr, w, cluster, mrowptr, members, n_clusters, W.raw_rowptr,
                                                                             W.raw, W.sorted, W.raw_w, W.tmp_nbr, W.tmp_w, W.ucount, W.status);
       GEOBI_LAUNCH_OK("pool_rows");
     }
