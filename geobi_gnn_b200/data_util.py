@@ -83,10 +83,15 @@ def to_undirected_with_self_loops(ev_t, num_nodes=None):
     n = int(ev_t.max()) + 1 if num_nodes is None else num_nodes
     g = ops.csr_from_coo(ev_t, n, None, ops.COO_SYMMETRIZE | ops.COO_SORT_NBR | ops.COO_DEDUP)
     g.symmetric = True
-    loops = torch.arange(n, device=ev_t.device, dtype=torch.int64).unsqueeze(0).repeat(2, 1)
+    return with_self_loops_appended(g)
+
+
+def with_self_loops_appended(g):
+    """[sorted undirected list | (i,i) for every node] from the loop-free symmetric CSR of a vertex graph."""
+    n = g.n
+    loops = torch.arange(n, device=g.rowptr.device, dtype=torch.int64).unsqueeze(0).repeat(2, 1)
     ei = torch.cat([g.edge_index(), loops], 1)
-    has_loops_in_g = False  # mesh edges carry none; the CSR holds exactly the non-loop part
-    gnn.tag_of(ei)["tgt"] = g
+    gnn.tag_of(ei)["tgt"] = g          # mesh edges carry no loops: the CSR holds exactly the non-loop part
     return ei
 
 

@@ -18,17 +18,23 @@ from .data import Data
 
 
 def _t(a, dtype, device):
+    if torch.is_tensor(a):                      # topology.DeviceTriMesh hands over device tensors
+        return a.to(device=device, dtype=dtype)
     return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(device)
 
 
 def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda"):
     """dataset.py:196-243."""
-    ev, fv = _t(mesh_n.ev, torch.long, device), _t(mesh_n.fv, torch.long, device)
+    fv = _t(mesh_n.fv, torch.long, device)
     vf = _t(mesh_n.vf, torch.long, device)
     edge_dual_fv = data_util.build_edge_fv(fv)
     pos_v = _t(mesh_n.points, torch.float32, device)
     normal_v = _t(mesh_n.vertex_normals, torch.float32, device)
-    edge_idx_v = data_util.to_undirected_with_self_loops(ev.t().contiguous(), pos_v.size(0))
+    if getattr(mesh_n, "vertex_csr", None) is not None:      # DeviceTriMesh already holds to_undirected(ev) as a CSR
+        edge_idx_v = data_util.with_self_loops_appended(mesh_n.vertex_csr)
+    else:
+        ev = _t(mesh_n.ev, torch.long, device)
+        edge_idx_v = data_util.to_undirected_with_self_loops(ev.t().contiguous(), pos_v.size(0))
     edge_wei_v = data_util.calc_weight(pos_v, normal_v, edge_idx_v)
     graph_v = Data(name=f"{name}-v", pos=pos_v, normal=normal_v, edge_index=edge_idx_v, edge_weight=edge_wei_v,
                    depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1], coalesced_undirected=True)
@@ -46,8 +52,12 @@ def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda"):
     return graph_v, graph_f
 
 
-def attach_normalisation(dual_data, points_noisy, ev):
-    """dataset.py:140,151-152: centroid / scale of the whole noisy mesh (numpy fp32, as upstream)."""
+def attach_normalisation(dual_data, points_noisy, ev, precomputed=None):
+    """dataset.py:140,151-152: centroid / scale of the whole noisy mesh (numpy fp32, as upstream).
+    `precomputed` = (centroid tensor, scale) lets a caller that normalises many patches of one mesh pay for it once."""
+    if precomputed is not None:
+        dual_data[0].centroid, dual_data[0].scale = precomputed
+        return dual_data
     p = np.asarray(points_noisy, dtype=np.float32)
     centroid = p.mean(0, keepdims=True)
     q = p - centroid

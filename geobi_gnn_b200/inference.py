@@ -17,10 +17,14 @@ from . import batching, data_util, dataset, patches, synth
 
 
 def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device="cuda", n_iter: int = 60, rank: int = 0, world: int = 1,
-                 forced: Optional[List] = None, return_parts: bool = False):
+                 forced: Optional[List] = None, return_parts: bool = False, device_topology: bool = True):
     """Returns (V [Nv,3] updated vertices, Np [Nf,3] unit facet normals, Vp [Nv,3] network vertices) on `device`
     (meaningful on rank 0 when world > 1).  `forced`: per patch, the 4 pooling layers' raw label lists (tests)."""
     dev = torch.device(device)
+    from . import topology
+    # device_topology: per-patch index arrays and normals come from topology.DeviceTriMesh (GPU) instead of the numpy
+    # stand-in for OpenMesh (synth.TriMesh, ~1.2 s per million faces on the host)
+    make_sub = (lambda pts, fcs: topology.DeviceTriMesh(pts, fcs, dev)) if device_topology else synth.TriMesh
     points_noisy = np.asarray(mesh.points, dtype=np.float32)
     poolings = [net.gnn_v.pooling1, net.gnn_v.pooling2, net.gnn_f.pooling1, net.gnn_f.pooling2]
 
@@ -45,14 +49,16 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         n_patches = len(parts)
         st = patches.Stitcher(mesh.n_vertices, mesh.n_faces, dev)
         slot = np.full(mesh.n_vertices, -1, dtype=np.int64)
+        norm = None                                                 # (centroid, scale) of the WHOLE mesh, computed once
         for k, (sel, seed) in enumerate(parts):
             if k % world != rank:
                 continue
             v_idx, faces = patches.get_submesh(mesh.fv, sel, _slot=slot)
-            sub = synth.TriMesh(mesh.points[v_idx], faces)
+            sub = make_sub(mesh.points[v_idx], faces)
             dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev)
-            dataset.attach_normalisation(dual, points_noisy, mesh.ev)   # centroid / scale of the WHOLE mesh (dataset.py:140,179-180)
+            dataset.attach_normalisation(dual, points_noisy, mesh.ev, precomputed=norm)   # dataset.py:140,179-180
             centroid, scale = dual[0].centroid, dual[0].scale
+            norm = (centroid, scale)
             dual = dataset.post_processing(dual, data_type)
             vert_p, norm_p = run(dual, k)
             st.add(vert_p, norm_p, v_idx, sel)
