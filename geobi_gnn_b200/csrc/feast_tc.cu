@@ -6,6 +6,9 @@
 // tcgen05.commit -> mbarrier, accumulator read back with tcgen05.ld (32 lanes x 32 columns per warp).
 // Operands come from fp32 global memory and are rounded to bf16 on the way into shared memory, so no bf16 copy of
 // the activations ever exists in HBM.  No TMA: the A operand is produced by threads (converted / aggregated).
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "tc.cuh"
 
 namespace geobi {
@@ -169,12 +172,165 @@ __global__ void __launch_bounds__(128) tc_gemm_kernel(const __nv_bfloat16* __res
   if (warp == 0) tmem_dealloc(tmem_d, NT < 32 ? 32 : NT);
 }
 
+// ------------------------------------------------------------------------------ same GEMM, operands moved by TMA
+// One elected thread of warp 0 streams the operand tiles with cp.async.bulk.tensor (SWIZZLE_128B tensor maps: the boxes
+// land directly in the K-major UMMA layout), one elected thread of warp 1 issues the MMAs; full[] / empty[] mbarriers
+// form the ring.  Against the cp.async version this removes ~24 address computations + copies per thread per stage
+// (the 128-thread CTA was spending its issue slots on them) and the per-stage __syncthreads.
+template <int NT, int PASSES, int STAGES>
+__global__ void __launch_bounds__(128) tc_gemm_tma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                                                          const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                                                          int64_t M, int kpad, const float* __restrict__ bias, float slope,
+                                                          float* __restrict__ out, int64_t ldo) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[STAGES];
+  __shared__ __align__(8) uint64_t empty[STAGES];
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_slot;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int SPLIT = PASSES == 3 ? 2 : 1;
+  constexpr int A_BYTES = BM * 128, B_BYTES = NT * 128;
+  constexpr int STAGE = SPLIT * (A_BYTES + B_BYTES);   // [A_hi | A_lo | B_hi | B_lo]
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, NT < 32 ? 32 : NT);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+  constexpr uint32_t idesc = make_idesc(BM, NT);
+  const int KB = kpad / BK;
+
+  if (warp == 0) {
+    if (elect_one()) {                                   // ---- producer
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        if (kb >= STAGES) mbar_wait(&empty[s], (uint32_t)(((kb / STAGES) - 1) & 1));   // the MMAs that read this slot are done
+        const uint32_t st = base + (uint32_t)(s * STAGE);
+        mbar_expect_tx(&full[s], (uint32_t)STAGE);
+        tma_load_2d(st, &tm_a_hi, kb * BK, (int)m0, &full[s]);
+        if (PASSES == 3) tma_load_2d(st + A_BYTES, &tm_a_lo, kb * BK, (int)m0, &full[s]);
+        tma_load_2d(st + SPLIT * A_BYTES, &tm_b_hi, kb * BK, 0, &full[s]);
+        if (PASSES == 3) tma_load_2d(st + SPLIT * A_BYTES + B_BYTES, &tm_b_lo, kb * BK, 0, &full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {                                   // ---- MMA issue
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&full[s], (uint32_t)((kb / STAGES) & 1));
+        tc_fence_after();
+        const uint32_t st = base + (uint32_t)(s * STAGE);
+        const uint64_t ah = make_desc(st), bh = make_desc(st + SPLIT * A_BYTES);
+#pragma unroll
+        for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bh + 2 * k16, idesc, (kb | k16) ? 1u : 0u);
+        if (PASSES == 3) {
+          const uint64_t al = make_desc(st + A_BYTES), bl = make_desc(st + SPLIT * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bl + 2 * k16, idesc, 1u);
+#pragma unroll
+          for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, al + 2 * k16, bh + 2 * k16, idesc, 1u);
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(&done);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&done, 0u);
+  tc_fence_after();
+
+  // epilogue: thread = output row (TMEM lane); 32 columns at a time
+  const int64_t m = m0 + tid;
+  const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+  for (int c0 = 0; c0 < NT; c0 += 32) {
+    float v[32];
+    tmem_ld32(lane_addr + (uint32_t)c0, v);
+    if (m < M) {
+      float* o = out + m * ldo + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 r;
+        r.x = v[j] + bias[c0 + j];
+        r.y = v[j + 1] + bias[c0 + j + 1];
+        r.z = v[j + 2] + bias[c0 + j + 2];
+        r.w = v[j + 3] + bias[c0 + j + 3];
+        r.x = r.x > 0.f ? r.x : r.x * slope;
+        r.y = r.y > 0.f ? r.y : r.y * slope;
+        r.z = r.z > 0.f ? r.z : r.z * slope;
+        r.w = r.w > 0.f ? r.w : r.w * slope;
+        *reinterpret_cast<float4*>(o + j) = r;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, NT < 32 ? 32 : NT);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libgeobi links cudart statically, not libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    cudaGetLastError();
+  }
+  return fn;
+}
+// bf16 [rows, kpad] row-major, box = 64 columns (128 B, the swizzle span) x box_rows
+static bool make_tmap(CUtensorMap* m, const __nv_bfloat16* g, int64_t rows, int kpad, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || rows <= 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)kpad * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t es[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(g), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NT, int PASSES>
 static int launch_gemm(const __nv_bfloat16* A, int64_t a_plane, int64_t M, int kpad, const __nv_bfloat16* Bq, const float* bias, float slope,
                        float* out, int64_t ldo, cudaStream_t st) {
   constexpr int STAGE_BYTES = (PASSES == 3 ? 2 : 1) * (BM * 128 + NT * 128);
-  constexpr int STAGES = 3 * STAGE_BYTES <= 200 * 1024 ? 3 : 2;     // stay under the 227 KB per-CTA limit
+  // as many stages as fit under the 227 KB per-CTA limit (one CTA per SM: the bytes in flight are what hides HBM latency)
+  // two CTAs per SM when at least two stages fit in half the shared memory: one CTA's prologue / TMEM drain then overlaps
+  // the other's main loop (A/B on the bench: NT=64 530 -> 501 us, NT=32 (K = 128 only) 159 -> 97 us per step)
+  constexpr int FIT2 = (110 * 1024) / STAGE_BYTES;
+  constexpr int FIT = FIT2 >= 2 ? FIT2 : (220 * 1024) / STAGE_BYTES;
+  constexpr int STAGES = FIT > 6 ? 6 : (FIT < 2 ? 2 : FIT);
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  if (getenv("GEOBI_GEMM_CPASYNC") == nullptr && M > 0 && (reinterpret_cast<uintptr_t>(A) & 127) == 0 && (reinterpret_cast<uintptr_t>(Bq) & 127) == 0 &&
+      (a_plane * 2) % 128 == 0) {
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    const bool split = PASSES == 3;
+    bool ok = make_tmap(&ta_hi, A, M, kpad, BM) && make_tmap(&tb_hi, Bq, NT, kpad, NT);
+    ok = ok && make_tmap(&ta_lo, split ? A + a_plane : A, M, kpad, BM) && make_tmap(&tb_lo, split ? Bq + (int64_t)NT * kpad : Bq, NT, kpad, NT);
+    if (ok) {
+      GEOBI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tma_kernel<NT, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_gemm_tma_kernel<NT, PASSES, STAGES><<<(unsigned)cdiv(M, BM), 128, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, kpad, bias, slope, out, ldo);
+      GEOBI_LAUNCH_OK("tc_gemm_tma");
+      return GEOBI_OK;
+    }
+  }
   GEOBI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_kernel<NT, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tc_gemm_kernel<NT, PASSES, STAGES><<<(unsigned)cdiv(M, BM), 128, smem, st>>>(A, a_plane, M, kpad, Bq, bias, slope, out, ldo);
   GEOBI_LAUNCH_OK("tc_gemm");
