@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
   const int row = (warp & 3) * 32 + lane;
   const int chalf = warp >> 2;                         // which 128 columns of the chunk this warp consumes
   const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * 128);
-  float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+  float y0 = 0.f, y1 = 0.f, y2 = 0.f, y0b = 0.f, y1b = 0.f, y2b = 0.f;
 
   const int n_chunks = hidden / FC_CHUNK;
   for (int ch = 0; ch < n_chunks; ++ch) {
@@ -446,22 +446,38 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
     mbar_wait(&mbar, (uint32_t)(ch & 1));
     tc_fence_after();
     const float4* t4 = tab + ch * FC_CHUNK + chalf * 128;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
-      float v[32];
-      tmem_ld32(lane_addr + (uint32_t)c0, v);
+    // two register sets: the TMEM read of the next 32 columns is in flight while the current 32 are consumed; even / odd
+    // columns accumulate separately so each output has two independent FMA chains
+    uint32_t va[32], vb[32];
+    tmem_ld32_issue(lane_addr, va);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      tmem_ld_wait();
+      tmem_ld32_issue(lane_addr + (uint32_t)(64 * half + 32), vb);
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float4 t = t4[c0 + j];
-        float h = v[j] + t.x;
-        h = h > 0.f ? h : 0.2f * h;
-        y0 = fmaf(t.y, h, y0);
-        y1 = fmaf(t.z, h, y1);
-        y2 = fmaf(t.w, h, y2);
+        const float4 t = t4[64 * half + j];
+        float h = __uint_as_float(va[j]) + t.x;
+        h = fmaxf(h, 0.2f * h);
+        if (j & 1) { y0b = fmaf(t.y, h, y0b); y1b = fmaf(t.z, h, y1b); y2b = fmaf(t.w, h, y2b); }
+        else { y0 = fmaf(t.y, h, y0); y1 = fmaf(t.z, h, y1); y2 = fmaf(t.w, h, y2); }
+      }
+      tmem_ld_wait();
+      if (half == 0) tmem_ld32_issue(lane_addr + 64u, va);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float4 t = t4[64 * half + 32 + j];
+        float h = __uint_as_float(vb[j]) + t.x;
+        h = fmaxf(h, 0.2f * h);
+        if (j & 1) { y0b = fmaf(t.y, h, y0b); y1b = fmaf(t.z, h, y1b); y2b = fmaf(t.w, h, y2b); }
+        else { y0 = fmaf(t.y, h, y0); y1 = fmaf(t.z, h, y1); y2 = fmaf(t.w, h, y2); }
       }
     }
     tc_fence_before();
   }
+  y0 += y0b;
+  y1 += y1b;
+  y2 += y2b;
   if (chalf == 1) {
     part[row][0] = y0;
     part[row][1] = y1;

@@ -96,12 +96,14 @@ class HostBatchRunner:
         nxt = runner.upload(host_v, host_f)            # dicts of pinned CPU tensors: x, edge_index, edge_weight (+ fv_indices)
         for ...:
             cur, nxt = nxt, runner.upload(next_host_v, next_host_f)
-            vert_host, normal_host = runner.run(cur)   # valid after torch.cuda.current_stream().synchronize()
+            vert_host, normal_host = runner.run(cur)   # valid after runner.wait() (the read-back runs on its own stream)
     """
 
     def __init__(self, net, device="cuda", coalesced_undirected: bool = False):
         self.net, self.dev = net, torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.dev)
+        self.read_stream = torch.cuda.Stream(self.dev)      # D2H of the outputs: its own stream (and copy engine)
+        self.read_done = None
         self.flag = coalesced_undirected      # the host lists come from dataset.py's builders (see nn.input_graph)
         self.out_host = {}
 
@@ -127,8 +129,22 @@ class HostBatchRunner:
                     t.record_stream(cur)       # allocated on the copy stream, consumed here
         with torch.no_grad():
             vert_p, norm_p, _ = self.net([dv, df])
-        for k, t in (("v", vert_p), ("n", norm_p)):
-            if k not in self.out_host or self.out_host[k].shape != t.shape:
-                self.out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            self.out_host[k].copy_(t, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        if self.read_done is not None:
+            self.read_done.synchronize()       # the previous batch's host buffers are about to be overwritten
+        with torch.cuda.stream(self.read_stream):
+            self.read_stream.wait_event(ready)
+            for k, t in (("v", vert_p), ("n", norm_p)):
+                if k not in self.out_host or self.out_host[k].shape != t.shape:
+                    self.out_host[k] = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                t.record_stream(self.read_stream)
+                self.out_host[k].copy_(t, non_blocking=True)
+            self.read_done = torch.cuda.Event()
+            self.read_done.record(self.read_stream)
         return self.out_host["v"], self.out_host["n"]
+
+    def wait(self):
+        """Block until the host buffers returned by the last run() hold that batch's results."""
+        if self.read_done is not None:
+            self.read_done.synchronize()

@@ -179,5 +179,5 @@ def test_host_batch_runner_equals_direct_forward():
         if i + 1 < 3:
             nxt = runner.upload(*host[i + 1])
         v, n = runner.run(cur)
-        torch.cuda.synchronize()
+        runner.wait()
         assert torch.equal(v, want[i][0]) and torch.equal(n, want[i][1])
