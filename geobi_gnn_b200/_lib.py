@@ -55,7 +55,8 @@ SIGNATURES = {
     "geobi_segment_max_bwd": (_i32, [_p, _i64, _i32, _p, _p, _i64, _p, _i64, _p, _i64, _p]),
     "geobi_linear_tc_ws_bytes": (_sz, [_i64, _i32, _i32]),
     "geobi_linear_tc": (_i32, [_p, _i64, _i64, _i32, _p, _i32, _p, _f32, _p, _i64, _i32, _p, _sz, _p]),
-    "geobi_fc_head_fwd": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i32, _p]),
+    "geobi_fc_head_ws_bytes": (_sz, [_i32]),
+    "geobi_fc_head_fwd": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i32, _p, _sz, _p]),
     "geobi_face_normal": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p]),
     "geobi_v2f_transfer": (_i32, [_p, _i64, _p, _p, _i64, _i32, _i64, _p, _i64, _p]),
     "geobi_update_position_ws_bytes": (_sz, [_i64, _i64]),

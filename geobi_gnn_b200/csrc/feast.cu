@@ -1039,7 +1039,8 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
                     void* ws, size_t ws_bytes, cudaStream_t st);
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
-                   int64_t ldo, cudaStream_t st);
+                   int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t fc_head_tc_ws_bytes(int hidden);
 
 }  // namespace geobi
 
@@ -1095,9 +1096,11 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   return GEOBI_OK;
 }
 
+extern "C" size_t geobi_fc_head_ws_bytes(int hidden) { return fc_head_tc_ws_bytes(hidden); }
+
 extern "C" int geobi_fc_head_fwd(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                                  const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2,
-                                 float* out, int64_t ldo, int precision, void* stream) {
+                                 float* out, int64_t ldo, int precision, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GEOBI_REQUIRE(f && W1 && b1 && W2 && b2 && out && n >= 0, "fc_head_fwd: null argument");
   GEOBI_REQUIRE(c_in == 32 || c_in == 64, "fc_head_fwd: c_in must be 32 or 64 (got %d)", c_in);
@@ -1109,7 +1112,7 @@ extern "C" int geobi_fc_head_fwd(const float* f, int64_t ldf, int64_t n, int c_i
   GEOBI_REQUIRE(precision >= GEOBI_PREC_FP32 && precision <= GEOBI_PREC_BF16X3, "fc_head_fwd: unknown precision %d", precision);
   if (n == 0) return GEOBI_OK;
   if (precision != GEOBI_PREC_FP32 && c_in == 32 && c_out <= 3 && hidden % 256 == 0)
-    return fc_head_fwd_tc(f, ldf, n, c_in, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2, ldres2, out, ldo, st);
+    return fc_head_fwd_tc(f, ldf, n, c_in, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2, ldres2, out, ldo, ws, ws_bytes, st);
   const unsigned blocks = (unsigned)cdiv(n, 64);
   if (c_in == 32)
     fc_head_kernel<32><<<blocks, 256, 0, st>>>(f, ldf, n, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2, ldres2, out, ldo);

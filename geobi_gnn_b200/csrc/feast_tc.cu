@@ -373,30 +373,76 @@ __global__ void split_rows_kernel(const float* __restrict__ A, int64_t lda, int6
 // +b1, leaky_relu, dotted with W2 (<= 4 outputs) on CUDA cores.  The [N,1024] hidden never reaches shared memory or HBM.
 // 256 threads: warps w and w+4 share a TMEM lane quadrant and split each chunk's columns.
 constexpr int FC_CHUNK = 256;
-__global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict__ f, int64_t ldf, int64_t N, const float* __restrict__ W1,
+// W1 [hidden, 32] fp32 -> [hidden, 64] bf16 rows: hi(W1[r, :]) | lo(W1[r, :]) - one 128-byte swizzle row per hidden unit, so a
+// 256-row TMA box is a ready B-operand tile (k 0..31 = hi, 32..63 = lo).  Done once per call instead of by every CTA per chunk.
+__global__ void fc_w1_split_kernel(const float* __restrict__ W1, int hidden, __nv_bfloat16* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= hidden * 32) return;
+  const int r = t >> 5, c = t & 31;
+  const float v = W1[t];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  out[r * 64 + c] = hi;
+  out[r * 64 + 32 + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ unsigned long long pack_u2(uint32_t lo, uint32_t hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict__ f, int64_t ldf, int64_t N,
+                                                         const __grid_constant__ CUtensorMap tm_w1,
                                                          const float* __restrict__ b1, int hidden, const float* __restrict__ W2,
                                                          const float* __restrict__ b2, int CO, int epilogue, const float* __restrict__ res,
                                                          int64_t ldres, const float* __restrict__ res2, int64_t ldres2,
                                                          float* __restrict__ out, int64_t ldo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(8) uint64_t w_full[2];          // W1 chunk landed in b_t[0 / 1] (TMA, byte-counted)
   __shared__ uint32_t tmem_slot;
   __shared__ float part[128][4];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* a_t = sm;                                   // [128 rows x 128 B]: k 0..31 = hi, 32..63 = lo
-  uint8_t* b_t = sm + BM * 128;                        // [256 rows x 128 B]: same packing for the W1 chunk
-  float4* tab = reinterpret_cast<float4*>(sm + BM * 128 + FC_CHUNK * 128);   // [hidden] {b1, w2_0, w2_1, w2_2}
+  uint8_t* b_t = sm + BM * 128;                        // 2 x [256 rows x 128 B]: same packing for the W1 chunks (double buffered)
+  // [hidden / 2][2] float4: {b1[j], b1[j+1], w2_0[j], w2_0[j+1]}, {w2_1[j], w2_1[j+1], w2_2[j], w2_2[j+1]} - pairs of hidden units
+  // so that the epilogue runs on packed f32x2 instructions
+  float4* tab = reinterpret_cast<float4*>(sm + BM * 128 + 2 * FC_CHUNK * 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
 
+  const int n_chunks = hidden / FC_CHUNK;
   if (tid == 0) {
     mbar_init(&mbar, 1);
+    mbar_init(&w_full[0], 1);
+    mbar_init(&w_full[1], 1);
     fence_mbar_init();
+    for (int c = 0; c < 2 && c < n_chunks; ++c) {      // the first two weight chunks start streaming right away
+      mbar_expect_tx(&w_full[c], FC_CHUNK * 128);
+      tma_load_2d(smem_u32(b_t + c * FC_CHUNK * 128), &tm_w1, 0, c * FC_CHUNK, &w_full[c]);
+    }
   }
   if (warp == 0) tmem_alloc(&tmem_slot, FC_CHUNK);
-  for (int j = tid; j < hidden; j += 256)
-    tab[j] = make_float4(b1[j], W2[j], CO > 1 ? W2[hidden + j] : 0.f, CO > 2 ? W2[2 * hidden + j] : 0.f);
+  for (int j2 = tid; j2 < hidden / 2; j2 += 256) {
+    const int j = 2 * j2;
+    tab[2 * j2] = make_float4(b1[j], b1[j + 1], W2[j], W2[j + 1]);
+    tab[2 * j2 + 1] = make_float4(CO > 1 ? W2[hidden + j] : 0.f, CO > 1 ? W2[hidden + j + 1] : 0.f, CO > 2 ? W2[2 * hidden + j] : 0.f,
+                                  CO > 2 ? W2[2 * hidden + j + 1] : 0.f);
+  }
   // A tile: 128 rows x 8 float4
   for (int idx = tid; idx < BM * 8; idx += 256) {
     const int r = idx >> 3, c4 = idx & 7;
@@ -416,25 +462,16 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
   const int row = (warp & 3) * 32 + lane;
   const int chalf = warp >> 2;                         // which 128 columns of the chunk this warp consumes
   const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * 128);
-  float y0 = 0.f, y1 = 0.f, y2 = 0.f, y0b = 0.f, y1b = 0.f, y2b = 0.f;
+  unsigned long long y0p = 0ull, y1p = 0ull, y2p = 0ull;   // (even, odd) hidden-unit partial sums of the three outputs
 
-  const int n_chunks = hidden / FC_CHUNK;
   for (int ch = 0; ch < n_chunks; ++ch) {
-    // W1 chunk: 256 rows x 8 float4 (the previous chunk's MMAs have retired: we waited on mbar before its epilogue)
-    for (int idx = tid; idx < FC_CHUNK * 8; idx += 256) {
-      const int r = idx >> 3, c4 = idx & 7;
-      const float4 v = *reinterpret_cast<const float4*>(W1 + (int64_t)(ch * FC_CHUNK + r) * 32 + c4 * 4);
-      uint2 hi, lo;
-      split_bf16x4(v, hi, lo);
-      *reinterpret_cast<uint2*>(b_t + sw128_off(r, c4 >> 1) + (c4 & 1) * 8) = hi;
-      *reinterpret_cast<uint2*>(b_t + sw128_off(r, 4 + (c4 >> 1)) + (c4 & 1) * 8) = lo;
-    }
-    fence_proxy_async();
+    if (ch == 0) fence_proxy_async();                  // the A tile was written with generic stores
     tc_fence_before();
-    __syncthreads();                                   // also: every warp has finished reading TMEM of the previous chunk
+    __syncthreads();                                   // every warp has finished reading TMEM of the previous chunk
     if (tid < 32 && elect_one()) {
+      mbar_wait(&w_full[ch & 1], (uint32_t)((ch >> 1) & 1));
       tc_fence_after();
-      const uint64_t ad = make_desc(smem_u32(a_t)), bd = make_desc(smem_u32(b_t));
+      const uint64_t ad = make_desc(smem_u32(a_t)), bd = make_desc(smem_u32(b_t + (ch & 1) * FC_CHUNK * 128));
       mma_f16(tmem_d, ad + 0, bd + 0, idesc, 0u);      // hi . hi   (k 0..15)
       mma_f16(tmem_d, ad + 2, bd + 2, idesc, 1u);      // hi . hi   (k 16..31)
       mma_f16(tmem_d, ad + 0, bd + 4, idesc, 1u);      // hi . lo
@@ -445,39 +482,42 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
     }
     mbar_wait(&mbar, (uint32_t)(ch & 1));
     tc_fence_after();
-    const float4* t4 = tab + ch * FC_CHUNK + chalf * 128;
-    // two register sets: the TMEM read of the next 32 columns is in flight while the current 32 are consumed; even / odd
-    // columns accumulate separately so each output has two independent FMA chains
+    if (tid == 0 && ch + 2 < n_chunks) {               // this chunk's MMAs are done with b_t[ch & 1]: refill it with chunk ch + 2
+      mbar_expect_tx(&w_full[ch & 1], FC_CHUNK * 128);
+      tma_load_2d(smem_u32(b_t + (ch & 1) * FC_CHUNK * 128), &tm_w1, 0, (ch + 2) * FC_CHUNK, &w_full[ch & 1]);
+    }
+    const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tab) + ch * FC_CHUNK + chalf * 128;   // 2 entries per column pair
+    // two register sets: the TMEM read of the next 32 columns is in flight while the current 32 are consumed; a column pair
+    // costs 2 LDS.128 + add2 + mul2 + 2 max + 3 fma2 (9 issue slots instead of 14 with scalar arithmetic)
     uint32_t va[32], vb[32];
+    auto consume = [&](const uint32_t* v, int col0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        const ulonglong2 ta = t2[col0 + j], tb = t2[col0 + j + 1];
+        unsigned long long h = add2(pack_u2(v[j], v[j + 1]), ta.x);          // + b1
+        const unsigned long long hs = mul2(h, 0x3e4ccccd3e4ccccdull);        // 0.2f, 0.2f
+        h = pack_u2(__float_as_uint(fmaxf(__uint_as_float((unsigned)h), __uint_as_float((unsigned)hs))),
+                    __float_as_uint(fmaxf(__uint_as_float((unsigned)(h >> 32)), __uint_as_float((unsigned)(hs >> 32)))));
+        y0p = fma2(ta.y, h, y0p);
+        y1p = fma2(tb.x, h, y1p);
+        y2p = fma2(tb.y, h, y2p);
+      }
+    };
     tmem_ld32_issue(lane_addr, va);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       tmem_ld_wait();
       tmem_ld32_issue(lane_addr + (uint32_t)(64 * half + 32), vb);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float4 t = t4[64 * half + j];
-        float h = __uint_as_float(va[j]) + t.x;
-        h = fmaxf(h, 0.2f * h);
-        if (j & 1) { y0b = fmaf(t.y, h, y0b); y1b = fmaf(t.z, h, y1b); y2b = fmaf(t.w, h, y2b); }
-        else { y0 = fmaf(t.y, h, y0); y1 = fmaf(t.z, h, y1); y2 = fmaf(t.w, h, y2); }
-      }
+      consume(va, 64 * half);
       tmem_ld_wait();
       if (half == 0) tmem_ld32_issue(lane_addr + 64u, va);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float4 t = t4[64 * half + 32 + j];
-        float h = __uint_as_float(vb[j]) + t.x;
-        h = fmaxf(h, 0.2f * h);
-        if (j & 1) { y0b = fmaf(t.y, h, y0b); y1b = fmaf(t.z, h, y1b); y2b = fmaf(t.w, h, y2b); }
-        else { y0 = fmaf(t.y, h, y0); y1 = fmaf(t.z, h, y1); y2 = fmaf(t.w, h, y2); }
-      }
+      consume(vb, 64 * half + 32);
     }
     tc_fence_before();
   }
-  y0 += y0b;
-  y1 += y1b;
-  y2 += y2b;
+  const float y0 = __uint_as_float((unsigned)y0p) + __uint_as_float((unsigned)(y0p >> 32));
+  const float y1 = __uint_as_float((unsigned)y1p) + __uint_as_float((unsigned)(y1p >> 32));
+  const float y2 = __uint_as_float((unsigned)y2p) + __uint_as_float((unsigned)(y2p >> 32));
   if (chalf == 1) {
     part[row][0] = y0;
     part[row][1] = y1;
@@ -563,16 +603,30 @@ int feast_fwd_tc(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t
   return tc::gemm_dispatch(Wk.Z, (int64_t)N * kpad, N, kpad, Wk.Bq, c_out, bias, act_slope, out, ldo, passes, st);
 }
 
+size_t fc_head_tc_ws_bytes(int hidden) { return align256((size_t)hidden * 64 * sizeof(__nv_bfloat16)) + 256; }
+
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
-                   int64_t ldo, cudaStream_t st) {
+                   int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
   GEOBI_REQUIRE(c_in == 32, "fc_head_fwd (tensor core): c_in must be 32 (got %d)", c_in);
   GEOBI_REQUIRE(hidden % tc::FC_CHUNK == 0 && hidden <= 4096, "fc_head_fwd (tensor core): hidden must be a multiple of 256, <= 4096");
   GEOBI_REQUIRE(c_out <= 3, "fc_head_fwd (tensor core): c_out must be <= 3 (got %d)", c_out);
   GEOBI_REQUIRE(ldf % 4 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "fc_head_fwd (tensor core): feature rows must be 16-byte aligned");
-  const size_t smem = (size_t)tc::BM * 128 + tc::FC_CHUNK * 128 + (size_t)hidden * 16 + 1024;
+  if (!ws || ws_bytes < fc_head_tc_ws_bytes(hidden) || (reinterpret_cast<uintptr_t>(ws) & 127) != 0) {
+    set_error("fc_head_fwd (tensor core): workspace missing, too small or not 128-byte aligned");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  if (n == 0) return GEOBI_OK;
+  __nv_bfloat16* w1q = static_cast<__nv_bfloat16*>(ws);
+  tc::fc_w1_split_kernel<<<(unsigned)cdiv((int64_t)hidden * 32, 256), 256, 0, st>>>(W1, hidden, w1q);
+  CUtensorMap tm;
+  if (!tc::make_tmap(&tm, w1q, hidden, 64, tc::FC_CHUNK)) {
+    set_error("fc_head_fwd (tensor core): cuTensorMapEncodeTiled unavailable");
+    return GEOBI_ERR_CUDA;
+  }
+  const size_t smem = (size_t)tc::BM * 128 + 2 * tc::FC_CHUNK * 128 + (size_t)hidden * 16 + 1024;
   GEOBI_CUDA_OK(cudaFuncSetAttribute(tc::fc_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::fc_head_tc_kernel<<<(unsigned)cdiv(n, tc::BM), 256, smem, st>>>(f, ldf, n, W1, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2,
+  tc::fc_head_tc_kernel<<<(unsigned)cdiv(n, tc::BM), 256, smem, st>>>(f, ldf, n, tm, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2,
                                                                      ldres2, out, ldo);
   GEOBI_LAUNCH_OK("fc_head_tc");
   return GEOBI_OK;

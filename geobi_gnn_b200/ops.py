@@ -520,10 +520,11 @@ def fc_head_fwd(f: torch.Tensor, W1, b1, W2, b2, epilogue: int = 0, res: Optiona
         res, ldres, _ = _rows(res)
     if res2 is not None:
         res2, ldres2, _ = _rows(res2)
+    ws = _ws(lib.geobi_fc_head_ws_bytes(hidden), f.device, slot=1)
     _lib.check(lib.geobi_fc_head_fwd(_ptr(f), ldf, n, c_in, _ptr(W1.contiguous()), _ptr(b1.contiguous()), hidden, _ptr(W2.contiguous()),
                                      _ptr(b2.contiguous()), c_out, epilogue, _ptr(res), ldres, _ptr(res2), ldres2, _ptr(out), oc,
-                                     precision, _stream()), "fc_head_fwd")
-    _count()
+                                     precision, _ptr(ws), ws.numel(), _stream()), "fc_head_fwd")
+    _count(1 if precision == PREC_FP32 else 2)      # tensor-core path: weight split + fused head
     return out
 
 

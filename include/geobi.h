@@ -260,11 +260,13 @@ GEOBI_API int geobi_linear_tc(const float* A, int64_t lda, int64_t M, int K, con
  * reaches HBM:  y = W2 . leaky_relu(W1 . f + b1, 0.2) + b2, then epilogue
  *   0: none | 1: y += res (network.py:332) | 2: y = y * res2 (force_depth, :327; c_out==1
  *   broadcasts) then += res | 3: y = normalize(y) (network.py:343, eps 1e-12).
- * f [N, c_in] (c_in <= 64), W1 [hidden, c_in], W2 [c_out, hidden], c_out <= 4. */
+ * f [N, c_in] (c_in <= 64), W1 [hidden, c_in], W2 [c_out, hidden], c_out <= 4.
+ * ws (tensor-core precisions): the split-bf16 copy of W1 that every CTA streams with TMA; 128-byte aligned. */
+GEOBI_API size_t geobi_fc_head_ws_bytes(int hidden);
 GEOBI_API int geobi_fc_head_fwd(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1,
                       int hidden, const float* W2, const float* b2, int c_out, int epilogue,
                       const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
-                      int64_t ldo, int precision, void* stream);
+                      int64_t ldo, int precision, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ dual-domain transfer */
 
