@@ -488,45 +488,96 @@ __global__ void __launch_bounds__(256) feast_aggregate_packed_kernel(const float
 // there is no shared memory and no warp barrier.  The generic kernel above spends a whole warp on such a node with
 // 6 or 12 of its 32 lanes active.
 template <int V, int OUT>
-__global__ void __launch_bounds__(256, V == 4 ? 3 : 2) feast_aggregate_small_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
+__global__ void __launch_bounds__(256, 2) feast_aggregate_small_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
                                                                     const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                                     const double* __restrict__ P, const float* __restrict__ cvec,
                                                                     void* __restrict__ Zout, int64_t ldz) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, sl = lane & 3;
-  const int64_t w0 = ((int64_t)blockIdx.x * 8 + warp) * 8;
-  if (w0 >= N) return;                               // whole warp past the end
-  const int64_t i_raw = w0 + g;
-  const bool live = i_raw < N;
-  const int64_t i = live ? i_raw : N - 1;            // dead quads shadow the last node and never store
-  const int b = rowptr[i];
-  const int total = rowptr[i + 1] - b + 1;           // neighbours + implicit self loop (slot 0)
-  int maxtotal = total;
-#pragma unroll
-  for (int o = 16; o >= 4; o >>= 1) maxtotal = max(maxtotal, __shfl_xor_sync(0xffffffffu, maxtotal, o));
   const int c0 = sl * V;
   const bool active = c0 < C;                        // C % V == 0 (host)
   const unsigned ldx32 = (unsigned)ldx;
   const float* xl = x + (active ? c0 : 0);
-  double Pi[H];
   float ch[H];
 #pragma unroll
-  for (int h = 0; h < H; ++h) {
-    Pi[h] = P[i * H + h];
-    ch[h] = cvec[h];
-  }
+  for (int h = 0; h < H; ++h) ch[h] = cvec[h];
+
+  // Persistent warps over contiguous ranges of 8-node tiles with a two-deep index pipeline (as feast_aggregate_ps_kernel):
+  // tile t runs on (b, total, its 16 first neighbour ids) fetched during tiles t-2 / t-1, so per chunk only the P rows and the
+  // feature rows - issued together - are a fresh round trip.
+  const int64_t n_tiles = (N + 7) / 8;
+  const int64_t wid = (int64_t)blockIdx.x * 8 + warp, n_warps = (int64_t)gridDim.x * 8;
+  const int64_t t_begin = (n_tiles * wid) / n_warps, t_end = (n_tiles * (wid + 1)) / n_warps;
+  if (t_begin >= t_end) return;
+  auto node_of = [&](int64_t tile) -> int64_t {
+    const int64_t r = tile * 8 + g;
+    return r < N ? r : N - 1;                        // dead quads shadow the last node and never store
+  };
+  auto load_rowptr = [&](int64_t tile, int& b_, int& total_) {
+    if (tile < t_end) {
+      const int64_t i_ = node_of(tile);
+      b_ = rowptr[i_];
+      total_ = rowptr[i_ + 1] - b_ + 1;              // neighbours + implicit self loop (slot 0)
+    } else {
+      b_ = 0;
+      total_ = 1;
+    }
+  };
+  constexpr int PRE = 4;                             // chunks whose neighbour ids are fetched ahead (16 slots: every mesh row)
+  auto load_js = [&](int64_t tile, int b_, int total_, int* jv) {
+    const int self = (int)node_of(tile < t_end ? tile : t_begin);
+#pragma unroll
+    for (int k = 0; k < PRE; ++k) {
+      const int s_ = 4 * k + sl;
+      jv[k] = (tile < t_end && s_ > 0 && s_ < total_) ? nbr[b_ + s_ - 1] : self;
+    }
+  };
+  int b_cur, total_cur, b_nxt, total_nxt, b_nx2 = 0, total_nx2 = 1;
+  int j_cur[PRE], j_nxt[PRE];
+  load_rowptr(t_begin, b_cur, total_cur);
+  load_rowptr(t_begin + 1, b_nxt, total_nxt);
+  load_js(t_begin, b_cur, total_cur, j_cur);
+
+  for (int64_t tile = t_begin; tile < t_end; ++tile) {
+  const int64_t i_raw = tile * 8 + g;
+  const bool live = i_raw < N;
+  const int64_t i = live ? i_raw : N - 1;
+  const int b = b_cur;
+  const int total = total_cur;
+  load_js(tile + 1, b_nxt, total_nxt, j_nxt);
+  load_rowptr(tile + 2, b_nx2, total_nx2);
+  int maxtotal = total;
+#pragma unroll
+  for (int o = 16; o >= 4; o >>= 1) maxtotal = max(maxtotal, __shfl_xor_sync(0xffffffffu, maxtotal, o));
+  double Pi[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) Pi[h] = P[i * H + h];
   float acc[H][V];
 #pragma unroll
   for (int h = 0; h < H; ++h)
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[h][k] = 0.f;
 
+#pragma unroll 1
   for (int s0 = 0; s0 < maxtotal; s0 += 4) {
     const int s = s0 + sl;
     int j = (int)i;                                  // padding slots: weight 0 on the node's own (valid) row
+    if (s0 < 4 * PRE) {
+#pragma unroll
+      for (int k = 0; k < PRE; ++k)
+        if (s0 == 4 * k) j = j_cur[k];
+    } else if (s < total) {
+      j = nbr[b + s - 1];
+    }
+    // the chunk's four feature rows go out together with the P row (both depend only on j)
+    float xv[4][V];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned jt = (unsigned)__shfl_sync(0xffffffffu, j, t, 4);
+      VecLoad<V>::ld(xl + jt * ldx32, xv[t]);
+    }
     float l[H];
     if (s < total) {
-      if (s > 0) j = nbr[b + s - 1];
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
@@ -548,18 +599,19 @@ __global__ void __launch_bounds__(256, V == 4 ? 3 : 2) feast_aggregate_small_ker
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const unsigned jt = (unsigned)__shfl_sync(0xffffffffu, j, t, 4);
-      float xv[V];
-      VecLoad<V>::ld(xl + jt * ldx32, xv);
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         const float q = __shfl_sync(0xffffffffu, l[h], t, 4);
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[h][k] = fmaf(q, xv[k], acc[h][k]);
+        for (int k = 0; k < V; ++k) acc[h][k] = fmaf(q, xv[t][k], acc[h][k]);
       }
     }
   }
-  if (!live) return;
+  b_cur = b_nxt; total_cur = total_nxt;
+  b_nxt = b_nx2; total_nxt = total_nx2;
+#pragma unroll
+  for (int k = 0; k < PRE; ++k) j_cur[k] = j_nxt[k];
+  if (!live) continue;
   if (!active) {
     // bf16 planes feed a GEMM whose K is padded to a multiple of 64: the first idle lane zero-fills columns [9C, ldz)
     if (OUT != 0 && c0 == C) {
@@ -570,7 +622,7 @@ __global__ void __launch_bounds__(256, V == 4 ? 3 : 2) feast_aggregate_small_ker
         if (OUT == 2) *reinterpret_cast<uint32_t*>(zlo + k) = 0u;
       }
     }
-    return;
+    continue;
   }
   const float rcnt = 1.0f / (float)total;            // mean over the neighbourhood (scatter-mean upstream)
   // one 4V-byte (fp32) / 2V-byte (bf16) store per head: C, c0 and ldz are multiples of V (host)
@@ -602,12 +654,21 @@ __global__ void __launch_bounds__(256, V == 4 ? 3 : 2) feast_aggregate_small_ker
       }
     }
   }
+  }   // tile loop
 }
 
 template <int V>
 static void launch_small(int out_mode, cudaStream_t st, const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr,
                          const int32_t* nbr, const double* P, const float* c, void* Z, int64_t ldz) {
-  const unsigned blocks = (unsigned)cdiv(N, 64);
+  static int resident = 0;
+  if (resident == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident = sms * 2;                              // __launch_bounds__(256, 2)
+  }
+  const int64_t want = cdiv(N, 64);
+  const unsigned blocks = (unsigned)(want < resident ? want : resident);
   if (out_mode == 0) feast_aggregate_small_kernel<V, 0><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
   else if (out_mode == 1) feast_aggregate_small_kernel<V, 1><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
   else feast_aggregate_small_kernel<V, 2><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, Z, ldz);
