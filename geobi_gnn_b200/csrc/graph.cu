@@ -508,12 +508,15 @@ __device__ __forceinline__ bool precedes(int rv, int v, int ru, int u) { return 
 // blk[u] caches the node u is waiting for, so a blocked node costs 3 loads per sweep.
 constexpr int GRACLUS_MAX_SWEEPS = 1 << 20;
 
-// One evaluation of node u.  Neighbour rows are read in chunks of 8 with all loads of a chunk (ids -> states, weights)
-// issued back to back, so a decision costs ~2 dependent memory latencies per chunk instead of 3 per neighbour:
+// One evaluation of node u.  Neighbour rows are read in chunks of GCH with all loads of a chunk (ids -> states, weights)
+// issued back to back, so a decision costs ~2 dependent memory latencies per chunk instead of 3 per neighbour.
+// GCH = 4 and two register-resident nodes per thread keep the kernel at 32 registers = 2048 resident threads per SM: the
+// matcher speeds up with the number of nodes that have their own thread (A/B on the bench graphs: 64 registers / chunks
+// of 8 -> 0.58 ms, 32 registers / chunks of 4 -> 0.38 ms on the 512 000-node facet graph; chunks of 16 -> 1.9 ms);
 // the critical path of the whole matching is (dependency depth ~18) x (decision latency).
 // st[v] = {label, rank} interleaved: one 8-byte gather per neighbour returns both (the kernel is bound by L2 sector
 // requests: ~50 scattered reads per evaluation with separate arrays, ~25 with the pair).
-constexpr int GCH = 8;
+constexpr int GCH = 4;
 __device__ __forceinline__ int2 ld_state(const int2* st, int v) {
   const long long raw = __ldcg(reinterpret_cast<const long long*>(st) + v);
   return make_int2((int)(raw & 0xffffffffll), (int)(raw >> 32));
@@ -588,14 +591,14 @@ __global__ void graclus_init_kernel(const int* __restrict__ rank, int n, int2* _
   pos[u] = -1;                           // node this one is waiting for (-1 none, -2 done)
 }
 
-__global__ void __launch_bounds__(256) graclus_async_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(256, 8) graclus_async_kernel(const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                             const float* __restrict__ w, int2* st, int* __restrict__ label, int n, int* pos,
                                                             int* undecided) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
   // per-node wait state: -2 done, -1 evaluate, >= 0 blocker.  The first GR_OWN nodes of a thread live in registers
   // (a co-resident grid owns ~2 nodes per thread at the sizes of this path), any further ones in pos[].
-  constexpr int GR_OWN = 4;
+  constexpr int GR_OWN = 2;
   int blk[GR_OWN];
   int left = 0;
 #pragma unroll
