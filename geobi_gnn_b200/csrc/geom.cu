@@ -32,6 +32,38 @@ __global__ void __launch_bounds__(256) segment_reduce_kernel(const float* __rest
   out[s * ldo + c] = acc;
 }
 
+// float4 variant (C, ldx, ldo multiples of 4, 16-byte aligned bases): thread = (segment, 4 channels)
+__global__ void __launch_bounds__(256) segment_reduce_vec_kernel(const float* __restrict__ x, int64_t ldx, int C4, const int* __restrict__ rowptr,
+                                                                 const int* __restrict__ idx, int fixed, int64_t n_seg, int op,
+                                                                 float* __restrict__ out, int64_t ldo) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t s = t / C4;
+  if (s >= n_seg) return;
+  const int c = (int)(t - s * C4) * 4;
+  const int64_t b = rowptr ? (int64_t)rowptr[s] : s * (int64_t)fixed;
+  const int64_t e = rowptr ? (int64_t)rowptr[s + 1] : b + fixed;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (op == 1) {
+    if (e > b) {
+      acc = *reinterpret_cast<const float4*>(x + (int64_t)idx[b] * ldx + c);
+      for (int64_t k = b + 1; k < e; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)idx[k] * ldx + c);
+        acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+      }
+    }
+  } else {
+    for (int64_t k = b; k < e; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)idx[k] * ldx + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (op == 0) {
+      const float cnt = (float)(e - b > 1 ? e - b : 1);
+      acc.x = acc.x / cnt; acc.y = acc.y / cnt; acc.z = acc.z / cnt; acc.w = acc.w / cnt;
+    }
+  }
+  *reinterpret_cast<float4*>(out + s * ldo + c) = acc;
+}
+
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ x, int64_t ldx, int C, const int* __restrict__ idx,
                                                           int64_t n_out, float* __restrict__ out, int64_t ldo) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -249,8 +281,14 @@ extern "C" int geobi_segment_reduce(const float* x, int64_t ldx, int channels, c
                                     int64_t n_seg, int op, float* out, int64_t ldo, void* stream) {
   GEOBI_REQUIRE(x && idx && out && channels > 0 && n_seg >= 0 && op >= 0 && op <= 2 && (rowptr || fixed > 0), "segment_reduce: bad arguments");
   if (n_seg == 0) return GEOBI_OK;
-  segment_reduce_kernel<<<(unsigned)cdiv(n_seg * channels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, channels, rowptr, idx, fixed,
-                                                                                                              n_seg, op, out, ldo);
+  const bool vec = channels % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (vec)
+    segment_reduce_vec_kernel<<<(unsigned)cdiv(n_seg * (channels / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, ldx, channels / 4, rowptr, idx, fixed, n_seg, op, out, ldo);
+  else
+    segment_reduce_kernel<<<(unsigned)cdiv(n_seg * channels, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, channels, rowptr, idx, fixed,
+                                                                                                                n_seg, op, out, ldo);
   GEOBI_LAUNCH_OK("segment_reduce");
   return GEOBI_OK;
 }
