@@ -23,17 +23,24 @@ using namespace tc;
 #define PREFETCH_MODE 3   // 3: P rows of the next tile into L1 at the end of a tile (A/B: -2 %); x-row prefetches (1, 2) lost
 #endif
 constexpr int C_IN = 64, C_OUT = 32;
-constexpr int NT = 32;            // nodes per tile = MMA N
-constexpr int WARPS = 16;         // aggregation warps, 2 nodes each
+#ifndef FUSED_WARPS
+#define FUSED_WARPS 16
+#endif
+constexpr int WARPS = FUSED_WARPS;   // aggregation warps, 2 nodes each (a multiple of 4: the drain warps must be warps 0, 1 mod 4)
+constexpr int NT = 2 * WARPS;        // nodes per tile = MMA N
+static_assert(WARPS % 4 == 0 && NT % 8 == 0 && NT <= 64, "tile shape");
+constexpr int ACC_COLS = 64;         // TMEM column pitch of the two accumulators
 constexpr int EPI_WARPS = 2;      // warps 16, 17 drain TMEM quadrants 0, 1 (a warp reaches lanes 32*(warp%4)..+31)
 constexpr int MMA_WARP = WARPS + EPI_WARPS;   // warp 18 issues the MMAs
 constexpr int THREADS = (WARPS + EPI_WARPS + 1) * 32;
 constexpr int KB = H;             // one 64-wide K block per head
-constexpr int TILE_BYTES = 32 * 128;   // [32 rows x 128 B] of one K block (W rows = channels, Z rows = nodes)
+constexpr int TILE_BYTES = 32 * 128;   // W: [32 channel rows x 128 B] of one K block
 constexpr int PLANE_BYTES = KB * TILE_BYTES;
+constexpr int ZTILE_BYTES = NT * 128;  // Z: [NT node rows x 128 B] of one K block
+constexpr int ZPLANE_BYTES = KB * ZTILE_BYTES;
 constexpr int QROW = 12;          // floats per soft-assignment row (9 used; 48-byte rows keep the float4 reads aligned)
 constexpr int SCRATCH = 32 * QROW * 4;   // per-warp scratch: the soft-assignment rows of the chunk's 32 slots
-constexpr int SMEM_BYTES = 4 * PLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * SCRATCH + WARPS * 32 * 4 + 64 + 1024;
+constexpr int SMEM_BYTES = 2 * PLANE_BYTES + 2 * ZPLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * SCRATCH + WARPS * 32 * 4 + 64 + 1024;
 
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
@@ -84,9 +91,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* w_hi = sm;
   uint8_t* w_lo = sm + PLANE_BYTES;
+  // the A operand (M = 64) over-reads 32 rows past each W tile: after the last W_lo tile that is the first Z tile - harmless
+  // (those accumulator rows are never read), and the spare TILE_BYTES keeps the Z planes 1024-byte aligned
   uint8_t* z_hi = sm + 2 * PLANE_BYTES;
-  uint8_t* z_lo = sm + 3 * PLANE_BYTES;
-  uint8_t* scratch_all = sm + 4 * PLANE_BYTES + TILE_BYTES;
+  uint8_t* z_lo = sm + 2 * PLANE_BYTES + ZPLANE_BYTES;
+  uint8_t* scratch_all = sm + 2 * PLANE_BYTES + 2 * ZPLANE_BYTES + TILE_BYTES;
   unsigned* joff_all = reinterpret_cast<unsigned*>(scratch_all + WARPS * SCRATCH);
   float* chs = reinterpret_cast<float*>(joff_all + WARPS * 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     mbar_init(&acc_free[1], EPI_WARPS);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 64);
+  if (warp == 0) tmem_alloc(&tmem_slot, 2 * ACC_COLS);
   if (tid < H) chs[tid] = cvec[tid];
   for (int idx = tid; idx < 2 * KB * 32 * 8; idx += THREADS) {
     const int plane = idx / (KB * 32 * 8), rem = idx - plane * (KB * 32 * 8);
@@ -130,7 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       if (k >= 2) mbar_wait(&acc_free[buf], ((k >> 1) - 1) & 1);   // tile k-2 has been drained out of this accumulator
       if (elect_one()) {
         tc_fence_after();
-        const uint32_t acc = tmem_d + buf * NT;
+        const uint32_t acc = tmem_d + buf * ACC_COLS;
         // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
         // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
         uint32_t ah = wh_lo, al = wl_lo, bh = zh_lo, bl = zl_lo;
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(acc, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
 #endif
-          ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += TILE_BYTES >> 4; bl += TILE_BYTES >> 4;
+          ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += ZTILE_BYTES >> 4; bl += ZTILE_BYTES >> 4;
         }
         mma_commit(&mma_done[buf]);
       }
@@ -165,8 +174,14 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       mbar_wait(&mma_done[buf], (k >> 1) & 1);
       tc_fence_after();
       if (quad == 0) TL(2);
-      float v[32];
-      tmem_ld32(tmem_d + buf * NT + ((uint32_t)(quad * 32) << 16), v);
+      float v[NT];
+      {
+        const uint32_t ta = tmem_d + buf * ACC_COLS + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+        for (int c = 0; c + 32 <= NT; c += 32) tmem_ld32(ta + c, v + c);
+#pragma unroll
+        for (int c = NT & ~31; c < NT; c += 8) tmem_ld8(ta + c, v + c);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_free[buf]);  // values are in registers: the accumulator may be overwritten
@@ -396,8 +411,8 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
         const float4 z = make_float4(lo32(acc[h][0]), hi32(acc[h][0]), lo32(acc[h][1]), hi32(acc[h][1]));
         uint2 hi, lo;
         split_bf16x4(z, hi, lo);
-        *reinterpret_cast<uint2*>(z_hi + h * TILE_BYTES + off) = hi;
-        *reinterpret_cast<uint2*>(z_lo + h * TILE_BYTES + off) = lo;
+        *reinterpret_cast<uint2*>(z_hi + h * ZTILE_BYTES + off) = hi;
+        *reinterpret_cast<uint2*>(z_lo + h * ZTILE_BYTES + off) = lo;
       }
     }
     // the next tile's first 16 rows of x and P: pull them into L1 now (their indices, loaded at the top of this
@@ -427,7 +442,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_d, 64);
+    tmem_dealloc(tmem_d, 2 * ACC_COLS);
   }
 }
 
