@@ -80,7 +80,7 @@ class PoolingLayer(torch.nn.Module):
             self.att_r = Parameter(torch.empty(1, in_channel))
             init.xavier_uniform_(self.att_l.data, gain=1.414)
             init.xavier_uniform_(self.att_r.data, gain=1.414)
-        self._unpool_i32 = None
+        self._clusts, self._unpool_i32_val = None, None
         self._unpool_i64 = None
         self.perm_fn = None          # callable(n) -> permutation (upstream draws torch.randperm); None = random keys on device
         self.forced = None           # list of raw label tensors (teacher forcing)
@@ -171,10 +171,9 @@ class PoolingLayer(torch.nn.Module):
             # own cluster: identity pooling) and keeps the edge count on the device, so we only stop when it is known.
             if empty_in or g.cap == 0:
                 break
-        up = clusts[-1]
-        for c in clusts[-2::-1]:
-            up = torch.index_select(up, 0, c)          # composition of the per-step maps (net_util.py:153-156)
-        self._unpool_i32 = up.contiguous()
+        # composition of the per-step maps (net_util.py:153-156): deferred to the first read (the decoder, several layers
+        # later) - right here the GPU queue is empty behind the last count read-back and the next conv should go out first
+        self._clusts, self._unpool_i32_val = clusts, None
         self._unpool_i64 = None
         out = Data(x, None, edge_dual=edge_dual, pos=pos, fv_indices=face)
 
@@ -193,6 +192,15 @@ class PoolingLayer(torch.nn.Module):
         out.set_lazy("edge_weight", coarse_edge_weight)
         out.csr = g
         return out
+
+    @property
+    def _unpool_i32(self):
+        if self._unpool_i32_val is None and self._clusts:
+            up = self._clusts[-1]
+            for c in self._clusts[-2::-1]:
+                up = torch.index_select(up, 0, c)
+            self._unpool_i32_val = up.contiguous()
+        return self._unpool_i32_val
 
     @property
     def unpool_map(self):
