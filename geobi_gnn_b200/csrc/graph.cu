@@ -1150,7 +1150,7 @@ __global__ void sorted_rowptr_kernel(const int* __restrict__ rows32, const int32
                                      int64_t n, int32_t* __restrict__ rowptr, int* __restrict__ bad) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nnz = offs[E];
-  if (p > nnz) return;
+  if (p > nnz || *bad) return;            // out-of-range entries (found by the scatter) left holes in rows32: do not walk them
   const int64_t r = p < nnz ? rows32[p] : n;
   const int64_t prev = p > 0 ? rows32[p - 1] : -1;
   if (p > 0 && p < nnz && (prev > r || (prev == r && nbr[p - 1] >= nbr[p]))) *bad = 1;   // not sorted / duplicate
@@ -1159,7 +1159,7 @@ __global__ void sorted_rowptr_kernel(const int* __restrict__ rows32, const int32
 __global__ void sorted_symmetry_kernel(const int* __restrict__ rows32, const int32_t* __restrict__ nbr, const int* __restrict__ offs, int64_t E,
                                        const int32_t* __restrict__ rowptr, int* __restrict__ bad) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= offs[E]) return;
+  if (p >= offs[E] || *bad) return;       // an unsorted list has no usable rowptr to search in
   const int r = rows32[p], c = nbr[p];
   int lo = rowptr[c], hi = rowptr[c + 1];            // find r in row c
   while (lo < hi) {
@@ -1169,8 +1169,12 @@ __global__ void sorted_symmetry_kernel(const int* __restrict__ rows32, const int
   }
   if (lo >= rowptr[c + 1] || nbr[lo] != r) *bad = 1;
 }
+// a list that broke its promise leaves an EMPTY graph behind (every row [0, 0), count -1): whatever runs on it before the
+// host looks at the count touches no adjacency memory
 __global__ void sorted_verdict_kernel(const int* __restrict__ bad, int32_t* __restrict__ rowptr, int64_t n) {
-  if (*bad) rowptr[n] = -1;
+  if (!*bad) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n) rowptr[i] = i == n ? -1 : 0;
 }
 }  // namespace geobi
 
@@ -1206,7 +1210,7 @@ extern "C" int geobi_csr_from_sorted_coo(const int64_t* row, const int64_t* col,
   sorted_scatter_kernel<<<blocks, 256, 0, st>>>(row, col, w, n_edges, n_nodes, offs, rows32, nbr, w_out, ei_out, bad);
   sorted_rowptr_kernel<<<blocks, 256, 0, st>>>(rows32, nbr, offs, n_edges, n_nodes, rowptr, bad);
   if (flags & GEOBI_SORTED_CHECK_SYMMETRIC) sorted_symmetry_kernel<<<blocks, 256, 0, st>>>(rows32, nbr, offs, n_edges, rowptr, bad);
-  sorted_verdict_kernel<<<1, 1, 0, st>>>(bad, rowptr, n_nodes);
+  sorted_verdict_kernel<<<(unsigned)cdiv(n_nodes + 1, 256), 256, 0, st>>>(bad, rowptr, n_nodes);
   GEOBI_LAUNCH_OK("csr_from_sorted_coo");
   return GEOBI_OK;
 }

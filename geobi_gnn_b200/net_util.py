@@ -29,26 +29,43 @@ def _match_csr(data) -> Optional[CSRGraph]:
     """Source-indexed CSR (stable edge order) + weights, self loops dropped — what graclus sees.
     Also performs the reference's write-back of the stripped edge list (net_util.py:163-167)."""
     n = data.x.size(0)
-    if "csr" in data and data.csr.n == n:                # a PoolingLayer's output: its coarse CSR (weights included) is attached
+    if "csr" in data and data.csr.n == n and not data.csr.rejected:   # a PoolingLayer's output: its coarse CSR (weights included) is attached
         g = data.csr
         return None if g.cap == 0 else g
     ei = data.edge_index
     w = data.edge_weight if "edge_weight" in data else None
     tag = gnn.tag_of(ei)
     st = tag.get("sorted")
-    if st is not None and st[0].n == n and st[3] is w:   # nn.input_graph built it from this very (edge_index, edge_weight)
+    if st is not None and st[0].n == n and st[3] is w and not st[0].rejected:   # nn.input_graph built it from this very (edge_index, edge_weight)
         g, ei2, w2, _ = st
-        nnz = g.nnz                                      # the one sync of this level; raises if the list broke its promise
-        if nnz == 0:
+        if ei.size(1) == 0:
             return None
-        if nnz != ei.size(1):                            # the reference's write-back of the stripped list (net_util.py:163-167)
+        # No sync here: the entry count (which also carries the verdict of the coalesced-list check) is read back
+        # asynchronously and looked at behind the first cluster-count sync of the pooling loop (PoolingLayer._forward).
+        # The reference's write-back of the stripped list (net_util.py:163-167) happens when somebody reads it.
+        g.read_back_async()
+
+        def stripped_edge_index(g=g, ei=ei, ei2=ei2):
+            nnz = g.nnz
+            if nnz == ei.size(1):
+                return ei
             ei_s = ei2[:, :nnz]
             t2 = gnn.tag_of(ei_s)
             t2["tgt"] = t2["src"] = g
-            data.edge_index, data.edge_weight = ei_s, (None if w2 is None else w2[:nnz])
+            return ei_s
+
+        def stripped_edge_weight(g=g, ei=ei, w=w, w2=w2):
+            if w is None:
+                return None
+            return w if g.nnz == ei.size(1) else w2[:g.nnz]
+
+        data.set_lazy("edge_index", stripped_edge_index)
+        if w is not None:
+            data.set_lazy("edge_weight", stripped_edge_weight)
+        data.csr = g                     # set after the lazies: assigning edge_index / edge_weight drops a stale csr
         return g
     g = tag.get("src")
-    if g is not None and g.n == n:                       # built by us: no self loops, CSR order == edge order
+    if g is not None and g.n == n and not g.rejected:    # built by us: no self loops, CSR order == edge order
         if g.cap == 0:
             return None
         return g.with_weight(w)
@@ -129,6 +146,7 @@ class PoolingLayer(torch.nn.Module):
 
     def _forward(self, data, visual=False):
         g = self._get_edge_weight(data)
+        g_in = data.csr if "csr" in data else None     # the level's CSR as built (it may carry an asynchronous count read-back)
         x, pos = data.x, data.pos
         edge_dual = data.edge_dual if "edge_dual" in data else None
         face = data.fv_indices if "fv_indices" in data else None
@@ -150,12 +168,16 @@ class PoolingLayer(torch.nn.Module):
             if self.forced is None and not (torch.is_grad_enabled() and x.requires_grad):
                 # inference: the rest of the step is one library call (same kernels, queued right behind the count read-back)
                 cluster, nc, mrowptr, members, x, g, pos = ops.pool_step(g, label, x, op, pos)
+                if g_in is not None and g_in._pin is not None:
+                    g_in.nnz             # already on the host (queued before the sync pool_step just did): raises on a bad verdict
                 clusts.append(cluster)
                 edge_dual = None if edge_dual is None else cluster.long()[edge_dual]
                 if empty_in or g.cap == 0:
                     break
                 continue
             cluster, nc = ops.relabel_clusters(label)
+            if g_in is not None and g_in._pin is not None:
+                g_in.nnz
             clusts.append(cluster)
             # matcher output = clusters of one or two nodes: member CSR without a sort; arbitrary (forced) labels: general path
             mrowptr, members = ops.group_by(cluster, nc) if self.forced is not None else ops.group_pairs(label, cluster, nc)

@@ -43,7 +43,7 @@ def conv_csr(edge_index: Union[torch.Tensor, CSRGraph], n: int) -> CSRGraph:
         return edge_index
     tag = tag_of(edge_index)
     g = tag.get("tgt")
-    if g is None or g.n != n:
+    if g is None or g.n != n or g.rejected:
         g = ops.csr_from_coo(edge_index, n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR, sync=False)
         tag["tgt"] = g
     return g
@@ -53,12 +53,12 @@ def input_graph(data, n: int) -> CSRGraph:
     """Conv CSR of an input-level graph.  A Data that carries `coalesced_undirected=True` (dataset.py builds its graphs
     with to_undirected / build_facet_graph, so ours sets it) gets the sort-free builder, whose result also serves the
     matcher of the first pooling layer (net_util._match_csr); anything else goes through conv_csr."""
-    if "csr" in data and data.csr.n == n:      # a PoolingLayer's output carries its coarse CSR; edge_index stays unmaterialised
+    if "csr" in data and data.csr.n == n and not data.csr.rejected:      # a PoolingLayer's output carries its coarse CSR; edge_index stays unmaterialised
         return data.csr
     ei = data.edge_index
     tag = tag_of(ei)
     g = tag.get("tgt")
-    if g is not None and g.n == n:
+    if g is not None and g.n == n and not g.rejected:
         return g
     if "coalesced_undirected" in data and data.coalesced_undirected:
         w = data.edge_weight if "edge_weight" in data else None

@@ -126,6 +126,9 @@ def _rows(x: torch.Tensor):
 
 
 # ----------------------------------------------------------------------------- graph container
+_pin_pool = []      # recycled pinned int32[1] landing pads (CSRGraph.read_back_async)
+
+
 class CSRGraph:
     """int32 CSR adjacency without self loops (+ optional per-entry fp32 weight).
 
@@ -134,6 +137,7 @@ class CSRGraph:
 
     def __init__(self, rowptr, nbr, n, nnz=None, w=None, symmetric=False, _ei=None):
         self.rowptr, self._nbr, self.n, self._nnz, self._w, self.symmetric = rowptr, nbr, n, nnz, w, symmetric
+        self._pin = None      # (pinned int32[1], event): an asynchronous read-back of rowptr[n] already in flight
         # weak: the edge_index tensor carries this graph in its tag (nn.tag_of); a strong back-reference would be a cycle
         # that only the cyclic GC frees, i.e. hundreds of MB per forward released late and in bursts
         self._ei_ref = None if _ei is None else weakref.ref(_ei)
@@ -146,11 +150,24 @@ class CSRGraph:
     @property
     def nnz(self) -> int:
         if self._nnz is None:
-            self._nnz = int(self.rowptr[self.n].item()) if self.n > 0 else 0      # syncs
-            if self._nnz < 0:      # geobi_csr_from_sorted_coo's verdict
-                raise _lib.GeobiError("edge list was declared coalesced_undirected but is not: its non-loop entries must be sorted "
-                                      "by (row, col), unique, in range, and contain (j,i) for every (i,j)")
+            if self._pin is not None:
+                pin, ev = self._pin
+                ev.synchronize()                  # free when a later sync of the same stream has already happened
+                self._nnz = int(pin[0])
+                self._pin = None
+                _pin_pool.append(pin)
+            else:
+                self._nnz = int(self.rowptr[self.n].item()) if self.n > 0 else 0      # syncs
+        if self._nnz < 0:      # geobi_csr_from_sorted_coo's verdict
+            raise _lib.GeobiError("edge list was declared coalesced_undirected but is not: its non-loop entries must be sorted "
+                                  "by (row, col), unique, in range, and contain (j,i) for every (i,j)")
         return self._nnz
+
+    @property
+    def rejected(self) -> bool:
+        """True once the device-side check of a `coalesced_undirected` claim is known to have failed (such a graph is empty
+        and must not be served from a tensor's tag cache)."""
+        return self._nnz is not None and self._nnz < 0
 
     @property
     def nbr(self) -> torch.Tensor:
@@ -159,6 +176,16 @@ class CSRGraph:
     @property
     def w(self) -> Optional[torch.Tensor]:
         return self._w if (self._w is None or self._nnz is None) else self._w[:self._nnz]
+
+    def read_back_async(self):
+        """Queue the copy of the entry count (and, for csr_from_sorted_coo, its verdict) into pinned memory; `.nnz` then
+        costs no stream drain once any later synchronisation of this stream has returned."""
+        if self._nnz is None and self._pin is None and self.n > 0:
+            pin = _pin_pool.pop() if _pin_pool else torch.empty(1, dtype=torch.int32).pin_memory()
+            pin.copy_(self.rowptr[self.n:self.n + 1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.rowptr.device))
+            self._pin = (pin, ev)
 
     def with_weight(self, w) -> "CSRGraph":
         return CSRGraph(self.rowptr, self._nbr, self.n, self._nnz, w, self.symmetric, self._ei_ref() if self._ei_ref else None)

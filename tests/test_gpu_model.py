@@ -181,3 +181,30 @@ def test_host_batch_runner_equals_direct_forward():
         v, n = runner.run(cur)
         runner.wait()
         assert torch.equal(v, want[i][0]) and torch.equal(n, want[i][1])
+
+
+@pytest.mark.gpu
+def test_forward_rejects_a_false_coalesced_undirected_claim():
+    """A Data that claims coalesced_undirected but is not must not produce numbers: the device-side verdict surfaces as a
+    GeobiError behind the first pooling step's count read-back."""
+    from geobi_gnn_b200 import _lib, batching, dataset, network
+    torch.manual_seed(6)
+    net = network.DualGNN().to(DEV).eval()
+    mn, mo = util.noisy_icosphere(3, seed=1)
+    dv, df = dataset.build_dual_data(mn, mo, device=DEV)
+    a, b = batching.fresh_view(dv), batching.fresh_view(df)
+    perm = torch.randperm(a.edge_index.size(1), device=DEV)
+    shuffled_ei = a.edge_index[:, perm].contiguous()           # same edge set, no longer sorted
+    shuffled_w = a.edge_weight[perm].contiguous()
+    a.edge_index, a.edge_weight = shuffled_ei, shuffled_w
+    a.coalesced_undirected = True
+    with pytest.raises(_lib.GeobiError):
+        with torch.no_grad():
+            net([a, b])
+    # without the claim the same (unsorted) list is fine
+    a2, b2 = batching.fresh_view(dv), batching.fresh_view(df)
+    a2.edge_index, a2.edge_weight = shuffled_ei, shuffled_w
+    a2.coalesced_undirected = None
+    with torch.no_grad():
+        out = net([a2, b2])
+    assert torch.isfinite(out[0]).all()
