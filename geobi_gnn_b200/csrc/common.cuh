@@ -73,3 +73,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 }  // namespace geobi
+
+// The head projections P = X.U^T are computed in fp64 (feast_project_kernel) and stored as a double-float pair packed in the
+// 8 bytes of a double: low word = hi = (float)P, high word = lo = (float)(P - hi)  (|P - hi - lo| <= 2^-48 |P|).
+// p_diff(a, b) = fl(a - b) to within ~1.5 ulp of the DIFFERENCE on the fp32 pipe (3 FADD) - what the aggregation kernels
+// need for the soft assignments - instead of a DADD + F2F on the fp64 pipe per head and edge.
+#ifdef __CUDACC__
+__device__ __forceinline__ double p_pack(double v) {
+  const float hi = (float)v;
+  const float lo = (float)(v - (double)hi);
+  return __hiloint2double(__float_as_int(lo), __float_as_int(hi));
+}
+__device__ __forceinline__ float p_diff(double a, double b) {
+  const float ah = __int_as_float(__double2loint(a)), al = __int_as_float(__double2hiint(a));
+  const float bh = __int_as_float(__double2loint(b)), bl = __int_as_float(__double2hiint(b));
+  return (ah - bh) + (al - bl);
+}
+#endif

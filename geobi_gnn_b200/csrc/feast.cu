@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float
   double* ps = reinterpret_cast<double*>(xs0);               // 256 x 9 doubles = 18 KB <= one 36 KB x buffer
 #pragma unroll
   for (int h = 0; h < H; ++h) {
-    ps[tid * H + h] = acc[0][h];
-    ps[(tid + PROJ_THREADS) * H + h] = acc[1][h];
+    ps[tid * H + h] = p_pack(acc[0][h]);
+    ps[(tid + PROJ_THREADS) * H + h] = p_pack(acc[1][h]);
   }
   __syncthreads();
   const int64_t left = N - node0;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_kernel(const float* __res
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+        l[h] = p_diff(P[(int64_t)j * H + h], Pi[h]) + ch[h];
         m = fmaxf(m, l[h]);
       }
       float sum = 0.f;
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_packed_kernel(const float
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+        l[h] = p_diff(P[(int64_t)j * H + h], Pi[h]) + ch[h];
         m = fmaxf(m, l[h]);
       }
       float sum = 0.f;
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(256, 2) feast_aggregate_small_kernel(const flo
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+        l[h] = p_diff(P[(int64_t)j * H + h], Pi[h]) + ch[h];
         m = fmaxf(m, l[h]);
       }
       float sum = 0.f;
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
         float m = -INFINITY;
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+          l[h] = p_diff(P[(int64_t)j * H + h], Pi[h]) + ch[h];
           m = fmaxf(m, l[h]);
         }
         float sum = 0.f;

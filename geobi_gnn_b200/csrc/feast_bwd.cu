@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) feast_bwd_edges_kernel(const float* __res
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = (float)(P[(int64_t)j * H + h] - Pi[h]) + ch[h];
+        l[h] = p_diff(P[(int64_t)j * H + h], Pi[h]) + ch[h];
         m = fmaxf(m, l[h]);
       }
       float sum = 0.f;

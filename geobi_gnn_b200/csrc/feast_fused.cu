@@ -307,9 +307,9 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
 #ifdef EXP_NOPLOAD
           l[h] = (float)(__longlong_as_double((long long)(j + h)) - __longlong_as_double((long long)(i_src + h))) + chs[h];
 #elif defined(EXP_NOEXP)
-          l[h] = (float)(Pj[h] - Pi[h]) * 1e-30f + 0.111f;
+          l[h] = p_diff(Pj[h], Pi[h]) * 1e-30f + 0.111f;
 #else
-          l[h] = (float)(Pj[h] - Pi[h]) + chs[h];
+          l[h] = p_diff(Pj[h], Pi[h]) + chs[h];
 #endif
           m = fmaxf(m, l[h]);
         }

@@ -229,7 +229,9 @@ GEOBI_API int geobi_feast_fwd(const float* x, int64_t ldx, int64_t n_nodes, int 
 
 /* ---- training step (train_dual.py:199-218): pieces of the FeaSt / pooling backward that are not plain GEMMs ---- */
 
-/* Forward intermediates for the backward pass: P = X.U^T (fp64 [N,9]) and the aggregate Z (fp32 [N, 9*C_in],
+/* Forward intermediates for the backward pass: P = X.U^T ([N,9], computed in fp64 and stored as a double-float pair
+ * {hi = (float)P, lo = (float)(P - hi)} packed in 8 bytes - opaque to the caller, consumed by geobi_feast_bwd_edges) and the
+ * aggregate Z (fp32 [N, 9*C_in],
  * Z[i, h*C_in + c] = mean_{j in N(i)+{i}} q_ijh x_j[c]).  out = act(Z . W_flat^T + b) is then a dense product. */
 GEOBI_API int geobi_feast_aggregate(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
                                     const int32_t* nbr, const float* U, const float* c, double* P, float* Z, void* stream);
