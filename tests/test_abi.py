@@ -66,3 +66,29 @@ def test_module_surface_matches_reference():
     sd = {"weight": torch.zeros(6, 288), "u": torch.zeros(6, 9), "c": torch.zeros(9), "bias": torch.zeros(32)}
     conv.load_state_dict(sd)
     assert conv.lin.weight.shape == (288, 6)
+
+
+def test_data_container_lazy_attributes_and_csr_invalidation():
+    """geobi_gnn_b200.data.Data: the PyG container contract (None removes a key, optional keys read as None) plus the lazy
+    values PoolingLayer uses for the coarse edge_index / edge_weight, and the rule that re-assigning either drops `csr`."""
+    import torch
+    from geobi_gnn_b200.data import Data
+    calls = []
+    d = Data(x=torch.zeros(3, 2))
+    assert d.edge_index is None and "edge_index" not in d
+    d.set_lazy("edge_index", lambda: calls.append(1) or torch.ones(2, 4, dtype=torch.long))
+    d.csr = object()
+    assert "edge_index" in d and "<lazy>" in repr(d) and calls == []          # nothing evaluated yet
+    assert d.edge_index.shape == (2, 4) and calls == [1]
+    assert d.edge_index.shape == (2, 4) and calls == [1]                       # evaluated once
+    assert "csr" in d
+    d.edge_index = torch.zeros(2, 1, dtype=torch.long)                         # a new list invalidates the attached CSR
+    assert "csr" not in d
+    d.set_lazy("edge_weight", lambda: None)
+    assert d.edge_weight is None and "edge_weight" not in d                    # a thunk returning None removes the key
+    d.y = None
+    assert "y" not in d and d.y is None
+    c = d.clone()
+    assert torch.equal(c.edge_index, d.edge_index) and c.x is not d.x
+    with __import__("pytest").raises(AttributeError):
+        d.not_a_key
