@@ -281,8 +281,9 @@ def run_ours(args, rank, world, local_rank):
                            "priming": f"{PRIME_STEPS} untimed forwards before the {args.warmup} warm-up steps (caching-allocator high-water mark)"},
                 "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": round(ms_e2e / args.steps, 4),
-                        "path": "inference.HostBatchRunner: pinned host batch -> H2D on a copy stream (overlaps the previous batch's "
-                                "forward) -> DualGNN forward -> D2H of vertices and normals; one upload + one forward + one read-back per step"},
+                        "path": "inference.HostBatchRunner: pinned host batch -> H2D + input-level CSR build on a copy stream (under the "
+                                "previous batch's forward) -> DualGNN forward -> D2H of vertices and normals on a read-back stream; one "
+                                "upload + one forward + one read-back per step"},
                 "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
         print_json(line)
     if world > 1:

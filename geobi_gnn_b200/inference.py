@@ -99,8 +99,11 @@ class HostBatchRunner:
             vert_host, normal_host = runner.run(cur)   # valid after runner.wait() (the read-back runs on its own stream)
     """
 
-    def __init__(self, net, device="cuda", coalesced_undirected: bool = False):
+    def __init__(self, net, device="cuda", coalesced_undirected: bool = False, prebuild_graphs: bool = True):
         self.net, self.dev = net, torch.device(device)
+        # prebuild_graphs: the input-level CSRs (they depend on the edge lists only) are built on the copy stream right behind
+        # the upload, i.e. under the previous batch's forward; needs the coalesced_undirected promise (sort-free builder)
+        self.prebuild = prebuild_graphs and coalesced_undirected
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.read_stream = torch.cuda.Stream(self.dev)      # D2H of the outputs: its own stream (and copy engine)
         self.read_done = None
@@ -112,21 +115,32 @@ class HostBatchRunner:
         with torch.cuda.stream(self.copy_stream):
             dv = Data(**{k: t.to(self.dev, non_blocking=True) for k, t in host_v.items()})
             df = Data(**{k: t.to(self.dev, non_blocking=True) for k, t in host_f.items()})
+            if self.flag:
+                dv.coalesced_undirected = df.coalesced_undirected = True
+            if self.prebuild:
+                from . import nn as gnn
+                for d in (dv, df):
+                    gnn.input_graph(d, d.x.size(0))        # cached on the edge_index tensor; the forward picks it up
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        if self.flag:
-            dv.coalesced_undirected = df.coalesced_undirected = True
         return dv, df, ev
 
     def run(self, handle):
         dv, df, ev = handle
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(ev)
+        from . import nn as gnn
         for d in (dv, df):
             for k in d.keys:
                 t = getattr(d, k)
                 if torch.is_tensor(t):
                     t.record_stream(cur)       # allocated on the copy stream, consumed here
+            st = gnn.tag_of(d.edge_index).get("sorted")
+            if st is not None:                 # the prebuilt CSR and the stripped lists live on the copy stream's pool too
+                g = st[0]
+                for t in (g.rowptr, g._nbr, g._w, st[1], st[2]):
+                    if torch.is_tensor(t):
+                        t.record_stream(cur)
         with torch.no_grad():
             vert_p, norm_p, _ = self.net([dv, df])
         ready = torch.cuda.Event()

@@ -61,8 +61,9 @@ _ws_cache = {}
 
 
 def _ws(nbytes: int, device, slot: int = 0) -> torch.Tensor:
-    """Per-device scratch buffer, grown on demand (single-stream use)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    """Scratch buffer per (device, slot, current stream), grown on demand: ops queued on different streams never share one."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, slot, torch._C._cuda_getCurrentRawStream(idx))
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes * 1.25), 1 << 16), dtype=torch.uint8, device=device)
