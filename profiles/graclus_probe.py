@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from geobi_gnn_b200 import batching, dataset, ops
 dev = torch.device("cuda", 0); torch.cuda.set_device(dev)
-patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in bench.patch_meshes(bench.N_PATCHES, 0)]
+patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in bench.patch_meshes(int(os.environ.get("PATCHES", bench.N_PATCHES)), 0)]
 dv, df, _ = batching.collate_dual(patches)
 for name, d in (("facet", df), ("vertex", dv)):
     n = d.x.size(0)
