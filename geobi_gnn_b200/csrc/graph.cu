@@ -17,7 +17,7 @@ enum { ST_ERR = 0, ST_AUX = 1, ST_WORDS = 4 };
 
 // ------------------------------------------------------------------------------ scan
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 // exclusive scan of one int per thread over a 256-thread block; total -> *total (all threads)
