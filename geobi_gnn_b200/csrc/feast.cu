@@ -690,7 +690,7 @@ static void launch_packed(int out_mode, cudaStream_t st, const float* x, int64_t
 // version keeps only two rows per warp in flight (ncu: long-scoreboard stalls dominate, issue slots < 50 % busy).
 // SLOTS = edge slots per node per chunk (<= LPN).
 
-template <int NPW, int OUT, int SLOTS>
+template <int NPW, int OUT, int SLOTS, bool HAS_MAP>
 __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
                                                                  const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                                  const int* __restrict__ row_map,
@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
   auto load_first_j = [&](int64_t tile, int b_, int total_) -> int {
     int j_ = (int)node_of(tile < t_end ? tile : t_begin);
     if (tile < t_end && sl < SLOTS && sl > 0 && sl < total_) j_ = nbr[b_ + sl - 1];
-    return row_map ? row_map[j_] : j_;
+    return HAS_MAP ? row_map[j_] : j_;
   };
   if (t_begin >= t_end) return;
   int b_cur, total_cur, b_nxt, total_nxt, b_nx2 = 0, total_nx2 = 1;
@@ -756,7 +756,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
   int maxtotal = total;
 #pragma unroll
   for (int o = 16; o >= LPN; o >>= 1) maxtotal = max(maxtotal, __shfl_xor_sync(0xffffffffu, maxtotal, o));
-  const int i_src = row_map ? row_map[i] : (int)i;
+  const int i_src = HAS_MAP ? row_map[i] : (int)i;
   double Pi[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) Pi[h] = P[(int64_t)i_src * H + h];
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
     if (s0 == 0) j = j_cur;                         // first chunk: fetched one tile ago
     else if (sl < SLOTS && s < total) {
       j = nbr[b + s - 1];
-      if (row_map) j = row_map[j];
+      if (HAS_MAP) j = row_map[j];
     }
     // 1. launch every gather of the chunk: group g's lanes copy the LPN pieces of each of their node's rows
     for (int t = 0; t < cnt; ++t) {
@@ -870,24 +870,31 @@ __global__ void __launch_bounds__(256) feast_aggregate_ps_kernel(const float* __
   }   // tile loop
 }
 
-template <int NPW, int OUT, int SLOTS>
-static int launch_ps2(cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
+template <int NPW, int OUT, int SLOTS, bool HAS_MAP>
+static int launch_ps3(cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
                       const int32_t* row_map, const double* P, const float* c, void* Z, int64_t ldz) {
   constexpr int C = 128 / NPW;
   const size_t smem = (size_t)8 * NPW * SLOTS * (C + 12) * sizeof(float);
-  GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_aggregate_ps_kernel<NPW, OUT, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static int resident = 0;   // CTAs that fit on the device at once (per template instance)
   if (resident == 0) {
     int dev = 0, sms = 0, per_sm = 0;
     GEOBI_CUDA_OK(cudaGetDevice(&dev));
     GEOBI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GEOBI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, feast_aggregate_ps_kernel<NPW, OUT, SLOTS>, 256, smem));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_aggregate_ps_kernel<NPW, OUT, SLOTS, HAS_MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GEOBI_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, feast_aggregate_ps_kernel<NPW, OUT, SLOTS, HAS_MAP>, 256, smem));
     resident = sms * (per_sm > 0 ? per_sm : 1);
   }
   const int64_t want = cdiv(N, 8 * NPW);
   const unsigned grid = (unsigned)(want < resident ? want : resident);
-  feast_aggregate_ps_kernel<NPW, OUT, SLOTS><<<grid, 256, smem, st>>>(x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
+  feast_aggregate_ps_kernel<NPW, OUT, SLOTS, HAS_MAP><<<grid, 256, smem, st>>>(x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
   return GEOBI_OK;
+}
+// the row_map switch is a template parameter: a predicated-off row_map[j] still waits for the index load it would consume
+template <int NPW, int OUT, int SLOTS>
+static int launch_ps2(cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,
+                      const int32_t* row_map, const double* P, const float* c, void* Z, int64_t ldz) {
+  return row_map ? launch_ps3<NPW, OUT, SLOTS, true>(st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz)
+                 : launch_ps3<NPW, OUT, SLOTS, false>(st, x, ldx, N, rowptr, nbr, row_map, P, c, Z, ldz);
 }
 template <int NPW, int SLOTS>
 static int launch_ps(int out_mode, cudaStream_t st, const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr,

@@ -73,6 +73,9 @@ __device__ __forceinline__ unsigned long long now_ns() {
 #define TS(slot) do { } while (0)
 #endif
 
+// HAS_MAP: compile-time row_map switch - a predicated-off `row_map[j]` address computation still waits on the scoreboard of
+// the index load it would consume (5 % of the stall samples of the map-less instance before the split)
+template <bool HAS_MAP>
 __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const float* __restrict__ x, int64_t ldx, int64_t N,
                                                                        const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                                        const int* __restrict__ row_map,
@@ -237,7 +240,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   auto load_first_j = [&](int64_t tile, int b_, int total_) -> int {
     int j_ = (int)node_of(tile < t_end ? tile : t_begin);
     if (tile < t_end && sl > 0 && sl < total_) j_ = nbr[b_ + sl - 1];
-    return row_map ? row_map[j_] : j_;
+    return HAS_MAP ? row_map[j_] : j_;
   };
   int b_cur, total_cur, b_nxt, total_nxt, b_nx2 = 0, total_nx2 = 1;
   load_rowptr(t_begin, b_cur, total_cur);
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     j_nxt = load_first_j(tile + 1, b_nxt, total_nxt);
     load_rowptr(tile + 2, b_nx2, total_nx2);
     const int maxtotal = max(total, __shfl_xor_sync(0xffffffffu, total, 16));
-    const int i_src = row_map ? row_map[i] : (int)i;
+    const int i_src = HAS_MAP ? row_map[i] : (int)i;
     const float rcnt = live ? 1.0f / (float)total : 0.f;   // mean over N(i)+{i}, folded into q; dead rows become zeros
     // accumulators: acc[h][0] = channels (c0, c0+1), acc[h][1] = (c0+2, c0+3) of head h, as packed fp32 pairs (FFMA2)
     unsigned long long acc[H][2];
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       if (s0 == 0) j = j_cur;                      // first chunk: prefetched one tile ago
       else if (s < total) {
         j = nbr[b + s - 1];
-        if (row_map) j = row_map[j];
+        if (HAS_MAP) j = row_map[j];
       }
       const int cnt = min(LPN, maxtotal - s0);
 #ifdef EXP_NOGATHER
@@ -504,12 +507,17 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
     int dev = 0;
     GEOBI_CUDA_OK(cudaGetDevice(&dev));
     GEOBI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GEOBI_CUDA_OK(cudaFuncSetAttribute(fused::feast_fused_64_32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(fused::feast_fused_64_32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(fused::feast_fused_64_32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
   }
   const int64_t n_tiles = (N + fused::NT - 1) / fused::NT;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  fused::feast_fused_64_32_kernel<<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wq, bias, act_slope,
-                                                                                   out, ldo);
+  if (row_map)
+    fused::feast_fused_64_32_kernel<true><<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wq, bias,
+                                                                                           act_slope, out, ldo);
+  else
+    fused::feast_fused_64_32_kernel<false><<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wq, bias,
+                                                                                            act_slope, out, ldo);
   GEOBI_LAUNCH_OK("feast_fused");
   return GEOBI_OK;
 }
