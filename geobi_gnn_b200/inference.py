@@ -107,14 +107,36 @@ class HostBatchRunner:
         self.copy_stream = torch.cuda.Stream(self.dev)
         self.read_stream = torch.cuda.Stream(self.dev)      # D2H of the outputs: its own stream (and copy engine)
         self.read_done = None
+        self._slots = [{}, {}, {}]            # device landing buffers, used round-robin (a batch may be uploaded two ahead)
+        self._slot_free = [None, None, None]  # event: the forward that consumed the slot has been queued and finished
+        self._next_slot = 0
         self.flag = coalesced_undirected      # the host lists come from dataset.py's builders (see nn.input_graph)
         self.out_host = {}
 
+    def _slot_tensors(self, slot, which, host):
+        """Device-side landing buffers of one pipeline slot (allocated once per shape: no allocator traffic per batch)."""
+        bufs = self._slots[slot].setdefault(which, {})
+        out = {}
+        for k, t in host.items():
+            b = bufs.get(k)
+            if b is None or b.shape != t.shape or b.dtype != t.dtype:
+                b = bufs[k] = torch.empty(t.shape, dtype=t.dtype, device=self.dev)
+            out[k] = b
+        return out
+
     def upload(self, host_v: dict, host_f: dict):
         from .data import Data
+        slot = self._next_slot
+        self._next_slot = (slot + 1) % len(self._slots)
         with torch.cuda.stream(self.copy_stream):
-            dv = Data(**{k: t.to(self.dev, non_blocking=True) for k, t in host_v.items()})
-            df = Data(**{k: t.to(self.dev, non_blocking=True) for k, t in host_f.items()})
+            freed = self._slot_free[slot]
+            if freed is not None:
+                self.copy_stream.wait_event(freed)     # the forward that read this slot's buffers has finished
+            dv_t, df_t = self._slot_tensors(slot, "v", host_v), self._slot_tensors(slot, "f", host_f)
+            for dst, src in ((dv_t, host_v), (df_t, host_f)):
+                for k, t in src.items():
+                    dst[k].copy_(t, non_blocking=True)
+            dv, df = Data(**{k: t.view_as(t) for k, t in dv_t.items()}), Data(**{k: t.view_as(t) for k, t in df_t.items()})
             if self.flag:
                 dv.coalesced_undirected = df.coalesced_undirected = True
             if self.prebuild:
@@ -123,10 +145,10 @@ class HostBatchRunner:
                     gnn.input_graph(d, d.x.size(0))        # cached on the edge_index tensor; the forward picks it up
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
-        return dv, df, ev
+        return dv, df, ev, slot
 
     def run(self, handle):
-        dv, df, ev = handle
+        dv, df, ev, slot = handle
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(ev)
         from . import nn as gnn
@@ -145,6 +167,7 @@ class HostBatchRunner:
             vert_p, norm_p, _ = self.net([dv, df])
         ready = torch.cuda.Event()
         ready.record(cur)
+        self._slot_free[slot] = ready
         if self.read_done is not None:
             self.read_done.synchronize()       # the previous batch's host buffers are about to be overwritten
         with torch.cuda.stream(self.read_stream):
