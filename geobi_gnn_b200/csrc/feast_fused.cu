@@ -23,6 +23,9 @@ using namespace tc;
 #define PREFETCH_MODE 3   // 3: P rows of the next tile into L1 at the end of a tile (A/B: -2 %); x-row prefetches (1, 2) lost
 #endif
 constexpr int C_IN = 64, C_OUT = 32;
+#ifndef PAIR_SETS
+#define PAIR_SETS 2   // 3 = gathers issued two pair-consumptions ahead: no gain (0.526 vs 0.527 ms; 96 registers, spills)
+#endif
 #ifndef FUSED_WARPS
 #define FUSED_WARPS 16
 #endif
@@ -288,6 +291,12 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       const unsigned o1 = __shfl_sync(0xffffffffu, joff, 1, LPN);
       ulonglong2 xa = __ldg(reinterpret_cast<const ulonglong2*>(xl + o0));
       ulonglong2 xb = __ldg(reinterpret_cast<const ulonglong2*>(xl + o1));
+#if PAIR_SETS == 3
+      const unsigned o2 = __shfl_sync(0xffffffffu, joff, 2, LPN);   // slots past the row's end hold the node's own (valid) row
+      const unsigned o3 = __shfl_sync(0xffffffffu, joff, 3, LPN);
+      ulonglong2 xc = __ldg(reinterpret_cast<const ulonglong2*>(xl + o2));
+      ulonglong2 xd = __ldg(reinterpret_cast<const ulonglong2*>(xl + o3));
+#endif
 #if PREFETCH_MODE == 1
       if (sl >= 2 && s < total) {
         prefetch_l1(x + joff);
@@ -371,6 +380,34 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
           acc[h][1] = ffma2(vb.y, qq, acc[h][1]);
         }
       };
+#if PAIR_SETS == 3
+      // software pipeline over pairs of rows with THREE register sets: a pair's gathers are issued two pair-consumptions
+      // (~160 issue slots) before it is needed - with two sets an L1 miss (11 % of the rows) stalled the warp on L2
+      ulonglong2 xe = xa, xf = xb;
+#pragma unroll 1
+      for (int t = 0; t < cnt; t += 6) {
+        if (t + 4 < cnt) {
+          const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 4);
+          xe = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.x));
+          xf = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.y));
+        }
+        consume(xa, xb, t);
+        if (t + 2 >= cnt) break;
+        if (t + 6 < cnt) {
+          const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 6);
+          xa = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.x));
+          xb = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.y));
+        }
+        consume(xc, xd, t + 2);
+        if (t + 4 >= cnt) break;
+        if (t + 8 < cnt) {
+          const uint2 o = *reinterpret_cast<const uint2*>(jbase + t + 8);
+          xc = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.x));
+          xd = __ldg(reinterpret_cast<const ulonglong2*>(xl + o.y));
+        }
+        consume(xe, xf, t + 4);
+      }
+#else
       // software pipeline over pairs of rows with two register sets: the next pair's gathers are issued before the
       // current pair is consumed
       ulonglong2 xc = xa, xd = xb;
@@ -392,6 +429,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
           consume(xc, xd, t + 2);
         }
       }
+#endif
       __syncwarp();
     }
     b_cur = b_nxt; total_cur = total_nxt; j_cur = j_nxt;
