@@ -257,8 +257,8 @@ def run_ours(args, rank, world, local_rank):
         peak, how = peaks()
         achieved = alg / (t_ms / 1e3) / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this layer from the committed ncu --set full capture
-        # (profiles/r01_ncu_full_feast_fused_v2.csv): 226.1 MB + 50.8 MB
-        traffic = 276_911_360 if fused else None
+        # (profiles/r01_ncu_full_feast_fused_v2.csv): 226.1 MB + 51.7 MB
+        traffic = 277_800_960 if fused else None
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic,
                 "kernel": ("feast_fused_64_32_kernel" if fused else "geobi_feast_fwd (project + aggregate + gemm)") +
@@ -267,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
                 "l2": "flushed (256 MB write) between launches", "traffic_source": "ncu --set full, profiles/r01_ncu_full_feast_fused_v2.csv",
                 "note": "HBM is the nominal bound of a gather/segment-sum; this kernel's 9-head weighting costs 576 fp32 FMAs per gathered 256-byte "
                         "row, so at 100 % of the FP32 pipe (FFMA2 = 2 clk, profiles/micro/ffma2_bench.cu) it could reach ~0.3 of the HBM peak; "
-                        "ncu: fmaheavy pipe 46 % active, issue slots 54 %, DRAM traffic 1.23x the algorithmic bytes"}
+                        "ncu: fmaheavy pipe 47 % active, issue slots 55 %, DRAM traffic 1.23x the algorithmic bytes"}
 
     cpu = cpu_baseline(sample_seconds=12.0) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
