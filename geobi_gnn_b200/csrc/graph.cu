@@ -676,6 +676,10 @@ extern "C" int geobi_graclus(const int32_t* rowptr, const int32_t* nbr, const fl
   }
   int64_t nb = cdiv(n_nodes, 256);
   if (nb > coresident) nb = coresident;
+  if (const char* cap = getenv("GEOBI_GRACLUS_MAX_BLOCKS")) {   // test hook: forces many nodes per thread (register + memory wait state)
+    const int64_t c = atoll(cap);
+    if (c >= 1 && c < nb) nb = c;
+  }
   int n_all = (int)n_nodes;
   void* args[] = {(void*)&rowptr, (void*)&nbr, (void*)&w, (void*)&state, (void*)&label, (void*)&n_all, (void*)&pos, (void*)&undecided};
   // cooperative launch = the runtime refuses the launch unless all blocks are co-resident (no grid barrier is used)

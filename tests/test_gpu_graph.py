@@ -112,6 +112,35 @@ def test_graclus_equals_serial_greedy(n, weighted):
         assert torch.equal(cluster.cpu().long(), want_c) and nc == int(want_c.max()) + 1
 
 
+@pytest.mark.parametrize("max_blocks", [1, 2, 5])
+def test_graclus_many_nodes_per_thread_equals_serial_greedy(max_blocks):
+    """The matcher keeps two nodes per thread in registers and any further ones in memory; production graphs only reach the
+    second path beyond ~600 k nodes per GPU, so the grid is capped here (GEOBI_GRACLUS_MAX_BLOCKS) to run both on a small
+    graph: 16 000 facets on 256 / 512 / 1280 threads = up to 63 nodes per thread.  Also a random graph with hubs."""
+    import os
+    ops = _ops()
+    (dv, df), _, _ = util.oracle_inputs(20)
+    cases = [(df.edge_index, df.edge_weight, df.x.shape[0])]
+    torch.manual_seed(17)
+    n = 5000
+    src, dst = torch.randint(0, n, (30000,)), torch.randint(0, n, (30000,))
+    hub = torch.zeros(600, dtype=torch.long)
+    ei = torch.stack([torch.cat([src, hub]), torch.cat([dst, torch.randint(1, n, (600,))])])
+    ei = pyg.to_undirected(ei[:, ei[0] != ei[1]], n)
+    cases.append((ei, torch.rand(ei.size(1)), n))
+    os.environ["GEOBI_GRACLUS_MAX_BLOCKS"] = str(max_blocks)
+    try:
+        for ei, w, N in cases:
+            perm = torch.randperm(N, generator=torch.Generator().manual_seed(N))
+            ei2, w2 = pyg.remove_self_loops(ei, w)
+            want = pyg.graclus(ei2, w2, N, perm=perm)
+            g = ops.csr_from_coo(ei2.to(DEV), N, w2.to(DEV), 0)
+            got, und = ops.graclus(g, perm.to(DEV), check=True)
+            assert und == 0 and torch.equal(got.cpu().long(), want)
+    finally:
+        del os.environ["GEOBI_GRACLUS_MAX_BLOCKS"]
+
+
 def test_graclus_ties_and_isolated_nodes():
     ops = _ops()
     # path 0-1-2-3 with equal weights + isolated node 4: `>=` makes the LATER neighbour win
