@@ -114,3 +114,35 @@ def test_dualgnn_forward_bf16x3_matches_oracle():
     for gname in ("v", "f"):
         for k in ("l1", "l2", "l3", "l4", "r1", "r2", "r3", "r4"):
             assert util.rel_err(mine.taps[gname][k], ref.taps[gname][k]) < 5e-5, (gname, k)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("cin,cout", [(6, 32), (12, 32), (32, 64), (64, 32), (128, 64)])
+def test_feast_conv_high_degree_rows_all_kernels(cin, cout, prec):
+    """Mesh rows fit one chunk of edge slots; rows of degree 17..120 run the multi-chunk paths of every aggregation kernel
+    (first-layer quad kernel, packed cp.async kernels, fused 64->32 kernel), with and without the fused unpooling map."""
+    from geobi_gnn_b200 import ops
+    torch.manual_seed(cin * 7 + cout)
+    n = 3000
+    src, dst = torch.randint(0, n, (24000,)), torch.randint(0, n, (24000,))
+    hubs = torch.cat([torch.full((120,), 0), torch.full((40,), 1), torch.full((17,), 2)])
+    ei = torch.stack([torch.cat([src, hubs]), torch.cat([dst, torch.randint(3, n, (177,))])])
+    ei = pyg.to_undirected(ei[:, ei[0] != ei[1]], n)
+    conv = pyg.FeaStConv(cin, cout, 9)
+    P = [t.data.to(DEV) for t in (conv.lin.weight, conv.u.weight, conv.c, conv.bias)]
+    code = ops.PREC_FP32 if prec == "fp32" else ops.PREC_BF16X3
+    g = ops.csr_from_coo(ei.to(DEV), n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+    assert int((g.rowptr[1:] - g.rowptr[:-1]).max()) >= 120
+    x = torch.randn(n, cin) * 2.0
+    with torch.no_grad():
+        want = torch.nn.functional.leaky_relu(conv(x, ei), 0.2)
+    got = ops.feast_fwd(x.to(DEV), g, *P, act_slope=0.2, precision=code)
+    assert util.rel_err(got, want) < util.TOL_FP32
+    if cin in (64, 128):
+        nc = n // 3
+        xc = torch.randn(nc, cin) * 2.0
+        idx = torch.randint(0, nc, (n,))
+        with torch.no_grad():
+            want_m = conv(xc[idx], ei)
+        got_m = ops.feast_fwd(xc.to(DEV), g, *P, precision=code, row_map=idx.to(DEV).int())
+        assert util.rel_err(got_m, want_m) < util.TOL_FP32
