@@ -92,3 +92,34 @@ def test_data_container_lazy_attributes_and_csr_invalidation():
     assert torch.equal(c.edge_index, d.edge_index) and c.x is not d.x
     with __import__("pytest").raises(AttributeError):
         d.not_a_key
+
+
+def test_collate_keeps_the_coalesced_flag_and_size_buckets_are_stable():
+    """Host-side logic that needs no GPU: the disjoint-union batch keeps `coalesced_undirected` only if every patch has it,
+    fresh_view carries it along, and the capacity buckets of ops.valloc depend on the level's reference size only."""
+    import torch
+    from geobi_gnn_b200 import batching, ops
+    from geobi_gnn_b200.data import Data
+
+    def patch(n, flag):
+        ei = torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]])
+        dv = Data(x=torch.zeros(n, 6), edge_index=ei, edge_weight=torch.ones(4))
+        df = Data(x=torch.zeros(n, 6), edge_index=ei, edge_weight=torch.ones(4), fv_indices=torch.zeros(n, 3, dtype=torch.long))
+        if flag:
+            dv.coalesced_undirected = df.coalesced_undirected = True
+        return dv, df
+
+    dv, df, sl = batching.collate_dual([patch(3, True), patch(4, True)])
+    assert dv.coalesced_undirected and df.coalesced_undirected
+    assert dv.edge_index.tolist() == [[0, 1, 1, 2, 3, 4, 4, 5], [1, 0, 2, 1, 4, 3, 5, 4]]      # offsets keep the list sorted
+    assert sl["v"] == [(0, 3), (3, 7)] and df.fv_indices.shape == (7, 3)
+    assert batching.fresh_view(dv).coalesced_undirected and batching.fresh_view(dv).edge_index is not dv.edge_index
+    dv2, df2, _ = batching.collate_dual([patch(3, True), patch(4, False)])
+    assert "coalesced_undirected" not in dv2 and "coalesced_undirected" not in df2
+    assert batching.shard(list(range(7)), 1, 3) == [1, 4]
+    # capacity buckets: sizes that differ by a few percent from one forward to the next land in the same bucket
+    assert ops._cap(1000, 4096) == ops._cap(1010, 4096) == 1024
+    assert ops._cap(5000, 4096) == 5000 and ops._cap(0, 4096) == 256 and ops._cap(7, None) == 7
+    with ops.size_ref(4096):
+        t = ops.valloc(1000, (3,), torch.float32, torch.device("cpu"))
+    assert t.shape == (1000, 3) and t.untyped_storage().nbytes() == 1024 * 3 * 4
