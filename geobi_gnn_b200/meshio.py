@@ -1,0 +1,54 @@
+"""Wavefront .obj in / out - the two calls the reference makes through OpenMesh around the hot path:
+`om.read_trimesh(path)` (dataset.py:134-135, 296-300; test_dual.py reads the noisy mesh) and `om.write_mesh(path, mesh)`
+(test_dual.py:73 writes the denoised mesh).  Only what those calls use: vertex positions and faces; polygons are fan-
+triangulated as OpenMesh's TriMesh reader does, texture / normal indices (`f v/vt/vn`) and negative (relative) indices are
+accepted, everything else (`vn`, `vt`, groups, materials) is skipped.  Host-side numpy; the arrays feed synth.TriMesh /
+topology.DeviceTriMesh.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def read_obj(path):
+    """-> (points float64 [V,3], faces int64 [F,3])."""
+    pts, faces = [], []
+    with open(path, "r") as f:
+        for line in f:
+            if line.startswith("v "):
+                p = line.split()
+                pts.append((float(p[1]), float(p[2]), float(p[3])))
+            elif line.startswith("f "):
+                idx = []
+                for tok in line.split()[1:]:
+                    i = int(tok.split("/")[0])
+                    idx.append(i - 1 if i > 0 else len(pts) + i)
+                for k in range(1, len(idx) - 1):              # fan triangulation
+                    faces.append((idx[0], idx[k], idx[k + 1]))
+    points = np.asarray(pts, dtype=np.float64).reshape(-1, 3)
+    fv = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+    if fv.size and (fv.min() < 0 or fv.max() >= points.shape[0]):
+        raise ValueError(f"{path}: face index out of range")
+    return points, fv
+
+
+def write_obj(path, points, faces):
+    """Positions with 6 significant decimals (OpenMesh's default stream precision), 1-based faces."""
+    p = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    fv = np.asarray(faces, dtype=np.int64).reshape(-1, 3) + 1
+    with open(path, "w") as f:
+        f.write(f"# {p.shape[0]} vertices, {fv.shape[0]} faces\n")
+        f.write("".join(f"v {a:.6g} {b:.6g} {c:.6g}\n" for a, b, c in p))
+        f.write("".join(f"f {a} {b} {c}\n" for a, b, c in fv))
+
+
+def denoise_obj(net, path_in, path_out, sub_size: int = 20000, data_type: str = "Synthetic", device="cuda", n_iter: int = 60):
+    """test_dual.predict_one for one file: read -> predict_mesh (patch split, forward, stitch, 60-sweep vertex update) -> write.
+    Returns (updated vertices [V,3], facet normals [F,3]) as numpy."""
+    from . import inference, synth
+    points, fv = read_obj(path_in)
+    mesh = synth.TriMesh(points, fv)
+    V, Np, _ = inference.predict_mesh(net, mesh, sub_size, data_type=data_type, device=device, n_iter=n_iter)
+    V = V.detach().cpu().numpy()
+    write_obj(path_out, V, fv)
+    return V, Np.detach().cpu().numpy()

@@ -123,3 +123,26 @@ def test_collate_keeps_the_coalesced_flag_and_size_buckets_are_stable():
     with ops.size_ref(4096):
         t = ops.valloc(1000, (3,), torch.float32, torch.device("cpu"))
     assert t.shape == (1000, 3) and t.untyped_storage().nbytes() == 1024 * 3 * 4
+
+
+def test_obj_round_trip(tmp_path):
+    """meshio: what om.read_trimesh / om.write_mesh do for the path - positions, faces, fan triangulation,
+    `v/vt/vn` tokens and negative indices."""
+    import numpy as np
+    from geobi_gnn_b200 import meshio, synth
+    p, f = synth.icosphere(2)
+    path = tmp_path / "ico.obj"
+    meshio.write_obj(path, p, f)
+    p2, f2 = meshio.read_obj(path)
+    assert np.array_equal(f2, f) and np.abs(p2 - p).max() < 1e-6
+    m = synth.TriMesh(p2, f2)
+    assert m.n_faces == 80 and m.n_vertices == 42
+    quad = tmp_path / "quad.obj"
+    quad.write_text("# a quad and a triangle\nvn 0 0 1\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 2 0 0\nvt 0 0\n"
+                    "f 1/1/1 2/1/1 3/1/1 4/1/1\nf -4 -1 -3\n")
+    pq, fq = meshio.read_obj(quad)
+    assert pq.shape == (5, 3) and fq.tolist() == [[0, 1, 2], [0, 2, 3], [1, 4, 2]]
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nf 1 2 3\n")
+    with __import__("pytest").raises(ValueError):
+        meshio.read_obj(bad)

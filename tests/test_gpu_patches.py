@@ -63,3 +63,27 @@ def test_patched_inference_matches_oracle_pipeline():
     V1, N1, _ = inference.predict_mesh(mine, mesh, 10 ** 9, device=DEV)
     assert V1.shape == (mesh.n_vertices, 3) and torch.isfinite(V1).all()
     assert util.rel_err(N1.norm(dim=1), torch.ones(mesh.n_faces)) < 1e-5
+
+
+@pytest.mark.gpu
+def test_denoise_obj_file_to_file(tmp_path):
+    """meshio.denoise_obj = read .obj -> predict_mesh -> write .obj (test_dual.py:25-87 for one file)."""
+    import numpy as np
+    import torch
+    from geobi_gnn_b200 import inference, meshio, network, synth
+    from tests import util
+    torch.manual_seed(9)
+    net = network.DualGNN().to("cuda").eval()
+    for pl in util.poolings(net):
+        pl.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
+    p, f = synth.icosphere(5)
+    pn = synth.add_normal_noise(p, f, 0.2, seed=3)
+    src, dst = tmp_path / "noisy.obj", tmp_path / "out.obj"
+    meshio.write_obj(src, pn, f)
+    V, Np = meshio.denoise_obj(net, src, dst, sub_size=300, device="cuda")
+    p_in, f_in = meshio.read_obj(src)
+    want = inference.predict_mesh(net, synth.TriMesh(p_in, f_in), 300, device="cuda")
+    assert np.abs(V - want[0].cpu().numpy()).max() < 1e-4 * max(1.0, np.abs(V).max())
+    p_out, f_out = meshio.read_obj(dst)
+    assert np.array_equal(f_out, f) and np.abs(p_out - V).max() < 1e-5 * max(1.0, np.abs(V).max())
+    assert abs(np.linalg.norm(Np, axis=1) - 1).max() < 1e-5
