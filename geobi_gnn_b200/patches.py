@@ -73,15 +73,20 @@ def split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=
     taken = np.zeros(fv.shape[0], dtype=np.uint8)
     seed = int(np.argmax(d2))
     patches = []
+    # upstream rescans `np.where(~flag)` and `d2[left]` after every patch (dataset.py:188-192): O(F) index arrays per patch.
+    # Same seeds from a masked copy of d2: covered faces drop to -inf, the next seed is the first arg-max of what is left.
+    d2_left = d2.astype(np.float32, copy=True)
+    n_left = fv.shape[0]
     while True:
         sel = mesh_get_neighbor_np(fv, vf, seed, neighbor_count=submesh_size, _taken=taken)
+        n_left -= int(np.count_nonzero(~flag[sel]))
         flag[sel] = True
+        d2_left[sel] = -np.inf
         if len(sel) > filter_patch_count:
             patches.append((sel, seed))
-        left = np.where(~flag)[0]
-        if left.size == 0:
+        if n_left == 0:
             break
-        seed = int(left[np.argmax(d2[left])])
+        seed = int(np.argmax(d2_left))
     return patches
 
 
