@@ -25,7 +25,13 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     # device_topology: per-patch index arrays and normals come from topology.DeviceTriMesh (GPU) instead of the numpy
     # stand-in for OpenMesh (synth.TriMesh, ~1.2 s per million faces on the host)
     make_sub = (lambda pts, fcs: topology.DeviceTriMesh(pts, fcs, dev)) if device_topology else synth.TriMesh
-    points_noisy = np.asarray(mesh.points, dtype=np.float32)
+    # `mesh` may be a host object (numpy index arrays, e.g. synth.TriMesh / OpenMesh) or a topology.DeviceTriMesh built on the
+    # GPU from points + faces: the host parts of the pipeline (BFS patch splitter, normalisation) get numpy views of it
+    def _np(a):
+        return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+
+    mesh_points, mesh_fv, mesh_vf, mesh_ev = _np(mesh.points), _np(mesh.fv), _np(mesh.vf), _np(mesh.ev)
+    points_noisy = np.asarray(mesh_points, dtype=np.float32)
     poolings = [net.gnn_v.pooling1, net.gnn_v.pooling2, net.gnn_f.pooling1, net.gnn_f.pooling2]
 
     def run(dual, k):
@@ -39,13 +45,13 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     centroid = scale = None
     if mesh.n_faces <= sub_size:                                   # test_dual.py:44-47
         dual = dataset.process_one_submesh(mesh, "mesh", None, dev)
-        dataset.attach_normalisation(dual, points_noisy, mesh.ev)
+        dataset.attach_normalisation(dual, points_noisy, mesh_ev)
         centroid, scale = dual[0].centroid, dual[0].scale
         dual = dataset.post_processing(dual, data_type)
         Vp, Np = run(dual, 0) if rank == 0 else (None, None)
         n_patches = 1
     else:                                                          # test_dual.py:49-61
-        parts = patches.split_mesh(points_noisy, mesh.fv, mesh.vf, sub_size)
+        parts = patches.split_mesh(points_noisy, mesh_fv, mesh_vf, sub_size)
         n_patches = len(parts)
         st = patches.Stitcher(mesh.n_vertices, mesh.n_faces, dev)
         slot = np.full(mesh.n_vertices, -1, dtype=np.int64)
@@ -53,10 +59,10 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         for k, (sel, seed) in enumerate(parts):
             if k % world != rank:
                 continue
-            v_idx, faces = patches.get_submesh(mesh.fv, sel, _slot=slot)
-            sub = make_sub(mesh.points[v_idx], faces)
+            v_idx, faces = patches.get_submesh(mesh_fv, sel, _slot=slot)
+            sub = make_sub(mesh_points[v_idx], faces)
             dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev)
-            dataset.attach_normalisation(dual, points_noisy, mesh.ev, precomputed=norm)   # dataset.py:140,179-180
+            dataset.attach_normalisation(dual, points_noisy, mesh_ev, precomputed=norm)   # dataset.py:140,179-180
             centroid, scale = dual[0].centroid, dual[0].scale
             norm = (centroid, scale)
             dual = dataset.post_processing(dual, data_type)
@@ -69,7 +75,7 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         if centroid is None:                                        # a rank that received no patch
             centroid = torch.from_numpy(points_noisy.mean(0, keepdims=True)).to(dev)
             q = points_noisy - points_noisy.mean(0, keepdims=True)
-            e = q[mesh.ev]
+            e = q[mesh_ev]
             scale = float(1 / (((e[:, 0] - e[:, 1]) ** 2).sum(1) ** 0.5).mean())
         Vp, Np = st.finish()
     if forced is not None:
@@ -78,8 +84,8 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     if rank != 0:
         return None, None, None
     Vp = Vp / scale + centroid                                      # test_dual.py:63
-    fv = torch.from_numpy(np.ascontiguousarray(mesh.fv)).to(dev)
-    vf = torch.from_numpy(np.ascontiguousarray(mesh.vf)).to(dev)
+    fv = torch.as_tensor(mesh.fv, device=dev) if torch.is_tensor(mesh.fv) else torch.from_numpy(np.ascontiguousarray(mesh_fv)).to(dev)
+    vf = torch.as_tensor(mesh.vf, device=dev) if torch.is_tensor(mesh.vf) else torch.from_numpy(np.ascontiguousarray(mesh_vf)).to(dev)
     depth = None
     if data_type in ("Kinect_v1", "Kinect_v2"):
         depth = torch.nn.functional.normalize(torch.from_numpy(points_noisy).to(dev), dim=1)

@@ -60,3 +60,23 @@ def test_predict_mesh_device_topology_equals_host_topology():
     assert util.rel_err(out_d[2], out_h[2]) < 5e-5                             # network vertices
     assert float((out_d[1] - out_h[1]).abs().max()) < 5e-4                     # unit normals
     assert util.rel_err(out_d[0], out_h[0]) < 5e-5                             # updated vertices
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sub_size", [500, 100000])
+def test_predict_mesh_accepts_device_built_whole_mesh(sub_size):
+    """The WHOLE mesh handed over as a DeviceTriMesh (what meshio.denoise_obj does on a GPU) gives the result of the host
+    TriMesh: same patches, same stitched vertices; sub_size 100000 exercises the single-graph branch (test_dual.py:44-47)."""
+    from geobi_gnn_b200 import inference, network, synth, topology
+    torch.manual_seed(4)
+    net = network.DualGNN().to(DEV).eval()
+    for pl in util.poolings(net):
+        pl.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
+    p, f = synth.icosphere(8)
+    pn = synth.add_normal_noise(p, f, 0.2, seed=5)
+    out_h = inference.predict_mesh(net, synth.TriMesh(pn, f), sub_size, device=DEV, return_parts=True)
+    out_d = inference.predict_mesh(net, topology.DeviceTriMesh(pn, f, DEV), sub_size, device=DEV, return_parts=True)
+    assert out_h[3] == out_d[3] and (out_d[3] > 1) == (sub_size == 500)
+    assert util.rel_err(out_d[2], out_h[2]) < 5e-5
+    assert float((out_d[1] - out_h[1]).abs().max()) < 5e-4
+    assert util.rel_err(out_d[0], out_h[0]) < 5e-5
