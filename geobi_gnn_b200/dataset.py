@@ -52,17 +52,30 @@ def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda"):
     return graph_v, graph_f
 
 
+def normalisation(points_noisy, ev):
+    """(centroid [1,3] fp32, scale) of dataset.py:140,151-152: `q = p - centroid; e = q[ev]; 1 / |e0 - e1|.mean()`.  The per-edge
+    lengths come from one threaded C++ pass with numpy's fp32 operation order (bit-equal, tests/test_abi.py) and numpy takes
+    the mean, so the numbers are upstream's; the [E,2,3] temporaries of a 10 M-face mesh are not built."""
+    import ctypes as C
+    import os
+    from . import patches
+    host = lambda a: a.detach().cpu().numpy() if torch.is_tensor(a) else a      # a DeviceTriMesh hands over device tensors
+    p = np.ascontiguousarray(host(points_noisy), dtype=np.float32)
+    ev = np.ascontiguousarray(host(ev), dtype=np.int64)
+    centroid = np.ascontiguousarray(p.mean(0, keepdims=True))
+    length = np.empty(ev.shape[0], dtype=np.float32)
+    patches._host().geobi_host_edge_lengths(patches._p(p), patches._p(centroid), patches._p(ev), C.c_int64(ev.shape[0]), patches._p(length),
+                                            C.c_int(min(8, os.cpu_count() or 1)))
+    return centroid, 1 / length.mean()
+
+
 def attach_normalisation(dual_data, points_noisy, ev, precomputed=None):
     """dataset.py:140,151-152: centroid / scale of the whole noisy mesh (numpy fp32, as upstream).
     `precomputed` = (centroid tensor, scale) lets a caller that normalises many patches of one mesh pay for it once."""
     if precomputed is not None:
         dual_data[0].centroid, dual_data[0].scale = precomputed
         return dual_data
-    p = np.asarray(points_noisy, dtype=np.float32)
-    centroid = p.mean(0, keepdims=True)
-    q = p - centroid
-    e = q[ev]
-    scale = 1 / (((e[:, 0] - e[:, 1]) ** 2).sum(1) ** 0.5).mean()
+    centroid, scale = normalisation(points_noisy, ev)
     dual_data[0].centroid = torch.from_numpy(centroid).float().to(dual_data[0].pos.device)
     dual_data[0].scale = float(scale)
     return dual_data

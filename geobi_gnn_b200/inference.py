@@ -17,11 +17,22 @@ from . import batching, data_util, dataset, patches, synth
 
 
 def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device="cuda", n_iter: int = 60, rank: int = 0, world: int = 1,
-                 forced: Optional[List] = None, return_parts: bool = False, device_topology: bool = True):
+                 forced: Optional[List] = None, return_parts: bool = False, device_topology: bool = True,
+                 timings: Optional[dict] = None):
     """Returns (V [Nv,3] updated vertices, Np [Nf,3] unit facet normals, Vp [Nv,3] network vertices) on `device`
     (meaningful on rank 0 when world > 1).  `forced`: per patch, the 4 pooling layers' raw label lists (tests)."""
     dev = torch.device(device)
     from . import topology
+    import time
+    t_last = [time.perf_counter()]
+
+    def lap(name):                      # wall-clock phases for profiles/config4_probe.py; syncs only when asked to time
+        if timings is not None:
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
     # device_topology: per-patch index arrays and normals come from topology.DeviceTriMesh (GPU) instead of the numpy
     # stand-in for OpenMesh (synth.TriMesh, ~1.2 s per million faces on the host)
     make_sub = (lambda pts, fcs: topology.DeviceTriMesh(pts, fcs, dev)) if device_topology else synth.TriMesh
@@ -51,16 +62,28 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         Vp, Np = run(dual, 0) if rank == 0 else (None, None)
         n_patches = 1
     else:                                                          # test_dual.py:49-61
+        lap("host_views")
         parts = patches.split_mesh(points_noisy, mesh_fv, mesh_vf, sub_size)
+        lap("split_mesh")
         n_patches = len(parts)
         st = patches.Stitcher(mesh.n_vertices, mesh.n_faces, dev)
         slot = np.full(mesh.n_vertices, -1, dtype=np.int64)
         norm = None                                                 # (centroid, scale) of the WHOLE mesh, computed once
-        for k, (sel, seed) in enumerate(parts):
-            if k % world != rank:
-                continue
-            v_idx, faces = patches.get_submesh(mesh_fv, sel, _slot=slot)
-            sub = make_sub(mesh_points[v_idx], faces)
+        mine = [k for k in range(n_patches) if k % world == rank]
+
+        def cut(k):                                                 # host side of one patch (C++ re-indexing + a gather)
+            v_idx, faces = patches.get_submesh(mesh_fv, parts[k][0], _slot=slot)
+            return v_idx, faces, mesh_points[v_idx]
+
+        # one helper thread cuts patch k+1 out of the mesh while the GPU works on patch k (both calls release the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1)
+        nxt = pool.submit(cut, mine[0]) if mine else None
+        for i, k in enumerate(mine):
+            sel, seed = parts[k]
+            v_idx, faces, pts_k = nxt.result()
+            nxt = pool.submit(cut, mine[i + 1]) if i + 1 < len(mine) else None
+            sub = make_sub(pts_k, faces)
             dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev)
             dataset.attach_normalisation(dual, points_noisy, mesh_ev, precomputed=norm)   # dataset.py:140,179-180
             centroid, scale = dual[0].centroid, dual[0].scale
@@ -68,15 +91,15 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
             dual = dataset.post_processing(dual, data_type)
             vert_p, norm_p = run(dual, k)
             st.add(vert_p, norm_p, v_idx, sel)
+        pool.shutdown()
+        lap("patch_loop")
         if world > 1:
             import torch.distributed as dist
             for t in (st.sum_v, st.vp, st.np_):
                 dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
         if centroid is None:                                        # a rank that received no patch
-            centroid = torch.from_numpy(points_noisy.mean(0, keepdims=True)).to(dev)
-            q = points_noisy - points_noisy.mean(0, keepdims=True)
-            e = q[mesh_ev]
-            scale = float(1 / (((e[:, 0] - e[:, 1]) ** 2).sum(1) ** 0.5).mean())
+            c_np, scale = dataset.normalisation(points_noisy, mesh_ev)
+            centroid, scale = torch.from_numpy(c_np).to(dev), float(scale)
         Vp, Np = st.finish()
     if forced is not None:
         for pl in poolings:
@@ -89,7 +112,9 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     depth = None
     if data_type in ("Kinect_v1", "Kinect_v2"):
         depth = torch.nn.functional.normalize(torch.from_numpy(points_noisy).to(dev), dim=1)
+    lap("stitch")
     V = data_util.update_position2(Vp, fv, vf, Np, n_iter, depth_direction=depth)
+    lap("update_position")
     return (V, Np, Vp, n_patches) if return_parts else (V, Np, Vp)
 
 

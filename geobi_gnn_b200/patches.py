@@ -35,7 +35,7 @@ def _p(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def mesh_get_neighbor_np(fv_indices, vf_indices, seed_idx, neighbor_count=None, ring_count=None, _taken=None):
+def mesh_get_neighbor_np(fv_indices, vf_indices, seed_idx, neighbor_count=None, ring_count=None, _stamps=None):
     """data_util.py:55-84 — list of face ids in discovery order."""
     assert neighbor_count is not None or ring_count is not None, "'neighbor_count' and 'ring_count' are both None"
     fv = np.ascontiguousarray(fv_indices, dtype=np.int64)
@@ -44,10 +44,12 @@ def mesh_get_neighbor_np(fv_indices, vf_indices, seed_idx, neighbor_count=None, 
     big = np.iinfo(np.int64).max
     nc = big if neighbor_count is None else int(neighbor_count)
     rc = big if ring_count is None else int(ring_count)
-    taken = np.zeros(f, dtype=np.uint8) if _taken is None else _taken
+    # _stamps = [face stamps u32 [F], vertex stamps u32 [V], epoch]: scratch a caller growing many patches allocates once
+    st = [np.zeros(f, dtype=np.uint32), np.zeros(vf.shape[0], dtype=np.uint32), 0] if _stamps is None else _stamps
+    st[2] += 1
     out = np.empty(min(nc, f), dtype=np.int64)
     n = _host().geobi_host_grow_patch(_p(fv), _p(vf), C.c_int64(f), C.c_int64(vf.shape[1]), C.c_int64(int(seed_idx)), C.c_int64(nc),
-                                      C.c_int64(rc), _p(taken), _p(out))
+                                      C.c_int64(rc), _p(st[0]), _p(st[1]), C.c_uint32(st[2]), _p(out))
     return out[:n]
 
 
@@ -67,26 +69,28 @@ def split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=
     pts = np.asarray(points, dtype=np.float32)
     fv = np.ascontiguousarray(fv_indices, dtype=np.int64)
     vf = np.ascontiguousarray(vf_indices, dtype=np.int64)
-    centroid = pts.mean(0, keepdims=True)
-    d2 = ((pts[fv].mean(1) - centroid) ** 2).sum(1)
-    flag = np.zeros(fv.shape[0], dtype=bool)
-    taken = np.zeros(fv.shape[0], dtype=np.uint8)
+    pts = np.ascontiguousarray(pts)
+    centroid = np.ascontiguousarray(pts.mean(0, keepdims=True))
+    # d2 = ((pts[fv].mean(1) - centroid) ** 2).sum(1) (dataset.py:165-166) in one threaded pass with numpy's fp32 operation
+    # order: the seeds are arg-maxima of d2, so it has to match bit for bit (tests/test_abi.py checks it does)
+    d2 = np.empty(fv.shape[0], dtype=np.float32)
+    lib, nthr = _host(), min(8, os.cpu_count() or 1)
+    lib.geobi_host_face_d2(_p(pts), _p(fv), C.c_int64(fv.shape[0]), _p(centroid), _p(d2), C.c_int(nthr))
+    stamps = [np.zeros(fv.shape[0], dtype=np.uint32), np.zeros(vf.shape[0], dtype=np.uint32), 0]
     seed = int(np.argmax(d2))
     patches = []
     # upstream rescans `np.where(~flag)` and `d2[left]` after every patch (dataset.py:188-192): O(F) index arrays per patch.
     # Same seeds from a masked copy of d2: covered faces drop to -inf, the next seed is the first arg-max of what is left.
-    d2_left = d2.astype(np.float32, copy=True)
-    n_left = fv.shape[0]
+    n_left = C.c_int64(fv.shape[0])
+    lib.geobi_host_cover_next_seed.restype = C.c_int64
     while True:
-        sel = mesh_get_neighbor_np(fv, vf, seed, neighbor_count=submesh_size, _taken=taken)
-        n_left -= int(np.count_nonzero(~flag[sel]))
-        flag[sel] = True
-        d2_left[sel] = -np.inf
+        sel = mesh_get_neighbor_np(fv, vf, seed, neighbor_count=submesh_size, _stamps=stamps)
+        nxt = lib.geobi_host_cover_next_seed(_p(d2), C.c_int64(fv.shape[0]), _p(sel), C.c_int64(sel.shape[0]), C.byref(n_left), C.c_int(nthr))
         if len(sel) > filter_patch_count:
             patches.append((sel, seed))
-        if n_left == 0:
+        if nxt < 0:
             break
-        seed = int(np.argmax(d2_left))
+        seed = int(nxt)
     return patches
 
 

@@ -146,3 +146,25 @@ def test_obj_round_trip(tmp_path):
     bad.write_text("v 0 0 0\nf 1 2 3\n")
     with __import__("pytest").raises(ValueError):
         meshio.read_obj(bad)
+
+
+def test_mesh_normalisation_is_the_oracles_bit_for_bit():
+    """dataset.normalisation (threaded C++ edge lengths + numpy mean) against the oracle's numpy restatement of
+    dataset.py:140,151-152: same centroid and the same fp32 scale, also above the threading threshold and for torch inputs."""
+    import types
+    import numpy as np
+    import torch
+    from geobi_gnn_b200 import dataset, synth
+    from oracle import ref_dataset
+    for n, seed in ((6, 0), (25, 1), (160, 2)):                       # 160 -> 768 000 edges: several threads
+        p, f = synth.icosphere(n)
+        rng = np.random.default_rng(seed)
+        p = synth.add_normal_noise((p * rng.uniform(0.3, 50) + rng.normal(size=(1, 3)) * 7).astype(np.float32), f, 0.25, seed=seed)
+        ev = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+        ev = ev[ev[:, 0] < ev[:, 1]]
+        holder = [types.SimpleNamespace()]
+        ref_dataset.attach_normalisation(holder, p, ev)
+        c, s = dataset.normalisation(p, ev)
+        assert np.array_equal(c, holder[0].centroid.numpy()) and np.float32(s) == np.float32(holder[0].scale)
+        c2, s2 = dataset.normalisation(torch.from_numpy(np.asarray(p, dtype=np.float32)), torch.from_numpy(ev))
+        assert np.array_equal(c, c2) and s == s2

@@ -87,3 +87,75 @@ def test_denoise_obj_file_to_file(tmp_path):
     p_out, f_out = meshio.read_obj(dst)
     assert np.array_equal(f_out, f) and np.abs(p_out - V).max() < 1e-5 * max(1.0, np.abs(V).max())
     assert abs(np.linalg.norm(Np, axis=1) - 1).max() < 1e-5
+
+
+def _open_shuffled_mesh(n, seed):
+    """Icosphere with a cap of faces removed (boundary vertices, ragged vf rows) and faces / vertices renumbered at random."""
+    from geobi_gnn_b200 import synth
+    p, f = synth.icosphere(n)
+    rng = np.random.default_rng(seed)
+    f = f[p[f].mean(1)[:, 2] < 0.6]                                  # open the mesh
+    used = np.unique(f)
+    remap = np.full(p.shape[0], -1, dtype=np.int64)
+    order = rng.permutation(used.shape[0])
+    remap[used] = order
+    p2 = np.empty((used.shape[0], 3), dtype=np.float32)
+    p2[order] = p[used]
+    f = remap[f][rng.permutation(f.shape[0])]
+    return synth.TriMesh(synth.add_normal_noise(p2, f, 0.2, seed=seed).astype(np.float32), f)
+
+
+def test_splitter_open_mesh_random_numbering_and_filter():
+    """Boundary vertices (vf rows padded with -1 at different lengths), arbitrary numbering, and filter_patch_count
+    (dataset.py:183): still the oracle's patches, in order."""
+    from geobi_gnn_b200 import patches
+    mesh = _open_shuffled_mesh(10, 3)
+    assert (mesh.vf < 0).any()
+    for sub, filt in ((200, 0), (777, 0), (300, 299), (10 ** 6, 0)):
+        a = patches.split_mesh(mesh.points, mesh.fv, mesh.vf, sub, filt)
+        b = ref_patch.split_mesh(mesh.points, mesh.fv, mesh.vf, sub, filt)
+        assert len(a) == len(b) and len(a) >= 1
+        for (sel, seed), (sel2, seed2) in zip(a, b):
+            assert seed == seed2 and np.array_equal(sel, np.asarray(sel2))
+    for seed in (0, 5, mesh.n_faces - 1):                           # ring-limited growth, and a scratch reused across calls
+        st = [np.zeros(mesh.n_faces, np.uint32), np.zeros(mesh.n_vertices, np.uint32), 0]
+        for rings in (1, 3):
+            got = patches.mesh_get_neighbor_np(mesh.fv, mesh.vf, seed, ring_count=rings, _stamps=st)
+            assert np.array_equal(got, np.asarray(ref_patch.mesh_get_neighbor_np(mesh.fv, mesh.vf, seed, ring_count=rings)))
+
+
+def test_splitter_seed_arithmetic_is_numpys_bit_for_bit():
+    """The seeds are arg-maxima of ((pts[fv].mean(1) - centroid)**2).sum(1) (dataset.py:165-166,192); on a near-sphere the
+    winner is decided by the last bit, so the threaded C++ pass has to reproduce numpy's fp32 result exactly, and the
+    next-seed scan np.argmax's first-of-equal-maxima rule (sizes above the threading threshold)."""
+    import ctypes as C
+    from geobi_gnn_b200 import patches, synth
+    lib = patches._host()
+    lib.geobi_host_cover_next_seed.restype = C.c_int64
+    p, f = synth.icosphere(130)                                     # 338 000 faces: several threads
+    rng = np.random.default_rng(0)
+    p = (p * 37.5 + rng.normal(size=(1, 3)) * 4).astype(np.float32)
+    f = np.ascontiguousarray(f, dtype=np.int64)
+    cen = np.ascontiguousarray(p.mean(0, keepdims=True))
+    want = ((p[f].mean(1) - cen) ** 2).sum(1)
+    for nthr in (1, 3, 8):
+        got = np.empty(f.shape[0], dtype=np.float32)
+        lib.geobi_host_face_d2(patches._p(p), patches._p(f), C.c_int64(f.shape[0]), patches._p(cen), patches._p(got), C.c_int(nthr))
+        assert want.dtype == np.float32 and np.array_equal(want, got)
+    d2 = np.round(want * 4) / 4                                     # many exact ties
+    d2 = d2.astype(np.float32)
+    covered = np.zeros(f.shape[0], bool)
+    left = C.c_int64(f.shape[0])
+    for it in range(6):
+        sel = np.ascontiguousarray(rng.choice(f.shape[0], 50000, replace=False).astype(np.int64))
+        if it == 5:
+            sel = np.arange(f.shape[0], dtype=np.int64)             # everything covered -> -1
+        nxt = lib.geobi_host_cover_next_seed(patches._p(d2), C.c_int64(f.shape[0]), patches._p(sel), C.c_int64(sel.shape[0]), C.byref(left),
+                                             C.c_int(1 + it))
+        covered[sel] = True
+        assert left.value == int((~covered).sum())
+        if covered.all():
+            assert nxt == -1
+        else:
+            ref = np.where(covered, -np.inf, np.round(want * 4) / 4)
+            assert nxt == int(np.argmax(ref)) and not covered[nxt]
