@@ -118,6 +118,61 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     return (V, Np, Vp, n_patches) if return_parts else (V, Np, Vp)
 
 
+def predict_one(opt, net, device, filename, rst_filename=None, filename_gt=None, n_iter: int = 60):
+    """test_dual.py:25-87 for one .obj: denoise, write `<rst_filename minus .obj>-60.obj`, and - with a ground-truth file -
+    the mean angular errors (degrees) of the predicted normals and of the updated mesh's normals against the original's.
+    Returns (angle1, angle2, n_faces)."""
+    from . import meshio, network, topology
+    dev = torch.device(device)
+    points, fv = meshio.read_obj(filename)
+    mesh = topology.DeviceTriMesh(points, fv, dev) if dev.type == "cuda" else synth.TriMesh(points, fv)
+    V, Np, _ = predict_mesh(net, mesh, opt.sub_size, data_type=opt.data_type, device=dev, n_iter=n_iter)
+    if rst_filename is not None:
+        meshio.write_obj(f"{rst_filename[:-4]}-{n_iter}.obj", V.detach().cpu().numpy(), fv)
+    angle1 = angle2 = 0.0
+    if filename_gt is not None:
+        points_o, fv_o = meshio.read_obj(filename_gt)
+        fv_t = torch.from_numpy(fv_o).to(dev)
+        Nt = data_util.computer_face_normal(torch.from_numpy(points_o.astype(np.float32)).to(dev), fv_t)
+        angle1 = float(network.error_n(Np, Nt))
+        angle2 = float(network.error_n(data_util.computer_face_normal(V, fv_t), Nt))
+    return angle1, angle2, int(Np.shape[0])
+
+
+def predict_dir(params_path, data_dir=None, sub_size=None, gpu=-1, dataset_root=None):
+    """test_dual.py:90-150: every `<data_dir>/*.obj` (or, without data_dir, the test split of the run's data type with its
+    ground truth) through predict_one; results in `<data_dir>/result_<flag>/`.  Returns (faces, face-weighted mean angle1,
+    angle2) - upstream prints them."""
+    import glob
+    import os
+    from . import checkpoint
+    assert data_dir is None or os.path.exists(data_dir)
+    device = torch.device("cpu") if not torch.cuda.is_available() else torch.device(f"cuda:{gpu}" if gpu >= 0 else "cuda")
+    opt, net = checkpoint.load_run(params_path, device, sub_size)
+    filenames, filenames_gt = [], []
+    if data_dir is None:
+        data_dir = os.path.join(dataset.DATASET_DIR if dataset_root is None else dataset_root, opt.data_type, "test")
+        original_dir = os.path.join(data_dir, "original")
+        for name in sorted(os.path.basename(d)[:-4] for d in glob.glob(os.path.join(original_dir, "*.obj"))):
+            for name_n in sorted(glob.glob(os.path.join(data_dir, "noisy", f"{name}_n*.obj"))):
+                filenames.append(name_n)
+                filenames_gt.append(os.path.join(original_dir, f"{name}.obj"))
+    else:
+        filenames = sorted(glob.glob(os.path.join(data_dir, "*.obj")))
+    result_dir = os.path.join(data_dir, f"result_{opt.flag}")
+    os.makedirs(result_dir, exist_ok=True)
+    error_all = np.zeros((3, len(filenames)))
+    for i, noisy_file in enumerate(filenames):
+        rst_file = os.path.join(result_dir, os.path.basename(noisy_file))
+        angle1, angle2, count = predict_one(opt, net, device, noisy_file, rst_file, filenames_gt[i] if filenames_gt else None)
+        error_all[:, i] = (count, angle1, angle2)                                # test_dual.py:137-139
+    count_sum = int(error_all[0].sum())
+    mean1 = float((error_all[0] * error_all[1]).sum() / max(count_sum, 1))
+    mean2 = float((error_all[0] * error_all[2]).sum() / max(count_sum, 1))
+    print(f"\nNum_face: {count_sum:>6},  angle_mean1: {mean1:.6f},  angle_mean2: {mean2:.6f}")
+    return count_sum, mean1, mean2
+
+
 class HostBatchRunner:
     """DualGNN over a stream of HOST-resident batches (the reference's DataLoader hands the network CPU tensors,
     train_dual.py:204-218 / test_dual.py:44-61): batch k+1 is uploaded on a copy stream while batch k computes, and
