@@ -170,8 +170,103 @@ def _state_digest(net):
     return h.digest()
 
 
+GRAD_SAMPLE = 512          # gradient entries kept per parameter tensor (evenly strided), plus every tensor's L2 norm
+
+
+def grad_sample(t):
+    flat = t.detach().reshape(-1)
+    idx = torch.linspace(0, flat.numel() - 1, min(GRAD_SAMPLE, flat.numel())).long()
+    return flat[idx].numpy()
+
+
+def reference_training_case(ref, n, mesh_seed, weight_seed, data_type, wei_param):
+    """One micro-step of train_dual.py:204-214 on the case's mesh: forward, L1 / L1 dual loss, backward - the reference's
+    modules under torch autograd.  Stored: the loss, every parameter gradient's norm and a strided sample of its entries."""
+    p, f = synth.icosphere(n)
+    pn = synth.add_normal_noise(p, f, 0.2, seed=mesh_seed).astype(np.float32)
+    mesh_n, mesh_o = _OMTriMesh(pn, f), _OMTriMesh(p.astype(np.float32), f)
+    _, centroid, scale = ref.data_util.center_and_scale(pn, mesh_n.ev_indices())
+    dual = ref.dataset.DualDataset.process_one_submesh(mesh_n, "g", mesh_o)
+    dual[0].centroid = torch.from_numpy(np.asarray(centroid)).float()
+    dual[0].scale = scale
+    data_v, data_f = ref.dataset.DualDataset.post_processing(dual, data_type)
+    y_v, y_f = data_v.y, data_f.y
+    torch.manual_seed(weight_seed)
+    net = ref.network.DualGNN(force_depth=data_type in ("Kinect_v1", "Kinect_v2"), pool_type="max", wei_param=wei_param)
+    net.train()
+    rec = _RecordedGraclus(2000 + weight_seed)
+    ref.net_util.graclus = rec
+    vert_p, norm_p, _ = net([data_v, data_f])
+    nw = ref.network
+    loss = nw.dual_loss(nw.loss_v(vert_p, y_v, "L1"), nw.loss_n(norm_p, y_f, "L1"), v_scale=1, n_scale=1)
+    loss.backward()
+    out = {"loss": loss.detach().numpy(), "n_poolings": np.int64(len(rec.labels))}
+    for i, lab in enumerate(rec.labels):
+        out[f"labels_{i}"] = lab.numpy()
+    names = []
+    for name, prm in net.named_parameters():
+        names.append(name)
+        out[f"gnorm/{name}"] = prm.grad.norm().numpy()
+        out[f"gsample/{name}"] = grad_sample(prm.grad)
+    out["param_names"] = np.array(names)
+    return out
+
+
+def reference_pipeline_case(ref, n, mesh_seed, weight_seed, data_type, wei_param, sub_size, filter_patch_count):
+    """test_dual.predict_one (test_dual.py:25-87) as written, on a mesh big enough to take the patch branch: the reference's
+    process_one_data (BFS patches with mesh_get_neighbor_np / get_submesh), per-patch forward, stitch, de-normalisation and
+    60-sweep update_position2, plus the angle errors against the ground truth.  Mesh files are served from memory."""
+    import argparse
+    import openmesh
+    import test_dual                                   # /root/reference/code/test_dual.py
+    p, f = synth.icosphere(n)
+    p2, f2 = synth.icosphere(2)                        # + a small separate component (80 faces): a patch the filter drops
+    p, f = np.concatenate([p, p2 * 0.3 + np.array([[2.5, 0.0, 0.0]])]).astype(np.float32), np.concatenate([f, f2 + p.shape[0]])
+    pn = synth.add_normal_noise(p, f, 0.2, seed=mesh_seed).astype(np.float32)
+    files = {"/mem/noisy.obj": (pn, f), "/mem/original.obj": (p.astype(np.float32), f)}
+    written = {}
+    openmesh.read_trimesh = lambda name: _OMTriMesh(*files[name])
+    openmesh.write_mesh = lambda name, mesh: written.__setitem__(name, np.array(mesh.points()))
+    # the patch list on its own: (dual_data, V_idx, select_faces) per kept patch, in order (dataset.py:156-193)
+    holder = types.SimpleNamespace(filter_patch_count=filter_patch_count, processed_dir="/nonexistent", processed_files=[])
+    all_data = ref.dataset.DualDataset.process_one_data("/mem/noisy.obj", sub_size, "/mem/original.obj")
+    assert len(all_data) > 2
+    out = {"points_noisy": pn, "points_original": p.astype(np.float32), "faces": f.astype(np.int64), "n_patches": np.int64(len(all_data)),
+           "sub_size": np.int64(sub_size)}
+    for k, (dual, v_idx, sel) in enumerate(all_data):
+        out[f"patch{k}_faces"] = np.asarray(sel, dtype=np.int64)
+        out[f"patch{k}_vertices"] = np.asarray(v_idx, dtype=np.int64)
+    # the filtered variant of the same walk (train_dual.py:141 passes filter_patch_count through the DualDataset object);
+    # cache writes are redirected to nowhere: only the list of names it registers is of interest
+    torch_save, ref.dataset.torch.save = ref.dataset.torch.save, (lambda *a, **k: None)
+    try:
+        ref.dataset.DualDataset.process_one_data("/mem/noisy.obj", sub_size, "/mem/original.obj", obj=holder)
+    finally:
+        ref.dataset.torch.save = torch_save
+    out["filtered_names"] = np.array([os.path.basename(x) for x in holder.processed_files])
+    out["filter_patch_count"] = np.int64(filter_patch_count)
+    written.clear()                                    # the patch .obj files "for visualization" (dataset.py:185-186)
+    # the whole prediction
+    torch.manual_seed(weight_seed)
+    net = ref.network.DualGNN(force_depth=data_type in ("Kinect_v1", "Kinect_v2"), pool_type="max", wei_param=wei_param).eval()
+    rec = _RecordedGraclus(3000 + weight_seed)
+    ref.net_util.graclus = rec
+    opt = argparse.Namespace(sub_size=sub_size, data_type=data_type)
+    angle1, angle2, n_faces = test_dual.predict_one(opt, net, torch.device("cpu"), "/mem/noisy.obj", "/mem/result.obj", "/mem/original.obj")
+    assert list(written) == ["/mem/result-60.obj"] and len(rec.labels) == 8 * len(all_data)
+    out.update(updated_vertices=written["/mem/result-60.obj"].astype(np.float32), angle1=np.float32(angle1), angle2=np.float32(angle2),
+               n_faces=np.int64(n_faces))
+    for i, lab in enumerate(rec.labels):
+        out[f"labels_{i}"] = lab.numpy()
+    return out
+
+
 CASES = (dict(n=3, mesh_seed=0, weight_seed=0, data_type="Synthetic", wei_param=2),
          dict(n=5, mesh_seed=3, weight_seed=7, data_type="Kinect_v1", wei_param=10))
+
+
+TRAIN_CASE = dict(n=4, mesh_seed=1, weight_seed=2, data_type="Synthetic", wei_param=2)
+PIPELINE_CASE = dict(n=8, mesh_seed=4, weight_seed=3, data_type="Synthetic", wei_param=2, sub_size=300, filter_patch_count=150)
 
 
 def main():
@@ -183,6 +278,12 @@ def main():
         path = os.path.join(here, f"reference_ico{case['n']}.npz")
         np.savez_compressed(path, **out)
         print(path, os.path.getsize(path), "bytes,", sum(p.numel() for p in net.parameters()), "parameters, keys:", len(out))
+    for name, fn, case in (("reference_train_ico4.npz", reference_training_case, TRAIN_CASE),
+                           ("reference_pipeline_ico8.npz", reference_pipeline_case, PIPELINE_CASE)):
+        out = fn(ref, **case)
+        out["case"] = np.array(repr(sorted(case.items())))
+        np.savez_compressed(os.path.join(here, name), **out)
+        print(name, os.path.getsize(os.path.join(here, name)), "bytes, keys:", len(out))
 
 
 if __name__ == "__main__":

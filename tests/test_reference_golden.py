@@ -154,3 +154,123 @@ def test_cuda_path_reproduces_the_reference(n, front_end):
     V = data_util.update_position2(Vp, fv, vf, torch.from_numpy(g["norm_p"]).to(DEV), 60, depth_direction=depth)
     assert util.rel_err(V, g["updated_vertices"]) < 1e-5
     assert util.rel_err(data_util.computer_face_normal(V, fv), g["updated_normals"]) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- patches, pipeline, training
+def _per_patch_forced(g):
+    labels = [torch.from_numpy(g[f"labels_{i}"]) for i in range(8 * int(g["n_patches"]))]
+    return [[labels[8 * k + 2 * j: 8 * k + 2 * j + 2] for j in range(4)] for k in range(int(g["n_patches"]))]
+
+
+def test_patch_walk_is_the_references():
+    """dataset.py:156-193 with data_util.mesh_get_neighbor_np / get_submesh as the reference executes them: the oracle's and
+    the product's (host C++) splitters give the same patches - faces in discovery order, vertices in first-use order - and the
+    filtered walk registers the same cache names."""
+    from geobi_gnn_b200 import patches
+    from oracle import ref_patch
+    g = np.load(os.path.join(util.GOLDEN, "reference_pipeline_ico8.npz"))
+    mesh = synth.TriMesh(g["points_noisy"], g["faces"])
+    sub = int(g["sub_size"])
+    for split, cut in ((ref_patch.split_mesh, ref_patch.get_submesh), (patches.split_mesh, patches.get_submesh)):
+        parts = split(g["points_noisy"], mesh.fv, mesh.vf, sub)
+        assert len(parts) == int(g["n_patches"])
+        for k, (sel, seed) in enumerate(parts):
+            assert np.array_equal(np.asarray(sel), g[f"patch{k}_faces"]) and int(seed) == int(g[f"patch{k}_faces"][0])
+            v_idx, faces = cut(mesh.fv, sel)
+            assert np.array_equal(v_idx, g[f"patch{k}_vertices"])
+            assert np.array_equal(g[f"patch{k}_vertices"][faces], mesh.fv[np.asarray(sel)])
+        kept = split(g["points_noisy"], mesh.fv, mesh.vf, sub, int(g["filter_patch_count"]))
+        assert [f"noisy-sub{sub}-{seed}.pt" for _, seed in kept] == list(g["filtered_names"])
+        assert 0 < len(kept) == len(parts) - 1          # the 80-face component is dropped
+
+
+def test_oracle_pipeline_and_training_step_reproduce_the_reference():
+    from oracle import ref_patch
+    # test_dual.predict_one on a mesh that takes the patch branch
+    g = np.load(os.path.join(util.GOLDEN, "reference_pipeline_ico8.npz"))
+    mesh, mesh_o = synth.TriMesh(g["points_noisy"], g["faces"]), synth.TriMesh(g["points_original"], g["faces"])
+    torch.manual_seed(3)
+    net = ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2).eval()
+    forced, results = _per_patch_forced(g), []
+    for k in range(int(g["n_patches"])):
+        v_idx, faces = ref_patch.get_submesh(mesh.fv, g[f"patch{k}_faces"])
+        dd = ref_dataset.process_one_submesh(synth.TriMesh(g["points_noisy"][v_idx], faces))
+        ref_dataset.attach_normalisation(dd, g["points_noisy"], mesh.ev)
+        centroid, scale = dd[0].centroid, dd[0].scale
+        dd = ref_dataset.post_processing(dd)
+        for pl, f in zip(util.poolings(net), forced[k]):
+            pl.forced = f
+        with torch.no_grad():
+            vp, nrm, _ = net([dd[0], dd[1]])
+        results.append((vp, nrm, torch.from_numpy(v_idx), torch.from_numpy(g[f"patch{k}_faces"])))
+    Vp, Np = ref_dataset.stitch_patches(mesh.n_vertices, mesh.n_faces, results)
+    V = ref_data_util.update_position2(Vp / scale + centroid, torch.from_numpy(mesh.fv), torch.from_numpy(mesh.vf), Np, 60)
+    assert util.rel_err(V, g["updated_vertices"]) < 1e-5
+    Nt = torch.from_numpy(np.asarray(mesh_o.face_normals, dtype=np.float32))
+    assert abs(float(ref_network.error_n(Np, Nt)) / float(g["angle1"]) - 1) < 1e-4
+    assert abs(float(ref_network.error_n(ref_data_util.computer_face_normal(V, torch.from_numpy(mesh.fv)), Nt)) / float(g["angle2"]) - 1) < 1e-4
+    # one training micro-step (train_dual.py:204-214)
+    t = np.load(os.path.join(util.GOLDEN, "reference_train_ico4.npz"))
+    (dv, df), _, _ = util.oracle_inputs(4, seed=1)
+    torch.manual_seed(2)
+    net = ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2).train()
+    labels = [torch.from_numpy(t[f"labels_{i}"]) for i in range(8)]
+    for j, pl in enumerate(util.poolings(net)):
+        pl.forced = labels[2 * j: 2 * j + 2]
+    y_v, y_f = dv.y, df.y
+    vp, nrm, _ = net([dv, df])
+    loss = ref_network.dual_loss(ref_network.loss_v(vp, y_v, "L1"), ref_network.loss_n(nrm, y_f, "L1"))
+    loss.backward()
+    assert abs(float(loss) / float(t["loss"]) - 1) < 1e-5
+    assert [n for n, _ in net.named_parameters()] == list(t["param_names"])
+    for name, prm in net.named_parameters():
+        _check_grad(name, prm.grad, t, 1e-4)
+
+
+def _check_grad(name, grad, t, tol):
+    flat = grad.detach().reshape(-1).cpu()
+    idx = torch.linspace(0, flat.numel() - 1, min(512, flat.numel())).long()
+    want = torch.from_numpy(t[f"gsample/{name}"])
+    scale = float(t[f"gnorm/{name}"]) / max(flat.numel(), 1) ** 0.5 + 1e-12          # rms entry of the reference gradient
+    assert abs(float(flat.norm()) - float(t[f"gnorm/{name}"])) <= tol * float(t[f"gnorm/{name}"]) + 1e-9, name
+    assert float((flat[idx] - want).abs().max()) <= 10 * tol * max(scale, float(want.abs().max())), name
+
+
+@pytest.mark.gpu
+def test_cuda_pipeline_and_training_step_reproduce_the_reference():
+    """inference.predict_mesh (split -> per-patch forward -> stitch -> 60-sweep update) and one training micro-step through the
+    CUDA kernels, teacher-forced with the reference's clusters, against what the reference's own code produced."""
+    from geobi_gnn_b200 import data_util, inference, network
+    DEV = "cuda"
+    g = np.load(os.path.join(util.GOLDEN, "reference_pipeline_ico8.npz"))
+    mesh, mesh_o = synth.TriMesh(g["points_noisy"], g["faces"]), synth.TriMesh(g["points_original"], g["faces"])
+    torch.manual_seed(3)
+    ref = ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2)
+    net = network.DualGNN(force_depth=False, pool_type="max", wei_param=2).to(DEV).eval()
+    net.load_state_dict(ref.state_dict())
+    V, Np, Vp, n_patches = inference.predict_mesh(net, mesh, int(g["sub_size"]), device=DEV, forced=_per_patch_forced(g), return_parts=True)
+    assert n_patches == int(g["n_patches"])
+    assert util.rel_err(V, g["updated_vertices"]) < 5e-5
+    Nt = torch.from_numpy(np.asarray(mesh_o.face_normals, dtype=np.float32)).to(DEV)
+    fv = torch.from_numpy(mesh.fv).to(DEV)
+    assert abs(float(network.error_n(Np, Nt)) / float(g["angle1"]) - 1) < 1e-3
+    assert abs(float(network.error_n(data_util.computer_face_normal(V, fv), Nt)) / float(g["angle2"]) - 1) < 1e-3
+    # training micro-step
+    t = np.load(os.path.join(util.GOLDEN, "reference_train_ico4.npz"))
+    (dv, df), _, _ = util.oracle_inputs(4, seed=1)
+    torch.manual_seed(2)
+    ref = ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2)
+    net = network.DualGNN(force_depth=False, pool_type="max", wei_param=2).to(DEV).train()
+    net.load_state_dict(ref.state_dict())
+    labels = [torch.from_numpy(t[f"labels_{i}"]) for i in range(8)]
+    for j, pl in enumerate(util.poolings(net)):
+        pl.forced = labels[2 * j: 2 * j + 2]
+    dv_m, df_m = util.data_to(dv, DEV), util.data_to(df, DEV)
+    y_v, y_f = dv_m.y, df_m.y
+    vp, nrm, _ = net([dv_m, df_m])
+    loss = network.dual_loss(network.loss_v(vp, y_v, "L1"), network.loss_n(nrm, y_f, "L1"))
+    loss.backward()
+    assert abs(float(loss) / float(t["loss"]) - 1) < 1e-4
+    assert [n for n, _ in net.named_parameters()] == list(t["param_names"])
+    for name, prm in net.named_parameters():
+        _check_grad(name, prm.grad, t, 2e-3)
