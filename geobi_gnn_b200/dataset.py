@@ -4,8 +4,9 @@ on the device.
 ``process_one_submesh`` / ``post_processing`` keep their names, argument meaning and the layout
 of the returned ``(graph_v, graph_f)`` tuple.  OpenMesh (not installable here) is replaced by
 any object exposing its index arrays as numpy: ``points, ev, fv, vf, vv, face_normals,
-vertex_normals`` (geobi_gnn_b200/synth.py:TriMesh).  File I/O, the .pt
-cache and the Kinect readers are out of scope.
+vertex_normals`` (geobi_gnn_b200/synth.py:TriMesh, topology.DeviceTriMesh).
+The directory data set with its .pt cache, the augmentation and the collater (dataset.py:19-283)
+are in the second half of this file; the Kinect depth-map readers are out of scope.
 """
 from __future__ import annotations
 

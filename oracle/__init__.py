@@ -10,11 +10,22 @@ packages is vendored in the reference, none is pinned (no requirements file),
 and none is installable here, so their behaviour is restated from their
 published algorithms; see SURVEY.md section 8(c).
 
-**PARITY UNPINNED.**  The reference has no tests, golden vectors or fixtures
- and cannot be imported in this container, so this oracle
-could not be checked against reference outputs.  It is pinned only against
-itself: ``tests/golden/`` holds vectors generated by ``tests/golden/make_golden.py``
-from this oracle, which guards against drift, not against a misreading.
+**Parity status: the reference's own files are PINNED, the third-party operators are
+UNPINNED.**  The reference has no tests, golden vectors or fixtures (SURVEY.md
+section 4).  ``tests/golden/make_reference_golden.py`` therefore EXECUTES the
+unmodified reference modules (``dataset``, ``data_util``, ``net_util``, ``network``,
+``test_dual``) in the build container, with stand-ins only for the third-party
+packages they import, and stores what they produce: graph / feature assembly, a
+DualGNN forward on two configurations (Synthetic and Kinect ``force_depth``), losses
+and errors, ``update_position2``, the BFS patch walk, a whole ``predict_one`` over
+11 patches and the parameter gradients of one training micro-step
+(``tests/golden/reference_*.npz``).  ``tests/test_reference_golden.py`` checks this
+oracle against those vectors (bit-equal weights and index arrays, floats to 1e-6 /
+1e-5) and, under ``-m gpu``, the CUDA path.  What stays unpinned: FeaStConv,
+graclus, scatter, coalesce and the OpenMesh index arrays themselves - both sides
+take them from ``oracle/pyg.py`` / ``synth.TriMesh``, restated from the published
+behaviour.  ``tests/golden/dualgnn_ico3.npz`` (``make_golden.py``) is the older
+self-generated vector set that guards against drift.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
 ``--impl reference`` legs may import this package.  The product

@@ -14,7 +14,8 @@
  *     unweighted: take the first unlabelled neighbour.
  *     if found: label[u] = label[v] = min(u, v)
  *
- * PARITY UNPINNED: the reference has no tests or vectors for this.
+ * PARITY UNPINNED: the reference has no tests or vectors for this (third-party
+ * algorithm; cross-checked only against the pure-Python loop in oracle/pyg.py).
  * Build: make -C oracle   (gcc -O2 -shared -fPIC)
  */
 #include <stdint.h>

@@ -11,7 +11,8 @@ are not installable here) from the published behaviour of
 * torch_sparse     — ``coalesce``    (net_util.py:9,263,294; data_util.py:432,455)
 * torch_cluster    — ``graclus``     (via net_util.py:127)
 
-All unpinned by the reference (no requirements file).  PARITY UNPINNED.
+All unpinned by the reference (no requirements file).  PARITY UNPINNED for this file: the reference's own modules
+are executed over these functions to produce tests/golden/reference_*.npz, so a misreading here is shared by both sides.
 Everything is plain PyTorch on CPU in the reference's evaluation order (per-edge
 FeaSt projection, materialised per-edge tensors, unsorted scatter).
 """

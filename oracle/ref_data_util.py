@@ -2,8 +2,8 @@
 
 Restates /root/reference/code/data_util.py:182-230 (face normal, centre/scale) and
 :383-556 (bilateral weight, graph / incidence builders, vertex update) in plain
-PyTorch on CPU.  PARITY UNPINNED (the reference module cannot be imported here:
-openmesh / torch_scatter / torch_sparse / matplotlib are absent).
+PyTorch on CPU.  Pinned against the reference's own data_util.py, executed over stand-ins for openmesh /
+torch_scatter / torch_sparse / matplotlib (tests/golden/make_reference_golden.py, tests/test_reference_golden.py).
 """
 from __future__ import annotations
 

@@ -4,7 +4,8 @@ Restates /root/reference/code/dataset.py:196-269 (``process_one_submesh`` and
 ``post_processing``) and the patch stitch of /root/reference/code/test_dual.py:49-61.
 OpenMesh is replaced by any object exposing the same index arrays as numpy
 (``points, ev, fv, vf, vv, face_normals, vertex_normals`` — see
-geobi_gnn_b200/synth.py:TriMesh).  PARITY UNPINNED.
+geobi_gnn_b200/synth.py:TriMesh).  Pinned against the reference's own
+dataset.py executed over the same mesh stand-in (tests/test_reference_golden.py); the OpenMesh arrays are unpinned.
 """
 from __future__ import annotations
 

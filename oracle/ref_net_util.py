@@ -2,7 +2,8 @@
 
 Restates /root/reference/code/net_util.py:56-302 (PoolingLayer with its 12
 edge-weight modes, DualFusionLayer, pool_edge, pool_face) in plain PyTorch on
-CPU over the shims in oracle/pyg.py.  PARITY UNPINNED.
+CPU over the shims in oracle/pyg.py.  Pinned against the reference's own net_util.py executed over the same shims
+(tests/golden/make_reference_golden.py, tests/test_reference_golden.py); the shims themselves are unpinned.
 
 Two test hooks that the reference does not have (its matching is random, so
 parity needs them; SURVEY.md section 8c "parity protocol"):

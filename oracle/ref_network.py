@@ -2,7 +2,9 @@
 
 Restates /root/reference/code/network.py:254-343 (GNNModule, DualGNN) and
 :347-413 (losses, metrics) in plain PyTorch fp32 on CPU, reference evaluation
-order (FeaSt projection per edge, materialised [N,1024] hidden).  PARITY UNPINNED.
+order (FeaSt projection per edge, materialised [N,1024] hidden).  Pinned against the reference's own network.py executed
+over oracle/pyg.py (same seeded weights bit for bit, same outputs and gradients: tests/test_reference_golden.py);
+the third-party operators in oracle/pyg.py are unpinned.
 
 ``DualGNN.forward`` additionally stores every intermediate the parity tests
 teacher-force with, in ``self.taps`` (a dict), when ``self.record`` is True.

@@ -1,7 +1,8 @@
 """CPU oracle: patch growth / submesh extraction / mesh splitting.  TEST INFRASTRUCTURE ONLY.
 
 Restates /root/reference/code/data_util.py:55-84 (``mesh_get_neighbor_np``), :318-336 (``get_submesh``) and the
-splitting loop of /root/reference/code/dataset.py:156-193 in pure Python / numpy (small cases only).  PARITY UNPINNED.
+splitting loop of /root/reference/code/dataset.py:156-193 in pure Python / numpy (small cases only).  Pinned: the reference's own
+functions produce the same patches (tests/golden/reference_pipeline_ico8.npz, tests/test_reference_golden.py).
 """
 from __future__ import annotations
 
