@@ -265,6 +265,45 @@ CASES = (dict(n=3, mesh_seed=0, weight_seed=0, data_type="Synthetic", wei_param=
          dict(n=5, mesh_seed=3, weight_seed=7, data_type="Kinect_v1", wei_param=10))
 
 
+POOLING_MODES = (-1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10)
+
+
+def reference_pooling_cases(ref, n=3, mesh_seed=2):
+    """net_util.PoolingLayer (net_util.py:56-245) for every edge_weight_type x pool_type on the facet graph of a small mesh:
+    the matcher's input weights (`_get_edge_weight`), the pooled graph and the unpooling indices."""
+    p, f = synth.icosphere(n)
+    pn = synth.add_normal_noise(p, f, 0.2, seed=mesh_seed).astype(np.float32)
+    mesh_n = _OMTriMesh(pn, f)
+    _, centroid, scale = ref.data_util.center_and_scale(pn, mesh_n.ev_indices())
+    out = {"points_noisy": pn, "faces": f.astype(np.int64), "modes": np.array(POOLING_MODES)}
+    for t in POOLING_MODES:
+        for pool_type in ("max", "mean"):
+            dual = ref.dataset.DualDataset.process_one_submesh(_OMTriMesh(pn, f), "g", None)
+            dual[0].centroid, dual[0].scale = torch.from_numpy(np.asarray(centroid)).float(), scale
+            _, data_f = ref.dataset.DualDataset.post_processing(dual, "Synthetic", is_plot=True)     # keeps pos (pooled too)
+            torch.manual_seed(t + 20)
+            layer = ref.net_util.PoolingLayer(6, pool_type, 2, t, 2)
+            rec = _RecordedGraclus(50 + t)
+            ref.net_util.graclus = rec
+            with torch.no_grad():
+                w_in = layer._get_edge_weight(data_f)
+                pooled = layer(data_f)
+            key = f"t{t}_{pool_type}"
+            out[f"{key}/x"] = pooled.x.numpy()
+            out[f"{key}/edge_index"] = pooled.edge_index.numpy()
+            out[f"{key}/pos"] = pooled.pos.numpy()
+            out[f"{key}/fv_is_none"] = np.bool_(pooled.fv_indices is None) if "fv_indices" in pooled else np.bool_(True)
+            if pooled.edge_weight is not None:
+                out[f"{key}/edge_weight"] = pooled.edge_weight.numpy()
+            if w_in is not None:
+                out[f"{key}/matcher_weight"] = w_in.numpy()
+            out[f"{key}/unpooling_indices"] = layer.unpooling_indices.numpy()
+            for i, lab in enumerate(rec.labels):
+                out[f"{key}/labels_{i}"] = lab.numpy()
+            out[f"{key}/unpooled"] = layer.unpooling(pooled.x).numpy()
+    return out
+
+
 TRAIN_CASE = dict(n=4, mesh_seed=1, weight_seed=2, data_type="Synthetic", wei_param=2)
 PIPELINE_CASE = dict(n=8, mesh_seed=4, weight_seed=3, data_type="Synthetic", wei_param=2, sub_size=300, filter_patch_count=150)
 
@@ -284,6 +323,9 @@ def main():
         out["case"] = np.array(repr(sorted(case.items())))
         np.savez_compressed(os.path.join(here, name), **out)
         print(name, os.path.getsize(os.path.join(here, name)), "bytes, keys:", len(out))
+    out = reference_pooling_cases(ref)
+    np.savez_compressed(os.path.join(here, "reference_pooling_ico3.npz"), **out)
+    print("reference_pooling_ico3.npz", os.path.getsize(os.path.join(here, "reference_pooling_ico3.npz")), "bytes, keys:", len(out))
 
 
 if __name__ == "__main__":

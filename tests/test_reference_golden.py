@@ -274,3 +274,62 @@ def test_cuda_pipeline_and_training_step_reproduce_the_reference():
     assert [n for n, _ in net.named_parameters()] == list(t["param_names"])
     for name, prm in net.named_parameters():
         _check_grad(name, prm.grad, t, 2e-3)
+
+
+# --------------------------------------------------------------------------------------------- PoolingLayer, every mode
+def _pooling_input(g):
+    mesh = synth.TriMesh(g["points_noisy"], g["faces"])
+    dd = ref_dataset.process_one_submesh(mesh, "g", None)
+    ref_dataset.attach_normalisation(dd, g["points_noisy"], mesh.ev)
+    pos_f = dd[1].pos.clone()
+    _, df = ref_dataset.post_processing(dd, "Synthetic")
+    df.pos = pos_f                                       # is_plot=True upstream: the facet positions stay and are pooled too
+    return df
+
+
+def _check_pooled(g, key, layer, pooled, tol):
+    assert np.array_equal(pooled.edge_index.cpu().numpy(), g[f"{key}/edge_index"])
+    assert np.array_equal(layer.unpooling_indices.cpu().numpy(), g[f"{key}/unpooling_indices"])
+    assert util.rel_err(pooled.x, g[f"{key}/x"]) < tol and util.rel_err(layer.unpooling(pooled.x), g[f"{key}/unpooled"]) < tol
+    assert util.rel_err(pooled.pos, g[f"{key}/pos"]) < tol
+    if f"{key}/edge_weight" in g.files:
+        assert util.rel_err(pooled.edge_weight, g[f"{key}/edge_weight"]) < max(tol, 1e-6)
+    else:
+        assert pooled.edge_weight is None
+
+
+@pytest.mark.parametrize("pool_type", ["max", "mean"])
+def test_oracle_pooling_layer_is_the_references_in_every_mode(pool_type):
+    from oracle import ref_net_util
+    g = np.load(os.path.join(util.GOLDEN, "reference_pooling_ico3.npz"))
+    for t in g["modes"].tolist():
+        key = f"t{t}_{pool_type}"
+        torch.manual_seed(t + 20)
+        layer = ref_net_util.PoolingLayer(6, pool_type, 2, t, 2)
+        g_perm = torch.Generator().manual_seed(50 + t)
+        layer.perm_fn = lambda n: torch.randperm(n, generator=g_perm)        # free-running on the reference's seed
+        with torch.no_grad():
+            pooled = layer(_pooling_input(g))
+        for i, tr in enumerate(layer.trace):
+            assert np.array_equal(tr[3].numpy(), g[f"{key}/labels_{i}"]), (key, i)
+            if i == 0 and f"{key}/matcher_weight" in g.files:
+                assert util.rel_err(tr[1], g[f"{key}/matcher_weight"]) < 1e-6, key
+        _check_pooled(g, key, layer, pooled, 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pool_type", ["max", "mean"])
+def test_cuda_pooling_layer_is_the_references_in_every_mode(pool_type):
+    from geobi_gnn_b200 import net_util
+    from oracle import ref_net_util
+    g = np.load(os.path.join(util.GOLDEN, "reference_pooling_ico3.npz"))
+    for t in g["modes"].tolist():
+        key = f"t{t}_{pool_type}"
+        torch.manual_seed(t + 20)
+        ref = ref_net_util.PoolingLayer(6, pool_type, 2, t, 2)               # the reference's seeded parameters (CPU test)
+        layer = net_util.PoolingLayer(6, pool_type, 2, t, 2).to("cuda")
+        layer.load_state_dict(ref.state_dict())
+        layer.forced = [torch.from_numpy(g[f"{key}/labels_{i}"]) for i in range(2)]
+        with torch.no_grad():
+            pooled = layer(util.data_to(_pooling_input(g), "cuda"))
+        _check_pooled(g, key, layer, pooled, 1e-5)
