@@ -304,6 +304,49 @@ def reference_pooling_cases(ref, n=3, mesh_seed=2):
     return out
 
 
+def reference_data_util_case(ref, n=4, mesh_seed=6):
+    """The remaining data_util entry points of SURVEY.md 8a that the forward cases do not reach: center_and_scale in all four
+    scale modes (numpy and tensor inputs), build_vertex_graph (2-ring), build_edge_vf, computer_face_normal, update_position
+    (the scatter variant, with and without the depth constraint)."""
+    p, f = synth.icosphere(n)
+    keep = p[f].mean(1)[:, 2] < 0.7                      # an OPEN mesh: boundary vertices, ragged vf / vv rows
+    f = f[keep]
+    used = np.unique(f)
+    remap = np.full(p.shape[0], -1, dtype=np.int64)
+    remap[used] = np.arange(used.shape[0])
+    p, f = p[used], remap[f]
+    pn = synth.add_normal_noise(p.astype(np.float32), f, 0.2, seed=mesh_seed).astype(np.float32)
+    m = _OMTriMesh(pn, f)
+    du = ref.data_util
+    out = {"points_noisy": pn, "faces": f.astype(np.int64)}
+    ev = m.ev_indices()
+    for s_type in (0, 1, 2, 3):
+        q, c, sc = du.center_and_scale(pn, ev, s_type)
+        out[f"cs_np{s_type}/points"], out[f"cs_np{s_type}/centroid"], out[f"cs_np{s_type}/scale"] = q, c, np.float32(sc)
+        q, c, sc = du.center_and_scale(torch.from_numpy(pn), torch.from_numpy(ev).long(), s_type)
+        out[f"cs_t{s_type}/points"], out[f"cs_t{s_type}/centroid"], out[f"cs_t{s_type}/scale"] = q.numpy(), c.numpy(), sc.numpy()
+    ev_t, vv_t = torch.from_numpy(ev).long(), torch.from_numpy(m.vv_indices()).long()
+    fv_t, vf_t = torch.from_numpy(m.fv_indices()).long(), torch.from_numpy(m.vf_indices()).long()
+    out["vertex_graph_2ring"] = du.build_vertex_graph(ev_t, vv_t).numpy()
+    out["edge_vf"] = du.build_edge_vf(vf_t).numpy()
+    out["edge_fv"] = du.build_edge_fv(fv_t).numpy()
+    out["facet_graph"] = du.build_facet_graph(fv_t, vf_t).numpy()
+    pts = torch.from_numpy(pn)
+    normals = du.computer_face_normal(pts, fv_t)
+    out["face_normals"] = normals.numpy()
+    target = torch.nn.functional.normalize(normals + 0.3 * torch.randn(normals.shape, generator=torch.Generator().manual_seed(1)), dim=1)
+    out["target_normals"] = target.numpy()
+    depth = torch.nn.functional.normalize(pts, dim=1)
+    out["update_position_10"] = du.update_position(pts, fv_t, vf_t, target, 10).numpy()
+    out["update_position_10_depth"] = du.update_position(pts, fv_t, vf_t, target, 10, depth_direction=depth).numpy()
+    out["update_position2_10"] = du.update_position2(pts, fv_t, vf_t, target, 10).numpy()
+    out["update_position2_10_depth"] = du.update_position2(pts, fv_t, vf_t, target, 10, depth_direction=depth).numpy()
+    vn = torch.from_numpy(np.asarray(m.vertex_normals(), dtype=np.float32))
+    ei = torch.cat([ev_t.t(), ev_t.t().flip(0)], 1)
+    out["calc_weight_vertex"] = du.calc_weight(pts, vn, ei).numpy()
+    return out
+
+
 TRAIN_CASE = dict(n=4, mesh_seed=1, weight_seed=2, data_type="Synthetic", wei_param=2)
 PIPELINE_CASE = dict(n=8, mesh_seed=4, weight_seed=3, data_type="Synthetic", wei_param=2, sub_size=300, filter_patch_count=150)
 
@@ -323,6 +366,9 @@ def main():
         out["case"] = np.array(repr(sorted(case.items())))
         np.savez_compressed(os.path.join(here, name), **out)
         print(name, os.path.getsize(os.path.join(here, name)), "bytes, keys:", len(out))
+    out = reference_data_util_case(ref)
+    np.savez_compressed(os.path.join(here, "reference_data_util_ico4.npz"), **out)
+    print("reference_data_util_ico4.npz", os.path.getsize(os.path.join(here, "reference_data_util_ico4.npz")), "bytes, keys:", len(out))
     out = reference_pooling_cases(ref)
     np.savez_compressed(os.path.join(here, "reference_pooling_ico3.npz"), **out)
     print("reference_pooling_ico3.npz", os.path.getsize(os.path.join(here, "reference_pooling_ico3.npz")), "bytes, keys:", len(out))

@@ -333,3 +333,39 @@ def test_cuda_pooling_layer_is_the_references_in_every_mode(pool_type):
         with torch.no_grad():
             pooled = layer(util.data_to(_pooling_input(g), "cuda"))
         _check_pooled(g, key, layer, pooled, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ data_util entry points
+def _check_data_util(du, g, dev, tol):
+    pn = torch.from_numpy(g["points_noisy"]).to(dev)
+    mesh = synth.TriMesh(g["points_noisy"], g["faces"])                       # open mesh: ragged vf / vv rows
+    ev, vv = torch.from_numpy(mesh.ev).to(dev), torch.from_numpy(mesh.vv).to(dev)
+    fv, vf = torch.from_numpy(mesh.fv).to(dev), torch.from_numpy(mesh.vf).to(dev)
+    for s_type in (0, 1, 2, 3):
+        q, c, sc = du.center_and_scale(pn, ev, s_type)
+        for kind in ("np", "t"):                                              # the reference's numpy and tensor branches agree
+            assert util.rel_err(q, g[f"cs_{kind}{s_type}/points"]) < tol and util.rel_err(c, g[f"cs_{kind}{s_type}/centroid"]) < tol
+            assert abs(float(sc) / float(g[f"cs_{kind}{s_type}/scale"]) - 1) < tol
+    assert np.array_equal(du.build_vertex_graph(ev, vv).cpu().numpy(), g["vertex_graph_2ring"])
+    assert np.array_equal(du.build_edge_vf(vf).cpu().numpy(), g["edge_vf"])
+    assert np.array_equal(du.build_edge_fv(fv).cpu().numpy(), g["edge_fv"])
+    assert np.array_equal(du.build_facet_graph(fv, vf).cpu().numpy(), g["facet_graph"])
+    assert util.rel_err(du.computer_face_normal(pn, fv), g["face_normals"]) < tol
+    target, depth = torch.from_numpy(g["target_normals"]).to(dev), torch.nn.functional.normalize(pn, dim=1)
+    assert util.rel_err(du.update_position(pn, fv, vf, target, 10), g["update_position_10"]) < tol
+    assert util.rel_err(du.update_position(pn, fv, vf, target, 10, depth_direction=depth), g["update_position_10_depth"]) < tol
+    assert util.rel_err(du.update_position2(pn, fv, vf, target, 10), g["update_position2_10"]) < tol
+    assert util.rel_err(du.update_position2(pn, fv, vf, target, 10, depth_direction=depth), g["update_position2_10_depth"]) < tol
+    vn = torch.from_numpy(np.asarray(mesh.vertex_normals, dtype=np.float32)).to(dev)
+    ei = torch.cat([ev.t(), ev.t().flip(0)], 1).contiguous()
+    assert util.rel_err(du.calc_weight(pn, vn, ei), g["calc_weight_vertex"]) < tol
+
+
+def test_oracle_data_util_is_the_references():
+    _check_data_util(ref_data_util, np.load(os.path.join(util.GOLDEN, "reference_data_util_ico4.npz")), "cpu", 1e-6)
+
+
+@pytest.mark.gpu
+def test_cuda_data_util_is_the_references():
+    from geobi_gnn_b200 import data_util
+    _check_data_util(data_util, np.load(os.path.join(util.GOLDEN, "reference_data_util_ico4.npz")), "cuda", 1e-5)
