@@ -304,6 +304,39 @@ def reference_pooling_cases(ref, n=3, mesh_seed=2):
     return out
 
 
+def reference_config0_case(ref, n=32, mesh_seed=0, weight_seed=0):
+    """BASELINE.json configs[0] at full size: one noisy icosphere of 20 480 faces (10 242 vertices), Synthetic, random-init
+    weights, through the reference's dataset assembly and DualGNN.forward.  The mesh is regenerated by the tests from
+    synth.icosphere / add_normal_noise (sha-256 of both arrays stored); kept here: outputs, cluster labels (int32), losses."""
+    import hashlib
+    p, f = synth.icosphere(n)
+    pn = synth.add_normal_noise(p, f, 0.2, seed=mesh_seed).astype(np.float32)
+    mesh_n, mesh_o = _OMTriMesh(pn, f), _OMTriMesh(p.astype(np.float32), f)
+    _, centroid, scale = ref.data_util.center_and_scale(pn, mesh_n.ev_indices())
+    dual = ref.dataset.DualDataset.process_one_submesh(mesh_n, "g", mesh_o)
+    dual[0].centroid, dual[0].scale = torch.from_numpy(np.asarray(centroid)).float(), scale
+    sizes = np.array([dual[0].pos.shape[0], dual[1].pos.shape[0], dual[0].edge_index.shape[1], dual[1].edge_index.shape[1]])
+    ei_sha = hashlib.sha256(dual[0].edge_index.numpy().tobytes() + dual[1].edge_index.numpy().tobytes()).digest()
+    data_v, data_f = ref.dataset.DualDataset.post_processing(dual, "Synthetic")
+    y_v, y_f = data_v.y, data_f.y
+    torch.manual_seed(weight_seed)
+    net = ref.network.DualGNN(force_depth=False, pool_type="max", wei_param=2).eval()
+    rec = _RecordedGraclus(4000 + weight_seed)
+    ref.net_util.graclus = rec
+    with torch.no_grad():
+        vert_p, norm_p, _ = net([data_v, data_f])
+    nw = ref.network
+    out = {"mesh_sha": np.frombuffer(hashlib.sha256(pn.tobytes() + f.astype(np.int64).tobytes()).digest(), dtype=np.uint8),
+           "edge_index_sha": np.frombuffer(ei_sha, dtype=np.uint8), "sizes": sizes, "scale": np.float32(scale),
+           "centroid": np.asarray(centroid, dtype=np.float32), "vert_p": vert_p.numpy(), "norm_p": norm_p.numpy(),
+           "loss_v_L1": nw.loss_v(vert_p, y_v, "L1").numpy(), "loss_n_L1": nw.loss_n(norm_p, y_f, "L1").numpy(),
+           "error_v": nw.error_v(vert_p, y_v).numpy(), "error_n": nw.error_n(norm_p, y_f).numpy(),
+           "level_sizes": np.array([int(l.max()) + 1 for l in rec.labels])}
+    for i, lab in enumerate(rec.labels):
+        out[f"labels_{i}"] = lab.numpy().astype(np.int32)
+    return out
+
+
 def reference_data_util_case(ref, n=4, mesh_seed=6):
     """The remaining data_util entry points of SURVEY.md 8a that the forward cases do not reach: center_and_scale in all four
     scale modes (numpy and tensor inputs), build_vertex_graph (2-ring), build_edge_vf, computer_face_normal, update_position
@@ -366,6 +399,9 @@ def main():
         out["case"] = np.array(repr(sorted(case.items())))
         np.savez_compressed(os.path.join(here, name), **out)
         print(name, os.path.getsize(os.path.join(here, name)), "bytes, keys:", len(out))
+    out = reference_config0_case(ref)
+    np.savez_compressed(os.path.join(here, "reference_config0_ico32.npz"), **out)
+    print("reference_config0_ico32.npz", os.path.getsize(os.path.join(here, "reference_config0_ico32.npz")), "bytes, sizes:", out["sizes"])
     out = reference_data_util_case(ref)
     np.savez_compressed(os.path.join(here, "reference_data_util_ico4.npz"), **out)
     print("reference_data_util_ico4.npz", os.path.getsize(os.path.join(here, "reference_data_util_ico4.npz")), "bytes, keys:", len(out))

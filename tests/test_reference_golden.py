@@ -369,3 +369,66 @@ def test_oracle_data_util_is_the_references():
 def test_cuda_data_util_is_the_references():
     from geobi_gnn_b200 import data_util
     _check_data_util(data_util, np.load(os.path.join(util.GOLDEN, "reference_data_util_ico4.npz")), "cuda", 1e-5)
+
+
+# --------------------------------------------------------------------------- BASELINE configs[0] at full size (20 480 faces)
+def _config0():
+    g = np.load(os.path.join(util.GOLDEN, "reference_config0_ico32.npz"))
+    p, f = synth.icosphere(32)
+    pn = synth.add_normal_noise(p, f, 0.2, seed=0).astype(np.float32)
+    sha = hashlib.sha256(pn.tobytes() + f.astype(np.int64).tobytes()).digest()
+    assert np.array_equal(np.frombuffer(sha, dtype=np.uint8), g["mesh_sha"]), "synthetic mesh generator changed"
+    forced = [torch.from_numpy(g[f"labels_{i}"]).long() for i in range(8)]
+    return g, pn, p.astype(np.float32), f, [forced[0:2], forced[2:4], forced[4:6], forced[6:8]]
+
+
+def _check_config0(g, vp, nrm, y_v, y_f, nw, tol_v, tol_n):
+    assert util.rel_err(vp, g["vert_p"]) < tol_v and util.rel_err(nrm, g["norm_p"]) < tol_n
+    for name, val in (("loss_v_L1", nw.loss_v(vp, y_v, "L1")), ("loss_n_L1", nw.loss_n(nrm, y_f, "L1")),
+                      ("error_v", nw.error_v(vp, y_v)), ("error_n", nw.error_n(nrm, y_f))):
+        assert abs(float(val) / float(g[name]) - 1) < 1e-4, name
+
+
+def test_oracle_config0_full_size_is_the_references():
+    g, pn, p, f, forced = _config0()
+    dd = ref_dataset.process_one_submesh(synth.TriMesh(pn, f), "g", synth.TriMesh(p, f))
+    sha = hashlib.sha256(dd[0].edge_index.numpy().tobytes() + dd[1].edge_index.numpy().tobytes()).digest()
+    assert np.array_equal(np.frombuffer(sha, dtype=np.uint8), g["edge_index_sha"])                   # 71 682 + 266 180 pairs, bit-equal
+    assert [dd[0].pos.shape[0], dd[1].pos.shape[0], dd[0].edge_index.shape[1], dd[1].edge_index.shape[1]] == g["sizes"].tolist()
+    ref_dataset.attach_normalisation(dd, pn, synth.TriMesh(pn, f).ev)
+    dv, df = ref_dataset.post_processing(dd, "Synthetic")
+    y_v, y_f = dv.y, df.y
+    torch.manual_seed(0)
+    net = ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2).eval()
+    util.set_perm_fn(net, 4000)                                                                       # free-running on the reference's seed
+    with torch.no_grad():
+        vp, nrm, _ = net([dv, df])
+    labels = [t[3] for pl in util.poolings(net) for t in pl.trace]
+    assert all(np.array_equal(a.numpy(), g[f"labels_{i}"]) for i, a in enumerate(labels))
+    assert [int(l.max()) + 1 for l in labels] == g["level_sizes"].tolist()
+    _check_config0(g, vp, nrm, y_v, y_f, ref_network, 1e-5, 1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_config0_full_size_is_the_references():
+    from geobi_gnn_b200 import dataset, network, topology
+    g, pn, p, f, forced = _config0()
+    dd = dataset.process_one_submesh(topology.DeviceTriMesh(pn, f, "cuda"), "g", topology.DeviceTriMesh(p, f, "cuda"), "cuda")
+    sha = hashlib.sha256(dd[0].edge_index.cpu().numpy().tobytes() + dd[1].edge_index.cpu().numpy().tobytes()).digest()
+    assert np.array_equal(np.frombuffer(sha, dtype=np.uint8), g["edge_index_sha"])
+    dataset.attach_normalisation(dd, pn, synth.TriMesh(pn, f).ev)
+    dv, df = dataset.post_processing(dd, "Synthetic")
+    y_v, y_f = dv.y, df.y
+    torch.manual_seed(0)
+    net = network.DualGNN(force_depth=False, pool_type="max", wei_param=2).to("cuda").eval()
+    net.load_state_dict(_seeded_state(0))                      # == the reference's seeded weights (state_sha check above)
+    for pl, fl in zip(util.poolings(net), forced):
+        pl.forced = fl
+    with torch.no_grad():
+        vp, nrm, _ = net([dv, df])
+    _check_config0(g, vp, nrm, y_v, y_f, network, 5e-5, 2e-4)
+
+
+def _seeded_state(seed):
+    torch.manual_seed(seed)
+    return ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2).state_dict()
