@@ -377,6 +377,22 @@ def reference_data_util_case(ref, n=4, mesh_seed=6):
     vn = torch.from_numpy(np.asarray(m.vertex_normals(), dtype=np.float32))
     ei = torch.cat([ev_t.t(), ev_t.t().flip(0)], 1)
     out["calc_weight_vertex"] = du.calc_weight(pts, vn, ei).numpy()
+    # network.laplacian_loss (network.py:347-361) on the vertex graph with self loops, with and without the normal projection
+    ei_loops = torch.cat([ei, torch.arange(pts.shape[0]).repeat(2, 1)], 1)
+    moved = pts + 0.05 * torch.randn(pts.shape, generator=torch.Generator().manual_seed(2))
+    out["laplacian_loss"] = ref.network.laplacian_loss(moved, pts, ei_loops).numpy()
+    out["laplacian_loss_normal"] = ref.network.laplacian_loss(moved, pts, ei_loops, normal=vn).numpy()
+    out["moved_points"] = moved.numpy()
+    # net_util.DualFusionLayer (net_util.py:248-278) on the vertex <-> facet incidence (edge_dual of process_one_submesh)
+    edge_dual = du.build_edge_fv(fv_t)
+    gen = torch.Generator().manual_seed(3)
+    x_v, x_f = torch.randn(pts.shape[0], 8, generator=gen), torch.randn(fv_t.shape[0], 8, generator=gen)
+    torch.manual_seed(4)
+    fusion = ref.net_util.DualFusionLayer(8)
+    data_v, data_f = pyg.Data(x=x_v.clone(), edge_dual=edge_dual[1]), pyg.Data(x=x_f.clone(), edge_dual=edge_dual[0])
+    with torch.no_grad():
+        f_v, f_f = fusion(data_v, data_f)
+    out.update(fusion_x_v=x_v.numpy(), fusion_x_f=x_f.numpy(), fusion_out_v=f_v.numpy(), fusion_out_f=f_f.numpy())
     return out
 
 

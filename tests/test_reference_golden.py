@@ -432,3 +432,47 @@ def test_cuda_config0_full_size_is_the_references():
 def _seeded_state(seed):
     torch.manual_seed(seed)
     return ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2).state_dict()
+
+
+def _check_misc(nw, nu, g, dev, tol):
+    """laplacian_loss (network.py:347-361) and DualFusionLayer (net_util.py:248-278) against the reference's values."""
+    from oracle import ref_net_util
+    mesh = synth.TriMesh(g["points_noisy"], g["faces"])
+    pts, moved = torch.from_numpy(g["points_noisy"]).to(dev), torch.from_numpy(g["moved_points"]).to(dev)
+    ev = torch.from_numpy(mesh.ev).to(dev)
+    ei = torch.cat([ev.t(), ev.t().flip(0), torch.arange(pts.shape[0], device=dev).repeat(2, 1)], 1)
+    vn = torch.from_numpy(np.asarray(mesh.vertex_normals, dtype=np.float32)).to(dev)
+    assert abs(float(nw.laplacian_loss(moved, pts, ei)) / float(g["laplacian_loss"]) - 1) < tol
+    assert abs(float(nw.laplacian_loss(moved, pts, ei, normal=vn)) / float(g["laplacian_loss_normal"]) - 1) < tol
+    fv = torch.from_numpy(mesh.fv).to(dev)
+    edge_dual = torch.stack([torch.arange(fv.shape[0], device=dev).repeat_interleave(3), fv.reshape(-1)])     # build_edge_fv
+    torch.manual_seed(4)
+    seeded = ref_net_util.DualFusionLayer(8)                                 # the reference's seeded parameters
+    layer = nu.DualFusionLayer(8).to(dev)
+    layer.load_state_dict(seeded.state_dict())
+    make = (lambda **kw: util.data_to(util.pyg.Data(**kw), dev)) if dev != "cpu" else util.pyg.Data
+    data_v = make(x=torch.from_numpy(g["fusion_x_v"]).to(dev), edge_dual=edge_dual[1])
+    data_f = make(x=torch.from_numpy(g["fusion_x_f"]).to(dev), edge_dual=edge_dual[0])
+    with torch.no_grad():
+        out_v, out_f = layer(data_v, data_f)
+    assert util.rel_err(out_v, g["fusion_out_v"]) < tol and util.rel_err(out_f, g["fusion_out_f"]) < tol
+
+
+def test_oracle_laplacian_loss_and_fusion_layer_are_the_references():
+    from oracle import ref_net_util
+    g = np.load(os.path.join(util.GOLDEN, "reference_data_util_ico4.npz"))
+    _check_misc(ref_network, ref_net_util, g, "cpu", 1e-6)
+    from geobi_gnn_b200 import network                                     # the product's losses are tensor expressions: CPU-checkable
+    mesh = synth.TriMesh(g["points_noisy"], g["faces"])
+    pts, moved = torch.from_numpy(g["points_noisy"]), torch.from_numpy(g["moved_points"])
+    ev = torch.from_numpy(mesh.ev)
+    ei = torch.cat([ev.t(), ev.t().flip(0), torch.arange(pts.shape[0]).repeat(2, 1)], 1)
+    vn = torch.from_numpy(np.asarray(mesh.vertex_normals, dtype=np.float32))
+    assert abs(float(network.laplacian_loss(moved, pts, ei)) / float(g["laplacian_loss"]) - 1) < 1e-6
+    assert abs(float(network.laplacian_loss(moved, pts, ei, normal=vn)) / float(g["laplacian_loss_normal"]) - 1) < 1e-6
+
+
+@pytest.mark.gpu
+def test_cuda_laplacian_loss_and_fusion_layer_are_the_references():
+    from geobi_gnn_b200 import net_util, network
+    _check_misc(network, net_util, np.load(os.path.join(util.GOLDEN, "reference_data_util_ico4.npz")), "cuda", 1e-5)
