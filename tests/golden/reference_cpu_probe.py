@@ -1,7 +1,8 @@
 """Build container only (needs /root/reference): the reference's OWN DualGNN.forward (its modules executed over the third-party
 stand-ins of tests/golden/make_reference_golden.py) timed next to the oracle port on the same 8000-face patch, same weights,
 same threads.  Shows how representative bench.py's `cpu_baseline` (kind "port", the only one that can run on the GPU box) is of
-the reference's CPU path.  python profiles/reference_cpu_probe.py [n_subdiv=20] [repeats=5] > profiles/r01_reference_vs_port_cpu.json
+the reference's CPU path.  TEST INFRASTRUCTURE (lives under tests/ because it executes oracle/).
+python tests/golden/reference_cpu_probe.py [n_subdiv=20] [repeats=5] > profiles/r01_reference_vs_port_cpu.json
 """
 import json
 import os
@@ -12,7 +13,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 
