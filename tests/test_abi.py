@@ -168,3 +168,54 @@ def test_mesh_normalisation_is_the_oracles_bit_for_bit():
         assert np.array_equal(c, holder[0].centroid.numpy()) and np.float32(s) == np.float32(holder[0].scale)
         c2, s2 = dataset.normalisation(torch.from_numpy(np.asarray(p, dtype=np.float32)), torch.from_numpy(ev))
         assert np.array_equal(c, c2) and s == s2
+
+
+def test_native_obj_io_equals_the_python_specification(tmp_path):
+    """csrc/host_obj.cpp (threaded .obj reader / writer in libgeobi_host.so) against meshio._read_obj_py / _write_obj_py: the same
+    arrays bit for bit and the same bytes, for every thread count (chunk cuts land inside lines, between CR and LF, before
+    relative indices) and for the record forms a mesh file can hold."""
+    import filecmp
+    import numpy as np
+    import pytest
+    from geobi_gnn_b200 import meshio, synth
+    rng = np.random.default_rng(5)
+    p, f = synth.icosphere(7)
+    p = (p * rng.uniform(1e-4, 1e4, size=(p.shape[0], 1)) * rng.choice([-1.0, 1.0], size=p.shape)).astype(np.float32)
+    p[3] = [0.0, -0.0, 1e-30]
+    p[4] = [123456789.0, 1e20, -5e-7]
+    for T in (1, 3, 8):
+        meshio.write_obj(tmp_path / f"c{T}.obj", p, f, n_threads=T)
+    meshio._write_obj_py(tmp_path / "py.obj", p, f)
+    assert all(filecmp.cmp(tmp_path / f"c{T}.obj", tmp_path / "py.obj", shallow=False) for T in (1, 3, 8))
+    want = meshio._read_obj_py(tmp_path / "py.obj")
+    for T in (1, 2, 5, 16):
+        got = meshio.read_obj(tmp_path / "py.obj", n_threads=T)
+        assert got[0].dtype == np.float64 and got[1].dtype == np.int64
+        assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]) and np.array_equal(got[1], f)
+    # a file with everything else in it: CRLF and lone CR line ends, tabs, signs, exponents, v/vt/vn tokens, relative indices,
+    # polygons, a `v<TAB>` record (not a vertex for either reader), degenerate `f` records, comments, vn / vt / g / usemtl records, indented (ignored) records, no final newline
+    lines = ["# comment", "mtllib x.mtl", "v 0 0 0", "v 1\t0 \t 0   ", "v\t7 7 7", "v +1.5e0 1E+0 -0.0 0.5 0.5 0.5", "vn 0 0 1", "vt 0.5 0.5", "v 0 1 .5", "v 2. 0 1e-3",
+             "g group", "f 1 2 3", "f 1/1/1 2/1/1 3/1/1 4/1/1", "f -1 -2 -3", "f +1 2//1 -1 4/2", "f 1 2", "f 5", "  v 9 9 9", " f 1 2 3",
+             "usemtl m", "v 5 5 5", "f -1 1 2 3 4 5", "s off"]
+    for name, sep, tail in (("lf", "\n", "\n"), ("crlf", "\r\n", "\r\n"), ("cr", "\r", ""), ("mixed", "\n\n\r\n", "")):
+        path = tmp_path / f"{name}.obj"
+        path.write_bytes((sep.join(lines) + tail).encode())
+        want = meshio._read_obj_py(path)
+        assert want[0].shape == (6, 3) and want[1].shape[0] == 1 + 2 + 1 + 2 + 0 + 0 + 4
+        for T in (1, 2, 3, 7, 32):
+            got = meshio.read_obj(path, n_threads=T)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (name, T)
+            assert np.array_equal(np.signbit(got[0]), np.signbit(want[0]))
+    empty = tmp_path / "empty.obj"
+    empty.write_bytes(b"")
+    pe, fe = meshio.read_obj(empty)
+    assert pe.shape == (0, 3) and fe.shape == (0, 3)
+    for text in ("v 0 0 zero\nf 1 1 1\n", "v 0 0\n", "v 0 0 0\nf 1 x 1\n", "v 0 0 0\nf 1 2.5 1\n"):
+        bad = tmp_path / "bad.obj"
+        bad.write_text(text)
+        with pytest.raises(ValueError):
+            meshio.read_obj(bad)
+        with pytest.raises((ValueError, IndexError)):
+            meshio._read_obj_py(bad)
+    with pytest.raises(OSError):
+        meshio.write_obj(tmp_path / "no_such_dir" / "x.obj", p, f)
