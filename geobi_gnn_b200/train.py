@@ -213,6 +213,9 @@ def train(opt, dataset_root=None, log_root=None, tensorboard=True):
     params file (what upstream hands to predict_dir).  Upstream's `code_bak` copy of its own sources is not made."""
     from . import checkpoint, dataset
     rank, world = parallel.rank_world()
+    device = torch.device(f"cuda:{opt.gpu}" if (opt.gpu >= 0 and torch.cuda.is_available()) else "cpu")
+    if device.type != "cuda":                     # before any run directory is made
+        raise RuntimeError("training needs a CUDA device: the graph convolutions have no CPU path")
     training_name = f"GeoBi-GNN_{opt.data_type}"
     training_time = datetime.now().strftime("%Y%m%d-%H%M%S")
     flag = opt.flag
@@ -244,9 +247,6 @@ def train(opt, dataset_root=None, log_root=None, tensorboard=True):
             test_writer = ScalarWriter(os.path.join(log_dir, "test"), tensorboard)
             test_writer.add_text("train_params", str(opt))
 
-        device = torch.device(f"cuda:{opt.gpu}" if (opt.gpu >= 0 and torch.cuda.is_available()) else "cpu")
-        if device.type != "cuda":
-            raise RuntimeError("training needs a CUDA device: the graph convolutions have no CPU path")
         list_file = lambda name: name if os.path.exists(os.path.join(dataset_root or dataset.DATASET_DIR, opt.data_type, name)) else None
         train_set = dataset.DualDataset(opt.data_type, "train", data_list_txt=list_file("train_list.txt"),
                                         filter_patch_count=opt.filter_patch_count, submesh_size=opt.sub_size,
