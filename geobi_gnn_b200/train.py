@@ -218,10 +218,15 @@ def train(opt, dataset_root=None, log_root=None, tensorboard=True):
         raise RuntimeError("training needs a CUDA device: the graph convolutions have no CPU path")
     training_name = f"GeoBi-GNN_{opt.data_type}"
     training_time = datetime.now().strftime("%Y%m%d-%H%M%S")
-    flag = opt.flag
-    opt.flag = f"{training_name}_{flag}_{training_time}"
     if opt.seed is None:
         opt.seed = random.randint(1, 10000)
+    if world > 1:                                 # one run directory and one seed (= one set of initial weights) for all ranks
+        import torch.distributed as dist
+        shared = [training_time, opt.seed]
+        dist.broadcast_object_list(shared, src=0)
+        training_time, opt.seed = shared
+    flag = opt.flag
+    opt.flag = f"{training_name}_{flag}_{training_time}"
     random.seed(opt.seed)
     np.random.seed(opt.seed)
     torch.manual_seed(opt.seed)
