@@ -29,7 +29,6 @@ def read_obj(path, n_threads=None):
     lib.geobi_host_obj_count(patches._p(buf), C.c_int64(buf.size), C.c_int(n_threads), patches._p(counts))
     points = np.empty((int(counts[0]), 3), dtype=np.float64)
     fv = np.empty((int(counts[1]), 3), dtype=np.int64)
-    lib.geobi_host_obj_parse.restype = C.c_int64
     bad = lib.geobi_host_obj_parse(patches._p(buf), C.c_int64(buf.size), C.c_int(n_threads), patches._p(points), patches._p(fv))
     if bad >= 0:
         line = bytes(buf[bad:bad + 80]).split(b"\n")[0].decode("utf-8", "replace").rstrip()

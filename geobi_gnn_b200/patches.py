@@ -27,6 +27,7 @@ def _host():
         lib = C.CDLL(path)
         lib.geobi_host_grow_patch.restype = C.c_int64
         lib.geobi_host_submesh.restype = C.c_int64
+        lib.geobi_host_obj_parse.restype = C.c_int64
         _HOST = lib
     return _HOST
 
