@@ -219,3 +219,25 @@ def test_native_obj_io_equals_the_python_specification(tmp_path):
             meshio._read_obj_py(bad)
     with pytest.raises(OSError):
         meshio.write_obj(tmp_path / "no_such_dir" / "x.obj", p, f)
+
+
+def test_host_library_exports_what_its_header_declares():
+    """include/geobi_host.h <-> libgeobi_host.so (patch splitter, normalisation, .obj I/O): every declared entry point is
+    exported, nothing else is, and the header compiles as C and as C++ next to the definitions' signatures."""
+    import ctypes
+    import subprocess
+    header = os.path.join(util.ROOT, "include", "geobi_host.h")
+    src = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    names = sorted(set(re.findall(r"\b(geobi_host_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) == 8
+    path = os.path.join(util.ROOT, "geobi_gnn_b200", "libgeobi_host.so")
+    lib = ctypes.CDLL(path)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in geobi_host.h but not exported"
+    exported = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    assert sorted(l.split()[-1] for l in exported.splitlines() if " T geobi_" in l) == names
+    for compiler, lang in (("gcc", "c"), ("g++", "c++")):
+        subprocess.run([compiler, "-x", lang, "-fsyntax-only", "-Wall", "-Werror", header], check=True)
+    # the definitions agree with the declarations: compile both sources with the header force-included
+    for cpp in ("host_patch.cpp", "host_obj.cpp"):
+        subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-include", header, os.path.join(util.ROOT, "geobi_gnn_b200", "csrc", cpp)], check=True)
