@@ -241,3 +241,50 @@ def test_host_library_exports_what_its_header_declares():
     # the definitions agree with the declarations: compile both sources with the header force-included
     for cpp in ("host_patch.cpp", "host_obj.cpp"):
         subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-include", header, os.path.join(util.ROOT, "geobi_gnn_b200", "csrc", cpp)], check=True)
+
+
+def test_native_obj_reader_fuzz_against_the_python_specification(tmp_path):
+    """400 random line soups (valid and broken records, every line-end style, random thread counts): the native reader and the
+    Python specification either return identical arrays or both refuse the file."""
+    import numpy as np
+    from geobi_gnn_b200 import meshio
+    rng = np.random.default_rng(2024)
+    numbers = ["0", "1", "-1", "+2", "3.5", "-0.0", "1e3", "1E-3", "+.5", "7.", "1e", "abc", "", "2.5", "nan", "inf", "-inf", "12345678901234567890"]
+    indices = ["1", "2", "3", "4", "-1", "-2", "+1", "1/2", "2/1/3", "3//1", "//1", "x", "1.5", "0", "99"]
+    seps = [" ", "  ", "\t", " \t "]
+    ends = ["\n", "\r\n", "\r", "\n\n"]
+    agree_ok = agree_fail = 0
+    for case in range(400):
+        lines = []
+        for _ in range(int(rng.integers(0, 12))):
+            kind = rng.choice(["v", "v", "v", "f", "f", "vn", "#", "", " v", "g"], p=None)
+            if kind == "v":
+                toks = [str(rng.choice(numbers[:10] if rng.random() < 0.9 else numbers)) for _ in range(int(rng.choice([3, 3, 3, 4, 6, 2])))]
+                lines.append("v " + str(rng.choice(seps)).join(toks) + (" " if rng.random() < 0.2 else ""))
+            elif kind == "f":
+                toks = [str(rng.choice(indices[:9] if rng.random() < 0.9 else indices)) for _ in range(int(rng.integers(0, 6)))]
+                lines.append("f " + str(rng.choice(seps)).join(toks))
+            elif kind in ("vn", "g", " v"):
+                lines.append(f"{kind} 1 2 3")
+            else:
+                lines.append(kind + (" note" if kind else ""))
+        text = "".join(l + str(rng.choice(ends)) for l in lines)
+        if lines and rng.random() < 0.3:
+            text = text.rstrip("\r\n")
+        path = tmp_path / "fuzz.obj"
+        path.write_bytes(text.encode())
+        try:
+            want = meshio._read_obj_py(path)
+        except (ValueError, IndexError, OverflowError):
+            want = None
+        for T in (1, int(rng.integers(2, 9))):
+            try:
+                got = meshio.read_obj(path, n_threads=T)
+            except ValueError:
+                got = None
+            assert (got is None) == (want is None), (case, T, text)
+            if got is not None:
+                assert np.array_equal(got[0], want[0], equal_nan=True) and np.array_equal(got[1], want[1]), (case, T, text)
+        agree_ok += want is not None
+        agree_fail += want is None
+    assert agree_ok > 100 and agree_fail > 30
