@@ -211,3 +211,14 @@ def test_directory_walk_over_cached_files(tmp_path):
     assert not torch.equal(plain[0].x, turned[0].x)
     assert util.rel_err(turned[0].x.norm(dim=1), plain[0].x.norm(dim=1)) < 1e-5
     assert sum(1 for _ in ds2) == 6
+
+
+def test_building_a_sample_without_a_gpu_fails_loudly(tmp_path):
+    """No CPU fallback on the data path either: a sample that is not cached has to be built by the CUDA graph builders, and
+    asking for that on the CPU raises instead of quietly taking another route."""
+    from geobi_gnn_b200 import dataset, meshio, synth
+    from geobi_gnn_b200._lib import GeobiError
+    p, f = synth.icosphere(3)
+    meshio.write_obj(tmp_path / "a_n1.obj", p, f)
+    with pytest.raises(GeobiError, match="no CPU fallback"):
+        dataset.DualDataset.process_one_data(str(tmp_path / "a_n1.obj"), 10 ** 9, None, device="cpu")
