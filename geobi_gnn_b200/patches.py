@@ -67,6 +67,12 @@ def get_submesh(fv_indices, select_faces, _slot=None):
 
 def split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=0) -> List[Tuple[np.ndarray, int]]:
     """dataset.py:156-193 — [(select_faces, seed), ...]."""
+    return list(iter_split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count))
+
+
+def iter_split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=0):
+    """The same walk as a generator: each (select_faces, seed) is handed out as soon as it is grown, so a consumer can start on
+    patch k while patch k+1 is being found (`prefetch` below runs the walk on a helper thread; the library calls release the GIL)."""
     pts = np.asarray(points, dtype=np.float32)
     fv = np.ascontiguousarray(fv_indices, dtype=np.int64)
     vf = np.ascontiguousarray(vf_indices, dtype=np.int64)
@@ -79,7 +85,6 @@ def split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=
     lib.geobi_host_face_d2(_p(pts), _p(fv), C.c_int64(fv.shape[0]), _p(centroid), _p(d2), C.c_int(nthr))
     stamps = [np.zeros(fv.shape[0], dtype=np.uint32), np.zeros(vf.shape[0], dtype=np.uint32), 0]
     seed = int(np.argmax(d2))
-    patches = []
     # upstream rescans `np.where(~flag)` and `d2[left]` after every patch (dataset.py:188-192): O(F) index arrays per patch.
     # Same seeds from a masked copy of d2: covered faces drop to -inf, the next seed is the first arg-max of what is left.
     n_left = C.c_int64(fv.shape[0])
@@ -88,11 +93,34 @@ def split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=
         sel = mesh_get_neighbor_np(fv, vf, seed, neighbor_count=submesh_size, _stamps=stamps)
         nxt = lib.geobi_host_cover_next_seed(_p(d2), C.c_int64(fv.shape[0]), _p(sel), C.c_int64(sel.shape[0]), C.byref(n_left), C.c_int(nthr))
         if len(sel) > filter_patch_count:
-            patches.append((sel, seed))
+            yield sel, seed
         if nxt < 0:
             break
         seed = int(nxt)
-    return patches
+
+
+def prefetch(iterable, depth=2):
+    """Runs `iterable` on a helper thread, at most `depth` items ahead of the consumer; exceptions surface at the consumer."""
+    import queue
+    import threading
+    q, end = queue.Queue(maxsize=depth), object()
+
+    def work():
+        try:
+            for item in iterable:
+                q.put((item, None))
+            q.put((end, None))
+        except BaseException as exc:                  # handed to the consumer, which re-raises it
+            q.put((end, exc))
+
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item, exc = q.get()
+        if exc is not None:
+            raise exc
+        if item is end:
+            return
+        yield item
 
 
 class Stitcher:

@@ -159,3 +159,26 @@ def test_splitter_seed_arithmetic_is_numpys_bit_for_bit():
         else:
             ref = np.where(covered, -np.inf, np.round(want * 4) / 4)
             assert nxt == int(np.argmax(ref)) and not covered[nxt]
+
+
+def test_streaming_splitter_yields_the_same_patches():
+    """patches.iter_split_mesh (generator) and patches.prefetch (helper thread, bounded look-ahead) hand out exactly the list
+    split_mesh returns, in order; an exception inside the producer reaches the consumer."""
+    from geobi_gnn_b200 import patches
+    mesh = _open_shuffled_mesh(12, 3)
+    want = patches.split_mesh(mesh.points, mesh.fv, mesh.vf, 200, 60)
+    assert len(want) > 5
+    it = patches.iter_split_mesh(mesh.points, mesh.fv, mesh.vf, 200, 60)
+    first = next(it)
+    assert np.array_equal(first[0], want[0][0]) and first[1] == want[0][1]
+    rest = list(it)
+    assert len(rest) == len(want) - 1 and all(np.array_equal(a[0], b[0]) and a[1] == b[1] for a, b in zip(rest, want[1:]))
+    got = list(patches.prefetch(patches.iter_split_mesh(mesh.points, mesh.fv, mesh.vf, 200, 60), depth=2))
+    assert len(got) == len(want) and all(np.array_equal(a[0], b[0]) and a[1] == b[1] for a, b in zip(got, want))
+    assert list(patches.prefetch(iter(()))) == []
+
+    def broken():
+        yield 1
+        raise KeyError("inside the producer")
+    with pytest.raises(KeyError):
+        list(patches.prefetch(broken()))
