@@ -207,14 +207,16 @@ def train_epoch(net, optimizer, samples, opt, device, writer=None, first_iterati
     return last
 
 
-def train(opt, dataset_root=None, log_root=None, tensorboard=True):
+def train(opt, dataset_root=None, log_root=None, tensorboard=True, net_factory=None):
     """train_dual.py:100-288.  Run directory `<log_root>/GeoBi-GNN_<data_type>_<flag>/<time>/` with training_info.txt,
     `*_params.pth`, `*_model.pth` (best validation normal error so far) and the train / test scalars.  Returns the path of the
-    params file (what upstream hands to predict_dir).  Upstream's `code_bak` copy of its own sources is not made."""
+    params file (what upstream hands to predict_dir).  Upstream's `code_bak` copy of its own sources is not made.
+    `net_factory(opt) -> module` replaces DualGNN (the loop's own tests drive it with a stand-in on the CPU over a cached data
+    set); DualGNN itself needs a CUDA device."""
     from . import checkpoint, dataset
     rank, world = parallel.rank_world()
     device = torch.device(f"cuda:{opt.gpu}" if (opt.gpu >= 0 and torch.cuda.is_available()) else "cpu")
-    if device.type != "cuda":                     # before any run directory is made
+    if device.type != "cuda" and net_factory is None:                     # before any run directory is made
         raise RuntimeError("training needs a CUDA device: the graph convolutions have no CPU path")
     training_name = f"GeoBi-GNN_{opt.data_type}"
     training_time = datetime.now().strftime("%Y%m%d-%H%M%S")
@@ -262,7 +264,10 @@ def train(opt, dataset_root=None, log_root=None, tensorboard=True):
         print(f"Testing set:  {len(eval_set):>4} samples")
         print("===" * 30)
 
-        net = network.DualGNN(force_depth=opt.force_depth, pool_type=opt.pool_type, wei_param=opt.wei_param)
+        if net_factory is not None:
+            net = net_factory(opt)
+        else:
+            net = network.DualGNN(force_depth=opt.force_depth, pool_type=opt.pool_type, wei_param=opt.wei_param)
         print(f"Total parameters: {sum(p.numel() for p in net.parameters())}")
         last_epoch = 0
         if opt.restore:

@@ -169,3 +169,49 @@ def test_two_rank_epoch_equals_single_process_with_doubled_batch():
     train.train_epoch(net, train.make_optimizer(opt, net.parameters()), samples, opt, "cpu")
     for a, b in zip(got, net.parameters()):
         assert torch.allclose(torch.tensor(a), b, rtol=1e-5, atol=1e-6)
+
+
+def test_whole_training_run_on_a_cached_data_set(tmp_path):
+    """train.train end to end on the CPU: a cached data set (nothing to build), a stand-in network, 3 epochs with accumulation
+    over 2 and a step schedule - run directory, params / model files, log, scalar files, best-model rule, restored stdout."""
+    import sys
+    import numpy as np
+    from geobi_gnn_b200 import checkpoint, dataset, meshio, synth, train
+    from oracle import ref_dataset
+    from tests import util
+    root, logs = tmp_path / "dataset", tmp_path / "log"
+    for split, names in (("train", ("a", "b", "c")), ("test", ("t",))):
+        base = root / "Synthetic" / split
+        for sub in ("original", "noisy", "processed_data"):
+            (base / sub).mkdir(parents=True)
+        for i, name in enumerate(names):
+            mesh_n, mesh_o = util.noisy_icosphere(2, seed=i)
+            dd = ref_dataset.process_one_submesh(mesh_n, name, mesh_o)
+            ref_dataset.attach_normalisation(dd, mesh_n.points, mesh_n.ev)
+            meshio.write_obj(base / "original" / f"{name}.obj", mesh_o.points, mesh_o.fv)
+            meshio.write_obj(base / "noisy" / f"{name}_n1.obj", mesh_n.points, mesh_n.fv)
+            dataset.save_dual_data(tuple(util.data_to(d, "cpu") for d in dd), base / "processed_data" / f"{name}_n1.pt")
+    opt = train.parse_arguments(["--data_type=Synthetic", "--flag=cpu", "--gpu=-1", "--seed=3", "--max_epoch=3", "--batch_size=2",
+                                 "--lr_sch=step", "--lr_decay=0.5", "--lr_step", "1", "--lr=0.05", "--optimizer=sgd"])
+    stdout = sys.stdout
+    params_file = train.train(opt, dataset_root=str(root), log_root=str(logs), tensorboard=False, net_factory=lambda o: _Stub())
+    assert sys.stdout is stdout
+    run_dir = os.path.dirname(params_file)
+    assert os.path.dirname(os.path.dirname(run_dir)) == str(logs) and os.path.basename(os.path.dirname(run_dir)) == "GeoBi-GNN_Synthetic_cpu"
+    saved = checkpoint.load_params(params_file)
+    assert saved.flag.startswith("GeoBi-GNN_Synthetic_cpu_") and saved.model_name == "GeoBi-GNN_Synthetic_model.pth" and saved.seed == 3
+    state = torch.load(os.path.join(run_dir, saved.model_name), weights_only=True)
+    assert set(state) == {"lin_v.weight", "lin_v.bias", "lin_f.weight", "lin_f.bias"}
+    log = open(os.path.join(run_dir, "training_info.txt")).read()
+    assert "Training set:    3 samples" in log and "Testing set:     1 samples" in log and "Epoch   0" in log and "best error" in log
+    rows = [json.loads(l) for l in open(os.path.join(run_dir, "train", "scalars.jsonl"))]
+    steps = [r["step"] for r in rows if r.get("tag") == "dual_loss"]
+    assert steps == [-3 + 1, -3 + 2, 1, 2, 3 + 1, 3 + 2]            # len(loader) * (epoch - 1) + step, as upstream counts (train_dual.py:200)
+    evals = [r for r in (json.loads(l) for l in open(os.path.join(run_dir, "test", "scalars.jsonl"))) if r.get("tag") == "error_f"]
+    assert len(evals) == 3 and all(np.isfinite(r["value"]) for r in evals)
+    lrs = [float(x.split("lr:")[1].split()[0]) for x in log.splitlines() if x.startswith("Epoch")]
+    assert lrs and abs(lrs[0] - 0.05) < 1e-12                                           # epoch 0 runs at the initial rate
+    with pytest.raises(RuntimeError, match="CUDA"):
+        if torch.cuda.is_available():
+            raise RuntimeError("CUDA present: the refusal below is only for machines without one")
+        train.train(train.parse_arguments(["--data_type=Synthetic", "--flag=x", "--gpu=-1"]), dataset_root=str(root), log_root=str(logs))
