@@ -230,7 +230,7 @@ def train(opt, dataset_root=None, log_root=None, tensorboard=True, net_factory=N
     flag = opt.flag
     opt.flag = f"{training_name}_{flag}_{training_time}"
     random.seed(opt.seed)
-    np.random.seed(opt.seed)
+    np.random.seed(opt.seed + rank)               # the augmentation stream (RandomRotate): distinct rotations on every rank
     torch.manual_seed(opt.seed)
 
     log_dir = os.path.join(dataset.LOG_DIR if log_root is None else log_root, f"{training_name}_{flag}", training_time)
@@ -254,12 +254,16 @@ def train(opt, dataset_root=None, log_root=None, tensorboard=True, net_factory=N
             test_writer = ScalarWriter(os.path.join(log_dir, "test"), tensorboard)
             test_writer.add_text("train_params", str(opt))
 
+        if world > 1 and rank != 0:                  # rank 0 builds the cache files, the others then find them
+            torch.distributed.barrier()
         list_file = lambda name: name if os.path.exists(os.path.join(dataset_root or dataset.DATASET_DIR, opt.data_type, name)) else None
         train_set = dataset.DualDataset(opt.data_type, "train", data_list_txt=list_file("train_list.txt"),
                                         filter_patch_count=opt.filter_patch_count, submesh_size=opt.sub_size,
                                         transform=dataset.RandomRotate(False), root=dataset_root, device=device)
         eval_set = dataset.DualDataset(opt.data_type, "test", data_list_txt=list_file("test_list.txt"), submesh_size=opt.sub_size,
                                        root=dataset_root, device=device)
+        if world > 1 and rank == 0:
+            torch.distributed.barrier()
         print(f"\nTraining set: {len(train_set):>4} samples")
         print(f"Testing set:  {len(eval_set):>4} samples")
         print("===" * 30)

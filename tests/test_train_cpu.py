@@ -215,3 +215,66 @@ def test_whole_training_run_on_a_cached_data_set(tmp_path):
         if torch.cuda.is_available():
             raise RuntimeError("CUDA present: the refusal below is only for machines without one")
         train.train(train.parse_arguments(["--data_type=Synthetic", "--flag=x", "--gpu=-1"]), dataset_root=str(root), log_root=str(logs))
+
+
+def _make_cached_sets(root, n_train=4):
+    from geobi_gnn_b200 import dataset, meshio
+    from oracle import ref_dataset
+    from tests import util
+    for split, names in (("train", [f"m{i}" for i in range(n_train)]), ("test", ["t"])):
+        base = os.path.join(root, "Synthetic", split)
+        for sub in ("original", "noisy", "processed_data"):
+            os.makedirs(os.path.join(base, sub), exist_ok=True)
+        for i, name in enumerate(names):
+            mesh_n, mesh_o = util.noisy_icosphere(2, seed=i)
+            dd = ref_dataset.process_one_submesh(mesh_n, name, mesh_o)
+            ref_dataset.attach_normalisation(dd, mesh_n.points, mesh_n.ev)
+            meshio.write_obj(os.path.join(base, "original", f"{name}.obj"), mesh_o.points, mesh_o.fv)
+            meshio.write_obj(os.path.join(base, "noisy", f"{name}_n1.obj"), mesh_n.points, mesh_n.fv)
+            dataset.save_dual_data(tuple(util.data_to(d, "cpu") for d in dd), os.path.join(base, "processed_data", f"{name}_n1.pt"))
+
+
+def _train_worker(rank, world, port, root, logs, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from geobi_gnn_b200 import train
+    opt = train.parse_arguments(["--data_type=Synthetic", "--flag=ddp", "--gpu=-1", "--max_epoch=2", "--batch_size=1", "--lr=0.05",
+                                 "--optimizer=sgd"])                       # no --seed: rank 0 draws it, everyone must use it
+    made = []
+    params_file = train.train(opt, dataset_root=root, log_root=logs, tensorboard=False, net_factory=lambda o: made.append(_Stub()) or made[-1])
+    q.put((rank, params_file, opt.seed, opt.flag, [p.detach().tolist() for p in made[0].parameters()]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_training_run_shares_seed_run_directory_and_weights(tmp_path):
+    """train.train under a 2-rank process group (gloo): rank 0's seed and time stamp are everyone's, one run directory is
+    written (by rank 0), both ranks start from the same weights and stay in step (identical parameters at the end), and the saved
+    model is loadable.  (Equality with a single process at the doubled batch is checked at train_epoch level above; whole runs
+    differ in the augmentation draws, which every rank takes from its own copy of the seeded numpy stream.)"""
+    from geobi_gnn_b200 import checkpoint, train
+    root, logs = str(tmp_path / "dataset"), str(tmp_path / "log")
+    _make_cached_sets(root, n_train=4)
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, world, port, root, logs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, params0, seed0, flag0, w0), (_, params1, seed1, flag1, w1) = got
+    assert params0 == params1 and seed0 == seed1 and flag0 == flag1
+    runs = os.listdir(os.path.join(logs, "GeoBi-GNN_Synthetic_ddp"))
+    assert len(runs) == 1
+    for a, b in zip(w0, w1):
+        assert torch.allclose(torch.tensor(a), torch.tensor(b), rtol=1e-6, atol=1e-7)
+    torch.manual_seed(seed0)
+    untouched = _Stub()
+    assert any(not torch.allclose(torch.tensor(a), p) for a, p in zip(w0, untouched.parameters()))      # it did train
+    saved = checkpoint.load_params(params0)
+    state = torch.load(os.path.join(os.path.dirname(params0), saved.model_name), weights_only=True)
+    assert set(state) == {"lin_v.weight", "lin_v.bias", "lin_f.weight", "lin_f.bias"}
+    rows = [json.loads(l) for l in open(os.path.join(os.path.dirname(params0), "train", "scalars.jsonl"))]
+    assert len([r for r in rows if r.get("tag") == "dual_loss"]) == 2 * 2          # 2 epochs x (4 samples / 2 ranks) optimiser steps
