@@ -1152,6 +1152,12 @@ bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const 
 int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map, int64_t n_src,
                     const float* W, const float* U, const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws,
                     void* ws, size_t ws_bytes, cudaStream_t st);
+// feast_tcagg.cu: the same layer with the aggregation itself on tcgen05 (round 2); GEOBI_NO_TCAGG=1 selects the FP32-pipe kernel above
+bool feast_tcagg_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t n_src);
+size_t feast_fwd_tcagg_ws_bytes(int64_t n_src);
+int feast_fwd_tcagg(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map, int64_t n_src,
+                    const float* W, const float* U, const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws,
+                    void* ws, size_t ws_bytes, cudaStream_t st);
 int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden, const float* W2,
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
                    int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st);
@@ -1163,7 +1169,11 @@ using namespace geobi;
 
 extern "C" size_t geobi_feast_fwd_ws_bytes(int64_t n_nodes, int c_in, int c_out, int precision) {
   precision &= ~GEOBI_FEAST_REUSE_WS;
-  if (precision != GEOBI_PREC_FP32) return feast_fwd_tc_ws_bytes(n_nodes, c_in, c_out);
+  if (precision != GEOBI_PREC_FP32) {
+    const size_t a = feast_fwd_tc_ws_bytes(n_nodes, c_in, c_out);
+    const size_t b = (c_in == 64 && c_out == 32) ? feast_fwd_tcagg_ws_bytes(n_nodes) : 0;
+    return a > b ? a : b;
+  }
   NullCarverF c;
   carve_feast(c, n_nodes, c_in, c_out, nullptr);
   return c.s.total();
@@ -1185,6 +1195,8 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   if (N == 0) return GEOBI_OK;
   const bool fused = precision == GEOBI_PREC_BF16X3 && feast_fused_supported(c_in, c_out, ldx, ldo, x, n_src) && getenv("GEOBI_NO_FUSED") == nullptr;
   GEOBI_REQUIRE(!reuse_ws || fused, "feast_fwd: GEOBI_FEAST_REUSE_WS is only defined for the fused 64->32 bf16x3 kernel");
+  if (fused && feast_tcagg_supported(c_in, c_out, ldx, ldo, x, n_src) && getenv("GEOBI_NO_TCAGG") == nullptr)
+    return feast_fwd_tcagg(x, ldx, N, rowptr, nbr, row_map, n_src, W, U, c, bias, act_slope, out, ldo, reuse_ws, ws, ws_bytes, st);
   if (fused) return feast_fwd_fused(x, ldx, N, rowptr, nbr, row_map, n_src, W, U, c, bias, act_slope, out, ldo, reuse_ws, ws, ws_bytes, st);
   if (precision != GEOBI_PREC_FP32)
     return feast_fwd_tc(x, ldx, N, c_in, rowptr, nbr, row_map, n_src, W, U, c, bias, c_out, act_slope, out, ldo,
