@@ -16,11 +16,12 @@
 // the projection reads only Z from shared memory.  Measured on B200 (profiles/micro/tc_layout_probe.cu, tc_ts_probe.cu): an
 // SS-mode MMA costs (A + B bytes) / 128 per clock, a TS-mode MMA 16 clocks at N = 32.
 //
-// Warp roles (640 threads, 1 CTA / SM, persistent over contiguous tiles of 32 nodes):
+// Warp roles (768 threads, 1 CTA / SM, persistent over contiguous tiles of 32 nodes):
 //   warps 0-3    epilogue: projection accumulator -> +bias, leaky_relu -> out; also load W into TMEM at start
 //   warps 4-11   drain: aggregation accumulators -> Z operand tiles (two sets of 4 quadrant warps, alternating node pairs)
-//   warp  12     MMA issue (one elected lane)
-//   warps 13-19  producers: indices, cp.async gathers, soft assignments; two node pairs in flight per warp
+//   warp  12     issues the aggregation MMAs (four node pairs per batch of barrier waits)
+//   warp  13     issues the projection MMAs
+//   warps 14-23  producers: indices, cp.async gathers, soft assignments; two node pairs in flight per warp
 #include "tc.cuh"
 
 namespace geobi {
@@ -31,13 +32,14 @@ using namespace tc;
 constexpr int C_IN = 64, C_OUT = 32;
 constexpr int TILE = 32;              // nodes per projection tile = MMA N
 constexpr int PAIRS = TILE / 2;
-constexpr int G = 7;                  // producer warps
-constexpr int R = 2 * G;              // ring slots, one node pair (2 x (x_hi, x_lo, q)) each
+constexpr int G = 10;                 // producer warps (768 threads: ptxas grants 80 registers up to that count anyway)
+constexpr int R = 14;                 // ring slots, one node pair (2 x (x_hi, x_lo, q)) each; all the shared memory left
 constexpr int DS = 9;                 // aggregation accumulator slots in TMEM (one node pair each)
-constexpr int PIPE = 8;               // pairs of tile t issued ahead of the projection of tile t-1
-constexpr int EPI_WARPS = 4, DRAIN_WARPS = 8;
-constexpr int MMA_WARP = EPI_WARPS + DRAIN_WARPS;
-constexpr int PROD_WARP0 = MMA_WARP + 1;
+constexpr int NSETS = 2;               // drain sets (4 quadrant warps each) taking node pairs in turn
+constexpr int EPI_WARPS = 4, DRAIN_WARPS = 4 * NSETS;
+constexpr int AGG_WARP = EPI_WARPS + DRAIN_WARPS;   // issues the aggregation MMAs
+constexpr int PROJ_WARP = AGG_WARP + 1;              // issues the projection MMAs
+constexpr int PROD_WARP0 = PROJ_WARP + 1;
 constexpr int WARPS = PROD_WARP0 + G;
 constexpr int THREADS = WARPS * 32;
 
@@ -51,7 +53,7 @@ constexpr int ZCHUNK = TILE * 128;             // one 64-wide K block of the Z o
 constexpr int ZPLANE = 9 * ZCHUNK;
 constexpr int STAGE_BYTES = 2 * TILE * C_OUT * 4;
 constexpr int SMEM_BYTES = 2 * ZPLANE + R * SLOT_BYTES + STAGE_BYTES + 1024;
-constexpr int PROW = 20;                       // floats per row of the head projections: hi[9], 0, lo[9], 0
+constexpr int PROW = 12;                       // floats per row of the head projections u_h . x (computed in fp64): 9 + 3 pad
 
 __host__ __device__ constexpr uint32_t idesc_of(int M, int N, int a_mn, int b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -97,6 +99,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+__device__ __forceinline__ void mbar_wait_u(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  } while (!done);
+}
 // non-blocking probe of an mbarrier phase (warp-uniform answer: lane 0 tests, the result is broadcast)
 __device__ __forceinline__ bool phase_done(uint64_t* bar, uint32_t parity) {
   uint32_t done;
@@ -104,6 +113,14 @@ __device__ __forceinline__ bool phase_done(uint64_t* bar, uint32_t parity) {
                : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return __shfl_sync(0xffffffffu, done, 0) != 0;
 }
+
+#ifdef TCAGG_TIMELINE
+// per-role clock64() stamps of CTA 0 for pairs [128, 192) / tiles [8, 72): g_tl[role][index][event]
+__device__ long long g_tl[4 * 64 * 8];
+#define TLW(role, idx, ev) do { const int _i = (idx); if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && _i >= 0 && _i < 64) g_tl[((role) * 64 + _i) * 8 + (ev)] = clock64(); } while (0)
+#else
+#define TLW(role, idx, ev) do { } while (0)
+#endif
 
 #ifdef TCAGG_DEBUG
 // bounded waits: a wait that does not complete records (warp, tag) and raises a flag that lets every other wait fall through,
@@ -116,24 +133,35 @@ __device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, int tag
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) return;
-    if ((it & 1023) == 1023) {
-      if (*(volatile unsigned int*)&g_dbg[63]) return;
-      if (it > (1ll << 18)) {
-        if ((threadIdx.x & 31) == 0) g_dbg[(blockIdx.x == 0 ? 0 : 32) + (threadIdx.x >> 5)] = (unsigned)tag | (parity << 16) | 0x80000000u;
-        *(volatile unsigned int*)&g_dbg[63] = 1;
+    if ((it & 255) == 0) {
+      unsigned int who = *(volatile unsigned int*)&g_dbg[63];
+      if (who == 0 && it > (1ll << 17)) {
+        atomicCAS(&g_dbg[63], 0u, blockIdx.x + 1);
+        who = *(volatile unsigned int*)&g_dbg[63];
+      }
+      if (who) {       // the CTA whose wait timed out first records the FIRST wait each of its warps gave up on; everybody falls through
+        if (who == blockIdx.x + 1 && *(volatile unsigned int*)&g_dbg[threadIdx.x >> 5] == 0)
+          g_dbg[threadIdx.x >> 5] = (unsigned)tag | (parity << 31);
         return;
       }
     }
   }
 }
-#define WAIT(bar, parity, tag) wait_dbg(bar, parity, tag)
+#define PROGRESS(idx, val) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) g_dbg[idx] = (unsigned)(val); } while (0)
+#define WAIT(bar, parity, tag) wait_dbg(bar, parity, (tag) | ((int)((bar) - bars) << 8))
+#define WAIT_U(addr, parity, tag) wait_dbg(reinterpret_cast<uint64_t*>(__cvta_shared_to_generic(addr)), parity, (tag) | ((int)(((addr) - smem_u32(bars)) >> 3) << 8))
 #else
+#define PROGRESS(idx, val) do { } while (0)
 #define WAIT(bar, parity, tag) mbar_wait(bar, parity)
+#define WAIT_U(addr, parity, tag) mbar_wait_u(addr, parity)
 #endif
+__device__ __forceinline__ void mma_commit_u(uint32_t bar_addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
-// prep: x (fp32 rows) -> Xs[row] = bf16 hi[64] | lo[64]  (256 B)  and  P[row] = {hi[9], 0, lo[9], 0} of the fp64 head projections
-// u_h . x_row  (double-float pairs: the soft assignments need P_j - P_i to fp32 accuracy of the DIFFERENCE, feast.cu).
+// prep: x (fp32 rows) -> Xs[row] = bf16 hi[64] | lo[64]  (256 B)  and  P[row] = the head projections u_h . x_row, accumulated in fp64
+// and rounded once to fp32 (|error| <= 2^-24 |P|: the soft assignments use P_j - P_i, so their absolute error is ~1e-7 |P|).
 constexpr int PREP_ROWS = 64, PREP_THREADS = 256;
 __global__ void __launch_bounds__(PREP_THREADS) prep_x_kernel(const float* __restrict__ x, int64_t ldx, int64_t n, const float* __restrict__ U,
                                                              uint8_t* __restrict__ Xs, float* __restrict__ P) {
@@ -165,18 +193,10 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_x_kernel(const float* __res
     a2 = fma(xv, us[c][part + 8], a2);
   }
   float* pr = P + (row0 + r) * PROW;
-  {
-    float hi = (float)a0;
-    pr[part] = hi; pr[10 + part] = (float)(a0 - (double)hi);
-    hi = (float)a1;
-    pr[part + 4] = hi; pr[10 + part + 4] = (float)(a1 - (double)hi);
-    if (part == 0) {
-      hi = (float)a2;
-      pr[8] = hi; pr[18] = (float)(a2 - (double)hi);
-    } else if (part == 1) {
-      pr[9] = 0.f; pr[19] = 0.f;
-    }
-  }
+  pr[part] = (float)a0;
+  pr[part + 4] = (float)a1;
+  if (part == 0) pr[8] = (float)a2;
+  else pr[8 + part] = 0.f;
   // split this thread's 16 channels
   uint32_t hi[8], lo[8];
 #pragma unroll
@@ -232,9 +252,20 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
                                                                        const uint32_t* __restrict__ Wp, const float* __restrict__ bias,
                                                                        float slope, float* __restrict__ out, int64_t ldo) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full[R], xfree[R], dfull[DS], dfree[DS], zfull, zfree, ofull[2], ofree[2];
+  // one array so that the debug build can name a barrier by its index: full | xfree | dfull | dfree | zfull | zfree | ofull | ofree
+  __shared__ __align__(8) uint64_t bars[2 * R + 2 * DS + 6];
+  uint64_t* const full = bars;
+  uint64_t* const xfree = bars + R;
+  uint64_t* const dfull = bars + 2 * R;
+  uint64_t* const dfree = bars + 2 * R + DS;
+  uint64_t& zfull = bars[2 * R + 2 * DS];
+  uint64_t& zfree = bars[2 * R + 2 * DS + 1];
+  uint64_t* const ofull = bars + 2 * R + 2 * DS + 2;
+  uint64_t* const ofree = bars + 2 * R + 2 * DS + 4;
   __shared__ uint32_t tmem_slot;
+  __shared__ uint32_t agg_pos;      // ring sequence numbers issued so far by the aggregation-issue warp (see `slot_reusable`)
   __shared__ float chs[12];
+  __shared__ __align__(16) int jbuf[G][32];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* z_hi = sm;
@@ -260,8 +291,9 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     mbar_init(&ofree[1], EPI_WARPS);
     fence_mbar_init();
   }
-  if (warp == MMA_WARP) tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (warp == AGG_WARP) tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid < H) chs[tid] = cvec[tid];
+  if (tid == 32) agg_pos = 0;
   // slots that a node does not use keep whatever an earlier node left there (finite, and multiplied by q = 0): start finite
   for (int i = tid; i < R * SLOT_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(ring)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
@@ -326,42 +358,110 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     }
   };
 
-  if (warp == MMA_WARP) {
-    // ================================================== MMA issue ==================================================
-    constexpr uint32_t IA = idesc_of(64, 32, 1, 1), IB = idesc_of(64, 16, 1, 1), IP = idesc_of(64, 32, 0, 0);
-    constexpr uint32_t XHI = desc_hi(64, 2), QHI = desc_hi(32, 4), ZHI = desc_hi(64, 2);
+  if (warp == AGG_WARP) {
+    // ================================================== aggregation MMA issue ==================================================
+    // A single warp issues everything serially (~5 clk per dependent instruction, ~90 clk per mbarrier wait), so the common case -
+    // every pair of the tile takes one ring slot - is handled four pairs at a time: lanes 0-3 wait on the pairs' `full`
+    // barriers and lanes 4-7 on their `dfree` barriers concurrently, then one elected lane issues the 16 MMAs and 8 commits with
+    // incrementally maintained slot indices (no divisions).
+    constexpr uint32_t IA = idesc_of(64, 32, 1, 1), IB = idesc_of(64, 16, 1, 1);
+    constexpr uint32_t XHI = desc_hi(64, 2), QHI = desc_hi(32, 4);
     const uint32_t ring_lo = (smem_u32(ring) & 0x3FFFFu) >> 4;
-    const uint32_t zh_lo = ((smem_u32(z_hi) & 0x3FFFFu) >> 4) | (1u << 16), zl_lo = ((smem_u32(z_lo) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t full_u = smem_u32(&full[0]), xfree_u = smem_u32(&xfree[0]), dfull_u = smem_u32(&dfull[0]), dfree_u = smem_u32(&dfree[0]);
     int rb_n, re_n;
     load_rowptr(t_begin, rb_n, re_n);
     uint32_t seq_base = 0;
     TileInfo ti{};
-    auto do_pair = [&](uint32_t p, int pp) {
+    auto issue_pair = [&](uint32_t slot, uint32_t dslot, uint32_t acc, bool last) {
+      const uint32_t xa = ring_lo + slot * (SLOT_BYTES >> 4), qa = xa + (4 * XT >> 4);
+      const uint32_t dA = tmem + COL_D + dslot * 32, dB = dA + HALF;
+      mma_ss(dA, xa, XHI, qa, QHI, IA, acc);
+      mma_ss(dA, xa + (XT >> 4), XHI, qa, QHI, IB, 1u);
+      mma_ss(dB, xa + (2 * XT >> 4), XHI, qa + (1024 >> 4), QHI, IA, acc);
+      mma_ss(dB, xa + (3 * XT >> 4), XHI, qa + (1024 >> 4), QHI, IB, 1u);
+      mma_commit_u(xfree_u + 8 * slot);
+      if (last) mma_commit_u(dfull_u + 8 * dslot);
+    };
+    auto do_pair = [&](uint32_t p, int pp) {       // general path: pairs that take several rounds
       const uint32_t dslot = p % DS, dk = p / DS;
       const int rounds = __shfl_sync(0xffffffffu, ti.rounds, pp);
       const uint32_t seq0 = seq_base + (uint32_t)__shfl_sync(0xffffffffu, ti.excl, pp);
       for (int r = 0; r < rounds; ++r) {
         const uint32_t seq = seq0 + r, slot = seq % R, k = seq / R;
+        TLW(1, (int)p - 128, 0);
         WAIT(&full[slot], k & 1, 1);
+        TLW(1, (int)p - 128, 1);
         if (r == 0) WAIT(&dfree[dslot], (dk & 1) ^ 1, 2);
+        TLW(1, (int)p - 128, 2);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t xa = ring_lo + slot * (SLOT_BYTES >> 4), qa = xa + (4 * XT >> 4);
-          const uint32_t dA = tmem + COL_D + dslot * 32, dB = dA + HALF;
-          mma_ss(dA, xa, XHI, qa, QHI, IA, r > 0);
-          mma_ss(dA, xa + (XT >> 4), XHI, qa, QHI, IB, 1u);
-          mma_ss(dB, xa + (2 * XT >> 4), XHI, qa + (1024 >> 4), QHI, IA, r > 0);
-          mma_ss(dB, xa + (3 * XT >> 4), XHI, qa + (1024 >> 4), QHI, IB, 1u);
-          mma_commit(&xfree[slot]);
-          if (r == rounds - 1) mma_commit(&dfull[dslot]);
+          issue_pair(slot, dslot, r > 0, r == rounds - 1);
+          *(volatile uint32_t*)&agg_pos = seq + 1;
         }
         __syncwarp();
+        PROGRESS(32, (seq + 1) | (p << 16));
+        TLW(1, (int)p - 128, 3);
       }
     };
-    auto do_proj = [&](int t) {
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+      ti = tile_info(t_begin + t, rb_n, re_n);
+      load_rowptr(t_begin + t + 1, rb_n, re_n);
+      if (ti.total == PAIRS) {
+        const uint32_t p0 = (uint32_t)(PAIRS * t);
+        const uint32_t s0 = seq_base % R, k0 = (seq_base / R) & 1u, d0 = p0 % DS, dk0 = (p0 / DS) & 1u;
+#pragma unroll 1
+        for (uint32_t b4 = 0; b4 < PAIRS; b4 += 4) {
+          {   // lanes 0-3: full[pair b4 + lane]; lanes 4-7: dfree[pair b4 + lane - 4]
+            const uint32_t q = b4 + (lane & 3);
+            uint32_t s = s0 + q, ks = k0, d = d0 + q, kd = dk0 ^ 1u;
+            if (s >= R) { s -= R; ks ^= 1u; }
+            if (s >= R) { s -= R; ks ^= 1u; }
+            if (d >= DS) { d -= DS; kd ^= 1u; }
+            if (d >= DS) { d -= DS; kd ^= 1u; }
+            TLW(1, (int)(p0 + b4) - 128, 0);
+            if (lane < 8) WAIT_U(lane < 4 ? full_u + 8 * s : dfree_u + 8 * d, lane < 4 ? ks : kd, 1);
+            __syncwarp();
+          }
+#ifdef TCAGG_TIMELINE
+          for (int q = 0; q < 4; ++q) { TLW(1, (int)(p0 + b4) + q - 128, 1); TLW(1, (int)(p0 + b4) + q - 128, 2); }
+#endif
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (uint32_t q = 0; q < 4; ++q) {
+              uint32_t s = s0 + b4 + q, d = d0 + b4 + q;
+              if (s >= R) s -= R;
+              if (s >= R) s -= R;
+              if (d >= DS) d -= DS;
+              if (d >= DS) d -= DS;
+              issue_pair(s, d, 0u, true);
+            }
+            *(volatile uint32_t*)&agg_pos = seq_base + b4 + 4;
+          }
+          __syncwarp();
+#ifdef TCAGG_TIMELINE
+          for (int q = 0; q < 4; ++q) TLW(1, (int)(p0 + b4) + q - 128, 3);
+#endif
+        }
+      } else {
+#pragma unroll 1
+        for (int pp = 0; pp < PAIRS; ++pp) do_pair((uint32_t)(PAIRS * t + pp), pp);
+      }
+      seq_base += (uint32_t)ti.total;
+    }
+  } else if (warp == PROJ_WARP) {
+    // ================================================== projection MMA issue ==================================================
+    constexpr uint32_t IP = idesc_of(64, 32, 0, 0), ZHI = desc_hi(64, 2);
+    const uint32_t zh_lo = ((smem_u32(z_hi) & 0x3FFFFu) >> 4) | (1u << 16), zl_lo = ((smem_u32(z_lo) & 0x3FFFFu) >> 4) | (1u << 16);
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
       const uint32_t b = t & 1;
+      TLW(3, t - 8, 0);
       WAIT(&zfull, t & 1, 3);
+      TLW(3, t - 8, 1);
       WAIT(&ofree[b], ((t >> 1) & 1) ^ 1, 4);
+      TLW(3, t - 8, 2);
       tc_fence_after();
       if (elect_one()) {
 #pragma unroll
@@ -379,18 +479,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
         mma_commit(&ofull[b]);
       }
       __syncwarp();
-    };
-    for (int t = 0; t <= T; ++t) {
-      if (t < T) {
-        ti = tile_info(t_begin + t, rb_n, re_n);
-        load_rowptr(t_begin + t + 1, rb_n, re_n);
-        for (int pp = 0; pp < PIPE; ++pp) do_pair((uint32_t)(PAIRS * t + pp), pp);
-      }
-      if (t >= 1) do_proj(t - 1);
-      if (t < T) {
-        for (int pp = PIPE; pp < PAIRS; ++pp) do_pair((uint32_t)(PAIRS * t + pp), pp);
-        seq_base += (uint32_t)ti.total;
-      }
+      TLW(3, t - 8, 3);
     }
   } else if (warp < EPI_WARPS) {
     // ================================================== epilogue ==================================================
@@ -401,6 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     for (int t = 0; t < T; ++t) {
       const uint32_t b = t & 1;
       WAIT(&ofull[b], (t >> 1) & 1, 5);
+      if (warp == 0) TLW(3, t - 8, 4);
       tc_fence_after();
       float v[TILE];
       tmem_ld32(tmem + COL_O + 32 * b + ((uint32_t)(warp * 32) << 16), v);
@@ -417,86 +507,140 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (warp < 2 && lane < 16) {
         const int64_t n0 = (t_begin + t) * TILE;
+        const int live = (int)(N - n0 < TILE ? N - n0 : TILE);
+        float* op = out + n0 * ldo + o;
 #pragma unroll
         for (int n = 0; n < TILE; ++n) {
-          if (n0 + n < N) {
-            float r = v[n] + sb[n * C_OUT + o] + my_bias;
-            r = r > 0.f ? r : r * slope;
-            out[(n0 + n) * ldo + o] = r;
-          }
+          float r = v[n] + sb[n * C_OUT + o] + my_bias;
+          r = r > 0.f ? r : r * slope;
+          if (n < live) *op = r;
+          op += ldo;
         }
       }
+      if (warp == 0) TLW(3, t - 8, 5);
     }
-  } else if (warp < MMA_WARP) {
+  } else if (warp < AGG_WARP) {
     // ================================================== drain ==================================================
     const int set = (warp - EPI_WARPS) >> 2, qd = warp & 3;
     const int half = lane >> 4, c = 16 * qd + (lane & 15);
     const int npairs = PAIRS * T;
-    // this thread's byte offset inside a Z row: head pairs -> 32-bit word of channel c in K block 2 hp + (c >= 32); head 8 -> K block 8
-    const uint32_t ch16 = (uint32_t)(c & 31) >> 2, inner = (uint32_t)(c & 3) * 4;
-    const uint32_t ch16_8 = (uint32_t)c >> 3, inner_8 = (uint32_t)(c & 7) * 2;
-    for (int p = set; p < npairs; p += 2) {
-      const int t = p >> 4, pp = p & 15;
+    // this thread's byte offset inside a Z row: head pairs -> 32-bit word of channel c in K block 2 hp + (c >= 32); head 8 -> K block 8.
+    // The row of pair pp is (pp / 4) * 8 + (pp % 4) + 4 half, so row & 7 = (pp & 3) + 4 half and the swizzle term splits into a
+    // per-thread part and (pp & 3) << 4.
+    const uint32_t hconst = (uint32_t)half * 512;                                  // 4 rows of 128 B
+    const uint32_t sw_pair = ((((uint32_t)(c & 31) >> 2) ^ (4u * half)) << 4) + (uint32_t)(c & 3) * 4 + (uint32_t)(c >> 5) * ZCHUNK + hconst;
+    const uint32_t sw_h8 = ((((uint32_t)c >> 3) ^ (4u * half)) << 4) + (uint32_t)(c & 7) * 2 + 8 * ZCHUNK + hconst;
+    const uint32_t lane_t = tmem + COL_D + ((uint32_t)(qd * 32) << 16);
+    uint32_t ra[32], rb[32];
+    auto dwait_ld = [&](int p, uint32_t (&r)[32]) {
       const uint32_t dslot = (uint32_t)p % DS, dk = (uint32_t)p / DS;
+      if (qd == 0) TLW(2, p - 128, 0);
       WAIT(&dfull[dslot], dk & 1, 6);
+      if (qd == 0) TLW(2, p - 128, 1);
       tc_fence_after();
-      uint32_t rr[32];
-      tmem_ld32_issue(tmem + COL_D + dslot * 32 + ((uint32_t)(qd * 32) << 16), rr);
+      tmem_ld32_issue(lane_t + dslot * 32, r);
+    };
+    auto process = [&](int p, uint32_t (&r)[32], int p_next, uint32_t (&rn)[32]) -> bool {
+      const int t = p >> 4, pp = p & 15;
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&dfree[dslot]);
+      if (lane == 0) mbar_arrive(&dfree[(uint32_t)p % DS]);
+      if (qd == 0) TLW(2, p - 128, 2);
       float z[H];
 #pragma unroll
-      for (int h = 0; h < H; ++h) z[h] = __uint_as_float(rr[h]) + __uint_as_float(rr[16 + h]);
-      if (pp < 2 && t >= 1) {       // first pair of this warp in tile t: the projection of tile t-1 must have finished reading Z
+      for (int h = 0; h < H; ++h) z[h] = __uint_as_float(r[h]) + __uint_as_float(r[16 + h]);
+      // the next pair's accumulator, if it is already complete: its TMEM read overlaps the split below
+      bool pre = false;
+      if (p_next < npairs) {
+        pre = phase_done(&dfull[(uint32_t)p_next % DS], ((uint32_t)p_next / DS) & 1);
+        if (pre) {
+          tc_fence_after();
+          tmem_ld32_issue(lane_t + ((uint32_t)p_next % DS) * 32, rn);
+        }
+      }
+      if (pp < NSETS && t >= 1) {   // first pair of this warp in tile t: the projection of tile t-1 must have finished reading Z
         WAIT(&zfree, (t - 1) & 1, 7);
         tc_fence_after();
       }
-      const int row = (pp >> 2) * 8 + (pp & 3) + 4 * half;
-      const uint32_t rbase = (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128;
-      const uint32_t off = (uint32_t)(c >> 5) * ZCHUNK + rbase + ((ch16 ^ (uint32_t)(row & 7)) << 4) + inner;
+      if (qd == 0) TLW(2, p - 128, 3);
+      const uint32_t rowoff = (uint32_t)(pp >> 2) * 1024 + (uint32_t)(pp & 3) * 128, sx = (uint32_t)(pp & 3) << 4;
+      uint8_t* zh = z_hi + rowoff;
+      uint8_t* zl = z_lo + rowoff;
+      const uint32_t off = sw_pair ^ sx;      // (chunk ^ (row & 7)) << 4: the pair's part of the XOR only touches bits 4-5
 #pragma unroll
       for (int hp = 0; hp < 4; ++hp) {
-        const float a = z[2 * hp], b = z[2 * hp + 1];
-        const uint32_t h2 = pack_bf16x2(a, b);
+        const float za = z[2 * hp], zb = z[2 * hp + 1];
+        const uint32_t h2 = pack_bf16x2(za, zb);
         const float fa = __uint_as_float(h2 << 16), fb = __uint_as_float(h2 & 0xffff0000u);
-        const uint32_t l2 = pack_bf16x2(a - fa, b - fb);
-        *reinterpret_cast<uint32_t*>(z_hi + 2 * hp * ZCHUNK + off) = h2;
-        *reinterpret_cast<uint32_t*>(z_lo + 2 * hp * ZCHUNK + off) = l2;
+        const uint32_t l2 = pack_bf16x2(za - fa, zb - fb);
+        *reinterpret_cast<uint32_t*>(zh + 2 * hp * ZCHUNK + off) = h2;
+        *reinterpret_cast<uint32_t*>(zl + 2 * hp * ZCHUNK + off) = l2;
       }
       {
-        const uint32_t off8 = 8 * ZCHUNK + rbase + ((ch16_8 ^ (uint32_t)(row & 7)) << 4) + inner_8;
-        const __nv_bfloat16 bh = __float2bfloat16_rn(z[8]);
-        const __nv_bfloat16 bl = __float2bfloat16_rn(z[8] - __bfloat162float(bh));
-        *reinterpret_cast<__nv_bfloat16*>(z_hi + off8) = bh;
-        *reinterpret_cast<__nv_bfloat16*>(z_lo + off8) = bl;
+        const uint32_t off8 = sw_h8 ^ sx;
+        const uint32_t h1 = pack_bf16x2(z[8], 0.f);
+        const uint32_t l1 = pack_bf16x2(z[8] - __uint_as_float(h1 << 16), 0.f);
+        *reinterpret_cast<uint16_t*>(zh + off8) = (uint16_t)h1;
+        *reinterpret_cast<uint16_t*>(zl + off8) = (uint16_t)l1;
       }
+      if (qd == 0) TLW(2, p - 128, 4);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&zfull);
+      if (qd == 0) TLW(2, p - 128, 5);
+      if (qd == 0) PROGRESS(34 + set, p + 1);
+      return pre;
+    };
+    // two register sets alternate; `have` = the current set's TMEM read has been issued already
+    bool have = false;
+#pragma unroll 1
+    for (int p = set; p < npairs; p += 2 * NSETS) {
+      if (!have) dwait_ld(p, ra);
+      have = process(p, ra, p + NSETS, rb);
+      const int p2 = p + NSETS;
+      if (p2 < npairs) {
+        if (!have) dwait_ld(p2, rb);
+        have = process(p2, rb, p2 + NSETS, ra);
+      }
     }
   } else {
     // ================================================== producers ==================================================
     const int g = warp - PROD_WARP0;
     const int half = lane >> 4, sl = lane & 15;
     const uint32_t ring_u32 = smem_u32(ring);
+    int* jb = jbuf[g];
+    float cr[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) cr[h] = chs[h];
+    // per-lane constants of the gather: lanes 0-15 copy the 16 chunks (0-7 hi plane, 8-15 lo plane) of the row of slot-lane 2i,
+    // lanes 16-31 of slot-lane 2i+1; slot s = 2 (i & 7) + half of node i >> 3:
+    //   dst = slot base + (i >> 3) 4096 + ((i >> 2) & 1) 1024 + (i & 3) 256 + half 128 + plane 2048 + ((chunk ^ (s & 7)) << 4)
+    const uint32_t ch = (uint32_t)sl;
+    const uint32_t lane_c = (ch >> 3) * XT + (uint32_t)half * 128;
+    const uint32_t c7h = ((ch & 7) ^ (uint32_t)half) << 4;
+    const uint32_t gx0 = lane_c + (c7h ^ 0u), gx1 = lane_c + (c7h ^ 32u), gx2 = lane_c + (c7h ^ 64u), gx3 = lane_c + (c7h ^ 96u);
+    const uint8_t* src0 = Xs + ch * 16;
+    asm volatile("" : "+l"(src0));      // keep the pointer in registers (ptxas otherwise re-derives it from the parameter bank per copy)
+    // per-lane constants of the q tile row (SWIZZLE_64B): 64 B = chunks {q_hi h0-7, q_hi h8 + zeros, q_lo h0-7, q_lo h8 + zeros}
+    const uint32_t qrow = 4 * XT + (uint32_t)half * 1024 + (uint32_t)(sl >> 3) * 512 + (uint32_t)(sl & 7) * 64, qx = (uint32_t)(sl >> 1) & 3u;
+    const uint32_t q0 = qrow + ((0u ^ qx) << 4), q1 = qrow + ((1u ^ qx) << 4), q2 = qrow + ((2u ^ qx) << 4), q3 = qrow + ((3u ^ qx) << 4);
     // work items: (tile t, pair pp, round r) with (16 t + pp) % G == g, in order
     struct Item {
       int valid;
       uint32_t seq;     // ring sequence number
       int r;            // round
       int has;          // this lane's slot is a real neighbour / self slot
-      int j;            // source row of this lane's slot
+      int j;            // source row of this lane's slot (the node's own row when the slot is empty: finite data under q = 0)
       int self;         // source row of this lane's node
       float inv_d;
+      int p;            // pair index (timeline builds only)
     };
     int it_t = -1, it_pp = 0, it_r = 0, it_rounds = 0;
     uint32_t seq_base = 0, next_base = 0;
     TileInfo ti{};
     int rb_n, re_n;
     load_rowptr(t_begin, rb_n, re_n);
-    // first own pair: global pair index p = g
     int64_t p_next = g;
     auto next_item = [&]() {
       Item it{};
@@ -505,7 +649,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       } else {
         if (p_next >= (int64_t)PAIRS * T) return it;     // valid = 0
         const int t = (int)(p_next >> 4);
-        while (it_t < t) {                               // enter the next tile(s): every warp walks every tile
+        if (it_t < t) {                                  // enter the next tile: own pairs are G < 16 apart, so every warp walks every tile
           ++it_t;
           seq_base = next_base;
           ti = tile_info(t_begin + it_t, rb_n, re_n);
@@ -519,14 +663,14 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       }
       const int row = (it_pp >> 2) * 8 + (it_pp & 3) + 4 * half;
       const int rb = __shfl_sync(0xffffffffu, ti.rb, row), d = __shfl_sync(0xffffffffu, ti.d, row);
-      const int64_t node = (t_begin + it_t) * TILE + row;
       it.valid = 1;
+      it.p = it_r == 0 ? PAIRS * it_t + it_pp : -1000;
       it.seq = seq_base + (uint32_t)__shfl_sync(0xffffffffu, ti.excl, it_pp) + (uint32_t)it_r;
       it.r = it_r;
       const int s = 16 * it_r + sl;
       it.has = s < d;
       it.inv_d = d > 0 ? 1.0f / (float)d : 0.f;
-      int self = d > 0 ? (int)node : 0;
+      int self = d > 0 ? (int)((t_begin + it_t) * TILE + row) : 0;
       int j = self;
       if (it.has && s > 0) j = __ldg(nbr + rb + s - 1);
       if (HAS_MAP) {
@@ -537,127 +681,137 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       it.self = self;
       return it;
     };
+    // A parity wait cannot tell "the slot's previous occupant has been consumed" from "the occupant before that has been consumed
+    // and the previous one not even issued" - which happens once a producer runs two ring laps ahead of the issue warp (pairs that
+    // take several rounds spread a warp's items further than R apart).  So the xfree wait of sequence number s is only entered
+    // after the issue warp has issued s - R: from then on the barrier is at most one phase behind the one waited for.
+    auto occupant_issued = [&](uint32_t seq) { return seq < (uint32_t)R || *(volatile uint32_t*)&agg_pos + (uint32_t)R > seq; };
     // stage 1 of an item: ring slot free -> gathers in flight, P row of this lane's slot in flight
-    auto begin = [&](const Item& it, float4 (&Pn)[5]) {
+    auto begin = [&](const Item& it, float4 (&Pn)[3]) {
       const uint32_t slot = it.seq % R, k = it.seq / R;
+      TLW(0, it.p - 128, 0);
+      // the half warp that copies slot-lanes half, half + 2, ... finds their rows contiguous: index (L & 1) 16 + (L >> 1)
+      __syncwarp();
+      jb[(lane & 1) * 16 + (lane >> 1)] = it.j;
+      __syncwarp();
+      const unsigned mask = __ballot_sync(0xffffffffu, it.has);
+      const int cA = __popc(mask & 0xffffu), cB = __popc(mask >> 16);      // slots fill from 0: counts decide which iterations run
+      const int4* jv = reinterpret_cast<const int4*>(jb + half * 16);
+      const int4 j0 = jv[0], j1 = jv[1], j2 = jv[2], j3 = jv[3];
+      const int jr[16] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j2.x, j2.y, j2.z, j2.w, j3.x, j3.y, j3.z, j3.w};
+      while (!occupant_issued(it.seq)) __nanosleep(100);
       WAIT(&xfree[slot], (k & 1) ^ 1, 8);
+      TLW(0, it.p - 128, 1);
       tc_fence_after();
       const uint32_t sbase = ring_u32 + slot * SLOT_BYTES;
-      const unsigned mask = __ballot_sync(0xffffffffu, it.has);
-      const uint32_t ch = (uint32_t)sl;                   // 16-byte chunk of the 256-byte source row: 0-7 hi plane, 8-15 lo plane
-      const uint32_t lane_part = (ch >> 3) * XT;
+      const uint32_t gx[4] = {sbase + gx0, sbase + gx1, sbase + gx2, sbase + gx3};
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if ((mask >> (2 * i)) & 3u) {                     // warp-uniform
-          const int L = 2 * i + half;                     // slot-lane served by this half warp
-          const int jj = __shfl_sync(0xffffffffu, it.j, L);
-          if ((mask >> L) & 1u) {
-            const uint32_t s = (uint32_t)(L & 15);
-            const uint32_t dst = sbase + (uint32_t)(L >> 4) * (2 * XT) + lane_part + (s >> 3) * 1024 + (s & 7) * 128 + (((ch & 7) ^ (s & 7)) << 4);
-            cp_async16(dst, Xs + (size_t)(unsigned)jj * 256 + ch * 16);
-          }
-        }
+        const bool on = i < 8 ? 2 * i < cA : 2 * (i - 8) < cB;             // warp-uniform
+        if (on) cp_async16(gx[i & 3] + (uint32_t)((i >> 3) * (2 * XT) + ((i >> 2) & 1) * 1024 + (i & 3) * 256), src0 + (size_t)(unsigned)jr[i] * 256);
       }
       cp_async_commit();
       if (it.has) {
         const float4* pr = reinterpret_cast<const float4*>(P + (size_t)(unsigned)it.j * PROW);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) Pn[i] = __ldg(pr + i);
+        for (int i = 0; i < 3; ++i) Pn[i] = __ldg(pr + i);
       }
+      TLW(0, it.p - 128, 2);
     };
     // stage 2: soft assignments of the lane's slot -> q tile; the item's gathers have landed -> hand the slot to the MMA warp
-    auto finish = [&](const Item& it, const float4 (&Pc)[5], bool newer_in_flight) {
+    auto finish = [&](const Item& it, const float4 (&Pc)[3], bool newer_in_flight) {
       const uint32_t slot = it.seq % R;
-      uint8_t* qt = ring + slot * SLOT_BYTES + 4 * XT + half * 1024;
-      float4 Pi[5];
-      if (it.r == 0) {
+      TLW(0, it.p - 128, 3);
+      uint8_t* sl_base = ring + slot * SLOT_BYTES;
+      float4 Pi[3];
+      if (it.r == 0) {       // slot 0 of round 0 is the node itself
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < 3; ++i) {
           Pi[i].x = __shfl_sync(0xffffffffu, Pc[i].x, half * 16);
-          Pi[i].y = __shfl_sync(0xffffffffu, Pc[i].y, half * 16);
-          Pi[i].z = __shfl_sync(0xffffffffu, Pc[i].z, half * 16);
-          Pi[i].w = __shfl_sync(0xffffffffu, Pc[i].w, half * 16);
+          if (i < 2) {
+            Pi[i].y = __shfl_sync(0xffffffffu, Pc[i].y, half * 16);
+            Pi[i].z = __shfl_sync(0xffffffffu, Pc[i].z, half * 16);
+            Pi[i].w = __shfl_sync(0xffffffffu, Pc[i].w, half * 16);
+          }
         }
       } else {
         const float4* pr = reinterpret_cast<const float4*>(P + (size_t)(unsigned)it.self * PROW);
 #pragma unroll
-        for (int i = 0; i < 5; ++i) Pi[i] = __ldg(pr + i);
+        for (int i = 0; i < 3; ++i) Pi[i] = __ldg(pr + i);
       }
+      const float pj[H] = {Pc[0].x, Pc[0].y, Pc[0].z, Pc[0].w, Pc[1].x, Pc[1].y, Pc[1].z, Pc[1].w, Pc[2].x};
+      const float pi[H] = {Pi[0].x, Pi[0].y, Pi[0].z, Pi[0].w, Pi[1].x, Pi[1].y, Pi[1].z, Pi[1].w, Pi[2].x};
+      float l[H];
+      float m = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        l[h] = (pj[h] - pi[h]) + cr[h];
+        m = fmaxf(m, l[h]);
+      }
+      const float mb = -m * 1.4426950408889634f;
+      float sum = 0.f;
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(l[h], 1.4426950408889634f, mb)));
+        l[h] = e;
+        sum += e;
+      }
+      const float inv = it.has ? __fdividef(it.inv_d, sum) : 0.f;     // empty slots: q = 0 (their P registers hold finite leftovers)
+#pragma unroll
+      for (int h = 0; h < H; ++h) l[h] *= inv;
       uint32_t qh[5], ql[5];
-      if (it.has) {
-        const float pj[PROW] = {Pc[0].x, Pc[0].y, Pc[0].z, Pc[0].w, Pc[1].x, Pc[1].y, Pc[1].z, Pc[1].w, Pc[2].x, Pc[2].y,
-                                Pc[2].z, Pc[2].w, Pc[3].x, Pc[3].y, Pc[3].z, Pc[3].w, Pc[4].x, Pc[4].y, Pc[4].z, Pc[4].w};
-        const float pi[PROW] = {Pi[0].x, Pi[0].y, Pi[0].z, Pi[0].w, Pi[1].x, Pi[1].y, Pi[1].z, Pi[1].w, Pi[2].x, Pi[2].y,
-                                Pi[2].z, Pi[2].w, Pi[3].x, Pi[3].y, Pi[3].z, Pi[3].w, Pi[4].x, Pi[4].y, Pi[4].z, Pi[4].w};
-        float l[H];
-        float m = -INFINITY;
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          l[h] = ((pj[h] - pi[h]) + (pj[10 + h] - pi[10 + h])) + chs[h];
-          m = fmaxf(m, l[h]);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-          l[h] = __expf(l[h] - m);
-          sum += l[h];
-        }
-        const float inv = it.inv_d / sum;
-#pragma unroll
-        for (int h = 0; h < H; ++h) l[h] *= inv;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t h2 = pack_bf16x2(l[2 * i], l[2 * i + 1]);
-          qh[i] = h2;
-          ql[i] = pack_bf16x2(l[2 * i] - __uint_as_float(h2 << 16), l[2 * i + 1] - __uint_as_float(h2 & 0xffff0000u));
-        }
-        const uint32_t h8 = pack_bf16x2(l[8], 0.f);
-        qh[4] = h8;
-        ql[4] = pack_bf16x2(l[8] - __uint_as_float(h8 << 16), 0.f);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 5; ++i) qh[i] = ql[i] = 0u;
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t h2 = pack_bf16x2(l[2 * i], l[2 * i + 1]);
+        qh[i] = h2;
+        ql[i] = pack_bf16x2(l[2 * i] - __uint_as_float(h2 << 16), l[2 * i + 1] - __uint_as_float(h2 & 0xffff0000u));
       }
-      // row sl of the SWIZZLE_64B tile: 64 B = chunks {q_hi h0-7, q_hi h8 + zeros, q_lo h0-7, q_lo h8 + zeros}
-      uint8_t* qrow = qt + (sl >> 3) * 512 + (sl & 7) * 64;
-      const uint32_t x = (uint32_t)(sl >> 1) & 3u;
-      *reinterpret_cast<uint4*>(qrow + ((0u ^ x) << 4)) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
-      *reinterpret_cast<uint4*>(qrow + ((1u ^ x) << 4)) = make_uint4(qh[4], 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(qrow + ((2u ^ x) << 4)) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
-      *reinterpret_cast<uint4*>(qrow + ((3u ^ x) << 4)) = make_uint4(ql[4], 0u, 0u, 0u);
+      qh[4] = pack_bf16x2(l[8], 0.f);
+      ql[4] = pack_bf16x2(l[8] - __uint_as_float(qh[4] << 16), 0.f);
+      *reinterpret_cast<uint4*>(sl_base + q0) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+      *reinterpret_cast<uint4*>(sl_base + q1) = make_uint4(qh[4], 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(sl_base + q2) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+      *reinterpret_cast<uint4*>(sl_base + q3) = make_uint4(ql[4], 0u, 0u, 0u);
+      TLW(0, it.p - 128, 4);
       if (newer_in_flight) cp_async_wait<1>();
       else cp_async_wait<0>();
+      TLW(0, it.p - 128, 5);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[slot]);
+      TLW(0, it.p - 128, 6);
+      PROGRESS(40 + g, it.seq + 1);
     };
 
-    Item cur = next_item();            // indices loaded; gathers not yet issued
-    Item prev{};
-    float4 Pa[5], Pb[5];               // P rows of the item in stage 2 / of the item entering stage 1
+    // three-stage software pipeline, one call site per stage (the loop body has to stay inside the instruction cache):
+    //   iteration k: index loads of item k | gathers + P loads of item k-1 | soft assignments + hand-over of item k-2
+    Item a{}, b{};                     // a: indices in flight; b: gathers in flight
+    float4 Pa[3], Pb[3];               // P rows of b / of a
 #pragma unroll
-    for (int i = 0; i < 5; ++i) Pa[i] = Pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    while (cur.valid || prev.valid) {
-      Item nxt{};
-      if (cur.valid) nxt = next_item();          // index loads of the following item go out first
+    for (int i = 0; i < 3; ++i) Pa[i] = Pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (;;) {
+      const Item n = next_item();
       // a warp never blocks on a ring slot while it holds an item that the MMA warp is waiting for (the slot's previous
       // occupant may be behind that very item in the MMA warp's order when pairs take several rounds)
-      if (cur.valid && prev.valid && !phase_done(&xfree[cur.seq % R], ((cur.seq / R) & 1) ^ 1)) {
-        finish(prev, Pa, false);
-        prev.valid = 0;
+      const bool early = a.valid && b.valid && !(occupant_issued(a.seq) && phase_done(&xfree[a.seq % R], ((a.seq / R) & 1) ^ 1));
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        if (a.valid && pass == (early ? 1 : 0)) begin(a, Pb);
+        if (b.valid && pass == 0) finish(b, Pa, a.valid && !early);
       }
-      if (cur.valid) begin(cur, Pb);
-      if (prev.valid) finish(prev, Pa, cur.valid != 0);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) Pa[i] = Pb[i];
-      prev = cur;
-      cur = nxt;
+      for (int i = 0; i < 3; ++i) Pa[i] = Pb[i];
+      b = a;
+      a = n;
+      if (!a.valid && !b.valid) break;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == AGG_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, TMEM_COLS);
   }
@@ -731,6 +885,11 @@ int feast_fwd_tcagg(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
   return GEOBI_OK;
 }
 
+#ifdef TCAGG_TIMELINE
+extern "C" __attribute__((visibility("default"))) int geobi_debug_tcagg_timeline(long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, tcagg::g_tl, sizeof(long long) * 4 * 64 * 8);
+}
+#endif
 #ifdef TCAGG_DEBUG
 extern "C" __attribute__((visibility("default"))) int geobi_debug_tcagg(unsigned int* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, tcagg::g_dbg, sizeof(unsigned int) * 64);

@@ -20,10 +20,19 @@ def debug_dump(label):
     lib.geobi_debug_tcagg(buf)
     v = np.array(buf[:], dtype=np.uint32)
     if v[63]:
-        print(f"[{label}] STUCK WAITS (cta0 warps 0..31 | another cta):")
-        for i in range(63):
+        print(f"[{label}] STUCK: cta {int(v[63]) - 1}; per warp (tag, parity, barrier word offset >> 3):")
+        for i in range(32):
             if v[i]:
-                print(f"   {'cta0' if i < 32 else 'ctaX'} warp {i % 32}: {TAGS.get(int(v[i]) & 0xffff, '?')} parity {(int(v[i]) >> 16) & 1}")
+                b = (int(v[i]) >> 8) & 0xffff
+                names = [("full", 14), ("xfree", 14), ("dfull", 9), ("dfree", 9), ("zfull", 1), ("zfree", 1), ("ofull", 2), ("ofree", 2)]
+                nm = "?"
+                for name, cnt in names:
+                    if b < cnt:
+                        nm = f"{name}[{b}]"
+                        break
+                    b -= cnt
+                print(f"   warp {i}: {TAGS.get(int(v[i]) & 0xff, '?')} {nm} parity {int(v[i]) >> 31}")
+        print(f"   cta0 progress: agg last seq+1 {int(v[32]) & 0xffff} (pair {int(v[32]) >> 16}), drain sets pairs done {int(v[34])}, {int(v[35])}, producers last seq+1 finished {[int(x) for x in v[40:50]]}")
         return True
     return False
 
@@ -110,3 +119,38 @@ if stage in ("big", "all"):
         for label, (mean, mn, layer) in res.items():
             print(f"[bench-{name}] {label}: kernel mean {mean:.4f} ms (min {mn:.4f}), whole layer {layer:.4f} ms, "
                   f"algorithmic {alg / 1e6:.1f} MB -> {alg / mean / 1e6:.1f} GB/s = {alg / mean / 1e6 / bench.peaks()[0]:.4f} of peak", flush=True)
+
+if hasattr(lib, "geobi_debug_tcagg_timeline"):
+    # the last launch was the vertex graph with the fp32agg switch restored -> rerun one tcagg launch on the facet graph
+    n = df.x.size(0)
+    g = ops.csr_from_coo(df.edge_index, n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+    x = torch.randn(n, 64, device=dev)
+    ops.feast_fwd(x, g, *P, 0.2, precision=ops.PREC_BF16X3)
+    torch.cuda.synchronize()
+    buf = (ctypes.c_longlong * (4 * 64 * 8))()
+    lib.geobi_debug_tcagg_timeline(buf)
+    tl = np.array(buf[:], dtype=np.int64).reshape(4, 64, 8)
+    t0 = tl[1, 0, 0]
+    np.set_printoptions(linewidth=220, suppress=True)
+    def d(a, b):
+        return (b - a)
+    pr, mm, dr, ti = tl[0], tl[1], tl[2], tl[3]
+    print("pair period (MMA issue to issue), clk: mean %.0f" % np.diff(mm[:, 3]).mean())
+    print("producer per pair, clk: xfree wait %.0f | gather+P issue %.0f | begin->finish gap %.0f | softmax+q %.0f | cp.async wait %.0f | fence+arrive %.0f | total %.0f" % (
+        d(pr[:, 0], pr[:, 1]).mean(), d(pr[:, 1], pr[:, 2]).mean(), d(pr[:, 2], pr[:, 3]).mean(), d(pr[:, 3], pr[:, 4]).mean(), d(pr[:, 4], pr[:, 5]).mean(),
+        d(pr[:, 5], pr[:, 6]).mean(), d(pr[:, 0], pr[:, 6]).mean()))
+    print("mma per pair, clk: full wait %.0f | dfree wait %.0f | issue %.0f ; producer arrive -> mma sees full %.0f" % (
+        d(mm[:, 0], mm[:, 1]).mean(), d(mm[:, 1], mm[:, 2]).mean(), d(mm[:, 2], mm[:, 3]).mean(), d(pr[:, 6], mm[:, 1]).mean()))
+    print("drain per pair, clk: dfull wait %.0f | ld %.0f | zfree wait %.0f | split+store %.0f | fence+arrive %.0f | total busy %.0f ; mma issue -> drain sees dfull %.0f" % (
+        d(dr[:, 0], dr[:, 1]).mean(), d(dr[:, 1], dr[:, 2]).mean(), d(dr[:, 2], dr[:, 3]).mean(), d(dr[:, 3], dr[:, 4]).mean(), d(dr[:, 4], dr[:, 5]).mean(),
+        d(dr[:, 1], dr[:, 5]).mean(), d(mm[:, 3], dr[:, 1]).mean()))
+    tt = ti[:56]
+    print("tile, clk: period %.0f | zfull wait %.0f | ofree wait %.0f | proj issue %.0f | proj issue -> epilogue sees ofull %.0f | epilogue %.0f" % (
+        np.diff(tt[:, 3]).mean(), d(tt[:, 0], tt[:, 1]).mean(), d(tt[:, 1], tt[:, 2]).mean(), d(tt[:, 2], tt[:, 3]).mean(), d(tt[:, 3], tt[:, 4]).mean(),
+        d(tt[:, 4], tt[:, 5]).mean()))
+    print("first 3 tiles of the window, relative clk per pair: [prod begin, xfree ok, issued, fin start, q done, cp done, arrived | mma full ok, dfree ok, issued | drain dfull ok, ld done, zfree ok, stored, arrived]")
+    for i in range(48):
+        print(i + 128, (pr[i, :7] - t0).tolist(), (mm[i, 1:4] - t0).tolist(), (dr[i, 1:6] - t0).tolist())
+    print("tiles: [zfull wait start, zfull ok, ofree ok, proj issued, epi ofull ok, epi done]")
+    for i in range(4):
+        print(i + 8, (ti[i, :6] - t0).tolist())
