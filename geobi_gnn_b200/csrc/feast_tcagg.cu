@@ -86,6 +86,18 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const u
                "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -99,12 +111,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or ~10 ms pass) instead of
+// re-issuing the probe (ncu on the first version: a third of all issued warp instructions sat in wait loops)
 __device__ __forceinline__ void mbar_wait_u(uint32_t addr, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-  } while (!done);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_LOOP_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(addr), "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 // non-blocking probe of an mbarrier phase (warp-uniform answer: lane 0 tests, the result is broadcast)
 __device__ __forceinline__ bool phase_done(uint64_t* bar, uint32_t parity) {
@@ -116,7 +134,7 @@ __device__ __forceinline__ bool phase_done(uint64_t* bar, uint32_t parity) {
 
 #ifdef TCAGG_TIMELINE
 // per-role clock64() stamps of CTA 0 for pairs [128, 192) / tiles [8, 72): g_tl[role][index][event]
-__device__ long long g_tl[4 * 64 * 8];
+__device__ long long g_tl[5 * 64 * 8];
 #define TLW(role, idx, ev) do { const int _i = (idx); if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && _i >= 0 && _i < 64) g_tl[((role) * 64 + _i) * 8 + (ev)] = clock64(); } while (0)
 #else
 #define TLW(role, idx, ev) do { } while (0)
@@ -152,7 +170,7 @@ __device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, int tag
 #define WAIT_U(addr, parity, tag) wait_dbg(reinterpret_cast<uint64_t*>(__cvta_shared_to_generic(addr)), parity, (tag) | ((int)(((addr) - smem_u32(bars)) >> 3) << 8))
 #else
 #define PROGRESS(idx, val) do { } while (0)
-#define WAIT(bar, parity, tag) mbar_wait(bar, parity)
+#define WAIT(bar, parity, tag) mbar_wait_u(smem_u32(bar), parity)
 #define WAIT_U(addr, parity, tag) mbar_wait_u(addr, parity)
 #endif
 __device__ __forceinline__ void mma_commit_u(uint32_t bar_addr) {
@@ -325,6 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
   // rounds = max(1, ceil(max(d_A, d_B) / 16)) ring slots in sequence (d = neighbours + 1; nodes past N have d = 0).
   struct TileInfo {
     int rb, d;          // lane = tile row: first CSR entry and slot count of node base + lane
+    float inv_d;        // lane = tile row: 1 / d (0 for rows past N)
     int rounds, excl;   // lane = pair (lanes 0-15): ring slots of the pair and their exclusive prefix inside the tile
     int total;
   };
@@ -333,6 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     const int64_t node = tile * TILE + lane;
     ti.rb = rb_in;
     ti.d = node < N ? re_in - rb_in + 1 : 0;
+    ti.inv_d = ti.d > 0 ? __frcp_rn((float)ti.d) : 0.f;
     const int rA = ((lane >> 2) & 3) * 8 + (lane & 3);
     const int dA = __shfl_sync(0xffffffffu, ti.d, rA), dB = __shfl_sync(0xffffffffu, ti.d, rA + 4);
     int rounds = lane < PAIRS ? max(1, (max(dA, dB) + 15) >> 4) : 0;
@@ -492,29 +512,35 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       WAIT(&ofull[b], (t >> 1) & 1, 5);
       if (warp == 0) TLW(3, t - 8, 4);
       tc_fence_after();
-      float v[TILE];
-      tmem_ld32(tmem + COL_O + 32 * b + ((uint32_t)(warp * 32) << 16), v);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ofree[b]);
-#pragma unroll
-      for (int n = 0; n < TILE; ++n) v[n] += __shfl_xor_sync(0xffffffffu, v[n], 16);
       float* sb = stage + (t & 1) * (TILE * C_OUT);
-      if (warp >= 2 && lane < 16) {
+      const int64_t n0 = (t_begin + t) * TILE;
+      const int live = (int)(N - n0 < TILE ? N - n0 : TILE);
+      // two passes of 16 nodes (32 accumulator registers at once do not fit under the 80-register cap of a 768-thread CTA)
+#pragma unroll 1
+      for (int hcol = 0; hcol < 2; ++hcol) {
+        float v[16];
+        tmem_ld16(tmem + COL_O + 32 * b + 16 * hcol + ((uint32_t)(warp * 32) << 16), v);
+        if (hcol == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ofree[b]);
+        }
 #pragma unroll
-        for (int n = 0; n < TILE; ++n) sb[n * C_OUT + o] = v[n];
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (warp < 2 && lane < 16) {
-        const int64_t n0 = (t_begin + t) * TILE;
-        const int live = (int)(N - n0 < TILE ? N - n0 : TILE);
-        float* op = out + n0 * ldo + o;
+        for (int n = 0; n < 16; ++n) v[n] += __shfl_xor_sync(0xffffffffu, v[n], 16);
+        if (warp >= 2 && lane < 16) {
 #pragma unroll
-        for (int n = 0; n < TILE; ++n) {
-          float r = v[n] + sb[n * C_OUT + o] + my_bias;
-          r = r > 0.f ? r : r * slope;
-          if (n < live) *op = r;
-          op += ldo;
+          for (int n = 0; n < 16; ++n) sb[(16 * hcol + n) * C_OUT + o] = v[n];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp < 2 && lane < 16) {
+          float* op = out + (n0 + 16 * hcol) * ldo + o;
+#pragma unroll
+          for (int n = 0; n < 16; ++n) {
+            float r = v[n] + sb[(16 * hcol + n) * C_OUT + o] + my_bias;
+            r = r > 0.f ? r : r * slope;
+            if (16 * hcol + n < live) *op = r;
+            op += ldo;
+          }
         }
       }
       if (warp == 0) TLW(3, t - 8, 5);
@@ -610,72 +636,80 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     const int half = lane >> 4, sl = lane & 15;
     const uint32_t ring_u32 = smem_u32(ring);
     int* jb = jbuf[g];
-    float cr[H];
-#pragma unroll
-    for (int h = 0; h < H; ++h) cr[h] = chs[h];
     // per-lane constants of the gather: lanes 0-15 copy the 16 chunks (0-7 hi plane, 8-15 lo plane) of the row of slot-lane 2i,
     // lanes 16-31 of slot-lane 2i+1; slot s = 2 (i & 7) + half of node i >> 3:
     //   dst = slot base + (i >> 3) 4096 + ((i >> 2) & 1) 1024 + (i & 3) 256 + half 128 + plane 2048 + ((chunk ^ (s & 7)) << 4)
     const uint32_t ch = (uint32_t)sl;
     const uint32_t lane_c = (ch >> 3) * XT + (uint32_t)half * 128;
     const uint32_t c7h = ((ch & 7) ^ (uint32_t)half) << 4;
-    const uint32_t gx0 = lane_c + (c7h ^ 0u), gx1 = lane_c + (c7h ^ 32u), gx2 = lane_c + (c7h ^ 64u), gx3 = lane_c + (c7h ^ 96u);
     const uint8_t* src0 = Xs + ch * 16;
     asm volatile("" : "+l"(src0));      // keep the pointer in registers (ptxas otherwise re-derives it from the parameter bank per copy)
     // per-lane constants of the q tile row (SWIZZLE_64B): 64 B = chunks {q_hi h0-7, q_hi h8 + zeros, q_lo h0-7, q_lo h8 + zeros}
     const uint32_t qrow = 4 * XT + (uint32_t)half * 1024 + (uint32_t)(sl >> 3) * 512 + (uint32_t)(sl & 7) * 64, qx = (uint32_t)(sl >> 1) & 3u;
-    const uint32_t q0 = qrow + ((0u ^ qx) << 4), q1 = qrow + ((1u ^ qx) << 4), q2 = qrow + ((2u ^ qx) << 4), q3 = qrow + ((3u ^ qx) << 4);
     // work items: (tile t, pair pp, round r) with (16 t + pp) % G == g, in order
-    struct Item {
-      int valid;
-      uint32_t seq;     // ring sequence number
-      int r;            // round
-      int has;          // this lane's slot is a real neighbour / self slot
-      int j;            // source row of this lane's slot (the node's own row when the slot is empty: finite data under q = 0)
-      int self;         // source row of this lane's node
+    struct Item {         // five registers: three items are live across the software pipeline
+      uint32_t seq;       // ring sequence number
+      uint32_t bits;      // slot (0-7) | xfree parity (8) | valid (9) | round 0 (10) | lane's slot is a real neighbour / self slot (11)
+      int j;              // source row of this lane's slot (the node's own row when the slot is empty: finite data under q = 0)
+      int self;           // source row of this lane's node
       float inv_d;
-      int p;            // pair index (timeline builds only)
+#ifdef TCAGG_TIMELINE
+      int p;              // pair index
+#endif
+      __device__ __forceinline__ bool valid() const { return (bits >> 9) & 1u; }
+      __device__ __forceinline__ uint32_t slot() const { return bits & 0xffu; }
+      __device__ __forceinline__ uint32_t par() const { return (bits >> 8) & 1u; }
+      __device__ __forceinline__ bool first() const { return (bits >> 10) & 1u; }
+      __device__ __forceinline__ bool has() const { return (bits >> 11) & 1u; }
     };
+#ifdef TCAGG_TIMELINE
+#define ITEM_P(it) ((it).p)
+#else
+#define ITEM_P(it) (-1000)
+#endif
+    const int n_items = PAIRS * T;
+    const int tile0 = (int)(t_begin * TILE);             // N < 2^31 (rowptr is int32)
     int it_t = -1, it_pp = 0, it_r = 0, it_rounds = 0;
     uint32_t seq_base = 0, next_base = 0;
     TileInfo ti{};
     int rb_n, re_n;
     load_rowptr(t_begin, rb_n, re_n);
-    int64_t p_next = g;
+    int p_next = g;
     auto next_item = [&]() {
       Item it{};
       if (it_t >= 0 && it_r + 1 < it_rounds) {
         ++it_r;
       } else {
-        if (p_next >= (int64_t)PAIRS * T) return it;     // valid = 0
-        const int t = (int)(p_next >> 4);
-        if (it_t < t) {                                  // enter the next tile: own pairs are G < 16 apart, so every warp walks every tile
+        if (p_next >= n_items) return it;                // bits = 0: not valid
+        if (it_t < (p_next >> 4)) {                      // enter the next tile: own pairs are G < 16 apart, so every warp walks every tile
           ++it_t;
           seq_base = next_base;
           ti = tile_info(t_begin + it_t, rb_n, re_n);
           load_rowptr(t_begin + it_t + 1, rb_n, re_n);
           next_base = seq_base + (uint32_t)ti.total;
         }
-        it_pp = (int)(p_next & 15);
+        it_pp = p_next & 15;
         it_r = 0;
         it_rounds = __shfl_sync(0xffffffffu, ti.rounds, it_pp);
         p_next += G;
       }
       const int row = (it_pp >> 2) * 8 + (it_pp & 3) + 4 * half;
       const int rb = __shfl_sync(0xffffffffu, ti.rb, row), d = __shfl_sync(0xffffffffu, ti.d, row);
-      it.valid = 1;
+      it.inv_d = __shfl_sync(0xffffffffu, ti.inv_d, row);
+#ifdef TCAGG_TIMELINE
       it.p = it_r == 0 ? PAIRS * it_t + it_pp : -1000;
+#endif
       it.seq = seq_base + (uint32_t)__shfl_sync(0xffffffffu, ti.excl, it_pp) + (uint32_t)it_r;
-      it.r = it_r;
+      const uint32_t k = it.seq / (uint32_t)R;
       const int s = 16 * it_r + sl;
-      it.has = s < d;
-      it.inv_d = d > 0 ? 1.0f / (float)d : 0.f;
-      int self = d > 0 ? (int)((t_begin + it_t) * TILE + row) : 0;
+      const bool has = s < d;
+      it.bits = (it.seq - k * (uint32_t)R) | (((k & 1u) ^ 1u) << 8) | (1u << 9) | ((it_r == 0 ? 1u : 0u) << 10) | ((has ? 1u : 0u) << 11);
+      int self = d > 0 ? tile0 + it_t * TILE + row : 0;
       int j = self;
-      if (it.has && s > 0) j = __ldg(nbr + rb + s - 1);
+      if (has && s > 0) j = __ldg(nbr + rb + s - 1);
       if (HAS_MAP) {
         if (d > 0) self = __ldg(row_map + self);
-        j = (it.has && s > 0) ? __ldg(row_map + j) : self;
+        j = (has && s > 0) ? __ldg(row_map + j) : self;
       }
       it.j = j;
       it.self = self;
@@ -687,65 +721,74 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     // after the issue warp has issued s - R: from then on the barrier is at most one phase behind the one waited for.
     auto occupant_issued = [&](uint32_t seq) { return seq < (uint32_t)R || *(volatile uint32_t*)&agg_pos + (uint32_t)R > seq; };
     // stage 1 of an item: ring slot free -> gathers in flight, P row of this lane's slot in flight
-    auto begin = [&](const Item& it, float4 (&Pn)[3]) {
-      const uint32_t slot = it.seq % R, k = it.seq / R;
-      TLW(0, it.p - 128, 0);
+    auto begin = [&](const Item& it) {
+      const uint32_t slot = it.slot();
+      TLW(0, ITEM_P(it) - 128, 0);
       // the half warp that copies slot-lanes half, half + 2, ... finds their rows contiguous: index (L & 1) 16 + (L >> 1)
       __syncwarp();
       jb[(lane & 1) * 16 + (lane >> 1)] = it.j;
       __syncwarp();
-      const unsigned mask = __ballot_sync(0xffffffffu, it.has);
+      const unsigned mask = __ballot_sync(0xffffffffu, it.has());
       const int cA = __popc(mask & 0xffffu), cB = __popc(mask >> 16);      // slots fill from 0: counts decide which iterations run
       const int4* jv = reinterpret_cast<const int4*>(jb + half * 16);
       const int4 j0 = jv[0], j1 = jv[1], j2 = jv[2], j3 = jv[3];
       const int jr[16] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j2.x, j2.y, j2.z, j2.w, j3.x, j3.y, j3.z, j3.w};
-      while (!occupant_issued(it.seq)) __nanosleep(100);
-      WAIT(&xfree[slot], (k & 1) ^ 1, 8);
-      TLW(0, it.p - 128, 1);
+      while (!occupant_issued(it.seq)) __nanosleep(256);
+      WAIT(&xfree[slot], it.par(), 8);
+      TLW(0, ITEM_P(it) - 128, 1);
       tc_fence_after();
       const uint32_t sbase = ring_u32 + slot * SLOT_BYTES;
-      const uint32_t gx[4] = {sbase + gx0, sbase + gx1, sbase + gx2, sbase + gx3};
+      const uint32_t gb = sbase + lane_c;
+      const uint32_t gx[4] = {gb + (c7h ^ 0u), gb + (c7h ^ 32u), gb + (c7h ^ 64u), gb + (c7h ^ 96u)};
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const bool on = i < 8 ? 2 * i < cA : 2 * (i - 8) < cB;             // warp-uniform
         if (on) cp_async16(gx[i & 3] + (uint32_t)((i >> 3) * (2 * XT) + ((i >> 2) & 1) * 1024 + (i & 3) * 256), src0 + (size_t)(unsigned)jr[i] * 256);
       }
-      cp_async_commit();
-      if (it.has) {
-        const float4* pr = reinterpret_cast<const float4*>(P + (size_t)(unsigned)it.j * PROW);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) Pn[i] = __ldg(pr + i);
+      // the lane's P row (48 B) travels through its own (still unused) q row of the slot: read back in stage 2
+      if (it.has()) {
+        const uint8_t* pr = reinterpret_cast<const uint8_t*>(P + (size_t)(unsigned)it.j * PROW);
+        const uint32_t pdst = sbase + qrow;
+        cp_async16(pdst, pr);
+        cp_async16(pdst + 16, pr + 16);
+        cp_async16(pdst + 32, pr + 32);
       }
-      TLW(0, it.p - 128, 2);
+      cp_async_commit();
+      TLW(0, ITEM_P(it) - 128, 2);
     };
     // stage 2: soft assignments of the lane's slot -> q tile; the item's gathers have landed -> hand the slot to the MMA warp
-    auto finish = [&](const Item& it, const float4 (&Pc)[3], bool newer_in_flight) {
-      const uint32_t slot = it.seq % R;
-      TLW(0, it.p - 128, 3);
+    auto finish = [&](const Item& it, bool newer_in_flight) {
+      const uint32_t slot = it.slot();
+      TLW(0, ITEM_P(it) - 128, 3);
       uint8_t* sl_base = ring + slot * SLOT_BYTES;
-      float4 Pi[3];
-      if (it.r == 0) {       // slot 0 of round 0 is the node itself
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          Pi[i].x = __shfl_sync(0xffffffffu, Pc[i].x, half * 16);
-          if (i < 2) {
-            Pi[i].y = __shfl_sync(0xffffffffu, Pc[i].y, half * 16);
-            Pi[i].z = __shfl_sync(0xffffffffu, Pc[i].z, half * 16);
-            Pi[i].w = __shfl_sync(0xffffffffu, Pc[i].w, half * 16);
-          }
-        }
+      if (newer_in_flight) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      TLW(0, ITEM_P(it) - 128, 5);
+      __syncwarp();            // the self slot's P row (lane 0 / 16 of the node's half warp) was written by another lane's copy
+      const float4* pq = reinterpret_cast<const float4*>(sl_base + qrow);
+      const float4 Pc0 = pq[0], Pc1 = pq[1];
+      const float pc8 = reinterpret_cast<const float*>(pq)[8];
+      float4 Pi0, Pi1;
+      float pi8;
+      if (it.first()) {      // slot 0 of round 0 is the node itself
+        const float4* ps = reinterpret_cast<const float4*>(sl_base + 4 * XT + (uint32_t)half * 1024);
+        Pi0 = ps[0];
+        Pi1 = ps[1];
+        pi8 = reinterpret_cast<const float*>(ps)[8];
       } else {
         const float4* pr = reinterpret_cast<const float4*>(P + (size_t)(unsigned)it.self * PROW);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) Pi[i] = __ldg(pr + i);
+        Pi0 = __ldg(pr);
+        Pi1 = __ldg(pr + 1);
+        pi8 = __ldg(reinterpret_cast<const float*>(pr) + 8);
       }
-      const float pj[H] = {Pc[0].x, Pc[0].y, Pc[0].z, Pc[0].w, Pc[1].x, Pc[1].y, Pc[1].z, Pc[1].w, Pc[2].x};
-      const float pi[H] = {Pi[0].x, Pi[0].y, Pi[0].z, Pi[0].w, Pi[1].x, Pi[1].y, Pi[1].z, Pi[1].w, Pi[2].x};
+      __syncwarp();            // every lane has read the P rows before any q row overwrites them
+      const float pj[H] = {Pc0.x, Pc0.y, Pc0.z, Pc0.w, Pc1.x, Pc1.y, Pc1.z, Pc1.w, pc8};
+      const float pi[H] = {Pi0.x, Pi0.y, Pi0.z, Pi0.w, Pi1.x, Pi1.y, Pi1.z, Pi1.w, pi8};
       float l[H];
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = (pj[h] - pi[h]) + cr[h];
+        l[h] = (pj[h] - pi[h]) + chs[h];
         m = fmaxf(m, l[h]);
       }
       const float mb = -m * 1.4426950408889634f;
@@ -757,7 +800,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
         l[h] = e;
         sum += e;
       }
-      const float inv = it.has ? __fdividef(it.inv_d, sum) : 0.f;     // empty slots: q = 0 (their P registers hold finite leftovers)
+      const float inv = it.has() ? __fdividef(it.inv_d, sum) : 0.f;     // empty slots: q = 0 (their P registers hold finite leftovers)
 #pragma unroll
       for (int h = 0; h < H; ++h) l[h] *= inv;
       uint32_t qh[5], ql[5];
@@ -769,43 +812,41 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       }
       qh[4] = pack_bf16x2(l[8], 0.f);
       ql[4] = pack_bf16x2(l[8] - __uint_as_float(qh[4] << 16), 0.f);
-      *reinterpret_cast<uint4*>(sl_base + q0) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
-      *reinterpret_cast<uint4*>(sl_base + q1) = make_uint4(qh[4], 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(sl_base + q2) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
-      *reinterpret_cast<uint4*>(sl_base + q3) = make_uint4(ql[4], 0u, 0u, 0u);
-      TLW(0, it.p - 128, 4);
-      if (newer_in_flight) cp_async_wait<1>();
-      else cp_async_wait<0>();
-      TLW(0, it.p - 128, 5);
+      uint8_t* qr = sl_base + qrow;
+      *reinterpret_cast<uint4*>(qr + ((0u ^ qx) << 4)) = make_uint4(qh[0], qh[1], qh[2], qh[3]);
+      *reinterpret_cast<uint4*>(qr + ((1u ^ qx) << 4)) = make_uint4(qh[4], 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(qr + ((2u ^ qx) << 4)) = make_uint4(ql[0], ql[1], ql[2], ql[3]);
+      *reinterpret_cast<uint4*>(qr + ((3u ^ qx) << 4)) = make_uint4(ql[4], 0u, 0u, 0u);
+      TLW(0, ITEM_P(it) - 128, 4);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[slot]);
-      TLW(0, it.p - 128, 6);
+      TLW(0, ITEM_P(it) - 128, 6);
       PROGRESS(40 + g, it.seq + 1);
     };
 
     // three-stage software pipeline, one call site per stage (the loop body has to stay inside the instruction cache):
     //   iteration k: index loads of item k | gathers + P loads of item k-1 | soft assignments + hand-over of item k-2
     Item a{}, b{};                     // a: indices in flight; b: gathers in flight
-    float4 Pa[3], Pb[3];               // P rows of b / of a
-#pragma unroll
-    for (int i = 0; i < 3; ++i) Pa[i] = Pb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
     for (;;) {
+      TLW(4, ITEM_P(a) - 128, 0);        // stamps of the iteration that begins item a
       const Item n = next_item();
+      TLW(4, ITEM_P(a) - 128, 1);
       // a warp never blocks on a ring slot while it holds an item that the MMA warp is waiting for (the slot's previous
       // occupant may be behind that very item in the MMA warp's order when pairs take several rounds)
-      const bool early = a.valid && b.valid && !(occupant_issued(a.seq) && phase_done(&xfree[a.seq % R], ((a.seq / R) & 1) ^ 1));
+      const bool early = a.valid() && b.valid() && !(occupant_issued(a.seq) && phase_done(&xfree[a.slot()], a.par()));
+      TLW(4, ITEM_P(a) - 128, 2);
+      if (early) TLW(4, ITEM_P(a) - 128, 3);
 #pragma unroll 1
       for (int pass = 0; pass < 2; ++pass) {
-        if (a.valid && pass == (early ? 1 : 0)) begin(a, Pb);
-        if (b.valid && pass == 0) finish(b, Pa, a.valid && !early);
+        if (a.valid() && pass == (early ? 1 : 0)) begin(a);
+        if (b.valid() && pass == 0) finish(b, a.valid() && !early);
       }
-#pragma unroll
-      for (int i = 0; i < 3; ++i) Pa[i] = Pb[i];
+      TLW(4, ITEM_P(a) - 128, 4);
       b = a;
       a = n;
-      if (!a.valid && !b.valid) break;
+      if (!a.valid() && !b.valid()) break;
     }
   }
 
@@ -887,7 +928,7 @@ int feast_fwd_tcagg(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
 
 #ifdef TCAGG_TIMELINE
 extern "C" __attribute__((visibility("default"))) int geobi_debug_tcagg_timeline(long long* host_out) {
-  return (int)cudaMemcpyFromSymbol(host_out, tcagg::g_tl, sizeof(long long) * 4 * 64 * 8);
+  return (int)cudaMemcpyFromSymbol(host_out, tcagg::g_tl, sizeof(long long) * 5 * 64 * 8);
 }
 #endif
 #ifdef TCAGG_DEBUG

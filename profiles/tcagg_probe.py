@@ -127,9 +127,9 @@ if hasattr(lib, "geobi_debug_tcagg_timeline"):
     x = torch.randn(n, 64, device=dev)
     ops.feast_fwd(x, g, *P, 0.2, precision=ops.PREC_BF16X3)
     torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (4 * 64 * 8))()
+    buf = (ctypes.c_longlong * (5 * 64 * 8))()
     lib.geobi_debug_tcagg_timeline(buf)
-    tl = np.array(buf[:], dtype=np.int64).reshape(4, 64, 8)
+    tl = np.array(buf[:], dtype=np.int64).reshape(5, 64, 8)
     t0 = tl[1, 0, 0]
     np.set_printoptions(linewidth=220, suppress=True)
     def d(a, b):
@@ -139,6 +139,9 @@ if hasattr(lib, "geobi_debug_tcagg_timeline"):
     print("producer per pair, clk: xfree wait %.0f | gather+P issue %.0f | begin->finish gap %.0f | softmax+q %.0f | cp.async wait %.0f | fence+arrive %.0f | total %.0f" % (
         d(pr[:, 0], pr[:, 1]).mean(), d(pr[:, 1], pr[:, 2]).mean(), d(pr[:, 2], pr[:, 3]).mean(), d(pr[:, 3], pr[:, 4]).mean(), d(pr[:, 4], pr[:, 5]).mean(),
         d(pr[:, 5], pr[:, 6]).mean(), d(pr[:, 0], pr[:, 6]).mean()))
+    lp = tl[4]
+    print("producer loop iteration that begins the pair, clk: next_item %.0f | early check %.0f | begin+finish(prev) %.0f | total %.0f | early taken %.0f %%" % (
+        d(lp[:, 0], lp[:, 1]).mean(), d(lp[:, 1], lp[:, 2]).mean(), d(lp[:, 2], lp[:, 4]).mean(), d(lp[:, 0], lp[:, 4]).mean(), 100.0 * (lp[:, 3] != 0).mean()))
     print("mma per pair, clk: full wait %.0f | dfree wait %.0f | issue %.0f ; producer arrive -> mma sees full %.0f" % (
         d(mm[:, 0], mm[:, 1]).mean(), d(mm[:, 1], mm[:, 2]).mean(), d(mm[:, 2], mm[:, 3]).mean(), d(pr[:, 6], mm[:, 1]).mean()))
     print("drain per pair, clk: dfull wait %.0f | ld %.0f | zfree wait %.0f | split+store %.0f | fence+arrive %.0f | total busy %.0f ; mma issue -> drain sees dfull %.0f" % (
@@ -154,3 +157,19 @@ if hasattr(lib, "geobi_debug_tcagg_timeline"):
     print("tiles: [zfull wait start, zfull ok, ofree ok, proj issued, epi ofull ok, epi done]")
     for i in range(4):
         print(i + 8, (ti[i, :6] - t0).tolist())
+
+if stage == "ncu":
+    # short run for `ncu --set full -k regex:feast_tcagg_64`: facet graph of PATCHES patches, three launches of the layer
+    import bench
+    patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in bench.patch_meshes(int(os.environ.get("PATCHES", 32)), 0)]
+    dv, df, _ = batching.collate_dual(patches)
+    n = df.x.size(0)
+    g = ops.csr_from_coo(df.edge_index, n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+    torch.manual_seed(0)
+    conv = gnn.FeaStConv(64, 32, 9).to(dev)
+    P = (conv.lin.weight.data, conv.u.weight.data, conv.c.data, conv.bias.data)
+    x = torch.randn(n, 64, device=dev)
+    for _ in range(3):
+        out = ops.feast_fwd(x, g, *P, 0.2, precision=ops.PREC_BF16X3)
+    torch.cuda.synchronize()
+    print("ncu stage done", n, float(out.abs().max()))
