@@ -1152,7 +1152,8 @@ bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const 
 int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map, int64_t n_src,
                     const float* W, const float* U, const float* c, const float* bias, float act_slope, float* out, int64_t ldo, bool reuse_ws,
                     void* ws, size_t ws_bytes, cudaStream_t st);
-// feast_tcagg.cu: the same layer with the aggregation itself on tcgen05 (round 2); GEOBI_NO_TCAGG=1 selects the FP32-pipe kernel above
+// feast_tcagg.cu: the same layer with the aggregation itself on tcgen05 (round 2).  Opt-in (GEOBI_TCAGG=1) until it beats the
+// FP32-pipe kernel above: 0.544 ms vs 0.527 ms per launch at N = 512 000 (profiles/r02_NOTES.md)
 bool feast_tcagg_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t n_src);
 size_t feast_fwd_tcagg_ws_bytes(int64_t n_src);
 int feast_fwd_tcagg(const float* x, int64_t ldx, int64_t N, const int32_t* rowptr, const int32_t* nbr, const int32_t* row_map, int64_t n_src,
@@ -1195,7 +1196,8 @@ extern "C" int geobi_feast_fwd(const float* x, int64_t ldx, int64_t N, int c_in,
   if (N == 0) return GEOBI_OK;
   const bool fused = precision == GEOBI_PREC_BF16X3 && feast_fused_supported(c_in, c_out, ldx, ldo, x, n_src) && getenv("GEOBI_NO_FUSED") == nullptr;
   GEOBI_REQUIRE(!reuse_ws || fused, "feast_fwd: GEOBI_FEAST_REUSE_WS is only defined for the fused 64->32 bf16x3 kernel");
-  if (fused && feast_tcagg_supported(c_in, c_out, ldx, ldo, x, n_src) && getenv("GEOBI_NO_TCAGG") == nullptr)
+  const char* tcagg_env = getenv("GEOBI_TCAGG");
+  if (fused && tcagg_env != nullptr && tcagg_env[0] == '1' && feast_tcagg_supported(c_in, c_out, ldx, ldo, x, n_src))
     return feast_fwd_tcagg(x, ldx, N, rowptr, nbr, row_map, n_src, W, U, c, bias, act_slope, out, ldo, reuse_ws, ws, ws_bytes, st);
   if (fused) return feast_fwd_fused(x, ldx, N, rowptr, nbr, row_map, n_src, W, U, c, bias, act_slope, out, ldo, reuse_ws, ws, ws_bytes, st);
   if (precision != GEOBI_PREC_FP32)

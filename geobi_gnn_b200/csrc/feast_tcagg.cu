@@ -34,7 +34,9 @@ constexpr int TILE = 32;              // nodes per projection tile = MMA N
 constexpr int PAIRS = TILE / 2;
 constexpr int G = 10;                 // producer warps (768 threads: ptxas grants 80 registers up to that count anyway)
 constexpr int R = 14;                 // ring slots, one node pair (2 x (x_hi, x_lo, q)) each; all the shared memory left
-constexpr int DS = 9;                 // aggregation accumulator slots in TMEM (one node pair each)
+constexpr int DS = 8;                 // aggregation accumulator slots in TMEM (one node pair each)
+// tcgen05.commit is not free (probe: +58 clk per pair when every pair commits, profiles/micro/tc_ts_probe.cu): ring slots and
+// accumulator slots are released / published two at a time - xfree[slot >> 1], dfull[dslot >> 1] - by one commit each.
 constexpr int NSETS = 2;               // drain sets (4 quadrant warps each) taking node pairs in turn
 constexpr int EPI_WARPS = 4, DRAIN_WARPS = 4 * NSETS;
 constexpr int AGG_WARP = EPI_WARPS + DRAIN_WARPS;   // issues the aggregation MMAs
@@ -271,15 +273,15 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
                                                                        float slope, float* __restrict__ out, int64_t ldo) {
   extern __shared__ uint8_t smem_raw[];
   // one array so that the debug build can name a barrier by its index: full | xfree | dfull | dfree | zfull | zfree | ofull | ofree
-  __shared__ __align__(8) uint64_t bars[2 * R + 2 * DS + 6];
-  uint64_t* const full = bars;
-  uint64_t* const xfree = bars + R;
-  uint64_t* const dfull = bars + 2 * R;
-  uint64_t* const dfree = bars + 2 * R + DS;
-  uint64_t& zfull = bars[2 * R + 2 * DS];
-  uint64_t& zfree = bars[2 * R + 2 * DS + 1];
-  uint64_t* const ofull = bars + 2 * R + 2 * DS + 2;
-  uint64_t* const ofree = bars + 2 * R + 2 * DS + 4;
+  __shared__ __align__(8) uint64_t bars[R + R / 2 + DS / 2 + DS + 6];
+  uint64_t* const full = bars;                          // [R]      per ring slot
+  uint64_t* const xfree = bars + R;                     // [R / 2]  per pair of ring slots
+  uint64_t* const dfull = bars + R + R / 2;             // [DS / 2] per pair of accumulator slots
+  uint64_t* const dfree = bars + R + R / 2 + DS / 2;    // [DS]     per accumulator slot
+  uint64_t& zfull = bars[R + R / 2 + DS / 2 + DS];
+  uint64_t& zfree = bars[R + R / 2 + DS / 2 + DS + 1];
+  uint64_t* const ofull = bars + R + R / 2 + DS / 2 + DS + 2;
+  uint64_t* const ofree = bars + R + R / 2 + DS / 2 + DS + 4;
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t agg_pos;      // ring sequence numbers issued so far by the aggregation-issue warp (see `slot_reusable`)
   __shared__ float chs[12];
@@ -293,14 +295,10 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (int i = 0; i < R; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&xfree[i], 1);
-    }
-    for (int i = 0; i < DS; ++i) {
-      mbar_init(&dfull[i], 1);
-      mbar_init(&dfree[i], 4);
-    }
+    for (int i = 0; i < R; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < R / 2; ++i) mbar_init(&xfree[i], 1);
+    for (int i = 0; i < DS / 2; ++i) mbar_init(&dfull[i], 1);
+    for (int i = 0; i < DS; ++i) mbar_init(&dfree[i], 4);
     mbar_init(&zfull, PAIRS * 4);
     mbar_init(&zfree, 1);
     mbar_init(&ofull[0], 1);
@@ -392,6 +390,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     load_rowptr(t_begin, rb_n, re_n);
     uint32_t seq_base = 0;
     TileInfo ti{};
+    // `last`: this is the pair's final round.  Commits go out when the second slot of a group has been issued.
     auto issue_pair = [&](uint32_t slot, uint32_t dslot, uint32_t acc, bool last) {
       const uint32_t xa = ring_lo + slot * (SLOT_BYTES >> 4), qa = xa + (4 * XT >> 4);
       const uint32_t dA = tmem + COL_D + dslot * 32, dB = dA + HALF;
@@ -399,8 +398,8 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       mma_ss(dA, xa + (XT >> 4), XHI, qa, QHI, IB, 1u);
       mma_ss(dB, xa + (2 * XT >> 4), XHI, qa + (1024 >> 4), QHI, IA, acc);
       mma_ss(dB, xa + (3 * XT >> 4), XHI, qa + (1024 >> 4), QHI, IB, 1u);
-      mma_commit_u(xfree_u + 8 * slot);
-      if (last) mma_commit_u(dfull_u + 8 * dslot);
+      if (slot & 1u) mma_commit_u(xfree_u + 8 * (slot >> 1));
+      if (last && (dslot & 1u)) mma_commit_u(dfull_u + 8 * (dslot >> 1));
     };
     auto do_pair = [&](uint32_t p, int pp) {       // general path: pairs that take several rounds
       const uint32_t dslot = p % DS, dk = p / DS;
@@ -561,7 +560,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     auto dwait_ld = [&](int p, uint32_t (&r)[32]) {
       const uint32_t dslot = (uint32_t)p % DS, dk = (uint32_t)p / DS;
       if (qd == 0) TLW(2, p - 128, 0);
-      WAIT(&dfull[dslot], dk & 1, 6);
+      WAIT(&dfull[dslot >> 1], dk & 1, 6);
       if (qd == 0) TLW(2, p - 128, 1);
       tc_fence_after();
       tmem_ld32_issue(lane_t + dslot * 32, r);
@@ -579,7 +578,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       // the next pair's accumulator, if it is already complete: its TMEM read overlaps the split below
       bool pre = false;
       if (p_next < npairs) {
-        pre = phase_done(&dfull[(uint32_t)p_next % DS], ((uint32_t)p_next / DS) & 1);
+        pre = phase_done(&dfull[((uint32_t)p_next % DS) >> 1], ((uint32_t)p_next / DS) & 1);
         if (pre) {
           tc_fence_after();
           tmem_ld32_issue(lane_t + ((uint32_t)p_next % DS) * 32, rn);
@@ -734,7 +733,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       const int4 j0 = jv[0], j1 = jv[1], j2 = jv[2], j3 = jv[3];
       const int jr[16] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j2.x, j2.y, j2.z, j2.w, j3.x, j3.y, j3.z, j3.w};
       while (!occupant_issued(it.seq)) __nanosleep(256);
-      WAIT(&xfree[slot], it.par(), 8);
+      WAIT(&xfree[slot >> 1], it.par(), 8);
       TLW(0, ITEM_P(it) - 128, 1);
       tc_fence_after();
       const uint32_t sbase = ring_u32 + slot * SLOT_BYTES;
@@ -835,7 +834,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       TLW(4, ITEM_P(a) - 128, 1);
       // a warp never blocks on a ring slot while it holds an item that the MMA warp is waiting for (the slot's previous
       // occupant may be behind that very item in the MMA warp's order when pairs take several rounds)
-      const bool early = a.valid() && b.valid() && !(occupant_issued(a.seq) && phase_done(&xfree[a.slot()], a.par()));
+      const bool early = a.valid() && b.valid() && !(occupant_issued(a.seq) && phase_done(&xfree[a.slot() >> 1], a.par()));
       TLW(4, ITEM_P(a) - 128, 2);
       if (early) TLW(4, ITEM_P(a) - 128, 3);
 #pragma unroll 1

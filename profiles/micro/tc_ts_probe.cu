@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(128, 1) pattern2_kernel(int tiles, int mode, l
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* sm = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t dummy[32];
   __shared__ uint32_t tmem_slot;
   constexpr int XN = 14;
   constexpr int X_BYTES = 4096, Q_BYTES = 1024;
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(128, 1) pattern2_kernel(int tiles, int mode, l
   for (int i = threadIdx.x; i < (16 * (X_BYTES + Q_BYTES) + W_BYTES + Z_BYTES) / 4; i += blockDim.x) ((uint32_t*)sm)[i] = 0x3c003c00u + i % 7;
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
+    for (int i = 0; i < 32; ++i) mbar_init(&dummy[i], 1);
     fence_mbar_init();
   }
   if (threadIdx.x < 32) tmem_alloc(&tmem_slot, 512);
@@ -347,6 +349,15 @@ __global__ void __launch_bounds__(128, 1) pattern2_kernel(int tiles, int mode, l
               "tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %6, q;\n\t}"
               ::"r"(d + (16u << 16)), "r"(xl + 256), "r"(ql + 64), "r"(xhi), "r"(qhi), "r"(ia), "r"(ib)
               : "memory");
+          if (mode & 8) {
+            mma_commit(&dummy[n & 15]);
+            mma_commit(&dummy[16 + (n & 15)]);
+            mma_commit(&dummy[(n + 1) & 15]);
+            mma_commit(&dummy[16 + ((n + 1) & 15)]);
+          } else if (mode & 16) {
+            mma_commit(&dummy[n & 15]);
+            mma_commit(&dummy[(n + 1) & 15]);
+          }
           s += 2;
           xl += 512; ql += 128;
           if (s >= XN) {
@@ -418,6 +429,9 @@ int main() {
   run_pattern2(n_sm, 3, d_clocks);
   run_pattern2(n_sm, 6, d_clocks);
   run_pattern2(n_sm, 7, d_clocks);
+  run_pattern2(n_sm, 1 | 16, d_clocks);
+  run_pattern2(n_sm, 1 | 8, d_clocks);
+  return 0;
   run_chain2(n_sm, 2, d_clocks, d_stores);
   run_chain2(n_sm, 1, d_clocks, d_stores);
   run_chain2(n_sm, 3, d_clocks, d_stores);

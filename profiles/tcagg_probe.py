@@ -9,6 +9,7 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 lib = _lib.load()
 stage = os.environ.get("STAGE", "all")
+os.environ["GEOBI_TCAGG"] = "1"      # this probe is about the tcgen05-aggregation kernel (opt-in in the library)
 TAGS = {1: "mma:full", 2: "mma:dfree", 3: "mma:zfull", 4: "mma:ofree", 5: "epi:ofull", 6: "drain:dfull", 7: "drain:zfree", 8: "prod:xfree"}
 
 
@@ -24,7 +25,7 @@ def debug_dump(label):
         for i in range(32):
             if v[i]:
                 b = (int(v[i]) >> 8) & 0xffff
-                names = [("full", 14), ("xfree", 14), ("dfull", 9), ("dfree", 9), ("zfull", 1), ("zfree", 1), ("ofull", 2), ("ofree", 2)]
+                names = [("full", 14), ("xfree", 7), ("dfull", 4), ("dfree", 8), ("zfull", 1), ("zfree", 1), ("ofull", 2), ("ofree", 2)]
                 nm = "?"
                 for name, cnt in names:
                     if b < cnt:
@@ -91,11 +92,8 @@ if stage in ("big", "all"):
         out = torch.empty(n, 32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         res = {}
-        for label, env in (("tcagg", None), ("fp32agg", "1")):
-            if env:
-                os.environ["GEOBI_NO_TCAGG"] = env
-            else:
-                os.environ.pop("GEOBI_NO_TCAGG", None)
+        for label, env in (("tcagg", "1"), ("fp32agg", "0")):
+            os.environ["GEOBI_TCAGG"] = env
             ops.feast_fwd(x, g, *P, 0.2, out=out, precision=ops.PREC_BF16X3)
             tk, tl = [], []
             for _ in range(12):
@@ -114,7 +112,7 @@ if stage in ("big", "all"):
                 torch.cuda.synchronize()
                 tl.append(a.elapsed_time(b))
             res[label] = (float(np.mean(tk[2:])), float(np.min(tk)), float(np.mean(tl[2:])))
-        os.environ.pop("GEOBI_NO_TCAGG", None)
+        os.environ["GEOBI_TCAGG"] = "1"
         alg = bench.feast_bytes_alg(n, g.nnz + n, 64, 32)
         for label, (mean, mn, layer) in res.items():
             print(f"[bench-{name}] {label}: kernel mean {mean:.4f} ms (min {mn:.4f}), whole layer {layer:.4f} ms, "

@@ -146,3 +146,62 @@ def test_feast_conv_high_degree_rows_all_kernels(cin, cout, prec):
             want_m = conv(xc[idx], ei)
         got_m = ops.feast_fwd(xc.to(DEV), g, *P, precision=code, row_map=idx.to(DEV).int())
         assert util.rel_err(got_m, want_m) < util.TOL_FP32
+
+
+@pytest.fixture
+def tcagg_on(monkeypatch):
+    """Selects feast_tcagg_64_32_kernel (aggregation on tcgen05, opt-in) for the 64 -> 32 layers; the library reads the switch per call."""
+    monkeypatch.setenv("GEOBI_TCAGG", "1")
+    yield
+    monkeypatch.delenv("GEOBI_TCAGG", raising=False)
+
+
+@pytest.mark.parametrize("case", ["mesh_v", "mesh_f", "hubs", "hubs_row_map", "tiny", "ragged_tail"])
+def test_feast_tcagg_kernel_matches_oracle(case, tcagg_on):
+    """The tcgen05-aggregation kernel against the oracle's FeaStConv (network.py:267-268 layers): mesh graphs (one ring slot per node
+    pair), hub rows of degree 17..128 (several rounds per pair, ring laps), the fused unpooling map, and tile tails."""
+    from geobi_gnn_b200 import ops
+    torch.manual_seed(11)
+    conv = pyg.FeaStConv(64, 32, 9)
+    P = [t.data.to(DEV) for t in (conv.lin.weight, conv.u.weight, conv.c, conv.bias)]
+    row_map = None
+    if case in ("mesh_v", "mesh_f"):
+        (dv, df), _, _ = util.oracle_inputs(7)
+        d = dv if case == "mesh_v" else df
+        n, ei = d.x.shape[0], d.edge_index
+    elif case == "tiny":
+        n, ei = 5, torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]])
+    elif case == "ragged_tail":
+        n = 32 * 5 + 3
+        src = torch.randint(0, n, (900,))
+        ei = torch.stack([src, torch.randint(0, n, (900,))])
+        ei = pyg.to_undirected(ei[:, ei[0] != ei[1]], n)
+    else:
+        n = 3000
+        src, dst = torch.randint(0, n - 10, (24000,)), torch.randint(0, n - 10, (24000,))
+        hubs = torch.cat([torch.full((120,), 0), torch.full((40,), 1), torch.full((17,), 2)])
+        ei = torch.stack([torch.cat([src, hubs]), torch.cat([dst, torch.randint(3, n - 10, (177,))])])
+        ei = pyg.to_undirected(ei[:, ei[0] != ei[1]], n)
+    g = ops.csr_from_coo(ei.to(DEV), n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+    if case == "hubs_row_map":
+        nc = n // 3
+        x = torch.randn(nc, 64) * 2.0
+        row_map = torch.randint(0, nc, (n,))
+        with torch.no_grad():
+            want = conv(x[row_map], ei)
+        got = ops.feast_fwd(x.to(DEV), g, *P, precision=ops.PREC_BF16X3, row_map=row_map.to(DEV).int())
+    else:
+        x = torch.randn(n, 64) * 2.0
+        with torch.no_grad():
+            want = torch.nn.functional.leaky_relu(conv(x, ei), 0.2)
+        got = ops.feast_fwd(x.to(DEV), g, *P, act_slope=0.2, precision=ops.PREC_BF16X3)
+    assert util.rel_err(got, want) < util.TOL_FP32
+    # the switch really selected another kernel: the FP32-pipe kernel's bits differ in the last places
+    import os
+    os.environ["GEOBI_TCAGG"] = "0"
+    other = ops.feast_fwd(x.to(DEV), g, *P, act_slope=1.0 if case == "hubs_row_map" else 0.2, precision=ops.PREC_BF16X3,
+                          row_map=None if row_map is None else row_map.to(DEV).int())
+    os.environ["GEOBI_TCAGG"] = "1"
+    assert util.rel_err(other, want) < util.TOL_FP32
+    if n > 100:
+        assert not torch.equal(other, got)
