@@ -1,0 +1,132 @@
+"""GPU: parity of the configurations the bench lines are quoted on.
+
+* BASELINE configs[1]: a disjoint-union batch of 8000-face patches in the benchmarked numeric mode ('bf16x3').  The reference cannot
+  batch (/root/reference/code/dataset.py:29-31: its Collater returns batch[0]; train_dual.py:142), so the oracle loops over the
+  patches and the product's union forward is compared slice by slice, with the oracle's matchings teacher-forced
+  (labels offset by each patch's node range at that pooling step, SURVEY.md 8c protocol item 3).
+* One mid-size single mesh (200 000 faces) the same way: sizes between configs[0] (20 480) and configs[2] (1 M).
+
+Tolerances: BASELINE.json north_star, 1e-5 max-norm relative; the measured worst case is printed.  The unit normals are compared
+as vectors (max |a - b|): a row whose pre-normalisation head output is short amplifies the 1e-6-level error of the head, see
+`NORMAL_TOL`.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TAPS = ("l1", "p1", "l2", "p2", "l3", "l4", "r1", "r2", "r3", "r4")
+# unit normals: |d n| ~ |d y| / |y|; over hundreds of thousands of faces the shortest |y| is ~1e-2 of the typical one, which turns
+# a 1e-7 absolute error of y into 1e-5 of n.  Measured worst cases (B200): see profiles/r02_NOTES.md section B.
+NORMAL_TOL = 5e-5
+
+
+def _record(name, payload):
+    out = os.path.join(util.ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "parity_worst_cases.jsonl"), "a") as f:
+        f.write(json.dumps({"test": name, **payload}) + "\n")
+
+
+def _oracle_loop(meshes, seed=0, perm_seed=77):
+    """Oracle forward per patch (recording taps and matchings)."""
+    from oracle import ref_dataset
+    ref = util.oracle_net(seed)
+    ref.record = True
+    outs = []
+    for i, (mn, mo) in enumerate(meshes):
+        dv, df = ref_dataset.build_dual_data(mn, mo)
+        util.set_perm_fn(ref, perm_seed + i)
+        with torch.no_grad():
+            vp, nrm, _ = ref([dv, df])
+        outs.append(dict(vp=vp, nrm=nrm, taps={g: {k: ref.taps[g][k].clone() for k in TAPS} for g in ("v", "f")},
+                         labels=[[t[3].clone() for t in pl.trace] for pl in util.poolings(ref)],
+                         unpool=[pl.unpooling_indices.clone() for pl in util.poolings(ref)]))
+    return ref, outs
+
+
+def _union_forced(outs):
+    """Per pooling layer, per step: the union's raw labels = each patch's labels shifted by the node offset of that patch at that step."""
+    forced = []
+    for li in range(4):
+        steps = []
+        for s in range(len(outs[0]["labels"][li])):
+            off, parts = 0, []
+            for o in outs:
+                lab = o["labels"][li][s]
+                parts.append(lab + off)
+                off += lab.numel()
+            steps.append(torch.cat(parts))
+        forced.append(steps)
+    return forced
+
+
+def _run_union(meshes, precision):
+    from geobi_gnn_b200 import batching, config, dataset, network
+    ref, outs = _oracle_loop(meshes)
+    patches = [dataset.build_dual_data(mn, mo, device=DEV) for mn, mo in meshes]
+    if len(patches) > 1:
+        dv, df, slices = batching.collate_dual(patches)
+    else:
+        (dv, df), slices = patches[0], dict(v=[(0, patches[0][0].x.size(0))], f=[(0, patches[0][1].x.size(0))])
+    mine = network.DualGNN().to(DEV).eval()
+    mine.load_state_dict(ref.state_dict())
+    for pl, steps in zip(util.poolings(mine), _union_forced(outs)):
+        pl.forced = steps
+    mine.taps = {}
+    config.set_precision(precision)
+    try:
+        with torch.no_grad():
+            vp, nrm, _ = mine([dv, df])
+    finally:
+        config.set_precision("fp32")
+    return outs, mine, vp, nrm, slices
+
+
+def _check(name, outs, mine, vp, nrm, slices):
+    worst = dict(vert=0.0, normal=0.0, taps={})
+    for i, o in enumerate(outs):
+        a, b = slices["v"][i]
+        worst["vert"] = max(worst["vert"], util.rel_err(vp[a:b], o["vp"]))
+        a, b = slices["f"][i]
+        worst["normal"] = max(worst["normal"], float((nrm[a:b].cpu() - o["nrm"]).abs().max()))
+    for g in ("v", "f"):
+        for k in TAPS:
+            want = torch.cat([o["taps"][g][k] for o in outs])          # patch order = union order at every level
+            worst["taps"][f"{g}.{k}"] = util.rel_err(mine.taps[g][k], want)
+    # integer structure: the union's unpooling maps are the patches' maps shifted by the coarse offsets
+    for li, pl in enumerate(util.poolings(mine)):
+        off_c, parts = 0, []
+        for o in outs:
+            u = o["unpool"][li]
+            parts.append(u + off_c)
+            off_c += int(u.max()) + 1
+        assert torch.equal(pl.unpooling_indices.cpu(), torch.cat(parts)), li
+    _record(name, worst)
+    print(name, json.dumps(worst))
+    tap_worst = max(worst["taps"].values())
+    assert worst["vert"] < util.TOL_FP32, worst
+    assert tap_worst < util.TOL_FP32, worst
+    assert worst["normal"] < NORMAL_TOL, worst
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp32"])
+def test_union_batch_of_bench_patches_matches_the_oracle_patch_by_patch(precision):
+    """8 patches x 8000 faces (the bench shape, configs[1]), per-patch noise seeds, in the benchmarked numeric mode."""
+    meshes = [util.noisy_icosphere(20, seed=s) for s in range(8)]
+    outs, mine, vp, nrm, slices = _run_union(meshes, precision)
+    assert vp.shape[0] == 8 * 4002 and nrm.shape[0] == 8 * 8000
+    _check(f"union8x8000-{precision}", outs, mine, vp, nrm, slices)
+
+
+def test_single_mesh_200k_faces_matches_the_oracle():
+    """One graph pair of 200 000 faces (icosphere frequency 100), 'bf16x3'."""
+    meshes = [util.noisy_icosphere(100, seed=3)]
+    outs, mine, vp, nrm, slices = _run_union(meshes, "bf16x3")
+    assert nrm.shape[0] == 200000
+    _check("single200k-bf16x3", outs, mine, vp, nrm, slices)

@@ -56,9 +56,9 @@ def test_patched_inference_matches_oracle_pipeline():
     mine = network.DualGNN().to(DEV).eval()
     mine.load_state_dict(ref.state_dict())
     V, Np_m, Vp_m = inference.predict_mesh(mine, mesh, sub, device=DEV, forced=forced)
-    assert util.rel_err(Vp_m, Vp) < 5e-5
-    assert util.rel_err(Np_m, Np) < 2e-4
-    assert util.rel_err(V, want_V) < 5e-5
+    assert util.rel_err(Vp_m, Vp) < util.TOL_FP32
+    assert util.rel_err(Np_m, Np) < util.TOL_NORMAL
+    assert util.rel_err(V, want_V) < util.TOL_FP32
     # unsplit branch (n_faces <= sub_size)
     V1, N1, _ = inference.predict_mesh(mine, mesh, 10 ** 9, device=DEV)
     assert V1.shape == (mesh.n_vertices, 3) and torch.isfinite(V1).all()

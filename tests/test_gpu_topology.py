@@ -57,9 +57,9 @@ def test_predict_mesh_device_topology_equals_host_topology():
     out_h = inference.predict_mesh(net, mesh, 500, device=DEV, device_topology=False, return_parts=True)
     out_d = inference.predict_mesh(net, mesh, 500, device=DEV, device_topology=True, return_parts=True)
     assert out_h[3] == out_d[3] > 1                                            # several patches
-    assert util.rel_err(out_d[2], out_h[2]) < 5e-5                             # network vertices
+    assert util.rel_err(out_d[2], out_h[2]) < util.TOL_FP32                             # network vertices
     assert float((out_d[1] - out_h[1]).abs().max()) < 5e-4                     # unit normals
-    assert util.rel_err(out_d[0], out_h[0]) < 5e-5                             # updated vertices
+    assert util.rel_err(out_d[0], out_h[0]) < util.TOL_FP32                             # updated vertices
 
 
 @pytest.mark.gpu
@@ -77,6 +77,6 @@ def test_predict_mesh_accepts_device_built_whole_mesh(sub_size):
     out_h = inference.predict_mesh(net, synth.TriMesh(pn, f), sub_size, device=DEV, return_parts=True)
     out_d = inference.predict_mesh(net, topology.DeviceTriMesh(pn, f, DEV), sub_size, device=DEV, return_parts=True)
     assert out_h[3] == out_d[3] and (out_d[3] > 1) == (sub_size == 500)
-    assert util.rel_err(out_d[2], out_h[2]) < 5e-5
+    assert util.rel_err(out_d[2], out_h[2]) < util.TOL_FP32
     assert float((out_d[1] - out_h[1]).abs().max()) < 5e-4
-    assert util.rel_err(out_d[0], out_h[0]) < 5e-5
+    assert util.rel_err(out_d[0], out_h[0]) < util.TOL_FP32

@@ -15,6 +15,10 @@ from oracle import pyg, ref_dataset, ref_network  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 TOL_FP32 = 1e-5   # BASELINE.json north_star: "within 1e-5 relative (fp32)"
 TOL_BF16 = 2e-3   # "... or 2e-3 (bf16 GEMM)"
+# Unit normals n = y / |y| are compared as vectors, max |dn|: |dn| ~ |dy| / |y|, so the faces whose head output y is short amplify
+# the ~1e-7 absolute error of y.  Over the meshes tested the shortest |y| is ~1e-2 of the typical one; measured worst cases are
+# written to gpurun_out/parity_worst_cases.jsonl by tests/test_gpu_batch.py and summarised in profiles/r02_NOTES.md (section B).
+TOL_NORMAL = 5e-5
 
 
 def rel_err(a, b):
