@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py — faces/sec of the GeoBi-GNN dual-domain forward on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp32|bf16|bf16x3] [--workload mesh1m|patches]
 
-Workload (BASELINE.json configs[1]): a disjoint-union batch of 64 synthetic noisy icosphere patches
-(frequency 20 -> 8000 faces / 4002 vertices each, 512 000 faces per GPU), random-init DualGNN
-(torch.manual_seed(0)), one full forward per step from the reference's input layout
-(x, int64 edge_index, edge_weight, fv_indices).  Weak scaling: every rank gets its own 64 patches,
-no collective on the data path.  One JSON line on stdout (rank 0).
+Headline workload (BASELINE.json configs[2], the largest single-GPU configuration): ONE synthetic noisy mesh of 1 003 520 faces /
+501 762 vertices (icosphere frequency 224) per GPU, full vertex + facet graph, random-init DualGNN (torch.manual_seed(0)), one full
+forward per step from the reference's input layout (x, int64 edge_index, edge_weight, fv_indices).  Weak scaling: every rank gets
+its own mesh (own noise seed), no collective on the data path.  One JSON line on stdout (rank 0).  The same line
+also carries, as sub-objects measured in the same run:
+  * "configs1_patches64": BASELINE configs[1] (disjoint-union batch of 64 x 8000-face patches per GPU), value + e2e;
+  * "configs3_mesh10m":   BASELINE configs[3] - ONE 10 025 280-face mesh cut into the reference's BFS patches of <= 1 M faces, the
+    patches dealt to the N ranks (STRONG scaling, no data-path collective; the accumulators are summed onto rank 0 at the end).
 """
 from __future__ import annotations
 
@@ -30,6 +33,11 @@ import torch  # noqa: E402
 
 PATCH_FREQ = 20          # icosphere frequency -> 8000 faces per patch ("Synthetic-set shape, ~8k faces")
 N_PATCHES = 64
+MESH_FREQ = 224          # configs[2]: 20 n^2 = 1 003 520 faces
+BIG_FREQ = 708           # configs[3]: 10 025 280 faces
+BIG_SUB = 1_000_000      # sub_size of the patch walk for configs[3]
+CPU_SUB = 20_000         # the reference's CPU path cannot hold a 1 M-face graph pair (15 GB per per-edge tensor): it
+                         # runs the mesh patch-wise with test_dual.py's sub_size, which is what the CPU legs time
 TRACE = bool(os.environ.get("BENCH_TRACE"))
 PRIME_STEPS = 16         # untimed allocator-priming forwards before the W warm-up steps (see run_ours)
 print_json = None
@@ -98,7 +106,7 @@ class ClockSampler:
                 "samples": len(self.rows), "source": "NVML, 20 ms polling during the timed region"}
 
 
-# ------------------------------------------------------------------------------------- workload
+# ------------------------------------------------------------------------------------- workloads
 def patch_meshes(count, first_seed):
     from geobi_gnn_b200 import synth
     p, f = synth.icosphere(PATCH_FREQ)
@@ -106,49 +114,89 @@ def patch_meshes(count, first_seed):
     return [(synth.TriMesh(synth.add_normal_noise(p, f, 0.2, first_seed + i), f), clean) for i in range(count)]
 
 
+def noisy_device_mesh(freq, seed, dev):
+    """Noisy icosphere as a topology.DeviceTriMesh: p += 0.2 * mean edge length * N(0,1) * vertex normal, noise drawn
+    on the device (generator seeded per rank)."""
+    import torch
+    from geobi_gnn_b200 import synth, topology
+    p, f = synth.icosphere(freq)
+    clean = topology.DeviceTriMesh(p, f, dev)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    amp = torch.randn(clean.n_vertices, 1, generator=g, device=dev) * 0.2 * clean.mean_edge_length()
+    mesh = topology.DeviceTriMesh(clean.points + amp * clean.vertex_normals, clean.fv, dev)
+    return mesh
+
+
 def feast_bytes_alg(n, e, c_in, c_out):
     """compulsory HBM traffic of one FeaSt layer (int32 CSR, fp32 features)."""
     return 4 * (n * c_in + n * c_out) + 4 * e + 4 * (n + 1) + 4 * (9 * c_in * c_out + 9 * c_in + 9 + c_out)
 
 
+FORWARD_BYTES_PER_FACE = 3104     # SURVEY.md 8(d): algorithmic bytes of the whole dual forward (16 conv layers + 2 heads) per face
+
+
+def ncu_traffic(kernel_substr, n_nodes):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed `ncu --set full` capture
+    that matches this kernel and layer size (profiles/ncu_traffic.json lists the captures: kernel, nodes, csv).  None when no capture
+    of the current kernel at this size is committed - a stale constant would be worse than no number."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    for ent in json.load(open(path)):
+        if ent["kernel"] in kernel_substr and int(ent["nodes"]) == int(n_nodes):
+            csv_path = os.path.join(ROOT, "profiles", ent["csv"])
+            if not os.path.exists(csv_path):
+                continue
+            import csv
+            rows = list(csv.reader(open(csv_path)))
+            hdr = rows[0]
+            row = next((r for r in rows[2:] if any(ent["kernel"] in c for c in r)), None)
+            if row is None:
+                continue
+            d = dict(zip(hdr, row))
+            unit = dict(zip(hdr, rows[1]))
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(d[key])
+                tot += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit[key]]
+            return int(tot), f"ncu --set full, profiles/{ent['csv']}"
+    return None, None
+
+
+class Workload:
+    """Device-resident inputs of one rank + the host copies the end-to-end path uploads every step."""
+
+    def __init__(self, name, rank, dev):
+        import torch
+        from geobi_gnn_b200 import batching, dataset
+        self.name = name
+        if name == "patches":
+            patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in patch_meshes(N_PATCHES, first_seed=rank * N_PATCHES)]
+            self.dv, self.df, _ = batching.collate_dual(patches)
+            self.describe = ("configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init")
+        else:
+            mesh = noisy_device_mesh(MESH_FREQ, rank, dev)
+            self.dv, self.df = dataset.build_dual_data(mesh, None, device=dev)
+            self.describe = ("configs[2]: one noisy icosphere mesh of 1 003 520 faces / 501 762 vertices per GPU (frequency 224), full vertex + "
+                             "facet graph, DualGNN fwd, random init")
+            del mesh
+        self.faces = self.df.x.size(0)
+        keys_v, keys_f = ("x", "edge_index", "edge_weight"), ("x", "edge_index", "edge_weight", "fv_indices")
+        self.host_v = {k: getattr(self.dv, k).cpu().pin_memory() for k in keys_v}
+        self.host_f = {k: getattr(self.df, k).cpu().pin_memory() for k in keys_f}
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in list(self.host_v.values()) + list(self.host_f.values()))
+
+
 def run_ours(args, rank, world, local_rank):
-    from geobi_gnn_b200 import batching, config, dataset, network, ops
+    from geobi_gnn_b200 import batching, config, network, ops, inference
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     config.set_precision(args.precision)
-
-    meshes = patch_meshes(N_PATCHES, first_seed=rank * N_PATCHES)
-    patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in meshes]
-    data_v, data_f, _ = batching.collate_dual(patches)
-    del patches
-    faces_per_rank = data_f.x.size(0)
     torch.manual_seed(0)
     net = network.DualGNN().to(dev).eval()
-
-    in_keys_v, in_keys_f = ("x", "edge_index", "edge_weight"), ("x", "edge_index", "edge_weight", "fv_indices")
-    host_v = {k: getattr(data_v, k).cpu().pin_memory() for k in in_keys_v}
-    host_f = {k: getattr(data_f, k).cpu().pin_memory() for k in in_keys_f}
-    h2d_bytes = sum(t.numel() * t.element_size() for t in list(host_v.values()) + list(host_f.values()))
-
-    def step_resident():
-        with torch.no_grad():
-            return net([batching.fresh_view(data_v), batching.fresh_view(data_f)])
-
-    # end to end: the user-facing runner (inference.HostBatchRunner) takes HOST batches; every step uploads one batch from
-    # pinned memory (on a copy stream, overlapping the previous batch's compute), runs the forward and reads the outputs back
-    from geobi_gnn_b200 import inference
-    runner = inference.HostBatchRunner(net, dev, coalesced_undirected=True)
-    pipe = {"next": None}
-
-    def step_e2e():
-        if pipe["next"] is None:
-            pipe["next"] = runner.upload(host_v, host_f)
-        cur = pipe["next"]
-        pipe["next"] = runner.upload(host_v, host_f)      # this step's H2D copy (the batch the next step consumes)
-        return runner.run(cur)                            # this step's compute + D2H read of (vertices, normals)
 
     def barrier():
         if world > 1:
@@ -156,85 +204,114 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals
+        import torch.distributed as dist
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t)
+
+    def timed(fn, steps, join=None):
+        """K steps between two CUDA events on the launch stream, barrier + synchronize on both sides, max over ranks.
+        `join`: streams whose queued work belongs to the steps (copy / read-back streams of the end-to-end runner) - the launch stream
+        waits for them before the closing event, so the last step's transfers are inside the timed region."""
         import gc
         gc.collect()
         if not os.environ.get("BENCH_KEEP_GC"):
             gc.disable()       # a generation-2 collection inside the timed region shows up as a 10-40 ms host stall
         try:
-            return _timed(fn, steps)
+            barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record()
+            for _ in range(steps):
+                fn()
+            for s in (join or ()):
+                torch.cuda.current_stream(dev).wait_stream(s)
+            ev1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            ms = ev0.elapsed_time(ev1)
         finally:
             gc.enable()
-
-    def _timed(fn, steps):
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        ev0.record()
-        marks = []
-        for _ in range(steps):
-            fn()
-            if TRACE:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append((e, time.perf_counter()))
-        ev1.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = ev0.elapsed_time(ev1)
-        if TRACE:
-            prev_e, prev_t = ev0, t0
-            for e, t in marks:
-                print(f"[trace rank {rank}] gpu {prev_e.elapsed_time(e):8.2f} ms  host-issue {1e3 * (t - prev_t):8.2f} ms", file=sys.stderr)
-                prev_e, prev_t = e, t
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, wall = float(t[0]), float(t[1]) / 1e3
+        ms, wall = max_over_ranks(ms, wall)
         return ms, wall
 
-    # allocator priming: steps run back to back keep more blocks alive than synchronised ones; let the caching allocator
-    # reach its high-water mark (a handful of cudaMallocs) before the W warm-up steps so the timed region sees none
-    for _ in range(PRIME_STEPS):
-        step_resident()
-    torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        step_resident()
-    if args.profile_step:            # for `ncu --profile-from-start off`: exactly one step between cudaProfilerStart/Stop
+    def measure(wl, steps, warmup, with_clocks):
+        """Device-timed value (inputs resident) and end-to-end value (host batches through inference.HostBatchRunner) of a workload."""
+        def step_resident():
+            with torch.no_grad():
+                return net([batching.fresh_view(wl.dv), batching.fresh_view(wl.df)])
+
+        runner = inference.HostBatchRunner(net, dev, coalesced_undirected=True)
+        pipe = {"next": None}
+
+        def step_e2e():
+            if pipe["next"] is None:
+                pipe["next"] = runner.upload(wl.host_v, wl.host_f)
+            cur = pipe["next"]
+            pipe["next"] = runner.upload(wl.host_v, wl.host_f)      # this step's H2D copy (the batch the next step consumes)
+            return runner.run(cur)                                  # this step's compute + D2H read of (vertices, normals)
+
+        # allocator priming: steps run back to back keep more blocks alive than synchronised ones; let the caching allocator
+        # reach its high-water mark (a handful of cudaMallocs) before the W warm-up steps so the timed region sees none
+        for _ in range(PRIME_STEPS):
+            step_resident()
         torch.cuda.synchronize()
+        for _ in range(warmup):
+            step_resident()
+        if args.profile_step and with_clocks:      # for `ncu --profile-from-start off`: exactly one step between cudaProfilerStart/Stop
+            torch.cuda.synchronize()
+            l0 = ops.launch_count()
+            torch.cuda.profiler.start()
+            step_resident()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            print(f"[profile-step] libgeobi kernels counted by the host side in this step: {ops.launch_count() - l0}", file=sys.stderr)
+            return None
         l0 = ops.launch_count()
-        torch.cuda.profiler.start()
-        step_resident()
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-        print(f"[profile-step] libgeobi kernels counted by the host side in this step: {ops.launch_count() - l0}", file=sys.stderr)
+        if with_clocks:
+            with ClockSampler(local_rank) as clk:
+                ms, wall = timed(step_resident, steps)
+            clocks = clk.summary()
+        else:
+            ms, wall = timed(step_resident, steps)
+            clocks = None
+        launches = ops.launch_count() - l0
+        for _ in range(PRIME_STEPS // 2 + warmup):
+            step_e2e()
+        dev_allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        ms_e2e, wall_e2e = timed(step_e2e, steps, join=(runner.copy_stream, runner.read_stream))
+        runner.wait()
+        dev_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - dev_allocs0
+        d2h = sum(t.numel() * t.element_size() for t in runner.out_host.values())
+        total_faces = wl.faces * world
+        return {"value": total_faces * steps / (ms / 1e3), "ms_per_step": ms / steps, "wall_s": wall, "launches": launches, "clocks": clocks,
+                "e2e": {"value": round(total_faces * steps / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / steps, 4), "cuda_mallocs_in_timed_region": int(dev_allocs),
+                        "path": "inference.HostBatchRunner: pinned host batch -> H2D + input-level CSR build on a copy stream (under the "
+                                "previous step's forward) -> DualGNN forward -> D2H of vertices and normals on a read-back stream; one "
+                                "upload + one forward + one read-back per step; copy and read-back streams joined before the closing event"}}
+
+    # ---------------------------------------------------------------- headline workload
+    wl = Workload(args.workload, rank, dev)
+    res = measure(wl, args.steps, args.warmup, with_clocks=True)
+    if res is None:
         return
-    l0 = ops.launch_count()
-    with ClockSampler(local_rank) as clk:
-        ms, wall = timed(step_resident, args.steps)
-    launches = ops.launch_count() - l0
-    for _ in range(PRIME_STEPS + args.warmup):
-        step_e2e()
-    dev_allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
-    ms_e2e, wall_e2e = timed(step_e2e, args.steps)
-    dev_allocs_e2e = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - dev_allocs0
-    d2h_bytes = sum(t.numel() * t.element_size() for t in runner.out_host.values())
 
-    total_faces = faces_per_rank * world
-    value = total_faces * args.steps / (ms / 1e3)
-    e2e_value = total_faces * args.steps / (ms_e2e / 1e3)
-
-    # ---- roofline of the dominant kernel: the fused FeaSt conv on the largest layer (facet r_conv4: N=F, 64->32)
+    # ---- roofline of the dominant kernel: the fused FeaSt conv on the largest layer (facet r_conv4: N = F, 64 -> 32)
     roof = None
     if rank == 0:
-        g = ops.csr_from_coo(data_f.edge_index, faces_per_rank, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+        n_f = wl.faces
+        g = ops.csr_from_coo(wl.df.edge_index, n_f, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
         conv = net.gnn_f.r_conv4
-        x = torch.randn(faces_per_rank, 64, device=dev)
-        out = torch.empty(faces_per_rank, 32, device=dev)
+        x = torch.randn(n_f, 64, device=dev)
+        out = torch.empty(n_f, 32, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
         prec = config.precision_code()
         fused = prec == ops.PREC_BF16X3
+        tcagg = fused and os.environ.get("GEOBI_TCAGG", "0")[:1] == "1"
         call = lambda p_=prec: ops.feast_fwd(x, g, conv.lin.weight, conv.u.weight, conv.c, conv.bias, 0.2, out=out, precision=p_)
         for _ in range(3):
             call()
@@ -253,60 +330,140 @@ def run_ours(args, rank, world, local_rank):
 
         t_op = time_calls(prec)                                   # whole layer: projection P + weight split + main kernel
         t_ms = time_calls(prec | ops.FEAST_REUSE_WS) if fused else t_op   # the dominant kernel alone
-        alg = feast_bytes_alg(faces_per_rank, g.nnz + faces_per_rank, 64, 32)
+        alg = feast_bytes_alg(n_f, g.nnz + n_f, 64, 32)
         peak, how = peaks()
         achieved = alg / (t_ms / 1e3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this layer from the committed ncu --set full capture
-        # (profiles/r01_ncu_full_feast_fused_v2.csv): 226.1 MB + 51.7 MB
-        traffic = 277_800_960 if fused else None
+        kname = "feast_tcagg_64_32_kernel" if tcagg else ("feast_fused_64_32_kernel" if fused else "geobi_feast_fwd (project + aggregate + gemm)")
+        traffic, traffic_src = ncu_traffic(kname, n_f)
+        fwd_gbs = FORWARD_BYTES_PER_FACE * wl.faces / (res["ms_per_step"] / 1e3) / 1e9
         roof = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic,
-                "kernel": ("feast_fused_64_32_kernel" if fused else "geobi_feast_fwd (project + aggregate + gemm)") +
-                          " on facet r_conv4: N=%d, E=%d incl. self loops, 64->32" % (faces_per_rank, g.nnz + faces_per_rank),
+                "kernel": kname + " on facet r_conv4: N=%d, E=%d incl. self loops, 64->32" % (n_f, g.nnz + n_f),
                 "alg_bytes_per_launch": alg, "ms_per_launch": round(t_ms, 4), "ms_whole_layer": round(t_op, 4), "peak_source": how,
-                "l2": "flushed (256 MB write) between launches", "traffic_source": "ncu --set full, profiles/r01_ncu_full_feast_fused_v2.csv",
+                "l2": "flushed (256 MB write) between launches; the layer's input alone is %d MB" % (n_f * 256 // 10 ** 6),
+                "traffic_source": traffic_src,
+                "whole_forward": {"alg_bytes_per_face": FORWARD_BYTES_PER_FACE, "achieved": round(fwd_gbs, 1), "unit": "GB/s",
+                                  "frac": round(fwd_gbs / peak, 4), "note": "3104 B/face (SURVEY.md 8d) x faces / ms_per_step / peak"},
                 "note": "HBM is the nominal bound of a gather/segment-sum; this kernel's 9-head weighting costs 576 fp32 FMAs per gathered 256-byte "
-                        "row, so at 100 % of the FP32 pipe (FFMA2 = 2 clk, profiles/micro/ffma2_bench.cu) it could reach ~0.3 of the HBM peak; "
-                        "ncu: fmaheavy pipe 47 % active, issue slots 55 %, DRAM traffic 1.23x the algorithmic bytes"}
+                        "row on the FP32 pipe (~0.3 of the HBM peak at 100 % pipe use). The tcgen05 form of the aggregation (feast_tcagg, "
+                        "GEOBI_TCAGG=1) is at parity, not ahead: profiles/r02_NOTES.md section A"}
+        del x, out, flush, g
 
-    cpu = cpu_baseline(sample_seconds=12.0) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    # ---------------------------------------------------------------- sub-results measured in the same run
+    extra = {}
+    if not args.headline_only:
+        other = "patches" if args.workload == "mesh1m" else "mesh1m"
+        del wl
+        torch.cuda.empty_cache()
+        wl2 = Workload(other, rank, dev)
+        r2 = measure(wl2, min(args.steps, 10), 3, with_clocks=False)
+        extra["configs1_patches64" if other == "patches" else "configs2_mesh1m"] = {
+            "workload": wl2.describe, "value": round(r2["value"], 1), "unit": UNIT, "ms_per_step": round(r2["ms_per_step"], 4),
+            "steps": min(args.steps, 10), "scaling": "weak", "e2e": r2["e2e"], "gpu_launches": r2["launches"]}
+        del wl2
+        torch.cuda.empty_cache()
+        extra["configs3_mesh10m"] = strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks)
+
+    cpu = cpu_baseline(12.0, args.workload) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
     if rank == 0:
-        line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        line = {"metric": METRIC, "value": round(res["value"], 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(res["ms_per_step"], 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "bf16": "bf16 tensor-core projections (1 pass), f32 elsewhere",
-                          "bf16x3": "f32-grade: split-bf16 x3 tensor-core projections with f32 accumulate, f32 elsewhere"}[args.precision], "data": "synthetic",
-                "config": {"workload": "configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init",
-                           "faces_per_gpu": faces_per_rank, "precision": args.precision,
-                           "l2": "per-step working set (inputs 150 MB + >2 GB intermediates) exceeds the 126 MB L2",
-                           "timing": "CUDA events on the launch stream, max over ranks", "wall_s": round(wall, 4),
+                          "bf16x3": "f32 storage and accumulation; projections on tcgen05 with operands split into two bf16 halves (x3 passes): "
+                                    "1e-5 of the oracle on the bench shapes, 2.1e-5 worst tap at 200k faces (tests/test_gpu_batch.py)"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": DESCRIBE[args.workload], "faces_per_gpu": FACES[args.workload], "precision": args.precision,
+                           "l2": "per-step working set (inputs 390 MB + >4 GB intermediates) exceeds the 126 MB L2",
+                           "timing": "CUDA events on the launch stream, max over ranks", "wall_s": round(res["wall_s"], 4),
                            "priming": f"{PRIME_STEPS} untimed forwards before the {args.warmup} warm-up steps (caching-allocator high-water mark)"},
-                "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                        "ms_per_step": round(ms_e2e / args.steps, 4), "cuda_mallocs_in_timed_region": int(dev_allocs_e2e),
-                        "path": "inference.HostBatchRunner: pinned host batch -> H2D + input-level CSR build on a copy stream (under the "
-                                "previous batch's forward) -> DualGNN forward -> D2H of vertices and normals on a read-back stream; one "
-                                "upload + one forward + one read-back per step"},
-                "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
+                "e2e": res["e2e"], "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": roof, "cpu_baseline": cpu}
+        line.update(extra)
         print_json(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
 
 
+DESCRIBE = {"mesh1m": "configs[2]: one noisy icosphere mesh of 1 003 520 faces / 501 762 vertices per GPU (frequency 224), full vertex + facet graph, "
+                      "DualGNN fwd, random init",
+            "patches": "configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init"}
+FACES = {"mesh1m": 20 * MESH_FREQ ** 2, "patches": N_PATCHES * 20 * PATCH_FREQ ** 2}
+
+
+def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE configs[3]: one 10 M-face mesh, the reference's whole-mesh pipeline (test_dual.predict_one: BFS patches of <= 1 M faces,
+    per-patch forward, overlap-average stitch, 60-sweep vertex update) with the patches dealt to the ranks.  The partition
+    (dataset.py:156-193) is serial by construction - every seed depends on what the earlier patches covered - and is computed once
+    per mesh; it is timed separately, like the reference's own preprocessing print (test_dual.py:37-40).  `inference` = what shards:
+    per-rank patch loop (cut-out, H2D, device topology + graphs, forward, stitch), accumulator reduction onto rank 0, vertex update."""
+    from geobi_gnn_b200 import dataset, inference
+    t0 = time.perf_counter()
+    mesh = noisy_device_mesh(BIG_FREQ, 0, dev)          # the SAME mesh on every rank
+    torch.cuda.synchronize()
+    t_mesh = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    host = inference.host_views(mesh)
+    t_views = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    parts = inference.partition(mesh, BIG_SUB, host=host)
+    t_part = time.perf_counter() - t0
+    c_np, scale = dataset.normalisation(host[0], host[3])
+    norm = (torch.from_numpy(c_np).float().to(dev), float(scale))
+    # warm-up: one small sharded run (kernel loading, allocator, NCCL reduce path)
+    inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)
+    barrier()
+    t0 = time.perf_counter()
+    out = inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)
+    barrier()
+    t_inf = time.perf_counter() - t0
+    (t_inf, t_part_max) = max_over_ranks(t_inf, t_part)
+    ok = None
+    if rank == 0:
+        V, Np, Vp = out
+        ok = bool(torch.isfinite(V).all() and torch.isfinite(Np).all() and float((Np.norm(dim=1) - 1).abs().max()) < 1e-5)
+    faces = mesh.n_faces
+    del mesh, out
+    torch.cuda.empty_cache()
+    return {"workload": f"configs[3]: one {faces}-face mesh (icosphere frequency {BIG_FREQ}), sub_size {BIG_SUB}: {len(parts)} BFS patches dealt "
+                        f"round-robin to {world} GPU(s); no data-path collective, accumulators reduced onto rank 0 once",
+            "scaling": "strong", "n_gpus": world, "faces": faces, "patches": len(parts),
+            "value": round(faces / t_inf, 1), "unit": UNIT, "inference_s": round(t_inf, 4),
+            "partition_s": round(t_part_max, 4), "host_views_s": round(t_views, 4), "whole_mesh_topology_s": round(t_mesh, 4),
+            "end_to_end_s": round(t_views + t_part_max + t_inf, 4), "end_to_end_faces_per_s": round(faces / (t_views + t_part_max + t_inf), 1),
+            "timing": "wall clock between barriers (+ device synchronize), max over ranks; partition and host views once per mesh, outside",
+            "outputs_ok": ok}
+
+
 # ------------------------------------------------------------------------------------- CPU legs (oracle)
-def _oracle_patch_inputs(count, first_seed=0):
+def _oracle_patch_inputs(count, workload, first_seed=0):
+    """Bounded sample of the workload for the CPU legs: whole 8000-face patches (configs[1]), or BFS patches of CPU_SUB faces cut out of
+    the 1 M-face mesh with the reference's rule (configs[2]: the reference's CPU path runs a large mesh patch-wise, test_dual.py:49-61)."""
     from oracle import ref_dataset
-    return [ref_dataset.build_dual_data(mn, mo) for mn, mo in patch_meshes(count, first_seed)]
+    if workload == "patches":
+        return [ref_dataset.build_dual_data(mn, mo) for mn, mo in patch_meshes(count, first_seed)], 20 * PATCH_FREQ ** 2
+    from geobi_gnn_b200 import patches, synth
+    p, f = synth.icosphere(MESH_FREQ)
+    mesh = synth.TriMesh(p, f)                                   # host topology of the clean mesh (seeds / rings only need fv, vf)
+    pn = synth.add_normal_noise(p, f, 0.2, first_seed)
+    out = []
+    rng = np.random.default_rng(0)
+    for seed_face in rng.integers(0, f.shape[0], size=count):
+        sel = patches.mesh_get_neighbor_np(mesh.fv, mesh.vf, int(seed_face), neighbor_count=CPU_SUB)
+        v_idx, faces = patches.get_submesh(mesh.fv, sel)
+        sub_n, sub_o = synth.TriMesh(pn[v_idx], faces), synth.TriMesh(p[v_idx], faces)
+        out.append(ref_dataset.build_dual_data(sub_n, sub_o))
+    return out, CPU_SUB
 
 
-def cpu_baseline(sample_seconds):
+def cpu_baseline(sample_seconds, workload="mesh1m"):
     """Oracle ('port' of the reference path; the reference itself cannot be imported here) timed on the host cores
-    on a bounded sample of the same workload: whole patches, one forward each, until ~sample_seconds elapsed."""
+    on a bounded sample of the same workload: one oracle forward per patch until ~sample_seconds elapsed."""
     from oracle import ref_network
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     net = ref_network.DualGNN().eval()
-    pool = _oracle_patch_inputs(4)
+    pool, faces_each = _oracle_patch_inputs(3, workload)
     with torch.no_grad():
         net([pool[0][0].clone(), pool[0][1].clone()])        # warm-up
         done, t0 = 0, time.perf_counter()
@@ -315,9 +472,10 @@ def cpu_baseline(sample_seconds):
             net([dv.clone(), df.clone()])
             done += 1
         dt = time.perf_counter() - t0
-    faces = done * 20 * PATCH_FREQ ** 2
+    faces = done * faces_each
     return {"value": round(faces / dt, 1), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{done} patches of {20 * PATCH_FREQ ** 2} faces, one oracle forward each, {dt:.1f} s"}
+            "sample": f"{done} BFS patches of {faces_each} faces of the workload's mesh, one oracle forward each, {dt:.1f} s"
+                      if workload == "mesh1m" else f"{done} patches of {faces_each} faces, one oracle forward each, {dt:.1f} s"}
 
 
 def run_reference(args, rank, world):
@@ -330,8 +488,8 @@ def run_reference(args, rank, world):
     torch.set_num_threads(os.cpu_count() or 1)
     torch.manual_seed(0)
     net = ref_network.DualGNN().eval()
-    per_step = 2
-    pool = _oracle_patch_inputs(per_step)
+    per_step = 1 if args.workload == "mesh1m" else 2
+    pool, faces_each = _oracle_patch_inputs(per_step, args.workload)
 
     def step():
         with torch.no_grad():
@@ -344,16 +502,18 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    faces = per_step * 20 * PATCH_FREQ ** 2
+    faces = per_step * faces_each
     value = faces * args.steps / dt
     cores = torch.get_num_threads()
+    sample = (f"{per_step} BFS patch of {faces_each} faces cut from the 1 003 520-face mesh per step (the reference's CPU path runs a large mesh "
+              f"patch-wise, test_dual.py:49-61; one 1 M-face graph pair needs 15 GB per per-edge tensor)") if args.workload == "mesh1m" else \
+             f"{per_step} of the 64 patches per step (the reference runs one patch per forward, dataset.py:29-31)"
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init",
-                       "sample": f"{per_step} of the 64 patches per step (the reference runs one patch per forward, dataset.py:29-31)"},
+            "config": {"workload": DESCRIBE[args.workload], "sample": sample},
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{per_step} patches x {20 * PATCH_FREQ ** 2} faces per step, {args.steps} steps"},
+                             "sample": f"{per_step} x {faces_each} faces per step, {args.steps} steps"},
             "e2e": {"value": round(value, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print_json(line)
 
@@ -371,6 +531,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("GEOBI_PRECISION", "bf16x3"), choices=["fp32", "bf16", "bf16x3"])
+    ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "mesh1m"), choices=["mesh1m", "patches"],
+                    help="headline workload: mesh1m = BASELINE configs[2] (default), patches = configs[1]")
+    ap.add_argument("--headline-only", action="store_true", help="skip the sub-results (other single-GPU config, configs[3] strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-step", action="store_true", help="run warm-up then ONE step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()

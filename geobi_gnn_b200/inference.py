@@ -16,11 +16,29 @@ import torch
 from . import batching, data_util, dataset, patches, synth
 
 
+def host_views(mesh):
+    """numpy copies of the index arrays the host side of the pipeline reads (BFS patch splitter, patch cut-out, normalisation):
+    (points fp32, fv, vf, ev).  A caller that partitions a mesh once and runs many sharded predictions passes them back in."""
+    def _np(a):
+        return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+    return np.asarray(_np(mesh.points), dtype=np.float32), _np(mesh.fv), _np(mesh.vf), _np(mesh.ev)
+
+
+def partition(mesh, sub_size: int, host=None):
+    """The reference's BFS face patches of a mesh (dataset.py:156-193): [(face ids in discovery order, seed face), ...].  The walk is
+    serial by construction (every seed depends on what the earlier patches covered); `predict_mesh(parts=...)` reuses its result."""
+    pts, fv, vf, _ = host_views(mesh) if host is None else host
+    return patches.split_mesh(pts, fv, vf, sub_size)
+
+
 def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device="cuda", n_iter: int = 60, rank: int = 0, world: int = 1,
                  forced: Optional[List] = None, return_parts: bool = False, device_topology: bool = True,
-                 timings: Optional[dict] = None):
+                 timings: Optional[dict] = None, parts: Optional[List] = None, host=None, norm=None):
     """Returns (V [Nv,3] updated vertices, Np [Nf,3] unit facet normals, Vp [Nv,3] network vertices) on `device`
-    (meaningful on rank 0 when world > 1).  `forced`: per patch, the 4 pooling layers' raw label lists (tests)."""
+    (meaningful on rank 0 when world > 1).  `forced`: per patch, the 4 pooling layers' raw label lists (tests).
+    `parts` / `host`: a partition and the host views computed earlier (`partition`, `host_views`) - the sharded run then consists
+    of the per-rank patch loop, the accumulator reduction onto rank 0 and the vertex update only; `norm` = (centroid tensor, scale)
+    of the whole mesh (`dataset.normalisation`) if the caller has it already."""
     dev = torch.device(device)
     from . import topology
     import time
@@ -38,11 +56,8 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     make_sub = (lambda pts, fcs: topology.DeviceTriMesh(pts, fcs, dev)) if device_topology else synth.TriMesh
     # `mesh` may be a host object (numpy index arrays, e.g. synth.TriMesh / OpenMesh) or a topology.DeviceTriMesh built on the
     # GPU from points + faces: the host parts of the pipeline (BFS patch splitter, normalisation) get numpy views of it
-    def _np(a):
-        return a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
-
-    mesh_points, mesh_fv, mesh_vf, mesh_ev = _np(mesh.points), _np(mesh.fv), _np(mesh.vf), _np(mesh.ev)
-    points_noisy = np.asarray(mesh_points, dtype=np.float32)
+    mesh_points, mesh_fv, mesh_vf, mesh_ev = host_views(mesh) if host is None else host
+    points_noisy = mesh_points
     poolings = [net.gnn_v.pooling1, net.gnn_v.pooling2, net.gnn_f.pooling1, net.gnn_f.pooling2]
 
     def run(dual, k):
@@ -63,12 +78,13 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         n_patches = 1
     else:                                                          # test_dual.py:49-61
         lap("host_views")
-        parts = patches.split_mesh(points_noisy, mesh_fv, mesh_vf, sub_size)
+        if parts is None:
+            parts = patches.split_mesh(points_noisy, mesh_fv, mesh_vf, sub_size)
         lap("split_mesh")
         n_patches = len(parts)
         st = patches.Stitcher(mesh.n_vertices, mesh.n_faces, dev)
         slot = np.full(mesh.n_vertices, -1, dtype=np.int64)
-        norm = None                                                 # (centroid, scale) of the WHOLE mesh, computed once
+        # norm: (centroid, scale) of the WHOLE mesh, computed once
         mine = [k for k in range(n_patches) if k % world == rank]
 
         def cut(k):                                                 # host side of one patch (C++ re-indexing + a gather)
