@@ -181,8 +181,10 @@ class Workload:
             del mesh
         self.faces = self.df.x.size(0)
         keys_v, keys_f = ("x", "edge_index", "edge_weight"), ("x", "edge_index", "edge_weight", "fv_indices")
-        self.host_v = {k: getattr(self.dv, k).cpu().pin_memory() for k in keys_v}
-        self.host_f = {k: getattr(self.df, k).cpu().pin_memory() for k in keys_f}
+        from geobi_gnn_b200.inference import HostBatchRunner
+        # the host batch as a data-loader worker hands it over: float tensors as they are, index tensors narrowed to int32 once
+        self.host_v = HostBatchRunner.pack({k: getattr(self.dv, k).cpu().pin_memory() for k in keys_v})
+        self.host_f = HostBatchRunner.pack({k: getattr(self.df, k).cpu().pin_memory() for k in keys_f})
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in list(self.host_v.values()) + list(self.host_f.values()))
 
 
@@ -289,8 +291,8 @@ def run_ours(args, rank, world, local_rank):
         return {"value": total_faces * steps / (ms / 1e3), "ms_per_step": ms / steps, "wall_s": wall, "launches": launches, "clocks": clocks,
                 "e2e": {"value": round(total_faces * steps / (ms_e2e / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
                         "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / steps, 4), "cuda_mallocs_in_timed_region": int(dev_allocs),
-                        "path": "inference.HostBatchRunner: pinned host batch -> H2D + input-level CSR build on a copy stream (under the "
-                                "previous step's forward) -> DualGNN forward -> D2H of vertices and normals on a read-back stream; one "
+                        "path": "inference.HostBatchRunner: pinned host batch (index tensors int32, widened on the device) -> H2D + input-level CSR "
+                                "build on a copy stream (under the previous step's forward) -> DualGNN forward -> D2H of vertices and normals on a read-back stream; one "
                                 "upload + one forward + one read-back per step; copy and read-back streams joined before the closing event"}}
 
     # ---------------------------------------------------------------- headline workload

@@ -153,8 +153,10 @@ def test_dualgnn_same_bits_with_and_without_the_coalesced_hint():
 
 
 @pytest.mark.gpu
-def test_host_batch_runner_equals_direct_forward():
-    """inference.HostBatchRunner (pinned host batches, upload on a copy stream) returns the bits of a plain forward."""
+@pytest.mark.parametrize("packed", [False, True])
+def test_host_batch_runner_equals_direct_forward(packed):
+    """inference.HostBatchRunner (pinned host batches, upload on a copy stream) returns the bits of a plain forward, from the
+    reference's int64 host layout and from the int32-narrowed one (HostBatchRunner.pack)."""
     from geobi_gnn_b200 import batching, dataset, inference, network
     torch.manual_seed(5)
     net = network.DualGNN().to(DEV).eval()
@@ -172,6 +174,9 @@ def test_host_batch_runner_equals_direct_forward():
             want.append((vp.cpu(), nrm.cpu()))
     host = [({k: getattr(dv, k).cpu().pin_memory() for k in ("x", "edge_index", "edge_weight")},
              {k: getattr(df, k).cpu().pin_memory() for k in ("x", "edge_index", "edge_weight", "fv_indices")}) for dv, df in batches]
+    if packed:
+        host = [(inference.HostBatchRunner.pack(hv), inference.HostBatchRunner.pack(hf)) for hv, hf in host]
+        assert host[0][0]["edge_index"].dtype == torch.int32 and host[0][1]["fv_indices"].dtype == torch.int32
     runner = inference.HostBatchRunner(net, DEV, coalesced_undirected=True)
     nxt = runner.upload(*host[0])
     for i in range(3):
