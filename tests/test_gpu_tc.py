@@ -96,8 +96,12 @@ def test_fc_head_tensor_core(n, force_depth):
     assert util.rel_err(got, want) < util.TOL_FP32 and util.rel_err(got, ref) < util.TOL_FP32
     if not force_depth:
         gn = ops.fc_head_fwd(f.to(DEV), *P, epilogue=3, precision=ops.PREC_BF16X3)
-        # unit vectors: rows with a small |y| amplify the (1e-6-level) error of y, same bar as the end-to-end normals
-        assert util.rel_err(gn, torch.nn.functional.normalize(y, dim=1)) < util.TOL_NORMAL
+        # unit vectors of RANDOM features: |dn| ~ |dy| / |y| and some rows have |y| ~ 1e-3 max|y|, so the deviation is weighed by
+        # the row's |y|: this bounds the error of the head output itself at the fp32 bar
+        nrm = torch.nn.functional.normalize(y, dim=1)
+        dev = (gn.cpu() - nrm).norm(dim=1) * y.norm(dim=1) / y.norm(dim=1).max()
+        assert float(dev.max()) < util.TOL_FP32
+        assert util.rel_err(gn.norm(dim=1), torch.ones(n)) < util.TOL_FP32
 
 
 def test_dualgnn_forward_bf16x3_matches_oracle():
