@@ -364,6 +364,7 @@ def run_ours(args, rank, world, local_rank):
         del wl2
         torch.cuda.empty_cache()
         extra["configs3_mesh10m"] = strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks)
+        extra["configs4_train"] = train_steps(dev, rank, world, barrier, max_over_ranks, args.precision)
 
     cpu = cpu_baseline(12.0, args.workload) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
 
@@ -434,6 +435,56 @@ def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks):
             "end_to_end_s": round(t_views + t_part_max + t_inf, 4), "end_to_end_faces_per_s": round(faces / (t_views + t_part_max + t_inf), 1),
             "timing": "wall clock between barriers (+ device synchronize), max over ranks; partition and host views once per mesh, outside",
             "outputs_ok": ok}
+
+
+def train_steps(dev, rank, world, barrier, max_over_ranks, precision, patches_per_rank=16, steps=8):
+    """BASELINE configs[4]: train_dual.py-style training step (forward, L1 losses, backward, ONE flat fp32 gradient all-reduce over
+    NCCL, Adam) on a batch of 16 x 8000-face patches per rank (weak scaling; one batch per rank = the reference's gradient
+    accumulation over `batch_size` meshes, train_dual.py:211-218).  The all-reduce alone is timed as well."""
+    from geobi_gnn_b200 import batching, dataset, network, parallel, train
+    patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in patch_meshes(patches_per_rank, first_seed=rank * patches_per_rank)]
+    dv, df, _ = batching.collate_dual(patches)
+    torch.manual_seed(0)
+    net = network.DualGNN().to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+    def step():
+        return train.train_step(net, opt, [batching.fresh_view(dv), batching.fresh_view(df)], world_size=world)
+
+    for _ in range(5):
+        loss, ev, en = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss, ev, en = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    ms_ar = 0.0
+    if world > 1:       # the collective alone: the same flat bucket, gradients in place from the last step
+        for _ in range(3):
+            parallel.allreduce_gradients(net.parameters(), average=False)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(10):
+            parallel.allreduce_gradients(net.parameters(), average=False)
+        a1.record()
+        barrier()
+        ms_ar = a0.elapsed_time(a1) / 10
+    ms, ms_ar = max_over_ranks(ms, ms_ar)
+    faces = df.x.size(0) * world
+    n_params = sum(p.numel() for p in net.parameters())
+    out = {"workload": f"configs[4]: training step on {patches_per_rank} patches x 8000 faces per GPU (fwd + L1 losses + bwd + flat gradient "
+                       f"all-reduce + Adam lr 1e-3), {world} GPU(s)",
+           "scaling": "weak", "n_gpus": world, "value": round(faces / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
+           "allreduce_ms": round(ms_ar, 4), "allreduce": f"one flat fp32 bucket of {n_params} gradients ({4 * n_params / 1e6:.2f} MB), NCCL" if world > 1 else None,
+           "precision": precision, "loss": float(loss), "error_n_deg": float(en),
+           "backward": "soft-assignment / gather part and segment max in libgeobi kernels; dense parts (dZ, dW, dX, dU, heads) on library GEMMs via autograd"}
+    del net, opt, dv, df, patches
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------- CPU legs (oracle)
