@@ -105,6 +105,21 @@ def post_processing(dual_data, data_type="Synthetic", is_plot=False):
     return data_v, data_f
 
 
+def build_dual_on_device(mesh_n, mesh_o=None, data_type="Synthetic", name="graph"):
+    """build_dual_data for a topology.DeviceTriMesh with the normalisation (dataset.py:140,151-152: centroid, 1 / mean edge length)
+    computed on the device as well - no host round trip and no stream synchronisation beyond the mesh's own entry counts.  The fp32
+    mean is taken by a device reduction instead of numpy's pairwise sum: centroid / scale agree with `normalisation` to ~1e-7."""
+    dev = mesh_n.points.device
+    dd = process_one_submesh(mesh_n, name, mesh_o, dev)
+    pts = mesh_n.points
+    centroid = pts.mean(0, keepdim=True)
+    q = pts - centroid
+    ev = mesh_n.ev
+    length = (q[ev[:, 0]] - q[ev[:, 1]]).pow(2).sum(1).sqrt()
+    dd[0].centroid, dd[0].scale = centroid, 1.0 / length.mean()
+    return post_processing(dd, data_type)
+
+
 def build_dual_data(mesh_n, mesh_o=None, data_type="Synthetic", name="graph", device="cuda"):
     """Single-patch branch of process_one_data (dataset.py:144-153) followed by post_processing."""
     dd = process_one_submesh(mesh_n, name, mesh_o, device)

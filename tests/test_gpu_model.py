@@ -213,3 +213,35 @@ def test_forward_rejects_a_false_coalesced_undirected_claim():
     with torch.no_grad():
         out = net([a2, b2])
     assert torch.isfinite(out[0]).all()
+
+
+@pytest.mark.gpu
+def test_host_batch_runner_upload_mesh_equals_direct_forward():
+    """upload_mesh (raw points + faces cross PCIe; topology, graphs, weights and features built on the copy stream) gives the bits of
+    a forward on inputs built by the same device front end on the main stream, and the oracle's features within the fp32 bar."""
+    from geobi_gnn_b200 import batching, dataset, inference, network, topology
+    torch.manual_seed(7)
+    net = network.DualGNN().to(DEV).eval()
+    for pl in util.poolings(net):
+        pl.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
+    meshes = [util.noisy_icosphere(6, seed=20 + s)[0] for s in range(3)]
+    want = []
+    with torch.no_grad():
+        for m in meshes:
+            dm = topology.DeviceTriMesh(m.points, m.fv, DEV)
+            dv, df = dataset.build_dual_on_device(dm, None)
+            (ov, of), _, _ = util.oracle_inputs(6, seed=20 + len(want))
+            assert util.rel_err(dv.x, ov.x) < util.TOL_FP32 and util.rel_err(df.x, of.x) < util.TOL_FP32
+            assert torch.equal(df.edge_index.cpu(), of.edge_index) and util.rel_err(df.edge_weight, of.edge_weight) < util.TOL_FP32
+            vp, nrm, _ = net([batching.fresh_view(dv), batching.fresh_view(df)])
+            want.append((vp.cpu(), nrm.cpu()))
+    host = [(torch.from_numpy(m.points.astype("float32")).pin_memory(), torch.from_numpy(m.fv.astype("int32")).pin_memory()) for m in meshes]
+    runner = inference.HostBatchRunner(net, DEV, coalesced_undirected=True)
+    nxt = runner.upload_mesh(*host[0])
+    for i in range(3):
+        cur = nxt
+        if i + 1 < 3:
+            nxt = runner.upload_mesh(*host[i + 1])
+        v, n = runner.run(cur)
+        runner.wait()
+        assert torch.equal(v, want[i][0]) and torch.equal(n, want[i][1])
