@@ -87,6 +87,24 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         # norm: (centroid, scale) of the WHOLE mesh, computed once
         mine = [k for k in range(n_patches) if k % world == rank]
 
+        on_device = device_topology and torch.is_tensor(mesh.fv) and mesh.fv.is_cuda and torch.is_tensor(mesh.points)
+        if on_device:
+            # the whole mesh lives on the device: a patch is cut out there (patches.get_submesh_device: same vertex order as the
+            # host routine); per patch only its face list crosses PCIe (int32, pinned)
+            for k in mine:
+                sel, seed = parts[k]
+                sel_dev = torch.from_numpy(np.ascontiguousarray(sel, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+                v_idx, faces = patches.get_submesh_device(mesh.fv, sel_dev, mesh.n_vertices)
+                sub = topology.DeviceTriMesh(mesh.points.index_select(0, v_idx), faces, dev)
+                dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev)
+                dataset.attach_normalisation(dual, points_noisy, mesh_ev, precomputed=norm)   # dataset.py:140,179-180
+                centroid, scale = dual[0].centroid, dual[0].scale
+                norm = (centroid, scale)
+                dual = dataset.post_processing(dual, data_type)
+                vert_p, norm_p = run(dual, k)
+                st.add(vert_p, norm_p, v_idx, sel_dev.long())
+            mine = []
+
         def cut(k):                                                 # host side of one patch (C++ re-indexing + a gather)
             v_idx, faces = patches.get_submesh(mesh_fv, parts[k][0], _slot=slot)
             return v_idx, faces, mesh_points[v_idx]

@@ -65,6 +65,23 @@ def get_submesh(fv_indices, select_faces, _slot=None):
     return v_idx[:nv].copy(), faces
 
 
+def get_submesh_device(fv_dev: torch.Tensor, select_faces_dev: torch.Tensor, n_vertices: int):
+    """get_submesh (data_util.py:318-336) on the device: (V_idx int64 in first-appearance order, faces re-indexed int64 [Fs,3]).
+    First appearance = smallest position in the selected faces' flattened corner list, so the vertex order (and with it every index
+    array derived from the patch) equals the host routine's; integer glue on a few tensor ops, no host round trip per patch."""
+    faces_g = fv_dev.index_select(0, select_faces_dev.long())
+    flat = faces_g.reshape(-1)
+    big = flat.numel()
+    first = torch.full((n_vertices,), big, dtype=torch.int64, device=fv_dev.device)
+    first.scatter_reduce_(0, flat, torch.arange(big, device=fv_dev.device), reduce="amin", include_self=True)
+    present = torch.nonzero(first < big).reshape(-1)
+    order = torch.argsort(first.index_select(0, present))
+    v_idx = present.index_select(0, order)
+    remap = torch.empty(n_vertices, dtype=torch.int64, device=fv_dev.device)
+    remap[v_idx] = torch.arange(v_idx.numel(), device=fv_dev.device)
+    return v_idx, remap[faces_g]
+
+
 def split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count=0) -> List[Tuple[np.ndarray, int]]:
     """dataset.py:156-193 — [(select_faces, seed), ...]."""
     return list(iter_split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_count))

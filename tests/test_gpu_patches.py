@@ -182,3 +182,22 @@ def test_streaming_splitter_yields_the_same_patches():
         raise KeyError("inside the producer")
     with pytest.raises(KeyError):
         list(patches.prefetch(broken()))
+
+
+@pytest.mark.gpu
+def test_get_submesh_device_equals_host_routine():
+    """The device cut-out (patches.get_submesh_device) reproduces data_util.get_submesh: vertices in first-appearance order, faces
+    re-indexed - on BFS patches (discovery order) and on a shuffled face selection."""
+    import numpy as np
+    from geobi_gnn_b200 import patches, synth
+    p, f = synth.icosphere(12)
+    mesh = synth.TriMesh(p, f)
+    fv_dev = torch.from_numpy(mesh.fv).cuda()
+    rng = np.random.default_rng(3)
+    sels = [patches.mesh_get_neighbor_np(mesh.fv, mesh.vf, int(s), neighbor_count=700) for s in (0, 123, 2000)]
+    sels.append(rng.permutation(f.shape[0])[:900].astype(np.int64))
+    for sel in sels:
+        v_host, faces_host = patches.get_submesh(mesh.fv, sel)
+        v_dev, faces_dev = patches.get_submesh_device(fv_dev, torch.from_numpy(np.ascontiguousarray(sel)).cuda(), mesh.n_vertices)
+        assert np.array_equal(v_dev.cpu().numpy(), v_host)
+        assert np.array_equal(faces_dev.cpu().numpy(), faces_host)
