@@ -33,6 +33,8 @@ SIGNATURES = {
     "geobi_csr_to_coo": (_i32, [_p, _p, _i64, _i64, _p, _p]),
     "geobi_build_facet_graph_ws_bytes": (_sz, [_i64, _i64]),
     "geobi_build_facet_graph": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "geobi_build_facet_graph_sorted_ws_bytes": (_sz, [_i64]),
+    "geobi_build_facet_graph_sorted": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "geobi_graclus_ws_bytes": (_sz, [_i64]),
     "geobi_graclus": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "geobi_relabel_ws_bytes": (_sz, [_i64]),

@@ -489,6 +489,81 @@ extern "C" int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int
   return GEOBI_OK;
 }
 
+// Facet 1-ring from SORTED incidence rows: a face's row is the union of its three corners' vf rows, each ascending with its -1
+// pads at the end (topology.DeviceTriMesh builds them that way): a three-way merge with duplicate removal, one thread per face,
+// instead of filling 3K keys per face and rank-sorting every row with a warp.  Pass 0 counts (and verifies the order: the
+// merge would silently drop or repeat entries on an unsorted row), pass 1 writes at the scanned offsets.
+namespace geobi {
+template <bool WRITE>
+__global__ void __launch_bounds__(256) facet_merge_kernel(const int64_t* __restrict__ fv, const int64_t* __restrict__ vf, int64_t F, int64_t V, int K,
+                                                          const int32_t* __restrict__ rowptr, int32_t* __restrict__ out, int* status) {
+  constexpr int64_t INF = (int64_t)1 << 62;
+  for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < F; f += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v0 = fv[3 * f], v1 = fv[3 * f + 1], v2 = fv[3 * f + 2];
+    if (v0 < 0 || v0 >= V || v1 < 0 || v1 >= V || v2 < 0 || v2 >= V) {
+      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+      if (!WRITE) out[f] = 0;
+      continue;
+    }
+    const int64_t* r0 = vf + v0 * K;
+    const int64_t* r1 = vf + v1 * K;
+    const int64_t* r2 = vf + v2 * K;
+    int i0 = 0, i1 = 0, i2 = 0;
+    auto head = [&](const int64_t* r, int i) -> int64_t {
+      if (i >= K) return INF;
+      const int64_t g = r[i];
+      return g < 0 ? INF : g;
+    };
+    int64_t a = head(r0, 0), b = head(r1, 0), c = head(r2, 0);
+    int32_t* dst = WRITE ? out + rowptr[f] : nullptr;
+    int n = 0;
+    bool bad = false;
+    for (;;) {
+      const int64_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
+      if (m == INF) break;
+      if (m >= F) { bad = true; break; }
+      if (WRITE) dst[n] = (int32_t)m;
+      ++n;
+      if (a == m) { a = head(r0, ++i0); bad |= a <= m; }
+      if (b == m) { b = head(r1, ++i1); bad |= b <= m; }
+      if (c == m) { c = head(r2, ++i2); bad |= c <= m; }
+      if (bad) break;
+    }
+    if (bad) atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+    if (!WRITE) out[f] = n;
+  }
+}
+}  // namespace geobi
+
+extern "C" size_t geobi_build_facet_graph_sorted_ws_bytes(int64_t n_faces) {
+  return align256((size_t)(n_faces + 1) * sizeof(int)) + align256(sizeof(int) * ST_WORDS) + scan_ws_bytes(n_faces + 1) + 1024;
+}
+
+extern "C" int geobi_build_facet_graph_sorted(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts, int64_t k, int32_t* rowptr,
+                                              int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(fv && vf && rowptr && nbr && n_faces > 0 && n_verts > 0 && k > 0, "build_facet_graph_sorted: bad arguments");
+  GEOBI_REQUIRE(n_faces * 3 * k < (int64_t)1 << 31, "build_facet_graph_sorted: 3*K*F exceeds int32 indexing");
+  if (ws_bytes < geobi_build_facet_graph_sorted_ws_bytes(n_faces) || !ws) {
+    set_error("build_facet_graph_sorted: workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  Carver c(ws, ws_bytes);
+  int* count = c.take<int>(n_faces + 1);
+  int* status = c.take<int>(ST_WORDS);
+  const size_t sb = scan_ws_bytes(n_faces + 1);
+  char* scan = c.take<char>(sb);
+  GEOBI_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int) * ST_WORDS, st));
+  facet_merge_kernel<false><<<grid_for(n_faces, 256), 256, 0, st>>>(fv, vf, n_faces, n_verts, (int)k, nullptr, count, status);
+  GEOBI_LAUNCH_OK("facet_merge (count)");
+  int rc = scan_i32(count, rowptr, n_faces, scan, sb, st);
+  if (rc) return rc;
+  facet_merge_kernel<true><<<grid_for(n_faces, 256), 256, 0, st>>>(fv, vf, n_faces, n_verts, (int)k, rowptr, nbr, status);
+  GEOBI_LAUNCH_OK("facet_merge (fill)");
+  if (nnz_host) return finish_sync(status, rowptr, n_faces, nnz_host, "build_facet_graph_sorted", st);
+  return GEOBI_OK;
+}
+
 // ------------------------------------------------------------------------------ graclus (exact parallel greedy)
 namespace geobi {
 constexpr int M_NONE = -1, M_SINGLE = -2;

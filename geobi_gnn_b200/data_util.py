@@ -42,10 +42,10 @@ def calc_weight(node_pos, node_normal, edge_index):
     return ops.calc_weight(node_pos, node_normal, edge_index)
 
 
-def build_facet_graph(fv_indices, vf_indices):
+def build_facet_graph(fv_indices, vf_indices, vf_sorted=False):
     """data_util.py:436-456 — sorted [2,E] with self entries; CSR (self entries dropped lazily by the
-    conv / matcher builders) is attached for reuse."""
-    g = ops.build_facet_graph_csr(fv_indices, vf_indices)
+    conv / matcher builders) is attached for reuse.  `vf_sorted` (not upstream): the caller guarantees ascending vf rows."""
+    g = ops.build_facet_graph_csr(fv_indices, vf_indices, vf_sorted)
     return g.edge_index()
 
 

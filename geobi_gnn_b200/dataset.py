@@ -45,7 +45,7 @@ def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda"):
                    depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1], coalesced_undirected=True)
     pos_f = pos_v[fv].mean(1)
     normal_f = _t(mesh_n.face_normals, torch.float32, device).reshape(-1, 3)
-    edge_idx_f = data_util.build_facet_graph(fv, vf)
+    edge_idx_f = data_util.build_facet_graph(fv, vf, vf_sorted=bool(getattr(mesh_n, "vf_sorted", False)))
     edge_wei_f = data_util.calc_weight(pos_f, normal_f, edge_idx_f)
     graph_f = Data(name=f"{name}-f", pos=pos_f, normal=normal_f, edge_index=edge_idx_f, edge_weight=edge_wei_f,
                    fv_indices=fv, edge_dual=edge_dual_fv[0], coalesced_undirected=True)

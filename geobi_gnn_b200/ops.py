@@ -273,8 +273,9 @@ def csr_from_sorted_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional
     return CSRGraph(rowptr, nbr, n_nodes, 0 if e == 0 else None, w_out, True), ei_out, w_out
 
 
-def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor) -> CSRGraph:
-    """Facet 1-ring CSR with the self entry (data_util.build_facet_graph).  Syncs once."""
+def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor, vf_sorted: bool = False) -> CSRGraph:
+    """Facet 1-ring CSR with the self entry (data_util.build_facet_graph).  Syncs once.
+    vf_sorted: every row of vf is ascending with its -1 pads last (topology.DeviceTriMesh) - merge instead of sort."""
     _need_cuda(fv, vf)
     lib = _lib.load()
     fv, vf = fv.contiguous().long(), vf.contiguous().long()
@@ -282,11 +283,17 @@ def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor) -> CSRGraph:
     dev = fv.device
     rowptr = torch.empty(f + 1, dtype=torch.int32, device=dev)
     nbr = torch.empty(max(3 * k * f, 1), dtype=torch.int32, device=dev)
-    ws = _ws(lib.geobi_build_facet_graph_ws_bytes(f, k), dev)
     nnz = C.c_int64(0)
-    _lib.check(lib.geobi_build_facet_graph(_ptr(fv), _ptr(vf), f, v, k, _ptr(rowptr), _ptr(nbr), C.byref(nnz), _ptr(ws), ws.numel(),
-                                           _stream()), "build_facet_graph")
-    _count(4)
+    if vf_sorted:
+        ws = _ws(lib.geobi_build_facet_graph_sorted_ws_bytes(f), dev)
+        _lib.check(lib.geobi_build_facet_graph_sorted(_ptr(fv), _ptr(vf), f, v, k, _ptr(rowptr), _ptr(nbr), C.byref(nnz), _ptr(ws), ws.numel(),
+                                                      _stream()), "build_facet_graph_sorted")
+        _count(3)
+    else:
+        ws = _ws(lib.geobi_build_facet_graph_ws_bytes(f, k), dev)
+        _lib.check(lib.geobi_build_facet_graph(_ptr(fv), _ptr(vf), f, v, k, _ptr(rowptr), _ptr(nbr), C.byref(nnz), _ptr(ws), ws.numel(),
+                                               _stream()), "build_facet_graph")
+        _count(4)
     n = int(nnz.value)
     return CSRGraph(rowptr, nbr[:n].clone(), f, n, None, True)
 

@@ -48,6 +48,7 @@ class DeviceTriMesh:
         cols = torch.arange(members.numel(), device=dev) - torch.repeat_interleave(mrowptr[:-1].long(), cnt)
         self.vf = torch.full((V, k), -1, dtype=torch.int64, device=dev)
         self.vf[rows, cols] = self.vf_members.long()
+        self.vf_sorted = True          # rows ascending, pads last: lets build_facet_graph merge instead of sort
         self.update_normals()
 
     def update_normals(self):

@@ -114,6 +114,11 @@ GEOBI_API size_t geobi_build_facet_graph_ws_bytes(int64_t n_faces, int64_t k);
 GEOBI_API int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts,
                             int64_t k, int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws,
                             size_t ws_bytes, void* stream);
+/* The same graph when every vf row is ASCENDING with its -1 pads at the end (topology.DeviceTriMesh): a three-way merge per face
+ * instead of a fill + per-row sort.  An unsorted row is detected on the device (GEOBI_ERR_RANGE at the sync). */
+GEOBI_API size_t geobi_build_facet_graph_sorted_ws_bytes(int64_t n_faces);
+GEOBI_API int geobi_build_facet_graph_sorted(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts, int64_t k,
+                                             int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream);
 
 /* Heavy-edge matching identical to torch_cluster.graclus's serial CPU kernel for the visiting
  * order `perm` (net_util.py:127), computed in parallel: a node acts when it precedes all its

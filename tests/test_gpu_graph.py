@@ -258,3 +258,26 @@ def test_pool_edges_fused_rows_equal_generic_pipeline_including_long_rows():
     # no weights
     f2 = ops.pool_edges(g.with_weight(None), cluster, mrowptr, members, nc)
     assert f2.nnz == generic.nnz and torch.equal(f2.nbr, generic.nbr) and f2.w is None
+
+
+@pytest.mark.gpu
+def test_facet_graph_from_sorted_incidence_equals_the_general_builder():
+    """geobi_build_facet_graph_sorted (three-way merge of ascending vf rows) gives the CSR of the fill + sort builder bit for bit, on a
+    closed mesh, an open one (ragged valences) and a mesh with an isolated vertex; an unsorted row is rejected."""
+    import numpy as np
+    from geobi_gnn_b200 import _lib, ops, synth, topology
+    cases = []
+    p, f = synth.icosphere(9)
+    cases.append((p, f))
+    cases.append((p, f[: f.shape[0] // 3]))                      # open mesh: boundary vertices of valence 1..5
+    cases.append((np.concatenate([p, [[2.0, 0, 0]]]), f))         # one vertex without faces (an all -1 row)
+    for pts, fcs in cases:
+        m = topology.DeviceTriMesh(pts, fcs, "cuda")
+        a = ops.build_facet_graph_csr(m.fv, m.vf, vf_sorted=True)
+        b = ops.build_facet_graph_csr(m.fv, m.vf, vf_sorted=False)
+        assert a.nnz == b.nnz and torch.equal(a.rowptr, b.rowptr) and torch.equal(a.nbr, b.nbr)
+    m = topology.DeviceTriMesh(p, f, "cuda")
+    vf_bad = m.vf.clone()
+    vf_bad[5, :2] = vf_bad[5, :2].flip(0)
+    with pytest.raises(_lib.GeobiError):
+        ops.build_facet_graph_csr(m.fv, vf_bad, vf_sorted=True)
