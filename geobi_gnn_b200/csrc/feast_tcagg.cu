@@ -35,6 +35,10 @@ constexpr int PAIRS = TILE / 2;
 constexpr int G = 10;                 // producer warps (768 threads: ptxas grants 80 registers up to that count anyway)
 constexpr int R = 14;                 // ring slots, one node pair (2 x (x_hi, x_lo, q)) each; all the shared memory left
 constexpr int DS = 8;                 // aggregation accumulator slots in TMEM (one node pair each)
+#ifndef TCAGG_AB
+#define TCAGG_AB 4
+#endif
+constexpr uint32_t AB = TCAGG_AB;     // node pairs the aggregation warp waits for and issues together (2 or 4; commits are per two slots)
 // tcgen05.commit is not free (probe: +58 clk per pair when every pair commits, profiles/micro/tc_ts_probe.cu): ring slots and
 // accumulator slots are released / published two at a time - xfree[slot >> 1], dfull[dslot >> 1] - by one commit each.
 constexpr int NSETS = 2;               // drain sets (4 quadrant warps each) taking node pairs in turn
@@ -430,25 +434,25 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
         const uint32_t p0 = (uint32_t)(PAIRS * t);
         const uint32_t s0 = seq_base % R, k0 = (seq_base / R) & 1u, d0 = p0 % DS, dk0 = (p0 / DS) & 1u;
 #pragma unroll 1
-        for (uint32_t b4 = 0; b4 < PAIRS; b4 += 4) {
-          {   // lanes 0-3: full[pair b4 + lane]; lanes 4-7: dfree[pair b4 + lane - 4]
-            const uint32_t q = b4 + (lane & 3);
+        for (uint32_t b4 = 0; b4 < PAIRS; b4 += AB) {
+          {   // lanes 0..AB-1: full[pair b4 + lane]; lanes AB..2AB-1: dfree[pair b4 + lane - AB]
+            const uint32_t q = b4 + (lane % AB);
             uint32_t s = s0 + q, ks = k0, d = d0 + q, kd = dk0 ^ 1u;
             if (s >= R) { s -= R; ks ^= 1u; }
             if (s >= R) { s -= R; ks ^= 1u; }
             if (d >= DS) { d -= DS; kd ^= 1u; }
             if (d >= DS) { d -= DS; kd ^= 1u; }
             TLW(1, (int)(p0 + b4) - 128, 0);
-            if (lane < 8) WAIT_U(lane < 4 ? full_u + 8 * s : dfree_u + 8 * d, lane < 4 ? ks : kd, 1);
+            if (lane < 2 * AB) WAIT_U(lane < AB ? full_u + 8 * s : dfree_u + 8 * d, lane < AB ? ks : kd, 1);
             __syncwarp();
           }
 #ifdef TCAGG_TIMELINE
-          for (int q = 0; q < 4; ++q) { TLW(1, (int)(p0 + b4) + q - 128, 1); TLW(1, (int)(p0 + b4) + q - 128, 2); }
+          for (int q = 0; q < (int)AB; ++q) { TLW(1, (int)(p0 + b4) + q - 128, 1); TLW(1, (int)(p0 + b4) + q - 128, 2); }
 #endif
           tc_fence_after();
           if (elect_one()) {
 #pragma unroll
-            for (uint32_t q = 0; q < 4; ++q) {
+            for (uint32_t q = 0; q < AB; ++q) {
               uint32_t s = s0 + b4 + q, d = d0 + b4 + q;
               if (s >= R) s -= R;
               if (s >= R) s -= R;
@@ -456,11 +460,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
               if (d >= DS) d -= DS;
               issue_pair(s, d, 0u, true);
             }
-            *(volatile uint32_t*)&agg_pos = seq_base + b4 + 4;
+            *(volatile uint32_t*)&agg_pos = seq_base + b4 + AB;
           }
           __syncwarp();
 #ifdef TCAGG_TIMELINE
-          for (int q = 0; q < 4; ++q) TLW(1, (int)(p0 + b4) + q - 128, 3);
+          for (int q = 0; q < (int)AB; ++q) TLW(1, (int)(p0 + b4) + q - 128, 3);
 #endif
         }
       } else {

@@ -5,14 +5,17 @@ import bench
 from geobi_gnn_b200 import batching, config, dataset, network
 config.set_precision(os.environ.get("GEOBI_PRECISION", "bf16x3"))
 dev = torch.device("cuda")
-patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in bench.patch_meshes(bench.N_PATCHES, 0)]
-dv, df, _ = batching.collate_dual(patches)
+if os.environ.get("WORKLOAD", "mesh1m") == "patches":
+    patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in bench.patch_meshes(bench.N_PATCHES, 0)]
+    dv, df, _ = batching.collate_dual(patches)
+else:
+    dv, df = dataset.build_dual_on_device(bench.noisy_device_mesh(bench.MESH_FREQ, 0, dev), None)
 torch.manual_seed(0)
 net = network.DualGNN().to(dev).eval()
 def step():
     with torch.no_grad():
         return net([batching.fresh_view(dv), batching.fresh_view(df)])
-for _ in range(4): step()
+for _ in range(12): step()
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
