@@ -32,7 +32,22 @@ using namespace tc;
 constexpr int C_IN = 64, C_OUT = 32;
 constexpr int TILE = 32;              // nodes per projection tile = MMA N
 constexpr int PAIRS = TILE / 2;
-constexpr int G = 10;                 // producer warps (768 threads: ptxas grants 80 registers up to that count anyway)
+// Build knobs (profiles/build_variant.sh builds A/B copies of the library; history and measurements in profiles/r02_NOTES.md A5).
+// The defaults are the fastest combination measured; -DTCAGG_CLASSIC restores the first design (software-pipelined producers,
+// whole-tile Z hand-over, 32-column drain loads, hinted try_wait everywhere, 10 producers).
+#ifndef TCAGG_CLASSIC
+#define TCAGG_SEQ 1          // producers take one item at a time (latency hidden by 12 warps, not by a 3-stage pipeline)
+#define TCAGG_ZHALF 1        // Z handed to the projection in two 16-node halves
+#define TCAGG_LD18 1         // drain warps read only the 18 useful accumulator columns
+#define TCAGG_SLEEPWAIT 1    // long waits: test_wait + plain nanosleep instead of the hinted try_wait loop
+#ifndef TCAGG_G
+#define TCAGG_G 12
+#endif
+#endif
+#ifndef TCAGG_G
+#define TCAGG_G 10
+#endif
+constexpr int G = TCAGG_G;            // producer warps (768 threads: ptxas grants 80 registers up to that count anyway)
 constexpr int R = 14;                 // ring slots, one node pair (2 x (x_hi, x_lo, q)) each; all the shared memory left
 constexpr int DS = 8;                 // aggregation accumulator slots in TMEM (one node pair each)
 #ifndef TCAGG_AB
@@ -41,8 +56,27 @@ constexpr int DS = 8;                 // aggregation accumulator slots in TMEM (
 constexpr uint32_t AB = TCAGG_AB;     // node pairs the aggregation warp waits for and issues together (2 or 4; commits are per two slots)
 // tcgen05.commit is not free (probe: +58 clk per pair when every pair commits, profiles/micro/tc_ts_probe.cu): ring slots and
 // accumulator slots are released / published two at a time - xfree[slot >> 1], dfull[dslot >> 1] - by one commit each.
-constexpr int NSETS = 2;               // drain sets (4 quadrant warps each) taking node pairs in turn
+#ifndef TCAGG_NSETS
+#define TCAGG_NSETS 2
+#endif
+constexpr int NSETS = TCAGG_NSETS;               // drain sets (4 quadrant warps each) taking node pairs in turn
 constexpr int EPI_WARPS = 4, DRAIN_WARPS = 4 * NSETS;
+// TCAGG_ZHALF: the Z tile is handed to the projection in two halves of 16 nodes (N = 16 MMAs): the projection of nodes 0-15 runs
+// while nodes 16-31 are drained and is long finished when the drain warps come back to rows 0-15 with the next tile - without it
+// the drain warps stop at every tile boundary until all 72 projection MMAs of the previous tile have read the (single) Z buffer
+#ifdef TCAGG_ZHALF
+constexpr int ZH = 2;
+#else
+constexpr int ZH = 1;
+#endif
+constexpr int ZPAIRS = PAIRS / ZH;               // node pairs per hand-over unit
+#ifdef TCAGG_ZARRIVE_PAIR
+static_assert(ZH == 1, "per-pair arrival is the old whole-tile protocol");
+constexpr uint32_t ZFULL_COUNT = PAIRS * 4;      // every drain warp arrives after every pair
+#else
+constexpr uint32_t ZFULL_COUNT = DRAIN_WARPS;    // every drain warp arrives once per tile, after its last pair of the tile
+static_assert(ZPAIRS % NSETS == 0, "each drain set takes the same pairs of every tile (half)");
+#endif
 constexpr int AGG_WARP = EPI_WARPS + DRAIN_WARPS;   // issues the aggregation MMAs
 constexpr int PROJ_WARP = AGG_WARP + 1;              // issues the projection MMAs
 constexpr int PROD_WARP0 = PROJ_WARP + 1;
@@ -104,6 +138,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the 18 useful columns of an aggregation accumulator (q_hi heads at columns 0-8, q_lo heads at 16-24): r[h] and r[9 + h]
+__device__ __forceinline__ void tmem_ld18_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%18];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%8}, [%19];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%9, %10, %11, %12, %13, %14, %15, %16}, [%20];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%17}, [%21];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17])
+      : "r"(taddr), "r"(taddr + 8), "r"(taddr + 16), "r"(taddr + 24)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -128,6 +174,22 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t addr, uint32_t parity) {
       "bra WAIT_LOOP_%=;\n\t"
       "DONE_%=:\n\t}"
       ::"r"(addr), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+// wait for long expected waits: non-blocking probe + a plain timed sleep.  The hinted try_wait above compiles to
+// SYNCS.TRYWAIT / NANOSLEEP.SYNCS / SYNCS.PHASECHK loops in which every mbarrier event of the CTA wakes every sleeper: ncu counted
+// ~450 SYNCS per node pair (20 % of the shared-memory data pipe, 44 % of the issued instructions with their branches) with ~100
+// iterations per producer / drain / epilogue wait.  A plain nanosleep is not woken by barrier traffic.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t addr, uint32_t parity, uint32_t ns) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "SWAIT_LOOP_%=:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SDONE_%=;\n\t"
+      "nanosleep.u32 %2;\n\t"
+      "bra SWAIT_LOOP_%=;\n\t"
+      "SDONE_%=:\n\t}"
+      ::"r"(addr), "r"(parity), "r"(ns)
       : "memory");
 }
 // non-blocking probe of an mbarrier phase (warp-uniform answer: lane 0 tests, the result is broadcast)
@@ -178,6 +240,20 @@ __device__ __forceinline__ void wait_dbg(uint64_t* bar, uint32_t parity, int tag
 #define PROGRESS(idx, val) do { } while (0)
 #define WAIT(bar, parity, tag) mbar_wait_u(smem_u32(bar), parity)
 #define WAIT_U(addr, parity, tag) mbar_wait_u(addr, parity)
+#endif
+#if defined(TCAGG_SLEEPWAIT) && !defined(TCAGG_DEBUG)
+#define WAIT_LONG(bar, parity, tag, ns) mbar_wait_sleep(smem_u32(bar), parity, ns)
+#else
+#define WAIT_LONG(bar, parity, tag, ns) WAIT(bar, parity, tag)
+#endif
+#ifndef TCAGG_NS_X
+#define TCAGG_NS_X 64
+#endif
+#ifndef TCAGG_NS_Z
+#define TCAGG_NS_Z 64
+#endif
+#ifndef TCAGG_NS_O
+#define TCAGG_NS_O 256
 #endif
 __device__ __forceinline__ void mma_commit_u(uint32_t bar_addr) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
@@ -277,18 +353,18 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
                                                                        float slope, float* __restrict__ out, int64_t ldo) {
   extern __shared__ uint8_t smem_raw[];
   // one array so that the debug build can name a barrier by its index: full | xfree | dfull | dfree | zfull | zfree | ofull | ofree
-  __shared__ __align__(8) uint64_t bars[R + R / 2 + DS / 2 + DS + 6];
+  __shared__ __align__(8) uint64_t bars[R + R / 2 + DS / 2 + DS + 8];
   uint64_t* const full = bars;                          // [R]      per ring slot
   uint64_t* const xfree = bars + R;                     // [R / 2]  per pair of ring slots
   uint64_t* const dfull = bars + R + R / 2;             // [DS / 2] per pair of accumulator slots
   uint64_t* const dfree = bars + R + R / 2 + DS / 2;    // [DS]     per accumulator slot
-  uint64_t& zfull = bars[R + R / 2 + DS / 2 + DS];
-  uint64_t& zfree = bars[R + R / 2 + DS / 2 + DS + 1];
-  uint64_t* const ofull = bars + R + R / 2 + DS / 2 + DS + 2;
-  uint64_t* const ofree = bars + R + R / 2 + DS / 2 + DS + 4;
+  uint64_t* const zfull = bars + R + R / 2 + DS / 2 + DS;        // [ZH] per node half of the Z tile (ZH = 1: the whole tile)
+  uint64_t* const zfree = bars + R + R / 2 + DS / 2 + DS + 2;    // [ZH]
+  uint64_t* const ofull = bars + R + R / 2 + DS / 2 + DS + 4;
+  uint64_t* const ofree = bars + R + R / 2 + DS / 2 + DS + 6;
   __shared__ uint32_t tmem_slot;
   __shared__ uint32_t agg_pos;      // ring sequence numbers issued so far by the aggregation-issue warp (see `slot_reusable`)
-  __shared__ float chs[12];
+  __shared__ __align__(16) float chs[12];
   __shared__ __align__(16) int jbuf[G][32];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -303,8 +379,8 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     for (int i = 0; i < R / 2; ++i) mbar_init(&xfree[i], 1);
     for (int i = 0; i < DS / 2; ++i) mbar_init(&dfull[i], 1);
     for (int i = 0; i < DS; ++i) mbar_init(&dfree[i], 4);
-    mbar_init(&zfull, PAIRS * 4);
-    mbar_init(&zfree, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&zfull[i], ZFULL_COUNT);
+    for (int i = 0; i < 2; ++i) mbar_init(&zfree[i], 1);
     mbar_init(&ofull[0], 1);
     mbar_init(&ofull[1], 1);
     mbar_init(&ofree[0], EPI_WARPS);
@@ -475,33 +551,39 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     }
   } else if (warp == PROJ_WARP) {
     // ================================================== projection MMA issue ==================================================
-    constexpr uint32_t IP = idesc_of(64, 32, 0, 0), ZHI = desc_hi(64, 2);
+    constexpr uint32_t IP = idesc_of(64, TILE / ZH, 0, 0), ZHI = desc_hi(64, 2);
     const uint32_t zh_lo = ((smem_u32(z_hi) & 0x3FFFFu) >> 4) | (1u << 16), zl_lo = ((smem_u32(z_lo) & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
       const uint32_t b = t & 1;
-      TLW(3, t - 8, 0);
-      WAIT(&zfull, t & 1, 3);
-      TLW(3, t - 8, 1);
-      WAIT(&ofree[b], ((t >> 1) & 1) ^ 1, 4);
-      TLW(3, t - 8, 2);
-      tc_fence_after();
-      if (elect_one()) {
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const uint32_t d = tmem + COL_O + 32 * b + hf * HALF, a0 = tmem + COL_W + hf * HALF;
-#pragma unroll 2
-          for (int i = 0; i < 18; ++i) {
-            const int ks = 18 * hf + i;
-            const uint32_t zoff = (uint32_t)(ks >> 2) * (ZCHUNK >> 4) + 2 * (ks & 3);
-            mma_ts(d, a0 + 8 * i, zh_lo + zoff, ZHI, IP, i > 0);
-            mma_ts(d, a0 + 8 * i, zl_lo + zoff, ZHI, IP, 1u);
-          }
+#pragma unroll 1
+      for (int nh = 0; nh < ZH; ++nh) {      // node half: Z rows 16 nh .. (2048 bytes into every 64-column chunk), accumulator columns 16 nh ..
+        if (nh == 0) TLW(3, t - 8, 0);
+        WAIT_LONG(&zfull[nh], t & 1, 3, TCAGG_NS_Z);
+        if (nh == 0) {
+          TLW(3, t - 8, 1);
+          WAIT(&ofree[b], ((t >> 1) & 1) ^ 1, 4);
+          TLW(3, t - 8, 2);
         }
-        mma_commit(&zfree);
-        mma_commit(&ofull[b]);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t zrow = (uint32_t)nh * (2048u >> 4), dcol = (uint32_t)nh * (TILE / ZH);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t d = tmem + COL_O + 32 * b + dcol + hf * HALF, a0 = tmem + COL_W + hf * HALF;
+#pragma unroll 2
+            for (int i = 0; i < 18; ++i) {
+              const int ks = 18 * hf + i;
+              const uint32_t zoff = (uint32_t)(ks >> 2) * (ZCHUNK >> 4) + 2 * (ks & 3) + zrow;
+              mma_ts(d, a0 + 8 * i, zh_lo + zoff, ZHI, IP, i > 0);
+              mma_ts(d, a0 + 8 * i, zl_lo + zoff, ZHI, IP, 1u);
+            }
+          }
+          mma_commit(&zfree[nh]);
+          if (nh == ZH - 1) mma_commit(&ofull[b]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
       TLW(3, t - 8, 3);
     }
   } else if (warp < EPI_WARPS) {
@@ -512,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     const float my_bias = bias[o];
     for (int t = 0; t < T; ++t) {
       const uint32_t b = t & 1;
-      WAIT(&ofull[b], (t >> 1) & 1, 5);
+      WAIT_LONG(&ofull[b], (t >> 1) & 1, 5, TCAGG_NS_O);
       if (warp == 0) TLW(3, t - 8, 4);
       tc_fence_after();
       float* sb = stage + (t & 1) * (TILE * C_OUT);
@@ -560,16 +642,30 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     const uint32_t sw_pair = ((((uint32_t)(c & 31) >> 2) ^ (4u * half)) << 4) + (uint32_t)(c & 3) * 4 + (uint32_t)(c >> 5) * ZCHUNK + hconst;
     const uint32_t sw_h8 = ((((uint32_t)c >> 3) ^ (4u * half)) << 4) + (uint32_t)(c & 7) * 2 + 8 * ZCHUNK + hconst;
     const uint32_t lane_t = tmem + COL_D + ((uint32_t)(qd * 32) << 16);
-    uint32_t ra[32], rb[32];
-    auto dwait_ld = [&](int p, uint32_t (&r)[32]) {
+#ifdef TCAGG_LD18
+    constexpr int NR = 18, LO = 9;
+#else
+    constexpr int NR = 32, LO = 16;
+#endif
+#ifdef TCAGG_DRAIN1
+    uint32_t ra[NR];
+#else
+    uint32_t ra[NR], rb[NR];
+#endif
+#ifdef TCAGG_LD18
+#define DRAIN_LD tmem_ld18_issue
+#else
+#define DRAIN_LD tmem_ld32_issue
+#endif
+    auto dwait_ld = [&](int p, uint32_t (&r)[NR]) {
       const uint32_t dslot = (uint32_t)p % DS, dk = (uint32_t)p / DS;
       if (qd == 0) TLW(2, p - 128, 0);
       WAIT(&dfull[dslot >> 1], dk & 1, 6);
       if (qd == 0) TLW(2, p - 128, 1);
       tc_fence_after();
-      tmem_ld32_issue(lane_t + dslot * 32, r);
+      DRAIN_LD(lane_t + dslot * 32, r);
     };
-    auto process = [&](int p, uint32_t (&r)[32], int p_next, uint32_t (&rn)[32]) -> bool {
+    auto process = [&](int p, uint32_t (&r)[NR], int p_next, uint32_t (&rn)[NR]) -> bool {
       const int t = p >> 4, pp = p & 15;
       tmem_ld_wait();
       tc_fence_before();
@@ -578,18 +674,21 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       if (qd == 0) TLW(2, p - 128, 2);
       float z[H];
 #pragma unroll
-      for (int h = 0; h < H; ++h) z[h] = __uint_as_float(r[h]) + __uint_as_float(r[16 + h]);
+      for (int h = 0; h < H; ++h) z[h] = __uint_as_float(r[h]) + __uint_as_float(r[LO + h]);
       // the next pair's accumulator, if it is already complete: its TMEM read overlaps the split below
       bool pre = false;
+#ifndef TCAGG_DRAIN1
       if (p_next < npairs) {
         pre = phase_done(&dfull[((uint32_t)p_next % DS) >> 1], ((uint32_t)p_next / DS) & 1);
         if (pre) {
           tc_fence_after();
-          tmem_ld32_issue(lane_t + ((uint32_t)p_next % DS) * 32, rn);
+          DRAIN_LD(lane_t + ((uint32_t)p_next % DS) * 32, rn);
         }
       }
-      if (pp < NSETS && t >= 1) {   // first pair of this warp in tile t: the projection of tile t-1 must have finished reading Z
-        WAIT(&zfree, (t - 1) & 1, 7);
+#endif
+      const int zu = pp / ZPAIRS, zp = pp % ZPAIRS;
+      if (zp < NSETS && t >= 1) {   // first pair of this warp in this (half) tile: the projection of tile t-1 must have finished reading these Z rows
+        WAIT_LONG(&zfree[zu], (t - 1) & 1, 7, TCAGG_NS_Z);
         tc_fence_after();
       }
       if (qd == 0) TLW(2, p - 128, 3);
@@ -614,14 +713,30 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
         *reinterpret_cast<uint16_t*>(zl + off8) = (uint16_t)l1;
       }
       if (qd == 0) TLW(2, p - 128, 4);
+#ifdef TCAGG_ZARRIVE_PAIR
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&zfull);
+      if (lane == 0) mbar_arrive(&zfull[0]);
+#else
+      if (zp >= ZPAIRS - NSETS) {   // this warp's last pair of the (half) tile: one fence + arrival per warp and hand-over unit
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&zfull[zu]);
+      }
+#endif
       if (qd == 0) TLW(2, p - 128, 5);
       if (qd == 0) PROGRESS(34 + set, p + 1);
       return pre;
     };
     // two register sets alternate; `have` = the current set's TMEM read has been issued already
+#ifdef TCAGG_DRAIN1
+    // one register set, no look-ahead: for builds with more drain sets under a tighter register cap
+#pragma unroll 1
+    for (int p = set; p < npairs; p += NSETS) {
+      dwait_ld(p, ra);
+      process(p, ra, npairs, ra);
+    }
+#else
     bool have = false;
 #pragma unroll 1
     for (int p = set; p < npairs; p += 2 * NSETS) {
@@ -633,6 +748,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
         have = process(p2, rb, p2 + NSETS, ra);
       }
     }
+#endif
   } else {
     // ================================================== producers ==================================================
     const int g = warp - PROD_WARP0;
@@ -684,7 +800,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
         ++it_r;
       } else {
         if (p_next >= n_items) return it;                // bits = 0: not valid
-        if (it_t < (p_next >> 4)) {                      // enter the next tile: own pairs are G < 16 apart, so every warp walks every tile
+        while (it_t < (p_next >> 4)) {                   // enter the next tile (every warp walks every tile: the ring sequence numbers are cumulative)
           ++it_t;
           seq_base = next_base;
           ti = tile_info(t_begin + it_t, rb_n, re_n);
@@ -722,6 +838,8 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
     // and the previous one not even issued" - which happens once a producer runs two ring laps ahead of the issue warp (pairs that
     // take several rounds spread a warp's items further than R apart).  So the xfree wait of sequence number s is only entered
     // after the issue warp has issued s - R: from then on the barrier is at most one phase behind the one waited for.
+    uint32_t prev_seq = 0;
+    bool have_prev = false;
     auto occupant_issued = [&](uint32_t seq) { return seq < (uint32_t)R || *(volatile uint32_t*)&agg_pos + (uint32_t)R > seq; };
     // stage 1 of an item: ring slot free -> gathers in flight, P row of this lane's slot in flight
     auto begin = [&](const Item& it) {
@@ -736,8 +854,14 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       const int4* jv = reinterpret_cast<const int4*>(jb + half * 16);
       const int4 j0 = jv[0], j1 = jv[1], j2 = jv[2], j3 = jv[3];
       const int jr[16] = {j0.x, j0.y, j0.z, j0.w, j1.x, j1.y, j1.z, j1.w, j2.x, j2.y, j2.z, j2.w, j3.x, j3.y, j3.z, j3.w};
-      while (!occupant_issued(it.seq)) __nanosleep(256);
-      WAIT(&xfree[slot >> 1], it.par(), 8);
+      // fast path: this warp's previous item passed its own xfree wait, so everything up to prev_seq - R has been consumed (the issue
+      // warp works in order); if the slot's occupant two laps back (seq - 2R) is among that, the barrier is at most one phase behind
+      // and the poll of agg_pos (one shared-memory wavefront per probe: it was a quarter of the kernel's shared traffic) is not needed
+      if (!(have_prev && it.seq - prev_seq <= (uint32_t)R))
+        while (!occupant_issued(it.seq)) __nanosleep(256);
+      prev_seq = it.seq;
+      have_prev = true;
+      WAIT_LONG(&xfree[slot >> 1], it.par(), 8, TCAGG_NS_X);
       TLW(0, ITEM_P(it) - 128, 1);
       tc_fence_after();
       const uint32_t sbase = ring_u32 + slot * SLOT_BYTES;
@@ -751,10 +875,11 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       // the lane's P row (48 B) travels through its own (still unused) q row of the slot: read back in stage 2
       if (it.has()) {
         const uint8_t* pr = reinterpret_cast<const uint8_t*>(P + (size_t)(unsigned)it.j * PROW);
+        // chunk c of the row at position c ^ qx (the q tile's own swizzle): the 64-byte pitch alone puts every other lane on the same banks
         const uint32_t pdst = sbase + qrow;
-        cp_async16(pdst, pr);
-        cp_async16(pdst + 16, pr + 16);
-        cp_async16(pdst + 32, pr + 32);
+        cp_async16(pdst + ((0u ^ qx) << 4), pr);
+        cp_async16(pdst + ((1u ^ qx) << 4), pr + 16);
+        cp_async16(pdst + ((2u ^ qx) << 4), pr + 32);
       }
       cp_async_commit();
       TLW(0, ITEM_P(it) - 128, 2);
@@ -768,9 +893,9 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       else cp_async_wait<0>();
       TLW(0, ITEM_P(it) - 128, 5);
       __syncwarp();            // the self slot's P row (lane 0 / 16 of the node's half warp) was written by another lane's copy
-      const float4* pq = reinterpret_cast<const float4*>(sl_base + qrow);
-      const float4 Pc0 = pq[0], Pc1 = pq[1];
-      const float pc8 = reinterpret_cast<const float*>(pq)[8];
+      const uint8_t* pq = sl_base + qrow;
+      const float4 Pc0 = *reinterpret_cast<const float4*>(pq + ((0u ^ qx) << 4)), Pc1 = *reinterpret_cast<const float4*>(pq + ((1u ^ qx) << 4));
+      const float pc8 = *reinterpret_cast<const float*>(pq + ((2u ^ qx) << 4));
       float4 Pi0, Pi1;
       float pi8;
       if (it.first()) {      // slot 0 of round 0 is the node itself
@@ -787,11 +912,13 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       __syncwarp();            // every lane has read the P rows before any q row overwrites them
       const float pj[H] = {Pc0.x, Pc0.y, Pc0.z, Pc0.w, Pc1.x, Pc1.y, Pc1.z, Pc1.w, pc8};
       const float pi[H] = {Pi0.x, Pi0.y, Pi0.z, Pi0.w, Pi1.x, Pi1.y, Pi1.z, Pi1.w, pi8};
+      const float4 c0 = *reinterpret_cast<const float4*>(chs), c1 = *reinterpret_cast<const float4*>(chs + 4);
+      const float cc[H] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, chs[8]};
       float l[H];
       float m = -INFINITY;
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        l[h] = (pj[h] - pi[h]) + chs[h];
+        l[h] = (pj[h] - pi[h]) + cc[h];
         m = fmaxf(m, l[h]);
       }
       const float mb = -m * 1.4426950408889634f;
@@ -830,6 +957,16 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
 
     // three-stage software pipeline, one call site per stage (the loop body has to stay inside the instruction cache):
     //   iteration k: index loads of item k | gathers + P loads of item k-1 | soft assignments + hand-over of item k-2
+#ifdef TCAGG_SEQ
+    // one item at a time per warp: latency is hidden by the number of producer warps instead of a software pipeline
+#pragma unroll 1
+    for (;;) {
+      const Item n = next_item();
+      if (!n.valid()) break;
+      begin(n);
+      finish(n, false);
+    }
+#else
     Item a{}, b{};                     // a: indices in flight; b: gathers in flight
 #pragma unroll 1
     for (;;) {
@@ -851,6 +988,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_tcagg_64_32_kernel(const uin
       a = n;
       if (!a.valid() && !b.valid()) break;
     }
+#endif
   }
 
   tc_fence_before();

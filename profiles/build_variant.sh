@@ -10,4 +10,4 @@ nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler
   -I../../include -I. "$@" -Xptxas -v -c feast_tcagg.cu -o build/var/feast_tcagg_$name.o 2> build/var/$name.ptxas.log
 objs=$(ls build/*.o | grep -v feast_tcagg.o)
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../build_variants/libgeobi_$name.so $objs build/var/feast_tcagg_$name.o -cudart static
-grep -A2 "tcagg_kernel" build/var/$name.ptxas.log | grep -i "registers\|spill" | head -4
+grep -A3 "feast_tcagg_64_32_kernel" build/var/$name.ptxas.log | grep -i "registers\|spill" | head -6

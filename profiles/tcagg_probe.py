@@ -25,7 +25,7 @@ def debug_dump(label):
         for i in range(32):
             if v[i]:
                 b = (int(v[i]) >> 8) & 0xffff
-                names = [("full", 14), ("xfree", 7), ("dfull", 4), ("dfree", 8), ("zfull", 1), ("zfree", 1), ("ofull", 2), ("ofree", 2)]
+                names = [("full", 14), ("xfree", 7), ("dfull", 4), ("dfree", 8), ("zfull", 2), ("zfree", 2), ("ofull", 2), ("ofree", 2)]
                 nm = "?"
                 for name, cnt in names:
                     if b < cnt:
