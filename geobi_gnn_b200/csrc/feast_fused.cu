@@ -42,7 +42,9 @@ constexpr int PLANE_BYTES = KB * TILE_BYTES;
 constexpr int ZTILE_BYTES = NT * 128;  // Z: [NT node rows x 128 B] of one K block
 constexpr int ZPLANE_BYTES = KB * ZTILE_BYTES;
 constexpr int QROW = 12;          // floats per soft-assignment row (9 used; 48-byte rows keep the float4 reads aligned)
-constexpr int SCRATCH = 32 * QROW * 4;   // per-warp scratch: the soft-assignment rows of the chunk's 32 slots
+constexpr int QPAD = 4;           // floats between the two nodes' halves: without it their rows sit 768 B apart = on the same banks, and every
+                                  // broadcast read of the pair loop (one address per half warp) took two shared-memory wavefronts
+constexpr int SCRATCH = (32 * QROW + QPAD) * 4;   // per-warp scratch: the soft-assignment rows of the chunk's 32 slots
 constexpr int SMEM_BYTES = 2 * PLANE_BYTES + 2 * ZPLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * SCRATCH + WARPS * 32 * 4 + 64 + 1024;
 
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
@@ -348,13 +350,13 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
         for (int h = 0; h < H; ++h) l[h] = rcnt * (1.0f / 9.0f);
       }
 #endif
-      float4* q4 = reinterpret_cast<float4*>(qs + lane * QROW);
+      float4* q4 = reinterpret_cast<float4*>(qs + lane * QROW + g * QPAD);
       q4[0] = make_float4(l[0], l[1], l[2], l[3]);
       q4[1] = make_float4(l[4], l[5], l[6], l[7]);
-      qs[lane * QROW + 8] = l[8];
+      qs[lane * QROW + g * QPAD + 8] = l[8];
       if (s0 == 0) TS(2);
       __syncwarp();
-      const float* qbase = qs + g * LPN * QROW;
+      const float* qbase = qs + g * (LPN * QROW + QPAD);
       const unsigned* jbase = joffs + g * LPN;
       // slots >= total hold zero assignments and a valid row (the node's own), so pairs need no tail handling
       auto consume = [&](const ulonglong2& va, const ulonglong2& vb, int t) {
