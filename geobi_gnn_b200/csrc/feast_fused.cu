@@ -4,11 +4,18 @@
 //   per tile of 32 target nodes (16 aggregation warps x 2 nodes, lanes own 4 adjacent channels):
 //     1. aggregate Z_i[h, :] = 1/d_i sum_j q_ijh x_j in registers (1/d_i folded into the soft assignments),
 //     2. write the rows, split x = hi + lo (bf16), straight into the K-major SWIZZLE_128B *B-operand* tiles in shared memory,
-//     3. warp 18 issues tcgen05.mma (M = 64: the weight tile W_flat[32 (+32 aliased) x 576] is the resident A operand,
-//        N = 32 nodes, 36 K-steps x 3 split passes) -> D^T[channel, node] in one of two TMEM accumulators,
-//     4. warps 16 and 17 drain that accumulator (+bias, leaky_relu) and write out[node, channel] while the next tile's MMAs
-//        fill the other one; the aggregation warps never touch TMEM, they only wait for the MMAs of tile t-1 before
-//        overwriting the operand tiles with tile t.
+//     3. warp 18 issues tcgen05.mma with the weights as the A operand IN TENSOR MEMORY (loaded once per CTA: output o = row o of an
+//        M = 64 tile whose rows 32-63 are unused; the bf16 hi plane of W sits in lanes 0-15 and the lo plane in lanes 16-31 of TMEM
+//        quadrants 0 and 1), N = 32 nodes, 36 K steps x {W_hi Z_hi, W_hi Z_lo, W_lo Z_hi} = 108 MMAs -> D^T[channel, node] in one of
+//        two TMEM accumulators (the hi-plane and lo-plane partial sums in the two lane halves),
+//     4. warps 16 and 17 drain that accumulator (partials added by a lane shuffle, +bias, leaky_relu) and write out[node, channel]
+//        while the next tile's MMAs fill the other one; the aggregation warps never touch TMEM, they only wait for the MMAs of
+//        tile t-1 before overwriting the operand tiles with tile t.
+//
+// Round 2: the weights moved from shared memory (108 SS MMAs per tile, each re-reading a 2 KB weight block: 81 of the kernel's
+// 165 shared-memory wavefronts per node, ncu: data pipe 87 % busy) to tensor memory (108 TS MMAs that read only the 1 KB Z block:
+// 27 wavefronts per node).  Stacking [W_hi; W_lo] on M (72 MMAs) needs four drain warps = 672 threads, which drops the register
+// cap from 96 to 80 and spills the aggregation warps' accumulators.
 //
 // Z (2.3 KB per node) never reaches HBM: per node the kernel reads 256 B of x per gathered row (L2) + 72 B of P, and writes
 // 128 B.  The unfused path writes and re-reads 2 x 2.3 KB per node (ncu: 1.12 GB written by the aggregation of one layer).
@@ -32,20 +39,21 @@ constexpr int C_IN = 64, C_OUT = 32;
 constexpr int WARPS = FUSED_WARPS;   // aggregation warps, 2 nodes each (a multiple of 4: the drain warps must be warps 0, 1 mod 4)
 constexpr int NT = 2 * WARPS;        // nodes per tile = MMA N
 static_assert(WARPS % 4 == 0 && NT % 8 == 0 && NT <= 64, "tile shape");
-constexpr int ACC_COLS = 64;         // TMEM column pitch of the two accumulators
 constexpr int EPI_WARPS = 2;      // warps 16, 17 drain TMEM quadrants 0, 1 (a warp reaches lanes 32*(warp%4)..+31)
 constexpr int MMA_WARP = WARPS + EPI_WARPS;   // warp 18 issues the MMAs
 constexpr int THREADS = (WARPS + EPI_WARPS + 1) * 32;
 constexpr int KB = H;             // one 64-wide K block per head
-constexpr int TILE_BYTES = 32 * 128;   // W: [32 channel rows x 128 B] of one K block
-constexpr int PLANE_BYTES = KB * TILE_BYTES;
+constexpr int KSTEPS = KB * 4;    // K = 16 steps
 constexpr int ZTILE_BYTES = NT * 128;  // Z: [NT node rows x 128 B] of one K block
 constexpr int ZPLANE_BYTES = KB * ZTILE_BYTES;
+// tensor memory: weights in columns [0, 288) (hi plane in lanes 0-15, lo plane in lanes 16-31), then the two accumulators (NT columns each)
+constexpr uint32_t COL_W = 0, COL_D = KSTEPS * 8, TMEM_COLS = 512, HALF = 16u << 16;
+static_assert(COL_D + 2 * NT <= TMEM_COLS, "tensor memory budget");
 constexpr int QROW = 12;          // floats per soft-assignment row (9 used; 48-byte rows keep the float4 reads aligned)
 constexpr int QPAD = 4;           // floats between the two nodes' halves: without it their rows sit 768 B apart = on the same banks, and every
                                   // broadcast read of the pair loop (one address per half warp) took two shared-memory wavefronts
 constexpr int SCRATCH = (32 * QROW + QPAD) * 4;   // per-warp scratch: the soft-assignment rows of the chunk's 32 slots
-constexpr int SMEM_BYTES = 2 * PLANE_BYTES + 2 * ZPLANE_BYTES + TILE_BYTES /* A-operand over-read */ + WARPS * SCRATCH + WARPS * 32 * 4 + 64 + 1024;
+constexpr int SMEM_BYTES = 2 * ZPLANE_BYTES + WARPS * SCRATCH + WARPS * 32 * 4 + 64 + 1024;
 
 __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
                                                                        const int* __restrict__ rowptr, const int* __restrict__ nbr,
                                                                        const int* __restrict__ row_map,
                                                                        const double* __restrict__ P, const float* __restrict__ cvec,
-                                                                       const __nv_bfloat16* __restrict__ Wq /* hi | lo, [32][576] each */,
+                                                                       const uint32_t* __restrict__ Wp /* [36 K steps][64 stacked rows][8] bf16 pairs */,
                                                                        const float* __restrict__ bias, float slope, float* __restrict__ out,
                                                                        int64_t ldo) {
   extern __shared__ uint8_t smem_raw[];
@@ -97,18 +105,14 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* w_hi = sm;
-  uint8_t* w_lo = sm + PLANE_BYTES;
-  // the A operand (M = 64) over-reads 32 rows past each W tile: after the last W_lo tile that is the first Z tile - harmless
-  // (those accumulator rows are never read), and the spare TILE_BYTES keeps the Z planes 1024-byte aligned
-  uint8_t* z_hi = sm + 2 * PLANE_BYTES;
-  uint8_t* z_lo = sm + 2 * PLANE_BYTES + ZPLANE_BYTES;
-  uint8_t* scratch_all = sm + 2 * PLANE_BYTES + 2 * ZPLANE_BYTES + TILE_BYTES;
+  uint8_t* z_hi = sm;
+  uint8_t* z_lo = sm + ZPLANE_BYTES;
+  uint8_t* scratch_all = sm + 2 * ZPLANE_BYTES;
   unsigned* joff_all = reinterpret_cast<unsigned*>(scratch_all + WARPS * SCRATCH);
   float* chs = reinterpret_cast<float*>(joff_all + WARPS * 32);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // ---- one-time setup: barrier, TMEM, resident weight tiles
+  // ---- one-time setup: barriers, TMEM, resident weights
   if (tid == 0) {
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
@@ -116,30 +120,36 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
     mbar_init(&acc_free[1], EPI_WARPS);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, 2 * ACC_COLS);
+  if (warp == MMA_WARP) tmem_alloc(&tmem_slot, TMEM_COLS);
   if (tid < H) chs[tid] = cvec[tid];
-  for (int idx = tid; idx < 2 * KB * 32 * 8; idx += THREADS) {
-    const int plane = idx / (KB * 32 * 8), rem = idx - plane * (KB * 32 * 8);
-    const int kb = rem / (32 * 8), r = (rem / 8) % 32, chk = rem % 8;
-    const uint4 v = *reinterpret_cast<const uint4*>(Wq + (int64_t)plane * C_OUT * (KB * 64) + (int64_t)r * (KB * 64) + kb * 64 + chk * 8);
-    *reinterpret_cast<uint4*>((plane ? w_lo : w_hi) + kb * TILE_BYTES + sw128_off(r, chk)) = v;
-  }
-  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_slot;
+  if (warp >= WARPS && warp < MMA_WARP) {
+    // weights -> tensor memory: lane l of quadrant warp q holds output row 16 q + (l & 15) of plane l >> 4 (stacked row 32 plane + output in Wp)
+    const int q = warp - WARPS, m = 32 * (lane >> 4) + 16 * q + (lane & 15);
+    const uint4* src = reinterpret_cast<const uint4*>(Wp);
+#pragma unroll 2
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      const uint4 a = __ldg(src + (ks * 64 + m) * 2), b = __ldg(src + (ks * 64 + m) * 2 + 1);
+      tmem_st8(tmem_d + COL_W + 8 * ks + ((uint32_t)(q * 32) << 16), a, b);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   const int64_t n_tiles = (N + NT - 1) / NT;
   const int64_t t_begin = (n_tiles * blockIdx.x) / gridDim.x, t_end = (n_tiles * (blockIdx.x + 1)) / gridDim.x;
 
   if (warp == MMA_WARP) {
-    // ===== MMA warp: per tile, wait for its rows, issue 36 K-steps x 3 split passes into accumulator k & 1, commit =====
+    // ===== MMA warp: per tile, wait for its rows, issue 36 K steps x {Z_hi, Z_lo} against the weights in tensor memory, commit =====
     constexpr uint32_t idesc = make_idesc(64, NT);
-    const uint64_t d0 = make_desc(smem_u32(w_hi));
+    const uint64_t d0 = make_desc(smem_u32(z_hi));
     const uint32_t desc_hi = (uint32_t)(d0 >> 32);
-    const uint32_t wh_lo = (uint32_t)d0, wl_lo = (uint32_t)make_desc(smem_u32(w_lo)), zh_lo = (uint32_t)make_desc(smem_u32(z_hi)),
-                   zl_lo = (uint32_t)make_desc(smem_u32(z_lo));
+    const uint32_t zh_lo = (uint32_t)d0, zl_lo = (uint32_t)make_desc(smem_u32(z_lo));
     for (int64_t tile = t_begin; tile < t_end; ++tile) {
       const uint32_t k = (uint32_t)(tile - t_begin), buf = k & 1;
       z_ready_wait();
@@ -147,36 +157,34 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       if (k >= 2) mbar_wait(&acc_free[buf], ((k >> 1) - 1) & 1);   // tile k-2 has been drained out of this accumulator
       if (elect_one()) {
         tc_fence_after();
-        const uint32_t acc = tmem_d + buf * ACC_COLS;
-        // all four operand descriptors share their high word (LBO | SBO | version | swizzle) and differ only in the 14-bit
-        // start-address field: + (TILE_BYTES >> 4) per K block, + 2 per K=16 step — plain 32-bit adds
-        uint32_t ah = wh_lo, al = wl_lo, bh = zh_lo, bl = zl_lo;
-#pragma unroll 1
-        for (int kb = 0; kb < KB; ++kb) {
-          if (kb == 0) mma_f16_first(acc, ah, bh, desc_hi, idesc);
-          else mma_f16_acc(acc, ah, bh, desc_hi, idesc);
-#pragma unroll
-          for (int k16 = 1; k16 < 4; ++k16) mma_f16_acc(acc, ah + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+        // the B descriptors differ only in the 14-bit start-address field: + (ZTILE_BYTES >> 4) per K block, + 2 per K = 16 step
+        const uint32_t acc_h = tmem_d + COL_D + buf * NT, acc_l = acc_h + HALF, a_h = tmem_d + COL_W, a_l = a_h + HALF;
+#pragma unroll 4
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t zoff = (uint32_t)(ks >> 2) * (ZTILE_BYTES >> 4) + 2 * (ks & 3);
+          mma_ts(acc_h, a_h + 8 * ks, zh_lo + zoff, desc_hi, idesc, ks > 0);
 #ifndef EXP_ONEPASS
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(acc, ah + 2 * k16, bl + 2 * k16, desc_hi, idesc);
-#pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) mma_f16_acc(acc, al + 2 * k16, bh + 2 * k16, desc_hi, idesc);
+          mma_ts(acc_h, a_h + 8 * ks, zl_lo + zoff, desc_hi, idesc, 1u);
+          mma_ts(acc_l, a_l + 8 * ks, zh_lo + zoff, desc_hi, idesc, ks > 0);
 #endif
-          ah += TILE_BYTES >> 4; al += TILE_BYTES >> 4; bh += ZTILE_BYTES >> 4; bl += ZTILE_BYTES >> 4;
         }
         mma_commit(&mma_done[buf]);
       }
       __syncwarp();
       TL(1);
     }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    tmem_dealloc(tmem_d, TMEM_COLS);
     return;
   }
   if (warp >= WARPS) {
-    // ===== drain warps: accumulator -> +bias, leaky_relu -> out[node, channel] =====
-    const int quad = warp - WARPS;                 // TMEM quadrant; for M = 64 accumulator row r lives in lane (r % 16) + 32 * (r / 16)
-    const float my_bias = bias[quad * 16 + (lane & 15)];
+    // ===== drain warps: accumulator -> hi-plane + lo-plane partial -> +bias, leaky_relu -> out[node, channel] =====
+    // quadrant q: lane l < 16 holds W_hi . Z of output 16 q + l, lane l + 16 the W_lo . Z_hi part of the same output
+    const int quad = warp - WARPS;
+    const int o = 16 * quad + (lane & 15);
+    const float my_bias = bias[o];
     for (int64_t tile = t_begin; tile < t_end; ++tile) {
       const uint32_t k = (uint32_t)(tile - t_begin), buf = k & 1;
       mbar_wait(&mma_done[buf], (k >> 1) & 1);
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       if (quad == 0) TL(2);
       float v[NT];
       {
-        const uint32_t ta = tmem_d + buf * ACC_COLS + ((uint32_t)(quad * 32) << 16);
+        const uint32_t ta = tmem_d + COL_D + buf * NT + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
         for (int c = 0; c + 32 <= NT; c += 32) tmem_ld32(ta + c, v + c);
 #pragma unroll
@@ -193,8 +201,9 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_free[buf]);  // values are in registers: the accumulator may be overwritten
+#pragma unroll
+      for (int col = 0; col < NT; ++col) v[col] += __shfl_xor_sync(0xffffffffu, v[col], 16);
       if (lane < 16) {
-        const int o = quad * 16 + lane;
         const int64_t n0 = tile * NT;
 #pragma unroll
         for (int col = 0; col < NT; ++col) {
@@ -211,6 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
       }
       if (quad == 0) TL(3);
     }
+    tc_fence_before();
     __syncthreads();
     return;
   }
@@ -483,10 +493,6 @@ __global__ void __launch_bounds__(THREADS, 1) feast_fused_64_32_kernel(const flo
 #endif
   }
   __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_d, 2 * ACC_COLS);
-  }
 }
 
 }  // namespace fused
@@ -496,13 +502,13 @@ int feast_project_only(const float* x, int64_t ldx, int64_t N, int c_in, const f
 
 struct FusedWs {
   double* P;
-  __nv_bfloat16* Wq;
+  uint32_t* Wp;
 };
 template <class C>
 static void carve_fused(C& c, int64_t N, FusedWs* out) {
   double* P = c.template take<double>((size_t)N * tc::H);
-  __nv_bfloat16* Wq = c.template take<__nv_bfloat16>((size_t)2 * fused::C_OUT * tc::H * fused::C_IN);
-  if (out) *out = FusedWs{P, Wq};
+  uint32_t* Wp = c.template take<uint32_t>((size_t)fused::KSTEPS * 64 * 8);
+  if (out) *out = FusedWs{P, Wp};
 }
 struct NullCarverFu {
   Sizer s;
@@ -516,9 +522,26 @@ size_t feast_fwd_fused_ws_bytes(int64_t N) {
   return c.s.total();
 }
 
-namespace tc {
-int prep_weight(const float* W, int N, int K, int kpad, int mode, int c_in, __nv_bfloat16* Bq, cudaStream_t st);  // feast_tc.cu
+namespace fused {
+// Wp[ks][m][8]: 32-bit words (bf16 pair, even k low) of stacked row m (m < 32: hi plane of output m, else lo plane of output m - 32) for
+// K = 16 step ks; k = h * 64 + c (head-major, as the Z tiles are laid out).  W is FeaStConv's lin.weight [9 * 32, 64].
+__global__ void prep_w_tmem_kernel(const float* __restrict__ W, uint32_t* __restrict__ Wp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= KSTEPS * 64 * 8) return;
+  const int ks = idx / 512, m = (idx >> 3) & 63, i = idx & 7;
+  const int o = m & 31, plane = m >> 5;
+  uint32_t word = 0;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = 16 * ks + 2 * i + e, h = k / C_IN, c = k % C_IN;
+    const float v = W[(h * C_OUT + o) * C_IN + c];
+    const __nv_bfloat16 bh = __float2bfloat16_rn(v);
+    const __nv_bfloat16 b = plane ? __float2bfloat16_rn(v - __bfloat162float(bh)) : bh;
+    word |= (uint32_t)(*reinterpret_cast<const uint16_t*>(&b)) << (16 * e);
+  }
+  Wp[idx] = word;
 }
+}  // namespace fused
 
 bool feast_fused_supported(int c_in, int c_out, int64_t ldx, int64_t ldo, const float* x, int64_t n_src) {
   return c_in == fused::C_IN && c_out == fused::C_OUT && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
@@ -535,11 +558,10 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
   Carver cv(ws, ws_bytes);
   FusedWs Wk;
   carve_fused(cv, n_src, &Wk);
-  const int K = tc::H * fused::C_IN;
   if (!reuse_ws) {   // P = X.U^T (fp64) and the split-bf16 weight planes; skipped when the caller re-runs on the same inputs
-    int rc = tc::prep_weight(W, fused::C_OUT, K, K, 1, fused::C_IN, Wk.Wq, st);
-    if (rc) return rc;
-    rc = feast_project_only(x, ldx, n_src, fused::C_IN, U, Wk.P, st);
+    fused::prep_w_tmem_kernel<<<(fused::KSTEPS * 64 * 8 + 255) / 256, 256, 0, st>>>(W, Wk.Wp);
+    GEOBI_LAUNCH_OK("feast_fused prep_w");
+    int rc = feast_project_only(x, ldx, n_src, fused::C_IN, U, Wk.P, st);
     if (rc) return rc;
   }
   static int sms = 0;
@@ -553,10 +575,10 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
   const int64_t n_tiles = (N + fused::NT - 1) / fused::NT;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
   if (row_map)
-    fused::feast_fused_64_32_kernel<true><<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wq, bias,
+    fused::feast_fused_64_32_kernel<true><<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wp, bias,
                                                                                            act_slope, out, ldo);
   else
-    fused::feast_fused_64_32_kernel<false><<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wq, bias,
+    fused::feast_fused_64_32_kernel<false><<<grid, fused::THREADS, fused::SMEM_BYTES, st>>>(x, ldx, N, rowptr, nbr, row_map, Wk.P, c, Wk.Wp, bias,
                                                                                             act_slope, out, ldo);
   GEOBI_LAUNCH_OK("feast_fused");
   return GEOBI_OK;

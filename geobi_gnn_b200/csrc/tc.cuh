@@ -106,6 +106,26 @@ __device__ __forceinline__ void mma_f16_first(uint32_t tmem_d, uint32_t a_lo, ui
       ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
       : "memory");
 }
+// A operand in tensor memory (TS form): rows in the 16-lanes-per-quadrant layout of an M = 64 accumulator, one 32-bit column per
+// bf16 pair (even k in the low half word), 8 columns per K = 16 step; A and D must sit in the same lane half (offset 0 or 16).
+// The B descriptor is passed as its two 32-bit words.  Probe: profiles/micro/tc_ts_probe.cu (16 clk per M64 N32 step against 24 clk
+// with A in shared memory - the instruction costs (A + B bytes read from shared memory) / 128 clocks).
+__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// eight 32-bit columns of this thread's TMEM lane; complete after tmem_st_wait()
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
