@@ -31,6 +31,28 @@ def partition(mesh, sub_size: int, host=None):
     return patches.split_mesh(pts, fv, vf, sub_size)
 
 
+_STAGE = {}     # device index -> (pinned int32 staging buffer, event of the last copy out of it)
+
+
+def _stage_int32(arr, dev):
+    """Host integer array -> int32 device tensor through ONE reusable pinned buffer per device (a fresh `pin_memory()` per patch is a
+    cudaHostAlloc of 4 MB, ~1 ms each).  The previous copy out of the buffer is waited for before it is overwritten."""
+    n = int(len(arr))
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    buf, ev = _STAGE.get(key, (None, None))
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 20), dtype=torch.int32).pin_memory()
+        ev = None
+    if ev is not None:
+        ev.synchronize()
+    buf[:n].numpy()[:] = arr
+    out = buf[:n].to(dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _STAGE[key] = (buf, ev)
+    return out
+
+
 def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device="cuda", n_iter: int = 60, rank: int = 0, world: int = 1,
                  forced: Optional[List] = None, return_parts: bool = False, device_topology: bool = True,
                  timings: Optional[dict] = None, parts: Optional[List] = None, host=None, norm=None):
@@ -93,7 +115,7 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
             # host routine); per patch only its face list crosses PCIe (int32, pinned)
             for k in mine:
                 sel, seed = parts[k]
-                sel_dev = torch.from_numpy(np.ascontiguousarray(sel, dtype=np.int32)).pin_memory().to(dev, non_blocking=True)
+                sel_dev = _stage_int32(sel, dev)
                 v_idx, faces = patches.get_submesh_device(mesh.fv, sel_dev, mesh.n_vertices)
                 sub = topology.DeviceTriMesh(mesh.points.index_select(0, v_idx), faces, dev)
                 dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev)
