@@ -34,7 +34,7 @@ SIGNATURES = {
     "geobi_build_facet_graph_ws_bytes": (_sz, [_i64, _i64]),
     "geobi_build_facet_graph": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "geobi_build_facet_graph_sorted_ws_bytes": (_sz, [_i64]),
-    "geobi_build_facet_graph_sorted": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "geobi_build_facet_graph_sorted": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _p, _p, _p, _p, _sz, _p]),
     "geobi_graclus_ws_bytes": (_sz, [_i64]),
     "geobi_graclus": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "geobi_relabel_ws_bytes": (_sz, [_i64]),
@@ -50,6 +50,7 @@ SIGNATURES = {
     "geobi_edge_weight_feat": (_i32, [_p, _i64, _i32, _p, _p, _i64, _p, _i32, _f32, _p, _p]),
     "geobi_calc_weight_ws_bytes": (_sz, [_i64]),
     "geobi_calc_weight": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _sz, _p]),
+    "geobi_calc_weight_csr": (_i32, [_p, _p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "geobi_feast_fwd_ws_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "geobi_feast_fwd": (_i32, [_p, _i64, _i64, _i32, _p, _p, _p, _i64, _p, _p, _p, _p, _i32, _f32, _p, _i64, _i32, _p, _sz, _p]),
     "geobi_feast_aggregate": (_i32, [_p, _i64, _i64, _i32, _p, _p, _p, _p, _p, _p, _p]),

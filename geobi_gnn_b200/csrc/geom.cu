@@ -191,6 +191,59 @@ __global__ void __launch_bounds__(256) calc_weight_kernel(const float* __restric
   }
 }
 
+// The same weights for a loop-free CSR (rows = sources), in CSR entry order: what the matcher reads.  The mean edge length is
+// taken over the reference's list, i.e. the CSR entries PLUS `n_loops` zero-length self loops (to_undirected_with_self_loops /
+// the facet builder's self entries).  8 lanes per row.
+__global__ void __launch_bounds__(256) edge_len_partial_csr_kernel(const float* __restrict__ pos, const int* __restrict__ rowptr,
+                                                                   const int* __restrict__ nbr, int64_t n, double* __restrict__ partial) {
+  double s = 0.0;
+  const int sub = threadIdx.x & 7;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < n; i += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int b = rowptr[i], e = rowptr[i + 1];
+    for (int q = b + sub; q < e; q += 8) s += (double)sqrtf(edge_l2(pos, i, nbr[q]));
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void __launch_bounds__(256) edge_len_final_csr_kernel(double* partial, int nb, const int* __restrict__ rowptr, int64_t n, int64_t n_loops) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nb; i += 256) s += partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int64_t E = (int64_t)rowptr[n] + n_loops;
+    partial[nb] = sh[0] / (double)(E > 0 ? E : 1);
+  }
+}
+__global__ void __launch_bounds__(256) calc_weight_csr_kernel(const float* __restrict__ pos, const float* __restrict__ nrm, const int* __restrict__ rowptr,
+                                                              const int* __restrict__ nbr, int64_t n, const double* __restrict__ mean_len,
+                                                              float* __restrict__ w_out) {
+  const float denom = -2.0f * (float)(*mean_len) + 1e-12f;
+  const int sub = threadIdx.x & 7;
+  for (int64_t a = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; a < n; a += ((int64_t)gridDim.x * blockDim.x) >> 3) {
+    const int b0 = rowptr[a], e0 = rowptr[a + 1];
+    for (int q = b0 + sub; q < e0; q += 8) {
+      const int64_t b = nbr[q];
+      const float l2 = edge_l2(pos, a, b);
+      float dn = nrm[a * 3] * nrm[b * 3];
+      dn += nrm[a * 3 + 1] * nrm[b * 3 + 1];
+      dn += nrm[a * 3 + 2] * nrm[b * 3 + 2];
+      w_out[q] = fmaxf(dn, 0.001f) * expf(l2 / denom);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ face normal / v->f transfer
 __device__ __forceinline__ void face_geom(const float* __restrict__ p, int64_t ldp, const int64_t* __restrict__ fv, int64_t f, float* cent,
                                           float* nrm) {
@@ -322,6 +375,22 @@ extern "C" int geobi_edge_weight_feat(const float* x, int64_t ldx, int channels,
 
 static const int CW_BLOCKS = 1024;
 extern "C" size_t geobi_calc_weight_ws_bytes(int64_t) { return align256((CW_BLOCKS + 2) * sizeof(double)) + 256; }
+
+extern "C" int geobi_calc_weight_csr(const float* pos, const float* nrm, const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes, int64_t n_loops,
+                                     float* w_out, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(pos && nrm && rowptr && nbr && w_out && n_nodes >= 0 && n_loops >= 0, "calc_weight_csr: bad arguments");
+  if (n_nodes == 0) return GEOBI_OK;
+  if (!ws || ws_bytes < geobi_calc_weight_ws_bytes(n_nodes)) { set_error("calc_weight_csr: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  double* partial = static_cast<double*>(ws);
+  int nb = (int)cdiv(n_nodes * 8, 256);
+  if (nb > CW_BLOCKS) nb = CW_BLOCKS;
+  edge_len_partial_csr_kernel<<<nb, 256, 0, st>>>(pos, rowptr, nbr, n_nodes, partial);
+  edge_len_final_csr_kernel<<<1, 256, 0, st>>>(partial, nb, rowptr, n_nodes, n_loops);
+  calc_weight_csr_kernel<<<nb, 256, 0, st>>>(pos, nrm, rowptr, nbr, n_nodes, partial + nb, w_out);
+  GEOBI_LAUNCH_OK("calc_weight_csr");
+  return GEOBI_OK;
+}
 
 extern "C" int geobi_calc_weight(const float* pos, const float* nrm, const int64_t* row, const int64_t* col, int64_t n_edges, float* w_out,
                                  void* ws, size_t ws_bytes, void* stream) {

@@ -496,7 +496,7 @@ extern "C" int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int
 namespace geobi {
 template <bool WRITE>
 __global__ void __launch_bounds__(256) facet_merge_kernel(const int64_t* __restrict__ fv, const int64_t* __restrict__ vf, int64_t F, int64_t V, int K,
-                                                          const int32_t* __restrict__ rowptr, int32_t* __restrict__ out, int* status) {
+                                                          int drop_self, const int32_t* __restrict__ rowptr, int32_t* __restrict__ out, int* status) {
   constexpr int64_t INF = (int64_t)1 << 62;
   for (int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; f < F; f += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v0 = fv[3 * f], v1 = fv[3 * f + 1], v2 = fv[3 * f + 2];
@@ -522,8 +522,10 @@ __global__ void __launch_bounds__(256) facet_merge_kernel(const int64_t* __restr
       const int64_t m = a < b ? (a < c ? a : c) : (b < c ? b : c);
       if (m == INF) break;
       if (m >= F) { bad = true; break; }
-      if (WRITE) dst[n] = (int32_t)m;
-      ++n;
+      if (!(drop_self && m == f)) {
+        if (WRITE) dst[n] = (int32_t)m;
+        ++n;
+      }
       if (a == m) { a = head(r0, ++i0); bad |= a <= m; }
       if (b == m) { b = head(r1, ++i1); bad |= b <= m; }
       if (c == m) { c = head(r2, ++i2); bad |= c <= m; }
@@ -539,8 +541,8 @@ extern "C" size_t geobi_build_facet_graph_sorted_ws_bytes(int64_t n_faces) {
   return align256((size_t)(n_faces + 1) * sizeof(int)) + align256(sizeof(int) * ST_WORDS) + scan_ws_bytes(n_faces + 1) + 1024;
 }
 
-extern "C" int geobi_build_facet_graph_sorted(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts, int64_t k, int32_t* rowptr,
-                                              int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int geobi_build_facet_graph_sorted(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts, int64_t k, int drop_self,
+                                              int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GEOBI_REQUIRE(fv && vf && rowptr && nbr && n_faces > 0 && n_verts > 0 && k > 0, "build_facet_graph_sorted: bad arguments");
   GEOBI_REQUIRE(n_faces * 3 * k < (int64_t)1 << 31, "build_facet_graph_sorted: 3*K*F exceeds int32 indexing");
@@ -554,11 +556,11 @@ extern "C" int geobi_build_facet_graph_sorted(const int64_t* fv, const int64_t* 
   const size_t sb = scan_ws_bytes(n_faces + 1);
   char* scan = c.take<char>(sb);
   GEOBI_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int) * ST_WORDS, st));
-  facet_merge_kernel<false><<<grid_for(n_faces, 256), 256, 0, st>>>(fv, vf, n_faces, n_verts, (int)k, nullptr, count, status);
+  facet_merge_kernel<false><<<grid_for(n_faces, 256), 256, 0, st>>>(fv, vf, n_faces, n_verts, (int)k, drop_self, nullptr, count, status);
   GEOBI_LAUNCH_OK("facet_merge (count)");
   int rc = scan_i32(count, rowptr, n_faces, scan, sb, st);
   if (rc) return rc;
-  facet_merge_kernel<true><<<grid_for(n_faces, 256), 256, 0, st>>>(fv, vf, n_faces, n_verts, (int)k, rowptr, nbr, status);
+  facet_merge_kernel<true><<<grid_for(n_faces, 256), 256, 0, st>>>(fv, vf, n_faces, n_verts, (int)k, drop_self, rowptr, nbr, status);
   GEOBI_LAUNCH_OK("facet_merge (fill)");
   if (nnz_host) return finish_sync(status, rowptr, n_faces, nnz_host, "build_facet_graph_sorted", st);
   return GEOBI_OK;

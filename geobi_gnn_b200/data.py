@@ -74,6 +74,10 @@ class Data:
     def keys(self):
         return list(self._items)
 
+    def tensors(self):
+        """(key, tensor) of the tensor-valued items that exist NOW: lazy items stay unevaluated."""
+        return [(k, v) for k, v in self._items.items() if torch.is_tensor(v)]
+
     @property
     def num_nodes(self):
         for key in ("x", "pos", "normal"):

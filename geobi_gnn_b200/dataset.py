@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from . import data_util
+from . import data_util, ops
 from .data import Data
 
 
@@ -28,27 +28,64 @@ def _t(a, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).to(device)
 
 
-def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda"):
-    """dataset.py:196-243."""
+def process_one_submesh(mesh_n, name="graph", mesh_o=None, device="cuda", csr_native=False):
+    """dataset.py:196-243.
+
+    csr_native (not upstream; needs a topology.DeviceTriMesh): both graphs are handed to the network as the loop-free CSRs the
+    device front end already holds (`Data.csr`, bilateral weights computed in CSR order by geobi_calc_weight_csr), and the
+    reference's int64 `edge_index` (with its self loops) / `edge_weight` become LAZY items, built by the list-based code below only
+    if a caller reads them - the same arrangement PoolingLayer uses for the coarse levels.  It saves the CSR -> list -> CSR round
+    trip (0.7 of the front end's 2.3 ms of GPU time per million faces); weights agree with the list-based ones to the last bit
+    unless the fp64 mean edge length rounds differently to fp32 (a different summation order)."""
     fv = _t(mesh_n.fv, torch.long, device)
     vf = _t(mesh_n.vf, torch.long, device)
     edge_dual_fv = data_util.build_edge_fv(fv)
     pos_v = _t(mesh_n.points, torch.float32, device)
     normal_v = _t(mesh_n.vertex_normals, torch.float32, device)
-    if getattr(mesh_n, "vertex_csr", None) is not None:      # DeviceTriMesh already holds to_undirected(ev) as a CSR
-        edge_idx_v = data_util.with_self_loops_appended(mesh_n.vertex_csr)
-    else:
-        ev = _t(mesh_n.ev, torch.long, device)
-        edge_idx_v = data_util.to_undirected_with_self_loops(ev.t().contiguous(), pos_v.size(0))
-    edge_wei_v = data_util.calc_weight(pos_v, normal_v, edge_idx_v)
-    graph_v = Data(name=f"{name}-v", pos=pos_v, normal=normal_v, edge_index=edge_idx_v, edge_weight=edge_wei_v,
-                   depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1], coalesced_undirected=True)
     pos_f = pos_v[fv].mean(1)
     normal_f = _t(mesh_n.face_normals, torch.float32, device).reshape(-1, 3)
-    edge_idx_f = data_util.build_facet_graph(fv, vf, vf_sorted=bool(getattr(mesh_n, "vf_sorted", False)))
-    edge_wei_f = data_util.calc_weight(pos_f, normal_f, edge_idx_f)
-    graph_f = Data(name=f"{name}-f", pos=pos_f, normal=normal_f, edge_index=edge_idx_f, edge_weight=edge_wei_f,
-                   fv_indices=fv, edge_dual=edge_dual_fv[0], coalesced_undirected=True)
+    vf_sorted = bool(getattr(mesh_n, "vf_sorted", False))
+    if csr_native:
+        if getattr(mesh_n, "vertex_csr", None) is None or not vf_sorted:
+            raise ValueError("process_one_submesh(csr_native=True) needs a topology.DeviceTriMesh")
+        g_v = mesh_n.vertex_csr
+        g_v = g_v.with_weight(ops.calc_weight_csr(pos_v, normal_v, g_v, pos_v.size(0)))
+        g_f = ops.build_facet_graph_csr(fv, vf, True, drop_self=True)
+        g_f.symmetric = True
+        g_f = g_f.with_weight(ops.calc_weight_csr(pos_f, normal_f, g_f, fv.size(0)))
+        graph_v = Data(name=f"{name}-v", pos=pos_v, normal=normal_v, depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1],
+                       coalesced_undirected=True)
+        graph_f = Data(name=f"{name}-f", pos=pos_f, normal=normal_f, fv_indices=fv, edge_dual=edge_dual_fv[0], coalesced_undirected=True)
+
+        def lists_v(cache=[]):
+            if not cache:
+                ei = data_util.with_self_loops_appended(mesh_n.vertex_csr)
+                cache.append((ei, data_util.calc_weight(pos_v, normal_v, ei)))
+            return cache[0]
+
+        def lists_f(cache=[]):
+            if not cache:
+                ei = data_util.build_facet_graph(fv, vf, vf_sorted=True)
+                cache.append((ei, data_util.calc_weight(pos_f, normal_f, ei)))
+            return cache[0]
+
+        for d, lists, g in ((graph_v, lists_v, g_v), (graph_f, lists_f, g_f)):
+            d.set_lazy("edge_index", lambda lists=lists: lists()[0])
+            d.set_lazy("edge_weight", lambda lists=lists: lists()[1])
+            d.csr = g                    # after the lazies: assigning edge_index / edge_weight drops a stale csr
+    else:
+        if getattr(mesh_n, "vertex_csr", None) is not None:      # DeviceTriMesh already holds to_undirected(ev) as a CSR
+            edge_idx_v = data_util.with_self_loops_appended(mesh_n.vertex_csr)
+        else:
+            ev = _t(mesh_n.ev, torch.long, device)
+            edge_idx_v = data_util.to_undirected_with_self_loops(ev.t().contiguous(), pos_v.size(0))
+        edge_wei_v = data_util.calc_weight(pos_v, normal_v, edge_idx_v)
+        graph_v = Data(name=f"{name}-v", pos=pos_v, normal=normal_v, edge_index=edge_idx_v, edge_weight=edge_wei_v,
+                       depth_direction=F.normalize(pos_v, dim=1), edge_dual=edge_dual_fv[1], coalesced_undirected=True)
+        edge_idx_f = data_util.build_facet_graph(fv, vf, vf_sorted=vf_sorted)
+        edge_wei_f = data_util.calc_weight(pos_f, normal_f, edge_idx_f)
+        graph_f = Data(name=f"{name}-f", pos=pos_f, normal=normal_f, edge_index=edge_idx_f, edge_weight=edge_wei_f,
+                       fv_indices=fv, edge_dual=edge_dual_fv[0], coalesced_undirected=True)
     # coalesced_undirected: both builders above emit sorted, duplicate-free, symmetric lists (self loops aside), which
     # lets the network build one CSR per graph without a sort (nn.input_graph); the device verifies the claim
     if mesh_o is not None:
@@ -105,12 +142,12 @@ def post_processing(dual_data, data_type="Synthetic", is_plot=False):
     return data_v, data_f
 
 
-def build_dual_on_device(mesh_n, mesh_o=None, data_type="Synthetic", name="graph"):
+def build_dual_on_device(mesh_n, mesh_o=None, data_type="Synthetic", name="graph", csr_native=False):
     """build_dual_data for a topology.DeviceTriMesh with the normalisation (dataset.py:140,151-152: centroid, 1 / mean edge length)
     computed on the device as well - no host round trip and no stream synchronisation beyond the mesh's own entry counts.  The fp32
     mean is taken by a device reduction instead of numpy's pairwise sum: centroid / scale agree with `normalisation` to ~1e-7."""
     dev = mesh_n.points.device
-    dd = process_one_submesh(mesh_n, name, mesh_o, dev)
+    dd = process_one_submesh(mesh_n, name, mesh_o, dev, csr_native=csr_native)
     pts = mesh_n.points
     centroid = pts.mean(0, keepdim=True)
     q = pts - centroid

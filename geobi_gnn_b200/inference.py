@@ -118,7 +118,7 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
                 sel_dev = _stage_int32(sel, dev)
                 v_idx, faces = patches.get_submesh_device(mesh.fv, sel_dev, mesh.n_vertices)
                 sub = topology.DeviceTriMesh(mesh.points.index_select(0, v_idx), faces, dev)
-                dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev)
+                dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev, csr_native=True)
                 dataset.attach_normalisation(dual, points_noisy, mesh_ev, precomputed=norm)   # dataset.py:140,179-180
                 centroid, scale = dual[0].centroid, dual[0].scale
                 norm = (centroid, scale)
@@ -320,7 +320,7 @@ class HostBatchRunner:
         """Same pipeline stage from the RAW mesh: pinned `points` fp32 [V,3] and `faces` int32/int64 [F,3] are all that crosses PCIe
         (18 MB per million faces instead of 250 MB of prebuilt graphs); topology, both graphs, the bilateral weights, the normalised
         features and the input-level CSRs are built on the copy stream by the device front end (topology.DeviceTriMesh,
-        dataset.build_dual_on_device: ~2.5 ms per million faces) under the previous batch's forward.  Returns a handle for run()."""
+        dataset.build_dual_on_device(csr_native=True): 1.6 ms of GPU time per million faces) under the previous batch's forward.  Returns a handle for run()."""
         from . import topology
         slot = self._next_slot
         self._next_slot = (slot + 1) % len(self._slots)
@@ -332,13 +332,8 @@ class HostBatchRunner:
             land["points"].copy_(points_host, non_blocking=True)
             land["faces"].copy_(faces_host, non_blocking=True)
             mesh = topology.DeviceTriMesh(land["points"], land["faces"].long(), self.dev)
-            dv, df = dataset.build_dual_on_device(mesh, None, data_type)
-            # hand the network what a caller holding the reference's input layout would (graph tags of the builders dropped); the
-            # lists are coalesced and undirected by construction (flag set by process_one_submesh): sort-free CSRs, built now
-            dv, df = batching.fresh_view(dv), batching.fresh_view(df)
-            from . import nn as gnn
-            for d in (dv, df):
-                gnn.input_graph(d, d.x.size(0))
+            # csr_native: the network walks the loop-free CSRs the front end holds (Data.csr); the reference's int64 edge lists stay lazy
+            dv, df = dataset.build_dual_on_device(mesh, None, data_type, csr_native=True)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         return dv, df, ev, slot
@@ -349,20 +344,22 @@ class HostBatchRunner:
         cur.wait_event(ev)
         from . import nn as gnn
         for d in (dv, df):
-            for k in d.keys:
-                t = getattr(d, k)
-                if torch.is_tensor(t):
-                    t.record_stream(cur)       # allocated on the copy stream, consumed here
-            tag = gnn.tag_of(d.edge_index)
-            st = tag.get("sorted")
+            for k, t in d.tensors():           # lazy items (a CSR-native mesh's edge lists) stay unevaluated
+                t.record_stream(cur)           # allocated on the copy stream, consumed here
             held = []
-            if st is not None:                 # the prebuilt CSR and the stripped lists live on the copy stream's pool too
-                g = st[0]
-                held += [g.rowptr, g._nbr, g._w, st[1], st[2]]
-            for key in ("tgt", "src"):
-                g = tag.get(key)
-                if g is not None:
-                    held += [g.rowptr, g._nbr, g._w]
+            if "csr" in d:                     # upload_mesh: the graph IS the attached CSR
+                g = d.csr
+                held += [g.rowptr, g._nbr, g._w]
+            else:
+                tag = gnn.tag_of(d.edge_index)
+                st = tag.get("sorted")
+                if st is not None:             # the prebuilt CSR and the stripped lists live on the copy stream's pool too
+                    g = st[0]
+                    held += [g.rowptr, g._nbr, g._w, st[1], st[2]]
+                for key in ("tgt", "src"):
+                    g = tag.get(key)
+                    if g is not None:
+                        held += [g.rowptr, g._nbr, g._w]
             for t in held:
                 if torch.is_tensor(t):
                     t.record_stream(cur)

@@ -273,9 +273,12 @@ def csr_from_sorted_coo(edge_index: torch.Tensor, n_nodes: int, weight: Optional
     return CSRGraph(rowptr, nbr, n_nodes, 0 if e == 0 else None, w_out, True), ei_out, w_out
 
 
-def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor, vf_sorted: bool = False) -> CSRGraph:
+def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor, vf_sorted: bool = False, drop_self: bool = False) -> CSRGraph:
     """Facet 1-ring CSR with the self entry (data_util.build_facet_graph).  Syncs once.
-    vf_sorted: every row of vf is ascending with its -1 pads last (topology.DeviceTriMesh) - merge instead of sort."""
+    vf_sorted: every row of vf is ascending with its -1 pads last (topology.DeviceTriMesh) - merge instead of sort.
+    drop_self (with vf_sorted): leave the self entries out - the loop-free CSR the network walks."""
+    if drop_self and not vf_sorted:
+        raise ValueError("build_facet_graph_csr(drop_self=True) needs vf_sorted=True")
     _need_cuda(fv, vf)
     lib = _lib.load()
     fv, vf = fv.contiguous().long(), vf.contiguous().long()
@@ -286,7 +289,7 @@ def build_facet_graph_csr(fv: torch.Tensor, vf: torch.Tensor, vf_sorted: bool = 
     nnz = C.c_int64(0)
     if vf_sorted:
         ws = _ws(lib.geobi_build_facet_graph_sorted_ws_bytes(f), dev)
-        _lib.check(lib.geobi_build_facet_graph_sorted(_ptr(fv), _ptr(vf), f, v, k, _ptr(rowptr), _ptr(nbr), C.byref(nnz), _ptr(ws), ws.numel(),
+        _lib.check(lib.geobi_build_facet_graph_sorted(_ptr(fv), _ptr(vf), f, v, k, int(drop_self), _ptr(rowptr), _ptr(nbr), C.byref(nnz), _ptr(ws), ws.numel(),
                                                       _stream()), "build_facet_graph_sorted")
         _count(3)
     else:
@@ -487,6 +490,20 @@ def calc_weight(pos: torch.Tensor, nrm: torch.Tensor, edge_index: torch.Tensor) 
     w = torch.empty(e, dtype=torch.float32, device=pos.device)
     ws = _ws(lib.geobi_calc_weight_ws_bytes(e), pos.device)
     _lib.check(lib.geobi_calc_weight(_ptr(pos), _ptr(nrm), _ptr(ei[0]), _ptr(ei[1]), e, _ptr(w), _ptr(ws), ws.numel(), _stream()), "calc_weight")
+    _count(3)
+    return w
+
+
+def calc_weight_csr(pos: torch.Tensor, nrm: torch.Tensor, g: CSRGraph, n_loops: int) -> torch.Tensor:
+    """calc_weight for the entries of a loop-free CSR, in CSR order; the mean edge length counts `n_loops` zero-length self loops
+    as the reference's list does (geobi_calc_weight_csr)."""
+    _need_cuda(pos, nrm, g.rowptr)
+    lib = _lib.load()
+    pos, nrm = pos.contiguous().float(), nrm.contiguous().float()
+    w = torch.empty(max(g._nbr.numel(), 1), dtype=torch.float32, device=pos.device)
+    ws = _ws(lib.geobi_calc_weight_ws_bytes(g.n), pos.device)
+    _lib.check(lib.geobi_calc_weight_csr(_ptr(pos), _ptr(nrm), _ptr(g.rowptr), _ptr(g._nbr), g.n, int(n_loops), _ptr(w), _ptr(ws), ws.numel(),
+                                         _stream()), "calc_weight_csr")
     _count(3)
     return w
 

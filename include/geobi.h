@@ -115,9 +115,10 @@ GEOBI_API int geobi_build_facet_graph(const int64_t* fv, const int64_t* vf, int6
                             int64_t k, int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws,
                             size_t ws_bytes, void* stream);
 /* The same graph when every vf row is ASCENDING with its -1 pads at the end (topology.DeviceTriMesh): a three-way merge per face
- * instead of a fill + per-row sort.  An unsorted row is detected on the device (GEOBI_ERR_RANGE at the sync). */
+ * instead of a fill + per-row sort.  An unsorted row is detected on the device (GEOBI_ERR_RANGE at the sync).  drop_self != 0 leaves
+ * the self entry out: the loop-free CSR the convolution and the matcher walk, without the list round trip. */
 GEOBI_API size_t geobi_build_facet_graph_sorted_ws_bytes(int64_t n_faces);
-GEOBI_API int geobi_build_facet_graph_sorted(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts, int64_t k,
+GEOBI_API int geobi_build_facet_graph_sorted(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t n_verts, int64_t k, int drop_self,
                                              int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream);
 
 /* Heavy-edge matching identical to torch_cluster.graclus's serial CPU kernel for the visiting
@@ -202,6 +203,11 @@ GEOBI_API int geobi_edge_weight_feat(const float* x, int64_t ldx, int channels, 
 GEOBI_API size_t geobi_calc_weight_ws_bytes(int64_t n_edges);
 GEOBI_API int geobi_calc_weight(const float* pos, const float* nrm, const int64_t* row, const int64_t* col,
                       int64_t n_edges, float* w_out, void* ws, size_t ws_bytes, void* stream);
+/* The same weights for a loop-free int32 CSR (rows = sources), written in CSR entry order (what geobi_graclus reads).  The mean edge
+ * length is taken over the reference's list: the CSR entries plus n_loops zero-length self loops (dataset.py:211 appends one per
+ * vertex, build_facet_graph keeps one per face).  Workspace: geobi_calc_weight_ws_bytes(n_nodes). */
+GEOBI_API int geobi_calc_weight_csr(const float* pos, const float* nrm, const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes,
+                          int64_t n_loops, float* w_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------ FeaSt convolution */
 

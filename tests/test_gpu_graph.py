@@ -281,3 +281,31 @@ def test_facet_graph_from_sorted_incidence_equals_the_general_builder():
     vf_bad[5, :2] = vf_bad[5, :2].flip(0)
     with pytest.raises(_lib.GeobiError):
         ops.build_facet_graph_csr(m.fv, vf_bad, vf_sorted=True)
+
+
+@pytest.mark.gpu
+def test_csr_native_front_end_pieces_equal_the_list_based_ones():
+    """The loop-free facet CSR of the merge builder (drop_self) = the general builder's list minus its self entries; the bilateral weights
+    computed in CSR order (geobi_calc_weight_csr, mean edge length counting the reference's self loops) = calc_weight on the
+    reference's lists, entry for entry (closed mesh, open mesh)."""
+    import numpy as np
+    from geobi_gnn_b200 import data_util, ops, synth, topology
+    p, f = synth.icosphere(9)
+    rng = np.random.default_rng(3)
+    for pts, fcs in ((p + 0.01 * rng.standard_normal(p.shape), f), (p, f[: f.shape[0] // 3])):
+        m = topology.DeviceTriMesh(pts, fcs, "cuda")
+        # facet graph
+        g = ops.build_facet_graph_csr(m.fv, m.vf, vf_sorted=True, drop_self=True)
+        ei = data_util.build_facet_graph(m.fv, m.vf)                      # sorted, self entries included
+        keep = ei[0] != ei[1]
+        assert g.nnz == int(keep.sum()) and torch.equal(g.edge_index(), ei[:, keep])
+        pos_f = m.points[m.fv].mean(1)
+        w_list = data_util.calc_weight(pos_f, m.face_normals, ei)
+        w_csr = ops.calc_weight_csr(pos_f, m.face_normals, g, m.n_faces)[: g.nnz]
+        assert torch.equal(w_csr, w_list[keep])
+        # vertex graph: the reference appends one self loop per vertex
+        gv = m.vertex_csr
+        eiv = data_util.with_self_loops_appended(gv)
+        w_list = data_util.calc_weight(m.points, m.vertex_normals, eiv)
+        w_csr = ops.calc_weight_csr(m.points, m.vertex_normals, gv, m.n_vertices)[: gv.nnz]
+        assert torch.equal(w_csr, w_list[: gv.nnz])

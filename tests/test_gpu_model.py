@@ -245,3 +245,27 @@ def test_host_batch_runner_upload_mesh_equals_direct_forward():
         v, n = runner.run(cur)
         runner.wait()
         assert torch.equal(v, want[i][0]) and torch.equal(n, want[i][1])
+
+
+@pytest.mark.gpu
+def test_csr_native_inputs_equal_list_inputs():
+    """dataset.build_dual_on_device(csr_native=True): same forward bits as the list-based inputs, and the lazy edge_index / edge_weight
+    read as the reference's lists when somebody asks for them (after the forward, which must not have touched them)."""
+    from geobi_gnn_b200 import batching, dataset, network, topology
+    from geobi_gnn_b200.data import _Lazy
+    torch.manual_seed(11)
+    net = network.DualGNN().to(DEV).eval()
+    for pl in util.poolings(net):
+        pl.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
+    m = util.noisy_icosphere(8, seed=5)[0]
+    dm = topology.DeviceTriMesh(m.points, m.fv, DEV)
+    with torch.no_grad():
+        lv, lf = dataset.build_dual_on_device(dm, None)
+        want = net([batching.fresh_view(lv), batching.fresh_view(lf)])
+        cv, cf = dataset.build_dual_on_device(dm, None, csr_native=True)
+        assert torch.equal(cv.x, lv.x) and torch.equal(cf.x, lf.x)        # before the forward: the network overwrites its inputs' x, as upstream
+        got = net([cv, cf])
+    assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+    for c, l in ((cv, lv), (cf, lf)):
+        assert isinstance(c._items["edge_index"], _Lazy) and isinstance(c._items["edge_weight"], _Lazy)     # the network never read them
+        assert torch.equal(c.edge_index, l.edge_index) and torch.equal(c.edge_weight, l.edge_weight)
