@@ -376,6 +376,22 @@ extern "C" int geobi_edge_weight_feat(const float* x, int64_t ldx, int channels,
 static const int CW_BLOCKS = 1024;
 extern "C" size_t geobi_calc_weight_ws_bytes(int64_t) { return align256((CW_BLOCKS + 2) * sizeof(double)) + 256; }
 
+__global__ void mean_to_float_kernel(const double* __restrict__ mean, float* __restrict__ out) { *out = (float)(*mean); }
+extern "C" int geobi_mean_edge_length_csr(const float* pos, const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes, float* mean_out, void* ws,
+                                          size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(pos && rowptr && nbr && mean_out && n_nodes > 0, "mean_edge_length_csr: bad arguments");
+  if (!ws || ws_bytes < geobi_calc_weight_ws_bytes(n_nodes)) { set_error("mean_edge_length_csr: workspace too small"); return GEOBI_ERR_WORKSPACE; }
+  double* partial = static_cast<double*>(ws);
+  int nb = (int)cdiv(n_nodes * 8, 256);
+  if (nb > CW_BLOCKS) nb = CW_BLOCKS;
+  edge_len_partial_csr_kernel<<<nb, 256, 0, st>>>(pos, rowptr, nbr, n_nodes, partial);
+  edge_len_final_csr_kernel<<<1, 256, 0, st>>>(partial, nb, rowptr, n_nodes, 0);
+  mean_to_float_kernel<<<1, 1, 0, st>>>(partial + nb, mean_out);
+  GEOBI_LAUNCH_OK("mean_edge_length_csr");
+  return GEOBI_OK;
+}
+
 extern "C" int geobi_calc_weight_csr(const float* pos, const float* nrm, const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes, int64_t n_loops,
                                      float* w_out, void* ws, size_t ws_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

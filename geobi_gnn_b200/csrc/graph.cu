@@ -887,6 +887,24 @@ extern "C" size_t geobi_group_by_ws_bytes(int64_t n, int64_t nc) {
   return s.total();
 }
 
+// member CSR -> the padded [n, k] int64 table of the reference's mesh arrays (vf_indices / vv_indices: OpenMesh circulators padded with -1)
+__global__ void __launch_bounds__(256) pad_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ members, int64_t n, int k,
+                                                       int divisor, int64_t* __restrict__ out) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * k; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / k;
+    const int c = (int)(t - i * k);
+    const int b = rowptr[i], e = rowptr[i + 1];
+    out[t] = b + c < e ? (int64_t)(members[b + c] / divisor) : -1;
+  }
+}
+extern "C" int geobi_pad_rows(const int32_t* rowptr, const int32_t* members, int64_t n_rows, int64_t k, int divisor, int64_t* out, void* stream) {
+  GEOBI_REQUIRE(rowptr && out && n_rows >= 0 && k > 0 && k < ((int64_t)1 << 31) && divisor > 0 && (members || n_rows == 0), "pad_rows: bad arguments");
+  if (n_rows == 0) return GEOBI_OK;
+  pad_rows_kernel<<<grid_for(n_rows * k, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rowptr, members, n_rows, (int)k, divisor, out);
+  GEOBI_LAUNCH_OK("pad_rows");
+  return GEOBI_OK;
+}
+
 extern "C" int geobi_group_by(const int32_t* cluster, int64_t n, int64_t nc, int32_t* mrowptr, int32_t* members, void* ws, size_t ws_bytes,
                               void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -150,10 +150,8 @@ def build_dual_on_device(mesh_n, mesh_o=None, data_type="Synthetic", name="graph
     dd = process_one_submesh(mesh_n, name, mesh_o, dev, csr_native=csr_native)
     pts = mesh_n.points
     centroid = pts.mean(0, keepdim=True)
-    q = pts - centroid
-    ev = mesh_n.ev
-    length = (q[ev[:, 0]] - q[ev[:, 1]]).pow(2).sum(1).sqrt()
-    dd[0].centroid, dd[0].scale = centroid, 1.0 / length.mean()
+    # mean undirected edge length = mean over the entries of the symmetric vertex CSR (fp64 sum of the fp32 lengths)
+    dd[0].centroid, dd[0].scale = centroid, 1.0 / ops.mean_edge_length_csr(pts - centroid, mesh_n.vertex_csr)
     return post_processing(dd, data_type)
 
 

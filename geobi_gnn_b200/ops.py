@@ -494,6 +494,31 @@ def calc_weight(pos: torch.Tensor, nrm: torch.Tensor, edge_index: torch.Tensor) 
     return w
 
 
+def pad_rows(rowptr: torch.Tensor, members: torch.Tensor, k: int, divisor: int = 1) -> torch.Tensor:
+    """Member CSR -> padded int64 [n, k] table, entries divided by `divisor`, -1 pads (the reference's vf_indices / vv_indices layout)."""
+    _need_cuda(rowptr, members)
+    lib = _lib.load()
+    n = rowptr.numel() - 1
+    out = torch.empty((n, max(int(k), 0)), dtype=torch.int64, device=rowptr.device)
+    if n and k:
+        _lib.check(lib.geobi_pad_rows(_ptr(rowptr), _ptr(members.contiguous()), n, int(k), int(divisor), _ptr(out), _stream()), "pad_rows")
+        _count()
+    return out
+
+
+def mean_edge_length_csr(pos: torch.Tensor, g: CSRGraph) -> torch.Tensor:
+    """Mean undirected edge length of a symmetric loop-free CSR as a 0-dim fp32 device tensor (no sync)."""
+    _need_cuda(pos, g.rowptr)
+    lib = _lib.load()
+    pos = pos.contiguous().float()
+    out = torch.empty((), dtype=torch.float32, device=pos.device)
+    ws = _ws(lib.geobi_calc_weight_ws_bytes(g.n), pos.device)
+    _lib.check(lib.geobi_mean_edge_length_csr(_ptr(pos), _ptr(g.rowptr), _ptr(g._nbr), g.n, _ptr(out), _ptr(ws), ws.numel(), _stream()),
+               "mean_edge_length_csr")
+    _count(3)
+    return out
+
+
 def calc_weight_csr(pos: torch.Tensor, nrm: torch.Tensor, g: CSRGraph, n_loops: int) -> torch.Tensor:
     """calc_weight for the entries of a loop-free CSR, in CSR order; the mean edge length counts `n_loops` zero-length self loops
     as the reference's list does (geobi_calc_weight_csr)."""

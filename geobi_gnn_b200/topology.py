@@ -37,17 +37,12 @@ class DeviceTriMesh:
         h = torch.stack([self.fv.reshape(-1), self.fv[:, [1, 2, 0]].reshape(-1)])
         self.vertex_csr = ops.csr_from_coo(h, V, None, ops.COO_SYMMETRIZE | ops.COO_SORT_NBR | ops.COO_DEDUP | ops.COO_DROP_SELF)
         self.vertex_csr.symmetric = True
-        ei = self.vertex_csr.edge_index()
-        self.ev = ei[:, ei[0] < ei[1]].t().contiguous()
+        self._ev = None                # unique undirected edges: built on first read (the device front end itself never needs them)
         # --- faces around each vertex, ascending, padded to the maximum valence
         mrowptr, members = ops.group_by(self.fv.reshape(-1).to(torch.int32), V)
         self.vf_rowptr, self.vf_members = mrowptr, members.div(3, rounding_mode="floor").to(torch.int32)
-        cnt = (mrowptr[1:] - mrowptr[:-1]).long()
-        k = int(cnt.max()) if V else 0
-        rows = torch.repeat_interleave(torch.arange(V, device=dev), cnt)
-        cols = torch.arange(members.numel(), device=dev) - torch.repeat_interleave(mrowptr[:-1].long(), cnt)
-        self.vf = torch.full((V, k), -1, dtype=torch.int64, device=dev)
-        self.vf[rows, cols] = self.vf_members.long()
+        k = int((mrowptr[1:] - mrowptr[:-1]).max()) if V else 0
+        self.vf = ops.pad_rows(mrowptr, members, k, 3)
         self.vf_sorted = True          # rows ascending, pads last: lets build_facet_graph merge instead of sort
         self.update_normals()
 
@@ -57,18 +52,19 @@ class DeviceTriMesh:
         self.vertex_normals = F.normalize(vn, dim=1, eps=1e-30)
 
     @property
+    def ev(self):
+        """Unique undirected edges [E,2] (min, max), sorted: the upper triangle of the vertex CSR."""
+        if self._ev is None:
+            ei = self.vertex_csr.edge_index()
+            self._ev = ei[:, ei[0] < ei[1]].t().contiguous()
+        return self._ev
+
+    @property
     def vv(self):
         """Neighbour table padded with -1 (only data_util.build_vertex_graph, dead code upstream, reads it)."""
         g = self.vertex_csr
-        cnt = (g.rowptr[1:] - g.rowptr[:-1]).long()
-        k = int(cnt.max()) if self.n_vertices else 0
-        dev = cnt.device
-        rows = torch.repeat_interleave(torch.arange(self.n_vertices, device=dev), cnt)
-        cols = torch.arange(g.nnz, device=dev) - torch.repeat_interleave(g.rowptr[:-1].long(), cnt)
-        out = torch.full((self.n_vertices, k), -1, dtype=torch.int64, device=dev)
-        out[rows, cols] = g.nbr.long()
-        return out
+        k = int((g.rowptr[1:] - g.rowptr[:-1]).max()) if self.n_vertices else 0
+        return ops.pad_rows(g.rowptr, g.nbr, k, 1)
 
     def mean_edge_length(self, centroid=None) -> float:
-        d = self.points[self.ev[:, 0]] - self.points[self.ev[:, 1]]
-        return float(d.pow(2).sum(1).sqrt().mean())
+        return float(ops.mean_edge_length_csr(self.points, self.vertex_csr))

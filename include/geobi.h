@@ -147,6 +147,11 @@ GEOBI_API size_t geobi_group_by_ws_bytes(int64_t n_nodes, int64_t n_clusters);
 GEOBI_API int geobi_group_by(const int32_t* cluster, int64_t n_nodes, int64_t n_clusters, int32_t* mrowptr,
                    int32_t* members, void* ws, size_t ws_bytes, void* stream);
 
+/* Member CSR -> padded [n_rows, k] int64 table (entry / divisor, -1 pads): OpenMesh's vf_indices / vv_indices layout
+ * (dataset.py:204-206) from geobi_group_by's output (divisor 3: corner index -> face id) or from a vertex CSR (divisor 1). */
+GEOBI_API int geobi_pad_rows(const int32_t* rowptr, const int32_t* members, int64_t n_rows, int64_t k, int divisor,
+                   int64_t* out, void* stream);
+
 /* Same member CSR when the labels come from a matching (clusters of one or two nodes, label = min member, as
  * geobi_graclus emits them): no sort, three elementwise kernels.  label = raw labels, cluster = dense ids. */
 GEOBI_API size_t geobi_group_pairs_ws_bytes(int64_t n_clusters);
@@ -206,6 +211,10 @@ GEOBI_API int geobi_calc_weight(const float* pos, const float* nrm, const int64_
 /* The same weights for a loop-free int32 CSR (rows = sources), written in CSR entry order (what geobi_graclus reads).  The mean edge
  * length is taken over the reference's list: the CSR entries plus n_loops zero-length self loops (dataset.py:211 appends one per
  * vertex, build_facet_graph keeps one per face).  Workspace: geobi_calc_weight_ws_bytes(n_nodes). */
+/* Mean length of the entries of a symmetric loop-free CSR = mean undirected edge length (the 1 / scale of dataset.py:151-152),
+ * written as one float on the device: no host round trip.  Workspace: geobi_calc_weight_ws_bytes(n_nodes). */
+GEOBI_API int geobi_mean_edge_length_csr(const float* pos, const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes,
+                               float* mean_out, void* ws, size_t ws_bytes, void* stream);
 GEOBI_API int geobi_calc_weight_csr(const float* pos, const float* nrm, const int32_t* rowptr, const int32_t* nbr, int64_t n_nodes,
                           int64_t n_loops, float* w_out, void* ws, size_t ws_bytes, void* stream);
 

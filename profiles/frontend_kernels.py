@@ -9,10 +9,13 @@ mesh0 = bench.noisy_device_mesh(bench.MESH_FREQ, 0, dev)
 pts, fcs = mesh0.points.clone(), mesh0.fv.to(torch.int32).clone()
 def front():
     mesh = topology.DeviceTriMesh(pts, fcs.long(), dev)
-    dv, df = dataset.build_dual_on_device(mesh, None, "Synthetic")
-    dv, df = batching.fresh_view(dv), batching.fresh_view(df)
-    for d in (dv, df):
-        gnn.input_graph(d, d.x.size(0))
+    if os.environ.get("LISTS"):      # the round-trip path: reference-layout lists, then sort-free CSRs from them
+        dv, df = dataset.build_dual_on_device(mesh, None, "Synthetic")
+        dv, df = batching.fresh_view(dv), batching.fresh_view(df)
+        for d in (dv, df):
+            gnn.input_graph(d, d.x.size(0))
+    else:                            # what upload_mesh queues: CSRs handed over directly, lists lazy
+        dv, df = dataset.build_dual_on_device(mesh, None, "Synthetic", csr_native=True)
     return dv, df
 for _ in range(3):
     front()
