@@ -51,6 +51,8 @@ SIGNATURES = {
     "geobi_calc_weight_ws_bytes": (_sz, [_i64]),
     "geobi_calc_weight": (_i32, [_p, _p, _p, _p, _i64, _p, _p, _sz, _p]),
     "geobi_mean_edge_length_csr": (_i32, [_p, _p, _p, _i64, _p, _p, _sz, _p]),
+    "geobi_mesh_vertex_csr_ws_bytes": (_sz, [_i64]),
+    "geobi_mesh_vertex_csr": (_i32, [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "geobi_pad_rows": (_i32, [_p, _p, _i64, _i64, _i32, _p, _p]),
     "geobi_calc_weight_csr": (_i32, [_p, _p, _p, _p, _i64, _i64, _p, _p, _sz, _p]),
     "geobi_feast_fwd_ws_bytes": (_sz, [_i64, _i32, _i32, _i32]),

@@ -887,6 +887,86 @@ extern "C" size_t geobi_group_by_ws_bytes(int64_t n, int64_t nc) {
   return s.total();
 }
 
+// ------------------------------------------------------------------------------ vertex 1-ring from the incidence CSR
+// Vertex adjacency of a triangle mesh (to_undirected of the unique edges, dataset.py:211, without the self loops) straight from the
+// faces around each vertex: vertex v's neighbours are the two other corners of its incident faces - at most 2 * valence candidates,
+// sorted and deduplicated in registers.  One thread per vertex, a count pass and a fill pass around a scan; rows come out ascending.
+// The general builder (symmetrise 3F half edges, count, fill, per-row rank sort, compact) does the same in six kernels over 6F entries.
+constexpr int RING_MAX_VALENCE = 24;
+template <bool WRITE>
+__global__ void __launch_bounds__(128) vertex_ring_kernel(const int64_t* __restrict__ fv, const int32_t* __restrict__ vf_rowptr,
+                                                          const int32_t* __restrict__ corners, int64_t V, int64_t F,
+                                                          const int32_t* __restrict__ rowptr, int32_t* __restrict__ out, int* status) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+    const int b = vf_rowptr[v], e = vf_rowptr[v + 1];
+    if (e - b > RING_MAX_VALENCE) {
+      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+      if (!WRITE) out[v] = 0;
+      continue;
+    }
+    int32_t cand[2 * RING_MAX_VALENCE];
+    int n = 0;
+    bool bad = false;
+    for (int q = b; q < e; ++q) {
+      const int m = corners[q];
+      const int64_t f = m / 3;
+      const int c = m - 3 * (int)f;
+      if (f < 0 || f >= F) { bad = true; break; }
+      const int64_t a0 = fv[3 * f + (c + 1) % 3], a1 = fv[3 * f + (c + 2) % 3];
+      if (a0 < 0 || a0 >= V || a1 < 0 || a1 >= V) { bad = true; break; }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int32_t x = (int32_t)(t ? a1 : a0);
+        if (x == (int32_t)v) continue;             // degenerate face: no self loop
+        // sorted insert without duplicates (rows are 6-12 long)
+        int pos = n;
+        while (pos > 0 && cand[pos - 1] > x) --pos;
+        if (pos > 0 && cand[pos - 1] == x) continue;
+        for (int r = n; r > pos; --r) cand[r] = cand[r - 1];
+        cand[pos] = x;
+        ++n;
+      }
+    }
+    if (bad) {
+      atomicExch(&status[ST_ERR], GEOBI_ERR_RANGE);
+      n = 0;
+    }
+    if (WRITE) {
+      int32_t* dst = out + rowptr[v];
+      for (int r = 0; r < n; ++r) dst[r] = cand[r];
+    } else {
+      out[v] = n;
+    }
+  }
+}
+extern "C" size_t geobi_mesh_vertex_csr_ws_bytes(int64_t n_verts) {
+  return align256(sizeof(int) * (size_t)(n_verts + 1)) + align256(sizeof(int) * ST_WORDS) + align256(scan_ws_bytes(n_verts + 1)) + 512;
+}
+extern "C" int geobi_mesh_vertex_csr(const int64_t* fv, const int32_t* vf_rowptr, const int32_t* corners, int64_t n_verts, int64_t n_faces,
+                                     int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(fv && vf_rowptr && corners && rowptr && nbr && n_verts > 0 && n_faces > 0, "mesh_vertex_csr: bad arguments");
+  GEOBI_REQUIRE(n_faces * 6 < (int64_t)1 << 31, "mesh_vertex_csr: 6 F exceeds int32 indexing");
+  if (ws_bytes < geobi_mesh_vertex_csr_ws_bytes(n_verts) || !ws) {
+    set_error("mesh_vertex_csr: workspace too small");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  Carver c(ws, ws_bytes);
+  int* count = c.take<int>(n_verts + 1);
+  int* status = c.take<int>(ST_WORDS);
+  const size_t sb = scan_ws_bytes(n_verts + 1);
+  char* scan = c.take<char>(sb);
+  GEOBI_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int) * ST_WORDS, st));
+  vertex_ring_kernel<false><<<grid_for(n_verts, 128), 128, 0, st>>>(fv, vf_rowptr, corners, n_verts, n_faces, nullptr, count, status);
+  GEOBI_LAUNCH_OK("vertex_ring (count)");
+  int rc = scan_i32(count, rowptr, n_verts, scan, sb, st);
+  if (rc) return rc;
+  vertex_ring_kernel<true><<<grid_for(n_verts, 128), 128, 0, st>>>(fv, vf_rowptr, corners, n_verts, n_faces, rowptr, nbr, status);
+  GEOBI_LAUNCH_OK("vertex_ring (fill)");
+  if (nnz_host) return finish_sync(status, rowptr, n_verts, nnz_host, "mesh_vertex_csr", st);
+  return GEOBI_OK;
+}
+
 // member CSR -> the padded [n, k] int64 table of the reference's mesh arrays (vf_indices / vv_indices: OpenMesh circulators padded with -1)
 __global__ void __launch_bounds__(256) pad_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ members, int64_t n, int k,
                                                        int divisor, int64_t* __restrict__ out) {

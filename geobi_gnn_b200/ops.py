@@ -494,6 +494,28 @@ def calc_weight(pos: torch.Tensor, nrm: torch.Tensor, edge_index: torch.Tensor) 
     return w
 
 
+RING_MAX_VALENCE = 24
+
+
+def mesh_vertex_csr(fv: torch.Tensor, vf_rowptr: torch.Tensor, corners: torch.Tensor, n_verts: int) -> CSRGraph:
+    """Vertex 1-ring CSR (symmetric, ascending rows, no loops) from the faces-around-vertices CSR (group_by over fv.reshape(-1)).
+    Syncs once (entry count).  Valences above RING_MAX_VALENCE raise: use csr_from_coo on the half edges."""
+    _need_cuda(fv, vf_rowptr, corners)
+    lib = _lib.load()
+    fv = fv.contiguous().long()
+    f = fv.size(0)
+    dev = fv.device
+    rowptr = torch.empty(n_verts + 1, dtype=torch.int32, device=dev)
+    nbr = torch.empty(max(6 * f, 1), dtype=torch.int32, device=dev)
+    ws = _ws(lib.geobi_mesh_vertex_csr_ws_bytes(n_verts), dev)
+    nnz = C.c_int64(0)
+    _lib.check(lib.geobi_mesh_vertex_csr(_ptr(fv), _ptr(vf_rowptr), _ptr(corners.contiguous()), n_verts, f, _ptr(rowptr), _ptr(nbr), C.byref(nnz),
+                                         _ptr(ws), ws.numel(), _stream()), "mesh_vertex_csr")
+    _count(3)
+    k = int(nnz.value)
+    return CSRGraph(rowptr, nbr[:k], n_verts, k, None, True)
+
+
 def pad_rows(rowptr: torch.Tensor, members: torch.Tensor, k: int, divisor: int = 1) -> torch.Tensor:
     """Member CSR -> padded int64 [n, k] table, entries divided by `divisor`, -1 pads (the reference's vf_indices / vv_indices layout)."""
     _need_cuda(rowptr, members)

@@ -33,16 +33,19 @@ class DeviceTriMesh:
                                   dtype=torch.int64, device=dev).contiguous()
         V, Fc = self.points.size(0), self.fv.size(0)
         self.n_vertices, self.n_faces = V, Fc
-        # --- vertex adjacency (no loops, rows sorted, symmetric) and the unique undirected edges
-        h = torch.stack([self.fv.reshape(-1), self.fv[:, [1, 2, 0]].reshape(-1)])
-        self.vertex_csr = ops.csr_from_coo(h, V, None, ops.COO_SYMMETRIZE | ops.COO_SORT_NBR | ops.COO_DEDUP | ops.COO_DROP_SELF)
-        self.vertex_csr.symmetric = True
-        self._ev = None                # unique undirected edges: built on first read (the device front end itself never needs them)
         # --- faces around each vertex, ascending, padded to the maximum valence
         mrowptr, members = ops.group_by(self.fv.reshape(-1).to(torch.int32), V)
         self.vf_rowptr, self.vf_members = mrowptr, members.div(3, rounding_mode="floor").to(torch.int32)
         k = int((mrowptr[1:] - mrowptr[:-1]).max()) if V else 0
         self.vf = ops.pad_rows(mrowptr, members, k, 3)
+        # --- vertex adjacency (no loops, rows sorted, symmetric): the other corners of each vertex's faces, deduplicated per row
+        if 0 < k <= ops.RING_MAX_VALENCE and Fc:
+            self.vertex_csr = ops.mesh_vertex_csr(self.fv, mrowptr, members, V)
+        else:                          # very high valences (or an empty mesh): the general builder over the 3F half edges
+            h = torch.stack([self.fv.reshape(-1), self.fv[:, [1, 2, 0]].reshape(-1)])
+            self.vertex_csr = ops.csr_from_coo(h, V, None, ops.COO_SYMMETRIZE | ops.COO_SORT_NBR | ops.COO_DEDUP | ops.COO_DROP_SELF)
+        self.vertex_csr.symmetric = True
+        self._ev = None                # unique undirected edges: built on first read (the device front end itself never needs them)
         self.vf_sorted = True          # rows ascending, pads last: lets build_facet_graph merge instead of sort
         self.update_normals()
 

@@ -147,6 +147,15 @@ GEOBI_API size_t geobi_group_by_ws_bytes(int64_t n_nodes, int64_t n_clusters);
 GEOBI_API int geobi_group_by(const int32_t* cluster, int64_t n_nodes, int64_t n_clusters, int32_t* mrowptr,
                    int32_t* members, void* ws, size_t ws_bytes, void* stream);
 
+/* Vertex adjacency of a triangle mesh = to_undirected(unique edges) of dataset.py:211 without the self loops, from the incidence CSR
+ * (geobi_group_by over fv.reshape(-1): `corners` are flat corner indices 3 f + c): symmetric, rows ascending, duplicate-free - the CSR
+ * geobi_csr_from_coo(SYMMETRIZE | SORT_NBR | DEDUP | DROP_SELF) builds from the 3F half edges, in two kernels + a scan.  Valences
+ * above 24 are rejected on the device (GEOBI_ERR_RANGE): use the general builder.  nbr capacity 6 F.  SYNCS if nnz_host != NULL. */
+GEOBI_API size_t geobi_mesh_vertex_csr_ws_bytes(int64_t n_verts);
+GEOBI_API int geobi_mesh_vertex_csr(const int64_t* fv, const int32_t* vf_rowptr, const int32_t* corners, int64_t n_verts,
+                          int64_t n_faces, int32_t* rowptr, int32_t* nbr, int64_t* nnz_host, void* ws, size_t ws_bytes,
+                          void* stream);
+
 /* Member CSR -> padded [n_rows, k] int64 table (entry / divisor, -1 pads): OpenMesh's vf_indices / vv_indices layout
  * (dataset.py:204-206) from geobi_group_by's output (divisor 3: corner index -> face id) or from a vertex CSR (divisor 1). */
 GEOBI_API int geobi_pad_rows(const int32_t* rowptr, const int32_t* members, int64_t n_rows, int64_t k, int divisor,

@@ -309,3 +309,34 @@ def test_csr_native_front_end_pieces_equal_the_list_based_ones():
         w_list = data_util.calc_weight(m.points, m.vertex_normals, eiv)
         w_csr = ops.calc_weight_csr(m.points, m.vertex_normals, gv, m.n_vertices)[: gv.nnz]
         assert torch.equal(w_csr, w_list[: gv.nnz])
+
+
+@pytest.mark.gpu
+def test_vertex_ring_csr_equals_the_general_builder():
+    """geobi_mesh_vertex_csr (other corners of each vertex's faces, sorted + deduplicated per row) = csr_from_coo over the symmetrised half
+    edges, bit for bit: closed mesh, open mesh (boundary valences), an isolated vertex, a degenerate face; a fan of valence 30 (above the
+    kernel's limit) is rejected by the kernel and routed through the general builder by DeviceTriMesh."""
+    import numpy as np
+    from geobi_gnn_b200 import _lib, ops, synth, topology
+    p, f = synth.icosphere(7)
+    degenerate = np.concatenate([f, [[3, 3, 9]]])
+    cases = [(p, f), (p, f[: f.shape[0] // 3]), (np.concatenate([p, [[2.0, 0, 0]]]), f), (p, degenerate)]
+    for pts, fcs in cases:
+        fv = torch.as_tensor(np.asarray(fcs), dtype=torch.int64, device="cuda")
+        V = len(pts)
+        h = torch.stack([fv.reshape(-1), fv[:, [1, 2, 0]].reshape(-1)])
+        want = ops.csr_from_coo(h, V, None, ops.COO_SYMMETRIZE | ops.COO_SORT_NBR | ops.COO_DEDUP | ops.COO_DROP_SELF)
+        mrowptr, corners = ops.group_by(fv.reshape(-1).to(torch.int32), V)
+        got = ops.mesh_vertex_csr(fv, mrowptr, corners, V)
+        assert got.nnz == want.nnz and torch.equal(got.rowptr, want.rowptr) and torch.equal(got.nbr, want.nbr)
+    # a fan: vertex 0 with 30 incident faces
+    n = 30
+    ang = np.linspace(0, 2 * np.pi, n, endpoint=False)
+    pts = np.concatenate([[[0.0, 0, 0]], np.stack([np.cos(ang), np.sin(ang), 0 * ang], 1)])
+    fcs = np.array([[0, 1 + i, 1 + (i + 1) % n] for i in range(n)])
+    fv = torch.as_tensor(fcs, dtype=torch.int64, device="cuda")
+    mrowptr, corners = ops.group_by(fv.reshape(-1).to(torch.int32), n + 1)
+    with pytest.raises(_lib.GeobiError):
+        ops.mesh_vertex_csr(fv, mrowptr, corners, n + 1)
+    m = topology.DeviceTriMesh(pts, fcs, "cuda")
+    assert int((m.vertex_csr.rowptr[1:] - m.vertex_csr.rowptr[:-1]).max()) == n and m.vertex_csr.nnz == 4 * n
