@@ -372,7 +372,7 @@ __global__ void split_rows_kernel(const float* __restrict__ A, int64_t lda, int6
 // hi|lo packed side by side in one 128-byte swizzle row), the 256 hidden activations of a chunk are consumed straight out of TMEM:
 // +b1, leaky_relu, dotted with W2 (<= 4 outputs) on CUDA cores.  The [N,1024] hidden never reaches shared memory or HBM.
 // 256 threads: warps w and w+4 share a TMEM lane quadrant and split each chunk's columns.
-constexpr int FC_CHUNK = 256;
+constexpr int FC_CHUNK = 128;         // hidden units per MMA chunk: two row tiles x 128 columns = 256 TMEM columns per CTA (two CTAs per SM)
 // W1 [hidden, 32] fp32 -> [hidden, 64] bf16 rows: hi(W1[r, :]) | lo(W1[r, :]) - one 128-byte swizzle row per hidden unit, so a
 // 256-row TMA box is a ready B-operand tile (k 0..31 = hi, 32..63 = lo).  Done once per call instead of by every CTA per chunk.
 __global__ void fc_w1_split_kernel(const float* __restrict__ W1, int hidden, __nv_bfloat16* __restrict__ out) {
@@ -404,6 +404,9 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
   return d;
 }
+// Two 128-row tiles per CTA share every read of the {b1, W2} table: the epilogue is bound by those broadcast LDS.128 (ncu round 2:
+// 64 shared-memory wavefronts per node with one tile, data pipe 70 % + 15 % busy), so each table entry now serves two rows per thread.
+constexpr int FC_TILES = 2;
 __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict__ f, int64_t ldf, int64_t N,
                                                          const __grid_constant__ CUtensorMap tm_w1,
                                                          const float* __restrict__ b1, int hidden, const float* __restrict__ W2,
@@ -414,16 +417,16 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
   __shared__ __align__(8) uint64_t mbar;
   __shared__ __align__(8) uint64_t w_full[2];          // W1 chunk landed in b_t[0 / 1] (TMA, byte-counted)
   __shared__ uint32_t tmem_slot;
-  __shared__ float part[128][4];
+  __shared__ float part[FC_TILES * 128][4];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* a_t = sm;                                   // [128 rows x 128 B]: k 0..31 = hi, 32..63 = lo
-  uint8_t* b_t = sm + BM * 128;                        // 2 x [256 rows x 128 B]: same packing for the W1 chunks (double buffered)
+  uint8_t* a_t = sm;                                   // FC_TILES x [128 rows x 128 B]: k 0..31 = hi, 32..63 = lo
+  uint8_t* b_t = sm + FC_TILES * BM * 128;             // 2 x [FC_CHUNK rows x 128 B]: same packing for the W1 chunks (double buffered)
   // [hidden / 2][2] float4: {b1[j], b1[j+1], w2_0[j], w2_0[j+1]}, {w2_1[j], w2_1[j+1], w2_2[j], w2_2[j+1]} - pairs of hidden units
   // so that the epilogue runs on packed f32x2 instructions
-  float4* tab = reinterpret_cast<float4*>(sm + BM * 128 + 2 * FC_CHUNK * 128);
+  float4* tab = reinterpret_cast<float4*>(sm + FC_TILES * BM * 128 + 2 * FC_CHUNK * 128);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int64_t m0 = (int64_t)blockIdx.x * (FC_TILES * BM);
 
   const int n_chunks = hidden / FC_CHUNK;
   if (tid == 0) {
@@ -436,23 +439,24 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
       tma_load_2d(smem_u32(b_t + c * FC_CHUNK * 128), &tm_w1, 0, c * FC_CHUNK, &w_full[c]);
     }
   }
-  if (warp == 0) tmem_alloc(&tmem_slot, FC_CHUNK);
+  if (warp == 0) tmem_alloc(&tmem_slot, FC_TILES * FC_CHUNK);
   for (int j2 = tid; j2 < hidden / 2; j2 += 256) {
     const int j = 2 * j2;
     tab[2 * j2] = make_float4(b1[j], b1[j + 1], W2[j], W2[j + 1]);
     tab[2 * j2 + 1] = make_float4(CO > 1 ? W2[hidden + j] : 0.f, CO > 1 ? W2[hidden + j + 1] : 0.f, CO > 2 ? W2[2 * hidden + j] : 0.f,
                                   CO > 2 ? W2[2 * hidden + j + 1] : 0.f);
   }
-  // A tile: 128 rows x 8 float4
-  for (int idx = tid; idx < BM * 8; idx += 256) {
+  // A tiles: FC_TILES x 128 rows x 8 float4
+  for (int idx = tid; idx < FC_TILES * BM * 8; idx += 256) {
     const int r = idx >> 3, c4 = idx & 7;
     const int64_t m = m0 + r;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (m < N) v = *reinterpret_cast<const float4*>(f + m * ldf + c4 * 4);
     uint2 hi, lo;
     split_bf16x4(v, hi, lo);
-    *reinterpret_cast<uint2*>(a_t + sw128_off(r, c4 >> 1) + (c4 & 1) * 8) = hi;
-    *reinterpret_cast<uint2*>(a_t + sw128_off(r, 4 + (c4 >> 1)) + (c4 & 1) * 8) = lo;
+    uint8_t* at = a_t + (r >> 7) * (BM * 128);
+    *reinterpret_cast<uint2*>(at + sw128_off(r & 127, c4 >> 1) + (c4 & 1) * 8) = hi;
+    *reinterpret_cast<uint2*>(at + sw128_off(r & 127, 4 + (c4 >> 1)) + (c4 & 1) * 8) = lo;
   }
   tc_fence_before();
   __syncthreads();
@@ -460,24 +464,32 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
   const uint32_t tmem_d = tmem_slot;
   constexpr uint32_t idesc = make_idesc(BM, FC_CHUNK);
   const int row = (warp & 3) * 32 + lane;
-  const int chalf = warp >> 2;                         // which 128 columns of the chunk this warp consumes
-  const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * 128);
-  unsigned long long y0p = 0ull, y1p = 0ull, y2p = 0ull;   // (even, odd) hidden-unit partial sums of the three outputs
+  const int chalf = warp >> 2;                         // which half of the chunk's columns this warp consumes
+  constexpr int HC = FC_CHUNK / 2;                     // columns per warp and chunk
+  const uint32_t lane_addr = tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(chalf * HC);
+  unsigned long long yp[FC_TILES][3];                  // (even, odd) hidden-unit partial sums of the three outputs, per row tile
+#pragma unroll
+  for (int t = 0; t < FC_TILES; ++t) yp[t][0] = yp[t][1] = yp[t][2] = 0ull;
 
   for (int ch = 0; ch < n_chunks; ++ch) {
-    if (ch == 0) fence_proxy_async();                  // the A tile was written with generic stores
+    if (ch == 0) fence_proxy_async();                  // the A tiles were written with generic stores
     tc_fence_before();
     __syncthreads();                                   // every warp has finished reading TMEM of the previous chunk
     if (tid < 32 && elect_one()) {
       mbar_wait(&w_full[ch & 1], (uint32_t)((ch >> 1) & 1));
       tc_fence_after();
-      const uint64_t ad = make_desc(smem_u32(a_t)), bd = make_desc(smem_u32(b_t + (ch & 1) * FC_CHUNK * 128));
-      mma_f16(tmem_d, ad + 0, bd + 0, idesc, 0u);      // hi . hi   (k 0..15)
-      mma_f16(tmem_d, ad + 2, bd + 2, idesc, 1u);      // hi . hi   (k 16..31)
-      mma_f16(tmem_d, ad + 0, bd + 4, idesc, 1u);      // hi . lo
-      mma_f16(tmem_d, ad + 2, bd + 6, idesc, 1u);
-      mma_f16(tmem_d, ad + 4, bd + 0, idesc, 1u);      // lo . hi
-      mma_f16(tmem_d, ad + 6, bd + 2, idesc, 1u);
+      const uint64_t bd = make_desc(smem_u32(b_t + (ch & 1) * FC_CHUNK * 128));
+#pragma unroll
+      for (int t = 0; t < FC_TILES; ++t) {
+        const uint64_t ad = make_desc(smem_u32(a_t + t * (BM * 128)));
+        const uint32_t acc = tmem_d + (uint32_t)(t * FC_CHUNK);
+        mma_f16(acc, ad + 0, bd + 0, idesc, 0u);       // hi . hi   (k 0..15)
+        mma_f16(acc, ad + 2, bd + 2, idesc, 1u);       // hi . hi   (k 16..31)
+        mma_f16(acc, ad + 0, bd + 4, idesc, 1u);       // hi . lo
+        mma_f16(acc, ad + 2, bd + 6, idesc, 1u);
+        mma_f16(acc, ad + 4, bd + 0, idesc, 1u);       // lo . hi
+        mma_f16(acc, ad + 6, bd + 2, idesc, 1u);
+      }
       mma_commit(&mbar);
     }
     mbar_wait(&mbar, (uint32_t)(ch & 1));
@@ -486,67 +498,83 @@ __global__ void __launch_bounds__(256) fc_head_tc_kernel(const float* __restrict
       mbar_expect_tx(&w_full[ch & 1], FC_CHUNK * 128);
       tma_load_2d(smem_u32(b_t + (ch & 1) * FC_CHUNK * 128), &tm_w1, 0, (ch + 2) * FC_CHUNK, &w_full[ch & 1]);
     }
-    const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tab) + ch * FC_CHUNK + chalf * 128;   // 2 entries per column pair
-    // two register sets: the TMEM read of the next 32 columns is in flight while the current 32 are consumed; a column pair
-    // costs 2 LDS.128 + add2 + mul2 + 2 max + 3 fma2 (9 issue slots instead of 14 with scalar arithmetic)
-    uint32_t va[32], vb[32];
-    auto consume = [&](const uint32_t* v, int col0) {
+    const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tab) + ch * FC_CHUNK + chalf * HC;   // 2 entries per column pair
+    // per 16 columns: both tiles' accumulator values are read from TMEM (the next 16 columns' reads are in flight meanwhile), and a
+    // column pair costs 2 LDS.128 for BOTH rows + per row add2 + mul2 + 2 max + 3 fma2
+    uint32_t va[FC_TILES][16], vb[FC_TILES][16];
+    auto consume = [&](const uint32_t (&v)[FC_TILES][16], int col0) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
+      for (int j = 0; j < 16; j += 2) {
         const ulonglong2 ta = t2[col0 + j], tb = t2[col0 + j + 1];
-        unsigned long long h = add2(pack_u2(v[j], v[j + 1]), ta.x);          // + b1
-        const unsigned long long hs = mul2(h, 0x3e4ccccd3e4ccccdull);        // 0.2f, 0.2f
-        h = pack_u2(__float_as_uint(fmaxf(__uint_as_float((unsigned)h), __uint_as_float((unsigned)hs))),
-                    __float_as_uint(fmaxf(__uint_as_float((unsigned)(h >> 32)), __uint_as_float((unsigned)(hs >> 32)))));
-        y0p = fma2(ta.y, h, y0p);
-        y1p = fma2(tb.x, h, y1p);
-        y2p = fma2(tb.y, h, y2p);
+#pragma unroll
+        for (int t = 0; t < FC_TILES; ++t) {
+          unsigned long long h = add2(pack_u2(v[t][j], v[t][j + 1]), ta.x);          // + b1
+          const unsigned long long hs = mul2(h, 0x3e4ccccd3e4ccccdull);              // 0.2f, 0.2f
+          h = pack_u2(__float_as_uint(fmaxf(__uint_as_float((unsigned)h), __uint_as_float((unsigned)hs))),
+                      __float_as_uint(fmaxf(__uint_as_float((unsigned)(h >> 32)), __uint_as_float((unsigned)(hs >> 32)))));
+          yp[t][0] = fma2(ta.y, h, yp[t][0]);
+          yp[t][1] = fma2(tb.x, h, yp[t][1]);
+          yp[t][2] = fma2(tb.y, h, yp[t][2]);
+        }
       }
     };
-    tmem_ld32_issue(lane_addr, va);
+    auto issue = [&](uint32_t (&v)[FC_TILES][16], int col0) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+      for (int t = 0; t < FC_TILES; ++t) tmem_ld16_issue(lane_addr + (uint32_t)(t * FC_CHUNK + col0), v[t]);
+    };
+    issue(va, 0);
+#pragma unroll
+    for (int q = 0; q < HC / 32; ++q) {
       tmem_ld_wait();
-      tmem_ld32_issue(lane_addr + (uint32_t)(64 * half + 32), vb);
-      consume(va, 64 * half);
+      issue(vb, 32 * q + 16);
+      consume(va, 32 * q);
       tmem_ld_wait();
-      if (half == 0) tmem_ld32_issue(lane_addr + 64u, va);
-      consume(vb, 64 * half + 32);
+      if (q + 1 < HC / 32) issue(va, 32 * q + 32);
+      consume(vb, 32 * q + 16);
     }
     tc_fence_before();
   }
-  const float y0 = __uint_as_float((unsigned)y0p) + __uint_as_float((unsigned)(y0p >> 32));
-  const float y1 = __uint_as_float((unsigned)y1p) + __uint_as_float((unsigned)(y1p >> 32));
-  const float y2 = __uint_as_float((unsigned)y2p) + __uint_as_float((unsigned)(y2p >> 32));
-  if (chalf == 1) {
-    part[row][0] = y0;
-    part[row][1] = y1;
-    part[row][2] = y2;
-  }
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, FC_CHUNK);
-  const int64_t n = m0 + row;
-  if (chalf != 0 || n >= N) return;
-  float y[3] = {y0 + part[row][0] + b2[0], CO > 1 ? y1 + part[row][1] + b2[1] : 0.f, CO > 2 ? y2 + part[row][2] + b2[2] : 0.f};
-  int co = CO;
-  if (epilogue == 2) {
-    if (CO == 1) {
-      const float s0 = y[0];
-      for (int c = 0; c < 3; ++c) y[c] = s0 * res2[n * ldres2 + c];
-      co = 3;
-    } else {
-      for (int c = 0; c < co; ++c) y[c] *= res2[n * ldres2 + c];
+  float y0[FC_TILES], y1[FC_TILES], y2[FC_TILES];
+#pragma unroll
+  for (int t = 0; t < FC_TILES; ++t) {
+    y0[t] = __uint_as_float((unsigned)yp[t][0]) + __uint_as_float((unsigned)(yp[t][0] >> 32));
+    y1[t] = __uint_as_float((unsigned)yp[t][1]) + __uint_as_float((unsigned)(yp[t][1] >> 32));
+    y2[t] = __uint_as_float((unsigned)yp[t][2]) + __uint_as_float((unsigned)(yp[t][2] >> 32));
+    if (chalf == 1) {
+      part[t * 128 + row][0] = y0[t];
+      part[t * 128 + row][1] = y1[t];
+      part[t * 128 + row][2] = y2[t];
     }
   }
-  if (epilogue == 1 || epilogue == 2)
-    for (int c = 0; c < co; ++c) y[c] += res[n * ldres + c];
-  if (epilogue == 3) {
-    float s2 = 0.f;
-    for (int c = 0; c < co; ++c) s2 += y[c] * y[c];
-    const float d = fmaxf(sqrtf(s2), 1e-12f);
-    for (int c = 0; c < co; ++c) y[c] /= d;
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, FC_TILES * FC_CHUNK);
+  if (chalf != 0) return;
+#pragma unroll
+  for (int t = 0; t < FC_TILES; ++t) {
+    const int64_t n = m0 + t * 128 + row;
+    if (n >= N) continue;
+    const float* pt = part[t * 128 + row];
+    float y[3] = {y0[t] + pt[0] + b2[0], CO > 1 ? y1[t] + pt[1] + b2[1] : 0.f, CO > 2 ? y2[t] + pt[2] + b2[2] : 0.f};
+    int co = CO;
+    if (epilogue == 2) {
+      if (CO == 1) {
+        const float s0 = y[0];
+        for (int c = 0; c < 3; ++c) y[c] = s0 * res2[n * ldres2 + c];
+        co = 3;
+      } else {
+        for (int c = 0; c < co; ++c) y[c] *= res2[n * ldres2 + c];
+      }
+    }
+    if (epilogue == 1 || epilogue == 2)
+      for (int c = 0; c < co; ++c) y[c] += res[n * ldres + c];
+    if (epilogue == 3) {
+      float s2 = 0.f;
+      for (int c = 0; c < co; ++c) s2 += y[c] * y[c];
+      const float d = fmaxf(sqrtf(s2), 1e-12f);
+      for (int c = 0; c < co; ++c) y[c] /= d;
+    }
+    for (int c = 0; c < co; ++c) out[n * ldo + c] = y[c];
   }
-  for (int c = 0; c < co; ++c) out[n * ldo + c] = y[c];
 }
 
 }  // namespace tc
@@ -609,7 +637,7 @@ int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float
                    const float* b2, int c_out, int epilogue, const float* res, int64_t ldres, const float* res2, int64_t ldres2, float* out,
                    int64_t ldo, void* ws, size_t ws_bytes, cudaStream_t st) {
   GEOBI_REQUIRE(c_in == 32, "fc_head_fwd (tensor core): c_in must be 32 (got %d)", c_in);
-  GEOBI_REQUIRE(hidden % tc::FC_CHUNK == 0 && hidden <= 4096, "fc_head_fwd (tensor core): hidden must be a multiple of 256, <= 4096");
+  GEOBI_REQUIRE(hidden % tc::FC_CHUNK == 0 && hidden <= 4096, "fc_head_fwd (tensor core): hidden must be a multiple of 128, <= 4096");
   GEOBI_REQUIRE(c_out <= 3, "fc_head_fwd (tensor core): c_out must be <= 3 (got %d)", c_out);
   GEOBI_REQUIRE(ldf % 4 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "fc_head_fwd (tensor core): feature rows must be 16-byte aligned");
   if (!ws || ws_bytes < fc_head_tc_ws_bytes(hidden) || (reinterpret_cast<uintptr_t>(ws) & 127) != 0) {
@@ -624,9 +652,9 @@ int fc_head_fwd_tc(const float* f, int64_t ldf, int64_t n, int c_in, const float
     set_error("fc_head_fwd (tensor core): cuTensorMapEncodeTiled unavailable");
     return GEOBI_ERR_CUDA;
   }
-  const size_t smem = (size_t)tc::BM * 128 + 2 * tc::FC_CHUNK * 128 + (size_t)hidden * 16 + 1024;
+  const size_t smem = (size_t)tc::FC_TILES * tc::BM * 128 + 2 * tc::FC_CHUNK * 128 + (size_t)hidden * 16 + 1024;
   GEOBI_CUDA_OK(cudaFuncSetAttribute(tc::fc_head_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  tc::fc_head_tc_kernel<<<(unsigned)cdiv(n, tc::BM), 256, smem, st>>>(f, ldf, n, tm, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2,
+  tc::fc_head_tc_kernel<<<(unsigned)cdiv(n, tc::FC_TILES * tc::BM), 256, smem, st>>>(f, ldf, n, tm, b1, hidden, W2, b2, c_out, epilogue, res, ldres, res2,
                                                                      ldres2, out, ldo);
   GEOBI_LAUNCH_OK("fc_head_tc");
   return GEOBI_OK;
