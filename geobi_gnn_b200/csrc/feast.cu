@@ -36,9 +36,13 @@ static inline size_t proj_smem_bytes(int c_in) {
   return (size_t)H * cp * sizeof(double) + (size_t)(cp > PROJ_CC ? 2 : 1) * PROJ_NODES * PROJ_LD * sizeof(float);
 }
 
-__global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C,
+// CT: compile-time channel count (32 / 64 / 128: the network's layers; folds the divisions of the staging loop and the bounds tests -
+// the generic instance spent 43 M of its 62 M warp instructions per 1 M x 64 launch outside the DFMAs), 0 = runtime C.
+template <int CT>
+__global__ void __launch_bounds__(PROJ_THREADS) feast_project_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C_rt,
                                                                      const float* __restrict__ U, double* __restrict__ P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = CT ? CT : C_rt;
   const int Cp = (C + 3) & ~3;
   double* Us = reinterpret_cast<double*>(smem_raw);          // [H][Cp], zero padded
   float* xs0 = reinterpret_cast<float*>(Us + H * Cp);        // [2][PROJ_NODES][PROJ_LD] (one buffer when a single chunk covers C)
@@ -1077,11 +1081,19 @@ static void launch_aggregate(int out_mode, unsigned blocks, cudaStream_t st, con
 static int launch_project(const float* x, int64_t ldx, int64_t N, int c_in, const float* U, double* P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem_bytes(128)));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_project_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem_bytes(128)));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_project_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem_bytes(32)));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_project_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem_bytes(64)));
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(feast_project_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)proj_smem_bytes(128)));
     attr_set = true;
   }
   if (N == 0) return GEOBI_OK;
-  feast_project_kernel<<<(unsigned)cdiv(N, PROJ_NODES), PROJ_THREADS, proj_smem_bytes(c_in), st>>>(x, ldx, N, c_in, U, P);
+  const unsigned grid = (unsigned)cdiv(N, PROJ_NODES);
+  const size_t smem = proj_smem_bytes(c_in);
+  if (c_in == 32) feast_project_kernel<32><<<grid, PROJ_THREADS, smem, st>>>(x, ldx, N, c_in, U, P);
+  else if (c_in == 64) feast_project_kernel<64><<<grid, PROJ_THREADS, smem, st>>>(x, ldx, N, c_in, U, P);
+  else if (c_in == 128) feast_project_kernel<128><<<grid, PROJ_THREADS, smem, st>>>(x, ldx, N, c_in, U, P);
+  else feast_project_kernel<0><<<grid, PROJ_THREADS, smem, st>>>(x, ldx, N, c_in, U, P);
   GEOBI_LAUNCH_OK("feast_project");
   return GEOBI_OK;
 }
