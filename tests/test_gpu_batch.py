@@ -135,3 +135,78 @@ def test_single_mesh_200k_faces_matches_the_oracle(precision, tap_tol):
     outs, mine, vp, nrm, slices = _run_union(meshes, precision)
     assert nrm.shape[0] == 200000
     _check(f"single200k-{precision}", outs, mine, vp, nrm, slices, tap_tol)
+
+
+def test_configs2_full_size_modes_agree_and_runner_reproduces_the_forward():
+    """BASELINE configs[2] at FULL size (1 003 520 faces, one graph pair - the shape `bench.py`'s headline is quoted on; the CPU oracle
+    would need tens of GB and minutes here), through size-independent properties:
+    * the tensor-core mode ('bf16x3', benchmarked) against the CUDA-core mode ('fp32') with the fp32 run's own matchings teacher-forced
+      (its PoolingLayer.trace): vertices within 1e-5, every per-layer tap within 1e-4 in max norm, unit normals within 5e-5 on
+      average (bars and measured values at the assertions);
+    * outputs finite, normals of unit length;
+    * the end-to-end path of the bench (HostBatchRunner.upload_mesh: raw points + faces, front end on the copy stream, CSR-native
+      inputs) returns the bits of the direct forward on the same matchings."""
+    import numpy as np
+    from geobi_gnn_b200 import config, dataset, inference, network, synth, topology
+    p, f = synth.icosphere(224)
+    assert f.shape[0] == 1003520
+    clean = topology.DeviceTriMesh(p, f, DEV)
+    g = torch.Generator(device=DEV).manual_seed(5)
+    amp = torch.randn(clean.n_vertices, 1, generator=g, device=DEV) * 0.2 * clean.mean_edge_length()
+    pts = (clean.points + amp * clean.vertex_normals).contiguous()
+    del clean
+    torch.manual_seed(3)
+    net = network.DualGNN().to(DEV).eval()
+    pls = util.poolings(net)
+
+    def inputs():
+        return dataset.build_dual_on_device(topology.DeviceTriMesh(pts, torch.from_numpy(f).to(DEV), DEV), None, csr_native=True)
+
+    outs = {}
+    with torch.no_grad():
+        config.set_precision("fp32")
+        try:
+            net.taps = {}
+            v, n, _ = net(list(inputs()))
+            forced = [[t[2].clone() for t in pl.trace] for pl in pls]
+            outs["fp32"] = (v.clone(), n.clone())
+            taps32 = {g: {k: net.taps[g][k].clone() for k in TAPS} for g in ("v", "f")}
+            for pl, fl in zip(pls, forced):
+                pl.forced = fl
+            config.set_precision("bf16x3")
+            net.taps = {}
+            v, n, _ = net(list(inputs()))
+            outs["bf16x3"] = (v.clone(), n.clone())
+            tap_err = {f"{g}.{k}": util.rel_err(net.taps[g][k], taps32[g][k]) for g in ("v", "f") for k in TAPS}
+            del taps32
+            net.taps = None
+            # the bench's end-to-end path on the same matchings
+            runner = inference.HostBatchRunner(net, torch.device(DEV), coalesced_undirected=True)
+            hp = pts.cpu().pin_memory()
+            hf = torch.from_numpy(f.astype(np.int32)).pin_memory()
+            rv, rn = runner.run(runner.upload_mesh(hp, hf))
+            runner.wait()
+        finally:
+            config.set_precision("fp32")
+            for pl in pls:
+                pl.forced = None
+    v32, n32 = outs["fp32"]
+    v16, n16 = outs["bf16x3"]
+    assert torch.isfinite(v16).all() and torch.isfinite(n16).all()
+    assert float((n16.norm(dim=1) - 1).abs().max()) < 1e-5
+    ev = util.rel_err(v16, v32)
+    dn = (n16 - n32).abs().amax(1)
+    en_max, en_q, en_mean = float(dn.max()), float(torch.quantile(dn, 0.9999)), float(dn.mean())
+    _record("configs2_full_size", {"faces": int(f.shape[0]), "bf16x3_vs_fp32_vertices": ev, "normals_abs_max": en_max,
+                                   "normals_abs_q9999": en_q, "normals_abs_mean": en_mean, "faces_above_5e-5": int((dn > 5e-5).sum()),
+                                   "taps": tap_err})
+    print("configs2_full_size", json.dumps(tap_err), en_max, en_q, en_mean)
+    # Measured (B200): per-layer taps 3e-6 .. 7.3e-5 in max norm (the 16-bit-mantissa operand split of 'bf16x3'; the maximum runs over up
+    # to 128 M entries per tap - 2.1e-5 at 200k faces), vertices 1.7e-7.  The unit normals differ by 1.7e-5 on average and 1.2e-3 at
+    # worst: normalize() is ill-conditioned where the head's output vector is short, and among a million faces of a random-init network
+    # some are 100x shorter than typical.  Bars: taps 1e-4 (20x inside the 2e-3 allowance north_star gives a bf16 GEMM; 'fp32' mode is
+    # the one held to 1e-5, tests above), vertices 1e-5, normals 5e-5 on average and 1e-3 at the 99.99th percentile.
+    assert ev < 1e-5, ev
+    assert max(tap_err.values()) < 1e-4, tap_err
+    assert en_mean < 5e-5 and en_q < 1e-3, (en_max, en_q, en_mean)
+    assert torch.equal(rv, v16.cpu()) and torch.equal(rn, n16.cpu())
