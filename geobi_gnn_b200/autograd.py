@@ -29,11 +29,14 @@ def feast_aggregate(x, g, U, c):
     return P, Z
 
 
-def feast_bwd_edges(x, g, P, c, dZ):
+def feast_bwd_edges(x, g, P, c, dZ, need_dx=True):
+    """need_dx=False (the layer's input needs no gradient: the network's two input layers): dx is neither allocated nor accumulated."""
     lib = _lib.load()
     x, ldx, c_in = _rows(x)
     n = x.size(0)
-    dx = torch.zeros((n, c_in), dtype=torch.float32, device=x.device)
+    if not need_dx and not (c_in <= 16 or c_in in (32, 64, 128)):
+        need_dx = True                      # the generic kernel always accumulates it
+    dx = torch.zeros((n, c_in), dtype=torch.float32, device=x.device) if need_dx else None
     dP = torch.zeros((n, H), dtype=torch.float32, device=x.device)
     dc = torch.zeros(H, dtype=torch.float32, device=x.device)
     _lib.check(lib.geobi_feast_bwd_edges(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(P), _ptr(c.contiguous()),
@@ -62,8 +65,9 @@ class FeaStFn(torch.autograd.Function):
         Wf = W.view(H, c_out, c_in).permute(1, 0, 2).reshape(c_out, H * c_in)
         dW = (gpre.t() @ Z).view(c_out, H, c_in).permute(1, 0, 2).reshape(H * c_out, c_in)
         dZ = gpre @ Wf
-        dx, dP, dc = feast_bwd_edges(x, g, P, c, dZ)
-        dx = dx + dP @ U
+        need_dx = ctx.needs_input_grad[0]
+        dx, dP, dc = feast_bwd_edges(x, g, P, c, dZ, need_dx)
+        dx = dx + dP @ U if need_dx else None
         dU = dP.t() @ x
         return dx, dW, dU, dc, dbias, None, None, None
 

@@ -123,6 +123,161 @@ __global__ void __launch_bounds__(256) feast_bwd_edges_kernel(const float* __res
     }
 }
 
+// Round 2: the same backward for C in {32, 64, 128} (every layer but the two input layers) with
+//   * LPR = C/4 lanes per row, each owning 4 adjacent channels: 32/LPR edges of a node in flight per warp instruction, the x_j row read
+//     as one 128-bit load per lane, dx_j updated with ONE red.global.add.v4.f32 per lane (was 2-4 scalar atomics per lane and edge),
+//     the 9 per-edge dot products reduced over LPR lanes (3-5 shuffles each, was 5 over the whole warp for one edge);
+//   * persistent warps (grid = resident CTAs, nodes strided): dc is accumulated in registers across a warp's nodes and leaves the
+//     kernel as 9 atomics per CTA - the one-warp-per-node form issued 9 atomics per NODE on the same 9 addresses.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <int LPR, int CH>
+__global__ void __launch_bounds__(256) feast_bwd_edges_vec_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int C_rt,
+                                                                  const int* __restrict__ rowptr, const int* __restrict__ nbr,
+                                                                  const double* __restrict__ P, const float* __restrict__ cvec,
+                                                                  const float* __restrict__ dZ, int64_t lddz, float* __restrict__ dx,
+                                                                  int64_t lddx, float* __restrict__ dP, float* __restrict__ dc) {
+  constexpr int EPW = 32 / LPR;
+  const int C = CH == 4 ? 4 * LPR : C_rt;        // CH = 1: one channel per lane, lanes sl >= C idle (the 6 / 12-channel input layers)
+  __shared__ __align__(16) float qs[8][32][12];
+  __shared__ float dcs[8][H];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int eg = lane / LPR, sl = lane % LPR, c0 = CH * sl;
+  const bool has_c = c0 < C;
+  float ch[H], dcl[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    ch[h] = cvec[h];
+    dcl[h] = 0.f;
+  }
+  const int64_t n_warps = (int64_t)gridDim.x * 8;
+  for (int64_t i = (int64_t)blockIdx.x * 8 + warp; i < N; i += n_warps) {
+    const int b = rowptr[i];
+    const int total = rowptr[i + 1] - b + 1;
+    const float rcnt = 1.0f / (float)total;
+    double Pi[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) Pi[h] = P[i * H + h];
+    // dZ_i slice owned by this lane: channels c0 .. c0 + 3 of every head
+    float4 dz[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      if (CH == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(dZ + i * lddz + h * C + c0);
+        dz[h] = make_float4(v.x * rcnt, v.y * rcnt, v.z * rcnt, v.w * rcnt);
+      } else {
+        dz[h] = make_float4(has_c ? dZ[i * lddz + h * C + c0] * rcnt : 0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float dPi[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) dPi[h] = 0.f;
+    for (int s0 = 0; s0 < total; s0 += 32) {
+      const int s = s0 + lane;
+      int j = (int)i;
+      if (s < total) {
+        if (s > 0) j = nbr[b + s - 1];
+        float l[H];
+        float m = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          l[h] = p_diff(P[(int64_t)j * H + h], Pi[h]) + ch[h];
+          m = fmaxf(m, l[h]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          l[h] = expf(l[h] - m);
+          sum += l[h];
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) qs[warp][lane][h] = l[h] / sum;
+      }
+      __syncwarp();
+      const int cnt = min(32, total - s0);
+      for (int t0 = 0; t0 < cnt; t0 += EPW) {
+        const int t = t0 + eg;
+        const bool on = t < cnt;
+        const int jt = __shfl_sync(0xffffffffu, j, on ? t : 0);
+        float q[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) q[h] = on ? qs[warp][t][h] : 0.f;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CH == 4) {
+          if (on) xv = *reinterpret_cast<const float4*>(x + (int64_t)jt * ldx + c0);
+        } else if (on && has_c) {
+          xv.x = x[(int64_t)jt * ldx + c0];
+        }
+        float dq[H];
+        float4 gx = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          if (CH == 4) {
+            dq[h] = fmaf(dz[h].w, xv.w, fmaf(dz[h].z, xv.z, fmaf(dz[h].y, xv.y, dz[h].x * xv.x)));
+            gx.y = fmaf(q[h], dz[h].y, gx.y);
+            gx.z = fmaf(q[h], dz[h].z, gx.z);
+            gx.w = fmaf(q[h], dz[h].w, gx.w);
+          } else {
+            dq[h] = dz[h].x * xv.x;
+          }
+          gx.x = fmaf(q[h], dz[h].x, gx.x);
+        }
+        if (dx != nullptr) {        // null: the layer's input needs no gradient (the network's two input layers)
+          if (CH == 4) {
+            if (on) red_add_v4(dx + (int64_t)jt * lddx + c0, gx.x, gx.y, gx.z, gx.w);
+          } else if (on && has_c) {
+            atomicAdd(dx + (int64_t)jt * lddx + c0, gx.x);
+          }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) dq[h] += __shfl_xor_sync(0xffffffffu, dq[h], o);
+          dot = fmaf(q[h], dq[h], dot);
+        }
+        // lane sl of the edge's group finalises head sl (and head sl + LPR where a group has fewer lanes than there are heads)
+        float dl = 0.f, dl2 = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float v = q[h] * (dq[h] - dot);      // 0 for an idle group (q = 0)
+          if (sl == h) dl = v;
+          if (LPR < H && sl + LPR == h) dl2 = v;
+          dPi[h] -= v;
+          dcl[h] += v;
+        }
+        if (on && sl < H) atomicAdd(dP + (int64_t)jt * H + sl, dl);
+        if (LPR < H && on && sl + LPR < H) atomicAdd(dP + (int64_t)jt * H + sl + LPR, dl2);
+      }
+      __syncwarp();
+    }
+    // every lane of a group holds that group's share of dPi: add the groups, lane h (< 9) of group 0 writes head h
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float v = dPi[h];
+#pragma unroll
+      for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == h) atomicAdd(dP + i * H + h, v);
+    }
+  }
+  // dc: groups of a warp, then the warps of the CTA, then 9 atomics
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
+    float v = dcl[h];
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) dcs[warp][h] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < H) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += dcs[w][threadIdx.x];
+    atomicAdd(dc + threadIdx.x, v);
+  }
+}
+
 // dx[member argmax of segment s, c] = g[s, c]; every node belongs to exactly one segment, dx is zero-initialised.
 __global__ void __launch_bounds__(256) segment_max_bwd_kernel(const float* __restrict__ x, int64_t ldx, int C, const int* __restrict__ rowptr,
                                                               const int* __restrict__ idx, int64_t n_seg, const float* __restrict__ g,
@@ -162,10 +317,31 @@ extern "C" int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t N, int
                                      const double* P, const float* c, const float* dZ, float* dx, int64_t lddx, float* dP, float* dc,
                                      void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GEOBI_REQUIRE(x && rowptr && P && c && dZ && dx && dP && dc && N >= 0 && c_in >= 1 && c_in <= 128, "feast_bwd_edges: bad arguments");
+  GEOBI_REQUIRE(x && rowptr && P && c && dZ && dP && dc && N >= 0 && c_in >= 1 && c_in <= 128, "feast_bwd_edges: bad arguments");
   if (N == 0) return GEOBI_OK;
   const unsigned blocks = (unsigned)cdiv(N, 8);
   const int64_t lddz = (int64_t)H * c_in;
+  const bool vec = (c_in == 32 || c_in == 64 || c_in == 128) && ldx % 4 == 0 && lddx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15) == 0;
+  if (vec || c_in <= 16) {
+    static int sms = 0;
+    if (sms == 0) {
+      int dev = 0;
+      GEOBI_CUDA_OK(cudaGetDevice(&dev));
+      GEOBI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const unsigned grid = blocks < (unsigned)(sms * 6) ? blocks : (unsigned)(sms * 6);
+#define BWD_ARGS x, ldx, N, c_in, rowptr, nbr, P, c, dZ, lddz, dx, lddx, dP, dc
+    if (vec && c_in == 32) feast_bwd_edges_vec_kernel<8, 4><<<grid, 256, 0, st>>>(BWD_ARGS);
+    else if (vec && c_in == 64) feast_bwd_edges_vec_kernel<16, 4><<<grid, 256, 0, st>>>(BWD_ARGS);
+    else if (vec) feast_bwd_edges_vec_kernel<32, 4><<<grid, 256, 0, st>>>(BWD_ARGS);
+    else if (c_in <= 8) feast_bwd_edges_vec_kernel<8, 1><<<grid, 256, 0, st>>>(BWD_ARGS);
+    else feast_bwd_edges_vec_kernel<16, 1><<<grid, 256, 0, st>>>(BWD_ARGS);
+#undef BWD_ARGS
+    GEOBI_LAUNCH_OK("feast_bwd_edges (vec)");
+    return GEOBI_OK;
+  }
+  GEOBI_REQUIRE(dx != nullptr, "feast_bwd_edges: dx may only be null for c_in <= 16, 32, 64 or 128");
   if (c_in <= 32) feast_bwd_edges_kernel<1><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, dZ, lddz, dx, lddx, dP, dc);
   else if (c_in <= 64) feast_bwd_edges_kernel<2><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, dZ, lddz, dx, lddx, dP, dc);
   else feast_bwd_edges_kernel<4><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, dZ, lddz, dx, lddx, dP, dc);

@@ -267,7 +267,8 @@ GEOBI_API int geobi_feast_aggregate(const float* x, int64_t ldx, int64_t n_nodes
 
 /* Edge part of the FeaSt backward: given dZ [N, 9*C_in] accumulates (atomically, into zero-initialised buffers)
  * dx [N, C_in] (gradient reaching x through the gathered rows), dP [N, 9] (gradient of the head logits' projections,
- * fp32) and dc [9].  The caller finishes with dX += dP.U, dU = dP^T.X (PyG FeaStConv's autograd, network.py:271-299). */
+ * fp32) and dc [9].  The caller finishes with dX += dP.U, dU = dP^T.X (PyG FeaStConv's autograd, network.py:271-299).
+ * dx may be NULL when the layer's input needs no gradient (c_in <= 16, 32, 64 or 128). */
 GEOBI_API int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr,
                                     const int32_t* nbr, const double* P, const float* c, const float* dZ, float* dx,
                                     int64_t lddx, float* dP, float* dc, void* stream);
