@@ -314,8 +314,9 @@ def run_ours(args, rank, world, local_rank):
             e2e = {"value": round(total_faces * steps / (ms_mesh / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_mesh_bytes,
                    "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_mesh / steps, 4), "cuda_mallocs_in_timed_region": int(allocs_mesh),
                    "path": "inference.HostBatchRunner.upload_mesh: the RAW mesh (points fp32 + faces int32, pinned) -> H2D -> device front end on "
-                           "the copy stream (topology, both graphs, bilateral weights, normalised features, input-level CSRs: "
-                           "topology.DeviceTriMesh + dataset.build_dual_on_device) under the previous step's forward -> DualGNN forward -> "
+                           "the copy stream (topology, both graphs as loop-free CSRs, bilateral weights, normalised features: "
+                           "topology.DeviceTriMesh + dataset.build_dual_on_device(csr_native=True), 0.9 ms of GPU time; the reference's int64 "
+                           "edge lists stay lazy) under the previous step's forward -> DualGNN forward -> "
                            "D2H of vertices and normals on a read-back stream; copy and read-back streams joined before the closing event",
                    "prebuilt_graphs": e2e_graphs}
         return {"value": total_faces * steps / (ms / 1e3), "ms_per_step": ms / steps, "wall_s": wall, "launches": launches, "clocks": clocks, "e2e": e2e}
@@ -371,8 +372,9 @@ def run_ours(args, rank, world, local_rank):
                 "whole_forward": {"alg_bytes_per_face": FORWARD_BYTES_PER_FACE, "achieved": round(fwd_gbs, 1), "unit": "GB/s",
                                   "frac": round(fwd_gbs / peak, 4), "note": "3104 B/face (SURVEY.md 8d) x faces / ms_per_step / peak"},
                 "note": "HBM is the nominal bound of a gather/segment-sum; this kernel's 9-head weighting costs 576 fp32 FMAs per gathered 256-byte "
-                        "row on the FP32 pipe (~0.3 of the HBM peak at 100 % pipe use). The tcgen05 form of the aggregation (feast_tcagg, "
-                        "GEOBI_TCAGG=1) is at parity, not ahead: profiles/r02_NOTES.md section A"}
+                        "row (~0.3 of the HBM peak at 100 % of the FP32 pipe) and ncu shows it bound by its shared-memory data pipe (62 % LSU + "
+                        "10 % tensor-core operand reads after the weights moved to tensor memory). The tcgen05 form of the aggregation "
+                        "(feast_tcagg, GEOBI_TCAGG=1) is 14 % faster as a kernel and level as a layer: profiles/r02_NOTES.md sections A, F"}
         del x, out, flush, g
 
     # ---------------------------------------------------------------- sub-results measured in the same run
