@@ -6,7 +6,6 @@ max-pool routing are libgeobi kernels (`geobi_feast_bwd_edges`, `geobi_segment_m
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import torch
 

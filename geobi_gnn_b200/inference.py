@@ -13,7 +13,7 @@ from typing import List, Optional
 import numpy as np
 import torch
 
-from . import batching, data_util, dataset, patches, synth
+from . import data_util, dataset, patches, synth
 
 
 def host_views(mesh):

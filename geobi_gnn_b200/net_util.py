@@ -12,7 +12,6 @@ and inspection in tests.
 """
 from __future__ import annotations
 
-import dataclasses
 from typing import Optional
 
 import torch
