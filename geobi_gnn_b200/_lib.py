@@ -66,6 +66,7 @@ SIGNATURES = {
     "geobi_fc_head_fwd": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _p, _i32, _i32, _p, _i64, _p, _i64, _p, _i64, _i32, _p, _sz, _p]),
     "geobi_face_normal": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p]),
     "geobi_v2f_transfer": (_i32, [_p, _i64, _p, _p, _i64, _i32, _i64, _p, _i64, _p]),
+    "geobi_v2f_transfer_bwd": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _p]),
     "geobi_update_position_ws_bytes": (_sz, [_i64, _i64]),
     "geobi_update_position": (_i32, [_p, _p, _p, _i64, _p, _i32, _p, _i64, _i64, _p, _p, _sz, _p]),
 }

@@ -123,3 +123,27 @@ class GatherRowsFn(torch.autograd.Function):
         dx = torch.zeros((ctx.n, go.size(1)), dtype=go.dtype, device=go.device)
         dx.index_add_(0, idx.long(), go)
         return dx, None
+
+
+class V2FTransferFn(torch.autograd.Function):
+    """[xf | corner mean of feat_v | face normal of feat_v] (network.py:335-337) with a native backward for feat_v
+    (geobi_v2f_transfer_bwd); xf is an input feature block and gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, feat_v, fv, xf):
+        ctx.save_for_backward(feat_v, fv)
+        ctx.cf = xf.size(1)
+        return ops.v2f_transfer(feat_v.detach(), fv, xf)
+
+    @staticmethod
+    def backward(ctx, go):
+        feat_v, fv = ctx.saved_tensors
+        lib = _lib.load()
+        p, ldv, _ = _rows(feat_v)
+        go = go.contiguous()
+        g = go[:, ctx.cf:]
+        d = torch.zeros((p.size(0), 3), dtype=torch.float32, device=p.device)
+        _lib.check(lib.geobi_v2f_transfer_bwd(_ptr(p), ldv, _ptr(fv.contiguous().long()), _ptr(g), go.stride(0), fv.size(0), _ptr(d), 3,
+                                              _stream()), "v2f_transfer_bwd")
+        _count()
+        return d, None, None

@@ -291,6 +291,50 @@ __global__ void __launch_bounds__(256) v2f_transfer_kernel(const float* __restri
   o[cf + 3] = n[0]; o[cf + 4] = n[1]; o[cf + 5] = n[2];
 }
 
+// Backward of the transfer (training step): g = d loss / d out[:, cf:cf+6] = (gradient of the corner mean | gradient of the unit normal).
+//   centroid: each corner gets g_c / 3;  normal n = u / max(|u|, eps), u = (p1 - p0) x (p2 - p0):
+//   g_u = (g_n - n <n, g_n>) / |u|  (g_n / eps below the clamp),  g_e1 = e2 x g_u,  g_e2 = g_u x e1,  p1 += g_e1, p2 += g_e2, p0 -= g_e1 + g_e2.
+// Vertices collect their faces' contributions with atomics (6 faces per vertex on average); d_feat_v is zero-initialised by the caller.
+__global__ void __launch_bounds__(256) v2f_transfer_bwd_kernel(const float* __restrict__ p, int64_t ldp, const int64_t* __restrict__ fv,
+                                                               const float* __restrict__ g, int64_t ldg, int64_t F, float* __restrict__ dp,
+                                                               int64_t lddp) {
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int64_t a = fv[f * 3], b = fv[f * 3 + 1], c = fv[f * 3 + 2];
+  const float ax = p[a * ldp], ay = p[a * ldp + 1], az = p[a * ldp + 2];
+  const float e1x = p[b * ldp] - ax, e1y = p[b * ldp + 1] - ay, e1z = p[b * ldp + 2] - az;
+  const float e2x = p[c * ldp] - ax, e2y = p[c * ldp + 1] - ay, e2z = p[c * ldp + 2] - az;
+  const float ux = e1y * e2z - e1z * e2y, uy = e1z * e2x - e1x * e2z, uz = e1x * e2y - e1y * e2x;
+  const float len = sqrtf(ux * ux + uy * uy + uz * uz);
+  const float* gr = g + f * ldg;
+  const float gcx = gr[0] / 3.0f, gcy = gr[1] / 3.0f, gcz = gr[2] / 3.0f;
+  const float gnx = gr[3], gny = gr[4], gnz = gr[5];
+  float gux, guy, guz;
+  if (len > 1e-12f) {
+    const float nx = ux / len, ny = uy / len, nz = uz / len;
+    const float dot = nx * gnx + ny * gny + nz * gnz;
+    gux = (gnx - nx * dot) / len;
+    guy = (gny - ny * dot) / len;
+    guz = (gnz - nz * dot) / len;
+  } else {                                  // below normalize's clamp the output is u / eps
+    gux = gnx / 1e-12f;
+    guy = gny / 1e-12f;
+    guz = gnz / 1e-12f;
+  }
+  // u = e1 x e2
+  const float g1x = e2y * guz - e2z * guy, g1y = e2z * gux - e2x * guz, g1z = e2x * guy - e2y * gux;   // e2 x g_u
+  const float g2x = guy * e1z - guz * e1y, g2y = guz * e1x - gux * e1z, g2z = gux * e1y - guy * e1x;   // g_u x e1
+  atomicAdd(dp + b * lddp, gcx + g1x);
+  atomicAdd(dp + b * lddp + 1, gcy + g1y);
+  atomicAdd(dp + b * lddp + 2, gcz + g1z);
+  atomicAdd(dp + c * lddp, gcx + g2x);
+  atomicAdd(dp + c * lddp + 1, gcy + g2y);
+  atomicAdd(dp + c * lddp + 2, gcz + g2z);
+  atomicAdd(dp + a * lddp, gcx - g1x - g2x);
+  atomicAdd(dp + a * lddp + 1, gcy - g1y - g2y);
+  atomicAdd(dp + a * lddp + 2, gcz - g1z - g2z);
+}
+
 // ------------------------------------------------------------------------------ vertex update
 __global__ void __launch_bounds__(256) face_centroid_kernel(const float* __restrict__ p, const int64_t* __restrict__ fv, int64_t F,
                                                             float* __restrict__ cent) {
@@ -438,6 +482,16 @@ extern "C" int geobi_v2f_transfer(const float* feat_v, int64_t ldv, const int64_
   if (n_faces == 0) return GEOBI_OK;
   v2f_transfer_kernel<<<(unsigned)cdiv(n_faces, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat_v, ldv, fv, xf, ldxf, cf, n_faces, out, ldo);
   GEOBI_LAUNCH_OK("v2f_transfer");
+  return GEOBI_OK;
+}
+
+extern "C" int geobi_v2f_transfer_bwd(const float* feat_v, int64_t ldv, const int64_t* fv, const float* g_out, int64_t ldg, int64_t n_faces,
+                                      float* d_feat_v, int64_t lddv, void* stream) {
+  GEOBI_REQUIRE(feat_v && fv && g_out && d_feat_v && n_faces >= 0 && ldv >= 3 && ldg >= 6 && lddv >= 3, "v2f_transfer_bwd: bad arguments");
+  if (n_faces == 0) return GEOBI_OK;
+  v2f_transfer_bwd_kernel<<<(unsigned)cdiv(n_faces, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat_v, ldv, fv, g_out, ldg, n_faces,
+                                                                                                        d_feat_v, lddv);
+  GEOBI_LAUNCH_OK("v2f_transfer_bwd");
   return GEOBI_OK;
 }
 

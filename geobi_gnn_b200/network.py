@@ -142,17 +142,14 @@ class DualGNN(nn.Module):
 
 
     def _forward_train_tail(self, data_v, data_f, g_v, xyz):
-        """Training step: heads are plain library GEMMs, the transfer is elementwise (autograd handles both)."""
+        """Training step: heads are plain library GEMMs (autograd), the transfer runs the inference kernel with a native backward."""
         import torch.nn.functional as F
         feat_v = self.fc_v2(F.leaky_relu(self.fc_v1(g_v), 0.2))
         if self.force_depth:
             feat_v = feat_v * data_v.depth_direction
         feat_v = feat_v + xyz
-        fv = data_f.fv_indices
-        tri = feat_v[fv]
-        cent = tri.mean(1)
-        nrm = F.normalize(torch.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], dim=1), dim=1)
-        data_f.x = torch.cat((data_f.x, cent, nrm), 1)
+        from .autograd import V2FTransferFn      # same forward kernel as inference, native backward (geobi_v2f_transfer_bwd)
+        data_f.x = V2FTransferFn.apply(feat_v, data_f.fv_indices, data_f.x)
         g_f = self.gnn_f(data_f)
         feat_f = self.fc_f2(F.leaky_relu(self.fc_f1(g_f), 0.2))
         return feat_v, F.normalize(feat_f, dim=1), None

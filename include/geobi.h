@@ -311,6 +311,12 @@ GEOBI_API int geobi_face_normal(const float* points, int64_t ldp, const int64_t*
 GEOBI_API int geobi_v2f_transfer(const float* feat_v, int64_t ldv, const int64_t* fv, const float* xf, int64_t ldxf,
                        int cf, int64_t n_faces, float* out, int64_t ldo, void* stream);
 
+/* Backward of geobi_v2f_transfer for the training step (the autograd of network.py:335-337: corner mean + normalize(cross)):
+ * g_out [F, >= 6] = gradients of (corner mean | face normal), i.e. columns cf .. cf+5 of the transfer's output (pass the pointer to
+ * column cf); d_feat_v [V, >= 3] is ACCUMULATED into (zero it first).  Covers SURVEY.md 8(b)'s geobi_face_normal_bwd. */
+GEOBI_API int geobi_v2f_transfer_bwd(const float* feat_v, int64_t ldv, const int64_t* fv, const float* g_out, int64_t ldg,
+                           int64_t n_faces, float* d_feat_v, int64_t lddv, void* stream);
+
 /* data_util.update_position2 (data_util.py:529-556; test_dual.py:72 runs 60 iterations):
  * n_iter Jacobi sweeps p_v += mean_{f in vf[v]} n_f (n_f . (c_f - p_v)), optional projection on
  * depth_direction.  vf [V,K] int64 padded -1.  out may not alias points. */

@@ -64,3 +64,29 @@ def test_dualgnn_training_step_gradients_match_oracle():
         torch.optim.Adam(net.parameters(), lr=1e-3).step()
     for (name, p), (_, q) in zip(mine.named_parameters(), ref.named_parameters()):
         assert util.rel_err(p.data, q.data) < 1e-3, name
+
+
+def test_v2f_transfer_backward_matches_eager_autograd():
+    """geobi_v2f_transfer_bwd (corner mean + normalize(cross)) against autograd of the reference's tensor expression (network.py:335-337),
+    on a noisy sphere; a thin face (one corner moved to 5 % of an edge) is compared at a looser bar - its normal is ill-conditioned
+    in fp32 whoever computes it."""
+    import torch.nn.functional as F
+    from geobi_gnn_b200.autograd import V2FTransferFn
+    mesh = util.noisy_icosphere(6, seed=2)[0]
+    pts = torch.from_numpy(mesh.points.astype("float32")).to(DEV)
+    fv = torch.from_numpy(mesh.fv).to(DEV)
+    pts[fv[5, 1]] = pts[fv[5, 0]] + 0.05 * (pts[fv[5, 2]] - pts[fv[5, 0]]) + 0.02 * pts[fv[5, 0]]      # a thin face
+    xf = torch.randn(fv.size(0), 6, device=DEV)
+    gout = torch.randn(fv.size(0), 12, device=DEV)
+    a = pts.clone().requires_grad_(True)
+    tri = a[fv]
+    want_out = torch.cat((xf, tri.mean(1), F.normalize(torch.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], dim=1), dim=1)), 1)
+    want_out.backward(gout)
+    b = pts.clone().requires_grad_(True)
+    got_out = V2FTransferFn.apply(b, fv, xf)
+    got_out.backward(gout)
+    assert util.rel_err(got_out.detach(), want_out.detach()) < 1e-5
+    assert util.rel_err(b.grad, a.grad) < 1e-4
+    keep = torch.ones(pts.size(0), dtype=torch.bool, device=DEV)
+    keep[fv[5]] = False                                        # vertices that do not touch the thin face: fp32 bar
+    assert util.rel_err(b.grad[keep], a.grad[keep]) < 1e-5
