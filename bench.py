@@ -507,7 +507,8 @@ def train_steps(dev, rank, world, barrier, max_over_ranks, precision, patches_pe
            "scaling": "weak", "n_gpus": world, "value": round(faces / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
            "allreduce_ms": round(ms_ar, 4), "allreduce": f"one flat fp32 bucket of {n_params} gradients ({4 * n_params / 1e6:.2f} MB), NCCL" if world > 1 else None,
            "precision": precision, "loss": float(loss), "error_n_deg": float(en),
-           "backward": "soft-assignment / gather part and segment max in libgeobi kernels; dense parts (dZ, dW, dX, dU, heads) on library GEMMs via autograd"}
+           "backward": "soft-assignment / gather part (feast_bwd_edges_vec_kernel), segment max and the vertex-to-facet transfer in libgeobi kernels; "
+                       "dense parts (dZ, dW, dX, dU, heads) on library GEMMs via autograd"}
     del net, opt, dv, df, patches
     torch.cuda.empty_cache()
     return out
