@@ -81,7 +81,9 @@ def release_workspaces():
 # and fall back to cudaMalloc / cudaFree (device-wide syncs: 10-300 ms spikes).  Inside `size_ref(ref)` every variable-size
 # buffer is instead carved from a capacity rounded up to ref/16 steps (never above ref), so the request sizes are the same
 # on every forward and the allocator always hits its cache.
-_REF = None
+import threading
+
+_TLS = threading.local()     # per host thread: the forward and a front end running on a helper thread (HostBatchRunner) must not share it
 
 
 class size_ref:
@@ -89,13 +91,12 @@ class size_ref:
         self.ref = int(ref)
 
     def __enter__(self):
-        global _REF
-        self.prev, _REF = _REF, self.ref
+        self.prev = getattr(_TLS, "ref", None)
+        _TLS.ref = self.ref
         return self
 
     def __exit__(self, *a):
-        global _REF
-        _REF = self.prev
+        _TLS.ref = self.prev
 
 
 def _cap(n: int, ref) -> int:
@@ -107,7 +108,7 @@ def _cap(n: int, ref) -> int:
 
 def valloc(n: int, tail, dtype, device, ref=None) -> torch.Tensor:
     """Uninitialised [n, *tail] tensor (contiguous) backed by a capacity-bucketed allocation (see above)."""
-    ref = _REF if ref is None else ref
+    ref = getattr(_TLS, "ref", None) if ref is None else ref
     m = 1
     for t in tail:
         m *= t

@@ -216,7 +216,8 @@ def test_forward_rejects_a_false_coalesced_undirected_claim():
 
 
 @pytest.mark.gpu
-def test_host_batch_runner_upload_mesh_equals_direct_forward():
+@pytest.mark.parametrize("helper_thread", [False, True])
+def test_host_batch_runner_upload_mesh_equals_direct_forward(helper_thread):
     """upload_mesh (raw points + faces cross PCIe; topology, graphs, weights and features built on the copy stream) gives the bits of
     a forward on inputs built by the same device front end on the main stream, and the oracle's features within the fp32 bar."""
     from geobi_gnn_b200 import batching, dataset, inference, network, topology
@@ -237,11 +238,12 @@ def test_host_batch_runner_upload_mesh_equals_direct_forward():
             want.append((vp.cpu(), nrm.cpu()))
     host = [(torch.from_numpy(m.points.astype("float32")).pin_memory(), torch.from_numpy(m.fv.astype("int32")).pin_memory()) for m in meshes]
     runner = inference.HostBatchRunner(net, DEV, coalesced_undirected=True)
-    nxt = runner.upload_mesh(*host[0])
+    up = runner.upload_mesh_async if helper_thread else runner.upload_mesh      # the front end queued by a helper thread: same bits
+    nxt = up(*host[0])
     for i in range(3):
         cur = nxt
         if i + 1 < 3:
-            nxt = runner.upload_mesh(*host[i + 1])
+            nxt = up(*host[i + 1])
         v, n = runner.run(cur)
         runner.wait()
         assert torch.equal(v, want[i][0]) and torch.equal(n, want[i][1])
