@@ -262,7 +262,8 @@ def run_ours(args, rank, world, local_rank):
                 return runner.run(cur)                                  # this step's compute + D2H read of (vertices, normals)
             return step
 
-        step_graphs = make_step(lambda: runner.upload(wl.host_v, wl.host_f))                  # prebuilt graphs cross PCIe
+        up_graphs = runner.upload if os.environ.get("GEOBI_BENCH_SYNC_UPLOAD") else runner.upload_async
+        step_graphs = make_step(lambda: up_graphs(wl.host_v, wl.host_f))                      # prebuilt graphs cross PCIe
         # the front end of the NEXT mesh is queued by a helper thread while this thread queues the current forward (upload_mesh_async)
         up_mesh = runner.upload_mesh if os.environ.get("GEOBI_BENCH_SYNC_UPLOAD") else runner.upload_mesh_async
         step_mesh = None if wl.h2d_mesh_bytes is None else make_step(lambda: up_mesh(wl.host_points, wl.host_faces))
@@ -313,7 +314,7 @@ def run_ours(args, rank, world, local_rank):
                       "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_graphs / steps, 4), "cuda_mallocs_in_timed_region": int(allocs_graphs),
                       "path": "inference.HostBatchRunner.upload: PREBUILT graphs as a data loader reading the reference's cached .pt files hands "
                               "them over (x, edge_index, edge_weight, fv_indices; index tensors int32, widened on the device) -> H2D + "
-                              "input-level CSR build on a copy stream (under the previous step's forward) -> DualGNN forward -> D2H of vertices "
+                              "input-level CSR build on a copy stream, queued by a helper thread (upload_async) -> DualGNN forward -> D2H of vertices "
                               "and normals on a read-back stream; copy and read-back streams joined before the closing event"}
         if ms_mesh is None:
             e2e = e2e_graphs

@@ -343,11 +343,18 @@ class HostBatchRunner:
         """upload_mesh on a helper thread: returns a future that run() accepts.  The front end's host side (70 launches and its three
         entry-count read-backs, which block on the copy stream) then runs while the main thread queues the current forward, so its
         kernels fill the forward's gaps instead of running after it."""
+        return self._submit(self.upload_mesh, points_host, faces_host, data_type)
+
+    def upload_async(self, *args, **kwargs):
+        """upload() (prebuilt graphs) on the same helper thread."""
+        return self._submit(self.upload, *args, **kwargs)
+
+    def _submit(self, fn, *args, **kwargs):
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
             idx = self.dev.index if self.dev.index is not None else torch.cuda.current_device()
             self._pool = ThreadPoolExecutor(max_workers=1, initializer=lambda: torch.cuda.set_device(idx))
-        return self._pool.submit(self.upload_mesh, points_host, faces_host, data_type)
+        return self._pool.submit(fn, *args, **kwargs)
 
     def run(self, handle):
         if hasattr(handle, "result"):          # a future from upload_mesh_async
