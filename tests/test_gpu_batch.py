@@ -184,8 +184,15 @@ def test_configs2_full_size_modes_agree_and_runner_reproduces_the_forward():
             runner = inference.HostBatchRunner(net, torch.device(DEV), coalesced_undirected=True)
             hp = pts.cpu().pin_memory()
             hf = torch.from_numpy(f.astype(np.int32)).pin_memory()
-            rv, rn = runner.run(runner.upload_mesh(hp, hf))
+            # pipelined as the bench does: the next upload is queued by the helper thread while this thread queues a forward
+            h1 = runner.upload_mesh_async(hp, hf)
+            h2 = runner.upload_mesh_async(hp, hf)
+            rv, rn = runner.run(h1)
             runner.wait()
+            rv, rn = rv.clone(), rn.clone()
+            rv2, rn2 = runner.run(h2)
+            runner.wait()
+            assert torch.equal(rv2, rv) and torch.equal(rn2, rn)
         finally:
             config.set_precision("fp32")
             for pl in pls:
