@@ -171,10 +171,14 @@ class Workload:
         if name == "patches":
             patches = [dataset.build_dual_data(mn, mo, device=dev) for mn, mo in patch_meshes(N_PATCHES, first_seed=rank * N_PATCHES)]
             self.dv, self.df, _ = batching.collate_dual(patches)
+            self.dv_res, self.df_res = self.dv, self.df        # the union batch in the reference layout (lists; sort-free CSRs built per step)
             self.describe = ("configs[1]: 64 noisy icosphere patches x 8000 faces per GPU, disjoint-union batch, DualGNN fwd, random init")
         else:
             mesh = noisy_device_mesh(MESH_FREQ, rank, dev)
-            self.dv, self.df = dataset.build_dual_on_device(mesh, None)
+            self.dv, self.df = dataset.build_dual_on_device(mesh, None)                       # reference layout (int64 lists): what the prebuilt path ships
+            # resident inputs of `value`: the graph pair as the device front end hands it to the network (features + loop-free CSRs with
+            # their weights, Data.csr) - the same inputs the end-to-end path's forward gets
+            self.dv_res, self.df_res = dataset.build_dual_on_device(mesh, None, csr_native=True)
             # what the end-to-end path uploads for a single mesh: the raw mesh (the device front end builds the graphs every step)
             self.host_points = mesh.points.cpu().pin_memory()
             self.host_faces = mesh.fv.to(torch.int32).cpu().pin_memory()
@@ -244,91 +248,172 @@ def run_ours(args, rank, world, local_rank):
         ms, wall = max_over_ranks(ms, wall)
         return ms, wall
 
+    # ---------------------------------------------------------------- concurrent lanes
+    # W host threads, each with its own CUDA stream, module replica (same weights; PoolingLayer keeps per-forward state on the module)
+    # and end-to-end runner, take steps from one counter: the latency-bound stretches of a forward (matcher on the coarse levels, scans,
+    # the ten count read-backs) overlap with another mesh's kernels.  profiles/two_stream_probe.py: 12.2 -> 10.8 ms per 1 M-face mesh
+    # with two lanes, 10.7 with three.  W = 1 (--streams 1) is the single-stream figure, reported beside it.
+    import copy
+    import itertools
+    import threading
+    W = max(1, int(args.streams))
+    nets = [net] + [copy.deepcopy(net).eval() for _ in range(W - 1)]
+    lane_streams = [torch.cuda.Stream(dev) for _ in range(W)]
+
+    def run_lanes(fns, steps):
+        """`steps` calls in total, dealt to len(fns) threads (thread i calls fns[i] on lane stream i)."""
+        ticket = itertools.count()
+        errs = []
+
+        def work(i):
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(lane_streams[i]):
+                    while next(ticket) < steps:
+                        fns[i]()
+            except BaseException as e:      # surfaced by the caller: a failed lane must not look like a fast one
+                errs.append(e)
+
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(len(fns))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def timed_lanes(fns, steps, join=(), before_close=None):
+        """timed() for concurrent lanes: events on the launch stream around all lanes' work (the launch stream waits for every lane
+        stream and for `join` before the closing event)."""
+        import gc
+        gc.collect()
+        if not os.environ.get("BENCH_KEEP_GC"):
+            gc.disable()
+        try:
+            barrier()
+            main = torch.cuda.current_stream(dev)
+            for s_ in lane_streams:
+                s_.wait_stream(main)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev0.record()
+            run_lanes(fns, steps)
+            if before_close is not None:
+                before_close()
+            for s_ in list(lane_streams) + list(join):
+                main.wait_stream(s_)
+            ev1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            ms = ev0.elapsed_time(ev1)
+        finally:
+            gc.enable()
+        ms, wall = max_over_ranks(ms, wall)
+        return ms, wall
+
     def measure(wl, steps, warmup, with_clocks):
         """Device-timed value (inputs resident) and end-to-end value (host batches through inference.HostBatchRunner) of a workload."""
-        def step_resident():
-            with torch.no_grad():
-                return net([batching.fresh_view(wl.dv), batching.fresh_view(wl.df)])
-
-        runner = inference.HostBatchRunner(net, dev, coalesced_undirected=True)
-        pipe = {"next": None}
-
-        def make_step(upload):
+        def resident(i):
             def step():
-                if pipe["next"] is None:
-                    pipe["next"] = upload()
-                cur = pipe["next"]
-                pipe["next"] = upload()                                 # this step's H2D copy (the batch the next step consumes)
-                return runner.run(cur)                                  # this step's compute + D2H read of (vertices, normals)
+                with torch.no_grad():
+                    return nets[i]([batching.fresh_view(wl.dv_res), batching.fresh_view(wl.df_res)])
             return step
 
-        up_graphs = runner.upload if os.environ.get("GEOBI_BENCH_SYNC_UPLOAD") else runner.upload_async
-        step_graphs = make_step(lambda: up_graphs(wl.host_v, wl.host_f))                      # prebuilt graphs cross PCIe
-        # the front end of the NEXT mesh is queued by a helper thread while this thread queues the current forward (upload_mesh_async)
-        up_mesh = runner.upload_mesh if os.environ.get("GEOBI_BENCH_SYNC_UPLOAD") else runner.upload_mesh_async
-        step_mesh = None if wl.h2d_mesh_bytes is None else make_step(lambda: up_mesh(wl.host_points, wl.host_faces))
+        res_fns = [resident(i) for i in range(W)]
+        runners = [inference.HostBatchRunner(nets[i], dev, coalesced_undirected=True) for i in range(W)]
+        pipes = [{"next": None} for _ in range(W)]
+        sync_upload = bool(os.environ.get("GEOBI_BENCH_SYNC_UPLOAD"))
+
+        def make_step(i, kind):
+            r = runners[i]
+            if kind == "graphs":      # prebuilt graphs cross PCIe
+                up = (lambda: r.upload(wl.host_v, wl.host_f)) if sync_upload else (lambda: r.upload_async(wl.host_v, wl.host_f))
+            else:                     # the raw mesh; its front end is queued by the runner's helper thread while this thread queues a forward
+                up = (lambda: r.upload_mesh(wl.host_points, wl.host_faces)) if sync_upload else (lambda: r.upload_mesh_async(wl.host_points, wl.host_faces))
+
+            def step():
+                if pipes[i]["next"] is None:
+                    pipes[i]["next"] = up()
+                cur = pipes[i]["next"]
+                pipes[i]["next"] = up()                                 # this step's H2D copy (the batch the next step of this lane consumes)
+                return r.run(cur)                                       # this step's compute + D2H read of (vertices, normals)
+            return step
 
         # allocator priming: steps run back to back keep more blocks alive than synchronised ones; let the caching allocator
-        # reach its high-water mark (a handful of cudaMallocs) before the W warm-up steps so the timed region sees none
-        for _ in range(PRIME_STEPS):
-            step_resident()
-        torch.cuda.synchronize()
-        for _ in range(warmup):
-            step_resident()
+        # reach its high-water mark (a handful of cudaMallocs per stream) before the warm-up steps so the timed region sees none
         if args.profile_step and with_clocks:      # for `ncu --profile-from-start off`: exactly one step between cudaProfilerStart/Stop
+            for _ in range(PRIME_STEPS + warmup):
+                res_fns[0]()
             torch.cuda.synchronize()
             l0 = ops.launch_count()
             torch.cuda.profiler.start()
-            step_resident()
+            res_fns[0]()
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
             print(f"[profile-step] libgeobi kernels counted by the host side in this step: {ops.launch_count() - l0}", file=sys.stderr)
             return None
+        for s_ in lane_streams:
+            s_.wait_stream(torch.cuda.current_stream(dev))
+        run_lanes(res_fns, (PRIME_STEPS + warmup) * W)
+        torch.cuda.synchronize()
         l0 = ops.launch_count()
         if with_clocks:
             with ClockSampler(local_rank) as clk:
-                ms, wall = timed(step_resident, steps)
+                ms, wall = timed_lanes(res_fns, steps)
             clocks = clk.summary()
         else:
-            ms, wall = timed(step_resident, steps)
+            ms, wall = timed_lanes(res_fns, steps)
             clocks = None
         launches = ops.launch_count() - l0
-        def run_e2e(step):
-            pipe["next"] = None
-            for _ in range(PRIME_STEPS // 2 + warmup):
-                step()
+        ms_single = None
+        if W > 1:                                  # the single-stream figure beside it (lane 0 alone)
+            ms_single, _ = timed_lanes(res_fns[:1], steps)
+
+        def run_e2e(kind):
+            fns = [make_step(i, kind) for i in range(W)]
+            for p_ in pipes:
+                p_["next"] = None
+            run_lanes(fns, (PRIME_STEPS // 2 + warmup) * W)
             a0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
-            def settle():        # the trailing upload (queued by the helper thread) belongs to the timed region like the others
-                nx = pipe["next"]
-                if hasattr(nx, "result"):
-                    pipe["next"] = nx.result()
-            ms_, _ = timed(step, steps, join=(runner.copy_stream, runner.read_stream), before_close=settle)
-            runner.wait()
+
+            def settle():        # the trailing uploads (queued by the helper threads) belong to the timed region like the others
+                for p_ in pipes:
+                    nx = p_["next"]
+                    if hasattr(nx, "result"):
+                        p_["next"] = nx.result()
+            join = [st_ for r in runners for st_ in (r.copy_stream, r.read_stream)]
+            ms_, _ = timed_lanes(fns, steps, join=join, before_close=settle)
+            for r in runners:
+                r.wait()
             return ms_, torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - a0
 
-        ms_graphs, allocs_graphs = run_e2e(step_graphs)
-        ms_mesh, allocs_mesh = run_e2e(step_mesh) if step_mesh is not None else (None, None)
-        d2h = sum(t.numel() * t.element_size() for t in runner.out_host.values())
+        ms_graphs, allocs_graphs = run_e2e("graphs")
+        ms_mesh, allocs_mesh = run_e2e("mesh") if wl.h2d_mesh_bytes is not None else (None, None)
+        d2h = sum(t.numel() * t.element_size() for t in runners[0].out_host.values())
         total_faces = wl.faces * world
+        lanes_txt = "%d concurrent lane(s): host thread + CUDA stream + module replica + runner each; " % W
         e2e_graphs = {"value": round(total_faces * steps / (ms_graphs / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes,
                       "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_graphs / steps, 4), "cuda_mallocs_in_timed_region": int(allocs_graphs),
-                      "path": "inference.HostBatchRunner.upload: PREBUILT graphs as a data loader reading the reference's cached .pt files hands "
-                              "them over (x, edge_index, edge_weight, fv_indices; index tensors int32, widened on the device) -> H2D + "
+                      "path": lanes_txt + "inference.HostBatchRunner.upload: PREBUILT graphs as a data loader reading the reference's cached .pt "
+                              "files hands them over (x, edge_index, edge_weight, fv_indices; index tensors int32, widened on the device) -> H2D + "
                               "input-level CSR build on a copy stream, queued by a helper thread (upload_async) -> DualGNN forward -> D2H of vertices "
-                              "and normals on a read-back stream; copy and read-back streams joined before the closing event"}
+                              "and normals on a read-back stream; every lane, copy and read-back stream joined before the closing event"}
         if ms_mesh is None:
             e2e = e2e_graphs
         else:
             e2e = {"value": round(total_faces * steps / (ms_mesh / 1e3), 1), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_mesh_bytes,
                    "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_mesh / steps, 4), "cuda_mallocs_in_timed_region": int(allocs_mesh),
-                   "path": "inference.HostBatchRunner.upload_mesh: the RAW mesh (points fp32 + faces int32, pinned) -> H2D -> device front end on "
-                           "the copy stream (topology, both graphs as loop-free CSRs, bilateral weights, normalised features: "
+                   "path": lanes_txt + "inference.HostBatchRunner.upload_mesh: the RAW mesh (points fp32 + faces int32, pinned) -> H2D -> device "
+                           "front end on the copy stream (topology, both graphs as loop-free CSRs, bilateral weights, normalised features: "
                            "topology.DeviceTriMesh + dataset.build_dual_on_device(csr_native=True), 0.9 ms of GPU time; the reference's int64 "
-                           "edge lists stay lazy), queued by a helper thread (upload_mesh_async) while this thread queues the current step's "
-                           "forward -> DualGNN forward -> "
-                           "D2H of vertices and normals on a read-back stream; copy and read-back streams joined before the closing event",
+                           "edge lists stay lazy), queued by a helper thread (upload_mesh_async) while the lane's thread queues its current "
+                           "forward -> DualGNN forward -> D2H of vertices and normals on a read-back stream; every lane, copy and read-back "
+                           "stream joined before the closing event",
                    "prebuilt_graphs": e2e_graphs}
-        return {"value": total_faces * steps / (ms / 1e3), "ms_per_step": ms / steps, "wall_s": wall, "launches": launches, "clocks": clocks, "e2e": e2e}
+        out = {"value": total_faces * steps / (ms / 1e3), "ms_per_step": ms / steps, "wall_s": wall, "launches": launches, "clocks": clocks, "e2e": e2e}
+        if ms_single is not None:
+            out["single_stream"] = {"value": round(total_faces * steps / (ms_single / 1e3), 1), "ms_per_step": round(ms_single / steps, 4)}
+        return out
 
     # ---------------------------------------------------------------- headline workload
     wl = Workload(args.workload, rank, dev)
@@ -396,7 +481,8 @@ def run_ours(args, rank, world, local_rank):
         r2 = measure(wl2, min(args.steps, 10), 3, with_clocks=False)
         extra["configs1_patches64" if other == "patches" else "configs2_mesh1m"] = {
             "workload": wl2.describe, "value": round(r2["value"], 1), "unit": UNIT, "ms_per_step": round(r2["ms_per_step"], 4),
-            "steps": min(args.steps, 10), "scaling": "weak", "e2e": r2["e2e"], "gpu_launches": r2["launches"]}
+            "steps": min(args.steps, 10), "scaling": "weak", "e2e": r2["e2e"], "gpu_launches": r2["launches"],
+            "concurrent_forwards": max(1, int(args.streams)), "single_stream": r2.get("single_stream")}
         del wl2
         torch.cuda.empty_cache()
         extra["configs3_mesh10m"] = strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks)
@@ -413,9 +499,19 @@ def run_ours(args, rank, world, local_rank):
                 "data": "synthetic",
                 "config": {"workload": DESCRIBE[args.workload], "faces_per_gpu": FACES[args.workload], "precision": args.precision,
                            "l2": "per-step working set (inputs 390 MB + >4 GB intermediates) exceeds the 126 MB L2",
-                           "timing": "CUDA events on the launch stream, max over ranks", "wall_s": round(res["wall_s"], 4),
+                           "concurrent_forwards": max(1, int(args.streams)),
+                           "concurrency": "steps are dealt to %d host thread(s), each with its own CUDA stream and module replica (same weights): one "
+                                          "mesh's latency-bound stretches (coarse-level matcher, scans, count read-backs) overlap with another's "
+                                          "kernels; ms_per_step = timed region / steps; `single_stream` = lane 0 alone" % max(1, int(args.streams)),
+                           "resident_inputs": "mesh1m: the graph pair as the device front end produces it (features, loop-free CSRs with their "
+                                              "bilateral weights: Data.csr; the reference's int64 edge lists stay lazy); patches: the union batch in "
+                                              "the reference layout (lists; sort-free CSRs rebuilt every step)",
+                           "timing": "CUDA events on the launch stream around all lanes (it waits for every lane stream before the closing event), "
+                                     "max over ranks", "wall_s": round(res["wall_s"], 4),
                            "priming": f"{PRIME_STEPS} untimed forwards before the {args.warmup} warm-up steps (caching-allocator high-water mark)"},
                 "e2e": res["e2e"], "gpu_launches": res["launches"], "clocks": res["clocks"], "roofline": roof, "cpu_baseline": cpu}
+        if "single_stream" in res:
+            line["single_stream"] = res["single_stream"]
         line.update(extra)
         print_json(line)
     if world > 1:
@@ -619,6 +715,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("BENCH_STREAMS", "2")),
+                    help="concurrent forwards per GPU (host thread + CUDA stream + module replica each); 1 = single stream")
     ap.add_argument("--precision", default=os.environ.get("GEOBI_PRECISION", "bf16x3"), choices=["fp32", "bf16", "bf16x3"])
     ap.add_argument("--workload", default=os.environ.get("BENCH_WORKLOAD", "mesh1m"), choices=["mesh1m", "patches"],
                     help="headline workload: mesh1m = BASELINE configs[2] (default), patches = configs[1]")

@@ -56,6 +56,8 @@ def fresh_view(data: Data) -> Data:
     """New Data over the same tensors with graph tags dropped: what a caller holding only the
     reference's input layout (x, int64 edge_index, edge_weight, fv_indices) would pass (the `coalesced_undirected`
     flag, a fact about how the dataset built the list, travels with it)."""
+    if "csr" in data:                 # CSR-native inputs (device front end): the graph IS the attached CSR, the lists are lazy items
+        return data.shallow_copy()
     out = Data()
     for k in data.keys:
         v = getattr(data, k)

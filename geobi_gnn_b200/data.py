@@ -74,6 +74,12 @@ class Data:
     def keys(self):
         return list(self._items)
 
+    def shallow_copy(self):
+        """New Data over the same items; lazy items stay lazy (and shared: the first reader of either copy evaluates the thunk)."""
+        out = Data()
+        out._items.update(self._items)
+        return out
+
     def tensors(self):
         """(key, tensor) of the tensor-valued items that exist NOW: lazy items stay unevaluated."""
         return [(k, v) for k, v in self._items.items() if torch.is_tensor(v)]

@@ -19,16 +19,21 @@ FEAST_REUSE_WS = 0x100
 COO_BY_COL, COO_DROP_SELF, COO_SORT_NBR, COO_DEDUP, COO_W_MEAN, COO_SYMMETRIZE = 1, 2, 4, 8, 16, 32
 OP_MEAN, OP_MAX, OP_SUM = 0, 1, 2
 
-_launches = 0  # kernels-launching ABI calls made (bench.py reports it)
+import itertools
+
+_launch_ticks = itertools.count()   # kernel launches made through the ABI (bench.py reports it); next() is atomic under the GIL, so
+_launch_base = [0]                  # forwards running on several host threads do not lose counts
 
 
 def launch_count() -> int:
-    return _launches
+    # peek without consuming: itertools.count has no read accessor, so take a tick and compensate
+    _launch_base[0] -= 1
+    return next(_launch_ticks) + _launch_base[0] + 1
 
 
 def _count(n=1):
-    global _launches
-    _launches += n
+    for _ in range(n):
+        next(_launch_ticks)
 
 
 def _need_cuda(*tensors):
@@ -183,7 +188,10 @@ class CSRGraph:
         """Queue the copy of the entry count (and, for csr_from_sorted_coo, its verdict) into pinned memory; `.nnz` then
         costs no stream drain once any later synchronisation of this stream has returned."""
         if self._nnz is None and self._pin is None and self.n > 0:
-            pin = _pin_pool.pop() if _pin_pool else torch.empty(1, dtype=torch.int32).pin_memory()
+            try:                                   # several host threads may run forwards at once (bench.py, serving)
+                pin = _pin_pool.pop()
+            except IndexError:
+                pin = torch.empty(1, dtype=torch.int32).pin_memory()
             pin.copy_(self.rowptr[self.n:self.n + 1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.rowptr.device))

@@ -271,3 +271,52 @@ def test_csr_native_inputs_equal_list_inputs():
     for c, l in ((cv, lv), (cf, lf)):
         assert isinstance(c._items["edge_index"], _Lazy) and isinstance(c._items["edge_weight"], _Lazy)     # the network never read them
         assert torch.equal(c.edge_index, l.edge_index) and torch.equal(c.edge_weight, l.edge_weight)
+
+
+@pytest.mark.gpu
+def test_concurrent_forwards_on_replicas_equal_sequential_ones():
+    """bench.py runs several forwards at once (one host thread + CUDA stream + module replica each): with fixed visiting orders every
+    concurrent forward returns the bits of the same forward run alone - the library's per-stream workspaces, thread-local size hints
+    and pinned landing pads do not leak between threads."""
+    import copy
+    import threading
+    from geobi_gnn_b200 import batching, dataset, network, topology
+    torch.manual_seed(21)
+    net = network.DualGNN().to(DEV).eval()
+    meshes = [util.noisy_icosphere(n, seed=30 + n)[0] for n in (10, 12, 14)]
+    inputs = []
+    for m in meshes:
+        dm = topology.DeviceTriMesh(m.points, m.fv, DEV)
+        inputs.append(dataset.build_dual_on_device(dm, None, csr_native=True))
+    nets = [net] + [copy.deepcopy(net).eval() for _ in range(2)]
+    for n_ in nets:
+        for pl in util.poolings(n_):
+            pl.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
+    with torch.no_grad():
+        want = [[t.clone() for t in net([batching.fresh_view(dv), batching.fresh_view(df)])[:2]] for dv, df in inputs]
+    torch.cuda.synchronize()
+    got = [None] * 3
+    errs = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(torch.device(DEV).index or 0)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.default_stream())
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(4):              # several rounds each, to interleave
+                    dv, df = inputs[i]
+                    out = nets[i]([batching.fresh_view(dv), batching.fresh_view(df)])
+                got[i] = [out[0].clone(), out[1].clone()]
+            s.synchronize()
+        except BaseException as e:
+            errs.append(e)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    assert not errs, errs
+    for i in range(3):
+        assert torch.equal(got[i][0], want[i][0]) and torch.equal(got[i][1], want[i][1]), i
