@@ -1,8 +1,10 @@
 """Autograd wrappers for the training step (train_dual.py:199-218).
 
-Forward passes are the same libgeobi kernels as inference.  Backward passes: the edge part of the FeaSt backward and the
-max-pool routing are libgeobi kernels (`geobi_feast_bwd_edges`, `geobi_segment_max_bwd`); the dense parts
-(dZ = g.W_flat, dW = g^T.Z, dX += dP.U, dU = dP^T.X) are plain library GEMMs (torch.matmul, fp32).
+Forward passes are the same libgeobi kernels as inference.  Backward passes: a FeaStConv layer's whole backward is ONE library
+call (`geobi_feast_bwd`: dZ = g.W_flat and dW = g^T.Z on tcgen05 with split bf16 operands, the edge part, dX += dP.U, dU = dP^T.X)
+in the tensor-core precisions; with precision 'fp32' the edge part and the max-pool routing are libgeobi kernels
+(`geobi_feast_bwd_edges`, `geobi_segment_max_bwd`) and the dense parts are plain library GEMMs (torch.matmul, fp32) - the
+cross-check path of tests/test_gpu_train.py.
 """
 from __future__ import annotations
 
@@ -44,18 +46,52 @@ def feast_bwd_edges(x, g, P, c, dZ, need_dx=True):
     return dx, dP, dc
 
 
+def feast_bwd(x, g, W, U, c, out, go, slope, need_dx=True):
+    """geobi_feast_bwd: (dx | None, dW, dU, dc, dbias) of one FeaStConv layer from the gradient `go` of its (activated) output."""
+    lib = _lib.load()
+    x, ldx, c_in = _rows(x)
+    n, c_out = x.size(0), go.size(1)
+    go, ldg, _ = _rows(go)
+    if ldg % 4 or go.data_ptr() % 16:
+        go, ldg = go.contiguous(), c_out
+    o, ldo = None, 0
+    if slope != 1.0:
+        o, ldo, _ = _rows(out)
+        if ldo % 4 or o.data_ptr() % 16:
+            o, ldo = o.contiguous(), c_out
+    dev = x.device
+    dx = torch.empty((n, c_in), dtype=torch.float32, device=dev) if need_dx else None
+    dW = torch.empty((H * c_out, c_in), dtype=torch.float32, device=dev)
+    dU = torch.empty((H, c_in), dtype=torch.float32, device=dev)
+    dc = torch.empty(H, dtype=torch.float32, device=dev)
+    db = torch.empty(c_out, dtype=torch.float32, device=dev)
+    ws = ops._ws(lib.geobi_feast_bwd_ws_bytes(n, c_in, c_out), dev, slot=2)
+    _lib.check(lib.geobi_feast_bwd(_ptr(x), ldx, n, c_in, _ptr(g.rowptr), _ptr(g._nbr), _ptr(W.contiguous()), _ptr(U.contiguous()),
+                                   _ptr(c.contiguous()), c_out, float(slope), _ptr(o), ldo, _ptr(go), ldg, _ptr(dx), c_in, _ptr(dW),
+                                   _ptr(dU), _ptr(dc), _ptr(db), _ptr(ws), ws.numel(), _stream()), "feast_bwd")
+    kpad, chunks = -(-H * c_in // 64) * 64, 0
+    while kpad > 0:                         # dZ is produced in column chunks of 256 / 128 / 64
+        kpad -= 256 if kpad >= 256 else (128 if kpad >= 128 else 64)
+        chunks += 1
+    _count(8 + chunks)                      # prep g, prep W^T, projection, aggregation, dZ chunks, edges, split-K, reduce, dP.U
+    return dx, dW, dU, dc, db
+
+
 class FeaStFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, W, U, c, bias, g, act_slope, precision):
         out = ops.feast_fwd(x.detach(), g, W.detach(), U.detach(), c.detach(), bias.detach(), act_slope=act_slope, precision=precision)
         ctx.save_for_backward(x, W, U, c, out)
-        ctx.g, ctx.slope = g, act_slope
+        ctx.g, ctx.slope, ctx.native = g, act_slope, (precision & 0xff) == ops.PREC_BF16X3
         return out
 
     @staticmethod
     def backward(ctx, go):
         x, W, U, c, out = ctx.saved_tensors
         g, slope = ctx.g, ctx.slope
+        if ctx.native:
+            dx, dW, dU, dc, dbias = feast_bwd(x, g, W, U, c, out, go, slope, ctx.needs_input_grad[0])
+            return dx, dW, dU, dc, dbias, None, None, None
         c_in, c_out = x.size(1), out.size(1)
         gpre = go if slope == 1.0 else go * torch.where(out > 0, 1.0, slope)   # leaky_relu keeps the sign of its input
         gpre = gpre.contiguous()

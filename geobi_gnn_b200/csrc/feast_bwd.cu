@@ -313,15 +313,12 @@ extern "C" int geobi_feast_aggregate(const float* x, int64_t ldx, int64_t N, int
   return feast_project_and_aggregate(x, ldx, N, c_in, rowptr, nbr, nullptr, N, U, c, P, Z, (int64_t)H * c_in, 0, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
-                                     const double* P, const float* c, const float* dZ, float* dx, int64_t lddx, float* dP, float* dc,
-                                     void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  GEOBI_REQUIRE(x && rowptr && P && c && dZ && dP && dc && N >= 0 && c_in >= 1 && c_in <= 128, "feast_bwd_edges: bad arguments");
-  if (N == 0) return GEOBI_OK;
+namespace geobi {
+// dZ has row stride lddz (>= 9*c_in; a multiple of 4 for the vector kernels): geobi_feast_bwd hands over its kpad-strided buffer
+int feast_bwd_edges_launch(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr, const double* P,
+                           const float* c, const float* dZ, int64_t lddz, float* dx, int64_t lddx, float* dP, float* dc, cudaStream_t st) {
   const unsigned blocks = (unsigned)cdiv(N, 8);
-  const int64_t lddz = (int64_t)H * c_in;
-  const bool vec = (c_in == 32 || c_in == 64 || c_in == 128) && ldx % 4 == 0 && lddx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+  const bool vec = (c_in == 32 || c_in == 64 || c_in == 128) && ldx % 4 == 0 && lddx % 4 == 0 && lddz % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(dx) & 15) == 0 && (reinterpret_cast<uintptr_t>(dZ) & 15) == 0;
   if (vec || c_in <= 16) {
     static int sms = 0;
@@ -347,6 +344,15 @@ extern "C" int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t N, int
   else feast_bwd_edges_kernel<4><<<blocks, 256, 0, st>>>(x, ldx, N, c_in, rowptr, nbr, P, c, dZ, lddz, dx, lddx, dP, dc);
   GEOBI_LAUNCH_OK("feast_bwd_edges");
   return GEOBI_OK;
+}
+}  // namespace geobi
+
+extern "C" int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t N, int c_in, const int32_t* rowptr, const int32_t* nbr,
+                                     const double* P, const float* c, const float* dZ, float* dx, int64_t lddx, float* dP, float* dc,
+                                     void* stream) {
+  GEOBI_REQUIRE(x && rowptr && P && c && dZ && dP && dc && N >= 0 && c_in >= 1 && c_in <= 128, "feast_bwd_edges: bad arguments");
+  if (N == 0) return GEOBI_OK;
+  return feast_bwd_edges_launch(x, ldx, N, c_in, rowptr, nbr, P, c, dZ, (int64_t)H * c_in, dx, lddx, dP, dc, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int geobi_segment_max_bwd(const float* x, int64_t ldx, int channels, const int32_t* rowptr, const int32_t* idx, int64_t n_seg,

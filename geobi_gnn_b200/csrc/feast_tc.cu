@@ -296,7 +296,7 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 // bf16 [rows, kpad] row-major, box = 64 columns (128 B, the swizzle span) x box_rows
-static bool make_tmap(CUtensorMap* m, const __nv_bfloat16* g, int64_t rows, int kpad, int box_rows) {
+bool make_tmap(CUtensorMap* m, const __nv_bfloat16* g, int64_t rows, int kpad, int box_rows) {   // also used by feast_bwd_tc.cu
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn || rows <= 0) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)kpad, (cuuint64_t)rows};

@@ -278,6 +278,22 @@ GEOBI_API int geobi_feast_bwd_edges(const float* x, int64_t ldx, int64_t n_nodes
 GEOBI_API int geobi_segment_max_bwd(const float* x, int64_t ldx, int channels, const int32_t* rowptr, const int32_t* idx,
                                     int64_t n_seg, const float* g, int64_t ldg, float* dx, int64_t lddx, void* stream);
 
+/* Whole backward of one FeaStConv layer (replaces autograd through torch_geometric's FeaStConv in the training step,
+ * train_dual.py:199-218; layer built at network.py:258-268, called at :271-299) in ONE call:
+ *   g = g_out * act'(out)  (leaky_relu slope act_slope; out = the layer's forward output, may be NULL when act_slope == 1),
+ *   dbias = sum_n g,  dZ = g . W_flat,  dW = g^T . Z  (Z = the forward's aggregate, recomputed),  the edge part
+ *   (geobi_feast_bwd_edges),  dx += dP . U,  dU = dP^T . x.
+ * The products with a long reduction or a wide output (dZ, dW) run on tcgen05 with operands split hi + lo (three bf16 passes, fp32
+ * accumulation in tensor memory: fp32-grade results); dW's reduction over the nodes is a split-K kernel whose operands are TMA boxes
+ * of the node-major planes used as MN-major UMMA tiles, with a fixed-order second pass (deterministic).
+ * Outputs are OVERWRITTEN: dx [N, c_in] (row stride lddx; NULL when the layer's input needs no gradient), dW [9*c_out, c_in]
+ * (lin.weight's layout), dU [9, c_in], dc [9], dbias [c_out].  Rows of g_out / out must be 16-byte aligned; ws 128-byte aligned. */
+GEOBI_API size_t geobi_feast_bwd_ws_bytes(int64_t n_nodes, int c_in, int c_out);
+GEOBI_API int geobi_feast_bwd(const float* x, int64_t ldx, int64_t n_nodes, int c_in, const int32_t* rowptr, const int32_t* nbr,
+                              const float* W, const float* U, const float* c, int c_out, float act_slope, const float* out,
+                              int64_t ldo, const float* g_out, int64_t ldg, float* dx, int64_t lddx, float* dW, float* dU,
+                              float* dc, float* dbias, void* ws, size_t ws_bytes, void* stream);
+
 /* Per-node linear layer on the tcgen05 tensor cores: out = act(A . W^T + bias), A fp32 [M,K] rounded to bf16
  * (split hi + lo for BF16X3), W fp32 [N,K] (nn.Linear layout), fp32 accumulation in TMEM.  Any K (zero padded to a
  * multiple of 64), N in {32,64,128,256}, out rows 16-byte aligned.  Replaces F.linear / cuBLAS sgemm for the

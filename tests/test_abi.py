@@ -36,6 +36,8 @@ def test_queries_work_without_gpu():
     assert lib.geobi_scan_ws_bytes(1000) > 0
     assert lib.geobi_csr_from_coo_ws_bytes(1000, 100, 0) > 1000 * 16
     assert lib.geobi_feast_fwd_ws_bytes(1000, 64, 32, 0) >= 1000 * 9 * 64 * 4
+    assert lib.geobi_feast_bwd_ws_bytes(1000, 64, 32) >= 1000 * 9 * 64 * 8
+    assert lib.geobi_feast_bwd_ws_bytes(1000, 129, 32) == 0
 
 
 def test_ops_refuse_cpu_tensors():

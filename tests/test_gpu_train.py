@@ -10,12 +10,9 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-@pytest.mark.parametrize("cin,cout,slope", [(12, 32, 0.2), (64, 32, 1.0), (128, 64, 0.2)])
-def test_feast_backward_matches_autograd(cin, cout, slope):
-    from geobi_gnn_b200 import ops
-    from geobi_gnn_b200.autograd import FeaStFn
-    (dv, df), _, _ = util.oracle_inputs(5)
-    torch.manual_seed(cin + cout)
+def _feast_case(cin, cout, slope, level=5, seed=None):
+    (dv, df), _, _ = util.oracle_inputs(level)
+    torch.manual_seed(cin + cout if seed is None else seed)
     conv = pyg.FeaStConv(cin, cout, 9)
     n = df.x.shape[0]
     x = (torch.randn(n, cin) * 2).requires_grad_()
@@ -23,6 +20,15 @@ def test_feast_backward_matches_autograd(cin, cout, slope):
     y = conv(x, df.edge_index)
     y = y if slope == 1.0 else torch.nn.functional.leaky_relu(y, slope)
     y.backward(gout)
+    return conv, df, n, x, gout, y
+
+
+@pytest.mark.parametrize("cin,cout,slope", [(12, 32, 0.2), (64, 32, 1.0), (128, 64, 0.2)])
+def test_feast_backward_matches_autograd(cin, cout, slope):
+    """precision 'fp32': libgeobi edge kernel + library GEMMs (the cross-check path)."""
+    from geobi_gnn_b200 import ops
+    from geobi_gnn_b200.autograd import FeaStFn
+    conv, df, n, x, gout, y = _feast_case(cin, cout, slope)
     g = ops.csr_from_coo(df.edge_index.to(DEV), n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
     xm = x.detach().to(DEV).requires_grad_()
     P = [t.detach().to(DEV).requires_grad_() for t in (conv.lin.weight, conv.u.weight, conv.c, conv.bias)]
@@ -32,6 +38,64 @@ def test_feast_backward_matches_autograd(cin, cout, slope):
     for got, want, name in ((xm.grad, x.grad, "x"), (P[0].grad, conv.lin.weight.grad, "W"), (P[1].grad, conv.u.weight.grad, "U"),
                             (P[2].grad, conv.c.grad, "c"), (P[3].grad, conv.bias.grad, "bias")):
         assert util.rel_err(got, want) < 2e-4, (name, util.rel_err(got, want))
+
+
+# every (C_in, C_out) pair of GNNModule (network.py:258-268), both activations, with and without dx
+NATIVE_CASES = [(6, 32, 0.2, False), (12, 32, 0.2, False), (32, 64, 0.2, True), (64, 128, 0.2, True), (128, 128, 0.2, True),
+                (128, 64, 1.0, True), (128, 64, 0.2, True), (64, 32, 1.0, True), (64, 32, 0.2, True)]
+
+
+@pytest.mark.parametrize("cin,cout,slope,need_dx", NATIVE_CASES)
+def test_native_feast_backward_matches_autograd(cin, cout, slope, need_dx):
+    """geobi_feast_bwd (one call per layer: dZ and the split-K dW on tcgen05, edge kernel, dP.U / dP^T.x) against autograd through
+    the oracle's FeaStConv; bar 1e-4 max-norm relative, measured ~1e-6."""
+    from geobi_gnn_b200 import ops
+    from geobi_gnn_b200.autograd import FeaStFn
+    conv, df, n, x, gout, y = _feast_case(cin, cout, slope)
+    g = ops.csr_from_coo(df.edge_index.to(DEV), n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR)
+    xm = x.detach().to(DEV).requires_grad_(need_dx)
+    P = [t.detach().to(DEV).requires_grad_() for t in (conv.lin.weight, conv.u.weight, conv.c, conv.bias)]
+    ym = FeaStFn.apply(xm, *P, g, slope, ops.PREC_BF16X3)
+    ym.backward(gout.to(DEV))
+    assert util.rel_err(ym, y) < 1e-5
+    checks = [(P[0].grad, conv.lin.weight.grad, "W"), (P[1].grad, conv.u.weight.grad, "U"), (P[2].grad, conv.c.grad, "c"),
+              (P[3].grad, conv.bias.grad, "bias")]
+    if need_dx:
+        checks.append((xm.grad, x.grad, "x"))
+    else:
+        assert xm.grad is None
+    for got, want, name in checks:
+        assert got.shape == want.shape, name
+        assert util.rel_err(got, want) < 1e-4, (name, util.rel_err(got, want))
+
+
+def test_native_feast_backward_is_deterministic_in_dW_and_handles_ragged_node_counts():
+    """dW's split-K partial sums are added in a fixed order: two calls give the same bits.  Node counts that are not multiples of the
+    32-node stage or of the split size go through TMA's zero fill."""
+    from geobi_gnn_b200 import ops
+    from geobi_gnn_b200.autograd import feast_bwd
+    torch.manual_seed(3)
+    for n in (2, 31, 33, 1000, 20482):
+        cin, cout = 64, 32
+        ring = torch.arange(n)
+        ei = torch.stack((torch.cat((ring, (ring + 1) % n)), torch.cat(((ring + 1) % n, ring))))
+        ei = ei[:, ei[0] != ei[1]]
+        g = ops.csr_from_coo(ei.to(DEV), n, None, ops.COO_BY_COL | ops.COO_DROP_SELF | ops.COO_SORT_NBR | ops.COO_DEDUP)
+        x = torch.randn(n, cin, device=DEV)
+        W, U, c = torch.randn(9 * cout, cin, device=DEV) * 0.1, torch.randn(9, cin, device=DEV) * 0.1, torch.randn(9, device=DEV) * 0.1
+        bias = torch.zeros(cout, device=DEV)
+        out = ops.feast_fwd(x, g, W, U, c, bias, act_slope=0.2, precision=ops.PREC_BF16X3)
+        go = torch.randn(n, cout, device=DEV)
+        a = feast_bwd(x, g, W, U, c, out, go, 0.2, True)
+        b = feast_bwd(x, g, W, U, c, out, go, 0.2, True)
+        assert torch.equal(a[1], b[1])
+        # dW = g^T Z against the fp32 aggregate and a library product
+        from geobi_gnn_b200.autograd import feast_aggregate
+        _, Z = feast_aggregate(x, g, U, c)
+        gpre = go * torch.where(out > 0, 1.0, 0.2)
+        want = (gpre.double().t() @ Z.double()).view(cout, 9, cin).permute(1, 0, 2).reshape(9 * cout, cin)
+        assert util.rel_err(a[1], want.float()) < 1e-5, n
+        assert util.rel_err(a[4], gpre.double().sum(0).float()) < 1e-5, n
 
 
 def test_dualgnn_training_step_gradients_match_oracle():
