@@ -613,8 +613,9 @@ def train_steps(dev, rank, world, barrier, max_over_ranks, precision, patches_pe
            "scaling": "weak", "n_gpus": world, "value": round(faces / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 3), "steps": steps,
            "allreduce_ms": round(ms_ar, 4), "allreduce": f"one flat fp32 bucket of {n_params} gradients ({4 * n_params / 1e6:.2f} MB), NCCL" if world > 1 else None,
            "precision": precision, "loss": float(loss), "error_n_deg": float(en),
-           "backward": "soft-assignment / gather part (feast_bwd_edges_vec_kernel), segment max and the vertex-to-facet transfer in libgeobi kernels; "
-                       "dense parts (dZ, dW, dX, dU, heads) on library GEMMs via autograd"}
+           "backward": "every FeaStConv layer is one geobi_feast_bwd call (dZ = g.W_flat and the split-K dW = g^T.Z on tcgen05 with split bf16 operands, "
+                       "soft-assignment / gather part, dX += dP.U, dU = dP^T.X), segment max and the vertex-to-facet transfer in libgeobi kernels; "
+                       "the two FC heads on library GEMMs via autograd"}
     del net, opt, dv, df, patches
     torch.cuda.empty_cache()
     return out
