@@ -107,6 +107,43 @@ class FeaStFn(torch.autograd.Function):
         return dx, dW, dU, dc, dbias, None, None, None
 
 
+def mlp_head_bwd(f, W1, b1, W2, dy, slope=0.2, need_df=True):
+    """geobi_mlp_head_bwd: (df | None, dW1, db1, dW2, db2) of y = W2.leaky_relu(W1.f + b1) + b2 from dy = dL/dy."""
+    lib = _lib.load()
+    f, ldf, c_in = _rows(f)
+    if ldf % 4 or f.data_ptr() % 16:
+        f, ldf = f.contiguous(), c_in
+    dy, lddy, c_out = _rows(dy)
+    n, hidden, dev = f.size(0), W1.size(0), f.device
+    df = torch.empty((n, c_in), dtype=torch.float32, device=dev) if need_df else None
+    dW1 = torch.empty((hidden, c_in), dtype=torch.float32, device=dev)
+    db1 = torch.empty(hidden, dtype=torch.float32, device=dev)
+    dW2 = torch.empty((c_out, hidden), dtype=torch.float32, device=dev)
+    db2 = torch.empty(c_out, dtype=torch.float32, device=dev)
+    ws = ops._ws(lib.geobi_mlp_head_bwd_ws_bytes(n, c_in, hidden), dev, slot=2)
+    _lib.check(lib.geobi_mlp_head_bwd(_ptr(f), ldf, n, c_in, _ptr(W1.contiguous()), _ptr(b1.contiguous()), hidden, _ptr(W2.contiguous()), c_out,
+                                      float(slope), _ptr(dy), lddy, _ptr(df), c_in, _ptr(dW1), _ptr(db1), _ptr(dW2), _ptr(db2), _ptr(ws),
+                                      ws.numel(), _stream()), "mlp_head_bwd")
+    _count(9 if need_df else 8)     # split f, W1 prep, split dy, hidden planes, 2 x (split-K + reduce), df GEMM
+    return df, dW1, db1, dW2, db2
+
+
+class HeadFn(torch.autograd.Function):
+    """fc2(leaky_relu(fc1(f), 0.2)) (network.py:324-325,340-341): the fused inference kernel forward (the [N,1024] hidden never
+    reaches HBM), geobi_mlp_head_bwd backward; the head's epilogue (residual / force_depth / normalize) stays with the caller."""
+
+    @staticmethod
+    def forward(ctx, f, W1, b1, W2, b2, precision):
+        ctx.save_for_backward(f, W1, b1, W2)
+        return ops.fc_head_fwd(f.detach(), W1.detach(), b1.detach(), W2.detach(), b2.detach(), epilogue=0, precision=precision)
+
+    @staticmethod
+    def backward(ctx, dy):
+        f, W1, b1, W2 = ctx.saved_tensors
+        df, dW1, db1, dW2, db2 = mlp_head_bwd(f, W1, b1, W2, dy, 0.2, ctx.needs_input_grad[0])
+        return df, dW1, db1, dW2, db2, None
+
+
 class SegmentMaxFn(torch.autograd.Function):
     """scatter(x, cluster, reduce='max') through the cluster-member CSR."""
 

@@ -322,10 +322,11 @@ struct Plan {
   uint32_t tmem_cols;
   size_t smem;
 };
-static Plan plan_of(int64_t N, int c_in, int c_out) {
+// split-K product D[rows <= gpad, kpad] = G^T . Z over N nodes (G planes [N, gpad], Z planes [N, kpad])
+static Plan plan_dims(int64_t N, int kpad, int gpad, int rows) {
   Plan p{};
-  p.kpad = (int)(cdiv(H * c_in, BK) * BK);
-  p.gpad = c_out <= 64 ? 64 : 128;
+  p.kpad = kpad;
+  p.gpad = gpad;
   p.mh = p.gpad / 64;
   p.ct = p.kpad / 64;
   p.nsl = (int)cdiv(p.ct, 6);
@@ -340,11 +341,263 @@ static Plan plan_of(int64_t N, int c_in, int c_out) {
   const int64_t blocks = cdiv(N > 0 ? N : 1, KB);
   int64_t s = 148 / p.nsl;
   if (s > blocks / 8) s = blocks / 8;
-  if (s > N / (4 * (int64_t)c_out)) s = N / (4 * (int64_t)c_out);
+  if (s > N / (4 * (int64_t)rows)) s = N / (4 * (int64_t)rows);
   if (s < 1) s = 1;
   p.nodes_per_split = cdiv(blocks, s) * KB;
   p.splits = cdiv(N > 0 ? N : 1, p.nodes_per_split);
   return p;
+}
+static Plan plan_of(int64_t N, int c_in, int c_out) {
+  return plan_dims(N, (int)(cdiv(H * c_in, BK) * BK), c_out <= 64 ? 64 : 128, c_out);
+}
+// partial[split][rows][kpad] = sum over the split's nodes of G[n, row] Z[n, col]
+static int launch_dw_splitk(const Plan& p, const __nv_bfloat16* G, const __nv_bfloat16* Z, int64_t N, int rows, float* partial, cudaStream_t st) {
+  CUtensorMap tg_hi, tg_lo, tz_hi, tz_lo;
+  const bool ok = make_tmap(&tg_hi, G, N, p.gpad, KB) && make_tmap(&tg_lo, G + N * (int64_t)p.gpad, N, p.gpad, KB) &&
+                  make_tmap(&tz_hi, Z, N, p.kpad, KB) && make_tmap(&tz_lo, Z + N * (int64_t)p.kpad, N, p.kpad, KB);
+  if (!ok) {
+    set_error("split-K product: cuTensorMapEncodeTiled unavailable");
+    return GEOBI_ERR_CUDA;
+  }
+  GEOBI_CUDA_OK(cudaFuncSetAttribute(dw_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  dw_splitk_kernel<<<dim3((unsigned)p.splits, (unsigned)p.nsl), 128, p.smem, st>>>(tg_hi, tg_lo, tz_hi, tz_lo, N, p.nodes_per_split, p.mh, p.nc, p.ct,
+                                                                                    p.stages, rows, p.kpad, p.tmem_cols, partial);
+  GEOBI_LAUNCH_OK("dw_splitk");
+  return GEOBI_OK;
+}
+
+// ============================================================================== FC head backward (network.py:324-325,340-341)
+// y = W2 . a + b2,  a = leaky_relu(h),  h = W1 . f + b1.  Given dy [N, c_out]:
+//   da = dy . W2,  dh = da * act'(h),  dW2 = dy^T . a,  db2 = sum dy,  dW1 = dh^T . f,  db1 = sum dh,  df = dh . W1.
+// head_bwd_hidden_kernel recomputes h on tcgen05 (f and W1 split hi + lo; b1 rides along as column C_IN of W1 against a column of
+// ones in f) and writes a and dh as bf16 hi | lo planes [N, hidden]; the three products that follow are the kernels above
+// (split-K over the nodes for dW2 and [dW1; db1], tc_gemm_tma_kernel for df).
+
+constexpr int HEAD_CIN = 32;      // fc_v1 / fc_f1 input width
+constexpr int HEAD_NT = 256;      // hidden units per CTA
+
+// fp32 [N, 32] -> planes [N, 64]: columns 0-31 = f, column 32 = 1 (bias / db1 column), rest 0
+__global__ void head_split_f_kernel(const float* __restrict__ f, int64_t ldf, int64_t N, __nv_bfloat16* __restrict__ F) {
+  const int64_t total = N * 16;                      // one thread = 4 columns
+  const int64_t plane = N * 64;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = t >> 4;
+    const int c0 = (int)(t & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 < HEAD_CIN) v = *reinterpret_cast<const float4*>(f + n * ldf + c0);
+    else if (c0 == HEAD_CIN) v.x = 1.0f;
+    uint2 hi, lo;
+    split_bf16x4(v, hi, lo);
+    *reinterpret_cast<uint2*>(F + n * 64 + c0) = hi;
+    *reinterpret_cast<uint2*>(F + plane + n * 64 + c0) = lo;
+  }
+}
+// dy fp32 [N, c_out <= 4] -> planes [N, 64] (columns >= c_out zero); db2 = sum_n dy.  One thread = 8 columns of a row.
+__global__ void __launch_bounds__(256) head_split_dy_kernel(const float* __restrict__ dy, int64_t lddy, int64_t N, int c_out,
+                                                            __nv_bfloat16* __restrict__ DY, float* __restrict__ db2) {
+  __shared__ float part[4][32];
+  const int64_t plane = N * 64;
+  const int tid = threadIdx.x, grp = tid & 7;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t n = (int64_t)blockIdx.x * 32 + (tid >> 3); n < N; n += (int64_t)gridDim.x * 32) {
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+    if (grp == 0) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      v.x = dy[n * lddy];
+      if (c_out > 1) v.y = dy[n * lddy + 1];
+      if (c_out > 2) v.z = dy[n * lddy + 2];
+      if (c_out > 3) v.w = dy[n * lddy + 3];
+      acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      uint2 h2, l2;
+      split_bf16x4(v, h2, l2);
+      hi.x = h2.x; hi.y = h2.y;
+      lo.x = l2.x; lo.y = l2.y;
+    }
+    *reinterpret_cast<uint4*>(DY + n * 64 + grp * 8) = hi;
+    *reinterpret_cast<uint4*>(DY + plane + n * 64 + grp * 8) = lo;
+  }
+  if (grp == 0)
+    for (int k = 0; k < 4; ++k) part[k][tid >> 3] = acc[k];
+  __syncthreads();
+  if (tid < c_out) {
+    float s = 0.f;
+    for (int r = 0; r < 32; ++r) s += part[tid][r];
+    atomicAdd(db2 + tid, s);
+  }
+}
+// W1p planes [hidden, 64]: columns 0-31 = W1[j, :], column 32 = b1[j];  W1t planes [32, hidden]: W1t[c, j] = W1[j, c]
+__global__ void head_prep_w1_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int hidden, __nv_bfloat16* __restrict__ W1p,
+                                    __nv_bfloat16* __restrict__ W1t) {
+  const int total = hidden * 64;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int j = t >> 6, c = t & 63;
+    const float v = c < HEAD_CIN ? W1[j * HEAD_CIN + c] : (c == HEAD_CIN ? b1[j] : 0.f);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    W1p[t] = hi;
+    W1p[total + t] = lo;
+    if (c < HEAD_CIN) {
+      W1t[c * hidden + j] = hi;
+      W1t[HEAD_CIN * hidden + c * hidden + j] = lo;
+    }
+  }
+}
+
+// grid = (row tiles of 128, hidden / 256).  One K block (64 columns of the f planes): TMA loads the four operand tiles, one thread
+// issues the 12 MMAs (M128 N256 K16 x 4 K steps x 3 passes), then thread = row reads h from TMEM 32 hidden units at a time.
+__global__ void __launch_bounds__(128) head_bwd_hidden_kernel(const __grid_constant__ CUtensorMap tm_f_hi, const __grid_constant__ CUtensorMap tm_f_lo,
+                                                              const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                                                              int64_t N, int hidden, const float* __restrict__ W2, int c_out,
+                                                              const float* __restrict__ dy, int64_t lddy, float slope,
+                                                              __nv_bfloat16* __restrict__ Aq, __nv_bfloat16* __restrict__ Dq) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full;
+  __shared__ __align__(8) uint64_t done;
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float w2s[4][HEAD_NT];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr int A_BYTES = BM * 128, B_BYTES = HEAD_NT * 128;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int j0 = blockIdx.y * HEAD_NT;
+
+  if (tid == 0) {
+    mbar_init(&full, 1);
+    mbar_init(&done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_slot, HEAD_NT);
+  for (int t = tid; t < 4 * HEAD_NT; t += 128) {
+    const int k = t / HEAD_NT, j = t - k * HEAD_NT;
+    w2s[k][j] = k < c_out ? W2[(int64_t)k * hidden + j0 + j] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(&full, (uint32_t)(2 * A_BYTES + 2 * B_BYTES));
+      tma_load_2d(base, &tm_f_hi, 0, (int)m0, &full);
+      tma_load_2d(base + A_BYTES, &tm_f_lo, 0, (int)m0, &full);
+      tma_load_2d(base + 2 * A_BYTES, &tm_w_hi, 0, j0, &full);
+      tma_load_2d(base + 2 * A_BYTES + B_BYTES, &tm_w_lo, 0, j0, &full);
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_wait(&full, 0u);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc(BM, HEAD_NT);
+      const uint64_t ah = make_desc(base), al = make_desc(base + A_BYTES);
+      const uint64_t bh = make_desc(base + 2 * A_BYTES), bl = make_desc(base + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+      for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bh + 2 * k16, idesc, k16 ? 1u : 0u);
+#pragma unroll
+      for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, ah + 2 * k16, bl + 2 * k16, idesc, 1u);
+#pragma unroll
+      for (int k16 = 0; k16 < BK / 16; ++k16) mma_f16(tmem_d, al + 2 * k16, bh + 2 * k16, idesc, 1u);
+      mma_commit(&done);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&done, 0u);
+  tc_fence_after();
+
+  const int64_t m = m0 + tid;
+  const bool live = m < N;
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+  if (live) {
+    d0 = dy[m * lddy];
+    if (c_out > 1) d1 = dy[m * lddy + 1];
+    if (c_out > 2) d2 = dy[m * lddy + 2];
+    if (c_out > 3) d3 = dy[m * lddy + 3];
+  }
+  const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+  const int64_t plane = N * (int64_t)hidden;
+  __nv_bfloat16* arow = Aq + m * hidden + j0;
+  __nv_bfloat16* drow = Dq + m * hidden + j0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < HEAD_NT; c0 += 32) {
+    float v[32];
+    tmem_ld32(lane_addr + (uint32_t)c0, v);
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint2 ah[2], al[2], dh[2], dl[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int jj = c0 + j + 4 * q;
+          const float4 w0 = *reinterpret_cast<const float4*>(&w2s[0][jj]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&w2s[1][jj]);
+          const float4 w2 = *reinterpret_cast<const float4*>(&w2s[2][jj]);
+          const float4 w3 = *reinterpret_cast<const float4*>(&w2s[3][jj]);
+          const float h0 = v[j + 4 * q], h1 = v[j + 4 * q + 1], h2 = v[j + 4 * q + 2], h3 = v[j + 4 * q + 3];
+          float4 a, d;
+          d.x = fmaf(d3, w3.x, fmaf(d2, w2.x, fmaf(d1, w1.x, d0 * w0.x)));
+          d.y = fmaf(d3, w3.y, fmaf(d2, w2.y, fmaf(d1, w1.y, d0 * w0.y)));
+          d.z = fmaf(d3, w3.z, fmaf(d2, w2.z, fmaf(d1, w1.z, d0 * w0.z)));
+          d.w = fmaf(d3, w3.w, fmaf(d2, w2.w, fmaf(d1, w1.w, d0 * w0.w)));
+          a.x = h0 > 0.f ? h0 : h0 * slope;  d.x = h0 > 0.f ? d.x : d.x * slope;
+          a.y = h1 > 0.f ? h1 : h1 * slope;  d.y = h1 > 0.f ? d.y : d.y * slope;
+          a.z = h2 > 0.f ? h2 : h2 * slope;  d.z = h2 > 0.f ? d.z : d.z * slope;
+          a.w = h3 > 0.f ? h3 : h3 * slope;  d.w = h3 > 0.f ? d.w : d.w * slope;
+          split_bf16x4(a, ah[q], al[q]);
+          split_bf16x4(d, dh[q], dl[q]);
+        }
+        *reinterpret_cast<uint4*>(arow + c0 + j) = make_uint4(ah[0].x, ah[0].y, ah[1].x, ah[1].y);
+        *reinterpret_cast<uint4*>(arow + plane + c0 + j) = make_uint4(al[0].x, al[0].y, al[1].x, al[1].y);
+        *reinterpret_cast<uint4*>(drow + c0 + j) = make_uint4(dh[0].x, dh[0].y, dh[1].x, dh[1].y);
+        *reinterpret_cast<uint4*>(drow + plane + c0 + j) = make_uint4(dl[0].x, dl[0].y, dl[1].x, dl[1].y);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, HEAD_NT);
+}
+
+// out[r][col] = sum over the splits (fixed order) of partial[s][r][col];  transpose: rows 0..c_in-1 go to dW1[col][r] and row c_in
+// to db1[col] (the [dW1; db1] product), otherwise rows go to dW2[r][col]
+__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ partial, int splits, int rows, int kpad, int transpose,
+                                                          float* __restrict__ out_a, float* __restrict__ out_b) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rows * kpad) return;
+  const int r = t / kpad, col = t - r * kpad;
+  const int64_t stride = (int64_t)rows * kpad;
+  const float* p = partial + (int64_t)r * kpad + col;
+  float s0 = 0.f, s1 = 0.f;
+  int s = 0;
+  for (; s + 2 <= splits; s += 2) {
+    s0 += p[(int64_t)s * stride];
+    s1 += p[(int64_t)(s + 1) * stride];
+  }
+  if (s < splits) s0 += p[(int64_t)s * stride];
+  const float v = s0 + s1;
+  if (!transpose) out_a[(int64_t)r * kpad + col] = v;
+  else if (r < rows - 1) out_a[(int64_t)col * (rows - 1) + r] = v;
+  else out_b[col] = v;
+}
+
+struct HeadWs {
+  __nv_bfloat16 *F, *W1p, *W1t, *DY, *A, *D;
+  float *zero, *partial;
+};
+template <class C>
+static void carve_head(C& c, int64_t N, int hidden, HeadWs* out) {
+  const Plan pa = plan_dims(N, hidden, 64, 4), pb = plan_dims(N, hidden, 64, HEAD_CIN + 1);
+  HeadWs w;
+  w.F = c.template take<__nv_bfloat16>((size_t)2 * N * 64);
+  w.W1p = c.template take<__nv_bfloat16>((size_t)2 * hidden * 64);
+  w.W1t = c.template take<__nv_bfloat16>((size_t)2 * HEAD_CIN * hidden);
+  w.DY = c.template take<__nv_bfloat16>((size_t)2 * N * 64);
+  w.A = c.template take<__nv_bfloat16>((size_t)2 * N * hidden);
+  w.D = c.template take<__nv_bfloat16>((size_t)2 * N * hidden);
+  w.zero = c.template take<float>(256);
+  const size_t pa_n = (size_t)pa.splits * 4 * hidden, pb_n = (size_t)pb.splits * (HEAD_CIN + 1) * hidden;
+  w.partial = c.template take<float>(pa_n > pb_n ? pa_n : pb_n);
+  if (out) *out = w;
 }
 
 struct Ws {
@@ -440,22 +693,10 @@ extern "C" int geobi_feast_bwd(const float* x, int64_t ldx, int64_t N, int c_in,
   if (rc) return rc;
 
   // dW = g^T . Z
-  {
-    CUtensorMap tg_hi, tg_lo, tz_hi, tz_lo;
-    const bool ok = tc::make_tmap(&tg_hi, w.G, N, p.gpad, bwd::KB) && tc::make_tmap(&tg_lo, w.G + N * (int64_t)p.gpad, N, p.gpad, bwd::KB) &&
-                    tc::make_tmap(&tz_hi, w.Z, N, p.kpad, bwd::KB) && tc::make_tmap(&tz_lo, w.Z + N * (int64_t)p.kpad, N, p.kpad, bwd::KB);
-    if (!ok) {
-      set_error("feast_bwd: cuTensorMapEncodeTiled unavailable");
-      return GEOBI_ERR_CUDA;
-    }
-    GEOBI_CUDA_OK(cudaFuncSetAttribute(bwd::dw_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    bwd::dw_splitk_kernel<<<dim3((unsigned)p.splits, (unsigned)p.nsl), 128, p.smem, st>>>(tg_hi, tg_lo, tz_hi, tz_lo, N, p.nodes_per_split, p.mh,
-                                                                                          p.nc, p.ct, p.stages, c_out, p.kpad, p.tmem_cols,
-                                                                                          w.partial);
-    GEOBI_LAUNCH_OK("dw_splitk");
-    bwd::dw_reduce_kernel<<<(unsigned)cdiv((int64_t)c_out * K, 256), 256, 0, st>>>(w.partial, (int)p.splits, c_out, c_in, p.kpad, dW);
-    GEOBI_LAUNCH_OK("dw_reduce");
-  }
+  rc = bwd::launch_dw_splitk(p, w.G, w.Z, N, c_out, w.partial, st);
+  if (rc) return rc;
+  bwd::dw_reduce_kernel<<<(unsigned)cdiv((int64_t)c_out * K, 256), 256, 0, st>>>(w.partial, (int)p.splits, c_out, c_in, p.kpad, dW);
+  GEOBI_LAUNCH_OK("dw_reduce");
 
   // dx += dP . U,  dU = dP^T . x
   {
@@ -465,6 +706,87 @@ extern "C" int geobi_feast_bwd(const float* x, int64_t ldx, int64_t N, int c_in,
     const int64_t want = cdiv(N, rpb);
     bwd::bwd_dpu_kernel<<<(unsigned)(want < 148 * 4 ? want : 148 * 4), 256, 0, st>>>(x, ldx, N, c_in, cp, w.dP, U, dx, lddx, dU);
     GEOBI_LAUNCH_OK("bwd_dpu");
+  }
+  return GEOBI_OK;
+}
+
+extern "C" size_t geobi_mlp_head_bwd_ws_bytes(int64_t n, int c_in, int hidden) {
+  if (n < 0 || c_in != bwd::HEAD_CIN || hidden < bwd::HEAD_NT || hidden % bwd::HEAD_NT != 0 || hidden > 4096) return 0;
+  bwd::NullCarver c;
+  bwd::carve_head(c, n, hidden, nullptr);
+  return c.s.total();
+}
+
+extern "C" int geobi_mlp_head_bwd(const float* f, int64_t ldf, int64_t N, int c_in, const float* W1, const float* b1, int hidden,
+                                  const float* W2, int c_out, float act_slope, const float* dy, int64_t lddy, float* df, int64_t lddf,
+                                  float* dW1, float* db1, float* dW2, float* db2, void* ws, size_t ws_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GEOBI_REQUIRE(f && W1 && b1 && W2 && dy && dW1 && db1 && dW2 && db2 && N >= 0, "mlp_head_bwd: bad arguments");
+  GEOBI_REQUIRE(c_in == bwd::HEAD_CIN, "mlp_head_bwd: c_in must be 32 (got %d)", c_in);
+  GEOBI_REQUIRE(hidden >= bwd::HEAD_NT && hidden % bwd::HEAD_NT == 0 && hidden <= 4096, "mlp_head_bwd: hidden must be a multiple of 256, <= 4096");
+  GEOBI_REQUIRE(c_out >= 1 && c_out <= 4, "mlp_head_bwd: c_out must be 1..4 (got %d)", c_out);
+  GEOBI_REQUIRE(ldf % 4 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0, "mlp_head_bwd: feature rows must be 16-byte aligned");
+  GEOBI_REQUIRE(df == nullptr || (lddf % 4 == 0 && (reinterpret_cast<uintptr_t>(df) & 15) == 0), "mlp_head_bwd: df rows must be 16-byte aligned");
+  if (!ws || ws_bytes < geobi_mlp_head_bwd_ws_bytes(N, c_in, hidden) || (reinterpret_cast<uintptr_t>(ws) & 127) != 0) {
+    set_error("mlp_head_bwd: workspace missing, too small or not 128-byte aligned");
+    return GEOBI_ERR_WORKSPACE;
+  }
+  GEOBI_CUDA_OK(cudaMemsetAsync(dW1, 0, sizeof(float) * (size_t)hidden * c_in, st));
+  GEOBI_CUDA_OK(cudaMemsetAsync(db1, 0, sizeof(float) * (size_t)hidden, st));
+  GEOBI_CUDA_OK(cudaMemsetAsync(dW2, 0, sizeof(float) * (size_t)c_out * hidden, st));
+  GEOBI_CUDA_OK(cudaMemsetAsync(db2, 0, sizeof(float) * (size_t)c_out, st));
+  if (N == 0) return GEOBI_OK;
+  Carver cv(ws, ws_bytes);
+  bwd::HeadWs w;
+  bwd::carve_head(cv, N, hidden, &w);
+  GEOBI_CUDA_OK(cudaMemsetAsync(w.zero, 0, sizeof(float) * 256, st));
+
+  const int64_t nb = cdiv(N * 16, 256);
+  bwd::head_split_f_kernel<<<(unsigned)(nb < 148 * 16 ? nb : 148 * 16), 256, 0, st>>>(f, ldf, N, w.F);
+  bwd::head_prep_w1_kernel<<<64, 256, 0, st>>>(W1, b1, hidden, w.W1p, w.W1t);
+  {
+    const int64_t want = cdiv(N, 32);
+    bwd::head_split_dy_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(dy, lddy, N, c_out, w.DY, db2);
+  }
+  GEOBI_LAUNCH_OK("mlp_head_bwd prep");
+
+  // a = leaky_relu(h) and dh = (dy . W2) * act'(h) as bf16 planes
+  {
+    CUtensorMap tf_hi, tf_lo, tw_hi, tw_lo;
+    const bool ok = tc::make_tmap(&tf_hi, w.F, N, 64, tc::BM) && tc::make_tmap(&tf_lo, w.F + N * 64, N, 64, tc::BM) &&
+                    tc::make_tmap(&tw_hi, w.W1p, hidden, 64, bwd::HEAD_NT) && tc::make_tmap(&tw_lo, w.W1p + (int64_t)hidden * 64, hidden, 64, bwd::HEAD_NT);
+    if (!ok) {
+      set_error("mlp_head_bwd: cuTensorMapEncodeTiled unavailable");
+      return GEOBI_ERR_CUDA;
+    }
+    const size_t smem = (size_t)2 * tc::BM * 128 + (size_t)2 * bwd::HEAD_NT * 128 + 1024;
+    GEOBI_CUDA_OK(cudaFuncSetAttribute(bwd::head_bwd_hidden_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    bwd::head_bwd_hidden_kernel<<<dim3((unsigned)cdiv(N, tc::BM), (unsigned)(hidden / bwd::HEAD_NT)), 128, smem, st>>>(
+        tf_hi, tf_lo, tw_hi, tw_lo, N, hidden, W2, c_out, dy, lddy, act_slope, w.A, w.D);
+    GEOBI_LAUNCH_OK("head_bwd_hidden");
+  }
+
+  // dW2 = dy^T . a
+  {
+    const bwd::Plan p = bwd::plan_dims(N, hidden, 64, 4);
+    int rc = bwd::launch_dw_splitk(p, w.DY, w.A, N, c_out, w.partial, st);
+    if (rc) return rc;
+    bwd::head_reduce_kernel<<<(unsigned)cdiv((int64_t)c_out * hidden, 256), 256, 0, st>>>(w.partial, (int)p.splits, c_out, hidden, 0, dW2, nullptr);
+    GEOBI_LAUNCH_OK("head_reduce (dW2)");
+  }
+  // [dW1; db1] = [f | 1]^T . dh
+  {
+    const int rows = bwd::HEAD_CIN + 1;
+    const bwd::Plan p = bwd::plan_dims(N, hidden, 64, rows);
+    int rc = bwd::launch_dw_splitk(p, w.F, w.D, N, rows, w.partial, st);
+    if (rc) return rc;
+    bwd::head_reduce_kernel<<<(unsigned)cdiv((int64_t)rows * hidden, 256), 256, 0, st>>>(w.partial, (int)p.splits, rows, hidden, 1, dW1, db1);
+    GEOBI_LAUNCH_OK("head_reduce (dW1, db1)");
+  }
+  // df = dh . W1
+  if (df != nullptr) {
+    int rc = tc::gemm_dispatch(w.D, N * (int64_t)hidden, N, hidden, w.W1t, bwd::HEAD_CIN, w.zero, 1.0f, df, lddf, 3, st);
+    if (rc) return rc;
   }
   return GEOBI_OK;
 }

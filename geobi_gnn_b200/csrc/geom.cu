@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(256) v2f_transfer_kernel(const float* __restri
 // Vertices collect their faces' contributions with atomics (6 faces per vertex on average); d_feat_v is zero-initialised by the caller.
 __global__ void __launch_bounds__(256) v2f_transfer_bwd_kernel(const float* __restrict__ p, int64_t ldp, const int64_t* __restrict__ fv,
                                                                const float* __restrict__ g, int64_t ldg, int64_t F, float* __restrict__ dp,
-                                                               int64_t lddp) {
+                                                               int64_t lddp, bool normals_only) {
   const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const int64_t a = fv[f * 3], b = fv[f * 3 + 1], c = fv[f * 3 + 2];
@@ -307,8 +307,9 @@ __global__ void __launch_bounds__(256) v2f_transfer_bwd_kernel(const float* __re
   const float ux = e1y * e2z - e1z * e2y, uy = e1z * e2x - e1x * e2z, uz = e1x * e2y - e1y * e2x;
   const float len = sqrtf(ux * ux + uy * uy + uz * uz);
   const float* gr = g + f * ldg;
-  const float gcx = gr[0] / 3.0f, gcy = gr[1] / 3.0f, gcz = gr[2] / 3.0f;
-  const float gnx = gr[3], gny = gr[4], gnz = gr[5];
+  // normals_only (geobi_face_normal_bwd): a row of g is the normal's gradient alone
+  const float gcx = normals_only ? 0.f : gr[0] / 3.0f, gcy = normals_only ? 0.f : gr[1] / 3.0f, gcz = normals_only ? 0.f : gr[2] / 3.0f;
+  const float gnx = normals_only ? gr[0] : gr[3], gny = normals_only ? gr[1] : gr[4], gnz = normals_only ? gr[2] : gr[5];
   float gux, guy, guz;
   if (len > 1e-12f) {
     const float nx = ux / len, ny = uy / len, nz = uz / len;
@@ -490,8 +491,18 @@ extern "C" int geobi_v2f_transfer_bwd(const float* feat_v, int64_t ldv, const in
   GEOBI_REQUIRE(feat_v && fv && g_out && d_feat_v && n_faces >= 0 && ldv >= 3 && ldg >= 6 && lddv >= 3, "v2f_transfer_bwd: bad arguments");
   if (n_faces == 0) return GEOBI_OK;
   v2f_transfer_bwd_kernel<<<(unsigned)cdiv(n_faces, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(feat_v, ldv, fv, g_out, ldg, n_faces,
-                                                                                                        d_feat_v, lddv);
+                                                                                                        d_feat_v, lddv, false);
   GEOBI_LAUNCH_OK("v2f_transfer_bwd");
+  return GEOBI_OK;
+}
+
+extern "C" int geobi_face_normal_bwd(const float* points, int64_t ldp, const int64_t* fv, const float* g_normal, int64_t ldg, int64_t n_faces,
+                                     float* d_points, int64_t lddp, void* stream) {
+  GEOBI_REQUIRE(points && fv && g_normal && d_points && n_faces >= 0 && ldp >= 3 && ldg >= 3 && lddp >= 3, "face_normal_bwd: bad arguments");
+  if (n_faces == 0) return GEOBI_OK;
+  v2f_transfer_bwd_kernel<<<(unsigned)cdiv(n_faces, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(points, ldp, fv, g_normal, ldg, n_faces,
+                                                                                                        d_points, lddp, true);
+  GEOBI_LAUNCH_OK("face_normal_bwd");
   return GEOBI_OK;
 }
 

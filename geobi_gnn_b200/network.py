@@ -142,16 +142,26 @@ class DualGNN(nn.Module):
 
 
     def _forward_train_tail(self, data_v, data_f, g_v, xyz):
-        """Training step: heads are plain library GEMMs (autograd), the transfer runs the inference kernel with a native backward."""
+        """Training step.  Tensor-core precisions: each head is the fused inference kernel with a native backward
+        (autograd.HeadFn -> geobi_mlp_head_bwd); precision 'fp32': plain library GEMMs through autograd (cross-check path).
+        The transfer runs the inference kernel with a native backward either way."""
         import torch.nn.functional as F
-        feat_v = self.fc_v2(F.leaky_relu(self.fc_v1(g_v), 0.2))
+        from .autograd import HeadFn, V2FTransferFn
+        prec = config.precision_code()
+        native = prec != ops.PREC_FP32 and self.fc_v1.in_features == 32 and self.fc_v1.out_features % 256 == 0
+
+        def head(fc1, fc2, f):
+            if native:
+                return HeadFn.apply(f, fc1.weight, fc1.bias, fc2.weight, fc2.bias, prec)
+            return fc2(F.leaky_relu(fc1(f), 0.2))
+
+        feat_v = head(self.fc_v1, self.fc_v2, g_v)
         if self.force_depth:
             feat_v = feat_v * data_v.depth_direction
         feat_v = feat_v + xyz
-        from .autograd import V2FTransferFn      # same forward kernel as inference, native backward (geobi_v2f_transfer_bwd)
-        data_f.x = V2FTransferFn.apply(feat_v, data_f.fv_indices, data_f.x)
+        data_f.x = V2FTransferFn.apply(feat_v, data_f.fv_indices, data_f.x)     # geobi_v2f_transfer / geobi_v2f_transfer_bwd
         g_f = self.gnn_f(data_f)
-        feat_f = self.fc_f2(F.leaky_relu(self.fc_f1(g_f), 0.2))
+        feat_f = head(self.fc_f1, self.fc_f2, g_f)
         return feat_v, F.normalize(feat_f, dim=1), None
 
 

@@ -294,6 +294,19 @@ GEOBI_API int geobi_feast_bwd(const float* x, int64_t ldx, int64_t n_nodes, int 
                               int64_t ldo, const float* g_out, int64_t ldg, float* dx, int64_t lddx, float* dW, float* dU,
                               float* dc, float* dbias, void* ws, size_t ws_bytes, void* stream);
 
+/* Backward of one FC head (fc_v1/fc_v2, fc_f1/fc_f2: network.py:324-325,340-341; replaces autograd through the two F.linear calls in
+ * the training step): y = W2 . a + b2, a = leaky_relu(h, act_slope), h = W1 . f + b1; given dy = dL/dy [N, c_out] (the gradient
+ * BEFORE the head's epilogue - residual / force_depth / normalize stay with the caller):
+ *   dW2 = dy^T . a,  db2 = sum dy,  dh = (dy . W2) * act'(h),  dW1 = dh^T . f,  db1 = sum dh,  df = dh . W1.
+ * h is recomputed on tcgen05 (split bf16 operands, b1 folded in as an extra operand column); a and dh are written once as bf16
+ * hi | lo planes [N, hidden] in the workspace and consumed by the split-K kernel of geobi_feast_bwd (dW2, [dW1; db1]: reduction over
+ * the rows) and by the TMA GEMM (df).  c_in must be 32, hidden a multiple of 256 (<= 4096), c_out <= 4.  Outputs are overwritten;
+ * df [N, 32] may be NULL.  ws 128-byte aligned. */
+GEOBI_API size_t geobi_mlp_head_bwd_ws_bytes(int64_t n, int c_in, int hidden);
+GEOBI_API int geobi_mlp_head_bwd(const float* f, int64_t ldf, int64_t n, int c_in, const float* W1, const float* b1, int hidden,
+                                 const float* W2, int c_out, float act_slope, const float* dy, int64_t lddy, float* df, int64_t lddf,
+                                 float* dW1, float* db1, float* dW2, float* db2, void* ws, size_t ws_bytes, void* stream);
+
 /* Per-node linear layer on the tcgen05 tensor cores: out = act(A . W^T + bias), A fp32 [M,K] rounded to bf16
  * (split hi + lo for BF16X3), W fp32 [N,K] (nn.Linear layout), fp32 accumulation in TMEM.  Any K (zero padded to a
  * multiple of 64), N in {32,64,128,256}, out rows 16-byte aligned.  Replaces F.linear / cuBLAS sgemm for the
@@ -332,6 +345,12 @@ GEOBI_API int geobi_v2f_transfer(const float* feat_v, int64_t ldv, const int64_t
  * column cf); d_feat_v [V, >= 3] is ACCUMULATED into (zero it first).  Covers SURVEY.md 8(b)'s geobi_face_normal_bwd. */
 GEOBI_API int geobi_v2f_transfer_bwd(const float* feat_v, int64_t ldv, const int64_t* fv, const float* g_out, int64_t ldg,
                            int64_t n_faces, float* d_feat_v, int64_t lddv, void* stream);
+
+/* Backward of geobi_face_normal (data_util.computer_face_normal, data_util.py:182-198: normalize(cross(p1-p0, p2-p0))):
+ * d_points (zero-initialised by the caller, [V, >=3]) += the gradient reaching the three corners of every face from
+ * g_normal [F, 3].  Same kernel as geobi_v2f_transfer_bwd without the corner-mean part. */
+GEOBI_API int geobi_face_normal_bwd(const float* points, int64_t ldp, const int64_t* fv, const float* g_normal, int64_t ldg,
+                                    int64_t n_faces, float* d_points, int64_t lddp, void* stream);
 
 /* data_util.update_position2 (data_util.py:529-556; test_dual.py:72 runs 60 iterations):
  * n_iter Jacobi sweeps p_v += mean_{f in vf[v]} n_f (n_f . (c_f - p_v)), optional projection on

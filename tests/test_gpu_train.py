@@ -155,3 +155,45 @@ def test_v2f_transfer_backward_matches_eager_autograd():
     keep = torch.ones(pts.size(0), dtype=torch.bool, device=DEV)
     keep[fv[5]] = False                                        # vertices that do not touch the thin face: fp32 bar
     assert util.rel_err(b.grad[keep], a.grad[keep]) < 1e-5
+
+
+@pytest.mark.parametrize("n,c_out", [(1, 3), (127, 3), (4002, 3), (20480, 3), (3000, 1)])
+def test_native_head_backward_matches_autograd(n, c_out):
+    """geobi_mlp_head_bwd (h recomputed on tcgen05, a / dh planes, split-K dW2 and [dW1; db1], TMA GEMM for df) against fp64 autograd
+    through the reference's two F.linear calls (network.py:324-325,340-341); bar 1e-4 max-norm relative, measured ~1e-5."""
+    import torch.nn.functional as F
+    from geobi_gnn_b200 import ops
+    from geobi_gnn_b200.autograd import HeadFn
+    torch.manual_seed(n + c_out)
+    fc1, fc2 = torch.nn.Linear(32, 1024), torch.nn.Linear(1024, c_out)
+    f = torch.randn(n, 32)
+    dy = torch.randn(n, c_out)
+    ref = [t.detach().double().requires_grad_() for t in (f, fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    y = F.linear(F.leaky_relu(F.linear(ref[0], ref[1], ref[2]), 0.2), ref[3], ref[4])
+    y.backward(dy.double())
+    mine = [t.detach().to(DEV).requires_grad_() for t in (f, fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    ym = HeadFn.apply(*mine, ops.PREC_BF16X3)
+    ym.backward(dy.to(DEV))
+    assert util.rel_err(ym.detach(), y.detach().float()) < 1e-5
+    for got, want, name in zip(mine, ref, ("f", "W1", "b1", "W2", "b2")):
+        assert got.grad.shape == want.grad.shape, name
+        assert util.rel_err(got.grad, want.grad.float()) < 1e-4, (name, n, util.rel_err(got.grad, want.grad.float()))
+
+
+def test_face_normal_backward_matches_eager_autograd():
+    """geobi_face_normal_bwd against autograd of normalize(cross(p1 - p0, p2 - p0)) (data_util.py:182-198)."""
+    import ctypes as C
+    import torch.nn.functional as F
+    from geobi_gnn_b200 import _lib
+    mesh = util.noisy_icosphere(6, seed=4)[0]
+    pts = torch.from_numpy(mesh.points.astype("float32")).to(DEV)
+    fv = torch.from_numpy(mesh.fv).to(DEV).long().contiguous()
+    g = torch.randn(fv.size(0), 3, device=DEV)
+    a = pts.clone().requires_grad_(True)
+    tri = a[fv]
+    F.normalize(torch.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0], dim=1), dim=1).backward(g)
+    d = torch.zeros_like(pts)
+    lib = _lib.load()
+    _lib.check(lib.geobi_face_normal_bwd(C.c_void_p(pts.data_ptr()), 3, C.c_void_p(fv.data_ptr()), C.c_void_p(g.data_ptr()), 3, fv.size(0),
+                                         C.c_void_p(d.data_ptr()), 3, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "face_normal_bwd")
+    assert util.rel_err(d, a.grad) < 1e-5
