@@ -167,6 +167,13 @@ def test_native_head_backward_matches_autograd(n, c_out):
     torch.manual_seed(n + c_out)
     fc1, fc2 = torch.nn.Linear(32, 1024), torch.nn.Linear(1024, c_out)
     f = torch.randn(n, 32)
+    # leaky_relu's derivative jumps at h = 0: a hidden unit within rounding distance of the kink (h is fp32-grade, ~1e-5) may take
+    # the other branch than the fp64 reference and move one term of df by 80 % - rows with such a unit are left out (about 1 in 8)
+    with torch.no_grad():
+        h = F.linear(f.double(), fc1.weight.double(), fc1.bias.double())
+        f = f[h.abs().min(1).values > 1e-4]
+    assert f.size(0) >= max(1, n // 2)
+    n = f.size(0)
     dy = torch.randn(n, c_out)
     ref = [t.detach().double().requires_grad_() for t in (f, fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
     y = F.linear(F.leaky_relu(F.linear(ref[0], ref[1], ref[2]), 0.2), ref[3], ref[4])
