@@ -240,11 +240,21 @@ def _check_grad(name, grad, t, tol):
     assert float((flat[idx] - want).abs().max()) <= 10 * tol * max(scale, float(want.abs().max())), name
 
 
+@pytest.fixture
+def train_precision(request):
+    from geobi_gnn_b200 import config
+    old = config.get_precision()
+    yield request.param
+    config.set_precision(old)
+
+
 @pytest.mark.gpu
-def test_cuda_pipeline_and_training_step_reproduce_the_reference():
+@pytest.mark.parametrize("train_precision", ["fp32", "bf16x3"], indirect=True)
+def test_cuda_pipeline_and_training_step_reproduce_the_reference(train_precision):
     """inference.predict_mesh (split -> per-patch forward -> stitch -> 60-sweep update) and one training micro-step through the
-    CUDA kernels, teacher-forced with the reference's clusters, against what the reference's own code produced."""
-    from geobi_gnn_b200 import data_util, inference, network
+    CUDA kernels, teacher-forced with the reference's clusters, against what the reference's own code produced.  The training step
+    runs in 'fp32' (library GEMMs in the backward) and in 'bf16x3' (all-native backward: the mode bench.py trains in)."""
+    from geobi_gnn_b200 import config, data_util, inference, network
     DEV = "cuda"
     g = np.load(os.path.join(util.GOLDEN, "reference_pipeline_ico8.npz"))
     mesh, mesh_o = synth.TriMesh(g["points_noisy"], g["faces"]), synth.TriMesh(g["points_original"], g["faces"])
@@ -266,6 +276,7 @@ def test_cuda_pipeline_and_training_step_reproduce_the_reference():
     ref = ref_network.DualGNN(force_depth=False, pool_type="max", wei_param=2)
     net = network.DualGNN(force_depth=False, pool_type="max", wei_param=2).to(DEV).train()
     net.load_state_dict(ref.state_dict())
+    config.set_precision(train_precision)
     labels = [torch.from_numpy(t[f"labels_{i}"]) for i in range(8)]
     for j, pl in enumerate(util.poolings(net)):
         pl.forced = labels[2 * j: 2 * j + 2]
