@@ -250,29 +250,38 @@ __global__ void __launch_bounds__(128) tc_gemm_tma_kernel(const __grid_constant_
   mbar_wait(&done, 0u);
   tc_fence_after();
 
-  // epilogue: thread = output row (TMEM lane); 32 columns at a time
-  const int64_t m = m0 + tid;
+  // epilogue: thread = output row (TMEM lane), 32 columns at a time.  The 32 x 32 block of a warp leaves through a 4 KB staging
+  // area in the (now dead) operand ring - rows of 128 B, 16-byte chunks XOR-ed with row % 8 - so that 8 lanes write one full
+  // 128-byte line of a row; straight from the row-per-thread layout every store instruction touched 32 different lines (the
+  // wide-N, short-K products of the backward pass, dZ = g . W_flat, ran at 2.1 TB/s of output).
+  const int lane = tid & 31;
   const uint32_t lane_addr = tmem_d + ((uint32_t)(warp * 32) << 16);
+  uint8_t* stg = smem_raw + (base - smem_u32(smem_raw)) + warp * 4096;
 #pragma unroll 1
   for (int c0 = 0; c0 < NT; c0 += 32) {
     float v[32];
     tmem_ld32(lane_addr + (uint32_t)c0, v);
-    if (m < M) {
-      float* o = out + m * ldo + c0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 r;
-        r.x = v[j] + bias[c0 + j];
-        r.y = v[j + 1] + bias[c0 + j + 1];
-        r.z = v[j + 2] + bias[c0 + j + 2];
-        r.w = v[j + 3] + bias[c0 + j + 3];
-        r.x = r.x > 0.f ? r.x : r.x * slope;
-        r.y = r.y > 0.f ? r.y : r.y * slope;
-        r.z = r.z > 0.f ? r.z : r.z * slope;
-        r.w = r.w > 0.f ? r.w : r.w * slope;
-        *reinterpret_cast<float4*>(o + j) = r;
-      }
+    for (int j = 0; j < 32; j += 4) {
+      float4 r;
+      r.x = v[j] + bias[c0 + j];
+      r.y = v[j + 1] + bias[c0 + j + 1];
+      r.z = v[j + 2] + bias[c0 + j + 2];
+      r.w = v[j + 3] + bias[c0 + j + 3];
+      r.x = r.x > 0.f ? r.x : r.x * slope;
+      r.y = r.y > 0.f ? r.y : r.y * slope;
+      r.z = r.z > 0.f ? r.z : r.z * slope;
+      r.w = r.w > 0.f ? r.w : r.w * slope;
+      *reinterpret_cast<float4*>(stg + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = r;
     }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rr = 4 * i + (lane >> 3), ch = lane & 7;
+      const int64_t mr = m0 + warp * 32 + rr;
+      if (mr < M) *reinterpret_cast<float4*>(out + mr * ldo + c0 + 4 * ch) = *reinterpret_cast<const float4*>(stg + rr * 128 + ((ch ^ (rr & 7)) << 4));
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -326,7 +335,11 @@ static int launch_gemm(const __nv_bfloat16* A, int64_t a_plane, int64_t M, int k
     ok = ok && make_tmap(&ta_lo, split ? A + a_plane : A, M, kpad, BM) && make_tmap(&tb_lo, split ? Bq + (int64_t)NT * kpad : Bq, NT, kpad, NT);
     if (ok) {
       GEOBI_CUDA_OK(cudaFuncSetAttribute(tc_gemm_tma_kernel<NT, PASSES, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      tc_gemm_tma_kernel<NT, PASSES, STAGES><<<(unsigned)cdiv(M, BM), 128, smem, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, kpad, bias, slope, out, ldo);
+      // a product with fewer K blocks than ring slots (dZ = g . W_flat: K = C_out, one or two blocks) only ever touches the first
+      // kpad / 64 slots: asking for just those lets two CTAs share an SM where the full ring allows one (NT = 256: 197 -> 99 KB)
+      const int kblocks = kpad / BK;
+      const size_t smem_used = (size_t)(kblocks < STAGES ? kblocks : STAGES) * STAGE_BYTES + 1024;
+      tc_gemm_tma_kernel<NT, PASSES, STAGES><<<(unsigned)cdiv(M, BM), 128, smem_used, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, M, kpad, bias, slope, out, ldo);
       GEOBI_LAUNCH_OK("tc_gemm_tma");
       return GEOBI_OK;
     }
