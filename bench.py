@@ -614,8 +614,12 @@ def train_steps(dev, rank, world, barrier, max_over_ranks, precision, patches_pe
            "allreduce_ms": round(ms_ar, 4), "allreduce": f"one flat fp32 bucket of {n_params} gradients ({4 * n_params / 1e6:.2f} MB), NCCL" if world > 1 else None,
            "precision": precision, "loss": float(loss), "error_n_deg": float(en),
            "backward": "every FeaStConv layer is one geobi_feast_bwd call (dZ = g.W_flat and the split-K dW = g^T.Z on tcgen05 with split bf16 operands, "
-                       "soft-assignment / gather part, dX += dP.U, dU = dP^T.X), segment max and the vertex-to-facet transfer in libgeobi kernels; "
-                       "the two FC heads on library GEMMs via autograd"}
+                       "soft-assignment / gather part, dX += dP.U, dU = dP^T.X), each FC head one geobi_mlp_head_bwd call (hidden layer recomputed on "
+                       "tcgen05, the same split-K and TMA GEMM kernels), segment max and the vertex-to-facet transfer in libgeobi kernels; no library "
+                       "GEMM in the step",
+           "roofline_dw_splitk": {"bound": "hbm", "achieved": 5426.0, "peak": 6542.1, "unit": "GB/s", "frac": 0.83,
+                                  "source": "ncu --set full, profiles/r02/r02b_ncu_full_dw_splitk.csv: dW = g^T.Z of a 64->32 layer at 128 000 nodes reads "
+                                            "327.7 MB (= its algorithmic bytes) in 60.4 us; not re-measured by this run"}}
     del net, opt, dv, df, patches
     torch.cuda.empty_cache()
     return out
