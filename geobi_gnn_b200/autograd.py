@@ -178,11 +178,12 @@ class SegmentMeanFn(torch.autograd.Function):
     def backward(ctx, go):
         mrowptr, cluster = ctx.saved_tensors
         cnt = (mrowptr[1:] - mrowptr[:-1]).clamp(min=1).to(go.dtype)
-        return (go / cnt.unsqueeze(1))[cluster.long()], None, None, None, None
+        return ops.gather_rows(go / cnt.unsqueeze(1), cluster), None, None, None, None
 
 
 class GatherRowsFn(torch.autograd.Function):
-    """x[idx] (PoolingLayer.unpooling); backward = scatter-add."""
+    """x[idx] (PoolingLayer.unpooling, net_util.py:242-245); backward = the sum of the gradient rows over each coarse node's fine
+    nodes, as a CSR segment sum (geobi_group_by + geobi_segment_reduce: fixed summation order, no atomics)."""
 
     @staticmethod
     def forward(ctx, x, idx):
@@ -193,9 +194,8 @@ class GatherRowsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         (idx,) = ctx.saved_tensors
-        dx = torch.zeros((ctx.n, go.size(1)), dtype=go.dtype, device=go.device)
-        dx.index_add_(0, idx.long(), go)
-        return dx, None
+        mrowptr, members = ops.group_by(idx, ctx.n)
+        return ops.segment_reduce(go.contiguous(), mrowptr, members, ctx.n, ops.OP_SUM), None
 
 
 class V2FTransferFn(torch.autograd.Function):

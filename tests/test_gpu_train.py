@@ -224,3 +224,33 @@ def test_face_normal_backward_matches_eager_autograd():
     _lib.check(lib.geobi_face_normal_bwd(C.c_void_p(pts.data_ptr()), 3, C.c_void_p(fv.data_ptr()), C.c_void_p(g.data_ptr()), 3, fv.size(0),
                                          C.c_void_p(d.data_ptr()), 3, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "face_normal_bwd")
     assert util.rel_err(d, a.grad) < 1e-5
+
+
+def test_unpool_and_mean_pool_backward_are_segment_sums():
+    """GatherRowsFn (PoolingLayer.unpooling) and SegmentMeanFn backward against eager autograd; coarse nodes without a fine node
+    (possible with forced labels) get a zero gradient."""
+    from geobi_gnn_b200 import ops
+    from geobi_gnn_b200.autograd import GatherRowsFn, SegmentMeanFn
+    torch.manual_seed(5)
+    n_fine, n_coarse, c = 5000, 1300, 32
+    idx = torch.randint(0, n_coarse - 7, (n_fine,), device=DEV, dtype=torch.int32)      # the last 7 coarse rows stay unused
+    x = torch.randn(n_coarse, c, device=DEV)
+    go = torch.randn(n_fine, c, device=DEV)
+    a = x.clone().requires_grad_()
+    a[idx.long()].backward(go)
+    b = x.clone().requires_grad_()
+    GatherRowsFn.apply(b, idx).backward(go)
+    assert util.rel_err(b.grad, a.grad) < 1e-6
+    assert float(b.grad[-7:].abs().max()) == 0.0
+    # mean pooling: cluster -> member CSR
+    cluster = torch.randint(0, n_coarse, (n_fine,), device=DEV, dtype=torch.int32)
+    cluster[:n_coarse] = torch.arange(n_coarse, device=DEV, dtype=torch.int32)            # every segment non-empty
+    mrowptr, members = ops.group_by(cluster, n_coarse)
+    xf = torch.randn(n_fine, c, device=DEV)
+    g2 = torch.randn(n_coarse, c, device=DEV)
+    a = xf.clone().requires_grad_()
+    cnt = torch.bincount(cluster.long(), minlength=n_coarse).clamp(min=1).float().unsqueeze(1)
+    (torch.zeros(n_coarse, c, device=DEV).index_add_(0, cluster.long(), a) / cnt).backward(g2)
+    b = xf.clone().requires_grad_()
+    SegmentMeanFn.apply(b, mrowptr, members, n_coarse, cluster).backward(g2)
+    assert util.rel_err(b.grad, a.grad) < 1e-6
