@@ -155,16 +155,39 @@ class SegmentMaxFn(torch.autograd.Function):
         return out
 
     @staticmethod
-    def backward(ctx, go):
-        x, mrowptr, members = ctx.saved_tensors
+    def route(x, mrowptr, members, n_seg, go):
         lib = _lib.load()
         xr, ldx, c = _rows(x)
         go = go.contiguous()
         dx = torch.zeros((x.size(0), c), dtype=torch.float32, device=x.device)
-        _lib.check(lib.geobi_segment_max_bwd(_ptr(xr), ldx, c, _ptr(mrowptr), _ptr(members), ctx.n_seg, _ptr(go), c, _ptr(dx), c,
+        _lib.check(lib.geobi_segment_max_bwd(_ptr(xr), ldx, c, _ptr(mrowptr), _ptr(members), n_seg, _ptr(go), c, _ptr(dx), c,
                                              _stream()), "segment_max_bwd")
         _count()
-        return dx, None, None, None
+        return dx
+
+    @staticmethod
+    def backward(ctx, go):
+        x, mrowptr, members = ctx.saved_tensors
+        return SegmentMaxFn.route(x, mrowptr, members, ctx.n_seg, go), None, None, None
+
+
+class PoolStepFn(torch.autograd.Function):
+    """scatter(x, cluster, max | mean) whose forward value was already produced by geobi_pool_step (one library call for the whole
+    coarsening step, net_util.py:100-140); this node only routes the gradient: arg-max member (geobi_segment_max_bwd) or 1/count."""
+
+    @staticmethod
+    def forward(ctx, x, pooled, mrowptr, members, n_seg, op, cluster):
+        ctx.save_for_backward(x, mrowptr, members, cluster)
+        ctx.n_seg, ctx.op = n_seg, op
+        return pooled[0].view_as(pooled[0])
+
+    @staticmethod
+    def backward(ctx, go):
+        x, mrowptr, members, cluster = ctx.saved_tensors
+        if ctx.op == ops.OP_MAX:
+            return SegmentMaxFn.route(x, mrowptr, members, ctx.n_seg, go), None, None, None, None, None, None
+        cnt = (mrowptr[1:] - mrowptr[:-1]).clamp(min=1).to(go.dtype)
+        return ops.gather_rows(go / cnt.unsqueeze(1), cluster), None, None, None, None, None, None
 
 
 class SegmentMeanFn(torch.autograd.Function):

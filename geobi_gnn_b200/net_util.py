@@ -164,9 +164,15 @@ class PoolingLayer(torch.nn.Module):
                 perm = None if self.perm_fn is None else self.perm_fn(n).to(dev)   # None: random priority keys on the device
                 label, _ = ops.graclus(g, perm, use_weight=g._w is not None)
             self.trace.append((g, perm, label))
-            if self.forced is None and not (torch.is_grad_enabled() and x.requires_grad):
-                # inference: the rest of the step is one library call (same kernels, queued right behind the count read-back)
-                cluster, nc, mrowptr, members, x, g, pos = ops.pool_step(g, label, x, op, pos)
+            if self.forced is None:
+                # the rest of the step is one library call (same kernels, queued right behind the count read-back); in a training
+                # step the pooled features re-enter the autograd graph through PoolStepFn (backward: geobi_segment_max_bwd / gather)
+                train = torch.is_grad_enabled() and x.requires_grad
+                x_in = x
+                cluster, nc, mrowptr, members, x, g, pos = ops.pool_step(g, label, x_in.detach() if train else x_in, op, pos)
+                if train:
+                    from .autograd import PoolStepFn
+                    x = PoolStepFn.apply(x_in, [x], mrowptr, members, nc, op, cluster)
                 if g_in is not None and g_in._pin is not None:
                     g_in.nnz             # already on the host (queued before the sync pool_step just did): raises on a bad verdict
                 clusts.append(cluster)
