@@ -536,14 +536,27 @@ def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks):
     mesh = noisy_device_mesh(BIG_FREQ, 0, dev)          # the SAME mesh on every rank
     torch.cuda.synchronize()
     t_mesh = time.perf_counter() - t0
+    # everything stays on the device: normalisation (centroid from one D2H copy of the points, scale from the vertex CSR), the BFS
+    # partition (geobi_bfs_*: the reference's discovery order, ring-parallel) and the per-patch cut-outs; GEOBI_BENCH_HOST_SPLIT=1
+    # restores the host C++ splitter over host copies of the index arrays (round-2 first session: 0.38 s + 0.52 s)
+    host_split = os.environ.get("GEOBI_BENCH_HOST_SPLIT") == "1"
     t0 = time.perf_counter()
-    host = inference.host_views(mesh)
+    if host_split:
+        host = inference.host_views(mesh)
+        c_np, scale = dataset.normalisation(host[0], host[3])
+        norm, cen = (torch.from_numpy(c_np).float().to(dev), float(scale)), None
+    else:
+        host = None
+        norm, cen = inference.device_normalisation(mesh)
+    torch.cuda.synchronize()
     t_views = time.perf_counter() - t0
+    if not host_split:
+        inference.partition(mesh, BIG_SUB, centroid=cen)      # untimed first pass (workspace allocation, first launches)
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
-    parts = inference.partition(mesh, BIG_SUB, host=host)
+    parts = inference.partition(mesh, BIG_SUB, host=host, centroid=cen)
+    torch.cuda.synchronize()
     t_part = time.perf_counter() - t0
-    c_np, scale = dataset.normalisation(host[0], host[3])
-    norm = (torch.from_numpy(c_np).float().to(dev), float(scale))
     # warm-up: the same sharded run once, untimed (allocator high-water mark, NCCL reduce path)
     inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)   # untimed first pass
     barrier()
@@ -563,7 +576,11 @@ def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks):
                         f"round-robin to {world} GPU(s); no data-path collective, accumulators reduced onto rank 0 once",
             "scaling": "strong", "n_gpus": world, "faces": faces, "patches": len(parts),
             "value": round(faces / t_inf, 1), "unit": UNIT, "inference_s": round(t_inf, 4),
-            "partition_s": round(t_part_max, 4), "host_views_s": round(t_views, 4), "whole_mesh_topology_s": round(t_mesh, 4),
+            "partition_s": round(t_part_max, 4), "partition": "host C++ splitter over host copies of the index arrays" if host_split else
+            "device BFS splitter (geobi_bfs_begin / geobi_bfs_grow): identical patches, no host copy of the index arrays",
+            "host_views_s": round(t_views, 4), "host_views": "D2H of points / fv / vf / ev + numpy normalisation" if host_split else
+            "normalisation only: centroid from a D2H copy of the points, scale = 1 / mean edge length from the vertex CSR on the device",
+            "whole_mesh_topology_s": round(t_mesh, 4),
             "end_to_end_s": round(t_views + t_part_max + t_inf, 4), "end_to_end_faces_per_s": round(faces / (t_views + t_part_max + t_inf), 1),
             "timing": "wall clock between barriers (+ device synchronize), max over ranks; partition and host views once per mesh, outside",
             "outputs_ok": ok}

@@ -64,6 +64,9 @@ SIGNATURES = {
     "geobi_mlp_head_bwd_ws_bytes": (_sz, [_i64, _i32, _i32]),
     "geobi_mlp_head_bwd": (_i32, [_p, _i64, _i64, _i32, _p, _p, _i32, _p, _i32, _f32, _p, _i64, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "geobi_face_normal_bwd": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _p]),
+    "geobi_bfs_ws_bytes": (_sz, [_i64]),
+    "geobi_bfs_begin": (_i32, [_p, _p, _i64, _p, _p, _p, _sz, _p]),
+    "geobi_bfs_grow": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "geobi_segment_max_bwd": (_i32, [_p, _i64, _i32, _p, _p, _i64, _p, _i64, _p, _i64, _p]),
     "geobi_linear_tc_ws_bytes": (_sz, [_i64, _i32, _i32]),
     "geobi_linear_tc": (_i32, [_p, _i64, _i64, _i32, _p, _i32, _p, _f32, _p, _i64, _i32, _p, _sz, _p]),

@@ -24,11 +24,29 @@ def host_views(mesh):
     return np.asarray(_np(mesh.points), dtype=np.float32), _np(mesh.fv), _np(mesh.vf), _np(mesh.ev)
 
 
-def partition(mesh, sub_size: int, host=None):
-    """The reference's BFS face patches of a mesh (dataset.py:156-193): [(face ids in discovery order, seed face), ...].  The walk is
-    serial by construction (every seed depends on what the earlier patches covered); `predict_mesh(parts=...)` reuses its result."""
+def _on_device(mesh) -> bool:
+    return torch.is_tensor(mesh.fv) and mesh.fv.is_cuda and torch.is_tensor(mesh.points) and torch.is_tensor(mesh.vf) and mesh.vf.is_cuda
+
+
+def partition(mesh, sub_size: int, host=None, centroid=None):
+    """The reference's BFS face patches of a mesh (dataset.py:156-193): [(face ids in discovery order, seed face), ...].  Patch after
+    patch is serial by construction (every seed depends on what the earlier patches covered); `predict_mesh(parts=...)` reuses the
+    result.  A device-resident mesh (topology.DeviceTriMesh) without `host` views is split ON THE DEVICE (ring-parallel BFS with the
+    same discovery order, patches.split_mesh_device: face lists are int32 device tensors); otherwise by the host C++ splitter."""
+    if host is None and _on_device(mesh) and mesh.vf.size(1) <= 32:
+        return patches.split_mesh_device(mesh.points, mesh.fv, mesh.vf, sub_size, centroid=centroid)
     pts, fv, vf, _ = host_views(mesh) if host is None else host
     return patches.split_mesh(pts, fv, vf, sub_size)
+
+
+def device_normalisation(mesh):
+    """(centroid tensor [1,3], scale) of dataset.py:140,151-152 for a device-resident mesh without copying its edge list to the host:
+    centroid = numpy's fp32 mean of the points (one D2H copy of the points), scale = 1 / mean edge length from the vertex CSR on the
+    device (geobi_mean_edge_length_csr; agrees with numpy's mean over the centred edge vectors to ~1e-7 relative).
+    Returns (norm for predict_mesh(norm=...), centroid as a numpy [3] array for partition(centroid=...))."""
+    c_np = np.ascontiguousarray(mesh.points.detach().cpu().numpy().mean(0, keepdims=True))
+    scale = 1.0 / mesh.mean_edge_length()
+    return (torch.from_numpy(c_np).float().to(mesh.points.device), float(scale)), c_np.reshape(3)
 
 
 _STAGE = {}     # device index -> (pinned int32 staging buffer, event of the last copy out of it)
@@ -37,6 +55,8 @@ _STAGE = {}     # device index -> (pinned int32 staging buffer, event of the las
 def _stage_int32(arr, dev):
     """Host integer array -> int32 device tensor through ONE reusable pinned buffer per device (a fresh `pin_memory()` per patch is a
     cudaHostAlloc of 4 MB, ~1 ms each).  The previous copy out of the buffer is waited for before it is overwritten."""
+    if torch.is_tensor(arr) and arr.is_cuda:          # a face list the device splitter produced
+        return arr.to(torch.int32)
     n = int(len(arr))
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     buf, ev = _STAGE.get(key, (None, None))
@@ -78,7 +98,10 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     make_sub = (lambda pts, fcs: topology.DeviceTriMesh(pts, fcs, dev)) if device_topology else synth.TriMesh
     # `mesh` may be a host object (numpy index arrays, e.g. synth.TriMesh / OpenMesh) or a topology.DeviceTriMesh built on the
     # GPU from points + faces: the host parts of the pipeline (BFS patch splitter, normalisation) get numpy views of it
-    mesh_points, mesh_fv, mesh_vf, mesh_ev = host_views(mesh) if host is None else host
+    # a device-resident mesh with its partition and normalisation in hand needs no host copy of its index arrays at all
+    lean = (host is None and parts is not None and norm is not None and device_topology and _on_device(mesh)
+            and data_type not in ("Kinect_v1", "Kinect_v2") and mesh.n_faces > sub_size)
+    mesh_points, mesh_fv, mesh_vf, mesh_ev = (None, None, None, None) if lean else (host_views(mesh) if host is None else host)
     points_noisy = mesh_points
     poolings = [net.gnn_v.pooling1, net.gnn_v.pooling2, net.gnn_f.pooling1, net.gnn_f.pooling2]
 
@@ -101,11 +124,11 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
     else:                                                          # test_dual.py:49-61
         lap("host_views")
         if parts is None:
-            parts = patches.split_mesh(points_noisy, mesh_fv, mesh_vf, sub_size)
+            parts = patches.split_mesh(points_noisy, mesh_fv, mesh_vf, sub_size)     # host splitter: the host views are in hand here
         lap("split_mesh")
         n_patches = len(parts)
         st = patches.Stitcher(mesh.n_vertices, mesh.n_faces, dev)
-        slot = np.full(mesh.n_vertices, -1, dtype=np.int64)
+        slot = None if lean else np.full(mesh.n_vertices, -1, dtype=np.int64)
         # norm: (centroid, scale) of the WHOLE mesh, computed once
         mine = [k for k in range(n_patches) if k % world == rank]
 
@@ -153,7 +176,9 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
             import torch.distributed as dist
             for t in (st.sum_v, st.vp, st.np_):
                 dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-        if centroid is None:                                        # a rank that received no patch
+        if centroid is None and norm is not None:                   # a rank that received no patch
+            centroid, scale = norm
+        elif centroid is None:
             c_np, scale = dataset.normalisation(points_noisy, mesh_ev)
             centroid, scale = torch.from_numpy(c_np).to(dev), float(scale)
         Vp, Np = st.finish()

@@ -116,6 +116,43 @@ def iter_split_mesh(points, fv_indices, vf_indices, submesh_size, filter_patch_c
         seed = int(nxt)
 
 
+def iter_split_mesh_device(points, fv_dev: torch.Tensor, vf_dev: torch.Tensor, submesh_size: int, filter_patch_count: int = 0, centroid=None):
+    """The same walk on the device (geobi_bfs_begin / geobi_bfs_grow: ring-parallel BFS with the reference's discovery order,
+    dataset.py:156-193, data_util.py:55-84): yields (select_faces int32 DEVICE tensor, seed) - identical patches to `split_mesh`.
+    `points`: host array or device tensor [V,3]; `centroid` = points.mean(0) as numpy computes it (fp32 pairwise sum; the seeds are
+    arg-maxima decided by the last bit, so it is taken from the host copy unless the caller passes it); fv int64 [F,3] and the padded
+    incidence table vf int64 [V,k] on the device."""
+    from . import _lib, ops
+    lib = _lib.load()
+    dev = fv_dev.device
+    if centroid is None:
+        pts_h = points.detach().cpu().numpy() if torch.is_tensor(points) else np.asarray(points)
+        centroid = np.ascontiguousarray(np.asarray(pts_h, dtype=np.float32).mean(0, keepdims=True)).reshape(3)
+    centroid = np.ascontiguousarray(centroid, dtype=np.float32).reshape(3)
+    pts_d = points if torch.is_tensor(points) and points.is_cuda else torch.as_tensor(np.ascontiguousarray(points, dtype=np.float32)).to(dev)
+    pts_d = pts_d.contiguous().float()
+    fv_dev, vf_dev = fv_dev.contiguous().long(), vf_dev.contiguous().long()
+    f, k = fv_dev.size(0), vf_dev.size(1)
+    ws = torch.empty(lib.geobi_bfs_ws_bytes(f), dtype=torch.uint8, device=dev)      # carries the walk's state between calls
+    seed, n_out, nxt = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    with torch.cuda.device(dev):
+        stream = ops._stream()
+        _lib.check(lib.geobi_bfs_begin(ops._ptr(pts_d), ops._ptr(fv_dev), f, C.c_void_p(centroid.ctypes.data), C.byref(seed), ops._ptr(ws),
+                                       ws.numel(), stream), "bfs_begin")
+        cur = int(seed.value)
+        while cur >= 0:
+            out = torch.empty(min(int(submesh_size), f), dtype=torch.int32, device=dev)
+            _lib.check(lib.geobi_bfs_grow(ops._ptr(fv_dev), ops._ptr(vf_dev), f, k, cur, int(submesh_size), ops._ptr(out), C.byref(n_out),
+                                          C.byref(nxt), ops._ptr(ws), ws.numel(), stream), "bfs_grow")
+            if int(n_out.value) > filter_patch_count:
+                yield out[:int(n_out.value)], cur
+            cur = int(nxt.value)
+
+
+def split_mesh_device(points, fv_dev, vf_dev, submesh_size, filter_patch_count=0, centroid=None):
+    return list(iter_split_mesh_device(points, fv_dev, vf_dev, submesh_size, filter_patch_count, centroid))
+
+
 def prefetch(iterable, depth=2):
     """Runs `iterable` on a helper thread, at most `depth` items ahead of the consumer; exceptions surface at the consumer."""
     import queue

@@ -346,6 +346,23 @@ GEOBI_API int geobi_v2f_transfer(const float* feat_v, int64_t ldv, const int64_t
 GEOBI_API int geobi_v2f_transfer_bwd(const float* feat_v, int64_t ldv, const int64_t* fv, const float* g_out, int64_t ldg,
                            int64_t n_faces, float* d_feat_v, int64_t lddv, void* stream);
 
+/* ---------------------------------------------------------------- BFS face-patch splitter */
+/* The reference's mesh split (dataset.py:156-193 over data_util.mesh_get_neighbor_np, data_util.py:55-84; pure-Python loops
+ * upstream) on the device, with the reference's discovery order: seed = first arg-max of the squared face-centre distance to
+ * `centroid` over the faces no patch has covered; ring-by-ring growth through faces sharing a vertex (faces of the ring in list
+ * order, corners in order, incident faces in vf-row order), cut at exactly `neighbor_count` faces.  Identical patches to the host
+ * splitter (geobi_host_grow_patch).  The workspace carries the state between calls:
+ *   geobi_bfs_begin   distances (numpy's fp32 operation order), stamps; *seed_host = the first seed.  centroid_host: 3 floats on the HOST.
+ *   geobi_bfs_grow    grows the patch of `seed` into out_faces (device int32, at least min(neighbor_count, n_faces) entries),
+ *                     removes it from the uncovered set; *n_out_host = its size, *next_seed_host = the next seed or -1 when every
+ *                     face is covered.  Synchronises the stream (one state read-back per 32 rings).
+ * fv int64 [F,3], vf int64 [V,k] padded with -1 (k <= 32). */
+GEOBI_API size_t geobi_bfs_ws_bytes(int64_t n_faces);
+GEOBI_API int geobi_bfs_begin(const float* points, const int64_t* fv, int64_t n_faces, const float* centroid_host, int64_t* seed_host,
+                              void* ws, size_t ws_bytes, void* stream);
+GEOBI_API int geobi_bfs_grow(const int64_t* fv, const int64_t* vf, int64_t n_faces, int64_t k, int64_t seed, int64_t neighbor_count,
+                             int32_t* out_faces, int64_t* n_out_host, int64_t* next_seed_host, void* ws, size_t ws_bytes, void* stream);
+
 /* Backward of geobi_face_normal (data_util.computer_face_normal, data_util.py:182-198: normalize(cross(p1-p0, p2-p0))):
  * d_points (zero-initialised by the caller, [V, >=3]) += the gradient reaching the three corners of every face from
  * g_normal [F, 3].  Same kernel as geobi_v2f_transfer_bwd without the corner-mean part. */

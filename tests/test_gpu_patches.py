@@ -201,3 +201,58 @@ def test_get_submesh_device_equals_host_routine():
         v_dev, faces_dev = patches.get_submesh_device(fv_dev, torch.from_numpy(np.ascontiguousarray(sel)).cuda(), mesh.n_vertices)
         assert np.array_equal(v_dev.cpu().numpy(), v_host)
         assert np.array_equal(faces_dev.cpu().numpy(), faces_host)
+
+
+@pytest.mark.gpu
+def test_device_splitter_yields_the_host_splitters_patches():
+    """geobi_bfs_begin / geobi_bfs_grow (ring-parallel BFS, atomicMin claims, ordered compaction) against the host C++ splitter -
+    itself equal to the Python oracle (tests above): same seeds, same faces in the same discovery order, for closed and open /
+    shuffled meshes, patch sizes from a handful of faces to more than the mesh, with and without filter_patch_count."""
+    from geobi_gnn_b200 import patches
+    DEV = "cuda"
+    cases = [(util.noisy_icosphere(9)[0], ((2, 0), (50, 0), (333, 0), (1000, 0), (5000, 0))),
+             (_open_shuffled_mesh(10, 3), ((200, 0), (777, 0), (300, 299), (10 ** 6, 0))),
+             (util.noisy_icosphere(40)[0], ((4000, 0), (31999, 0)))]
+    for mesh, subs in cases:
+        fv_d, vf_d = torch.from_numpy(np.ascontiguousarray(mesh.fv)).to(DEV), torch.from_numpy(np.ascontiguousarray(mesh.vf)).to(DEV)
+        for sub, filt in subs:
+            want = patches.split_mesh(mesh.points, mesh.fv, mesh.vf, sub, filt)
+            got = patches.split_mesh_device(mesh.points, fv_d, vf_d, sub, filt)
+            assert len(got) == len(want) and len(got) >= 1, (sub, len(got), len(want))
+            for k, ((sel, seed), (sel2, seed2)) in enumerate(zip(got, want)):
+                assert seed == seed2, (sub, k)
+                assert sel.dtype == torch.int32 and np.array_equal(sel.cpu().numpy(), np.asarray(sel2)), (sub, k)
+    # points already on the device, centroid handed over
+    mesh = cases[0][0]
+    pts_d = torch.from_numpy(mesh.points.astype(np.float32)).to(DEV)
+    cen = mesh.points.astype(np.float32).mean(0)
+    got = patches.split_mesh_device(pts_d, torch.from_numpy(mesh.fv).to(DEV), torch.from_numpy(mesh.vf).to(DEV), 1000, centroid=cen)
+    want = patches.split_mesh(mesh.points, mesh.fv, mesh.vf, 1000)
+    assert [s for _, s in got] == [s for _, s in want]
+    assert all(np.array_equal(a.cpu().numpy(), np.asarray(b)) for (a, _), (b, _) in zip(got, want))
+
+
+@pytest.mark.gpu
+def test_predict_mesh_with_device_partition_and_normalisation():
+    """The all-device whole-mesh path (device BFS partition, device normalisation, no host copy of the index arrays: what bench.py's
+    configs[3] runs) against the default path of the same function (host splitter, numpy normalisation) on a device-resident mesh."""
+    from geobi_gnn_b200 import inference, network, topology
+    DEV = "cuda"
+    mesh_h, _ = util.noisy_icosphere(12)
+    mesh = topology.DeviceTriMesh(mesh_h.points, mesh_h.fv, DEV)
+    torch.manual_seed(1)
+    net = network.DualGNN().to(DEV).eval()
+    sub = 900
+    util.set_perm_fn(net, 3)
+    want = inference.predict_mesh(net, mesh, sub, device=DEV, return_parts=True)
+    norm, cen = inference.device_normalisation(mesh)
+    parts = inference.partition(mesh, sub, centroid=cen)
+    assert all(torch.is_tensor(sel) and sel.is_cuda for sel, _ in parts)
+    host_parts = inference.partition(mesh, sub, host=inference.host_views(mesh))
+    assert [s for _, s in parts] == [s for _, s in host_parts]
+    assert all(np.array_equal(a.cpu().numpy(), np.asarray(b)) for (a, _), (b, _) in zip(parts, host_parts))
+    util.set_perm_fn(net, 3)
+    got = inference.predict_mesh(net, mesh, sub, device=DEV, parts=parts, norm=norm, return_parts=True)
+    assert got[3] == want[3] == len(parts)
+    assert util.rel_err(got[0], want[0]) < util.TOL_FP32 and util.rel_err(got[2], want[2]) < util.TOL_FP32
+    assert util.rel_err(got[1], want[1]) < util.TOL_NORMAL
