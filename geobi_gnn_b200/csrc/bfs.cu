@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(THREADS) argmax_partial_kernel(const float* __
     part_idx[blockIdx.x] = si[0];
   }
 }
-// one block: final arg-max -> st[p].next_seed (or -1 when nothing is left); optionally also starts nothing else
+// one block: final arg-max over the partials -> next_seed of BOTH state copies (-1 when every face is covered); `fresh` (may be
+// null) = the number of faces the finished patch newly covered, subtracted from n_left first
 __global__ void __launch_bounds__(THREADS) argmax_final_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx, int parts,
                                                                const int* __restrict__ fresh, State* __restrict__ st, int p) {
   __shared__ float sv[THREADS];

@@ -8,7 +8,8 @@
 //     dx, dP, dc from dZ                    (feast_bwd_edges kernels, feast_bwd.cu)
 //     dx   += dP . U,   dU = dP^T . x       (bwd_dpu_kernel: K = 9, CUDA cores, one pass over x)
 // Every product with a long reduction or a wide output runs as three bf16 passes on split operands (hi.hi + hi.lo + lo.hi,
-// fp32 accumulation in TMEM: fp32-grade results), like the forward projections.
+// fp32 accumulation in TMEM: fp32-grade results), like the forward projections.  The second half of the file is the backward of the
+// two FC heads (geobi_mlp_head_bwd), built from the same two product kernels.
 //
 // dw_splitk_kernel.  D[o, k] = sum_n g[n, o] Z[n, k]: both operands are stored node-major, i.e. the reduction index is the SLOW
 // one, so both are MN-major UMMA operands: a TMA box of 32 nodes x 64 columns (bf16, SWIZZLE_128B) of the row-major planes IS the
