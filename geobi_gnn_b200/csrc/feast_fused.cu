@@ -564,13 +564,21 @@ int feast_fwd_fused(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
     int rc = feast_project_only(x, ldx, n_src, fused::C_IN, U, Wk.P, st);
     if (rc) return rc;
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    GEOBI_CUDA_OK(cudaGetDevice(&dev));
-    GEOBI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GEOBI_CUDA_OK(cudaFuncSetAttribute(fused::feast_fused_64_32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
-    GEOBI_CUDA_OK(cudaFuncSetAttribute(fused::feast_fused_64_32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES));
+  // one-time set-up as a thread-safe static initialiser: concurrent callers (bench.py runs two forwards per GPU from two host
+  // threads) must not see the SM count before the kernels' shared-memory limit is raised - a plain `if (sms == 0)` flag let the
+  // second thread launch with the 48 KB default ("invalid argument", seen once in ~10 bench runs)
+  static const int sms = []() -> int {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(fused::feast_fused_64_32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(fused::feast_fused_64_32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::SMEM_BYTES) != cudaSuccess)
+      return -1;
+    return n;
+  }();
+  if (sms <= 0) {
+    (void)cudaGetLastError();
+    set_error("feast_fused: device query or shared-memory opt-in failed");
+    return GEOBI_ERR_CUDA;
   }
   const int64_t n_tiles = (N + fused::NT - 1) / fused::NT;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);

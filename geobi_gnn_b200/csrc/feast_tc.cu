@@ -292,16 +292,15 @@ __global__ void __launch_bounds__(128) tc_gemm_tma_kernel(const __grid_constant_
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const EncodeTiledFn fn = []() -> EncodeTiledFn {      // thread-safe: a `tried` flag set before the pointer handed a second thread nullptr
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
+    EncodeTiledFn f = nullptr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
+      f = reinterpret_cast<EncodeTiledFn>(p);
     cudaGetLastError();
-  }
+    return f;
+  }();
   return fn;
 }
 // bf16 [rows, kpad] row-major, box = 64 columns (128 B, the swizzle span) x box_rows

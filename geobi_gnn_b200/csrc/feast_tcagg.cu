@@ -1032,13 +1032,18 @@ int feast_fwd_tcagg(const float* x, int64_t ldx, int64_t N, const int32_t* rowpt
     tcagg::prep_x_kernel<<<(unsigned)cdiv(n_src, tcagg::PREP_ROWS), tcagg::PREP_THREADS, 0, st>>>(x, ldx, n_src, U, Wk.Xs, Wk.P);
     GEOBI_LAUNCH_OK("tcagg prep_x");
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    GEOBI_CUDA_OK(cudaGetDevice(&dev));
-    GEOBI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    GEOBI_CUDA_OK(cudaFuncSetAttribute(tcagg::feast_tcagg_64_32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcagg::SMEM_BYTES));
-    GEOBI_CUDA_OK(cudaFuncSetAttribute(tcagg::feast_tcagg_64_32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcagg::SMEM_BYTES));
+  static const int sms = []() -> int {               // thread-safe one-time set-up (see feast_fused.cu)
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (cudaFuncSetAttribute(tcagg::feast_tcagg_64_32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcagg::SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(tcagg::feast_tcagg_64_32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcagg::SMEM_BYTES) != cudaSuccess)
+      return -1;
+    return n;
+  }();
+  if (sms <= 0) {
+    (void)cudaGetLastError();
+    set_error("feast_tcagg: device query or shared-memory opt-in failed");
+    return GEOBI_ERR_CUDA;
   }
   const int64_t n_tiles = (N + tcagg::TILE - 1) / tcagg::TILE;
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);

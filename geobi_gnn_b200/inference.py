@@ -192,10 +192,11 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
                 for s_ in streams:
                     s_.wait_stream(cur)
                 ticket, lock, errors = itertools.count(), threading.Lock(), []
+                dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
 
                 def lane(i):
                     try:
-                        torch.cuda.set_device(dev)
+                        torch.cuda.set_device(dev_index)
                         with torch.cuda.stream(streams[i]):
                             while True:
                                 with lock:
