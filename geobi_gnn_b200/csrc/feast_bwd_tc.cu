@@ -360,8 +360,9 @@ static int launch_dw_splitk(const Plan& p, const __nv_bfloat16* G, const __nv_bf
     set_error("split-K product: cuTensorMapEncodeTiled unavailable");
     return GEOBI_ERR_CUDA;
   }
-  // the limit is raised to the device maximum, not to this plan's need: concurrent callers with different plans must not lower it
-  GEOBI_CUDA_OK(cudaFuncSetAttribute(dw_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  // the limit is raised to the most any plan asks for (200 KB of stages + alignment slack), not to this plan's need: concurrent
+  // callers with different plans must not lower it under each other
+  GEOBI_CUDA_OK(cudaFuncSetAttribute(dw_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
   dw_splitk_kernel<<<dim3((unsigned)p.splits, (unsigned)p.nsl), 128, p.smem, st>>>(tg_hi, tg_lo, tz_hi, tz_lo, N, p.nodes_per_split, p.mh, p.nc, p.ct,
                                                                                     p.stages, rows, p.kpad, p.tmem_cols, partial);
   GEOBI_LAUNCH_OK("dw_splitk");
