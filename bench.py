@@ -485,7 +485,7 @@ def run_ours(args, rank, world, local_rank):
             "concurrent_forwards": max(1, int(args.streams)), "single_stream": r2.get("single_stream")}
         del wl2
         torch.cuda.empty_cache()
-        extra["configs3_mesh10m"] = strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks, lanes=max(1, int(args.streams)))
+        extra["configs3_mesh10m"] = strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks)
         extra["configs4_train"] = train_steps(dev, rank, world, barrier, max_over_ranks, args.precision)
 
     cpu = cpu_baseline(12.0, args.workload) if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
@@ -525,7 +525,7 @@ DESCRIBE = {"mesh1m": "configs[2]: one noisy icosphere mesh of 1 003 520 faces /
 FACES = {"mesh1m": 20 * MESH_FREQ ** 2, "patches": N_PATCHES * 20 * PATCH_FREQ ** 2}
 
 
-def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks, lanes=1):
+def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks):
     """BASELINE configs[3]: one 10 M-face mesh, the reference's whole-mesh pipeline (test_dual.predict_one: BFS patches of <= 1 M faces,
     per-patch forward, overlap-average stitch, 60-sweep vertex update) with the patches dealt to the ranks.  The partition
     (dataset.py:156-193) is serial by construction - every seed depends on what the earlier patches covered - and is computed once
@@ -558,10 +558,10 @@ def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks, lanes=1):
     torch.cuda.synchronize()
     t_part = time.perf_counter() - t0
     # warm-up: the same sharded run once, untimed (allocator high-water mark, NCCL reduce path)
-    inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm, lanes=lanes)   # untimed first pass
+    inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)   # untimed first pass
     barrier()
     t0 = time.perf_counter()
-    out = inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm, lanes=lanes)
+    out = inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)
     barrier()
     t_inf = time.perf_counter() - t0
     (t_inf, t_part_max) = max_over_ranks(t_inf, t_part)
@@ -574,7 +574,7 @@ def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks, lanes=1):
     torch.cuda.empty_cache()
     return {"workload": f"configs[3]: one {faces}-face mesh (icosphere frequency {BIG_FREQ}), sub_size {BIG_SUB}: {len(parts)} BFS patches dealt "
                         f"round-robin to {world} GPU(s); no data-path collective, accumulators reduced onto rank 0 once",
-            "scaling": "strong", "n_gpus": world, "faces": faces, "patches": len(parts), "concurrent_patches": lanes,
+            "scaling": "strong", "n_gpus": world, "faces": faces, "patches": len(parts),
             "value": round(faces / t_inf, 1), "unit": UNIT, "inference_s": round(t_inf, 4),
             "partition_s": round(t_part_max, 4), "partition": "host C++ splitter over host copies of the index arrays" if host_split else
             "device BFS splitter (geobi_bfs_begin / geobi_bfs_grow): identical patches, no host copy of the index arrays",

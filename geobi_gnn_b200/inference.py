@@ -73,34 +73,11 @@ def _stage_int32(arr, dev):
     return out
 
 
-_REPLICAS = {}      # id(net) -> (net, [module replicas]) for concurrent patch lanes
-
-
-def _lane_nets(net, lanes):
-    """`lanes` modules computing what `net` computes: `net` itself plus copies that SHARE its parameter storage (a PoolingLayer keeps
-    per-forward state on the module, so concurrent forwards need one module each).  Cached per net."""
-    import copy
-    ent = _REPLICAS.get(id(net))
-    if ent is None or ent[0] is not net:
-        ent = (net, [])
-        _REPLICAS[id(net)] = ent
-    reps = ent[1]
-    while len(reps) < lanes - 1:
-        r = copy.deepcopy(net)
-        for pr, pn in zip(r.parameters(), net.parameters()):
-            pr.data = pn.data                      # same weights, also after a later load_state_dict / optimizer step in place
-        reps.append(r.eval() if not net.training else r)
-    return [net] + reps[:lanes - 1]
-
-
 def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device="cuda", n_iter: int = 60, rank: int = 0, world: int = 1,
                  forced: Optional[List] = None, return_parts: bool = False, device_topology: bool = True,
-                 timings: Optional[dict] = None, parts: Optional[List] = None, host=None, norm=None, lanes: int = 1):
+                 timings: Optional[dict] = None, parts: Optional[List] = None, host=None, norm=None):
     """Returns (V [Nv,3] updated vertices, Np [Nf,3] unit facet normals, Vp [Nv,3] network vertices) on `device`
     (meaningful on rank 0 when world > 1).  `forced`: per patch, the 4 pooling layers' raw label lists (tests).
-    `lanes` > 1 (device-resident mesh whose partition holds device face lists, `norm` known): that many patches of this rank are in
-    flight at once, each on its own host thread, CUDA stream, module replica and accumulator set (merged at the end) - one patch's
-    latency-bound stretches (cut-out, front end, matcher, count read-backs) overlap with another's kernels.
     `parts` / `host`: a partition and the host views computed earlier (`partition`, `host_views`) - the sharded run then consists
     of the per-rank patch loop, the accumulator reduction onto rank 0 and the vertex update only; `norm` = (centroid tensor, scale)
     of the whole mesh (`dataset.normalisation`) if the caller has it already."""
@@ -159,70 +136,18 @@ def predict_mesh(net, mesh, sub_size: int, data_type: str = "Synthetic", device=
         if on_device:
             # the whole mesh lives on the device: a patch is cut out there (patches.get_submesh_device: same vertex order as the
             # host routine); per patch only its face list crosses PCIe (int32, pinned)
-            def one_patch(k, net_k, st_k, norm_k):
+            for k in mine:
                 sel, seed = parts[k]
                 sel_dev = _stage_int32(sel, dev)
                 v_idx, faces = patches.get_submesh_device(mesh.fv, sel_dev, mesh.n_vertices)
                 sub = topology.DeviceTriMesh(mesh.points.index_select(0, v_idx), faces, dev)
                 dual = dataset.process_one_submesh(sub, f"mesh-sub{sub_size}-{seed}", None, dev, csr_native=True)
-                dataset.attach_normalisation(dual, points_noisy, mesh_ev, precomputed=norm_k)   # dataset.py:140,179-180
-                norm_k = (dual[0].centroid, dual[0].scale)
+                dataset.attach_normalisation(dual, points_noisy, mesh_ev, precomputed=norm)   # dataset.py:140,179-180
+                centroid, scale = dual[0].centroid, dual[0].scale
+                norm = (centroid, scale)
                 dual = dataset.post_processing(dual, data_type)
-                if forced is not None:
-                    for pl, f in zip([net_k.gnn_v.pooling1, net_k.gnn_v.pooling2, net_k.gnn_f.pooling1, net_k.gnn_f.pooling2], forced[k]):
-                        pl.forced = f
-                with torch.no_grad():
-                    vert_p, norm_p, _ = net_k([dual[0], dual[1]])
-                st_k.add(vert_p, norm_p, v_idx, sel_dev.long())
-                return norm_k
-
-            n_lanes = max(1, min(int(lanes), len(mine)))
-            if n_lanes > 1 and (norm is None or not all(torch.is_tensor(parts[k][0]) and parts[k][0].is_cuda for k in mine)):
-                n_lanes = 1                          # the pinned staging buffer of host face lists is one per device
-            if n_lanes == 1:
-                for k in mine:
-                    norm = one_patch(k, net, st, norm)
-            else:
-                import itertools
-                import threading
-                nets = _lane_nets(net, n_lanes)
-                stitchers = [st] + [patches.Stitcher(mesh.n_vertices, mesh.n_faces, dev) for _ in range(n_lanes - 1)]
-                cur = torch.cuda.current_stream(dev)
-                streams = [torch.cuda.Stream(dev) for _ in range(n_lanes)]
-                for s_ in streams:
-                    s_.wait_stream(cur)
-                ticket, lock, errors = itertools.count(), threading.Lock(), []
-                dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
-
-                def lane(i):
-                    try:
-                        torch.cuda.set_device(dev_index)
-                        with torch.cuda.stream(streams[i]):
-                            while True:
-                                with lock:
-                                    j = next(ticket)
-                                if j >= len(mine) or errors:
-                                    return
-                                one_patch(mine[j], nets[i], stitchers[i], norm)
-                    except BaseException as exc:      # surfaces on the calling thread
-                        errors.append(exc)
-
-                threads = [threading.Thread(target=lane, args=(i,)) for i in range(n_lanes)]
-                for t_ in threads:
-                    t_.start()
-                for t_ in threads:
-                    t_.join()
-                if errors:
-                    raise errors[0]
-                for s_ in streams:
-                    cur.wait_stream(s_)
-                for other in stitchers[1:]:
-                    st.merge(other.sum_v, other.vp, other.np_)
-                for n_ in nets[1:]:
-                    for pl in (n_.gnn_v.pooling1, n_.gnn_v.pooling2, n_.gnn_f.pooling1, n_.gnn_f.pooling2):
-                        pl.forced = None
-            if mine and norm is not None:
-                centroid, scale = norm
+                vert_p, norm_p = run(dual, k)
+                st.add(vert_p, norm_p, v_idx, sel_dev.long())
             mine = []
 
         def cut(k):                                                 # host side of one patch (C++ re-indexing + a gather)

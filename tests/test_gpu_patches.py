@@ -256,27 +256,3 @@ def test_predict_mesh_with_device_partition_and_normalisation():
     assert got[3] == want[3] == len(parts)
     assert util.rel_err(got[0], want[0]) < util.TOL_FP32 and util.rel_err(got[2], want[2]) < util.TOL_FP32
     assert util.rel_err(got[1], want[1]) < util.TOL_NORMAL
-
-
-@pytest.mark.gpu
-def test_predict_mesh_concurrent_patch_lanes_match_the_sequential_loop():
-    """predict_mesh(lanes=2): two patches in flight (thread + stream + module replica + accumulator set each) give the sequential
-    loop's result; the matcher's visiting order is a stateless function of the node count here, so both runs form the same clusters."""
-    from geobi_gnn_b200 import inference, network, topology
-    DEV = "cuda"
-    mesh_h, _ = util.noisy_icosphere(14)
-    mesh = topology.DeviceTriMesh(mesh_h.points, mesh_h.fv, DEV)
-    torch.manual_seed(2)
-    net = network.DualGNN().to(DEV).eval()
-    for m in net.modules():
-        if hasattr(m, "perm_fn"):
-            m.perm_fn = lambda n: torch.randperm(n, generator=torch.Generator().manual_seed(n))
-    norm, cen = inference.device_normalisation(mesh)
-    parts = inference.partition(mesh, 600, centroid=cen)
-    assert len(parts) >= 6
-    want = inference.predict_mesh(net, mesh, 600, device=DEV, parts=parts, norm=norm)
-    got = inference.predict_mesh(net, mesh, 600, device=DEV, parts=parts, norm=norm, lanes=2)
-    again = inference.predict_mesh(net, mesh, 600, device=DEV, parts=parts, norm=norm, lanes=3)
-    for out in (got, again):
-        assert util.rel_err(out[0], want[0]) < 1e-6 and util.rel_err(out[2], want[2]) < 1e-6
-        assert float((out[1] - want[1]).abs().max()) < 1e-5
