@@ -559,11 +559,17 @@ def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks):
     t_part = time.perf_counter() - t0
     # warm-up: the same sharded run once, untimed (allocator high-water mark, NCCL reduce path)
     inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)   # untimed first pass
+    import gc
+    gc.collect()
     barrier()
-    t0 = time.perf_counter()
-    out = inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)
-    barrier()
-    t_inf = time.perf_counter() - t0
+    try:
+        gc.disable()      # as in timed(): a generation-2 collection inside this single timed pass is a 100+ ms stall on the rank it hits
+        t0 = time.perf_counter()
+        out = inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)
+        barrier()
+        t_inf = time.perf_counter() - t0
+    finally:
+        gc.enable()
     (t_inf, t_part_max) = max_over_ranks(t_inf, t_part)
     ok = None
     if rank == 0:
@@ -602,13 +608,19 @@ def train_steps(dev, rank, world, barrier, max_over_ranks, precision, patches_pe
 
     for _ in range(5):
         loss, ev, en = step()
+    import gc
+    gc.collect()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        loss, ev, en = step()
-    e1.record()
-    barrier()
+    try:
+        gc.disable()          # as in timed(): no generation-2 collection inside the timed steps
+        e0.record()
+        for _ in range(steps):
+            loss, ev, en = step()
+        e1.record()
+        barrier()
+    finally:
+        gc.enable()
     ms = e0.elapsed_time(e1) / steps
     ms_ar = 0.0
     if world > 1:       # the collective alone: the same flat bucket, gradients in place from the last step
