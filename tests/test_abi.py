@@ -38,6 +38,9 @@ def test_queries_work_without_gpu():
     assert lib.geobi_feast_fwd_ws_bytes(1000, 64, 32, 0) >= 1000 * 9 * 64 * 4
     assert lib.geobi_feast_bwd_ws_bytes(1000, 64, 32) >= 1000 * 9 * 64 * 8
     assert lib.geobi_feast_bwd_ws_bytes(1000, 129, 32) == 0
+    assert lib.geobi_mlp_head_bwd_ws_bytes(1000, 32, 1024) >= 1000 * 1024 * 8          # a and dh planes
+    assert lib.geobi_mlp_head_bwd_ws_bytes(1000, 64, 1024) == 0 and lib.geobi_mlp_head_bwd_ws_bytes(1000, 32, 1000) == 0
+    assert lib.geobi_bfs_ws_bytes(1000) >= 1000 * 16 and lib.geobi_bfs_ws_bytes(-1) == 0
 
 
 def test_ops_refuse_cpu_tensors():
