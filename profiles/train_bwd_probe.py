@@ -28,7 +28,8 @@ def timed(fn, reps=3):
 
 
 print(f"facet graph: N = {n}, nnz = {int(g.rowptr[-1])}")
-for cin, cout in ((12, 32), (64, 32), (32, 64)):
+only = os.environ.get("PROBE_ONLY", "")          # "head": the FC-head backward alone (for a short ncu capture)
+for cin, cout in (() if only == "head" else ((12, 32), (64, 32), (32, 64))):
     x = torch.randn(n, cin, device=dev)
     W, U, c = torch.randn(9 * cout, cin, device=dev) * 0.1, torch.randn(9, cin, device=dev) * 0.1, torch.randn(9, device=dev) * 0.1
     out = ops.feast_fwd(x, g, W, U, c, torch.zeros(cout, device=dev), act_slope=0.2, precision=ops.PREC_BF16X3)
