@@ -296,6 +296,7 @@ def test_full_size_training_step_native_backward_agrees_with_the_library_gemm_ba
     assert abs(losses["bf16x3"] - losses["fp32"]) < 1e-5 * abs(losses["fp32"])
     worst = max((util.rel_err(grads["bf16x3"][n], grads["fp32"][n]), n) for n in grads["fp32"])
     import json, os
+    os.makedirs(os.path.join(util.ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(util.ROOT, "gpurun_out", "parity_worst_cases.jsonl"), "a") as fh:
         fh.write(json.dumps({"test": "training_step_full_size_native_vs_library", "worst_grad_rel_err": worst[0], "param": worst[1]}) + "\n")
     assert worst[0] < 2e-3, worst
