@@ -559,17 +559,21 @@ def strong_mesh10m(net, dev, rank, world, barrier, max_over_ranks):
     t_part = time.perf_counter() - t0
     # warm-up: the same sharded run once, untimed (allocator high-water mark, NCCL reduce path)
     inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)   # untimed first pass
+    # A generation-2 collection inside this single timed pass scans everything the bench has built so far: a 100+ ms stall on the rank
+    # it hits (2 GPUs: 0.337 s instead of 0.177 s).  The collector stays ON - the per-patch objects hold cycles whose device memory must
+    # come back promptly (switched off, 23 patches on one GPU ran into fresh cudaMallocs: 0.58 s instead of 0.33 s) - but everything
+    # alive now is frozen into the permanent generation, so a full collection during the pass only looks at the pass's own objects.
     import gc
     gc.collect()
+    gc.freeze()
     barrier()
     try:
-        gc.disable()      # as in timed(): a generation-2 collection inside this single timed pass is a 100+ ms stall on the rank it hits
         t0 = time.perf_counter()
         out = inference.predict_mesh(net, mesh, BIG_SUB, device=dev, rank=rank, world=world, parts=parts, host=host, norm=norm)
         barrier()
         t_inf = time.perf_counter() - t0
     finally:
-        gc.enable()
+        gc.unfreeze()
     (t_inf, t_part_max) = max_over_ranks(t_inf, t_part)
     ok = None
     if rank == 0:
@@ -610,17 +614,17 @@ def train_steps(dev, rank, world, barrier, max_over_ranks, precision, patches_pe
         loss, ev, en = step()
     import gc
     gc.collect()
+    gc.freeze()               # as for configs[3]: a full collection inside the timed steps only scans the steps' own objects
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     try:
-        gc.disable()          # as in timed(): no generation-2 collection inside the timed steps
         e0.record()
         for _ in range(steps):
             loss, ev, en = step()
         e1.record()
         barrier()
     finally:
-        gc.enable()
+        gc.unfreeze()
     ms = e0.elapsed_time(e1) / steps
     ms_ar = 0.0
     if world > 1:       # the collective alone: the same flat bucket, gradients in place from the last step
